@@ -1,0 +1,8 @@
+"""autofunc_b200 -- B200-native dense-network differentiation path of unixpickle/autofunc.
+
+`autofunc_b200.api` mirrors the reference's Func/RFunc/Batcher/RBatcher + Result/RResult interface;
+`autofunc_b200._lib` is the ctypes binding of the C ABI in include/autofunc_b200.h.
+"""
+from . import _lib  # noqa: F401
+from .api import *  # noqa: F401,F403
+from .api import Context, DeviceVec, MLPPlan, context, set_context  # noqa: F401

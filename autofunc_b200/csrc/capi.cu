@@ -1,0 +1,522 @@
+// C ABI of libautofunc_b200 (include/autofunc_b200.h): context, memory, LinTran entry points,
+// fused dense layer, whole-MLP plan.
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.h"
+#include "gemm_dmma.cuh"
+
+namespace af {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return e == cudaErrorMemoryAllocation ? AF_ENOMEM : AF_ECUDA;
+}
+int after_launch(af_ctx* ctx, const char* what, int kind, double work) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  ctx->launches += 1;
+  if (ctx->tracing && ctx->trace_used + 1 < ctx->trace_events.size()) {
+    cudaEventRecord(ctx->trace_events[ctx->trace_used + 1], ctx->stream);
+    ctx->trace_kind.push_back(kind);
+    ctx->trace_work.push_back(work);
+    ctx->trace_used += 1;
+  }
+  return AF_OK;
+}
+
+int colsum_launch(af_ctx* ctx, const double* U, const double* UR, double* gb, double* rgb, long long len, long long n);
+
+}  // namespace af
+
+using namespace af;
+
+#define AF_CHECK_CTX(ctx) \
+  if (!(ctx)) return af::fail(AF_EINVAL, "null context"); \
+  af::DeviceGuard _guard((ctx)->device)
+#define AF_NEED(p) \
+  if (!(p)) return af::fail(AF_EINVAL, "null pointer argument: " #p)
+
+static int check_dims(int64_t rows, int64_t cols, int64_t n) {
+  if (rows < 0 || cols < 0 || n < 0) return fail(AF_ESHAPE, "negative dimension");
+  return AF_OK;
+}
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------
+// context / memory
+// ------------------------------------------------------------------------------------------
+static int ctx_create_impl(int device, void* stream, bool own, af_ctx** out) {
+  if (!out) return fail(AF_EINVAL, "null out pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  if (device < 0 || device >= count) return fail(AF_EINVAL, "no such CUDA device " + std::to_string(device));
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  AF_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(AF_ENOTSUP, std::string("autofunc_b200 is built for sm_100a only; device is ") + prop.name +
+                                " (sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+  af_ctx* c = new af_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (own) {
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreateWithFlags"); }
+    c->owns_stream = true;
+  } else {
+    c->stream = static_cast<cudaStream_t>(stream);
+  }
+  cudaDriverEntryPointQueryResult q;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &c->encode_tiled, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !c->encode_tiled) {
+    if (own) cudaStreamDestroy(c->stream);
+    delete c;
+    return fail(AF_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  }
+  c->scratch_doubles = 8192;
+  e = cudaMalloc(&c->scratch, c->scratch_doubles * sizeof(double));
+  if (e != cudaSuccess) {
+    if (own) cudaStreamDestroy(c->stream);
+    delete c;
+    return cuda_fail(e, "cudaMalloc(scratch)");
+  }
+  *out = c;
+  return AF_OK;
+}
+
+int af_ctx_create(int device, af_ctx** out) { return ctx_create_impl(device, nullptr, true, out); }
+int af_ctx_create_on_stream(int device, void* cuda_stream, af_ctx** out) {
+  return ctx_create_impl(device, cuda_stream, false, out);
+}
+
+int af_ctx_destroy(af_ctx* ctx) {
+  if (!ctx) return AF_OK;
+  DeviceGuard guard(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  for (cudaEvent_t ev : ctx->trace_events) cudaEventDestroy(ev);
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return AF_OK;
+}
+
+int af_sync(af_ctx* ctx) {
+  AF_CHECK_CTX(ctx);
+  AF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return AF_OK;
+}
+
+const char* af_last_error(void) { return g_last_error.c_str(); }
+int af_version(void) { return 100; }
+int64_t af_launch_count(af_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int af_trace_begin(af_ctx* ctx, int capacity) {
+  AF_CHECK_CTX(ctx);
+  if (capacity < 1) return fail(AF_EINVAL, "trace capacity must be positive");
+  while ((int)ctx->trace_events.size() < capacity + 1) {
+    cudaEvent_t ev;
+    AF_CUDA(cudaEventCreate(&ev));
+    ctx->trace_events.push_back(ev);
+  }
+  ctx->trace_kind.clear();
+  ctx->trace_work.clear();
+  ctx->trace_used = 0;
+  AF_CUDA(cudaEventRecord(ctx->trace_events[0], ctx->stream));
+  ctx->tracing = true;
+  return AF_OK;
+}
+
+int af_trace_end(af_ctx* ctx, int capacity, int* h_kind, double* h_work, float* h_ms, int* h_count) {
+  AF_CHECK_CTX(ctx); AF_NEED(h_count);
+  ctx->tracing = false;
+  AF_CUDA(cudaStreamSynchronize(ctx->stream));
+  int n = (int)ctx->trace_used;
+  if (n > capacity) n = capacity;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    AF_CUDA(cudaEventElapsedTime(&ms, ctx->trace_events[i], ctx->trace_events[i + 1]));
+    if (h_kind) h_kind[i] = ctx->trace_kind[i];
+    if (h_work) h_work[i] = ctx->trace_work[i];
+    if (h_ms) h_ms[i] = ms;
+  }
+  *h_count = n;
+  return AF_OK;
+}
+
+int af_set_gemm_path(af_ctx* ctx, int mode) {
+  if (!ctx) return fail(AF_EINVAL, "null context");
+  if (mode < 0 || mode > 2) return fail(AF_EINVAL, "gemm path must be 0, 1 or 2");
+  ctx->gemm_path = mode;
+  return AF_OK;
+}
+
+int af_malloc(af_ctx* ctx, int64_t n, double** out) {
+  AF_CHECK_CTX(ctx); AF_NEED(out);
+  if (n < 0) return fail(AF_ESHAPE, "negative allocation size");
+  *out = nullptr;
+  AF_CUDA(cudaMalloc(out, (size_t)(n > 0 ? n : 1) * sizeof(double)));
+  return AF_OK;
+}
+
+int af_free(af_ctx* ctx, double* p) {
+  AF_CHECK_CTX(ctx);
+  if (!p) return AF_OK;
+  AF_CUDA(cudaStreamSynchronize(ctx->stream));
+  AF_CUDA(cudaFree(p));
+  return AF_OK;
+}
+
+int af_upload(af_ctx* ctx, double* dst, const double* src, int64_t n) {
+  AF_CHECK_CTX(ctx);
+  if (n <= 0) return AF_OK;
+  AF_NEED(dst); AF_NEED(src);
+  AF_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  AF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return AF_OK;
+}
+
+int af_download(af_ctx* ctx, double* dst, const double* src, int64_t n) {
+  AF_CHECK_CTX(ctx);
+  if (n <= 0) return AF_OK;
+  AF_NEED(dst); AF_NEED(src);
+  AF_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  AF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return AF_OK;
+}
+
+int af_zero(af_ctx* ctx, double* p, int64_t n) {
+  AF_CHECK_CTX(ctx);
+  if (n <= 0) return AF_OK;
+  AF_NEED(p);
+  AF_CUDA(cudaMemsetAsync(p, 0, (size_t)n * 8, ctx->stream));
+  return AF_OK;
+}
+
+int af_copy(af_ctx* ctx, double* dst, const double* src, int64_t n) {
+  AF_CHECK_CTX(ctx);
+  if (n <= 0) return AF_OK;
+  AF_NEED(dst); AF_NEED(src);
+  AF_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  return AF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// LinTran
+// ------------------------------------------------------------------------------------------
+static int dense_fwd_impl(af_ctx* ctx, const double* W, const double* RW, const double* b, const double* Rb,
+                          const double* X, const double* RX, double* Y, double* RY, int64_t rows, int64_t cols,
+                          int64_t n, int epi, bool dual) {
+  GemmOperand A{X, dual ? RX : nullptr, LAY_KC, cols};
+  GemmOperand B{W, dual ? RW : nullptr, LAY_KC, cols};
+  GemmEpilogue e;
+  e.epi = epi; e.out0 = Y; e.out1 = RY; e.ldo = rows; e.bias0 = b; e.bias1 = Rb;
+  if (cols == 0) {
+    // empty contraction: fall through the generic kernel (Kd == 0 gives acc = 0)
+    int saved = ctx->gemm_path;
+    ctx->gemm_path = 1;
+    int rc = gemm_launch(ctx, A, B, dual, n, rows, cols, e);
+    ctx->gemm_path = saved;
+    return rc;
+  }
+  return gemm_launch(ctx, A, B, dual, n, rows, cols, e);
+}
+
+int af_lintran_fwd(af_ctx* ctx, const double* W, const double* X, double* Y, int64_t rows, int64_t cols, int64_t n) {
+  AF_CHECK_CTX(ctx); AF_TRY(check_dims(rows, cols, n));
+  if (rows * n == 0) return AF_OK;
+  AF_NEED(W); AF_NEED(X); AF_NEED(Y);
+  return dense_fwd_impl(ctx, W, nullptr, nullptr, nullptr, X, nullptr, Y, nullptr, rows, cols, n, EPI_STORE, false);
+}
+
+int af_lintran_fwd_r(af_ctx* ctx, const double* W, const double* RW, const double* X, const double* RX, double* Y,
+                     double* RY, int64_t rows, int64_t cols, int64_t n) {
+  AF_CHECK_CTX(ctx); AF_TRY(check_dims(rows, cols, n));
+  if (rows * n == 0) return AF_OK;
+  AF_NEED(W); AF_NEED(X); AF_NEED(RY);
+  return dense_fwd_impl(ctx, W, RW, nullptr, nullptr, X, RX, Y, RY, rows, cols, n, EPI_STORE, true);
+}
+
+static int wgrad_impl(af_ctx* ctx, const double* U, const double* UR, const double* X, const double* RX, double* gW,
+                      double* rgW, int64_t rows, int64_t cols, int64_t n) {
+  if (rows * cols == 0 || n == 0) return AF_OK;
+  const bool dual = rgW != nullptr;
+  if (!gW && !rgW) return AF_OK;
+  GemmOperand A{U, dual ? UR : nullptr, LAY_RC, rows};
+  GemmOperand B{X, dual ? RX : nullptr, LAY_RC, cols};
+  GemmEpilogue e;
+  e.epi = EPI_ACCUM; e.out0 = gW; e.out1 = rgW; e.ldo = cols;
+  return gemm_launch(ctx, A, B, dual, rows, cols, n, e);
+}
+
+int af_lintran_wgrad(af_ctx* ctx, const double* U, const double* X, double* gW, int64_t rows, int64_t cols, int64_t n) {
+  AF_CHECK_CTX(ctx); AF_TRY(check_dims(rows, cols, n));
+  if (rows * cols == 0 || n == 0) return AF_OK;
+  AF_NEED(U); AF_NEED(X); AF_NEED(gW);
+  return wgrad_impl(ctx, U, nullptr, X, nullptr, gW, nullptr, rows, cols, n);
+}
+
+int af_lintran_wgrad_r(af_ctx* ctx, const double* U, const double* UR, const double* X, const double* RX, double* gW,
+                       double* rgW, int64_t rows, int64_t cols, int64_t n) {
+  AF_CHECK_CTX(ctx); AF_TRY(check_dims(rows, cols, n));
+  if (rows * cols == 0 || n == 0) return AF_OK;
+  AF_NEED(U); AF_NEED(X);
+  return wgrad_impl(ctx, U, UR, X, RX, gW, rgW, rows, cols, n);
+}
+
+static int igrad_impl(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW,
+                      const double* S, const double* RS, double* D, double* DR, int64_t rows, int64_t cols, int64_t n) {
+  if (cols * n == 0) return AF_OK;
+  const bool dual = DR != nullptr;
+  GemmOperand A{U, dual ? UR : nullptr, LAY_KC, rows};
+  GemmOperand B{W, dual ? RW : nullptr, LAY_RC, cols};
+  GemmEpilogue e;
+  e.epi = S ? EPI_SIGMOID_BWD : EPI_STORE;
+  e.out0 = D; e.out1 = DR; e.ldo = cols; e.s = S; e.rs = RS; e.lds = cols;
+  if (rows == 0) {
+    int saved = ctx->gemm_path;
+    ctx->gemm_path = 1;
+    int rc = gemm_launch(ctx, A, B, dual, n, cols, rows, e);
+    ctx->gemm_path = saved;
+    return rc;
+  }
+  return gemm_launch(ctx, A, B, dual, n, cols, rows, e);
+}
+
+int af_lintran_igrad(af_ctx* ctx, const double* U, const double* W, double* D, int64_t rows, int64_t cols, int64_t n) {
+  AF_CHECK_CTX(ctx); AF_TRY(check_dims(rows, cols, n));
+  if (cols * n == 0) return AF_OK;
+  AF_NEED(U); AF_NEED(W); AF_NEED(D);
+  return igrad_impl(ctx, U, nullptr, W, nullptr, nullptr, nullptr, D, nullptr, rows, cols, n);
+}
+
+int af_lintran_igrad_r(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, double* D,
+                       double* DR, int64_t rows, int64_t cols, int64_t n) {
+  AF_CHECK_CTX(ctx); AF_TRY(check_dims(rows, cols, n));
+  if (cols * n == 0) return AF_OK;
+  AF_NEED(U); AF_NEED(W); AF_NEED(DR);
+  return igrad_impl(ctx, U, UR, W, RW, nullptr, nullptr, D, DR, rows, cols, n);
+}
+
+// ------------------------------------------------------------------------------------------
+// fused dense layer
+// ------------------------------------------------------------------------------------------
+int af_dense_fwd(af_ctx* ctx, const double* W, const double* RW, const double* b, const double* Rb, const double* X,
+                 const double* RX, double* S, double* RS, int64_t rows, int64_t cols, int64_t n, int activation) {
+  AF_CHECK_CTX(ctx); AF_TRY(check_dims(rows, cols, n));
+  if (activation != 0 && activation != 1) return fail(AF_EINVAL, "activation must be 0 (none) or 1 (sigmoid)");
+  if (rows * n == 0) return AF_OK;
+  AF_NEED(W); AF_NEED(X); AF_NEED(S);
+  return dense_fwd_impl(ctx, W, RW, b, Rb, X, RX, S, RS, rows, cols, n, activation ? EPI_BIAS_SIGMOID : EPI_BIAS,
+                        RS != nullptr);
+}
+
+int af_dense_igrad(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW,
+                   const double* Sprev, const double* RSprev, double* D, double* DR, int64_t rows, int64_t cols,
+                   int64_t n) {
+  AF_CHECK_CTX(ctx); AF_TRY(check_dims(rows, cols, n));
+  if (cols * n == 0) return AF_OK;
+  AF_NEED(U); AF_NEED(W); AF_NEED(D);
+  return igrad_impl(ctx, U, UR, W, RW, Sprev, RSprev, D, DR, rows, cols, n);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// whole-MLP plan (bench/mlp.go:24-126 batched)
+// ------------------------------------------------------------------------------------------
+struct af_mlp {
+  af_ctx* ctx = nullptr;
+  int L = 0;
+  int64_t n = 0;
+  std::vector<int64_t> sizes;
+  double* slab = nullptr;  // one allocation; everything below points into it
+  std::vector<double*> param, rvec, grad, rgrad;  // 2L each: W0,b0,W1,b1,...
+  std::vector<bool> has_rvec;
+  std::vector<double*> act, ract;      // L+1: act[0] = input
+  std::vector<double*> delta, rdelta;  // L+1: delta[L] = upstream buffer
+  int64_t total_params = 0;
+  int64_t param_len(int idx) const {
+    const int l = idx / 2;
+    return (idx & 1) ? sizes[l + 1] : sizes[l] * sizes[l + 1];
+  }
+};
+
+extern "C" {
+
+int af_mlp_create(af_ctx* ctx, const int64_t* sizes, int n_layers, int64_t batch, af_mlp** out) {
+  AF_CHECK_CTX(ctx); AF_NEED(sizes); AF_NEED(out);
+  if (n_layers < 1 || batch < 1) return fail(AF_ESHAPE, "need at least one layer and one sample");
+  for (int i = 0; i <= n_layers; ++i)
+    if (sizes[i] < 1) return fail(AF_ESHAPE, "layer widths must be positive");
+  af_mlp* m = new af_mlp();
+  m->ctx = ctx; m->L = n_layers; m->n = batch;
+  m->sizes.assign(sizes, sizes + n_layers + 1);
+  const int P = 2 * n_layers;
+  // every sub-buffer starts on a 256-byte boundary so TMA and vector accesses apply
+  auto pad = [](int64_t x) { return (x + 31) / 32 * 32; };
+  int64_t total = 0;
+  std::vector<int64_t> off;
+  auto take = [&](int64_t len) { off.push_back(total); total += pad(len); };
+  for (int rep = 0; rep < 4; ++rep)
+    for (int i = 0; i < P; ++i) take(m->param_len(i));
+  for (int rep = 0; rep < 2; ++rep)
+    for (int l = 0; l <= n_layers; ++l) take(batch * sizes[l]);  // act, ract
+  for (int rep = 0; rep < 2; ++rep)
+    for (int l = 0; l <= n_layers; ++l) take(l == 0 ? 0 : batch * sizes[l]);  // delta, rdelta
+  cudaError_t e = cudaMalloc(&m->slab, (size_t)total * 8);
+  if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaMalloc(mlp slab)"); }
+  e = cudaMemsetAsync(m->slab, 0, (size_t)total * 8, ctx->stream);
+  if (e != cudaSuccess) { cudaFree(m->slab); delete m; return cuda_fail(e, "cudaMemsetAsync(mlp slab)"); }
+  size_t k = 0;
+  auto next = [&]() { return m->slab + off[k++]; };
+  for (int i = 0; i < P; ++i) m->param.push_back(next());
+  for (int i = 0; i < P; ++i) m->rvec.push_back(next());
+  for (int i = 0; i < P; ++i) m->grad.push_back(next());
+  for (int i = 0; i < P; ++i) m->rgrad.push_back(next());
+  for (int l = 0; l <= n_layers; ++l) m->act.push_back(next());
+  for (int l = 0; l <= n_layers; ++l) m->ract.push_back(next());
+  for (int l = 0; l <= n_layers; ++l) m->delta.push_back(next());
+  for (int l = 0; l <= n_layers; ++l) m->rdelta.push_back(next());
+  m->has_rvec.assign(P, false);
+  for (int i = 0; i < P; ++i) m->total_params += m->param_len(i);
+  *out = m;
+  return AF_OK;
+}
+
+int af_mlp_destroy(af_mlp* m) {
+  if (!m) return AF_OK;
+  DeviceGuard guard(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  cudaFree(m->slab);
+  delete m;
+  return AF_OK;
+}
+
+static int mlp_index_ok(af_mlp* m, int index, int64_t len) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  if (index < 0 || index >= 2 * m->L) return fail(AF_EINVAL, "parameter index out of range");
+  if (len != m->param_len(index))
+    return fail(AF_ESHAPE, "parameter length should be " + std::to_string(m->param_len(index)) + " but got " +
+                               std::to_string(len));
+  return AF_OK;
+}
+
+int af_mlp_set_param(af_mlp* m, int index, const double* h, int64_t len) {
+  AF_TRY(mlp_index_ok(m, index, len)); AF_NEED(h);
+  return af_upload(m->ctx, m->param[index], h, len);
+}
+
+int af_mlp_set_rvector(af_mlp* m, int index, const double* h, int64_t len) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  if (index < 0 || index >= 2 * m->L) return fail(AF_EINVAL, "parameter index out of range");
+  if (!h) { m->has_rvec[index] = false; return AF_OK; }
+  AF_TRY(mlp_index_ok(m, index, len));
+  m->has_rvec[index] = true;
+  return af_upload(m->ctx, m->rvec[index], h, len);
+}
+
+#define MLP_PTR(name, expr)                      \
+  double* name(af_mlp* m, int index) {           \
+    if (!m || index < 0 || index >= 2 * m->L) return nullptr; \
+    return expr;                                 \
+  }
+MLP_PTR(af_mlp_param_ptr, m->param[index])
+MLP_PTR(af_mlp_rvector_ptr, (m->has_rvec[index] = true, m->rvec[index]))
+MLP_PTR(af_mlp_grad_ptr, m->grad[index])
+MLP_PTR(af_mlp_rgrad_ptr, m->rgrad[index])
+#undef MLP_PTR
+double* af_mlp_input_ptr(af_mlp* m) { return m ? m->act[0] : nullptr; }
+double* af_mlp_output_ptr(af_mlp* m) { return m ? m->act[m->L] : nullptr; }
+double* af_mlp_routput_ptr(af_mlp* m) { return m ? m->ract[m->L] : nullptr; }
+double* af_mlp_upstream_ptr(af_mlp* m) { return m ? m->delta[m->L] : nullptr; }
+double* af_mlp_upstream_r_ptr(af_mlp* m) { return m ? m->rdelta[m->L] : nullptr; }
+
+int af_mlp_zero_grads(af_mlp* m) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  DeviceGuard guard(m->ctx->device);
+  // grad and rgrad blocks are adjacent in the slab
+  const size_t bytes = (size_t)(m->act[0] - m->grad[0]) * 8;
+  AF_CUDA(cudaMemsetAsync(m->grad[0], 0, bytes, m->ctx->stream));
+  return AF_OK;
+}
+
+int af_mlp_step(af_mlp* m, int with_r, int backprop) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  af_ctx* ctx = m->ctx;
+  DeviceGuard guard(ctx->device);
+  const int L = m->L;
+  const int64_t n = m->n;
+  const bool R = with_r != 0;
+  auto rv = [&](int idx) -> const double* { return (R && m->has_rvec[idx]) ? m->rvec[idx] : nullptr; };
+  // forward: func.go:40-45 over {LinTran, LinAdd, Sigmoid} triples, one fused kernel per layer.
+  // The input is not in the RVector (bench/mlp.go:52; variable.go:85-91) so RX of layer 1 is zero.
+  for (int l = 0; l < L; ++l) {
+    const double* RX = (R && l > 0) ? m->ract[l] : nullptr;
+    AF_TRY(af_dense_fwd(ctx, m->param[2 * l], rv(2 * l), m->param[2 * l + 1], rv(2 * l + 1), m->act[l], RX,
+                        m->act[l + 1], R ? m->ract[l + 1] : nullptr, m->sizes[l + 1], m->sizes[l], n, 1));
+  }
+  if (!backprop) return AF_OK;
+  // backward: top sigmoid (math_funcs.go:326-333 / 357-374) on the caller's upstream, in place
+  const int64_t top = n * m->sizes[L];
+  if (R) AF_TRY(af_sigmoid_bwd_r(ctx, m->act[L], m->ract[L], m->delta[L], m->rdelta[L], top));
+  else AF_TRY(af_sigmoid_bwd(ctx, m->act[L], m->delta[L], top));
+  for (int l = L - 1; l >= 0; --l) {
+    const int64_t rows = m->sizes[l + 1], cols = m->sizes[l];
+    const double* U = m->delta[l + 1];
+    const double* UR = R ? m->rdelta[l + 1] : nullptr;
+    // lin_add.go:94-104 batched: gb += colsum(U), rgb += colsum(UR)
+    AF_TRY(colsum_launch(ctx, U, UR, m->grad[2 * l + 1], R ? m->rgrad[2 * l + 1] : nullptr, rows, n));
+    // lin_tran.go:410-418
+    const double* RX = (R && l > 0) ? m->ract[l] : nullptr;
+    AF_TRY(af_lintran_wgrad_r(ctx, U, UR, m->act[l], RX, m->grad[2 * l], R ? m->rgrad[2 * l] : nullptr, rows, cols, n));
+    // lin_tran.go:420-423: the input Variable is not in the gradient maps, so layer 1 stops here
+    if (l > 0)
+      AF_TRY(af_dense_igrad(ctx, U, UR, m->param[2 * l], rv(2 * l), m->act[l], R ? m->ract[l] : nullptr, m->delta[l],
+                            R ? m->rdelta[l] : nullptr, rows, cols, n));
+  }
+  return AF_OK;
+}
+
+int af_mlp_step_host(af_mlp* m, int with_r, const double* hX, const double* hU, const double* hUR, double* hOut,
+                     double* hROut, double* const* hGrads, double* const* hRGrads) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  AF_NEED(hX);
+  af_ctx* ctx = m->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int L = m->L;
+  const int64_t top = m->n * m->sizes[L];
+  AF_CUDA(cudaMemcpyAsync(m->act[0], hX, (size_t)(m->n * m->sizes[0]) * 8, cudaMemcpyHostToDevice, st));
+  if (hU) AF_CUDA(cudaMemcpyAsync(m->delta[L], hU, (size_t)top * 8, cudaMemcpyHostToDevice, st));
+  else AF_TRY(af_fill(ctx, m->delta[L], 1.0, top));  // bench/mlp.go:120-123
+  if (with_r) {
+    if (hUR) AF_CUDA(cudaMemcpyAsync(m->rdelta[L], hUR, (size_t)top * 8, cudaMemcpyHostToDevice, st));
+    else AF_CUDA(cudaMemsetAsync(m->rdelta[L], 0, (size_t)top * 8, st));  // bench/mlp.go:124
+  }
+  AF_TRY(af_mlp_zero_grads(m));
+  AF_TRY(af_mlp_step(m, with_r, 1));
+  if (hOut) AF_CUDA(cudaMemcpyAsync(hOut, m->act[L], (size_t)top * 8, cudaMemcpyDeviceToHost, st));
+  if (hROut && with_r) AF_CUDA(cudaMemcpyAsync(hROut, m->ract[L], (size_t)top * 8, cudaMemcpyDeviceToHost, st));
+  for (int i = 0; i < 2 * L; ++i) {
+    if (hGrads && hGrads[i])
+      AF_CUDA(cudaMemcpyAsync(hGrads[i], m->grad[i], (size_t)m->param_len(i) * 8, cudaMemcpyDeviceToHost, st));
+    if (with_r && hRGrads && hRGrads[i])
+      AF_CUDA(cudaMemcpyAsync(hRGrads[i], m->rgrad[i], (size_t)m->param_len(i) * 8, cudaMemcpyDeviceToHost, st));
+  }
+  AF_CUDA(cudaStreamSynchronize(st));
+  return AF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Shared host-side plumbing for libautofunc_b200: context, error reporting, launch accounting.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/autofunc_b200.h"
+
+struct af_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  int sm_count = 148;
+  int gemm_path = 0;  // 0 auto, 1 generic, 2 require DMMA
+  int64_t launches = 0;
+  // driver entry point, resolved at run time so the library loads on hosts without libcuda
+  void* encode_tiled = nullptr;
+  double* scratch = nullptr;  // small device scratch (reductions)
+  int64_t scratch_doubles = 0;
+  // launch trace (af_trace_begin/af_trace_end): one CUDA event after every kernel launch
+  bool tracing = false;
+  std::vector<cudaEvent_t> trace_events;  // [0] = start marker, [i+1] = after launch i
+  std::vector<int> trace_kind;
+  std::vector<double> trace_work;
+  size_t trace_used = 0;
+};
+
+namespace af {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define AF_CUDA(expr)                                          \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return ::af::cuda_fail(_e, #expr);  \
+  } while (0)
+
+#define AF_TRY(expr)          \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != AF_OK) return _rc; \
+  } while (0)
+
+// kernel kinds reported by the launch trace (include/autofunc_b200.h: AF_KIND_*)
+enum : int { KIND_GEMM_DUAL = 0, KIND_GEMM_SINGLE = 1, KIND_GEMM_GENERIC = 2, KIND_ELEMENTWISE = 3, KIND_REDUCE = 4 };
+
+// after a kernel launch: count it, surface launch errors, and (when tracing) record an event.
+// `work` is the launch's ALGORITHMIC work: flops for contractions, bytes for streaming kernels.
+int after_launch(af_ctx* ctx, const char* what, int kind, double work);
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ---- contraction front end (gemm.cu) --------------------------------------------------------
+struct GemmOperand {
+  const double* p0 = nullptr;  // primary (X, U, W)
+  const double* p1 = nullptr;  // R companion or NULL
+  int layout = 0;              // LAY_KC / LAY_RC
+  long long ld = 0;
+};
+struct GemmEpilogue {
+  int epi = 0;
+  double* out0 = nullptr;
+  double* out1 = nullptr;
+  long long ldo = 0;
+  const double* bias0 = nullptr;
+  const double* bias1 = nullptr;
+  const double* s = nullptr;
+  const double* rs = nullptr;
+  long long lds = 0;
+};
+// acc0 = A0 B0^T ; acc1 = A0 B1^T + A1 B0^T (dual when `dual`), I x J, contraction Kd
+int gemm_launch(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool dual, long long I, long long J,
+                long long Kd, const GemmEpilogue& e);
+
+}  // namespace af

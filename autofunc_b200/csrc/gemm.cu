@@ -1,0 +1,142 @@
+// Host front end of the FP64 contraction kernels: TMA descriptor construction, path selection
+// (TMA + DMMA vs. generic), split-K policy, launches.
+#include "common.h"
+#include "gemm_dmma.cuh"
+
+namespace af {
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool tma_compatible(const double* p, long long ld, long long rows, long long kd) {
+  if (p == nullptr) return true;
+  if (reinterpret_cast<uintptr_t>(p) & 15) return false;  // TMA global address: 16-byte aligned
+  if (ld & 1) return false;                               // row pitch: multiple of 16 bytes
+  if (ld * 8 >= (1ll << 40)) return false;
+  if (rows >= (1ll << 31) || kd >= (1ll << 31)) return false;
+  return true;
+}
+
+// KC: element (r,k) at p[r*ld + k] -> dims {Kd, R}, box {16, tile_rows}
+// RC: element (r,k) at p[k*ld + r] -> dims {R, Kd}, box {16, 16}
+int make_map(af_ctx* ctx, CUtensorMap* map, const double* p, int layout, long long rows, long long kd, long long ld,
+             int tile_rows) {
+  cuuint64_t dims[2];
+  cuuint32_t box[2];
+  if (layout == LAY_KC) {
+    dims[0] = (cuuint64_t)kd; dims[1] = (cuuint64_t)rows;
+    box[0] = kBK; box[1] = (cuuint32_t)tile_rows;
+  } else {
+    dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)kd;
+    box[0] = 16; box[1] = kBK;
+  }
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(p), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AF_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return AF_OK;
+}
+
+// algorithmic flops of one launch: 2 I J Kd per product that the reference would also compute
+double gemm_flops(const GemmArgs& a, bool dual) {
+  int products = 0;
+  if (a.out0) products += 1;
+  if (dual && a.out1) products += (a.has_a1 ? 1 : 0) + (a.has_b1 ? 1 : 0);
+  return 2.0 * a.I * a.J * a.Kd * products;
+}
+
+template <int ALAY, int BLAY, int NACC>
+int launch_dmma(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3 grid) {
+  auto kern = gemm_dmma_kernel<ALAY, BLAY, NACC>;
+  const int smem = (int)GemmSmem<NACC>::kTotal;
+  static bool configured = false;  // per template instantiation; attribute is per device function
+  if (!configured) {
+    AF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, kGemmThreads, smem, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], args);
+  return after_launch(ctx, "gemm_dmma_kernel", NACC == 2 ? KIND_GEMM_DUAL : KIND_GEMM_SINGLE, gemm_flops(args, NACC == 2));
+}
+
+template <int ALAY, int BLAY>
+int launch_generic(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool dual, const GemmArgs& args) {
+  dim3 grid((unsigned)((args.J + 15) / 16), (unsigned)((args.I + 15) / 16));
+  if (dual)
+    gemm_generic_kernel<ALAY, BLAY, true><<<grid, 256, 0, ctx->stream>>>(A.p0, A.p1, B.p0, B.p1, A.ld, B.ld, args);
+  else
+    gemm_generic_kernel<ALAY, BLAY, false><<<grid, 256, 0, ctx->stream>>>(A.p0, nullptr, B.p0, nullptr, A.ld, B.ld, args);
+  return after_launch(ctx, "gemm_generic_kernel", KIND_GEMM_GENERIC, gemm_flops(args, dual));
+}
+
+}  // namespace
+
+int gemm_launch(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool dual, long long I, long long J,
+                long long Kd, const GemmEpilogue& e) {
+  if (I <= 0 || J <= 0) return AF_OK;
+  if (I >= (1ll << 31) || J >= (1ll << 31) || Kd >= (1ll << 31)) return fail(AF_ESHAPE, "contraction extent exceeds 2^31");
+  GemmArgs args{};
+  args.I = (int)I; args.J = (int)J; args.Kd = (int)Kd;
+  args.has_a1 = dual && A.p1 != nullptr;
+  args.has_b1 = dual && B.p1 != nullptr;
+  args.epi = e.epi;
+  args.out0 = e.out0; args.out1 = dual ? e.out1 : nullptr; args.ldo = e.ldo;
+  args.bias0 = e.bias0; args.bias1 = e.bias1;
+  args.s = e.s; args.rs = e.rs; args.lds = e.lds;
+  const int kt_total = (int)((Kd + kBK - 1) / kBK);
+  args.k_tiles_per_split = kt_total > 0 ? kt_total : 1;
+
+  const bool tma_ok = ctx->encode_tiled != nullptr && tma_compatible(A.p0, A.ld, I, Kd) &&
+                      tma_compatible(A.p1, A.ld, I, Kd) && tma_compatible(B.p0, B.ld, J, Kd) &&
+                      tma_compatible(B.p1, B.ld, J, Kd) && Kd > 0;
+  const bool use_dmma = ctx->gemm_path != 1 && tma_ok;
+  if (!use_dmma && ctx->gemm_path == 2)
+    return fail(AF_ENOTSUP, "DMMA path required but operands violate TMA alignment (16-byte base, even pitch)");
+
+  if (!use_dmma) {
+    if (args.epi == EPI_ACCUM_ATOMIC) args.epi = EPI_ACCUM;
+    if (A.layout == LAY_KC && B.layout == LAY_KC) return launch_generic<LAY_KC, LAY_KC>(ctx, A, B, dual, args);
+    if (A.layout == LAY_KC && B.layout == LAY_RC) return launch_generic<LAY_KC, LAY_RC>(ctx, A, B, dual, args);
+    if (A.layout == LAY_RC && B.layout == LAY_RC) return launch_generic<LAY_RC, LAY_RC>(ctx, A, B, dual, args);
+    return fail(AF_EINVAL, "unsupported operand layout combination");
+  }
+
+  CUtensorMap maps[4];
+  AF_TRY(make_map(ctx, &maps[0], A.p0, A.layout, I, Kd, A.ld, kBM));
+  AF_TRY(make_map(ctx, &maps[2], B.p0, B.layout, J, Kd, B.ld, kBN));
+  if (args.has_a1) AF_TRY(make_map(ctx, &maps[1], A.p1, A.layout, I, Kd, A.ld, kBM)); else maps[1] = maps[0];
+  if (args.has_b1) AF_TRY(make_map(ctx, &maps[3], B.p1, B.layout, J, Kd, B.ld, kBN)); else maps[3] = maps[2];
+
+  dim3 grid((unsigned)((J + kBN - 1) / kBN), (unsigned)((I + kBM - 1) / kBM), 1);
+  if (args.epi == EPI_ACCUM) {
+    // split the contraction (the batch dimension for weight gradients) when the output has too few
+    // tiles to fill the chip; partial tiles are combined with red.global.add.f64
+    const long long tiles = (long long)grid.x * grid.y;
+    const long long target = 2ll * ctx->sm_count;
+    int splits = (int)((target + tiles - 1) / tiles);
+    const int max_splits = kt_total / 8 > 0 ? kt_total / 8 : 1;  // keep >= 8 k-tiles (128 samples) per split
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 1) {
+      args.k_tiles_per_split = (kt_total + splits - 1) / splits;
+      splits = (kt_total + args.k_tiles_per_split - 1) / args.k_tiles_per_split;
+      grid.z = (unsigned)splits;
+      args.epi = EPI_ACCUM_ATOMIC;
+    }
+  }
+  const int nacc = dual ? 2 : 1;
+#define AF_DISPATCH(AL, BL)                                                      \
+  if (A.layout == AL && B.layout == BL)                                          \
+    return nacc == 2 ? launch_dmma<AL, BL, 2>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1>(ctx, maps, args, grid);
+  AF_DISPATCH(LAY_KC, LAY_KC)
+  AF_DISPATCH(LAY_KC, LAY_RC)
+  AF_DISPATCH(LAY_RC, LAY_RC)
+#undef AF_DISPATCH
+  return fail(AF_EINVAL, "unsupported operand layout combination");
+}
+
+}  // namespace af

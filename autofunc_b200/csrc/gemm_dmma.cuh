@@ -1,0 +1,399 @@
+// FP64 tensor-core contraction for the LinTran kernels (lin_tran.go:79-359), sm_100a.
+//
+// One kernel template serves all six BLAS call sites of the reference.
+// In logical indices it computes, for an I x J output tile set and contraction length Kd,
+//
+//     acc0[i][j] = sum_k A0[i,k] * B0[j,k]
+//     acc1[i][j] = sum_k A0[i,k] * B1[j,k] + A1[i,k] * B0[j,k]        (NACC == 2 only)
+//
+//   forward  (G1+G2, lin_tran.go:113,172-173): A=X,RX  B=W,RW        out n x rows
+//   igrad    (G5+G6, lin_tran.go:302,354-355): A=U,UR  B=W,RW (k = row of W)   out n x cols
+//   wgrad    (G3+G4, lin_tran.go:210,267-268): A=U,UR (k = sample)  B=X,RX     out rows x cols, +=
+//
+// so the R-operator's dual products share one pass over the operand tiles instead of the
+// reference's 2-3 separate Gemm calls.
+//
+// Data path: TMA (cp.async.bulk.tensor.2d, 128B swizzle) -> 4-stage shared-memory ring guarded by
+// full/empty mbarriers, filled by one elected producer lane -> ld.shared.f64 fragments ->
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05 has no f64 kind).  CTA tile 128 x 64 x 16,
+// 8 consumer warps of 32 x 32.
+//
+// Operand layouts in global memory:
+//   LAY_KC  the contraction index is contiguous:  element (r,k) at ptr[r*ld + k]
+//   LAY_RC  the row index is contiguous:          element (r,k) at ptr[k*ld + r]
+// Shared-memory images (both 128B-swizzled by TMA, 16 doubles = 128 B per line):
+//   KC tile of R rows : line r holds k = 0..15           -> one box {16, R}
+//   RC tile of R rows : R/16 boxes of {16 rows, 16 k}; line k of box c holds rows 16c..16c+15
+// Bank conflicts: a half-warp reads 4 lines x 4 k for one fragment.  The k index an MMA lane j
+// supplies is arbitrary as long as A and B agree, so lane j of MMA step s takes
+// k = KJ[j] ^ MS[s] with KJ = {0,3,12,15}, MS = {0,1,4,5}: for KC tiles the four k's then cover
+// both 64-B halves and both 8-B parities, for RC tiles they differ in bits 1-2, and every
+// half-warp load touches 16 distinct 8-byte bank pairs in either layout.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace af {
+
+constexpr int kBK = 16;
+constexpr int kBM = 128;
+constexpr int kBN = 64;
+constexpr int kStages = 4;
+constexpr int kConsumerWarps = 8;
+constexpr int kGemmThreads = kConsumerWarps * 32;
+
+enum : int { LAY_KC = 0, LAY_RC = 1 };
+enum : int {
+  EPI_STORE = 0,         // out0 = acc0 ; out1 = acc1
+  EPI_BIAS = 1,          // out0 = acc0 + b0[j] ; out1 = acc1 + b1[j]           (lin_add.go:15-17,37-42)
+  EPI_BIAS_SIGMOID = 2,  // s = sigmoid(acc0+b0[j]) ; out1 = s(1-s)(acc1+b1[j]) (math_funcs.go:305-309)
+  EPI_SIGMOID_BWD = 3,   // sigmoid R-backward with (S,RS) read at (i,j)         (math_funcs.go:365-371)
+  EPI_ACCUM = 4,         // out += acc   (beta = 1, lin_tran.go:210,267-268)
+  EPI_ACCUM_ATOMIC = 5,  // out += acc with red.global.add.f64 (split-K)
+};
+
+struct GemmArgs {
+  int I, J, Kd;
+  int has_a1, has_b1;  // R operands present (NULL R-vector == zero, variable.go:85-91)
+  int epi;
+  int k_tiles_per_split;
+  double* out0;
+  double* out1;
+  long long ldo;
+  const double* bias0;
+  const double* bias1;
+  const double* s;
+  const double* rs;
+  long long lds;
+};
+
+// ---------------------------------------------------------------------------------------------
+// epilogue element functions (shared by the DMMA kernel and the generic kernel)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sigmoid_f64(double z) { return 1.0 / (1.0 + exp(-z)); }
+
+template <bool DUAL>
+__device__ __forceinline__ void epi_transform(const GemmArgs& p, long long i, int j, double& v0, double& v1) {
+  switch (p.epi) {
+    case EPI_BIAS:
+      if (p.bias0) v0 += p.bias0[j];
+      if (DUAL && p.bias1) v1 += p.bias1[j];
+      break;
+    case EPI_BIAS_SIGMOID: {
+      double z = v0 + (p.bias0 ? p.bias0[j] : 0.0);
+      double s = sigmoid_f64(z);
+      v0 = s;
+      if (DUAL) {
+        double rz = v1 + (p.bias1 ? p.bias1[j] : 0.0);
+        v1 = s * (1 - s) * rz;
+      }
+      break;
+    }
+    case EPI_SIGMOID_BWD: {
+      // math_funcs.go:365-371, operand order kept: u' = x(1-x)u ; uR' = xR(1-x)u - x xR u + x(1-x)uR
+      double x = p.s[i * p.lds + j];
+      double u = v0;
+      v0 = x * (1 - x) * u;
+      if (DUAL) {
+        double xr = p.rs ? p.rs[i * p.lds + j] : 0.0;
+        v1 = xr * (1 - x) * u - x * xr * u + x * (1 - x) * v1;
+      }
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+template <bool DUAL>
+__device__ __forceinline__ void epi_elem(const GemmArgs& p, long long i, int j, double v0, double v1) {
+  long long o = i * p.ldo + j;
+  if (p.epi == EPI_ACCUM) {
+    if (p.out0) p.out0[o] += v0;
+    if (DUAL && p.out1) p.out1[o] += v1;
+  } else if (p.epi == EPI_ACCUM_ATOMIC) {
+    if (p.out0) atomicAdd(p.out0 + o, v0);
+    if (DUAL && p.out1) atomicAdd(p.out1 + o, v1);
+  } else {
+    epi_transform<DUAL>(p, i, j, v0, v1);
+    if (p.out0) p.out0[o] = v0;
+    if (DUAL && p.out1) p.out1[o] = v1;
+  }
+}
+
+// two adjacent columns (j, j+1), j even; 16-byte accesses when the row pitch allows
+template <bool DUAL>
+__device__ __forceinline__ void epi_pair(const GemmArgs& p, bool vec_ok, long long i, int j, double a0, double a1,
+                                         double r0, double r1) {
+  if (j + 1 < p.J && vec_ok) {
+    long long o = i * p.ldo + j;
+    if (p.epi == EPI_ACCUM) {
+      if (p.out0) {
+        double2 c = *reinterpret_cast<double2*>(p.out0 + o);
+        c.x += a0; c.y += a1;
+        *reinterpret_cast<double2*>(p.out0 + o) = c;
+      }
+      if (DUAL && p.out1) {
+        double2 c = *reinterpret_cast<double2*>(p.out1 + o);
+        c.x += r0; c.y += r1;
+        *reinterpret_cast<double2*>(p.out1 + o) = c;
+      }
+    } else if (p.epi == EPI_ACCUM_ATOMIC) {
+      if (p.out0) { atomicAdd(p.out0 + o, a0); atomicAdd(p.out0 + o + 1, a1); }
+      if (DUAL && p.out1) { atomicAdd(p.out1 + o, r0); atomicAdd(p.out1 + o + 1, r1); }
+    } else {
+      epi_transform<DUAL>(p, i, j, a0, r0);
+      epi_transform<DUAL>(p, i, j + 1, a1, r1);
+      if (p.out0) *reinterpret_cast<double2*>(p.out0 + o) = make_double2(a0, a1);
+      if (DUAL && p.out1) *reinterpret_cast<double2*>(p.out1 + o) = make_double2(r0, r1);
+    }
+  } else {
+    if (j < p.J) epi_elem<DUAL>(p, i, j, a0, r0);
+    if (j + 1 < p.J) epi_elem<DUAL>(p, i, j + 1, a1, r1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "AF_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra AF_DONE;\n"
+      "bra AF_WAIT;\n"
+      "AF_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+// D(8x8) += A(8x4, row) * B(4x8, col); lane (g = lane/4, j = lane%4) supplies A[g][j], B[j][g],
+// holds C[g][2j], C[g][2j+1].  Lowers to DMMA.8x8x4 on sm_100a.
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int NACC>
+struct GemmSmem {
+  static constexpr uint32_t kABytes = kBM * kBK * 8;
+  static constexpr uint32_t kBBytes = kBN * kBK * 8;
+  static constexpr uint32_t kStageBytes = NACC * (kABytes + kBBytes);
+  static constexpr uint32_t kA0 = 0;
+  static constexpr uint32_t kA1 = kABytes;                    // NACC == 2 only
+  static constexpr uint32_t kB0 = NACC * kABytes;
+  static constexpr uint32_t kB1 = NACC * kABytes + kBBytes;   // NACC == 2 only
+  static constexpr uint32_t kBarOffset = kStages * kStageBytes;
+  static constexpr uint32_t kTotal = kBarOffset + 2 * kStages * 8 + 1024;  // + alignment slack
+};
+
+template <int LAY, int ROWS>
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* map, uint32_t bar, int row0, int k0) {
+  if (LAY == LAY_KC) {
+    tma_load_2d(dst, map, bar, k0, row0);
+  } else {
+#pragma unroll
+    for (int c = 0; c < ROWS / 16; ++c) tma_load_2d(dst + c * 2048, map, bar, row0 + 16 * c, k0);
+  }
+}
+
+// byte offset of fragment element (row = w0 + 8t + g, k) inside a tile, minus the t-dependent part
+template <int LAY>
+__device__ __forceinline__ uint32_t frag_base(int w0, int g, int k) {
+  if (LAY == LAY_KC) return (uint32_t)((w0 + g) * 128 + ((((k >> 1) ^ g) & 7) << 4) + ((k & 1) << 3));
+  return (uint32_t)((w0 >> 4) * 2048 + k * 128 + ((((g >> 1) ^ (k & 7)) & 7) << 4) + ((g & 1) << 3));
+}
+template <int LAY>
+__device__ __forceinline__ uint32_t frag_addr(uint32_t base, int t) {
+  if (LAY == LAY_KC) return base + t * 1024;
+  return (base + (t >> 1) * 2048) ^ ((t & 1) * 64);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int ALAY, int BLAY, int NACC>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs p) {
+  using L = GemmSmem<NACC>;
+  constexpr bool DUAL = (NACC == 2);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms are 1024-B aligned
+  const uint32_t bars = base + L::kBarOffset;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.y * kBM, j0 = blockIdx.x * kBN;
+  const int kt_total = (p.Kd + kBK - 1) / kBK;
+  const int kt_begin = blockIdx.z * p.k_tiles_per_split;
+  int nkt = kt_total - kt_begin;
+  if (nkt > p.k_tiles_per_split) nkt = p.k_tiles_per_split;
+  if (nkt <= 0) return;
+  const bool has_a1 = DUAL && p.has_a1, has_b1 = DUAL && p.has_b1;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bars + 8 * s, 1);                           // full: one expect_tx arrival + tx bytes
+      mbar_init(bars + 8 * (kStages + s), kConsumerWarps);  // empty: one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // Producer role: lane 0 of warp 0 keeps kStages-1 tiles in flight.  It is folded into a consumer
+  // warp (not a 9th warp) because registers are allocated per SM sub-partition: a 9th warp would put
+  // three warps on one sub-partition and cap every thread at 168 registers, spilling accumulators.
+  const uint32_t tx_bytes = L::kABytes + L::kBBytes + (has_a1 ? L::kABytes : 0) + (has_b1 ? L::kBBytes : 0);
+  auto produce = [&](int t) {
+    const int s = t % kStages;
+    const uint32_t ph = (t / kStages) & 1;
+    mbar_wait(bars + 8 * (kStages + s), ph ^ 1);  // all 8 warps released the stage's previous tile
+    const uint32_t full = bars + 8 * s;
+    const uint32_t st = base + s * L::kStageBytes;
+    const int k0 = (kt_begin + t) * kBK;
+    mbar_expect_tx(full, tx_bytes);
+    tma_load_tile<ALAY, kBM>(st + L::kA0, &tmA0, full, i0, k0);
+    tma_load_tile<BLAY, kBN>(st + L::kB0, &tmB0, full, j0, k0);
+    if (has_a1) tma_load_tile<ALAY, kBM>(st + L::kA1, &tmA1, full, i0, k0);
+    if (has_b1) tma_load_tile<BLAY, kBN>(st + L::kB1, &tmB1, full, j0, k0);
+  };
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < kStages - 1 && t < nkt; ++t) produce(t);
+  }
+
+  // ---------------- consumers: 8 warps, 4 (i) x 2 (j), 32 x 32 each ----------------
+  const int g = lane >> 2, j4 = lane & 3;
+  const int wi0 = (warp >> 1) * 32, wj0 = (warp & 1) * 32;
+  const int kj = ((j4 & 1) ? 3 : 0) | ((j4 & 2) ? 12 : 0);
+  uint32_t fa[4], fb[4];
+  {
+    const int ms[4] = {0, 1, 4, 5};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      fa[s] = frag_base<ALAY>(wi0, g, kj ^ ms[s]);
+      fb[s] = frag_base<BLAY>(wj0, g, kj ^ ms[s]);
+    }
+  }
+
+  double acc0[4][4][2], acc1[DUAL ? 4 : 1][4][2];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc0[t][u][0] = acc0[t][u][1] = 0.0;
+      if (DUAL) acc1[t][u][0] = acc1[t][u][1] = 0.0;
+    }
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int s = kt % kStages;
+    const uint32_t ph = (kt / kStages) & 1;
+    if (threadIdx.x == 0 && kt + kStages - 1 < nkt) produce(kt + kStages - 1);
+    __syncwarp();
+    mbar_wait(bars + 8 * s, ph);
+    const uint32_t st = base + s * L::kStageBytes;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      double a0[4], b0[4], a1[4], b1[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        a0[t] = lds_f64(st + L::kA0 + frag_addr<ALAY>(fa[ks], t));
+        b0[t] = lds_f64(st + L::kB0 + frag_addr<BLAY>(fb[ks], t));
+      }
+      if (has_a1) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) a1[t] = lds_f64(st + L::kA1 + frag_addr<ALAY>(fa[ks], t));
+      }
+      if (has_b1) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) b1[t] = lds_f64(st + L::kB1 + frag_addr<BLAY>(fb[ks], t));
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dmma_8x8x4(acc0[t][u][0], acc0[t][u][1], a0[t], b0[u]);
+      if (has_b1) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma_8x8x4(acc1[DUAL ? t : 0][u][0], acc1[DUAL ? t : 0][u][1], a0[t], b1[u]);
+      }
+      if (has_a1) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma_8x8x4(acc1[DUAL ? t : 0][u][0], acc1[DUAL ? t : 0][u][1], a1[t], b0[u]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 8 * (kStages + s));
+  }
+
+  // ---------------- epilogue: registers -> global, fused elementwise ----------------
+  const bool vec_ok = ((p.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.out0) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.out1) & 15) == 0);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const long long i = i0 + wi0 + 8 * t + g;
+    if (i < p.I) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + wj0 + 8 * u + 2 * j4;
+        if (j < p.J)
+          epi_pair<DUAL>(p, vec_ok, i, j, acc0[t][u][0], acc0[t][u][1], DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0,
+                         DUAL ? acc1[DUAL ? t : 0][u][1] : 0.0);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic kernel: any shape / alignment (odd leading dimensions, sliced views).  One output
+// element per thread, same index algebra and epilogue; used when TMA's 16-byte rules fail.
+// ---------------------------------------------------------------------------------------------
+template <int ALAY, int BLAY, bool DUAL>
+__global__ void __launch_bounds__(256) gemm_generic_kernel(const double* __restrict__ A0, const double* __restrict__ A1,
+                                                           const double* __restrict__ B0, const double* __restrict__ B1,
+                                                           long long lda, long long ldb, const GemmArgs p) {
+  const int j = blockIdx.x * 16 + (threadIdx.x & 15);
+  const long long i = (long long)blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (i >= p.I || j >= p.J) return;
+  double v0 = 0.0, v1 = 0.0;
+  for (int k = 0; k < p.Kd; ++k) {
+    const long long ia = (ALAY == LAY_KC) ? i * lda + k : (long long)k * lda + i;
+    const long long ib = (BLAY == LAY_KC) ? (long long)j * ldb + k : (long long)k * ldb + j;
+    const double a = A0[ia], b = B0[ib];
+    v0 = fma(a, b, v0);
+    if (DUAL) {
+      if (B1) v1 = fma(a, B1[ib], v1);
+      if (A1) v1 = fma(A1[ia], b, v1);
+    }
+  }
+  epi_elem<DUAL>(p, i, j, v0, v1);
+}
+
+}  // namespace af

@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline workload on B200: bench/mlp.go's MLP (1000-2000-512-10,
+sigmoid) doing forward + Gradient + RGradient (RunR with backProp, bench/mlp.go:43-57), batched,
+float64, samples/sec.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference
+
+One "step" = one pass of the hot path over one batch of synthetic inputs: zero the accumulators,
+fresh outGrad = 1 / outRGrad = 0 (bench/mlp.go:118-126), ApplyR, PropagateRGradient with non-nil
+grad; for N > 1 each rank owns `batch` samples (weak scaling) and the step ends with one NCCL
+sum all-reduce of {grad, rgrad}.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+LAYER_SIZES = [1000, 2000, 512, 10]  # bench/mlp.go:17-20
+METRIC = "mlp_fwd_gradient_rgradient_samples_per_sec"
+UNIT = "samples/s"
+
+
+def flops_per_sample(sizes, with_r=True):
+    """per dense layer 18 K M (12 K M for layer 1, whose input is constant) with R,
+    6 K M (4 K M) without."""
+    f = 0
+    for l in range(len(sizes) - 1):
+        km = sizes[l] * sizes[l + 1]
+        if with_r:
+            f += (12 if l == 0 else 18) * km
+        else:
+            f += (4 if l == 0 else 6) * km
+    return f
+
+
+def workload_name(batch):
+    return (f"bench/mlp.go MLP {'-'.join(map(str, LAYER_SIZES))} sigmoid, batched n={batch}/GPU, "
+            "fwd+Gradient+RGradient (RunR backProp=true), float64")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (numpy + OpenBLAS threads) -- the only place bench.py executes oracle/
+# ------------------------------------------------------------------------------------------------
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 0) for p in threadpool_info() if p.get("user_api") == "blas"]
+        if n:
+            return max(n)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def run_cpu_oracle(n, steps, warmup):
+    from oracle import autofunc_ref as ref
+    net = ref.MLP(LAYER_SIZES)
+    x = net.make_input(n)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        net.step_r(x, n)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.cpu_batch
+    times = run_cpu_oracle(n, args.steps, args.warmup)
+    total = sum(times)
+    value = n * len(times) / total
+    cores = cpu_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.batch), "layer_sizes": LAYER_SIZES, "batch_per_gpu": args.batch,
+                   "global_batch": args.batch * args.gpus},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} steps of {n} samples each (bounded sample of the n={args.batch} workload); "
+                                   "CPU restatement of the reference (oracle/autofunc_ref.py, numpy + OpenBLAS): "
+                                   "the reference is pure Go and no Go toolchain exists on this box"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread:
+            self._stop.set()
+            self._thread.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class _CudaArray:
+    """Zero-copy view of a device pointer for torch (NCCL all-reduce of the resident accumulators)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def measure_dgemm_peak(torch, size=8192, iters=6):
+    """cuBLAS Dgemm 8192^3 -- the FP64 denominator (MEASURED_PEAKS.json holds no FP64 figure)."""
+    a = torch.rand(size, size, dtype=torch.float64, device="cuda")
+    b = torch.rand(size, size, dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    best = 1e30
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 2.0 * size ** 3 / (best * 1e-3) / 1e12
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from autofunc_b200 import api, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- autofunc_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.batch
+    K, W = args.steps, args.warmup
+
+    stream = torch.cuda.current_stream()
+    ctx = api.Context(local_rank, stream=stream.cuda_stream)
+    api.set_context(ctx)
+    ctx.set_gemm_path(2)  # TMA + DMMA or an error; never a silent fallback
+    plan = api.MLPPlan(LAYER_SIZES, n, ctx)
+    params, rvecs = synth.mlp_params(LAYER_SIZES)
+    for i, (p, r) in enumerate(zip(params, rvecs)):
+        plan.set_param(i, p)
+        plan.set_rvector(i, r)
+    x_host = synth.mlp_input(LAYER_SIZES, n, seed=124 + 7919 * rank)
+    ctx.lib.af_upload(ctx.h, plan.input().ptr, x_host.ctypes.data, x_host.size)
+    n_out = n * LAYER_SIZES[-1]
+    up, upr = plan.upstream(), plan.upstream_r()
+    P = 2 * plan.L
+    n_params = sum(plan.param_len(i) for i in range(P))
+    g0 = plan.grad(0)
+    slab_len = (plan.input().ptr - g0.ptr) // 8  # grad and rgrad blocks are adjacent
+    slab = torch.as_tensor(_CudaArray(g0.ptr, slab_len), device=f"cuda:{local_rank}") if world > 1 else None
+
+    def step():
+        plan.zero_grads()
+        api.check(ctx.lib.af_fill(ctx.h, up.ptr, 1.0, n_out))  # fresh upstreams every step
+        api.check(ctx.lib.af_zero(ctx.h, upr.ptr, n_out))
+        plan.step(True, True)
+        if world > 1:
+            dist.all_reduce(slab)  # gradient.go:28-30 across ranks
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step()
+    barrier()
+    cap = 64 * K + 8
+    kinds, work, ms_arr = (C.c_int * cap)(), (C.c_double * cap)(), (C.c_float * cap)()
+    count = C.c_int(0)
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    api.check(ctx.lib.af_trace_begin(ctx.h, cap))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    api.check(ctx.lib.af_trace_end(ctx.h, cap, kinds, work, ms_arr, C.byref(count)))
+    launches = ctx.launch_count() - launches0
+    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_total.item())
+    value = world * n * K / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (the dual TMA+DMMA contraction), from the live trace ----
+    gemm_ms = sum(ms_arr[i] for i in range(count.value) if kinds[i] == 0)
+    gemm_flops = sum(work[i] for i in range(count.value) if kinds[i] == 0)
+    gemm_n = sum(1 for i in range(count.value) if kinds[i] == 0)
+    other_ms = sum(ms_arr[i] for i in range(count.value) if kinds[i] != 0)
+    peak = measure_dgemm_peak(torch) if rank == 0 else None
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
+    def pinned(count_):
+        return torch.empty(count_, dtype=torch.float64).pin_memory()
+    hx = pinned(x_host.size)
+    hx.numpy()[:] = x_host
+    hout, hrout = pinned(n_out), pinned(n_out)
+    hg = [pinned(plan.param_len(i)) for i in range(P)]
+    hrg = [pinned(plan.param_len(i)) for i in range(P)]
+    HP = C.c_void_p * P
+    g_arr, rg_arr = HP(*[t.data_ptr() for t in hg]), HP(*[t.data_ptr() for t in hrg])
+    h2d = x_host.size * 8
+    d2h = 2 * n_out * 8 + 2 * n_params * 8
+
+    def e2e_step():
+        if world == 1:
+            api.check(ctx.lib.af_mlp_step_host(plan.h, 1, hx.data_ptr(), None, None, hout.data_ptr(), hrout.data_ptr(),
+                                               g_arr, rg_arr))
+        else:
+            api.check(ctx.lib.af_upload(ctx.h, plan.input().ptr, hx.data_ptr(), x_host.size))
+            step()
+            api.check(ctx.lib.af_download(ctx.h, hout.data_ptr(), plan.output().ptr, n_out))
+            api.check(ctx.lib.af_download(ctx.h, hrout.data_ptr(), plan.routput().ptr, n_out))
+            for i in range(P):
+                api.check(ctx.lib.af_download(ctx.h, hg[i].data_ptr(), plan.grad(i).ptr, plan.param_len(i)))
+                api.check(ctx.lib.af_download(ctx.h, hrg[i].data_ptr(), plan.rgrad(i).ptr, plan.param_len(i)))
+    for _ in range(max(1, min(W, 3))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * K / float(e2e_s.item())
+
+    if rank == 0:
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n), "layer_sizes": LAYER_SIZES, "batch_per_gpu": n,
+                       "global_batch": n * world, "parallelism": f"dp{world}",
+                       "l2": "no flush: each step streams ~%.0f MB of activations/upstreams (> 126 MB L2)" %
+                             (n * sum(LAYER_SIZES) * 8 * 4 / 1e6),
+                       "flops_per_sample": flops_per_sample(LAYER_SIZES)},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if (achieved and peak) else None, "traffic": traffic,
+                         "kernel": "gemm_dmma_kernel<*,*,2> (TMA + DMMA.8x8x4 dual contraction)",
+                         "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
+                         "algorithmic_flops_per_launch": gemm_flops / gemm_n if gemm_n else None,
+                         "kernel_share_of_step": gemm_ms / ms_total if ms_total else None,
+                         "other_kernels_ms_per_step": other_ms / K,
+                         "peak_source": "cuBLAS Dgemm 8192^3 (torch.matmul f64, best of 6) measured in this run; "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "whole_step_tflops": flops_per_sample(LAYER_SIZES) * n * K / (ms_total * 1e-3) / 1e12},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            times = run_cpu_oracle(args.cpu_batch, 3, 1)
+            line["cpu_baseline"] = {
+                "value": args.cpu_batch * len(times) / sum(times), "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                "sample": f"3 steps of {args.cpu_batch} samples (same network, same step); oracle/autofunc_ref.py "
+                          "(numpy + OpenBLAS, all host threads) -- CPU restatement, Go unavailable"}
+        print(json.dumps(line), flush=True)
+    plan.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=1024, help="samples per CPU-oracle step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,203 @@
+/*
+ * autofunc_b200 -- C ABI of the B200-native dense differentiation path of unixpickle/autofunc.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: the path sits
+ * behind the Go interfaces Func/RFunc (func.go:7-27), Batcher/RBatcher (batcher.go:5-29) and
+ * Result/RResult (result.go:10-77).  A Go (cgo) shim -- go/b200/*.go, shown in INTEGRATION.md --
+ * implements those interfaces by calling the entry points below; each entry point cites the
+ * reference routine it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative AF_E* code; af_last_error() gives text.
+ *   - all numeric data is IEEE float64; matrices are row-major; a packed batch of n samples is
+ *     sample-major (batcher.go:6-17): X is n x cols, Y is n x rows.
+ *   - `const double*` / `double*` arguments named d_* are DEVICE pointers (cudaMalloc'ed by
+ *     af_malloc, or any other allocator sharing the device's primary context, e.g. torch);
+ *     arguments named h_* are HOST pointers.
+ *   - a NULL R-operand means "identically zero" (variable.go:85-91: a variable absent from the
+ *     RVector has a zero R-vector) and the corresponding product is skipped.
+ *   - gradient outputs ACCUMULATE (+=), as in the reference (variable.go:45; beta=1 at
+ *     lin_tran.go:210,267-268).
+ *   - one af_ctx = one device + one stream; calls on a ctx are serialised by the caller
+ *     (the reference is single-goroutine).  Work is asynchronous on the ctx stream until
+ *     af_sync() or a host-pointer call.
+ */
+#ifndef AUTOFUNC_B200_H_
+#define AUTOFUNC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AF_OK 0
+#define AF_ESHAPE (-1)   /* the reference panics: lin_tran.go:26,35,52,66; arithmetic.go:265 */
+#define AF_ECUDA (-2)
+#define AF_ENOMEM (-3)
+#define AF_EINVAL (-4)
+#define AF_ENOTSUP (-5)
+
+typedef struct af_ctx af_ctx;
+typedef struct af_mlp af_mlp;
+
+/* ---- context / memory ------------------------------------------------------------------- */
+int af_ctx_create(int device, af_ctx** out);
+/* Borrow an existing stream (e.g. torch's current stream); stream == NULL means legacy default. */
+int af_ctx_create_on_stream(int device, void* cuda_stream, af_ctx** out);
+int af_ctx_destroy(af_ctx* ctx);
+int af_sync(af_ctx* ctx);
+const char* af_last_error(void);
+int af_version(void);
+/* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
+int64_t af_launch_count(af_ctx* ctx);
+/* Launch trace for measurement (bench.py's roofline): between begin and end, one CUDA event is
+ * recorded on the ctx stream after every kernel launch.  af_trace_end synchronises and returns, per
+ * launch, its kind (AF_KIND_*), its algorithmic work (flops for contractions, bytes for streaming
+ * kernels) and the device time since the previous event in milliseconds.                        */
+#define AF_KIND_GEMM_DUAL 0     /* TMA+DMMA contraction, value and R accumulators */
+#define AF_KIND_GEMM_SINGLE 1   /* TMA+DMMA contraction, one accumulator */
+#define AF_KIND_GEMM_GENERIC 2  /* generic contraction (operands not TMA-aligned) */
+#define AF_KIND_ELEMENTWISE 3
+#define AF_KIND_REDUCE 4
+int af_trace_begin(af_ctx* ctx, int capacity);
+int af_trace_end(af_ctx* ctx, int capacity, int* h_kind, double* h_work, float* h_ms, int* h_count);
+/* Path selector for the LinTran contractions: 0 = auto (TMA + DMMA tensor-core kernel when the
+ * operands satisfy TMA alignment, else the generic kernel), 1 = force generic, 2 = require DMMA
+ * (returns AF_ENOTSUP instead of falling back). */
+int af_set_gemm_path(af_ctx* ctx, int mode);
+
+int af_malloc(af_ctx* ctx, int64_t n_doubles, double** d_out);
+int af_free(af_ctx* ctx, double* d_ptr);
+int af_upload(af_ctx* ctx, double* d_dst, const double* h_src, int64_t n);    /* sync */
+int af_download(af_ctx* ctx, double* h_dst, const double* d_src, int64_t n);  /* sync */
+int af_zero(af_ctx* ctx, double* d_ptr, int64_t n);
+int af_copy(af_ctx* ctx, double* d_dst, const double* d_src, int64_t n);
+
+/* ---- LinTran: lin_tran.go --------------------------------------------------------------- */
+/* W is rows x cols.  X, RX: n x cols.  Y, RY: n x rows.  U, UR: n x rows.  D, DR: n x cols.   */
+
+/* G1  LinTran.multiply (lin_tran.go:79-117):            Y  = X W^T                             */
+int af_lintran_fwd(af_ctx*, const double* d_W, const double* d_X, double* d_Y,
+                   int64_t rows, int64_t cols, int64_t n);
+/* G1+G2  LinTran.BatchR (lin_tran.go:64-77, 119-177):   Y  = X W^T ; RY = X RW^T + RX W^T
+ * d_RW and/or d_RX may be NULL.  d_Y may be NULL (R-output only).                              */
+int af_lintran_fwd_r(af_ctx*, const double* d_W, const double* d_RW, const double* d_X,
+                     const double* d_RX, double* d_Y, double* d_RY,
+                     int64_t rows, int64_t cols, int64_t n);
+/* G3  LinTran.dataGradient (lin_tran.go:179-212):       gW += U^T X                            */
+int af_lintran_wgrad(af_ctx*, const double* d_U, const double* d_X, double* d_gW,
+                     int64_t rows, int64_t cols, int64_t n);
+/* G3+G4  dataGradient + dataGradientR (lin_tran.go:214-270, called at :410-418):
+ *        gW += U^T X   (skipped when d_gW == NULL, i.e. grad == nil or W not in grad)
+ *        rgW += U^T RX + UR^T X  (skipped when d_rgW == NULL)                                  */
+int af_lintran_wgrad_r(af_ctx*, const double* d_U, const double* d_UR, const double* d_X,
+                       const double* d_RX, double* d_gW, double* d_rgW,
+                       int64_t rows, int64_t cols, int64_t n);
+/* G5  LinTran.inputGradient (lin_tran.go:272-306):      D  = U W                               */
+int af_lintran_igrad(af_ctx*, const double* d_U, const double* d_W, double* d_D,
+                     int64_t rows, int64_t cols, int64_t n);
+/* G5+G6  inputGradient + inputGradientR (lin_tran.go:308-359, called at :421-422):
+ *        D = U W ; DR = UR W + U RW                                                            */
+int af_lintran_igrad_r(af_ctx*, const double* d_U, const double* d_UR, const double* d_W,
+                       const double* d_RW, double* d_D, double* d_DR,
+                       int64_t rows, int64_t cols, int64_t n);
+
+/* ---- LinAdd (lin_add.go) in its batched form Add(x, Repeat(b,n)) ------------------------- */
+/* Y = X + b (per sample), RY = RX + Rb.  lin_add.go:13-50; arithmetic.go:17; slices.go:216.    */
+int af_bias_fwd(af_ctx*, const double* d_X, const double* d_b, double* d_Y, int64_t len, int64_t n);
+int af_bias_fwd_r(af_ctx*, const double* d_X, const double* d_RX, const double* d_b,
+                  const double* d_Rb, double* d_Y, double* d_RY, int64_t len, int64_t n);
+/* gb += sum over samples of U (lin_add.go:66-69,94-104; Repeat backward slices.go:244-250).
+ * Either accumulator may be NULL.                                                              */
+int af_bias_grad(af_ctx*, const double* d_U, double* d_gb, int64_t len, int64_t n);
+int af_bias_grad_r(af_ctx*, const double* d_U, const double* d_UR, double* d_gb, double* d_rgb,
+                   int64_t len, int64_t n);
+
+/* ---- elementwise RFuncs: math_funcs.go --------------------------------------------------- */
+/* Sigmoid (math_funcs.go:286-374).  fwd_r: S = 1/(1+exp(-X)), RS = S(1-S) RX.
+ * bwd: U <- U S(1-S) in place (:328-330).  bwd_r (:365-371), in place, reference operand order:
+ *   U' = S(1-S)U ;  UR' = RS(1-S)U - S RS U + S(1-S)UR                                         */
+int af_sigmoid_fwd(af_ctx*, const double* d_X, double* d_S, int64_t len);
+int af_sigmoid_fwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_S, double* d_RS, int64_t len);
+int af_sigmoid_bwd(af_ctx*, const double* d_S, double* d_U, int64_t len);
+int af_sigmoid_bwd_r(af_ctx*, const double* d_S, const double* d_RS, double* d_U, double* d_UR, int64_t len);
+/* Exp (math_funcs.go:12-97): E = exp(X), RE = E RX; bwd U <- U E; bwd_r UR <- UR E + U RE.     */
+int af_exp_fwd(af_ctx*, const double* d_X, double* d_E, int64_t len);
+int af_exp_fwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_E, double* d_RE, int64_t len);
+int af_exp_bwd(af_ctx*, const double* d_E, double* d_U, int64_t len);
+int af_exp_bwd_r(af_ctx*, const double* d_E, const double* d_RE, double* d_U, double* d_UR, int64_t len);
+
+/* ---- arithmetic.go hot subset ------------------------------------------------------------ */
+/* out = a + b (arithmetic.go:17,58) ; out = a - b (:105,144) ; out = a * b (:261)             */
+int af_add(af_ctx*, const double* d_a, const double* d_b, double* d_out, int64_t len);
+int af_sub(af_ctx*, const double* d_a, const double* d_b, double* d_out, int64_t len);
+int af_mul(af_ctx*, const double* d_a, const double* d_b, double* d_out, int64_t len);
+/* MulR R-output (arithmetic.go:325-329): out = a*bR + aR*b                                     */
+int af_mul_r(af_ctx*, const double* d_a, const double* d_aR, const double* d_b, const double* d_bR,
+             double* d_out, int64_t len);
+/* Mul backward toward one operand (arithmetic.go:291-293,358-362): D = U*o ; DR = U*oR + UR*o.
+ * d_UR/d_oR/d_DR may be NULL for the non-R form.                                               */
+int af_mul_bwd(af_ctx*, const double* d_U, const double* d_UR, const double* d_o, const double* d_oR,
+               double* d_D, double* d_DR, int64_t len);
+/* x <- f*x in place (Scale, arithmetic.go:436-493) ; y += f*x (gradient.go:40-52 Axpy)         */
+int af_scale(af_ctx*, double* d_x, double f, int64_t len);
+int af_axpy(af_ctx*, double f, const double* d_x, double* d_y, int64_t len);
+/* Square (arithmetic.go:696-770): fwd_r O = X^2, RO = 2 X RX; bwd_r UR <- 2(UR X + U RX), U <- 2 X U */
+int af_square_fwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_O, double* d_RO, int64_t len);
+int af_square_bwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_U, double* d_UR, int64_t len);
+/* SumAll (arithmetic.go:972-1047): *d_out = sum(x); (d_outR = sum(xR) when both non-NULL)      */
+int af_sum_all(af_ctx*, const double* d_x, const double* d_xR, double* d_out, double* d_outR, int64_t len);
+/* fill (SumAll backward broadcast, arithmetic.go:990-993)                                      */
+int af_fill(af_ctx*, double* d_x, double value, int64_t len);
+
+/* ---- fused dense layer: LinTran -> LinAdd -> Sigmoid in one kernel per direction ---------- */
+/* Forward with R (G1+G2+E1+E2):  S = sigmoid(X W^T + b) ; RS = S(1-S)(X RW^T + RX W^T + Rb).
+ * activation: 0 = none (S = pre-activation), 1 = sigmoid.  d_b/d_Rb/d_RW/d_RX/d_RS may be NULL
+ * (d_RS == NULL selects the non-R forward).                                                    */
+int af_dense_fwd(af_ctx*, const double* d_W, const double* d_RW, const double* d_b, const double* d_Rb,
+                 const double* d_X, const double* d_RX, double* d_S, double* d_RS,
+                 int64_t rows, int64_t cols, int64_t n, int activation);
+/* Input-gradient with the PREVIOUS layer's sigmoid backward fused in (G5+G6+E4):
+ *   D = U W ; DR = UR W + U RW ; then, when d_Sprev != NULL, the in-place sigmoid R-backward of
+ *   math_funcs.go:365-371 with (S,RS) = (Sprev, RSprev), written to d_D / d_DR.                */
+int af_dense_igrad(af_ctx*, const double* d_U, const double* d_UR, const double* d_W, const double* d_RW,
+                   const double* d_Sprev, const double* d_RSprev, double* d_D, double* d_DR,
+                   int64_t rows, int64_t cols, int64_t n);
+
+/* ---- whole-network fast path: bench/mlp.go:24-126 with n >= 1 samples ---------------------- */
+/* sizes[0..n_layers] = layer widths (bench/mlp.go:17-20: 1000,2000,512,10); batch = n.
+ * Parameters, R-vectors, activations and the four accumulators per layer stay resident in HBM. */
+int af_mlp_create(af_ctx*, const int64_t* sizes, int n_layers, int64_t batch, af_mlp** out);
+int af_mlp_destroy(af_mlp*);
+/* Parameter l in [0, 2*n_layers): even = W of layer l/2, odd = bias (order of bench/mlp.go:84-85). */
+int af_mlp_set_param(af_mlp*, int index, const double* h_value, int64_t len);
+int af_mlp_set_rvector(af_mlp*, int index, const double* h_value, int64_t len); /* NULL h_value => absent */
+double* af_mlp_param_ptr(af_mlp*, int index);   /* device pointers for zero-copy callers */
+double* af_mlp_rvector_ptr(af_mlp*, int index);
+double* af_mlp_grad_ptr(af_mlp*, int index);
+double* af_mlp_rgrad_ptr(af_mlp*, int index);
+double* af_mlp_input_ptr(af_mlp*);              /* n x sizes[0] */
+double* af_mlp_output_ptr(af_mlp*);             /* n x sizes[L] */
+double* af_mlp_routput_ptr(af_mlp*);
+double* af_mlp_upstream_ptr(af_mlp*);           /* n x sizes[L]: outGrad  (bench/mlp.go:118-126) */
+double* af_mlp_upstream_r_ptr(af_mlp*);         /* n x sizes[L]: outRGrad */
+int af_mlp_zero_grads(af_mlp*);
+/* One iteration of bench/mlp.go:52-54 on resident data: ApplyR, then PropagateRGradient with
+ * non-nil grad, accumulating into grad/rgrad.  with_r == 0 runs bench/mlp.go:36-38 instead
+ * (Apply + PropagateGradient).  The upstream buffers are consumed (clobbered), as the reference
+ * allows (result.go:24-29).  Asynchronous.                                                     */
+int af_mlp_step(af_mlp*, int with_r, int backprop);
+/* Host-buffer form (the reference-facing call): uploads h_X (n x sizes[0]), h_upstream /
+ * h_upstream_r (n x sizes[L]; NULL => ones / zeros as in bench/mlp.go:118-126), zeroes the
+ * accumulators, runs the step, and downloads h_out / h_rout (n x sizes[L]) and every gradient and
+ * R-gradient into h_grads[i] / h_rgrads[i] (arrays of 2*n_layers host pointers; entries or the
+ * arrays themselves may be NULL).  Synchronous.                                                */
+int af_mlp_step_host(af_mlp*, int with_r, const double* h_X, const double* h_upstream,
+                     const double* h_upstream_r, double* h_out, double* h_rout,
+                     double* const* h_grads, double* const* h_rgrads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUTOFUNC_B200_H_ */

@@ -1,0 +1,95 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, and refuses to run (loudly) without a B200 -- no compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from autofunc_b200 import _lib, build as af_build
+
+
+@pytest.fixture(scope="session")
+def lib():
+    af_build.build()
+    return _lib.load()
+
+
+def _declared_symbols():
+    text = open(_lib.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(af_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_what_binding_binds():
+    assert set(_declared_symbols()) == set(_lib.PROTOTYPES)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (af_[a-z0-9_]+)\b", out))
+    missing = [s for s in _declared_symbols() if s not in exported]
+    assert not missing, f"symbols declared in include/autofunc_b200.h but not exported: {missing}"
+
+
+def test_library_is_sm100a_tma_dmma():
+    """The shipped code object is sm_100a and carries the TMA + FP64 tensor-core instructions."""
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    assert "DMMA.8x8x4" in sass and "UTMALDG" in sass
+
+
+def test_no_gpu_means_loud_failure(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = lib.af_ctx_create(0, C.byref(h))
+    assert rc != 0 and lib.af_last_error()
+    from autofunc_b200 import api
+    with pytest.raises(_lib.AutofuncError):
+        api.Context(0)
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "autofunc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "oracle/" not in src, f
+
+
+def test_variable_wire_format_matches_reference_layout():
+    from autofunc_b200 import api
+    v = api.Variable(np.arange(5, dtype=np.float64) * 0.5)
+    b = v.serialize()  # variable.go:61-68: LE u64 count then LE f64s
+    assert b[:8] == (5).to_bytes(8, "little") and len(b) == 48
+    assert np.array_equal(api.Variable.deserialize(b).vector, v.vector)
+
+
+def test_fuse_dense_pattern():
+    from autofunc_b200 import api
+    w, b = api.Variable(np.zeros(12)), api.Variable(np.zeros(3))
+    net = [api.LinTran(w, 3, 4), api.LinAdd(b), api.Sigmoid(), api.Exp()]
+    fused = api.fuse_dense(net)
+    assert len(fused) == 2 and isinstance(fused[0], api.DenseSigmoid) and fused[0].activation
+    fused2 = api.fuse_dense(net[:2])
+    assert len(fused2) == 1 and not fused2[0].activation
+
+
+def test_synth_generator_matches_oracle_generator():
+    from autofunc_b200 import synth
+    from oracle import autofunc_ref as ref
+    for seed in (0, 123, 124, 125, 3125):
+        assert np.array_equal(synth.uniform(seed, 4097), ref.splitmix_uniform(seed, 4097))
+    params, rvecs = synth.mlp_params([7, 5, 3])
+    net = ref.MLP([7, 5, 3])
+    for p, v in zip(params, net.variables):
+        assert np.array_equal(p, v.vector)
+    for r, v in zip(rvecs, net.variables):
+        assert np.array_equal(r, net.rvec[v])
