@@ -1,0 +1,45 @@
+"""Data-parallel plumbing: the path shards over the batch.  Rank r owns a contiguous block
+of sample rows; parameters and R-vectors are replicated; after the local step the parameter gradients
+and R-gradients are summed across ranks -- the multi-device form of Gradient.Add (gradient.go:28-30,
+108-120; the reference's gradient is a SUM over samples, never a mean).
+
+torch.distributed is the transport (NCCL over NVLink on GPUs, gloo on CPU for tests)."""
+from __future__ import annotations
+
+import os
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_rows(n_total: int, world: int, rank: int) -> tuple[int, int]:
+    """(first row, row count) of rank's block; blocks differ by at most one row and cover [0, n)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    base, extra = divmod(n_total, world)
+    start = rank * base + min(rank, extra)
+    return start, base + (1 if rank < extra else 0)
+
+
+class CudaArrayView:
+    """Zero-copy torch view of a device buffer owned by libautofunc_b200 (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, n_doubles: int):
+        self.__cuda_array_interface__ = {"shape": (n_doubles,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def allreduce_sum_(tensor, group=None):
+    """In-place sum all-reduce of a gradient slab (any torch tensor: CUDA -> NCCL, CPU -> gloo)."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+    return tensor
+
+
+def plan_grad_slab(plan, device_index: int):
+    """The plan's contiguous {grad | rgrad} block as one torch CUDA tensor (one collective per step)."""
+    import torch
+    g0 = plan.grad(0)
+    n = (plan.input().ptr - g0.ptr) // 8
+    return torch.as_tensor(CudaArrayView(g0.ptr, n), device=f"cuda:{device_index}")

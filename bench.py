@@ -153,13 +153,6 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-class _CudaArray:
-    """Zero-copy view of a device pointer for torch (NCCL all-reduce of the resident accumulators)."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-
-
 def measure_dgemm_peak(torch, size=8192, iters=6):
     """cuBLAS Dgemm 8192^3 -- the FP64 denominator (MEASURED_PEAKS.json holds no FP64 figure)."""
     a = torch.rand(size, size, dtype=torch.float64, device="cuda")
@@ -184,7 +177,7 @@ def gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    from autofunc_b200 import api, synth
+    from autofunc_b200 import api, parallel, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,9 +205,7 @@ def gpu_arm(args):
     up, upr = plan.upstream(), plan.upstream_r()
     P = 2 * plan.L
     n_params = sum(plan.param_len(i) for i in range(P))
-    g0 = plan.grad(0)
-    slab_len = (plan.input().ptr - g0.ptr) // 8  # grad and rgrad blocks are adjacent
-    slab = torch.as_tensor(_CudaArray(g0.ptr, slab_len), device=f"cuda:{local_rank}") if world > 1 else None
+    slab = parallel.plan_grad_slab(plan, local_rank) if world > 1 else None  # grad | rgrad, contiguous
 
     def step():
         plan.zero_grads()
@@ -222,7 +213,7 @@ def gpu_arm(args):
         api.check(ctx.lib.af_zero(ctx.h, upr.ptr, n_out))
         plan.step(True, True)
         if world > 1:
-            dist.all_reduce(slab)  # gradient.go:28-30 across ranks
+            parallel.allreduce_sum_(slab)  # gradient.go:28-30 across ranks
 
     def barrier():
         if world > 1:
