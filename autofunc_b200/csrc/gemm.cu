@@ -3,6 +3,8 @@
 #include "common.h"
 #include "gemm_dmma.cuh"
 
+#include <utility>
+
 namespace af {
 
 namespace {
@@ -51,10 +53,10 @@ double gemm_flops(const GemmArgs& a, bool dual) {
   return 2.0 * a.I * a.J * a.Kd * products;
 }
 
-template <int ALAY, int BLAY, int NACC>
+template <int ALAY, int BLAY, int NACC, int CFG>
 int launch_dmma(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3 grid) {
-  auto kern = gemm_dmma_kernel<ALAY, BLAY, NACC>;
-  const int smem = (int)GemmSmem<NACC>::kTotal;
+  auto kern = gemm_dmma_kernel<ALAY, BLAY, NACC, CFG>;
+  const int smem = (int)GemmSmem<NACC, CFG>::kTotal;
   static bool configured = false;  // per template instantiation; attribute is per device function
   if (!configured) {
     AF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -62,6 +64,21 @@ int launch_dmma(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3
   }
   kern<<<grid, kGemmThreads, smem, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], args);
   return after_launch(ctx, "gemm_dmma_kernel", NACC == 2 ? KIND_GEMM_DUAL : KIND_GEMM_SINGLE, gemm_flops(args, NACC == 2));
+}
+
+// Split-K choice for accumulating outputs (weight gradients; the contraction runs over the batch).
+// Cost of `s` splits in k-tile units per SM: ceil(tiles*s / SMs) waves, each ceil(kt/s) k-tiles plus
+// ~1.5 k-tiles for the red.global.add epilogue.  Picks the wave count that quantises best.
+int choose_splits(long long tiles, int kt_total, int sms) {
+  int best = 1;
+  double best_cost = 1e300;
+  const int max_s = kt_total / 4 > 0 ? kt_total / 4 : 1;
+  for (int s = 1; s <= max_s && s <= 64; ++s) {
+    const long long waves = (tiles * s + sms - 1) / sms;
+    const double cost = (double)waves * ((kt_total + s - 1) / s + (s > 1 ? 1.5 : 0.25));
+    if (cost < best_cost * 0.995) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 
 template <int ALAY, int BLAY>
@@ -76,15 +93,25 @@ int launch_generic(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool
 
 }  // namespace
 
-int gemm_launch(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool dual, long long I, long long J,
+int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, bool dual, long long I, long long J,
                 long long Kd, const GemmEpilogue& e) {
   if (I <= 0 || J <= 0) return AF_OK;
   if (I >= (1ll << 31) || J >= (1ll << 31) || Kd >= (1ll << 31)) return fail(AF_ESHAPE, "contraction extent exceeds 2^31");
+  GemmOperand A = A_in, B = B_in;
   GemmArgs args{};
+  args.epi = e.epi;
+  const bool accumulate = e.epi == EPI_ACCUM;
+  // A weight gradient with very few rows (the 10-wide output layer): compute the transposed product so
+  // the short extent lands on the 16-wide J tile instead of wasting 118 of 128 I rows.  acc1 is symmetric
+  // under (A0,A1) <-> (B0,B1).
+  if (accumulate && I <= 16 && J > 16 && A.layout == LAY_RC && B.layout == LAY_RC) {
+    std::swap(A, B);
+    std::swap(I, J);
+    args.transpose_out = 1;
+  }
   args.I = (int)I; args.J = (int)J; args.Kd = (int)Kd;
   args.has_a1 = dual && A.p1 != nullptr;
   args.has_b1 = dual && B.p1 != nullptr;
-  args.epi = e.epi;
   args.out0 = e.out0; args.out1 = dual ? e.out1 : nullptr; args.ldo = e.ldo;
   args.bias0 = e.bias0; args.bias1 = e.bias1;
   args.s = e.s; args.rs = e.rs; args.lds = e.lds;
@@ -99,39 +126,38 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool du
     return fail(AF_ENOTSUP, "DMMA path required but operands violate TMA alignment (16-byte base, even pitch)");
 
   if (!use_dmma) {
-    if (args.epi == EPI_ACCUM_ATOMIC) args.epi = EPI_ACCUM;
     if (A.layout == LAY_KC && B.layout == LAY_KC) return launch_generic<LAY_KC, LAY_KC>(ctx, A, B, dual, args);
     if (A.layout == LAY_KC && B.layout == LAY_RC) return launch_generic<LAY_KC, LAY_RC>(ctx, A, B, dual, args);
     if (A.layout == LAY_RC && B.layout == LAY_RC) return launch_generic<LAY_RC, LAY_RC>(ctx, A, B, dual, args);
     return fail(AF_EINVAL, "unsupported operand layout combination");
   }
 
+  const int cfg = J <= 16 ? 1 : 0;
+  const int bm = cfg == 1 ? GemmSmem<2, 1>::kBMc : GemmSmem<2, 0>::kBMc;
+  const int bn = cfg == 1 ? GemmSmem<2, 1>::kBNc : GemmSmem<2, 0>::kBNc;
   CUtensorMap maps[4];
-  AF_TRY(make_map(ctx, &maps[0], A.p0, A.layout, I, Kd, A.ld, kBM));
-  AF_TRY(make_map(ctx, &maps[2], B.p0, B.layout, J, Kd, B.ld, kBN));
-  if (args.has_a1) AF_TRY(make_map(ctx, &maps[1], A.p1, A.layout, I, Kd, A.ld, kBM)); else maps[1] = maps[0];
-  if (args.has_b1) AF_TRY(make_map(ctx, &maps[3], B.p1, B.layout, J, Kd, B.ld, kBN)); else maps[3] = maps[2];
+  AF_TRY(make_map(ctx, &maps[0], A.p0, A.layout, I, Kd, A.ld, bm));
+  AF_TRY(make_map(ctx, &maps[2], B.p0, B.layout, J, Kd, B.ld, bn));
+  if (args.has_a1) AF_TRY(make_map(ctx, &maps[1], A.p1, A.layout, I, Kd, A.ld, bm)); else maps[1] = maps[0];
+  if (args.has_b1) AF_TRY(make_map(ctx, &maps[3], B.p1, B.layout, J, Kd, B.ld, bn)); else maps[3] = maps[2];
 
-  dim3 grid((unsigned)((J + kBN - 1) / kBN), (unsigned)((I + kBM - 1) / kBM), 1);
-  if (args.epi == EPI_ACCUM) {
-    // split the contraction (the batch dimension for weight gradients) when the output has too few
-    // tiles to fill the chip; partial tiles are combined with red.global.add.f64
-    const long long tiles = (long long)grid.x * grid.y;
-    const long long target = 2ll * ctx->sm_count;
-    int splits = (int)((target + tiles - 1) / tiles);
-    const int max_splits = kt_total / 8 > 0 ? kt_total / 8 : 1;  // keep >= 8 k-tiles (128 samples) per split
-    if (splits > max_splits) splits = max_splits;
+  dim3 grid((unsigned)((J + bn - 1) / bn), (unsigned)((I + bm - 1) / bm), 1);
+  if (accumulate) {
+    int splits = choose_splits((long long)grid.x * grid.y, kt_total, ctx->sm_count);
     if (splits > 1) {
       args.k_tiles_per_split = (kt_total + splits - 1) / splits;
       splits = (kt_total + args.k_tiles_per_split - 1) / args.k_tiles_per_split;
       grid.z = (unsigned)splits;
-      args.epi = EPI_ACCUM_ATOMIC;
+      args.epi = EPI_ACCUM_ATOMIC;  // partial tiles combine with red.global.add.f64
     }
   }
   const int nacc = dual ? 2 : 1;
-#define AF_DISPATCH(AL, BL)                                                      \
-  if (A.layout == AL && B.layout == BL)                                          \
-    return nacc == 2 ? launch_dmma<AL, BL, 2>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1>(ctx, maps, args, grid);
+#define AF_DISPATCH(AL, BL)                                                                        \
+  if (A.layout == AL && B.layout == BL) {                                                          \
+    if (cfg == 0)                                                                                  \
+      return nacc == 2 ? launch_dmma<AL, BL, 2, 0>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 0>(ctx, maps, args, grid); \
+    return nacc == 2 ? launch_dmma<AL, BL, 2, 1>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 1>(ctx, maps, args, grid);   \
+  }
   AF_DISPATCH(LAY_KC, LAY_KC)
   AF_DISPATCH(LAY_KC, LAY_RC)
   AF_DISPATCH(LAY_RC, LAY_RC)

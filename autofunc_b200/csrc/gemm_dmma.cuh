@@ -15,8 +15,8 @@
 //
 // Data path: TMA (cp.async.bulk.tensor.2d, 128B swizzle) -> 4-stage shared-memory ring guarded by
 // full/empty mbarriers, filled by one elected producer lane -> ld.shared.f64 fragments ->
-// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05 has no f64 kind).  CTA tile 128 x 64 x 16,
-// 8 consumer warps of 32 x 32.
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05 has no f64 kind).  CTA tile 128 x 64 x 16 with
+// 8 warps of 32 x 32 (or 64 x 16 for outputs at most 16 wide).
 //
 // Operand layouts in global memory:
 //   LAY_KC  the contraction index is contiguous:  element (r,k) at ptr[r*ld + k]
@@ -59,6 +59,7 @@ struct GemmArgs {
   int has_a1, has_b1;  // R operands present (NULL R-vector == zero, variable.go:85-91)
   int epi;
   int k_tiles_per_split;
+  int transpose_out;  // write element (i,j) at out[j*ldo + i] (operands were swapped by the host)
   double* out0;
   double* out1;
   long long ldo;
@@ -109,7 +110,7 @@ __device__ __forceinline__ void epi_transform(const GemmArgs& p, long long i, in
 
 template <bool DUAL>
 __device__ __forceinline__ void epi_elem(const GemmArgs& p, long long i, int j, double v0, double v1) {
-  long long o = i * p.ldo + j;
+  long long o = p.transpose_out ? (long long)j * p.ldo + i : i * p.ldo + j;
   if (p.epi == EPI_ACCUM) {
     if (p.out0) p.out0[o] += v0;
     if (DUAL && p.out1) p.out1[o] += v1;
@@ -198,10 +199,21 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <int NACC>
+// Tile configurations.  A CTA is 8 warps laid out WI x WJ; each warp owns TI x TJ DMMA tiles (8x8).
+//   CFG 0 "big"    : 4x2 warps of 32x32 -> 128 x 64   (everything with J > 16)
+//   CFG 1 "narrow" : 8x1 warps of  8x16 ->  64 x 16   (J <= 16: the 10-wide output layer, and, with
+//                    swapped operands + transposed store, its 10-row weight gradient)
+template <int CFG> struct TileCfg;
+template <> struct TileCfg<0> { static constexpr int WI = 4, WJ = 2, TI = 4, TJ = 4; };
+template <> struct TileCfg<1> { static constexpr int WI = 8, WJ = 1, TI = 1, TJ = 2; };
+
+template <int NACC, int CFG>
 struct GemmSmem {
-  static constexpr uint32_t kABytes = kBM * kBK * 8;
-  static constexpr uint32_t kBBytes = kBN * kBK * 8;
+  using T = TileCfg<CFG>;
+  static constexpr int kBMc = T::WI * T::TI * 8;
+  static constexpr int kBNc = T::WJ * T::TJ * 8;
+  static constexpr uint32_t kABytes = kBMc * kBK * 8;
+  static constexpr uint32_t kBBytes = kBNc * kBK * 8;
   static constexpr uint32_t kStageBytes = NACC * (kABytes + kBBytes);
   static constexpr uint32_t kA0 = 0;
   static constexpr uint32_t kA1 = kABytes;                    // NACC == 2 only
@@ -209,6 +221,9 @@ struct GemmSmem {
   static constexpr uint32_t kB1 = NACC * kABytes + kBBytes;   // NACC == 2 only
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   static constexpr uint32_t kTotal = kBarOffset + 2 * kStages * 8 + 1024;  // + alignment slack
+  static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "swizzle atoms must stay 1024-byte aligned");
+  static_assert(T::WI * T::WJ == kConsumerWarps, "8 warps per CTA");
+  static_assert((T::TI == 1 || (T::TI * 8) % 16 == 0) && (T::TJ == 1 || (T::TJ * 8) % 16 == 0), "frag_addr assumes 16-row alignment");
 };
 
 template <int LAY, int ROWS>
@@ -221,12 +236,14 @@ __device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* m
   }
 }
 
-// byte offset of fragment element (row = w0 + 8t + g, k) inside a tile, minus the t-dependent part
+// byte offset of fragment element (row = w0 + g, k) inside a swizzled tile image
 template <int LAY>
 __device__ __forceinline__ uint32_t frag_base(int w0, int g, int k) {
-  if (LAY == LAY_KC) return (uint32_t)((w0 + g) * 128 + ((((k >> 1) ^ g) & 7) << 4) + ((k & 1) << 3));
-  return (uint32_t)((w0 >> 4) * 2048 + k * 128 + ((((g >> 1) ^ (k & 7)) & 7) << 4) + ((g & 1) << 3));
+  const int row = w0 + g;
+  if (LAY == LAY_KC) return (uint32_t)(row * 128 + ((((k >> 1) ^ row) & 7) << 4) + ((k & 1) << 3));
+  return (uint32_t)((row >> 4) * 2048 + k * 128 + (((((row & 15) >> 1) ^ k) & 7) << 4) + ((row & 1) << 3));
 }
+// ... of row + 8t (w0 is a multiple of 16 whenever t > 0 is used)
 template <int LAY>
 __device__ __forceinline__ uint32_t frag_addr(uint32_t base, int t) {
   if (LAY == LAY_KC) return base + t * 1024;
@@ -236,17 +253,19 @@ __device__ __forceinline__ uint32_t frag_addr(uint32_t base, int t) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int ALAY, int BLAY, int NACC>
+template <int ALAY, int BLAY, int NACC, int CFG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs p) {
-  using L = GemmSmem<NACC>;
+  using L = GemmSmem<NACC, CFG>;
+  using T = TileCfg<CFG>;
   constexpr bool DUAL = (NACC == 2);
+  constexpr int TI = T::TI, TJ = T::TJ, BM = L::kBMc, BN = L::kBNc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms are 1024-B aligned
   const uint32_t bars = base + L::kBarOffset;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.y * kBM, j0 = blockIdx.x * kBN;
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
   const int kt_total = (p.Kd + kBK - 1) / kBK;
   const int kt_begin = blockIdx.z * p.k_tiles_per_split;
   int nkt = kt_total - kt_begin;
@@ -277,18 +296,18 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const uint32_t st = base + s * L::kStageBytes;
     const int k0 = (kt_begin + t) * kBK;
     mbar_expect_tx(full, tx_bytes);
-    tma_load_tile<ALAY, kBM>(st + L::kA0, &tmA0, full, i0, k0);
-    tma_load_tile<BLAY, kBN>(st + L::kB0, &tmB0, full, j0, k0);
-    if (has_a1) tma_load_tile<ALAY, kBM>(st + L::kA1, &tmA1, full, i0, k0);
-    if (has_b1) tma_load_tile<BLAY, kBN>(st + L::kB1, &tmB1, full, j0, k0);
+    tma_load_tile<ALAY, BM>(st + L::kA0, &tmA0, full, i0, k0);
+    tma_load_tile<BLAY, BN>(st + L::kB0, &tmB0, full, j0, k0);
+    if (has_a1) tma_load_tile<ALAY, BM>(st + L::kA1, &tmA1, full, i0, k0);
+    if (has_b1) tma_load_tile<BLAY, BN>(st + L::kB1, &tmB1, full, j0, k0);
   };
   if (threadIdx.x == 0) {
     for (int t = 0; t < kStages - 1 && t < nkt; ++t) produce(t);
   }
 
-  // ---------------- consumers: 8 warps, 4 (i) x 2 (j), 32 x 32 each ----------------
+  // ---------------- consumers: 8 warps, WI (i) x WJ (j) ----------------
   const int g = lane >> 2, j4 = lane & 3;
-  const int wi0 = (warp >> 1) * 32, wj0 = (warp & 1) * 32;
+  const int wi0 = (warp / T::WJ) * (TI * 8), wj0 = (warp % T::WJ) * (TJ * 8);
   const int kj = ((j4 & 1) ? 3 : 0) | ((j4 & 2) ? 12 : 0);
   uint32_t fa[4], fb[4];
   {
@@ -300,68 +319,87 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   }
 
-  double acc0[4][4][2], acc1[DUAL ? 4 : 1][4][2];
+  double acc0[TI][TJ][2], acc1[DUAL ? TI : 1][TJ][2];
 #pragma unroll
-  for (int t = 0; t < 4; ++t)
+  for (int t = 0; t < TI; ++t)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < TJ; ++u) {
       acc0[t][u][0] = acc0[t][u][1] = 0.0;
       if (DUAL) acc1[t][u][0] = acc1[t][u][1] = 0.0;
     }
 
+  // Fragment registers are double-buffered by hand ACROSS k-tile boundaries: the loads of MMA step
+  // q+1 (possibly the first step of the next stage) are issued before the DMMAs of step q, so the
+  // two warps of a sub-partition never both sit on an mbarrier wait + LDS latency with the tensor
+  // pipe idle.
+  double a0[2][TI], b0[2][TJ], a1[2][DUAL ? TI : 1], b1[2][DUAL ? TJ : 1];
+  auto load_frags = [&](int buf, uint32_t st, int ks) {
+#pragma unroll
+    for (int t = 0; t < TI; ++t) a0[buf][t] = lds_f64(st + L::kA0 + frag_addr<ALAY>(fa[ks], t));
+#pragma unroll
+    for (int u = 0; u < TJ; ++u) b0[buf][u] = lds_f64(st + L::kB0 + frag_addr<BLAY>(fb[ks], u));
+    if (has_a1) {
+#pragma unroll
+      for (int t = 0; t < TI; ++t) a1[buf][DUAL ? t : 0] = lds_f64(st + L::kA1 + frag_addr<ALAY>(fa[ks], t));
+    }
+    if (has_b1) {
+#pragma unroll
+      for (int u = 0; u < TJ; ++u) b1[buf][DUAL ? u : 0] = lds_f64(st + L::kB1 + frag_addr<BLAY>(fb[ks], u));
+    }
+  };
+  auto mma_step = [&](int buf) {
+#pragma unroll
+    for (int t = 0; t < TI; ++t)
+#pragma unroll
+      for (int u = 0; u < TJ; ++u) dmma_8x8x4(acc0[t][u][0], acc0[t][u][1], a0[buf][t], b0[buf][u]);
+    if (has_b1) {
+#pragma unroll
+      for (int t = 0; t < TI; ++t)
+#pragma unroll
+        for (int u = 0; u < TJ; ++u)
+          dmma_8x8x4(acc1[DUAL ? t : 0][u][0], acc1[DUAL ? t : 0][u][1], a0[buf][t], b1[buf][DUAL ? u : 0]);
+    }
+    if (has_a1) {
+#pragma unroll
+      for (int t = 0; t < TI; ++t)
+#pragma unroll
+        for (int u = 0; u < TJ; ++u)
+          dmma_8x8x4(acc1[DUAL ? t : 0][u][0], acc1[DUAL ? t : 0][u][1], a1[buf][DUAL ? t : 0], b0[buf][u]);
+    }
+  };
+
+  mbar_wait(bars + 0, 0);
+  load_frags(0, base, 0);
   for (int kt = 0; kt < nkt; ++kt) {
     const int s = kt % kStages;
-    const uint32_t ph = (kt / kStages) & 1;
+    const uint32_t st = base + s * L::kStageBytes;
     if (threadIdx.x == 0 && kt + kStages - 1 < nkt) produce(kt + kStages - 1);
     __syncwarp();
-    mbar_wait(bars + 8 * s, ph);
-    const uint32_t st = base + s * L::kStageBytes;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      double a0[4], b0[4], a1[4], b1[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        a0[t] = lds_f64(st + L::kA0 + frag_addr<ALAY>(fa[ks], t));
-        b0[t] = lds_f64(st + L::kB0 + frag_addr<BLAY>(fb[ks], t));
+      if (ks < 3) {
+        load_frags((ks + 1) & 1, st, ks + 1);
+      } else if (kt + 1 < nkt) {
+        const int s1 = (kt + 1) % kStages;
+        mbar_wait(bars + 8 * s1, ((kt + 1) / kStages) & 1);
+        load_frags(0, base + s1 * L::kStageBytes, 0);
       }
-      if (has_a1) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) a1[t] = lds_f64(st + L::kA1 + frag_addr<ALAY>(fa[ks], t));
-      }
-      if (has_b1) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) b1[t] = lds_f64(st + L::kB1 + frag_addr<BLAY>(fb[ks], t));
-      }
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) dmma_8x8x4(acc0[t][u][0], acc0[t][u][1], a0[t], b0[u]);
-      if (has_b1) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-#pragma unroll
-          for (int u = 0; u < 4; ++u) dmma_8x8x4(acc1[DUAL ? t : 0][u][0], acc1[DUAL ? t : 0][u][1], a0[t], b1[u]);
-      }
-      if (has_a1) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-#pragma unroll
-          for (int u = 0; u < 4; ++u) dmma_8x8x4(acc1[DUAL ? t : 0][u][0], acc1[DUAL ? t : 0][u][1], a1[t], b0[u]);
-      }
+      mma_step(ks & 1);
     }
+    // every ld.shared of this stage has been consumed by an issued DMMA: hand the slot back
     __syncwarp();
     if (lane == 0) mbar_arrive(bars + 8 * (kStages + s));
   }
 
   // ---------------- epilogue: registers -> global, fused elementwise ----------------
-  const bool vec_ok = ((p.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.out0) & 15) == 0) &&
+  const bool vec_ok = !p.transpose_out && ((p.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.out0) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.out1) & 15) == 0);
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < TI; ++t) {
     const long long i = i0 + wi0 + 8 * t + g;
     if (i < p.I) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < TJ; ++u) {
         const int j = j0 + wj0 + 8 * u + 2 * j4;
         if (j < p.J)
           epi_pair<DUAL>(p, vec_ok, i, j, acc0[t][u][0], acc0[t][u][1], DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0,
