@@ -29,6 +29,7 @@ PROTOTYPES = {
     "af_version": (INT, []),
     "af_launch_count": (I64, [P]),
     "af_set_gemm_path": (INT, [P, INT]),
+    "af_set_option": (INT, [P, C.c_char_p, INT]),
     "af_trace_begin": (INT, [P, INT]),
     "af_trace_end": (INT, [P, INT, C.POINTER(INT), C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(INT)]),
     "af_malloc": (INT, [P, I64, C.POINTER(D)]),

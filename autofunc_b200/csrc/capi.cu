@@ -155,6 +155,16 @@ int af_trace_end(af_ctx* ctx, int capacity, int* h_kind, double* h_work, float* 
   return AF_OK;
 }
 
+int af_set_option(af_ctx* ctx, const char* name, int value) {
+  if (!ctx || !name) return fail(AF_EINVAL, "null argument");
+  if (!strcmp(name, "big_cfg")) {
+    if (value != 0 && value != 2 && value != 3) return fail(AF_EINVAL, "big_cfg must be 0 (128x64, 8 warps), 2 (64x64, 2 CTAs/SM) or 3 (128x64, 16 warps)");
+    ctx->big_cfg = value;
+    return AF_OK;
+  }
+  return fail(AF_EINVAL, std::string("unknown option ") + name);
+}
+
 int af_set_gemm_path(af_ctx* ctx, int mode) {
   if (!ctx) return fail(AF_EINVAL, "null context");
   if (mode < 0 || mode > 2) return fail(AF_EINVAL, "gemm path must be 0, 1 or 2");

@@ -16,6 +16,7 @@ struct af_ctx {
   bool owns_stream = false;
   int sm_count = 148;
   int gemm_path = 0;  // 0 auto, 1 generic, 2 require DMMA
+  int big_cfg = 2;    // tile configuration for wide outputs: 0 = 128x64 x 8 warps, 2 = 64x64 x 2 CTAs/SM (default, fastest measured), 3 = 128x64 x 16 warps
   int64_t launches = 0;
   // driver entry point, resolved at run time so the library loads on hosts without libcuda
   void* encode_tiled = nullptr;

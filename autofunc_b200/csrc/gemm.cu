@@ -62,7 +62,7 @@ int launch_dmma(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3
     AF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, kGemmThreads, smem, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], args);
+  kern<<<grid, GemmSmem<NACC, CFG>::kThreads, smem, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], args);
   return after_launch(ctx, "gemm_dmma_kernel", NACC == 2 ? KIND_GEMM_DUAL : KIND_GEMM_SINGLE, gemm_flops(args, NACC == 2));
 }
 
@@ -132,9 +132,9 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
     return fail(AF_EINVAL, "unsupported operand layout combination");
   }
 
-  const int cfg = J <= 16 ? 1 : 0;
-  const int bm = cfg == 1 ? GemmSmem<2, 1>::kBMc : GemmSmem<2, 0>::kBMc;
-  const int bn = cfg == 1 ? GemmSmem<2, 1>::kBNc : GemmSmem<2, 0>::kBNc;
+  const int cfg = J <= 16 ? 1 : ctx->big_cfg;
+  const int bm = cfg == 1 ? GemmSmem<2, 1>::kBMc : cfg == 2 ? GemmSmem<2, 2>::kBMc : GemmSmem<2, 0>::kBMc;  // cfg 3 == cfg 0 shape
+  const int bn = cfg == 1 ? GemmSmem<2, 1>::kBNc : cfg == 2 ? GemmSmem<2, 2>::kBNc : GemmSmem<2, 0>::kBNc;
   CUtensorMap maps[4];
   AF_TRY(make_map(ctx, &maps[0], A.p0, A.layout, I, Kd, A.ld, bm));
   AF_TRY(make_map(ctx, &maps[2], B.p0, B.layout, J, Kd, B.ld, bn));
@@ -143,7 +143,7 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
 
   dim3 grid((unsigned)((J + bn - 1) / bn), (unsigned)((I + bm - 1) / bm), 1);
   if (accumulate) {
-    int splits = choose_splits((long long)grid.x * grid.y, kt_total, ctx->sm_count);
+    int splits = choose_splits((long long)grid.x * grid.y, kt_total, ctx->sm_count * (cfg == 2 ? 2 : 1));
     if (splits > 1) {
       args.k_tiles_per_split = (kt_total + splits - 1) / splits;
       splits = (kt_total + args.k_tiles_per_split - 1) / args.k_tiles_per_split;
@@ -156,6 +156,10 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   if (A.layout == AL && B.layout == BL) {                                                          \
     if (cfg == 0)                                                                                  \
       return nacc == 2 ? launch_dmma<AL, BL, 2, 0>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 0>(ctx, maps, args, grid); \
+    if (cfg == 2)                                                                                  \
+      return nacc == 2 ? launch_dmma<AL, BL, 2, 2>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 2>(ctx, maps, args, grid); \
+    if (cfg == 3)                                                                                  \
+      return nacc == 2 ? launch_dmma<AL, BL, 2, 3>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 3>(ctx, maps, args, grid); \
     return nacc == 2 ? launch_dmma<AL, BL, 2, 1>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 1>(ctx, maps, args, grid);   \
   }
   AF_DISPATCH(LAY_KC, LAY_KC)

@@ -40,9 +40,7 @@ namespace af {
 constexpr int kBK = 16;
 constexpr int kBM = 128;
 constexpr int kBN = 64;
-constexpr int kStages = 4;
-constexpr int kConsumerWarps = 8;
-constexpr int kGemmThreads = kConsumerWarps * 32;
+// stage count, warp count and CTAs per SM are per tile configuration (TileCfg below)
 
 enum : int { LAY_KC = 0, LAY_RC = 1 };
 enum : int {
@@ -204,8 +202,14 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 //   CFG 1 "narrow" : 8x1 warps of  8x16 ->  64 x 16   (J <= 16: the 10-wide output layer, and, with
 //                    swapped operands + transposed store, its 10-row weight gradient)
 template <int CFG> struct TileCfg;
-template <> struct TileCfg<0> { static constexpr int WI = 4, WJ = 2, TI = 4, TJ = 4; };
-template <> struct TileCfg<1> { static constexpr int WI = 8, WJ = 1, TI = 1, TJ = 2; };
+template <> struct TileCfg<0> { static constexpr int WI = 4, WJ = 2, TI = 4, TJ = 4, STAGES = 4, MIN_CTAS = 1, PREFETCH = 1; };
+template <> struct TileCfg<1> { static constexpr int WI = 8, WJ = 1, TI = 1, TJ = 2, STAGES = 4, MIN_CTAS = 1, PREFETCH = 1; };
+//   CFG 2 "paired" : 2x2 warps of 32x32 ->  64 x 64, 3 stages, TWO CTAs per SM: the two CTAs drift out of
+//                    phase, so one CTA's epilogue / pipeline fill overlaps the other's DMMA stream
+template <> struct TileCfg<2> { static constexpr int WI = 2, WJ = 2, TI = 4, TJ = 4, STAGES = 3, MIN_CTAS = 2, PREFETCH = 1; };
+//   CFG 3 "wide"   : 4x4 warps of 32x16 -> 128 x 64 with FOUR warps per sub-partition (<= 128 registers):
+//                    latency is hidden by warp count instead of register double-buffering
+template <> struct TileCfg<3> { static constexpr int WI = 4, WJ = 4, TI = 4, TJ = 2, STAGES = 4, MIN_CTAS = 1, PREFETCH = 0; };
 
 template <int NACC, int CFG>
 struct GemmSmem {
@@ -219,10 +223,12 @@ struct GemmSmem {
   static constexpr uint32_t kA1 = kABytes;                    // NACC == 2 only
   static constexpr uint32_t kB0 = NACC * kABytes;
   static constexpr uint32_t kB1 = NACC * kABytes + kBBytes;   // NACC == 2 only
+  static constexpr int kStages = T::STAGES;
+  static constexpr int kWarps = T::WI * T::WJ;
+  static constexpr int kThreads = kWarps * 32;
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   static constexpr uint32_t kTotal = kBarOffset + 2 * kStages * 8 + 1024;  // + alignment slack
   static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "swizzle atoms must stay 1024-byte aligned");
-  static_assert(T::WI * T::WJ == kConsumerWarps, "8 warps per CTA");
   static_assert((T::TI == 1 || (T::TI * 8) % 16 == 0) && (T::TJ == 1 || (T::TJ * 8) % 16 == 0), "frag_addr assumes 16-row alignment");
 };
 
@@ -254,13 +260,13 @@ __device__ __forceinline__ uint32_t frag_addr(uint32_t base, int t) {
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int ALAY, int BLAY, int NACC, int CFG>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(TileCfg<CFG>::WI * TileCfg<CFG>::WJ * 32, TileCfg<CFG>::MIN_CTAS)
 gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs p) {
   using L = GemmSmem<NACC, CFG>;
   using T = TileCfg<CFG>;
   constexpr bool DUAL = (NACC == 2);
-  constexpr int TI = T::TI, TJ = T::TJ, BM = L::kBMc, BN = L::kBNc;
+  constexpr int TI = T::TI, TJ = T::TJ, BM = L::kBMc, BN = L::kBNc, kStages = L::kStages, kConsumerWarps = L::kWarps;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms are 1024-B aligned
   const uint32_t bars = base + L::kBarOffset;
@@ -332,7 +338,8 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // q+1 (possibly the first step of the next stage) are issued before the DMMAs of step q, so the
   // two warps of a sub-partition never both sit on an mbarrier wait + LDS latency with the tensor
   // pipe idle.
-  double a0[2][TI], b0[2][TJ], a1[2][DUAL ? TI : 1], b1[2][DUAL ? TJ : 1];
+  constexpr int NB = T::PREFETCH ? 2 : 1;
+  double a0[NB][TI], b0[NB][TJ], a1[NB][DUAL ? TI : 1], b1[NB][DUAL ? TJ : 1];
   auto load_frags = [&](int buf, uint32_t st, int ks) {
 #pragma unroll
     for (int t = 0; t < TI; ++t) a0[buf][t] = lds_f64(st + L::kA0 + frag_addr<ALAY>(fa[ks], t));
@@ -368,27 +375,44 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   };
 
-  mbar_wait(bars + 0, 0);
-  load_frags(0, base, 0);
-  for (int kt = 0; kt < nkt; ++kt) {
-    const int s = kt % kStages;
-    const uint32_t st = base + s * L::kStageBytes;
-    if (threadIdx.x == 0 && kt + kStages - 1 < nkt) produce(kt + kStages - 1);
-    __syncwarp();
+  if (T::PREFETCH) {
+    mbar_wait(bars + 0, 0);
+    load_frags(0, base, 0);
+    for (int kt = 0; kt < nkt; ++kt) {
+      const int s = kt % kStages;
+      const uint32_t st = base + s * L::kStageBytes;
+      if (threadIdx.x == 0 && kt + kStages - 1 < nkt) produce(kt + kStages - 1);
+      __syncwarp();
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      if (ks < 3) {
-        load_frags((ks + 1) & 1, st, ks + 1);
-      } else if (kt + 1 < nkt) {
-        const int s1 = (kt + 1) % kStages;
-        mbar_wait(bars + 8 * s1, ((kt + 1) / kStages) & 1);
-        load_frags(0, base + s1 * L::kStageBytes, 0);
+      for (int ks = 0; ks < 4; ++ks) {
+        if (ks < 3) {
+          load_frags((ks + 1) & 1, st, ks + 1);
+        } else if (kt + 1 < nkt) {
+          const int s1 = (kt + 1) % kStages;
+          mbar_wait(bars + 8 * s1, ((kt + 1) / kStages) & 1);
+          load_frags(0, base + s1 * L::kStageBytes, 0);
+        }
+        mma_step(ks & 1);
       }
-      mma_step(ks & 1);
+      // every ld.shared of this stage has been consumed by an issued DMMA: hand the slot back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (kStages + s));
     }
-    // every ld.shared of this stage has been consumed by an issued DMMA: hand the slot back
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bars + 8 * (kStages + s));
+  } else {
+    for (int kt = 0; kt < nkt; ++kt) {
+      const int s = kt % kStages;
+      const uint32_t st = base + s * L::kStageBytes;
+      if (threadIdx.x == 0 && kt + kStages - 1 < nkt) produce(kt + kStages - 1);
+      __syncwarp();
+      mbar_wait(bars + 8 * s, (kt / kStages) & 1);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        load_frags(0, st, ks);
+        mma_step(0);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (kStages + s));
+    }
   }
 
   // ---------------- epilogue: registers -> global, fused elementwise ----------------

@@ -194,6 +194,8 @@ def gpu_arm(args):
     ctx = api.Context(local_rank, stream=stream.cuda_stream)
     api.set_context(ctx)
     ctx.set_gemm_path(2)  # TMA + DMMA or an error; never a silent fallback
+    if args.big_cfg is not None:
+        api.check(ctx.lib.af_set_option(ctx.h, b"big_cfg", args.big_cfg))
     plan = api.MLPPlan(LAYER_SIZES, n, ctx)
     params, rvecs = synth.mlp_params(LAYER_SIZES)
     for i, (p, r) in enumerate(zip(params, rvecs)):
@@ -239,6 +241,14 @@ def gpu_arm(args):
     clocks = sampler.stop()
     api.check(ctx.lib.af_trace_end(ctx.h, cap, kinds, work, ms_arr, C.byref(count)))
     launches = ctx.launch_count() - launches0
+    if args.trace and rank == 0:
+        per_step = count.value // K
+        names = {0: "gemm_dual", 1: "gemm_single", 2: "gemm_generic", 3: "elementwise", 4: "reduce"}
+        for i in range(count.value - per_step, count.value):
+            rate = work[i] / (ms_arr[i] * 1e-3) / 1e12 if ms_arr[i] > 0 else 0.0
+            unit = "TFLOP/s" if kinds[i] < 3 else "TB/s"
+            print(f"trace[{i - (count.value - per_step):2d}] {names[kinds[i]]:12s} {ms_arr[i] * 1e3:9.1f} us  work {work[i]:.4g}  {rate:7.2f} {unit}",
+                  file=sys.stderr)
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
@@ -344,6 +354,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=1024, help="samples per CPU-oracle step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--big-cfg", type=int, default=None, help="DMMA tile configuration for wide outputs (0 or 2)")
+    ap.add_argument("--trace", action="store_true", help="print the last step's per-launch device times to stderr")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3

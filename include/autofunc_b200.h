@@ -66,6 +66,9 @@ int af_trace_end(af_ctx* ctx, int capacity, int* h_kind, double* h_work, float* 
  * operands satisfy TMA alignment, else the generic kernel), 1 = force generic, 2 = require DMMA
  * (returns AF_ENOTSUP instead of falling back). */
 int af_set_gemm_path(af_ctx* ctx, int mode);
+/* Tuning knobs (measurement / A-B runs).  "big_cfg": tile configuration of the DMMA kernel for outputs
+ * wider than 16 columns: 0 = 128x64 tile, one CTA per SM; 2 = 64x64 tile, two CTAs per SM.          */
+int af_set_option(af_ctx* ctx, const char* name, int value);
 
 int af_malloc(af_ctx* ctx, int64_t n_doubles, double** d_out);
 int af_free(af_ctx* ctx, double* d_ptr);

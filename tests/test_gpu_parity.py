@@ -119,10 +119,11 @@ def _rand(seed, n):
 
 
 @pytest.mark.parametrize("rows,cols,n", SHAPES)
-@pytest.mark.parametrize("path", [2, 1])  # 2 = require TMA+DMMA (no silent fallback), 1 = generic kernel
-def test_lintran_kernels_match_oracle(api, rows, cols, n, path):
+@pytest.mark.parametrize("path,big_cfg", [(2, 0), (2, 2), (2, 3), (1, 0)])  # 2 = require TMA+DMMA (both tile configs), 1 = generic kernel
+def test_lintran_kernels_match_oracle(api, rows, cols, n, path, big_cfg):
     ctx = api.context()
     ctx.set_gemm_path(path)
+    api.check(ctx.lib.af_set_option(ctx.h, b"big_cfg", big_cfg))
     try:
         W, RW = _rand(1, rows * cols), _rand(2, rows * cols)
         X, RX = _rand(3, n * cols), _rand(4, n * cols)
@@ -172,6 +173,7 @@ def test_lintran_kernels_match_oracle(api, rows, cols, n, path):
         close(dDR.numpy(), dr, "G6 inputGradientR")
     finally:
         ctx.set_gemm_path(0)
+        api.check(ctx.lib.af_set_option(ctx.h, b"big_cfg", 2))
 
 
 def test_odd_pitch_falls_back_or_refuses(api):
