@@ -85,6 +85,24 @@ PROTOTYPES = {
     "af_mlp_zero_grads": (INT, [P]),
     "af_mlp_step": (INT, [P, INT, INT]),
     "af_mlp_step_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),
+    "af_copy_2d": (INT, [P, D, I64, D, I64, I64, I64]),
+    "af_lstm_create": (INT, [P, I64, I64, I64, I64, I64, C.POINTER(P)]),
+    "af_lstm_destroy": (INT, [P]),
+    "af_lstm_set_param": (INT, [P, INT, H, I64]),
+    "af_lstm_set_rvector": (INT, [P, INT, H, I64]),
+    "af_lstm_param_ptr": (D, [P, INT]),
+    "af_lstm_grad_ptr": (D, [P, INT]),
+    "af_lstm_rgrad_ptr": (D, [P, INT]),
+    "af_lstm_output_ptr": (D, [P]),
+    "af_lstm_routput_ptr": (D, [P]),
+    "af_lstm_upstream_ptr": (D, [P]),
+    "af_lstm_upstream_r_ptr": (D, [P]),
+    "af_lstm_grad_slab": (I64, [P, C.POINTER(D)]),
+    "af_lstm_zero_grads": (INT, [P]),
+    "af_lstm_set_inputs": (INT, [P, D]),
+    "af_lstm_forward": (INT, [P, INT]),
+    "af_lstm_backward": (INT, [P, INT]),
+    "af_lstm_run_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),
 }
 
 _lib = None

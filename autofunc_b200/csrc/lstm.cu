@@ -1,0 +1,381 @@
+// The LSTM of bench/lstm.go (lstmBlock :129-151, lstmNet.StepTime :169-198, PropagateGradient
+// :215-234), batched over B lanes and with the R-operator carried through, as one resident plan.
+//
+// Structure.  The four gate matrices share one input, concat(state, x)
+// (bench/lstm.go:140,188), so they are stored stacked as one (4H) x (H+I) matrix W4 and evaluated by
+// ONE fused contraction per time step (+bias, sigmoid, and the R forms in the epilogue); the cell
+// algebra (Mul/Add, arithmetic.go:17-96,261-376) is one pointwise kernel per step.  Everything that
+// does not depend on the recurrence is batched over all T*B rows: the output layer, its backward, and
+// every weight / bias gradient (contraction over T*B samples instead of T launches).
+//
+//   forward  t = 0..T-1 :  G_t = sigmoid(IN_t W4^T + b4)            [af_dense_fwd, 4H x (H+I), n = B]
+//                          s_t = f.s_{t-1} + m.i ; masked = s_t.o   [lstm_cell_fwd_kernel]
+//            after loop  :  RES = sigmoid(AUG Wout^T + bout)         [af_dense_fwd, n = T*B]
+//   backward before loop:  dOut = sigmoid'(RES) up ; gWout, gbout ; dAUG = dOut Wout
+//            t = T-1..0  :  delta4_t, sg' = sg.f                      [lstm_cell_bwd_kernel]
+//                          sg' += delta4_t W4[:, :H]                 [dual contraction, += , split-K]
+//            after loop  :  gW4 += delta4^T IN ; gb4 += colsum(delta4)   (n = T*B)
+#include <vector>
+
+#include "common.h"
+#include "gemm_dmma.cuh"
+
+namespace af {
+int colsum_launch(af_ctx* ctx, const double* U, const double* UR, double* gb, double* rgb, long long len, long long n);
+
+namespace {
+
+// dst[r][c] = src[r][c] for a rows x cols block with independent row pitches
+__global__ void __launch_bounds__(256) copy2d_kernel(double* __restrict__ dst, long long ldd, const double* __restrict__ src,
+                                                     long long lds, long long rows, long long cols) {
+  const long long n = rows * cols;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const long long r = i / cols, c = i - r * cols;
+    dst[r * ldd + c] = src[r * lds + c];
+  }
+}
+
+// Cell forward for one time step, B x H elements.  Gates G = [i | m | f | o] (B x 4H).
+//   s = f*sp + m*i            Add(Mul(forget, state), Mul(inMask, inState))   bench/lstm.go:147-150
+//   masked = s*o              Mul(outStateVar, outGate)                       bench/lstm.go:191
+// R forms follow MulR (arithmetic.go:325-329: x*yR + xR*y) and AddR (:58-65).
+__global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(const double* __restrict__ G, const double* __restrict__ RG,
+                                                            const double* __restrict__ INp, const double* __restrict__ RINp,
+                                                            double* __restrict__ INn, double* __restrict__ RINn,
+                                                            double* __restrict__ AUG, double* __restrict__ RAUG, int B,
+                                                            int H, int ld) {
+  const int n = B * H;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += gridDim.x * 256) {
+    const int b = e / H, j = e - b * H;
+    const double* g = G + (long long)b * 4 * H;
+    const double i = g[j], m = g[H + j], f = g[2 * H + j], o = g[3 * H + j];
+    const long long si = (long long)b * ld + j;
+    const double sp = INp[si];
+    const double s = f * sp + m * i;
+    INn[si] = s;
+    AUG[si] = s * o;
+    if (RG) {
+      const double* rg = RG + (long long)b * 4 * H;
+      const double ri = rg[j], rm = rg[H + j], rf = rg[2 * H + j], ro = rg[3 * H + j];
+      const double rsp = RINp[si];
+      const double rs = (f * rsp + rf * sp) + (m * ri + rm * i);
+      RINn[si] = rs;
+      RAUG[si] = s * ro + rs * o;
+    }
+  }
+}
+
+// Cell backward for one time step (bench/lstm.go:215-234 with the node backwards of
+// arithmetic.go:34-49,288-306 / 79-96,349-376 and math_funcs.go:326-333 / 357-374 inlined).
+//   sg  = sg_carry + dmasked*o          (grad[outStateVar] added to stateGrad, lstm.go:227-228)
+//   do  = dmasked*s                     -> delta_o = sigmoid'(o) do
+//   dm  = sg*i ; di = sg*m ; df = sg*sp -> delta_* = sigmoid'(gate) d*
+//   sg' = sg*f                          (Mul(forget,state) toward the state)
+// D4 = [delta_i | delta_m | delta_f | delta_o]; SGn receives sg' and is then accumulated into by the
+// input-gradient contraction (delta4 W4[:, :H]).
+__global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(
+    const double* __restrict__ G, const double* __restrict__ RG, const double* __restrict__ INp,
+    const double* __restrict__ RINp, const double* __restrict__ INn, const double* __restrict__ RINn,
+    const double* __restrict__ DAUG, const double* __restrict__ RDAUG, const double* __restrict__ SG,
+    const double* __restrict__ RSG, double* __restrict__ SGn, double* __restrict__ RSGn, double* __restrict__ D4,
+    double* __restrict__ RD4, int B, int H, int ld) {
+  const int n = B * H;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += gridDim.x * 256) {
+    const int b = e / H, j = e - b * H;
+    const long long gi = (long long)b * 4 * H, si = (long long)b * ld + j;
+    const double i = G[gi + j], m = G[gi + H + j], f = G[gi + 2 * H + j], o = G[gi + 3 * H + j];
+    const double sp = INp[si], s = INn[si];
+    const double dmask = DAUG[si];
+    const double sg = SG[e] + dmask * o;
+    const double d_o = dmask * s, d_m = sg * i, d_i = sg * m, d_f = sg * sp;
+    D4[gi + j] = i * (1 - i) * d_i;
+    D4[gi + H + j] = m * (1 - m) * d_m;
+    D4[gi + 2 * H + j] = f * (1 - f) * d_f;
+    D4[gi + 3 * H + j] = o * (1 - o) * d_o;
+    SGn[e] = sg * f;
+    if (RG) {
+      const double ri = RG[gi + j], rm = RG[gi + H + j], rf = RG[gi + 2 * H + j], ro = RG[gi + 3 * H + j];
+      const double rsp = RINp[si], rs = RINn[si];
+      const double rdmask = RDAUG[si];
+      // downstreamR = u*otherR + uR*other (arithmetic.go:358-362)
+      const double rsg = RSG[e] + (dmask * ro + rdmask * o);
+      const double rd_o = dmask * rs + rdmask * s;
+      const double rd_m = sg * ri + rsg * i, rd_i = sg * rm + rsg * m, rd_f = sg * rsp + rsg * sp;
+      // sigmoid R-backward, operand order of math_funcs.go:369-370
+      RD4[gi + j] = ri * (1 - i) * d_i - i * ri * d_i + i * (1 - i) * rd_i;
+      RD4[gi + H + j] = rm * (1 - m) * d_m - m * rm * d_m + m * (1 - m) * rd_m;
+      RD4[gi + 2 * H + j] = rf * (1 - f) * d_f - f * rf * d_f + f * (1 - f) * rd_f;
+      RD4[gi + 3 * H + j] = ro * (1 - o) * d_o - o * ro * d_o + o * (1 - o) * rd_o;
+      RSGn[e] = sg * rf + rsg * f;
+    }
+  }
+}
+
+int ew_grid(af_ctx* ctx, long long n) {
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+}  // namespace af
+
+using namespace af;
+
+struct af_lstm {
+  af_ctx* ctx = nullptr;
+  int64_t I = 0, H = 0, O = 0, T = 0, B = 0, C = 0;  // C = H + I
+  double* slab = nullptr;
+  // parameters: W4 (4H x C), b4 (4H), Wout (O x C), bout (O) and their R-vectors / accumulators
+  double *W4, *b4, *Wout, *bout, *RW4, *Rb4, *RWout, *Rbout;
+  double *gW4, *gb4, *gWout, *gbout, *rgW4, *rgb4, *rgWout, *rgbout;
+  bool has_r[10] = {false};
+  double *IN, *RIN;      // (T+1) x B x C : [:, :H] = state entering step t, [:, H:] = x_t
+  double *G, *RG;        // T x B x 4H gates
+  double *AUG, *RAUG;    // T x B x C : [masked | x_t]
+  double *RES, *RRES;    // T x B x O
+  double *UP, *RUP;      // T x B x O upstream (consumed)
+  double *DAUG, *RDAUG;  // T x B x C
+  double *D4, *RD4;      // T x B x 4H
+  double *SG[2], *RSG[2];
+  int64_t grad_doubles = 0;
+  int64_t param_len(int idx) const {
+    const int k = idx / 2;
+    const int64_t rows = k < 4 ? H : O;
+    return (idx & 1) ? rows : rows * C;
+  }
+  // reference order (bench/lstm.go:75-99): In, InGate, Forget, OutputGate, Output; weights then biases
+  double* block(int idx, double* w4, double* bb4, double* wout, double* bbout) const {
+    const int k = idx / 2;
+    if (k < 4) return (idx & 1) ? bb4 + k * H : w4 + k * H * C;
+    return (idx & 1) ? bbout : wout;
+  }
+};
+
+extern "C" {
+
+int af_copy_2d(af_ctx* ctx, double* d_dst, int64_t ld_dst, const double* d_src, int64_t ld_src, int64_t rows,
+               int64_t cols) {
+  if (!ctx) return fail(AF_EINVAL, "null context");
+  DeviceGuard guard(ctx->device);
+  if (rows <= 0 || cols <= 0) return AF_OK;
+  if (!d_dst || !d_src) return fail(AF_EINVAL, "null pointer argument");
+  if (ld_dst < cols || ld_src < cols) return fail(AF_ESHAPE, "row pitch smaller than the row length");
+  copy2d_kernel<<<ew_grid(ctx, rows * cols), 256, 0, ctx->stream>>>(d_dst, ld_dst, d_src, ld_src, rows, cols);
+  return after_launch(ctx, "copy2d_kernel", KIND_ELEMENTWISE, 16.0 * rows * cols);
+}
+
+int af_lstm_create(af_ctx* ctx, int64_t I, int64_t H, int64_t O, int64_t T, int64_t B, af_lstm** out) {
+  if (!ctx || !out) return fail(AF_EINVAL, "null argument");
+  if (I < 1 || H < 1 || O < 1 || T < 1 || B < 1) return fail(AF_ESHAPE, "LSTM dimensions must be positive");
+  DeviceGuard guard(ctx->device);
+  af_lstm* m = new af_lstm();
+  m->ctx = ctx; m->I = I; m->H = H; m->O = O; m->T = T; m->B = B; m->C = H + I;
+  const int64_t C = m->C;
+  auto pad = [](int64_t x) { return (x + 31) / 32 * 32; };
+  int64_t total = 0;
+  std::vector<int64_t> off;
+  auto take = [&](int64_t len) { off.push_back(total); total += pad(len); };
+  const int64_t plens[4] = {4 * H * C, 4 * H, O * C, O};
+  for (int rep = 0; rep < 4; ++rep)  // param, rvec, grad, rgrad
+    for (int k = 0; k < 4; ++k) take(plens[k]);
+  const int64_t TB = T * B;
+  take((T + 1) * B * C); take((T + 1) * B * C);  // IN, RIN
+  take(TB * 4 * H); take(TB * 4 * H);            // G, RG
+  take(TB * C); take(TB * C);                    // AUG, RAUG
+  take(TB * O); take(TB * O);                    // RES, RRES
+  take(TB * O); take(TB * O);                    // UP, RUP
+  take(TB * C); take(TB * C);                    // DAUG, RDAUG
+  take(TB * 4 * H); take(TB * 4 * H);            // D4, RD4
+  for (int k = 0; k < 4; ++k) take(B * H);       // SG[2], RSG[2]
+  cudaError_t e = cudaMalloc(&m->slab, (size_t)total * 8);
+  if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaMalloc(lstm slab)"); }
+  e = cudaMemsetAsync(m->slab, 0, (size_t)total * 8, ctx->stream);
+  if (e != cudaSuccess) { cudaFree(m->slab); delete m; return cuda_fail(e, "cudaMemsetAsync(lstm slab)"); }
+  size_t k = 0;
+  auto next = [&]() { return m->slab + off[k++]; };
+  m->W4 = next(); m->b4 = next(); m->Wout = next(); m->bout = next();
+  m->RW4 = next(); m->Rb4 = next(); m->RWout = next(); m->Rbout = next();
+  m->gW4 = next(); m->gb4 = next(); m->gWout = next(); m->gbout = next();
+  m->rgW4 = next(); m->rgb4 = next(); m->rgWout = next(); m->rgbout = next();
+  m->IN = next(); m->RIN = next(); m->G = next(); m->RG = next(); m->AUG = next(); m->RAUG = next();
+  m->RES = next(); m->RRES = next(); m->UP = next(); m->RUP = next(); m->DAUG = next(); m->RDAUG = next();
+  m->D4 = next(); m->RD4 = next();
+  m->SG[0] = next(); m->SG[1] = next(); m->RSG[0] = next(); m->RSG[1] = next();
+  m->grad_doubles = m->IN - m->gW4;  // grad | rgrad blocks are adjacent
+  *out = m;
+  return AF_OK;
+}
+
+int af_lstm_destroy(af_lstm* m) {
+  if (!m) return AF_OK;
+  DeviceGuard guard(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  cudaFree(m->slab);
+  delete m;
+  return AF_OK;
+}
+
+static int lstm_idx_ok(af_lstm* m, int idx, int64_t len) {
+  if (!m) return fail(AF_EINVAL, "null lstm");
+  if (idx < 0 || idx >= 10) return fail(AF_EINVAL, "parameter index out of range (0..9)");
+  if (len != m->param_len(idx))
+    return fail(AF_ESHAPE, "parameter length should be " + std::to_string(m->param_len(idx)) + " but got " + std::to_string(len));
+  return AF_OK;
+}
+
+int af_lstm_set_param(af_lstm* m, int idx, const double* h, int64_t len) {
+  AF_TRY(lstm_idx_ok(m, idx, len));
+  if (!h) return fail(AF_EINVAL, "null host pointer");
+  return af_upload(m->ctx, m->block(idx, m->W4, m->b4, m->Wout, m->bout), h, len);
+}
+
+// NULL h_value marks the variable as absent from the RVector (zero R, variable.go:85-91).  The four
+// gate matrices share one stacked R buffer, so an absent gate block is zero-filled rather than skipped.
+int af_lstm_set_rvector(af_lstm* m, int idx, const double* h, int64_t len) {
+  if (!m) return fail(AF_EINVAL, "null lstm");
+  if (idx < 0 || idx >= 10) return fail(AF_EINVAL, "parameter index out of range (0..9)");
+  double* dst = m->block(idx, m->RW4, m->Rb4, m->RWout, m->Rbout);
+  if (!h) {
+    m->has_r[idx] = false;
+    return af_zero(m->ctx, dst, m->param_len(idx));
+  }
+  AF_TRY(lstm_idx_ok(m, idx, len));
+  m->has_r[idx] = true;
+  return af_upload(m->ctx, dst, h, len);
+}
+
+double* af_lstm_param_ptr(af_lstm* m, int idx) { return (m && idx >= 0 && idx < 10) ? m->block(idx, m->W4, m->b4, m->Wout, m->bout) : nullptr; }
+double* af_lstm_grad_ptr(af_lstm* m, int idx) { return (m && idx >= 0 && idx < 10) ? m->block(idx, m->gW4, m->gb4, m->gWout, m->gbout) : nullptr; }
+double* af_lstm_rgrad_ptr(af_lstm* m, int idx) { return (m && idx >= 0 && idx < 10) ? m->block(idx, m->rgW4, m->rgb4, m->rgWout, m->rgbout) : nullptr; }
+double* af_lstm_output_ptr(af_lstm* m) { return m ? m->RES : nullptr; }
+double* af_lstm_routput_ptr(af_lstm* m) { return m ? m->RRES : nullptr; }
+double* af_lstm_upstream_ptr(af_lstm* m) { return m ? m->UP : nullptr; }
+double* af_lstm_upstream_r_ptr(af_lstm* m) { return m ? m->RUP : nullptr; }
+int64_t af_lstm_grad_slab(af_lstm* m, double** d_first) {
+  if (!m) return 0;
+  if (d_first) *d_first = m->gW4;
+  return m->grad_doubles;
+}
+
+int af_lstm_zero_grads(af_lstm* m) {
+  if (!m) return fail(AF_EINVAL, "null lstm");
+  DeviceGuard guard(m->ctx->device);
+  AF_CUDA(cudaMemsetAsync(m->gW4, 0, (size_t)m->grad_doubles * 8, m->ctx->stream));
+  return AF_OK;
+}
+
+// inputs: T x B x I (time-major, lane-major within a step: the packing seqfunc.MapBatcher produces,
+// seqfunc/map.go:262-270).  Device pointer.
+int af_lstm_set_inputs(af_lstm* m, const double* d_x) {
+  if (!m || !d_x) return fail(AF_EINVAL, "null argument");
+  af_ctx* ctx = m->ctx;
+  const int64_t TB = m->T * m->B;
+  // x_t is the tail of both concatenations: concat(state, x) and concat(masked, x) (lstm.go:140,193)
+  AF_TRY(af_copy_2d(ctx, m->IN + m->H, m->C, d_x, m->I, TB, m->I));
+  return af_copy_2d(ctx, m->AUG + m->H, m->C, d_x, m->I, TB, m->I);
+}
+
+int af_lstm_forward(af_lstm* m, int with_r) {
+  if (!m) return fail(AF_EINVAL, "null lstm");
+  af_ctx* ctx = m->ctx;
+  DeviceGuard guard(ctx->device);
+  const int64_t H = m->H, C = m->C, B = m->B, T = m->T, O = m->O;
+  const bool R = with_r != 0;
+  const int64_t BC = B * C;
+  // initial state is zero (lstm.go:175) with zero R
+  AF_CUDA(cudaMemset2DAsync(m->IN, C * 8, 0, H * 8, B, ctx->stream));
+  if (R) AF_CUDA(cudaMemset2DAsync(m->RIN, C * 8, 0, H * 8, B, ctx->stream));
+  for (int64_t t = 0; t < T; ++t) {
+    double* INt = m->IN + t * BC;
+    double* RINt = m->RIN + t * BC;
+    double* Gt = m->G + t * B * 4 * H;
+    double* RGt = m->RG + t * B * 4 * H;
+    // all four gates in one fused contraction (R-state of step 0 is identically zero: skip its product)
+    AF_TRY(af_dense_fwd(ctx, m->W4, R ? m->RW4 : nullptr, m->b4, R ? m->Rb4 : nullptr, INt, (R && t > 0) ? RINt : nullptr, Gt,
+                        R ? RGt : nullptr, 4 * H, C, B, 1));
+    lstm_cell_fwd_kernel<<<ew_grid(ctx, B * H), 256, 0, ctx->stream>>>(
+        Gt, R ? RGt : nullptr, INt, RINt, INt + BC, RINt + BC, m->AUG + t * BC, m->RAUG + t * BC, (int)B, (int)H, (int)C);
+    AF_TRY(after_launch(ctx, "lstm_cell_fwd_kernel", KIND_ELEMENTWISE, (R ? 2.0 : 1.0) * 7 * 8 * B * H));
+  }
+  // output layer for every step at once (lstm.go:193-194)
+  return af_dense_fwd(ctx, m->Wout, R ? m->RWout : nullptr, m->bout, R ? m->Rbout : nullptr, m->AUG, R ? m->RAUG : nullptr,
+                      m->RES, R ? m->RRES : nullptr, O, C, T * B, 1);
+}
+
+int af_lstm_backward(af_lstm* m, int with_r) {
+  if (!m) return fail(AF_EINVAL, "null lstm");
+  af_ctx* ctx = m->ctx;
+  DeviceGuard guard(ctx->device);
+  const int64_t H = m->H, C = m->C, B = m->B, T = m->T, O = m->O;
+  const bool R = with_r != 0;
+  const int64_t TB = T * B, BC = B * C;
+  // output layer backward for all steps: sigmoid', bias and weight gradients, gradient toward [masked | x]
+  if (R) AF_TRY(af_sigmoid_bwd_r(ctx, m->RES, m->RRES, m->UP, m->RUP, TB * O));
+  else AF_TRY(af_sigmoid_bwd(ctx, m->RES, m->UP, TB * O));
+  AF_TRY(colsum_launch(ctx, m->UP, R ? m->RUP : nullptr, m->gbout, R ? m->rgbout : nullptr, O, TB));
+  AF_TRY(af_lintran_wgrad_r(ctx, m->UP, R ? m->RUP : nullptr, m->AUG, R ? m->RAUG : nullptr, m->gWout, R ? m->rgWout : nullptr, O, C, TB));
+  AF_TRY(af_dense_igrad(ctx, m->UP, R ? m->RUP : nullptr, m->Wout, R ? m->RWout : nullptr, nullptr, nullptr, m->DAUG,
+                        R ? m->RDAUG : nullptr, O, C, TB));
+  AF_CUDA(cudaMemsetAsync(m->SG[0], 0, (size_t)(B * H) * 8, ctx->stream));
+  if (R) AF_CUDA(cudaMemsetAsync(m->RSG[0], 0, (size_t)(B * H) * 8, ctx->stream));
+  int cur = 0;
+  for (int64_t t = T - 1; t >= 0; --t) {
+    double* D4t = m->D4 + t * B * 4 * H;
+    double* RD4t = m->RD4 + t * B * 4 * H;
+    lstm_cell_bwd_kernel<<<ew_grid(ctx, B * H), 256, 0, ctx->stream>>>(
+        m->G + t * B * 4 * H, R ? m->RG + t * B * 4 * H : nullptr, m->IN + t * BC, m->RIN + t * BC, m->IN + (t + 1) * BC,
+        m->RIN + (t + 1) * BC, m->DAUG + t * BC, m->RDAUG + t * BC, m->SG[cur], m->RSG[cur], m->SG[cur ^ 1], m->RSG[cur ^ 1], D4t,
+        RD4t, (int)B, (int)H, (int)C);
+    AF_TRY(after_launch(ctx, "lstm_cell_bwd_kernel", KIND_ELEMENTWISE, (R ? 2.0 : 1.0) * 13 * 8 * B * H));
+    if (t > 0) {
+      // stateGrad += delta4 W4[:, :H]  (the four gates' inputGradient, lin_tran.go:272-359, restricted to the
+      // state columns: the x columns go to a Variable that is not in the gradient maps)
+      GemmOperand A{D4t, R ? RD4t : nullptr, LAY_KC, 4 * H};
+      GemmOperand Bop{m->W4, R ? m->RW4 : nullptr, LAY_RC, C};
+      GemmEpilogue e;
+      e.epi = EPI_ACCUM; e.out0 = m->SG[cur ^ 1]; e.out1 = R ? m->RSG[cur ^ 1] : nullptr; e.ldo = H;
+      AF_TRY(gemm_launch(ctx, A, Bop, R, B, H, 4 * H, e));
+    }
+    cur ^= 1;
+  }
+  // gate weight / bias gradients over all T*B rows at once (lstm.go's per-step dataGradient calls add up)
+  AF_TRY(colsum_launch(ctx, m->D4, R ? m->RD4 : nullptr, m->gb4, R ? m->rgb4 : nullptr, 4 * H, TB));
+  return af_lintran_wgrad_r(ctx, m->D4, R ? m->RD4 : nullptr, m->IN, R ? m->RIN : nullptr, m->gW4, R ? m->rgW4 : nullptr, 4 * H, C, TB);
+}
+
+// Host-buffer form of one bench iteration (bench/lstm.go:41-48): upload inputs (T x B x I) and the
+// per-step output gradients (T x B x O; h_upstreams_r may be NULL = zeros), zero the accumulators,
+// forward, BPTT, download outputs and every gradient (10 host pointers each, reference order).
+int af_lstm_run_host(af_lstm* m, int with_r, const double* h_x, const double* h_up, const double* h_upr, double* h_out,
+                     double* h_rout, double* const* h_grads, double* const* h_rgrads) {
+  if (!m || !h_x || !h_up) return fail(AF_EINVAL, "null argument");
+  af_ctx* ctx = m->ctx;
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const int64_t TB = m->T * m->B;
+  // stage x through D4 (free until the backward pass) so it can be scattered into IN / AUG
+  AF_CUDA(cudaMemcpyAsync(m->D4, h_x, (size_t)(TB * m->I) * 8, cudaMemcpyHostToDevice, st));
+  AF_TRY(af_lstm_set_inputs(m, m->D4));
+  AF_CUDA(cudaMemcpyAsync(m->UP, h_up, (size_t)(TB * m->O) * 8, cudaMemcpyHostToDevice, st));
+  if (with_r) {
+    if (h_upr) AF_CUDA(cudaMemcpyAsync(m->RUP, h_upr, (size_t)(TB * m->O) * 8, cudaMemcpyHostToDevice, st));
+    else AF_CUDA(cudaMemsetAsync(m->RUP, 0, (size_t)(TB * m->O) * 8, st));
+  }
+  AF_TRY(af_lstm_zero_grads(m));
+  AF_TRY(af_lstm_forward(m, with_r));
+  if (h_out) AF_CUDA(cudaMemcpyAsync(h_out, m->RES, (size_t)(TB * m->O) * 8, cudaMemcpyDeviceToHost, st));
+  if (h_rout && with_r) AF_CUDA(cudaMemcpyAsync(h_rout, m->RRES, (size_t)(TB * m->O) * 8, cudaMemcpyDeviceToHost, st));
+  AF_TRY(af_lstm_backward(m, with_r));
+  for (int i = 0; i < 10; ++i) {
+    if (h_grads && h_grads[i])
+      AF_CUDA(cudaMemcpyAsync(h_grads[i], af_lstm_grad_ptr(m, i), (size_t)m->param_len(i) * 8, cudaMemcpyDeviceToHost, st));
+    if (with_r && h_rgrads && h_rgrads[i])
+      AF_CUDA(cudaMemcpyAsync(h_rgrads[i], af_lstm_rgrad_ptr(m, i), (size_t)m->param_len(i) * 8, cudaMemcpyDeviceToHost, st));
+  }
+  AF_CUDA(cudaStreamSynchronize(st));
+  return AF_OK;
+}
+
+}  // extern "C"

@@ -200,6 +200,40 @@ int af_mlp_step_host(af_mlp*, int with_r, const double* h_X, const double* h_ups
                      const double* h_upstream_r, double* h_out, double* h_rout,
                      double* const* h_grads, double* const* h_rgrads);
 
+/* dst[r*ld_dst + c] = src[r*ld_src + c]: the copy behind Concat / Slice of packed batches
+ * (slices.go:13-119,130-206) when the parts are interleaved per sample.                          */
+int af_copy_2d(af_ctx*, double* d_dst, int64_t ld_dst, const double* d_src, int64_t ld_src, int64_t rows, int64_t cols);
+
+/* ---- LSTM fast path: bench/lstm.go:25-241, batched over B lanes, R-operator carried through ---- */
+/* Parameter index 0..9 in reference order (bench/lstm.go:75-99, 200-213): InWeights, InBiases,
+ * InGateWeights, InGateBiases, ForgetGateWeights, ForgetGateBiases, OutputGate, OutputGateBiases,
+ * OutputWeights, OutputBiases.  Gate matrices are H x (H+I) over concat(state, x) (lstm.go:140);
+ * OutputWeights is O x (H+I) over concat(masked, x) (lstm.go:193).  Sequences are time-major and
+ * lane-major within a step: T x B x I inputs, T x B x O outputs / upstreams (the packing
+ * seqfunc.MapBatcher produces, seqfunc/map.go:262-284).                                           */
+typedef struct af_lstm af_lstm;
+int af_lstm_create(af_ctx*, int64_t input_size, int64_t hidden_size, int64_t output_size, int64_t time_steps,
+                   int64_t lanes, af_lstm** out);
+int af_lstm_destroy(af_lstm*);
+int af_lstm_set_param(af_lstm*, int index, const double* h_value, int64_t len);
+int af_lstm_set_rvector(af_lstm*, int index, const double* h_value, int64_t len); /* NULL => absent (zero R) */
+double* af_lstm_param_ptr(af_lstm*, int index);
+double* af_lstm_grad_ptr(af_lstm*, int index);
+double* af_lstm_rgrad_ptr(af_lstm*, int index);
+double* af_lstm_output_ptr(af_lstm*);
+double* af_lstm_routput_ptr(af_lstm*);
+double* af_lstm_upstream_ptr(af_lstm*);
+double* af_lstm_upstream_r_ptr(af_lstm*);
+/* The contiguous {grad | rgrad} block (for one data-parallel all-reduce): returns its length in doubles. */
+int64_t af_lstm_grad_slab(af_lstm*, double** d_first);
+int af_lstm_zero_grads(af_lstm*);
+int af_lstm_set_inputs(af_lstm*, const double* d_x);          /* device T x B x I */
+int af_lstm_forward(af_lstm*, int with_r);                   /* Reset + T x StepTime (lstm.go:42-45) */
+int af_lstm_backward(af_lstm*, int with_r);                  /* PropagateGradient (lstm.go:215-234); consumes upstreams */
+int af_lstm_run_host(af_lstm*, int with_r, const double* h_inputs, const double* h_upstreams,
+                     const double* h_upstreams_r, double* h_outputs, double* h_routputs,
+                     double* const* h_grads, double* const* h_rgrads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -871,3 +871,98 @@ class MLP:
         grad = new_gradient(self.variables)
         res.propagate_gradient(u, grad)
         return res, grad
+
+
+# --------------------------------------------------------------------------------------
+# bench/lstm.go: lstmBlock + lstmNet, one lane at a time exactly as the reference runs it
+# (the reference bench is single-sample; a batch of B lanes is B independent runs whose
+# parameter gradients add -- the same contract seqfunc.MapBatcher gives, map_batcher.go:26-34)
+# --------------------------------------------------------------------------------------
+class LSTMNet:
+    """bench/lstm.go:73-241.  Parameters in the order
+    [InWeights, InBiases, InGateWeights, InGateBiases, ForgetGateWeights, ForgetGateBiases,
+     OutputGate, OutputGateBiases, OutputWeights, OutputBiases]."""
+
+    def __init__(self, input_size, hidden, output_size, seed=123, rseed=125, weight_scale=1.0):
+        self.I, self.H, self.O = input_size, hidden, output_size
+        cols = input_size + hidden
+        self.variables = []
+        for k in range(5):  # bench/lstm.go:102-127 generateLayer: U[-1,1) weights and biases
+            rows = hidden if k < 4 else output_size
+            self.variables.append(Variable(splitmix_uniform(seed + 1000 * k, rows * cols) * weight_scale))
+            self.variables.append(Variable(splitmix_uniform(seed + 1000 * k + 1, rows)))
+        v = self.variables
+        self.lin = [LinTran(v[2 * k], hidden if k < 4 else output_size, cols) for k in range(5)]
+        self.bias = [LinAdd(v[2 * k + 1]) for k in range(5)]
+        self.rvec = {p: splitmix_uniform(rseed + 1000 * j, len(p.vector)) for j, p in enumerate(self.variables)}
+
+    # -- non-R: bench/lstm.go:139-198, 215-234 ---------------------------------------------
+    def run(self, inputs, upstreams):
+        """inputs: list of T vectors (I); upstreams: list of T vectors (O).  Returns (outputs, grad)."""
+        s = Sigmoid()
+        in_states, out_states, out_state_vars, outputs = [], [], [], []
+        for x in inputs:
+            in_state = Variable(out_states[-1].output() if out_states else np.zeros(self.H))
+            xv = Variable(x)
+            inp = concat(in_state, xv)                                      # lstm.go:140
+            new = s.apply(self.bias[0].apply(self.lin[0].apply(inp)))       # inState   :143
+            mask = s.apply(self.bias[1].apply(self.lin[1].apply(inp)))      # inMask    :144
+            forget = s.apply(self.bias[2].apply(self.lin[2].apply(inp)))    # forgetMask:145
+            out_state = add(mul(forget, in_state), mul(mask, new))          # :147-150
+            osv = Variable(out_state.output())                              # :183
+            gate = s.apply(self.bias[3].apply(self.lin[3].apply(concat(in_state, xv))))   # :187-189
+            masked = mul(osv, gate)                                         # :191
+            res = s.apply(self.bias[4].apply(self.lin[4].apply(concat(masked, xv))))      # :193-194
+            in_states.append(in_state); out_states.append(out_state); out_state_vars.append(osv); outputs.append(res)
+        grad = new_gradient(self.variables)
+        state_grad = np.zeros(self.H)
+        for t in range(len(inputs) - 1, -1, -1):                            # :215-234
+            grad[out_state_vars[t]] = np.zeros(self.H)
+            grad[in_states[t]] = np.zeros(self.H)
+            outputs[t].propagate_gradient(vec(upstreams[t]).copy(), grad)
+            state_grad = state_grad + grad.pop(out_state_vars[t])
+            out_states[t].propagate_gradient(state_grad, grad)
+            state_grad = grad.pop(in_states[t])
+        return [o.output() for o in outputs], grad
+
+    # -- R: the same network through ConcatR/MulR/AddR/ApplyR, state R-derivative carried the way
+    #    seqfunc.MapRBatcher carries it (RVariable{value, R-value}, seqfunc/map_batcher.go:85-91) ----
+    def run_r(self, inputs, upstreams, upstreams_r=None):
+        s = Sigmoid()
+        rv = self.rvec
+
+        def rvar(v, r):
+            out = RVariable(v, {})
+            out.routput_vec = r
+            return out
+        in_states, out_states, out_state_vars, outputs = [], [], [], []
+        for x in inputs:
+            if out_states:
+                in_state = rvar(Variable(out_states[-1].output()), out_states[-1].routput())
+            else:
+                in_state = rvar(Variable(np.zeros(self.H)), np.zeros(self.H))
+            xv = RVariable(Variable(x), rv)                                  # input not in rv: zero R
+            inp = concat_r(in_state, xv)
+            new = s.apply_r(rv, self.bias[0].apply_r(rv, self.lin[0].apply_r(rv, inp)))
+            mask = s.apply_r(rv, self.bias[1].apply_r(rv, self.lin[1].apply_r(rv, inp)))
+            forget = s.apply_r(rv, self.bias[2].apply_r(rv, self.lin[2].apply_r(rv, inp)))
+            out_state = add_r(mul_r(forget, in_state), mul_r(mask, new))
+            osv = rvar(Variable(out_state.output()), out_state.routput())
+            gate = s.apply_r(rv, self.bias[3].apply_r(rv, self.lin[3].apply_r(rv, concat_r(in_state, xv))))
+            masked = mul_r(osv, gate)
+            res = s.apply_r(rv, self.bias[4].apply_r(rv, self.lin[4].apply_r(rv, concat_r(masked, xv))))
+            in_states.append(in_state); out_states.append(out_state); out_state_vars.append(osv); outputs.append(res)
+        grad, rgrad = new_gradient(self.variables), new_rgradient(self.variables)
+        sg, sgr = np.zeros(self.H), np.zeros(self.H)
+        T = len(inputs)
+        for t in range(T - 1, -1, -1):
+            for m in (grad, rgrad):
+                m[out_state_vars[t].variable] = np.zeros(self.H)
+                m[in_states[t].variable] = np.zeros(self.H)
+            ur = np.zeros(self.O) if upstreams_r is None else vec(upstreams_r[t]).copy()
+            outputs[t].propagate_rgradient(vec(upstreams[t]).copy(), ur, rgrad, grad)
+            sg = sg + grad.pop(out_state_vars[t].variable)
+            sgr = sgr + rgrad.pop(out_state_vars[t].variable)
+            out_states[t].propagate_rgradient(sg, sgr, rgrad, grad)
+            sg, sgr = grad.pop(in_states[t].variable), rgrad.pop(in_states[t].variable)
+        return [o.output() for o in outputs], [o.routput() for o in outputs], grad, rgrad
