@@ -158,7 +158,7 @@ int af_trace_end(af_ctx* ctx, int capacity, int* h_kind, double* h_work, float* 
 int af_set_option(af_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return fail(AF_EINVAL, "null argument");
   if (!strcmp(name, "big_cfg")) {
-    if (value != 0 && value != 2 && value != 3) return fail(AF_EINVAL, "big_cfg must be 0 (128x64, 8 warps), 2 (64x64, 2 CTAs/SM) or 3 (128x64, 16 warps)");
+    if (value != 0 && value != 2) return fail(AF_EINVAL, "big_cfg must be 0 (128x64, 8 warps, 1 CTA/SM) or 2 (64x64, 4 warps, 2 CTAs/SM)");
     ctx->big_cfg = value;
     return AF_OK;
   }

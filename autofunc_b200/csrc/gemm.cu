@@ -93,6 +93,22 @@ int launch_generic(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool
 
 }  // namespace
 
+// Deferred epilogue: applies the fused elementwise step (bias / sigmoid / sigmoid backward) in place on
+// outputs that were accumulated with split-K atomics.  Only small problems (few output tiles) take it.
+template <bool DUAL>
+__global__ void __launch_bounds__(256) gemm_epilogue_kernel(const GemmArgs p) {
+  const long long n = (long long)p.I * p.J;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
+    const long long i = e / p.J;
+    const int j = (int)(e - i * p.J);
+    const long long o = i * p.ldo + j;
+    double v0 = p.out0 ? p.out0[o] : 0.0, v1 = (DUAL && p.out1) ? p.out1[o] : 0.0;
+    epi_transform<DUAL>(p, i, j, v0, v1);
+    if (p.out0) p.out0[o] = v0;
+    if (DUAL && p.out1) p.out1[o] = v1;
+  }
+}
+
 int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, bool dual, long long I, long long J,
                 long long Kd, const GemmEpilogue& e) {
   if (I <= 0 || J <= 0) return AF_OK;
@@ -100,21 +116,14 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   GemmOperand A = A_in, B = B_in;
   GemmArgs args{};
   args.epi = e.epi;
-  const bool accumulate = e.epi == EPI_ACCUM;
-  // A weight gradient with very few rows (the 10-wide output layer): compute the transposed product so
-  // the short extent lands on the 16-wide J tile instead of wasting 118 of 128 I rows.  acc1 is symmetric
-  // under (A0,A1) <-> (B0,B1).
-  if (accumulate && I <= 16 && J > 16 && A.layout == LAY_RC && B.layout == LAY_RC) {
-    std::swap(A, B);
-    std::swap(I, J);
-    args.transpose_out = 1;
-  }
   args.I = (int)I; args.J = (int)J; args.Kd = (int)Kd;
   args.has_a1 = dual && A.p1 != nullptr;
   args.has_b1 = dual && B.p1 != nullptr;
   args.out0 = e.out0; args.out1 = dual ? e.out1 : nullptr; args.ldo = e.ldo;
   args.bias0 = e.bias0; args.bias1 = e.bias1;
   args.s = e.s; args.rs = e.rs; args.lds = e.lds;
+  const GemmArgs logical = args;  // un-swapped view, used by the generic kernel and the deferred epilogue
+  const bool accumulate = e.epi == EPI_ACCUM;
   const int kt_total = (int)((Kd + kBK - 1) / kBK);
   args.k_tiles_per_split = kt_total > 0 ? kt_total : 1;
 
@@ -132,41 +141,88 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
     return fail(AF_EINVAL, "unsupported operand layout combination");
   }
 
+  // Very few rows (n <= 16 samples; the 10-row weight gradient of the output layer): compute the
+  // transposed product so the short extent lands on the 16-wide J tile of the narrow configuration and
+  // the long operand (the weight matrix) is streamed exactly once.  acc1 is symmetric under
+  // (A0,A1) <-> (B0,B1).
+  const bool contiguous_out = (e.ldo == J);
+  bool swapped = false;
+  if (I <= 16 && J > 16 && (accumulate || contiguous_out)) {
+    std::swap(A, B);
+    std::swap(I, J);
+    std::swap(args.has_a1, args.has_b1);
+    args.I = (int)I; args.J = (int)J;
+    args.transpose_out = 1;
+    swapped = true;
+  }
   const int cfg = J <= 16 ? 1 : ctx->big_cfg;
-  const int bm = cfg == 1 ? GemmSmem<2, 1>::kBMc : cfg == 2 ? GemmSmem<2, 2>::kBMc : GemmSmem<2, 0>::kBMc;  // cfg 3 == cfg 0 shape
+  const int bm = cfg == 1 ? GemmSmem<2, 1>::kBMc : cfg == 2 ? GemmSmem<2, 2>::kBMc : GemmSmem<2, 0>::kBMc;
   const int bn = cfg == 1 ? GemmSmem<2, 1>::kBNc : cfg == 2 ? GemmSmem<2, 2>::kBNc : GemmSmem<2, 0>::kBNc;
+  dim3 grid((unsigned)((J + bn - 1) / bn), (unsigned)((I + bm - 1) / bm), 1);
+  const long long tiles = (long long)grid.x * grid.y;
+  const int slots = ctx->sm_count * (cfg == 2 ? 2 : 1);
+
+  // Split the contraction when the output has too few tiles to occupy the chip.  Accumulating outputs
+  // (weight gradients) combine partial tiles with red.global.add.f64 directly; storing outputs are zeroed,
+  // accumulated the same way, and get their fused elementwise step from gemm_epilogue_kernel afterwards.
+  bool deferred = false;
+  int splits = 1;
+  if (accumulate) {
+    splits = choose_splits(tiles, kt_total, slots);
+  } else if (contiguous_out && (swapped || (2 * tiles <= slots && kt_total >= 16))) {
+    splits = choose_splits(tiles, kt_total, slots);
+    deferred = swapped || splits > 1;
+  }
+  if (deferred) {
+    const size_t bytes = (size_t)logical.I * logical.J * 8;
+    if (args.out0) AF_CUDA(cudaMemsetAsync(args.out0, 0, bytes, ctx->stream));
+    if (args.out1) AF_CUDA(cudaMemsetAsync(args.out1, 0, bytes, ctx->stream));
+    args.epi = EPI_ACCUM_ATOMIC;
+  }
+  if (splits > 1) {
+    args.k_tiles_per_split = (kt_total + splits - 1) / splits;
+    splits = (kt_total + args.k_tiles_per_split - 1) / args.k_tiles_per_split;
+    grid.z = (unsigned)splits;
+    args.epi = EPI_ACCUM_ATOMIC;  // partial tiles combine with red.global.add.f64
+  }
+
   CUtensorMap maps[4];
   AF_TRY(make_map(ctx, &maps[0], A.p0, A.layout, I, Kd, A.ld, bm));
   AF_TRY(make_map(ctx, &maps[2], B.p0, B.layout, J, Kd, B.ld, bn));
   if (args.has_a1) AF_TRY(make_map(ctx, &maps[1], A.p1, A.layout, I, Kd, A.ld, bm)); else maps[1] = maps[0];
   if (args.has_b1) AF_TRY(make_map(ctx, &maps[3], B.p1, B.layout, J, Kd, B.ld, bn)); else maps[3] = maps[2];
 
-  dim3 grid((unsigned)((J + bn - 1) / bn), (unsigned)((I + bm - 1) / bm), 1);
-  if (accumulate) {
-    int splits = choose_splits((long long)grid.x * grid.y, kt_total, ctx->sm_count * (cfg == 2 ? 2 : 1));
-    if (splits > 1) {
-      args.k_tiles_per_split = (kt_total + splits - 1) / splits;
-      splits = (kt_total + args.k_tiles_per_split - 1) / args.k_tiles_per_split;
-      grid.z = (unsigned)splits;
-      args.epi = EPI_ACCUM_ATOMIC;  // partial tiles combine with red.global.add.f64
-    }
-  }
   const int nacc = dual ? 2 : 1;
+  int rc = AF_EINVAL;
+  bool dispatched = false;
 #define AF_DISPATCH(AL, BL)                                                                        \
-  if (A.layout == AL && B.layout == BL) {                                                          \
+  if (!dispatched && A.layout == AL && B.layout == BL) {                                           \
+    dispatched = true;                                                                             \
     if (cfg == 0)                                                                                  \
-      return nacc == 2 ? launch_dmma<AL, BL, 2, 0>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 0>(ctx, maps, args, grid); \
-    if (cfg == 2)                                                                                  \
-      return nacc == 2 ? launch_dmma<AL, BL, 2, 2>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 2>(ctx, maps, args, grid); \
-    if (cfg == 3)                                                                                  \
-      return nacc == 2 ? launch_dmma<AL, BL, 2, 3>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 3>(ctx, maps, args, grid); \
-    return nacc == 2 ? launch_dmma<AL, BL, 2, 1>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 1>(ctx, maps, args, grid);   \
+      rc = nacc == 2 ? launch_dmma<AL, BL, 2, 0>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 0>(ctx, maps, args, grid); \
+    else if (cfg == 2)                                                                             \
+      rc = nacc == 2 ? launch_dmma<AL, BL, 2, 2>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 2>(ctx, maps, args, grid); \
+    else                                                                                           \
+      rc = nacc == 2 ? launch_dmma<AL, BL, 2, 1>(ctx, maps, args, grid) : launch_dmma<AL, BL, 1, 1>(ctx, maps, args, grid); \
   }
   AF_DISPATCH(LAY_KC, LAY_KC)
   AF_DISPATCH(LAY_KC, LAY_RC)
   AF_DISPATCH(LAY_RC, LAY_RC)
 #undef AF_DISPATCH
-  return fail(AF_EINVAL, "unsupported operand layout combination");
+  if (!dispatched && A.layout == LAY_RC && B.layout == LAY_KC && cfg == 1) {  // swapped input-gradient, narrow only
+    dispatched = true;
+    rc = nacc == 2 ? launch_dmma<LAY_RC, LAY_KC, 2, 1>(ctx, maps, args, grid) : launch_dmma<LAY_RC, LAY_KC, 1, 1>(ctx, maps, args, grid);
+  }
+  if (!dispatched) return fail(AF_EINVAL, "unsupported operand layout combination");
+  AF_TRY(rc);
+  if (deferred && logical.epi != EPI_STORE) {
+    long long blocks = ((long long)logical.I * logical.J + 255) / 256;
+    if (blocks > 8ll * ctx->sm_count) blocks = 8ll * ctx->sm_count;
+    if (dual) gemm_epilogue_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(logical);
+    else gemm_epilogue_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(logical);
+    return after_launch(ctx, "gemm_epilogue_kernel", KIND_ELEMENTWISE, 16.0 * (dual ? 2 : 1) * logical.I * logical.J);
+  }
+  return AF_OK;
 }
 
 }  // namespace af

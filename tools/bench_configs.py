@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Timing of the BASELINE.json configs other than the headline one (which bench.py owns):
+  C1  bench/lintran.go  LinTran 1024x2048, n=10, fwd + Gradient + RGradient
+  C2' bench/mlp.go      MLP 1000-2000-512-10 at n=1 (reference-exact) and n=64/1024
+  C3  Hessian-vector step on a 4 x (2048->2048) MLP, n=4096
+  C4  bench/lstm.go     LSTM H=512, T=128, B=256 (I=30, O=10), forward + BPTT + R
+  C5  one rank's share of 4 x (8192->8192), n=8192 (the 8-GPU shard of n=65536)
+Inputs resident, CUDA events, 3 warm-ups.  One JSON line per config on stdout."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+from autofunc_b200 import api, synth
+from autofunc_b200.lstm import LSTMPlan
+
+
+def timed(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def mlp_config(ctx, name, sizes, n, steps, flops):
+    plan = api.MLPPlan(sizes, n, ctx)
+    params, rvecs = synth.mlp_params(sizes, weight_scale=lambda k: 1 / np.sqrt(k))
+    for i, (p, r) in enumerate(zip(params, rvecs)):
+        plan.set_param(i, p)
+        plan.set_rvector(i, r)
+    x = synth.mlp_input(sizes, n)
+    ctx.lib.af_upload(ctx.h, plan.input().ptr, x.ctypes.data, x.size)
+    n_out = n * sizes[-1]
+    up, upr = plan.upstream(), plan.upstream_r()
+
+    def step():
+        plan.zero_grads()
+        api.check(ctx.lib.af_fill(ctx.h, up.ptr, 1.0, n_out))
+        api.check(ctx.lib.af_zero(ctx.h, upr.ptr, n_out))
+        plan.step(True, True)
+    ms = timed(step, steps)
+    plan.close()
+    print(json.dumps({"config": name, "sizes": sizes, "n": n, "ms_per_step": ms, "samples_per_s": n / ms * 1e3,
+                      "tflops_executed": flops / ms / 1e9}), flush=True)
+
+
+def executed_flops(sizes, n):
+    f = 0
+    for l in range(len(sizes) - 1):
+        f += (8 if l == 0 else 18) * sizes[l] * sizes[l + 1]  # layer 1: zero-RX products are skipped
+    return f * n
+
+
+def lintran_config(ctx, steps):
+    rows, cols, n = 1024, 2048, 10
+    W, RW = synth.uniform(1, rows * cols), synth.uniform(2, rows * cols)
+    X, RX = synth.uniform(3, n * cols), synth.uniform(4, n * cols)
+    U, UR = synth.uniform(5, n * rows), synth.uniform(6, n * rows)
+    d = {k: ctx.upload(v) for k, v in dict(W=W, RW=RW, X=X, RX=RX, U=U, UR=UR).items()}
+    Y, RY, D, DR = ctx.empty(n * rows), ctx.empty(n * rows), ctx.empty(n * cols), ctx.empty(n * cols)
+    gW, rgW, gX, rgX = ctx.zeros(rows * cols), ctx.zeros(rows * cols), ctx.zeros(n * cols), ctx.zeros(n * cols)
+    L, h = ctx.lib, ctx.h
+
+    def step():  # bench/lintran.go:83-89: BatchR + PropagateRGradient with W and X both in the maps
+        api.check(L.af_lintran_fwd_r(h, d["W"].ptr, d["RW"].ptr, d["X"].ptr, d["RX"].ptr, Y.ptr, RY.ptr, rows, cols, n))
+        api.check(L.af_lintran_wgrad_r(h, d["U"].ptr, d["UR"].ptr, d["X"].ptr, d["RX"].ptr, gW.ptr, rgW.ptr, rows, cols, n))
+        api.check(L.af_lintran_igrad_r(h, d["U"].ptr, d["UR"].ptr, d["W"].ptr, d["RW"].ptr, D.ptr, DR.ptr, rows, cols, n))
+        api.check(L.af_axpy(h, 1.0, D.ptr, gX.ptr, n * cols))
+        api.check(L.af_axpy(h, 1.0, DR.ptr, rgX.ptr, n * cols))
+    ms = timed(step, steps)
+    algo_bytes = 8 * 8 * rows * cols  # W, RW read twice + gW, rgW read-modify-write
+    print(json.dumps({"config": "C1 lintran 1024x2048 n=10 fwd+Grad+RGrad", "ms_per_step": ms, "us_per_step": ms * 1e3,
+                      "algorithmic_GBps": algo_bytes / ms / 1e6, "samples_per_s": n / ms * 1e3}), flush=True)
+
+
+def lstm_config(ctx, I, H, O, T, B, steps):
+    plan = LSTMPlan(I, H, O, T, B, ctx)
+    for i in range(10):
+        plan.set_param(i, synth.uniform(900 + i, plan.param_len(i)) * (0.05 if i % 2 == 0 else 1.0))
+        plan.set_rvector(i, synth.uniform(950 + i, plan.param_len(i)))
+    x = ctx.upload(synth.uniform(11, T * B * I, 0, 1))
+    upv = ctx.upload(synth.uniform(12, T * B * O, 0, 1))
+    plan.set_inputs(x)
+    up, upr = plan.upstream(), plan.upstream_r()
+
+    def step():
+        plan.zero_grads()
+        api.check(ctx.lib.af_copy(ctx.h, up.ptr, upv.ptr, up.n))
+        api.check(ctx.lib.af_zero(ctx.h, upr.ptr, upr.n))
+        plan.forward(True)
+        plan.backward(True)
+    ms = timed(step, steps)
+    flops = 18.0 * (4 * H + O) * (H + I) * T * B
+    plan.close()
+    print(json.dumps({"config": f"C4 lstm I={I} H={H} O={O} T={T} B={B} fwd+BPTT+R", "ms_per_step": ms,
+                      "sequences_per_s": B / ms * 1e3, "tflops_reference_count": flops / ms / 1e9}), flush=True)
+
+
+def main():
+    which = set(sys.argv[1:]) or {"c1", "c2", "c3", "c4"}
+    ctx = api.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    api.set_context(ctx)
+    if "c1" in which:
+        lintran_config(ctx, 50)
+    if "c2" in which:
+        for n in (1, 64, 1024):
+            mlp_config(ctx, f"C2 mlp n={n}", [1000, 2000, 512, 10], n, 20, executed_flops([1000, 2000, 512, 10], n))
+    if "c3" in which:
+        s = [2048] * 5
+        mlp_config(ctx, "C3 hessian-vector 4x(2048->2048) n=4096", s, 4096, 5, executed_flops(s, 4096))
+    if "c4" in which:
+        lstm_config(ctx, 30, 512, 10, 128, 256, 3)
+    if "c5" in which:
+        s = [8192] * 5
+        mlp_config(ctx, "C5 shard 4x(8192->8192) n=8192 (1/8 of n=65536)", s, 8192, 2, executed_flops(s, 8192))
+
+
+if __name__ == "__main__":
+    main()
