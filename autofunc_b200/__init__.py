@@ -6,3 +6,7 @@
 from . import _lib  # noqa: F401
 from .api import *  # noqa: F401,F403
 from .api import Context, DeviceVec, MLPPlan, context, set_context  # noqa: F401
+from .slices import concat, concat_r, slice_, slice_r, repeat, repeat_r, concat_batched, concat_batched_r  # noqa: F401,E402
+from . import api as _api  # noqa: E402
+for _n in ("concat", "concat_r", "slice_", "slice_r", "repeat", "repeat_r", "concat_batched", "concat_batched_r"):
+    setattr(_api, _n, globals()[_n])  # the operator namespace tests and callers use is `api`
