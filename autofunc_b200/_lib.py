@@ -85,6 +85,8 @@ PROTOTYPES = {
     "af_mlp_zero_grads": (INT, [P]),
     "af_mlp_step": (INT, [P, INT, INT]),
     "af_mlp_step_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),
+    "af_mlp_submit_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),
+    "af_mlp_wait": (INT, [P]),
     "af_copy_2d": (INT, [P, D, I64, D, I64, I64, I64]),
     "af_lstm_create": (INT, [P, I64, I64, I64, I64, I64, C.POINTER(P)]),
     "af_lstm_destroy": (INT, [P]),

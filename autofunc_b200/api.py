@@ -1109,6 +1109,20 @@ class MLPPlan:
                                             ptr(rout), g_arr, rg_arr))
         return out, rout, grads, rgrads
 
+    def submit_host(self, x, with_r=True, upstream=None, upstream_r=None, out=None, rout=None, grads=None, rgrads=None):
+        """Pipelined step_host: queue the step and return; results are valid after the matching wait().
+        All arrays must stay alive (and should be pinned) until then."""
+        P = 2 * self.L
+        HP = C.c_void_p * P
+        g_arr = HP(*[g.ctypes.data for g in grads]) if grads is not None else None
+        rg_arr = HP(*[g.ctypes.data for g in rgrads]) if rgrads is not None else None
+        ptr = lambda a: None if a is None else a.ctypes.data
+        check(self.ctx.lib.af_mlp_submit_host(self.h, int(with_r), ptr(x), ptr(upstream), ptr(upstream_r), ptr(out),
+                                              ptr(rout), g_arr, rg_arr))
+
+    def wait(self):
+        check(self.ctx.lib.af_mlp_wait(self.h))
+
     def close(self):
         if self.h is not None:
             self.ctx.lib.af_mlp_destroy(self.h)

@@ -361,6 +361,19 @@ struct af_mlp {
     const int l = idx / 2;
     return (idx & 1) ? sizes[l + 1] : sizes[l] * sizes[l + 1];
   }
+  // host-buffer pipeline (af_mlp_submit_host / af_mlp_wait): slot 1 duplicates of the buffers a step
+  // reads from or writes for the host, so step k+1 can compute while step k downloads and k+2 uploads
+  struct Slot {
+    double* x = nullptr;                 // input batch
+    std::vector<double*> grad, rgrad;    // accumulators
+    double *out = nullptr, *rout = nullptr;
+    cudaEvent_t in_ready = nullptr, compute_done = nullptr, out_done = nullptr;
+    bool busy = false;
+  };
+  Slot slot[2];
+  double* alt = nullptr;  // backing store of slot 1
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  int64_t submitted = 0, waited = 0;
 };
 
 extern "C" {
@@ -409,6 +422,12 @@ int af_mlp_destroy(af_mlp* m) {
   if (!m) return AF_OK;
   DeviceGuard guard(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  if (m->copy_in) { cudaStreamSynchronize(m->copy_in); cudaStreamDestroy(m->copy_in); }
+  if (m->copy_out) { cudaStreamSynchronize(m->copy_out); cudaStreamDestroy(m->copy_out); }
+  for (auto& sl : m->slot)
+    for (cudaEvent_t ev : {sl.in_ready, sl.compute_done, sl.out_done})
+      if (ev) cudaEventDestroy(ev);
+  if (m->alt) cudaFree(m->alt);
   cudaFree(m->slab);
   delete m;
   return AF_OK;
@@ -499,12 +518,103 @@ int af_mlp_step(af_mlp* m, int with_r, int backprop) {
   return AF_OK;
 }
 
+// ---- pipelined host-buffer steps ------------------------------------------------------------------
+static int mlp_pipeline_init(af_mlp* m) {
+  if (m->copy_in) return AF_OK;
+  const int L = m->L, P = 2 * L;
+  auto pad = [](int64_t x) { return (x + 31) / 32 * 32; };
+  const int64_t gr_doubles = m->act[0] - m->grad[0];  // grad | rgrad, padded, adjacent
+  const int64_t x_doubles = pad(m->n * m->sizes[0]), o_doubles = pad(m->n * m->sizes[L]);
+  AF_CUDA(cudaMalloc(&m->alt, (size_t)(gr_doubles + x_doubles + 2 * o_doubles) * 8));
+  AF_CUDA(cudaStreamCreateWithFlags(&m->copy_in, cudaStreamNonBlocking));
+  AF_CUDA(cudaStreamCreateWithFlags(&m->copy_out, cudaStreamNonBlocking));
+  m->slot[0].x = m->act[0]; m->slot[0].grad = m->grad; m->slot[0].rgrad = m->rgrad;
+  m->slot[0].out = m->act[L]; m->slot[0].rout = m->ract[L];
+  m->slot[1].grad.resize(P); m->slot[1].rgrad.resize(P);
+  for (int i = 0; i < P; ++i) {
+    m->slot[1].grad[i] = m->alt + (m->grad[i] - m->grad[0]);
+    m->slot[1].rgrad[i] = m->alt + (m->rgrad[i] - m->grad[0]);
+  }
+  m->slot[1].x = m->alt + gr_doubles;
+  m->slot[1].out = m->slot[1].x + x_doubles;
+  m->slot[1].rout = m->slot[1].out + o_doubles;
+  for (auto& sl : m->slot) {
+    AF_CUDA(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
+    AF_CUDA(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+    AF_CUDA(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+  }
+  return AF_OK;
+}
+
+static void mlp_bind_slot(af_mlp* m, int k) {
+  const af_mlp::Slot& sl = m->slot[k];
+  m->act[0] = sl.x; m->grad = sl.grad; m->rgrad = sl.rgrad;
+  m->act[m->L] = sl.out; m->ract[m->L] = sl.rout;
+}
+
+int af_mlp_wait(af_mlp* m) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  if (m->waited >= m->submitted) return AF_OK;
+  DeviceGuard guard(m->ctx->device);
+  af_mlp::Slot& sl = m->slot[m->waited & 1];
+  AF_CUDA(cudaEventSynchronize(sl.out_done));
+  sl.busy = false;
+  m->waited += 1;
+  return AF_OK;
+}
+
+int af_mlp_submit_host(af_mlp* m, int with_r, const double* hX, const double* hU, const double* hUR, double* hOut,
+                       double* hROut, double* const* hGrads, double* const* hRGrads) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  AF_NEED(hX);
+  af_ctx* ctx = m->ctx;
+  DeviceGuard guard(ctx->device);
+  AF_TRY(mlp_pipeline_init(m));
+  while (m->submitted - m->waited >= 2) AF_TRY(af_mlp_wait(m));  // at most two steps in flight
+  const int k = (int)(m->submitted & 1);
+  af_mlp::Slot& sl = m->slot[k];
+  const int L = m->L;
+  const int64_t top = m->n * m->sizes[L];
+  // upload on the copy-in stream; the slot's previous user has fully drained (out_done waited above)
+  AF_CUDA(cudaMemcpyAsync(sl.x, hX, (size_t)(m->n * m->sizes[0]) * 8, cudaMemcpyHostToDevice, m->copy_in));
+  AF_CUDA(cudaEventRecord(sl.in_ready, m->copy_in));
+  cudaStream_t st = ctx->stream;
+  AF_CUDA(cudaStreamWaitEvent(st, sl.in_ready, 0));
+  mlp_bind_slot(m, k);
+  if (hU) AF_CUDA(cudaMemcpyAsync(m->delta[L], hU, (size_t)top * 8, cudaMemcpyHostToDevice, st));
+  else AF_TRY(af_fill(ctx, m->delta[L], 1.0, top));
+  if (with_r) {
+    if (hUR) AF_CUDA(cudaMemcpyAsync(m->rdelta[L], hUR, (size_t)top * 8, cudaMemcpyHostToDevice, st));
+    else AF_CUDA(cudaMemsetAsync(m->rdelta[L], 0, (size_t)top * 8, st));
+  }
+  AF_TRY(af_mlp_zero_grads(m));
+  AF_TRY(af_mlp_step(m, with_r, 1));
+  AF_CUDA(cudaEventRecord(sl.compute_done, st));
+  // download on the copy-out stream while the next step computes into the other slot
+  cudaStream_t co = m->copy_out;
+  AF_CUDA(cudaStreamWaitEvent(co, sl.compute_done, 0));
+  if (hOut) AF_CUDA(cudaMemcpyAsync(hOut, sl.out, (size_t)top * 8, cudaMemcpyDeviceToHost, co));
+  if (hROut && with_r) AF_CUDA(cudaMemcpyAsync(hROut, sl.rout, (size_t)top * 8, cudaMemcpyDeviceToHost, co));
+  for (int i = 0; i < 2 * L; ++i) {
+    if (hGrads && hGrads[i])
+      AF_CUDA(cudaMemcpyAsync(hGrads[i], sl.grad[i], (size_t)m->param_len(i) * 8, cudaMemcpyDeviceToHost, co));
+    if (with_r && hRGrads && hRGrads[i])
+      AF_CUDA(cudaMemcpyAsync(hRGrads[i], sl.rgrad[i], (size_t)m->param_len(i) * 8, cudaMemcpyDeviceToHost, co));
+  }
+  AF_CUDA(cudaEventRecord(sl.out_done, co));
+  sl.busy = true;
+  m->submitted += 1;
+  return AF_OK;
+}
+
 int af_mlp_step_host(af_mlp* m, int with_r, const double* hX, const double* hU, const double* hUR, double* hOut,
                      double* hROut, double* const* hGrads, double* const* hRGrads) {
   if (!m) return fail(AF_EINVAL, "null mlp");
   AF_NEED(hX);
   af_ctx* ctx = m->ctx;
   DeviceGuard guard(ctx->device);
+  while (m->waited < m->submitted) AF_TRY(af_mlp_wait(m));
+  if (m->copy_in) mlp_bind_slot(m, 0);
   cudaStream_t st = ctx->stream;
   const int L = m->L;
   const int64_t top = m->n * m->sizes[L];

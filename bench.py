@@ -265,34 +265,49 @@ def gpu_arm(args):
     # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
     def pinned(count_):
         return torch.empty(count_, dtype=torch.float64).pin_memory()
-    hx = pinned(x_host.size)
-    hx.numpy()[:] = x_host
-    hout, hrout = pinned(n_out), pinned(n_out)
-    hg = [pinned(plan.param_len(i)) for i in range(P)]
-    hrg = [pinned(plan.param_len(i)) for i in range(P)]
-    HP = C.c_void_p * P
-    g_arr, rg_arr = HP(*[t.data_ptr() for t in hg]), HP(*[t.data_ptr() for t in hrg])
+    # two sets of pinned host buffers: the N=1 path keeps two steps in flight (af_mlp_submit_host)
+    sets = []
+    for _ in range(2):
+        hx = pinned(x_host.size)
+        hx.numpy()[:] = x_host
+        hg = [pinned(plan.param_len(i)) for i in range(P)]
+        hrg = [pinned(plan.param_len(i)) for i in range(P)]
+        HP = C.c_void_p * P
+        sets.append(dict(hx=hx, hout=pinned(n_out), hrout=pinned(n_out), hg=hg, hrg=hrg,
+                         g_arr=HP(*[t.data_ptr() for t in hg]), rg_arr=HP(*[t.data_ptr() for t in hrg])))
     h2d = x_host.size * 8
     d2h = 2 * n_out * 8 + 2 * n_params * 8
+    e2e_k = [0]
 
     def e2e_step():
+        b = sets[e2e_k[0] & 1]
+        e2e_k[0] += 1
         if world == 1:
-            api.check(ctx.lib.af_mlp_step_host(plan.h, 1, hx.data_ptr(), None, None, hout.data_ptr(), hrout.data_ptr(),
-                                               g_arr, rg_arr))
+            # the reference-facing host-buffer call, pipelined: upload of step k+1 and download of step k-1
+            # overlap the compute of step k; every step still moves its own inputs and results
+            api.check(ctx.lib.af_mlp_submit_host(plan.h, 1, b["hx"].data_ptr(), None, None, b["hout"].data_ptr(),
+                                                 b["hrout"].data_ptr(), b["g_arr"], b["rg_arr"]))
         else:
-            api.check(ctx.lib.af_upload(ctx.h, plan.input().ptr, hx.data_ptr(), x_host.size))
+            api.check(ctx.lib.af_upload(ctx.h, plan.input().ptr, b["hx"].data_ptr(), x_host.size))
             step()
-            api.check(ctx.lib.af_download(ctx.h, hout.data_ptr(), plan.output().ptr, n_out))
-            api.check(ctx.lib.af_download(ctx.h, hrout.data_ptr(), plan.routput().ptr, n_out))
+            api.check(ctx.lib.af_download(ctx.h, b["hout"].data_ptr(), plan.output().ptr, n_out))
+            api.check(ctx.lib.af_download(ctx.h, b["hrout"].data_ptr(), plan.routput().ptr, n_out))
             for i in range(P):
-                api.check(ctx.lib.af_download(ctx.h, hg[i].data_ptr(), plan.grad(i).ptr, plan.param_len(i)))
-                api.check(ctx.lib.af_download(ctx.h, hrg[i].data_ptr(), plan.rgrad(i).ptr, plan.param_len(i)))
+                api.check(ctx.lib.af_download(ctx.h, b["hg"][i].data_ptr(), plan.grad(i).ptr, plan.param_len(i)))
+                api.check(ctx.lib.af_download(ctx.h, b["hrg"][i].data_ptr(), plan.rgrad(i).ptr, plan.param_len(i)))
+
+    def e2e_drain():
+        if world == 1:
+            api.check(ctx.lib.af_mlp_wait(plan.h))
+            api.check(ctx.lib.af_mlp_wait(plan.h))
     for _ in range(max(1, min(W, 3))):
         e2e_step()
+    e2e_drain()
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
         e2e_step()
+    e2e_drain()
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -200,6 +200,16 @@ int af_mlp_step_host(af_mlp*, int with_r, const double* h_X, const double* h_ups
                      const double* h_upstream_r, double* h_out, double* h_rout,
                      double* const* h_grads, double* const* h_rgrads);
 
+/* Pipelined form of af_mlp_step_host: returns as soon as the step is queued.  Two steps may be in
+ * flight: while step k computes, step k-1 downloads its results on a copy stream and step k+1 uploads
+ * its inputs on another.  Host buffers should be pinned and must stay valid until the matching
+ * af_mlp_wait(), which waits for the OLDEST queued step (its host outputs are then complete).
+ * A third submit first waits for the oldest step.                                                */
+int af_mlp_submit_host(af_mlp*, int with_r, const double* h_X, const double* h_upstream,
+                       const double* h_upstream_r, double* h_out, double* h_rout,
+                       double* const* h_grads, double* const* h_rgrads);
+int af_mlp_wait(af_mlp*);
+
 /* dst[r*ld_dst + c] = src[r*ld_src + c]: the copy behind Concat / Slice of packed batches
  * (slices.go:13-119,130-206) when the parts are interleaved per sample.                          */
 int af_copy_2d(af_ctx*, double* d_dst, int64_t ld_dst, const double* d_src, int64_t ld_src, int64_t rows, int64_t cols);

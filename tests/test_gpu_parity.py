@@ -320,6 +320,36 @@ def test_mlp_plan_matches_oracle(api, scaled, with_r, n):
     plan.close()
 
 
+def test_mlp_pipelined_host_steps_match_blocking_steps(api):
+    """af_mlp_submit_host / af_mlp_wait (two steps in flight, double-buffered slots) give the same results
+    as af_mlp_step_host, step by step, for different inputs per step."""
+    sizes, n, steps = [64, 48, 10], 200, 5
+    onet = ref.MLP(sizes, weight_scale=lambda k: 1 / np.sqrt(k))
+    plan = api.MLPPlan(sizes, n)
+    for i, v in enumerate(onet.variables):
+        plan.set_param(i, v.vector)
+        plan.set_rvector(i, onet.rvec[v])
+    xs = [ref.splitmix_uniform(300 + k, n * sizes[0]) for k in range(steps)]
+    want = [plan.step_host(x) for x in xs]
+    P = 2 * plan.L
+    bufs = [dict(out=np.empty(n * 10), rout=np.empty(n * 10), grads=[np.empty(plan.param_len(i)) for i in range(P)],
+                 rgrads=[np.empty(plan.param_len(i)) for i in range(P)]) for _ in range(steps)]
+    for k in range(steps):
+        plan.submit_host(xs[k], **bufs[k])
+    for k in range(steps):
+        plan.wait()
+    for k in range(steps):
+        out, rout, grads, rgrads = want[k]
+        assert np.array_equal(bufs[k]["out"], out) and np.array_equal(bufs[k]["rout"], rout)
+        for i in range(P):
+            close(bufs[k]["grads"][i], grads[i], f"step {k} grad[{i}]")
+            close(bufs[k]["rgrads"][i], rgrads[i], f"step {k} rgrad[{i}]")
+    # and the blocking call still works afterwards (rebinds slot 0)
+    out, rout, grads, rgrads = plan.step_host(xs[0])
+    assert np.array_equal(out, want[0][0])
+    plan.close()
+
+
 def test_mlp_plan_missing_rvectors(api):
     """Variables absent from the RVector have zero R (variable.go:85-91; arithmetic_test.go:33-34)."""
     sizes, n = [32, 24, 8], 40
