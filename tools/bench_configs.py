@@ -102,6 +102,20 @@ def lstm_config(ctx, I, H, O, T, B, steps):
         plan.forward(True)
         plan.backward(True)
     ms = timed(step, steps)
+    if os.environ.get("AF_TRACE"):
+        cap = 4096
+        kinds, work, msa, cnt = (C.c_int * cap)(), (C.c_double * cap)(), (C.c_float * cap)(), C.c_int(0)
+        api.check(ctx.lib.af_trace_begin(ctx.h, cap))
+        step()
+        api.check(ctx.lib.af_trace_end(ctx.h, cap, kinds, work, msa, C.byref(cnt)))
+        agg = {}
+        for i in range(cnt.value):
+            key = (kinds[i], round(work[i]))
+            a = agg.setdefault(key, [0, 0.0])
+            a[0] += 1
+            a[1] += msa[i]
+        for (k, w), (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"  kind={k} work={w:.4g} launches={c} total={t:.3f} ms avg={t / c * 1e3:.1f} us rate={w * c / t / 1e9 if t else 0:.2f} (TF/s or TB/s)", file=sys.stderr)
     flops = 18.0 * (4 * H + O) * (H + I) * T * B
     plan.close()
     print(json.dumps({"config": f"C4 lstm I={I} H={H} O={O} T={T} B={B} fwd+BPTT+R", "ms_per_step": ms,
