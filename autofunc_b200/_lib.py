@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libautofunc_b200.so")
+LIB_PATH = os.environ.get("AUTOFUNC_B200_LIB") or os.path.join(_HERE, "libautofunc_b200.so")  # override: A/B builds only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "autofunc_b200.h")
 
 AF_OK, AF_ESHAPE, AF_ECUDA, AF_ENOMEM, AF_EINVAL, AF_ENOTSUP = 0, -1, -2, -3, -4, -5

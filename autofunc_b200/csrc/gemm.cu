@@ -53,9 +53,9 @@ double gemm_flops(const GemmArgs& a, bool dual) {
   return 2.0 * a.I * a.J * a.Kd * products;
 }
 
-template <int ALAY, int BLAY, int NACC, int CFG>
-int launch_dmma(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3 grid) {
-  auto kern = gemm_dmma_kernel<ALAY, BLAY, NACC, CFG>;
+template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI>
+int launch_dmma_impl(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3 grid) {
+  auto kern = gemm_dmma_kernel<ALAY, BLAY, NACC, CFG, MULTI>;
   const int smem = (int)GemmSmem<NACC, CFG>::kTotal;
   static bool configured = false;  // per template instantiation; attribute is per device function
   if (!configured) {
@@ -66,19 +66,12 @@ int launch_dmma(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3
   return after_launch(ctx, "gemm_dmma_kernel", NACC == 2 ? KIND_GEMM_DUAL : KIND_GEMM_SINGLE, gemm_flops(args, NACC == 2));
 }
 
-// Split-K choice for accumulating outputs (weight gradients; the contraction runs over the batch).
-// Cost of `s` splits in k-tile units per SM: ceil(tiles*s / SMs) waves, each ceil(kt/s) k-tiles plus
-// ~1.5 k-tiles for the red.global.add epilogue.  Picks the wave count that quantises best.
-int choose_splits(long long tiles, int kt_total, int sms) {
-  int best = 1;
-  double best_cost = 1e300;
-  const int max_s = kt_total / 4 > 0 ? kt_total / 4 : 1;
-  for (int s = 1; s <= max_s && s <= 64; ++s) {
-    const long long waves = (tiles * s + sms - 1) / sms;
-    const double cost = (double)waves * ((kt_total + s - 1) / s + (s > 1 ? 1.5 : 0.25));
-    if (cost < best_cost * 0.995) { best_cost = cost; best = s; }
-  }
-  return best;
+// stream-K (ranges spanning tiles) is instantiated for the default and the narrow configuration only
+template <int ALAY, int BLAY, int NACC, int CFG>
+int launch_dmma(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3 grid) {
+  if (CFG != 0 && args.units_per_tile == args.kt_total && args.units_per_cta != args.kt_total)
+    return launch_dmma_impl<ALAY, BLAY, NACC, CFG, (CFG != 0)>(ctx, maps, args, grid);
+  return launch_dmma_impl<ALAY, BLAY, NACC, CFG, false>(ctx, maps, args, grid);
 }
 
 template <int ALAY, int BLAY>
@@ -125,7 +118,6 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   const GemmArgs logical = args;  // un-swapped view, used by the generic kernel and the deferred epilogue
   const bool accumulate = e.epi == EPI_ACCUM;
   const int kt_total = (int)((Kd + kBK - 1) / kBK);
-  args.k_tiles_per_split = kt_total > 0 ? kt_total : 1;
 
   const bool tma_ok = ctx->encode_tiled != nullptr && tma_compatible(A.p0, A.ld, I, Kd) &&
                       tma_compatible(A.p1, A.ld, I, Kd) && tma_compatible(B.p0, B.ld, J, Kd) &&
@@ -158,33 +150,56 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   const int cfg = J <= 16 ? 1 : ctx->big_cfg;
   const int bm = cfg == 1 ? GemmSmem<2, 1>::kBMc : cfg == 2 ? GemmSmem<2, 2>::kBMc : GemmSmem<2, 0>::kBMc;
   const int bn = cfg == 1 ? GemmSmem<2, 1>::kBNc : cfg == 2 ? GemmSmem<2, 2>::kBNc : GemmSmem<2, 0>::kBNc;
-  dim3 grid((unsigned)((J + bn - 1) / bn), (unsigned)((I + bm - 1) / bm), 1);
-  const long long tiles = (long long)grid.x * grid.y;
+  const long long tiles_j = (J + bn - 1) / bn, tiles_i = (I + bm - 1) / bm;
+  const long long tiles = tiles_i * tiles_j;
   const int slots = ctx->sm_count * (cfg == 2 ? 2 : 1);
+  args.kt_total = kt_total;
+  args.tiles_j = (int)tiles_j;
+  args.total_units = tiles * kt_total;
 
-  // Split the contraction when the output has too few tiles to occupy the chip.  Accumulating outputs
-  // (weight gradients) combine partial tiles with red.global.add.f64 directly; storing outputs are zeroed,
-  // accumulated the same way, and get their fused elementwise step from gemm_epilogue_kernel afterwards.
-  bool deferred = false;
-  int splits = 1;
-  if (accumulate) {
-    splits = choose_splits(tiles, kt_total, slots);
-  } else if (contiguous_out && (swapped || (2 * tiles <= slots && kt_total >= 16))) {
-    splits = choose_splits(tiles, kt_total, slots);
-    deferred = swapped || splits > 1;
+  // Work decomposition (see gemm_dmma_kernel), chosen by a small cost model in k-tile units per CTA slot:
+  //   one tile per CTA : waves(tiles) * (kt + 0.5)                       fused epilogue, plain stores
+  //   aligned split-K s: waves(tiles*s) * (ceil(kt/s) + cf)              partial tiles via red.global.add.f64
+  //   stream-K         : U + cf * (segments per CTA), U = total/slots    equal contiguous unit ranges
+  // Store-type outputs pay cd more on the two atomic paths (zeroing + gemm_epilogue_kernel afterwards).
+  const double cf = 3.5, cd = accumulate ? 0.0 : 3.0;
+  auto waves_of = [&](long long ctas) { return (double)((ctas + slots - 1) / slots); };
+  const bool may_split = kt_total >= 8 && (accumulate || contiguous_out);
+  const bool must_defer = swapped && !accumulate;  // transposed stores always go through the deferred epilogue
+  int mode = 0, best_s = 1;                         // 0 = one tile per CTA, 1 = aligned split, 2 = stream-K
+  double best = must_defer ? 1e300 : waves_of(tiles) * (kt_total + 0.5);
+  long long sk_units = (args.total_units + slots - 1) / slots;
+  if (sk_units < 4) sk_units = 4;
+  if (may_split || must_defer) {
+    for (int sp = 2; sp <= 64 && sp <= kt_total / 4; ++sp) {
+      const double c = waves_of(tiles * sp) * ((kt_total + sp - 1) / sp + cf) + cd;
+      if (c < best * 0.98) { best = c; mode = 1; best_s = sp; }
+    }
+    const double segs = 1.0 + (double)(sk_units - 1) / kt_total;
+    const double c = 1.03 * (sk_units + cf * segs) + cd;
+    if (cfg != 0 && (c < best * 0.98 || (must_defer && mode == 0))) { best = c; mode = 2; }
   }
-  if (deferred) {
-    const size_t bytes = (size_t)logical.I * logical.J * 8;
-    if (args.out0) AF_CUDA(cudaMemsetAsync(args.out0, 0, bytes, ctx->stream));
-    if (args.out1) AF_CUDA(cudaMemsetAsync(args.out1, 0, bytes, ctx->stream));
+  bool deferred = false;
+  long long units_per_cta = kt_total, units_per_tile = kt_total;
+  if (mode == 1) {
+    units_per_cta = (kt_total + best_s - 1) / best_s;
+    units_per_tile = units_per_cta * best_s;
+  } else if (mode == 2) {
+    units_per_cta = sk_units;
+  }
+  if (mode != 0) {
+    if (!accumulate) {
+      deferred = true;
+      const size_t bytes = (size_t)logical.I * logical.J * 8;
+      if (args.out0) AF_CUDA(cudaMemsetAsync(args.out0, 0, bytes, ctx->stream));
+      if (args.out1) AF_CUDA(cudaMemsetAsync(args.out1, 0, bytes, ctx->stream));
+    }
     args.epi = EPI_ACCUM_ATOMIC;
   }
-  if (splits > 1) {
-    args.k_tiles_per_split = (kt_total + splits - 1) / splits;
-    splits = (kt_total + args.k_tiles_per_split - 1) / args.k_tiles_per_split;
-    grid.z = (unsigned)splits;
-    args.epi = EPI_ACCUM_ATOMIC;  // partial tiles combine with red.global.add.f64
-  }
+  args.units_per_cta = (int)units_per_cta;
+  args.units_per_tile = (int)units_per_tile;
+  args.total_units = tiles * units_per_tile;
+  dim3 grid((unsigned)((args.total_units + units_per_cta - 1) / units_per_cta), 1, 1);
 
   CUtensorMap maps[4];
   AF_TRY(make_map(ctx, &maps[0], A.p0, A.layout, I, Kd, A.ld, bm));

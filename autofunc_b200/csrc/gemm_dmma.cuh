@@ -56,7 +56,11 @@ struct GemmArgs {
   int I, J, Kd;
   int has_a1, has_b1;  // R operands present (NULL R-vector == zero, variable.go:85-91)
   int epi;
-  int k_tiles_per_split;
+  int kt_total;            // k-tiles per output tile
+  int tiles_j;             // output tiles along J (tile index = ti * tiles_j + tj)
+  int units_per_cta;       // contiguous (tile, k-tile) units per CTA; == kt_total for one tile per CTA
+  int units_per_tile;      // == kt_total (stream-K, one tile per CTA) or splits * units_per_cta (aligned split-K)
+  long long total_units;
   int transpose_out;  // write element (i,j) at out[j*ldo + i] (operands were swapped by the host)
   double* out0;
   double* out1;
@@ -259,7 +263,17 @@ __device__ __forceinline__ uint32_t frag_addr(uint32_t base, int t) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int ALAY, int BLAY, int NACC, int CFG>
+// Work decomposition ("stream-K"): the output tiles x k-tiles form one linear sequence of UNITS,
+// unit u = (tile u / kt_total, k-tile u % kt_total), tiles ordered j-fastest.  CTA c owns the contiguous
+// range [c*U, (c+1)*U).  U == kt_total is the classic one-tile-per-CTA launch (fused epilogue, plain
+// stores); any other U lets a CTA end in the middle of a tile or span several, which balances the chip
+// for ANY shape (e.g. 512 tiles on 296 CTA slots = 1.73 waves -> every CTA gets 1.73 tiles' worth);
+// partial tiles are then combined with red.global.add.f64 (the host zeroes store-type outputs first and
+// applies the elementwise step afterwards with gemm_epilogue_kernel).  The TMA ring and the fragment
+// prefetch run across tile boundaries, so a new tile's pipeline fill overlaps the previous tile's math.
+// MULTI = false: the CTA's range lies inside one tile (one tile per CTA, or aligned split-K): one segment, one
+// epilogue after the loop -- the leanest code.  MULTI = true: stream-K, the range may span tiles.
+template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI>
 __global__ void __launch_bounds__(TileCfg<CFG>::WI * TileCfg<CFG>::WJ * 32, TileCfg<CFG>::MIN_CTAS)
 gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs p) {
@@ -271,12 +285,16 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms are 1024-B aligned
   const uint32_t bars = base + L::kBarOffset;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
-  const int kt_total = (p.Kd + kBK - 1) / kBK;
-  const int kt_begin = blockIdx.z * p.k_tiles_per_split;
-  int nkt = kt_total - kt_begin;
-  if (nkt > p.k_tiles_per_split) nkt = p.k_tiles_per_split;
-  if (nkt <= 0) return;
+  const int kt_total = p.kt_total;
+  const long long u0 = (long long)blockIdx.x * p.units_per_cta;
+  long long u1 = u0 + p.units_per_cta;
+  if (u1 > p.total_units) u1 = p.total_units;
+  int nun = (int)(u1 - u0);
+  const int tile0 = (int)(u0 / p.units_per_tile);
+  const int kt0 = (int)(u0 - (long long)tile0 * p.units_per_tile);
+  // aligned split-K pads every tile to a multiple of units_per_cta: clip the padding
+  if (p.units_per_tile != kt_total && nun > kt_total - kt0) nun = kt_total - kt0;
+  if (nun <= 0) return;
   const bool has_a1 = DUAL && p.has_a1, has_b1 = DUAL && p.has_b1;
 
   if (threadIdx.x == 0) {
@@ -290,28 +308,35 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   __syncthreads();
 
-  // Producer role: lane 0 of warp 0 keeps kStages-1 tiles in flight.  It is folded into a consumer
-  // warp (not a 9th warp) because registers are allocated per SM sub-partition: a 9th warp would put
+  // Producer role: lane 0 of warp 0 keeps kStages-1 units in flight.  It is folded into a consumer
+  // warp (not an extra warp) because registers are allocated per SM sub-partition: an extra warp would put
   // three warps on one sub-partition and cap every thread at 168 registers, spilling accumulators.
   const uint32_t tx_bytes = L::kABytes + L::kBBytes + (has_a1 ? L::kABytes : 0) + (has_b1 ? L::kBBytes : 0);
+  // the producer walks the unit sequence incrementally (no divisions in the loop)
+  int p_kt = kt0, p_tj = tile0 % p.tiles_j, p_ti = tile0 / p.tiles_j;
   auto produce = [&](int t) {
     const int s = t % kStages;
     const uint32_t ph = (t / kStages) & 1;
-    mbar_wait(bars + 8 * (kStages + s), ph ^ 1);  // all 8 warps released the stage's previous tile
+    mbar_wait(bars + 8 * (kStages + s), ph ^ 1);  // all warps released the stage's previous unit
     const uint32_t full = bars + 8 * s;
     const uint32_t st = base + s * L::kStageBytes;
-    const int k0 = (kt_begin + t) * kBK;
+    const int k0 = p_kt * kBK, i0 = p_ti * BM, j0 = p_tj * BN;
     mbar_expect_tx(full, tx_bytes);
     tma_load_tile<ALAY, BM>(st + L::kA0, &tmA0, full, i0, k0);
     tma_load_tile<BLAY, BN>(st + L::kB0, &tmB0, full, j0, k0);
     if (has_a1) tma_load_tile<ALAY, BM>(st + L::kA1, &tmA1, full, i0, k0);
     if (has_b1) tma_load_tile<BLAY, BN>(st + L::kB1, &tmB1, full, j0, k0);
+    ++p_kt;
+    if (MULTI && p_kt == kt_total) {
+      p_kt = 0;
+      if (++p_tj == p.tiles_j) { p_tj = 0; ++p_ti; }
+    }
   };
   if (threadIdx.x == 0) {
-    for (int t = 0; t < kStages - 1 && t < nkt; ++t) produce(t);
+    for (int t = 0; t < kStages - 1 && t < nun; ++t) produce(t);
   }
 
-  // ---------------- consumers: 8 warps, WI (i) x WJ (j) ----------------
+  // ---------------- consumers: WI (i) x WJ (j) warps ----------------
   const int g = lane >> 2, j4 = lane & 3;
   const int wi0 = (warp / T::WJ) * (TI * 8), wj0 = (warp % T::WJ) * (TJ * 8);
   const int kj = ((j4 & 1) ? 3 : 0) | ((j4 & 2) ? 12 : 0);
@@ -326,18 +351,19 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 
   double acc0[TI][TJ][2], acc1[DUAL ? TI : 1][TJ][2];
+  auto zero_acc = [&]() {
 #pragma unroll
-  for (int t = 0; t < TI; ++t)
+    for (int t = 0; t < TI; ++t)
 #pragma unroll
-    for (int u = 0; u < TJ; ++u) {
-      acc0[t][u][0] = acc0[t][u][1] = 0.0;
-      if (DUAL) acc1[t][u][0] = acc1[t][u][1] = 0.0;
-    }
+      for (int u = 0; u < TJ; ++u) {
+        acc0[t][u][0] = acc0[t][u][1] = 0.0;
+        if (DUAL) acc1[t][u][0] = acc1[t][u][1] = 0.0;
+      }
+  };
+  zero_acc();
 
-  // Fragment registers are double-buffered by hand ACROSS k-tile boundaries: the loads of MMA step
-  // q+1 (possibly the first step of the next stage) are issued before the DMMAs of step q, so the
-  // two warps of a sub-partition never both sit on an mbarrier wait + LDS latency with the tensor
-  // pipe idle.
+  // Fragment registers are double-buffered by hand ACROSS unit boundaries: the loads of MMA step q+1
+  // (possibly the first step of the next stage) are issued before the DMMAs of step q.
   constexpr int NB = T::PREFETCH ? 2 : 1;
   double a0[NB][TI], b0[NB][TJ], a1[NB][DUAL ? TI : 1], b1[NB][DUAL ? TJ : 1];
   auto load_frags = [&](int buf, uint32_t st, int ks) {
@@ -375,62 +401,76 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
   };
 
+  // registers -> global for the tile that just ended (or was interrupted by the end of this CTA's range)
+  const bool vec_ok = !p.transpose_out && ((p.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.out0) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.out1) & 15) == 0);
+  auto flush = [&](int tile) {
+    const int i0 = (tile / p.tiles_j) * BM, j0 = (tile % p.tiles_j) * BN;
+#pragma unroll
+    for (int t = 0; t < TI; ++t) {
+      const long long i = i0 + wi0 + 8 * t + g;
+      if (i < p.I) {
+#pragma unroll
+        for (int u = 0; u < TJ; ++u) {
+          const int j = j0 + wj0 + 8 * u + 2 * j4;
+          if (j < p.J)
+            epi_pair<DUAL>(p, vec_ok, i, j, acc0[t][u][0], acc0[t][u][1], DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0,
+                           DUAL ? acc1[DUAL ? t : 0][u][1] : 0.0);
+        }
+      }
+    }
+  };
+
+  // Outer loop: one iteration per tile segment of this CTA's unit range; the epilogue stays outside the
+  // hot loop.  The ring and the fragment prefetch simply continue into the next segment.
+  int kt_cur = kt0, tile_cur = tile0;
   if (T::PREFETCH) {
     mbar_wait(bars + 0, 0);
     load_frags(0, base, 0);
-    for (int kt = 0; kt < nkt; ++kt) {
-      const int s = kt % kStages;
+  }
+  int un = 0;
+  while (un < nun) {
+    int seg_end = nun;
+    if (MULTI) {
+      seg_end = un + (kt_total - kt_cur);
+      if (seg_end > nun) seg_end = nun;
+    }
+    for (; un < seg_end; ++un) {
+      const int s = un % kStages;
       const uint32_t st = base + s * L::kStageBytes;
-      if (threadIdx.x == 0 && kt + kStages - 1 < nkt) produce(kt + kStages - 1);
+      if (threadIdx.x == 0 && un + kStages - 1 < nun) produce(un + kStages - 1);
       __syncwarp();
+      if (T::PREFETCH) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        if (ks < 3) {
-          load_frags((ks + 1) & 1, st, ks + 1);
-        } else if (kt + 1 < nkt) {
-          const int s1 = (kt + 1) % kStages;
-          mbar_wait(bars + 8 * s1, ((kt + 1) / kStages) & 1);
-          load_frags(0, base + s1 * L::kStageBytes, 0);
+        for (int ks = 0; ks < 4; ++ks) {
+          if (ks < 3) {
+            load_frags((ks + 1) & 1, st, ks + 1);
+          } else if (un + 1 < nun) {
+            const int s1 = (un + 1) % kStages;
+            mbar_wait(bars + 8 * s1, ((un + 1) / kStages) & 1);
+            load_frags(0, base + s1 * L::kStageBytes, 0);
+          }
+          mma_step(ks & 1);
         }
-        mma_step(ks & 1);
+      } else {
+        mbar_wait(bars + 8 * s, (un / kStages) & 1);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          load_frags(0, st, ks);
+          mma_step(0);
+        }
       }
       // every ld.shared of this stage has been consumed by an issued DMMA: hand the slot back
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 8 * (kStages + s));
     }
-  } else {
-    for (int kt = 0; kt < nkt; ++kt) {
-      const int s = kt % kStages;
-      const uint32_t st = base + s * L::kStageBytes;
-      if (threadIdx.x == 0 && kt + kStages - 1 < nkt) produce(kt + kStages - 1);
-      __syncwarp();
-      mbar_wait(bars + 8 * s, (kt / kStages) & 1);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        load_frags(0, st, ks);
-        mma_step(0);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 8 * (kStages + s));
-    }
+    if (!MULTI || un >= nun) break;  // the last (or only) segment is flushed after the loop
+    flush(tile_cur);
+    zero_acc();
+    kt_cur = 0;
+    ++tile_cur;
   }
-
-  // ---------------- epilogue: registers -> global, fused elementwise ----------------
-  const bool vec_ok = !p.transpose_out && ((p.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.out0) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(p.out1) & 15) == 0);
-#pragma unroll
-  for (int t = 0; t < TI; ++t) {
-    const long long i = i0 + wi0 + 8 * t + g;
-    if (i < p.I) {
-#pragma unroll
-      for (int u = 0; u < TJ; ++u) {
-        const int j = j0 + wj0 + 8 * u + 2 * j4;
-        if (j < p.J)
-          epi_pair<DUAL>(p, vec_ok, i, j, acc0[t][u][0], acc0[t][u][1], DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0,
-                         DUAL ? acc1[DUAL ? t : 0][u][1] : 0.0);
-      }
-    }
-  }
+  flush(tile_cur);
 }
 
 // ---------------------------------------------------------------------------------------------
