@@ -84,6 +84,7 @@ PROTOTYPES = {
     "af_mlp_upstream_r_ptr": (D, [P]),
     "af_mlp_zero_grads": (INT, [P]),
     "af_mlp_step": (INT, [P, INT, INT]),
+    "af_mlp_set_graph": (INT, [P, INT]),
     "af_mlp_step_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),
     "af_mlp_submit_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),
     "af_mlp_wait": (INT, [P]),

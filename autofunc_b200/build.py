@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libautofunc_b200.so")
-SOURCES = ["capi.cu", "gemm.cu", "elementwise.cu", "lstm.cu"]
+SOURCES = ["capi.cu", "gemm.cu", "elementwise.cu", "lstm.cu", "small_n.cu"]
 HEADERS = ["common.h", "gemm_dmma.cuh", os.path.join("..", "..", "include", "autofunc_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",

@@ -162,6 +162,10 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->big_cfg = value;
     return AF_OK;
   }
+  if (!strcmp(name, "small_n")) {
+    ctx->small_n_off = value == 0;
+    return AF_OK;
+  }
   return fail(AF_EINVAL, std::string("unknown option ") + name);
 }
 
@@ -232,6 +236,8 @@ static int dense_fwd_impl(af_ctx* ctx, const double* W, const double* RW, const 
   GemmOperand B{W, dual ? RW : nullptr, LAY_KC, cols};
   GemmEpilogue e;
   e.epi = epi; e.out0 = Y; e.out1 = RY; e.ldo = rows; e.bias0 = b; e.bias1 = Rb;
+  if (small_n_applicable(ctx, rows, cols, n, {W, RW, X, RX}))  // the reference's Gemv branch, lin_tran.go:90-99,138-152
+    return small_fwd_launch(ctx, W, RW, X, RX, rows, cols, n, e, dual);
   if (cols == 0) {
     // empty contraction: fall through the generic kernel (Kd == 0 gives acc = 0)
     int saved = ctx->gemm_path;
@@ -263,6 +269,8 @@ static int wgrad_impl(af_ctx* ctx, const double* U, const double* UR, const doub
   if (rows * cols == 0 || n == 0) return AF_OK;
   const bool dual = rgW != nullptr;
   if (!gW && !rgW) return AF_OK;
+  if (small_n_applicable(ctx, rows, cols, n, {X, RX, gW, rgW}))  // Ger branch, lin_tran.go:187-196,223-241
+    return small_wgrad_launch(ctx, U, dual ? UR : nullptr, X, dual ? RX : nullptr, gW, rgW, rows, cols, n);
   GemmOperand A{U, dual ? UR : nullptr, LAY_RC, rows};
   GemmOperand B{X, dual ? RX : nullptr, LAY_RC, cols};
   GemmEpilogue e;
@@ -294,6 +302,8 @@ static int igrad_impl(af_ctx* ctx, const double* U, const double* UR, const doub
   GemmEpilogue e;
   e.epi = S ? EPI_SIGMOID_BWD : EPI_STORE;
   e.out0 = D; e.out1 = DR; e.ldo = cols; e.s = S; e.rs = RS; e.lds = cols;
+  if (rows > 0 && small_n_applicable(ctx, rows, cols, n, {W, RW, D, DR}))  // Gemv T branch, lin_tran.go:285-288,329-334
+    return small_igrad_launch(ctx, U, UR, W, RW, rows, cols, n, e, dual);
   if (rows == 0) {
     int saved = ctx->gemm_path;
     ctx->gemm_path = 1;
@@ -371,10 +381,26 @@ struct af_mlp {
     bool busy = false;
   };
   Slot slot[2];
+  int bound_slot = 0;
+  // CUDA-graph replay of the step (small batches are launch-bound: ~25 short kernels per step).  One graph
+  // per (with_r, backprop, slot); captured on the second call of a configuration, dropped whenever the set
+  // of present R-vectors changes.
+  struct StepGraph { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; };
+  StepGraph graphs[2][2][2];
+  bool use_graph = false;
   double* alt = nullptr;  // backing store of slot 1
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   int64_t submitted = 0, waited = 0;
 };
+static void mlp_drop_graphs(af_mlp* m) {
+  for (auto& a : m->graphs)
+    for (auto& b : a)
+      for (auto& g : b) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = af_mlp::StepGraph();
+      }
+}
+
 
 extern "C" {
 
@@ -413,6 +439,7 @@ int af_mlp_create(af_ctx* ctx, const int64_t* sizes, int n_layers, int64_t batch
   for (int l = 0; l <= n_layers; ++l) m->delta.push_back(next());
   for (int l = 0; l <= n_layers; ++l) m->rdelta.push_back(next());
   m->has_rvec.assign(P, false);
+  m->use_graph = batch <= 256;  // launch-bound regime
   for (int i = 0; i < P; ++i) m->total_params += m->param_len(i);
   *out = m;
   return AF_OK;
@@ -427,6 +454,7 @@ int af_mlp_destroy(af_mlp* m) {
   for (auto& sl : m->slot)
     for (cudaEvent_t ev : {sl.in_ready, sl.compute_done, sl.out_done})
       if (ev) cudaEventDestroy(ev);
+  mlp_drop_graphs(m);
   if (m->alt) cudaFree(m->alt);
   cudaFree(m->slab);
   delete m;
@@ -450,8 +478,13 @@ int af_mlp_set_param(af_mlp* m, int index, const double* h, int64_t len) {
 int af_mlp_set_rvector(af_mlp* m, int index, const double* h, int64_t len) {
   if (!m) return fail(AF_EINVAL, "null mlp");
   if (index < 0 || index >= 2 * m->L) return fail(AF_EINVAL, "parameter index out of range");
-  if (!h) { m->has_rvec[index] = false; return AF_OK; }
+  if (!h) {
+    if (m->has_rvec[index]) mlp_drop_graphs(m);
+    m->has_rvec[index] = false;
+    return AF_OK;
+  }
   AF_TRY(mlp_index_ok(m, index, len));
+  if (!m->has_rvec[index]) mlp_drop_graphs(m);
   m->has_rvec[index] = true;
   return af_upload(m->ctx, m->rvec[index], h, len);
 }
@@ -462,7 +495,7 @@ int af_mlp_set_rvector(af_mlp* m, int index, const double* h, int64_t len) {
     return expr;                                 \
   }
 MLP_PTR(af_mlp_param_ptr, m->param[index])
-MLP_PTR(af_mlp_rvector_ptr, (m->has_rvec[index] = true, m->rvec[index]))
+MLP_PTR(af_mlp_rvector_ptr, ((m->has_rvec[index] ? (void)0 : mlp_drop_graphs(m)), m->has_rvec[index] = true, m->rvec[index]))
 MLP_PTR(af_mlp_grad_ptr, m->grad[index])
 MLP_PTR(af_mlp_rgrad_ptr, m->rgrad[index])
 #undef MLP_PTR
@@ -481,10 +514,52 @@ int af_mlp_zero_grads(af_mlp* m) {
   return AF_OK;
 }
 
+static int mlp_step_launches(af_mlp* m, int with_r, int backprop);
+
+int af_mlp_set_graph(af_mlp* m, int enable) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  m->use_graph = enable != 0;
+  if (!enable) mlp_drop_graphs(m);
+  return AF_OK;
+}
+
 int af_mlp_step(af_mlp* m, int with_r, int backprop) {
   if (!m) return fail(AF_EINVAL, "null mlp");
   af_ctx* ctx = m->ctx;
   DeviceGuard guard(ctx->device);
+  // the legacy default stream cannot be captured
+  if (!m->use_graph || ctx->tracing || ctx->stream == nullptr || ctx->stream == cudaStreamLegacy)
+    return mlp_step_launches(m, with_r, backprop);
+  af_mlp::StepGraph& g = m->graphs[with_r ? 1 : 0][backprop ? 1 : 0][m->bound_slot];
+  if (g.exec) {
+    AF_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+    ctx->launches += g.launches;
+    return AF_OK;
+  }
+  if (g.seen++ == 0) return mlp_step_launches(m, with_r, backprop);  // first call also sets kernel attributes
+  const int64_t before = ctx->launches;
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();  // capture not possible on this stream: run eagerly from now on
+    m->use_graph = false;
+    return mlp_step_launches(m, with_r, backprop);
+  }
+  const int rc = mlp_step_launches(m, with_r, backprop);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+  if (rc != AF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+  g.launches = ctx->launches - before;
+  ctx->launches = before;
+  const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) { g.exec = nullptr; return cuda_fail(ie, "cudaGraphInstantiate"); }
+  AF_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+  ctx->launches += g.launches;
+  return AF_OK;
+}
+
+static int mlp_step_launches(af_mlp* m, int with_r, int backprop) {
+  af_ctx* ctx = m->ctx;
   const int L = m->L;
   const int64_t n = m->n;
   const bool R = with_r != 0;
@@ -547,6 +622,7 @@ static int mlp_pipeline_init(af_mlp* m) {
 }
 
 static void mlp_bind_slot(af_mlp* m, int k) {
+  m->bound_slot = k;
   const af_mlp::Slot& sl = m->slot[k];
   m->act[0] = sl.x; m->grad = sl.grad; m->rgrad = sl.rgrad;
   m->act[m->L] = sl.out; m->ract[m->L] = sl.rout;

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -17,6 +18,7 @@ struct af_ctx {
   int sm_count = 148;
   int gemm_path = 0;  // 0 auto, 1 generic, 2 require DMMA
   int big_cfg = 2;    // tile configuration for wide outputs: 0 = 128x64 x 8 warps, 2 = 64x64 x 2 CTAs/SM (default, fastest measured), 3 = 128x64 x 16 warps
+  bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   int64_t launches = 0;
   // driver entry point, resolved at run time so the library loads on hosts without libcuda
   void* encode_tiled = nullptr;
@@ -49,7 +51,7 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 // kernel kinds reported by the launch trace (include/autofunc_b200.h: AF_KIND_*)
-enum : int { KIND_GEMM_DUAL = 0, KIND_GEMM_SINGLE = 1, KIND_GEMM_GENERIC = 2, KIND_ELEMENTWISE = 3, KIND_REDUCE = 4 };
+enum : int { KIND_GEMM_DUAL = 0, KIND_GEMM_SINGLE = 1, KIND_GEMM_GENERIC = 2, KIND_ELEMENTWISE = 3, KIND_REDUCE = 4, KIND_SMALL_N = 5 };
 
 // after a kernel launch: count it, surface launch errors, and (when tracing) record an event.
 // `work` is the launch's ALGORITHMIC work: flops for contractions, bytes for streaming kernels.
@@ -88,5 +90,14 @@ struct GemmEpilogue {
 // acc0 = A0 B0^T ; acc1 = A0 B1^T + A1 B0^T (dual when `dual`), I x J, contraction Kd
 int gemm_launch(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool dual, long long I, long long J,
                 long long Kd, const GemmEpilogue& e);
+
+// small-batch (n <= 16) streaming kernels, small_n.cu: the reference's Gemv / Ger branch
+bool small_n_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs);
+int small_fwd_launch(af_ctx* ctx, const double* W, const double* RW, const double* X, const double* RX, long long rows,
+                     long long cols, long long n, const GemmEpilogue& e, bool dual);
+int small_wgrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* X, const double* RX, double* gW,
+                       double* rgW, long long rows, long long cols, long long n);
+int small_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, long long rows,
+                       long long cols, long long n, const GemmEpilogue& e, bool dual);
 
 }  // namespace af

@@ -102,6 +102,15 @@ __global__ void __launch_bounds__(256) gemm_epilogue_kernel(const GemmArgs p) {
   }
 }
 
+int gemm_deferred_epilogue(af_ctx* ctx, const GemmArgs& logical, bool dual) {
+  long long blocks = ((long long)logical.I * logical.J + 255) / 256;
+  if (blocks > 8ll * ctx->sm_count) blocks = 8ll * ctx->sm_count;
+  if (blocks < 1) blocks = 1;
+  if (dual) gemm_epilogue_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(logical);
+  else gemm_epilogue_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(logical);
+  return after_launch(ctx, "gemm_epilogue_kernel", KIND_ELEMENTWISE, 16.0 * (dual ? 2 : 1) * logical.I * logical.J);
+}
+
 int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, bool dual, long long I, long long J,
                 long long Kd, const GemmEpilogue& e) {
   if (I <= 0 || J <= 0) return AF_OK;
@@ -230,13 +239,7 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   }
   if (!dispatched) return fail(AF_EINVAL, "unsupported operand layout combination");
   AF_TRY(rc);
-  if (deferred && logical.epi != EPI_STORE) {
-    long long blocks = ((long long)logical.I * logical.J + 255) / 256;
-    if (blocks > 8ll * ctx->sm_count) blocks = 8ll * ctx->sm_count;
-    if (dual) gemm_epilogue_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(logical);
-    else gemm_epilogue_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(logical);
-    return after_launch(ctx, "gemm_epilogue_kernel", KIND_ELEMENTWISE, 16.0 * (dual ? 2 : 1) * logical.I * logical.J);
-  }
+  if (deferred && logical.epi != EPI_STORE) return gemm_deferred_epilogue(ctx, logical, dual);
   return AF_OK;
 }
 

@@ -1,0 +1,244 @@
+// Small-batch LinTran kernels: the reference's own n == 1 branch (Gemv / Ger instead of Gemm,
+// lin_tran.go:90-99, 138-152, 187-196, 223-241, 285-288, 329-334), generalised to n <= 8 samples (9..16 take the
+// tensor-core kernel with transposed narrow tiles, which measured faster there).
+//
+// With a handful of samples the six contractions are HBM-bound streaming passes over the weight
+// matrix, not tensor-core work: the algorithmic traffic is W, RW read once per forward and once per
+// input-gradient pass, and gW, rgW read-modify-written once (8 passes of 8*M*K bytes per
+// R-step).  Each kernel below makes exactly those passes with 16-byte coalesced accesses, keeps the
+// n samples' partial sums in registers, and applies the fused elementwise step where one thread block
+// owns a complete output (forward); the input gradient is split over row chunks and combined with
+// red.global.add.f64, its elementwise step applied afterwards by a tiny pass.
+#include "common.h"
+#include "gemm_dmma.cuh"
+
+namespace af {
+namespace {
+
+constexpr int kSmallThreads = 256;
+
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// ---- forward: `wpr` warps per weight row --------------------------------------------------------
+// Y[i][m] = sum_k X[i][k] W[m][k] ;  RY[i][m] = sum_k X[i][k] RW[m][k] + RX[i][k] W[m][k]
+// (Gemv N at lin_tran.go:99,151-152), then + bias, sigmoid and the R form in the same block.
+// A block of 8 warps owns 8/wpr rows; the warps of a row split K, reduce by shuffle, then through
+// shared memory, so that even a 512-row layer puts >= 256 blocks on the chip.
+template <int NMAX>
+__global__ void __launch_bounds__(kSmallThreads) small_fwd_kernel(const double* __restrict__ W, const double* __restrict__ RW,
+                                                                  const double* __restrict__ X, const double* __restrict__ RX,
+                                                                  int rows, int cols, int n, int wpr, const GemmArgs p) {
+  __shared__ double part[8][2 * NMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per_block = 8 / wpr;
+  const int m = blockIdx.x * rows_per_block + warp / wpr;
+  const int ws = warp % wpr;
+  const bool live = m < rows;
+  double y[NMAX], ry[NMAX];
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) y[i] = ry[i] = 0.0;
+  if (live) {
+    const double* w = W + (long long)m * cols;
+    const double* rw = RW ? RW + (long long)m * cols : nullptr;
+#pragma unroll 2
+    for (int k = 2 * lane + 64 * ws; k < cols; k += 64 * wpr) {
+      const double2 wv = ld2(w + k);
+      double2 rwv = make_double2(0.0, 0.0);
+      if (rw) rwv = ld2(rw + k);
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) {
+        if (i < n) {
+          const double2 xv = ld2(X + (long long)i * cols + k);
+          y[i] = fma(xv.x, wv.x, fma(xv.y, wv.y, y[i]));
+          if (rw) ry[i] = fma(xv.x, rwv.x, fma(xv.y, rwv.y, ry[i]));
+          if (RX) {
+            const double2 rxv = ld2(RX + (long long)i * cols + k);
+            ry[i] = fma(rxv.x, wv.x, fma(rxv.y, wv.y, ry[i]));
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      y[i] += __shfl_xor_sync(0xffffffffu, y[i], o);
+      ry[i] += __shfl_xor_sync(0xffffffffu, ry[i], o);
+    }
+    if (lane == 0) { part[warp][2 * i] = y[i]; part[warp][2 * i + 1] = ry[i]; }
+  }
+  __syncthreads();
+  // the first warp of each row group folds the group's partial sums; lane i finishes sample i
+  if (live && ws == 0 && lane < n) {
+    double a = 0.0, b = 0.0;
+    for (int q = 0; q < wpr; ++q) { a += part[warp + q][2 * lane]; b += part[warp + q][2 * lane + 1]; }
+    epi_elem<true>(p, lane, m, a, b);
+  }
+}
+
+// ---- weight gradient: rank-n update ------------------------------------------------------------
+// gW[m][k] += sum_i U[i][m] X[i][k] ; rgW[m][k] += sum_i U[i][m] RX[i][k] + UR[i][m] X[i][k]
+// (Ger at lin_tran.go:196,240-241).  One pass: gW and rgW are read and written once.
+template <int NMAX>
+__global__ void __launch_bounds__(kSmallThreads) small_wgrad_kernel(const double* __restrict__ U, const double* __restrict__ UR,
+                                                                    const double* __restrict__ X, const double* __restrict__ RX,
+                                                                    double* __restrict__ gW, double* __restrict__ rgW, int rows,
+                                                                    int cols, int n) {
+  const int m = blockIdx.y;
+  const int k = 2 * (blockIdx.x * kSmallThreads + threadIdx.x);
+  if (k >= cols) return;
+  double2 g = make_double2(0.0, 0.0), rg = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {
+      const double u = U[(long long)i * rows + m];
+      const double2 xv = ld2(X + (long long)i * cols + k);
+      g.x = fma(u, xv.x, g.x); g.y = fma(u, xv.y, g.y);
+      if (rgW) {
+        if (RX) {
+          const double2 rxv = ld2(RX + (long long)i * cols + k);
+          rg.x = fma(u, rxv.x, rg.x); rg.y = fma(u, rxv.y, rg.y);
+        }
+        if (UR) {
+          const double ur = UR[(long long)i * rows + m];
+          rg.x = fma(ur, xv.x, rg.x); rg.y = fma(ur, xv.y, rg.y);
+        }
+      }
+    }
+  }
+  const long long o = (long long)m * cols + k;
+  if (gW) {
+    double2 c = ld2(gW + o);
+    c.x += g.x; c.y += g.y;
+    *reinterpret_cast<double2*>(gW + o) = c;
+  }
+  if (rgW) {
+    double2 c = ld2(rgW + o);
+    c.x += rg.x; c.y += rg.y;
+    *reinterpret_cast<double2*>(rgW + o) = c;
+  }
+}
+
+// ---- input gradient: column-wise reduction over a chunk of weight rows --------------------------
+// D[i][k] = sum_m U[i][m] W[m][k] ; DR[i][k] = sum_m UR[i][m] W[m][k] + U[i][m] RW[m][k]
+// (Gemv T at lin_tran.go:288,333-334).  Thread = column pair, block row = chunk of `mchunk` rows;
+// partial sums go to the zeroed outputs with red.global.add.f64.
+template <int NMAX>
+__global__ void __launch_bounds__(kSmallThreads) small_igrad_kernel(const double* __restrict__ U, const double* __restrict__ UR,
+                                                                    const double* __restrict__ W, const double* __restrict__ RW,
+                                                                    double* __restrict__ D, double* __restrict__ DR, int rows,
+                                                                    int cols, int n, int mchunk) {
+  extern __shared__ double su[];  // U and UR for this row chunk: [2][NMAX][mchunk]
+  const int m0 = blockIdx.y * mchunk;
+  const int mc = min(mchunk, rows - m0);
+  for (int e = threadIdx.x; e < NMAX * mchunk; e += kSmallThreads) {
+    const int i = e / mchunk, mm = e - i * mchunk;
+    const bool ok = i < n && mm < mc;
+    su[e] = ok ? U[(long long)i * rows + m0 + mm] : 0.0;
+    su[NMAX * mchunk + e] = (ok && UR) ? UR[(long long)i * rows + m0 + mm] : 0.0;
+  }
+  __syncthreads();
+  const int k = 2 * (blockIdx.x * kSmallThreads + threadIdx.x);
+  if (k >= cols) return;
+  double2 d[NMAX], dr[NMAX];
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) d[i] = dr[i] = make_double2(0.0, 0.0);
+  for (int mm = 0; mm < mc; ++mm) {
+    const long long wo = (long long)(m0 + mm) * cols + k;
+    const double2 wv = ld2(W + wo);
+    double2 rwv = make_double2(0.0, 0.0);
+    if (RW) rwv = ld2(RW + wo);
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) {
+      if (i < n) {
+        const double u = su[i * mchunk + mm];
+        d[i].x = fma(u, wv.x, d[i].x); d[i].y = fma(u, wv.y, d[i].y);
+        if (DR) {
+          const double ur = su[NMAX * mchunk + i * mchunk + mm];
+          dr[i].x = fma(ur, wv.x, fma(u, rwv.x, dr[i].x));
+          dr[i].y = fma(ur, wv.y, fma(u, rwv.y, dr[i].y));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    if (i < n) {
+      const long long o = (long long)i * cols + k;
+      if (D) { atomicAdd(D + o, d[i].x); atomicAdd(D + o + 1, d[i].y); }
+      if (DR) { atomicAdd(DR + o, dr[i].x); atomicAdd(DR + o + 1, dr[i].y); }
+    }
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+bool small_n_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs) {
+  if (ctx->gemm_path == 1 || ctx->small_n_off) return false;
+  if (n < 1 || n > 8 || (cols & 1) || rows < 1 || cols < 2 || rows > (1 << 30) || cols > (1 << 30)) return false;
+  for (const void* p : ptrs)
+    if (p && !aligned16(p)) return false;
+  return true;
+}
+
+// S (and RS) = epilogue(X W^T + ..., X RW^T + RX W^T + ...); `e` carries bias / activation like gemm_launch's
+int small_fwd_launch(af_ctx* ctx, const double* W, const double* RW, const double* X, const double* RX, long long rows,
+                     long long cols, long long n, const GemmEpilogue& e, bool dual) {
+  GemmArgs a{};
+  a.I = (int)n; a.J = (int)rows; a.Kd = (int)cols;
+  a.epi = e.epi; a.out0 = e.out0; a.out1 = dual ? e.out1 : nullptr; a.ldo = e.ldo;
+  a.bias0 = e.bias0; a.bias1 = e.bias1;
+  int wpr = 1;  // warps per row: enough blocks to cover the chip twice
+  while (wpr < 8 && (rows * wpr + 7) / 8 < 2ll * ctx->sm_count) wpr *= 2;
+  const unsigned blocks = (unsigned)((rows + 8 / wpr - 1) / (8 / wpr));
+  const double* rw = dual ? RW : nullptr;
+  const double* rx = dual ? RX : nullptr;
+  if (n <= 2) small_fwd_kernel<2><<<blocks, kSmallThreads, 0, ctx->stream>>>(W, rw, X, rx, (int)rows, (int)cols, (int)n, wpr, a);
+  else small_fwd_kernel<8><<<blocks, kSmallThreads, 0, ctx->stream>>>(W, rw, X, rx, (int)rows, (int)cols, (int)n, wpr, a);
+  const int products = 1 + (dual ? (rw ? 1 : 0) + (rx ? 1 : 0) : 0);
+  return after_launch(ctx, "small_fwd_kernel", KIND_SMALL_N, 8.0 * rows * cols * (rw ? 2 : 1) + 0.0 * products);
+}
+
+int small_wgrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* X, const double* RX, double* gW,
+                       double* rgW, long long rows, long long cols, long long n) {
+  dim3 grid((unsigned)((cols / 2 + kSmallThreads - 1) / kSmallThreads), (unsigned)rows);
+  if (n <= 2) small_wgrad_kernel<2><<<grid, kSmallThreads, 0, ctx->stream>>>(U, UR, X, RX, gW, rgW, (int)rows, (int)cols, (int)n);
+  else small_wgrad_kernel<8><<<grid, kSmallThreads, 0, ctx->stream>>>(U, UR, X, RX, gW, rgW, (int)rows, (int)cols, (int)n);
+  return after_launch(ctx, "small_wgrad_kernel", KIND_SMALL_N, 16.0 * rows * cols * ((gW ? 1 : 0) + (rgW ? 1 : 0)));
+}
+
+int gemm_deferred_epilogue(af_ctx* ctx, const GemmArgs& logical, bool dual);
+
+int small_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, long long rows,
+                       long long cols, long long n, const GemmEpilogue& e, bool dual) {
+  double* D = e.out0;
+  double* DR = dual ? e.out1 : nullptr;
+  if (D) AF_CUDA(cudaMemsetAsync(D, 0, (size_t)(n * cols) * 8, ctx->stream));
+  if (DR) AF_CUDA(cudaMemsetAsync(DR, 0, (size_t)(n * cols) * 8, ctx->stream));
+  const long long xblocks = (cols / 2 + kSmallThreads - 1) / kSmallThreads;
+  long long ychunks = (2ll * ctx->sm_count + xblocks - 1) / xblocks;
+  if (ychunks > rows) ychunks = rows;
+  if (ychunks < 1) ychunks = 1;
+  int mchunk = (int)((rows + ychunks - 1) / ychunks);
+  if (mchunk > 128) mchunk = 128;
+  dim3 grid((unsigned)xblocks, (unsigned)((rows + mchunk - 1) / mchunk));
+  const double* ur = dual ? UR : nullptr;
+  const double* rw = dual ? RW : nullptr;
+#define AF_SMALL_IGRAD(NM)                                                                                              \
+  small_igrad_kernel<NM><<<grid, kSmallThreads, (size_t)2 * NM * mchunk * 8, ctx->stream>>>(U, ur, W, rw, D, DR, (int)rows, \
+                                                                                            (int)cols, (int)n, mchunk)
+  if (n <= 2) AF_SMALL_IGRAD(2);
+  else AF_SMALL_IGRAD(8);
+#undef AF_SMALL_IGRAD
+  AF_TRY(after_launch(ctx, "small_igrad_kernel", KIND_SMALL_N, 8.0 * rows * cols * (rw ? 2 : 1)));
+  if (e.epi == EPI_STORE) return AF_OK;
+  GemmArgs a{};
+  a.I = (int)n; a.J = (int)cols; a.epi = e.epi; a.out0 = D; a.out1 = DR; a.ldo = e.ldo;
+  a.s = e.s; a.rs = e.rs; a.lds = e.lds;
+  return gemm_deferred_epilogue(ctx, a, dual);
+}
+
+}  // namespace af

@@ -60,6 +60,7 @@ int64_t af_launch_count(af_ctx* ctx);
 #define AF_KIND_GEMM_GENERIC 2  /* generic contraction (operands not TMA-aligned) */
 #define AF_KIND_ELEMENTWISE 3
 #define AF_KIND_REDUCE 4
+#define AF_KIND_SMALL_N 5       /* n <= 16 streaming kernels (the reference's Gemv/Ger branch); work in bytes */
 int af_trace_begin(af_ctx* ctx, int capacity);
 int af_trace_end(af_ctx* ctx, int capacity, int* h_kind, double* h_work, float* h_ms, int* h_count);
 /* Path selector for the LinTran contractions: 0 = auto (TMA + DMMA tensor-core kernel when the
@@ -67,7 +68,9 @@ int af_trace_end(af_ctx* ctx, int capacity, int* h_kind, double* h_work, float* 
  * (returns AF_ENOTSUP instead of falling back). */
 int af_set_gemm_path(af_ctx* ctx, int mode);
 /* Tuning knobs (measurement / A-B runs).  "big_cfg": tile configuration of the DMMA kernel for outputs
- * wider than 16 columns: 0 = 128x64 tile, one CTA per SM; 2 = 64x64 tile, two CTAs per SM.          */
+ * wider than 16 columns: 0 = 128x64 tile, one CTA per SM; 2 = 64x64 tile, two CTAs per SM.
+ * "small_n": 1 (default) = batches of <= 16 samples use the streaming Gemv/Ger kernels, 0 = they go
+ * through the tensor-core kernel (transposed narrow tiles + split-K).                               */
 int af_set_option(af_ctx* ctx, const char* name, int value);
 
 int af_malloc(af_ctx* ctx, int64_t n_doubles, double** d_out);
@@ -191,6 +194,9 @@ int af_mlp_zero_grads(af_mlp*);
  * (Apply + PropagateGradient).  The upstream buffers are consumed (clobbered), as the reference
  * allows (result.go:24-29).  Asynchronous.                                                     */
 int af_mlp_step(af_mlp*, int with_r, int backprop);
+/* Replay the step from a CUDA graph (captured on the second call of a configuration).  On by default for
+ * batches <= 256, where the ~25 short kernels of a step are launch-bound.                          */
+int af_mlp_set_graph(af_mlp*, int enable);
 /* Host-buffer form (the reference-facing call): uploads h_X (n x sizes[0]), h_upstream /
  * h_upstream_r (n x sizes[L]; NULL => ones / zeros as in bench/mlp.go:118-126), zeroes the
  * accumulators, runs the step, and downloads h_out / h_rout (n x sizes[L]) and every gradient and

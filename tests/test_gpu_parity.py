@@ -119,11 +119,14 @@ def _rand(seed, n):
 
 
 @pytest.mark.parametrize("rows,cols,n", SHAPES)
-@pytest.mark.parametrize("path,big_cfg", [(2, 0), (2, 2), (1, 0)])  # 2 = require TMA+DMMA (both tile configs), 1 = generic kernel
-def test_lintran_kernels_match_oracle(api, rows, cols, n, path, big_cfg):
+# path 2 = no generic fallback (tensor-core kernel in both tile configs; n <= 16 takes the streaming Gemv/Ger
+# kernels unless small_n = 0 forces those shapes through the tensor-core kernel too), path 1 = generic kernel
+@pytest.mark.parametrize("path,big_cfg,small_n", [(2, 0, 1), (2, 2, 1), (2, 2, 0), (1, 0, 1)])
+def test_lintran_kernels_match_oracle(api, rows, cols, n, path, big_cfg, small_n):
     ctx = api.context()
     ctx.set_gemm_path(path)
     api.check(ctx.lib.af_set_option(ctx.h, b"big_cfg", big_cfg))
+    api.check(ctx.lib.af_set_option(ctx.h, b"small_n", small_n))
     try:
         W, RW = _rand(1, rows * cols), _rand(2, rows * cols)
         X, RX = _rand(3, n * cols), _rand(4, n * cols)
@@ -174,6 +177,7 @@ def test_lintran_kernels_match_oracle(api, rows, cols, n, path, big_cfg):
     finally:
         ctx.set_gemm_path(0)
         api.check(ctx.lib.af_set_option(ctx.h, b"big_cfg", 2))
+        api.check(ctx.lib.af_set_option(ctx.h, b"small_n", 1))
 
 
 def test_odd_pitch_falls_back_or_refuses(api):
@@ -317,6 +321,14 @@ def test_mlp_plan_matches_oracle(api, scaled, with_r, n):
     api.check(plan.ctx.lib.af_zero(plan.ctx.h, plan.upstream_r().ptr, n * 10))
     plan.step(with_r=with_r)
     close(plan.grad(0).numpy(), 2 * ograd[onet.variables[0]], "accumulated grad[0]")
+    # third and fourth steps: for batches <= 256 these replay the captured CUDA graph of the step
+    for k in (3, 4):
+        api.check(plan.ctx.lib.af_fill(plan.ctx.h, plan.upstream().ptr, 1.0, n * 10))
+        api.check(plan.ctx.lib.af_zero(plan.ctx.h, plan.upstream_r().ptr, n * 10))
+        plan.step(with_r=with_r)
+        close(plan.grad(0).numpy(), k * ograd[onet.variables[0]], f"accumulated grad[0] x{k}")
+        close(plan.grad(5).numpy(), k * ograd[onet.variables[5]], f"accumulated grad[5] x{k}")
+    close(plan.output().numpy(), ores.output(), "Output after graph replay")
     plan.close()
 
 

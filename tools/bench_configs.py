@@ -51,6 +51,14 @@ def mlp_config(ctx, name, sizes, n, steps, flops):
         api.check(ctx.lib.af_zero(ctx.h, upr.ptr, n_out))
         plan.step(True, True)
     ms = timed(step, steps)
+    if os.environ.get("AF_TRACE"):
+        cap = 256
+        kinds, work, msa, cnt = (C.c_int * cap)(), (C.c_double * cap)(), (C.c_float * cap)(), C.c_int(0)
+        api.check(ctx.lib.af_trace_begin(ctx.h, cap))
+        step()
+        api.check(ctx.lib.af_trace_end(ctx.h, cap, kinds, work, msa, C.byref(cnt)))
+        for i in range(cnt.value):
+            print(f"  [{i:2d}] kind={kinds[i]} work={work[i]:.4g} {msa[i] * 1e3:7.1f} us", file=sys.stderr)
     plan.close()
     print(json.dumps({"config": name, "sizes": sizes, "n": n, "ms_per_step": ms, "samples_per_s": n / ms * 1e3,
                       "tflops_executed": flops / ms / 1e9}), flush=True)
@@ -124,12 +132,14 @@ def lstm_config(ctx, I, H, O, T, B, steps):
 
 def main():
     which = set(sys.argv[1:]) or {"c1", "c2", "c3", "c4"}
-    ctx = api.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()  # a real stream (the legacy default stream cannot be graph-captured)
+    torch.cuda.set_stream(stream)
+    ctx = api.Context(0, stream=stream.cuda_stream)
     api.set_context(ctx)
     if "c1" in which:
         lintran_config(ctx, 50)
     if "c2" in which:
-        for n in (1, 64, 1024):
+        for n in (1, 4, 8, 64, 1024):
             mlp_config(ctx, f"C2 mlp n={n}", [1000, 2000, 512, 10], n, 20, executed_flops([1000, 2000, 512, 10], n))
     if "c3" in which:
         s = [2048] * 5
