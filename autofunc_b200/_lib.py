@@ -88,6 +88,10 @@ PROTOTYPES = {
     "af_mlp_step_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),
     "af_mlp_submit_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),
     "af_mlp_wait": (INT, [P]),
+    "af_mlp_submit_compute_host": (INT, [P, INT, H, H, H]),
+    "af_mlp_submit_download_host": (INT, [P, INT, H, H, C.POINTER(H), C.POINTER(H)]),
+    "af_mlp_bind_slot": (INT, [P, INT]),
+    "af_mlp_set_grad_ready": (INT, [P, C.c_void_p, C.c_void_p, INT]),
     "af_copy_2d": (INT, [P, D, I64, D, I64, I64, I64]),
     "af_lstm_create": (INT, [P, I64, I64, I64, I64, I64, C.POINTER(P)]),
     "af_lstm_destroy": (INT, [P]),
@@ -107,6 +111,8 @@ PROTOTYPES = {
     "af_lstm_backward": (INT, [P, INT]),
     "af_lstm_run_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),
 }
+
+GRAD_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64)
 
 _lib = None
 

@@ -388,6 +388,12 @@ struct af_mlp {
   struct StepGraph { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; };
   StepGraph graphs[2][2][2];
   bool use_graph = false;
+  // data-parallel hook: called (on the host, at enqueue time) as soon as the launches that complete a range of
+  // accumulators are on the stream, so the caller can start that range's all-reduce while the rest of the
+  // backward pass runs.  Layer 1's weight gradient -- the largest and the last -- is produced in row chunks.
+  af_grad_ready_fn grad_ready = nullptr;
+  void* grad_ready_user = nullptr;
+  int grad_ready_chunks = 1;
   double* alt = nullptr;  // backing store of slot 1
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   int64_t submitted = 0, waited = 0;
@@ -418,8 +424,12 @@ int af_mlp_create(af_ctx* ctx, const int64_t* sizes, int n_layers, int64_t batch
   int64_t total = 0;
   std::vector<int64_t> off;
   auto take = [&](int64_t len) { off.push_back(total); total += pad(len); };
-  for (int rep = 0; rep < 4; ++rep)
-    for (int i = 0; i < P; ++i) take(m->param_len(i));
+  for (int rep = 0; rep < 2; ++rep)
+    for (int i = 0; i < P; ++i) take(m->param_len(i));  // param, rvec
+  // accumulators, one contiguous block per layer: gW_l, gb_l, rgW_l, rgb_l (a layer's all-reduce is one range)
+  for (int l = 0; l < n_layers; ++l)
+    for (int rep = 0; rep < 2; ++rep)
+      for (int j = 0; j < 2; ++j) take(m->param_len(2 * l + j));
   for (int rep = 0; rep < 2; ++rep)
     for (int l = 0; l <= n_layers; ++l) take(batch * sizes[l]);  // act, ract
   for (int rep = 0; rep < 2; ++rep)
@@ -432,8 +442,11 @@ int af_mlp_create(af_ctx* ctx, const int64_t* sizes, int n_layers, int64_t batch
   auto next = [&]() { return m->slab + off[k++]; };
   for (int i = 0; i < P; ++i) m->param.push_back(next());
   for (int i = 0; i < P; ++i) m->rvec.push_back(next());
-  for (int i = 0; i < P; ++i) m->grad.push_back(next());
-  for (int i = 0; i < P; ++i) m->rgrad.push_back(next());
+  m->grad.resize(P); m->rgrad.resize(P);
+  for (int l = 0; l < n_layers; ++l) {
+    m->grad[2 * l] = next(); m->grad[2 * l + 1] = next();
+    m->rgrad[2 * l] = next(); m->rgrad[2 * l + 1] = next();
+  }
   for (int l = 0; l <= n_layers; ++l) m->act.push_back(next());
   for (int l = 0; l <= n_layers; ++l) m->ract.push_back(next());
   for (int l = 0; l <= n_layers; ++l) m->delta.push_back(next());
@@ -516,6 +529,26 @@ int af_mlp_zero_grads(af_mlp* m) {
 
 static int mlp_step_launches(af_mlp* m, int with_r, int backprop);
 
+static int mlp_pipeline_init(af_mlp* m);
+static void mlp_bind_slot(af_mlp* m, int k);
+
+int af_mlp_set_grad_ready(af_mlp* m, af_grad_ready_fn fn, void* user, int layer1_chunks) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  m->grad_ready = fn;
+  m->grad_ready_user = user;
+  m->grad_ready_chunks = layer1_chunks < 1 ? 1 : layer1_chunks;
+  return AF_OK;
+}
+
+int af_mlp_bind_slot(af_mlp* m, int slot) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  if (slot != 0 && slot != 1) return fail(AF_EINVAL, "slot must be 0 or 1");
+  DeviceGuard guard(m->ctx->device);
+  AF_TRY(mlp_pipeline_init(m));
+  mlp_bind_slot(m, slot);
+  return AF_OK;
+}
+
 int af_mlp_set_graph(af_mlp* m, int enable) {
   if (!m) return fail(AF_EINVAL, "null mlp");
   m->use_graph = enable != 0;
@@ -528,7 +561,7 @@ int af_mlp_step(af_mlp* m, int with_r, int backprop) {
   af_ctx* ctx = m->ctx;
   DeviceGuard guard(ctx->device);
   // the legacy default stream cannot be captured
-  if (!m->use_graph || ctx->tracing || ctx->stream == nullptr || ctx->stream == cudaStreamLegacy)
+  if (!m->use_graph || m->grad_ready || ctx->tracing || ctx->stream == nullptr || ctx->stream == cudaStreamLegacy)
     return mlp_step_launches(m, with_r, backprop);
   af_mlp::StepGraph& g = m->graphs[with_r ? 1 : 0][backprop ? 1 : 0][m->bound_slot];
   if (g.exec) {
@@ -584,7 +617,30 @@ static int mlp_step_launches(af_mlp* m, int with_r, int backprop) {
     AF_TRY(colsum_launch(ctx, U, UR, m->grad[2 * l + 1], R ? m->rgrad[2 * l + 1] : nullptr, rows, n));
     // lin_tran.go:410-418
     const double* RX = (R && l > 0) ? m->ract[l] : nullptr;
-    AF_TRY(af_lintran_wgrad_r(ctx, U, UR, m->act[l], RX, m->grad[2 * l], R ? m->rgrad[2 * l] : nullptr, rows, cols, n));
+    double* gW = m->grad[2 * l];
+    double* rgW = R ? m->rgrad[2 * l] : nullptr;
+    const int chunks = (m->grad_ready && l == 0 && m->grad_ready_chunks > 1) ? m->grad_ready_chunks : 1;
+    if (chunks == 1) {
+      AF_TRY(af_lintran_wgrad_r(ctx, U, UR, m->act[l], RX, gW, rgW, rows, cols, n));
+      if (m->grad_ready)  // the whole layer block gW_l .. rgb_l is complete
+        m->grad_ready(m->grad_ready_user, gW, (l + 1 < L ? m->grad[2 * l + 2] : m->act[0]) - gW);
+    } else {
+      // row chunks of the weight gradient (rows of W = columns of U): each chunk's all-reduce can start while
+      // the next chunk is being computed
+      m->grad_ready(m->grad_ready_user, m->grad[2 * l + 1], m->param_len(2 * l + 1));
+      if (R) m->grad_ready(m->grad_ready_user, m->rgrad[2 * l + 1], m->param_len(2 * l + 1));
+      const int64_t step_rows = ((rows + chunks - 1) / chunks + 63) / 64 * 64;
+      for (int64_t r0 = 0; r0 < rows; r0 += step_rows) {
+        const int64_t rc = rows - r0 < step_rows ? rows - r0 : step_rows;
+        GemmOperand A{U + r0, UR ? UR + r0 : nullptr, LAY_RC, rows};
+        GemmOperand Bop{m->act[l], RX, LAY_RC, cols};
+        GemmEpilogue e;
+        e.epi = EPI_ACCUM; e.out0 = gW + r0 * cols; e.out1 = rgW ? rgW + r0 * cols : nullptr; e.ldo = cols;
+        AF_TRY(gemm_launch(ctx, A, Bop, rgW != nullptr, rc, cols, n, e));
+        m->grad_ready(m->grad_ready_user, gW + r0 * cols, rc * cols);
+        if (rgW) m->grad_ready(m->grad_ready_user, rgW + r0 * cols, rc * cols);
+      }
+    }
     // lin_tran.go:420-423: the input Variable is not in the gradient maps, so layer 1 stops here
     if (l > 0)
       AF_TRY(af_dense_igrad(ctx, U, UR, m->param[2 * l], rv(2 * l), m->act[l], R ? m->ract[l] : nullptr, m->delta[l],
@@ -639,8 +695,8 @@ int af_mlp_wait(af_mlp* m) {
   return AF_OK;
 }
 
-int af_mlp_submit_host(af_mlp* m, int with_r, const double* hX, const double* hU, const double* hUR, double* hOut,
-                       double* hROut, double* const* hGrads, double* const* hRGrads) {
+// Phase 1 of a pipelined step: upload on the copy-in stream, compute on the ctx stream into the next slot.
+int af_mlp_submit_compute_host(af_mlp* m, int with_r, const double* hX, const double* hU, const double* hUR) {
   if (!m) return fail(AF_EINVAL, "null mlp");
   AF_NEED(hX);
   af_ctx* ctx = m->ctx;
@@ -651,7 +707,7 @@ int af_mlp_submit_host(af_mlp* m, int with_r, const double* hX, const double* hU
   af_mlp::Slot& sl = m->slot[k];
   const int L = m->L;
   const int64_t top = m->n * m->sizes[L];
-  // upload on the copy-in stream; the slot's previous user has fully drained (out_done waited above)
+  // the slot's previous user has fully drained (out_done waited above)
   AF_CUDA(cudaMemcpyAsync(sl.x, hX, (size_t)(m->n * m->sizes[0]) * 8, cudaMemcpyHostToDevice, m->copy_in));
   AF_CUDA(cudaEventRecord(sl.in_ready, m->copy_in));
   cudaStream_t st = ctx->stream;
@@ -665,8 +721,23 @@ int af_mlp_submit_host(af_mlp* m, int with_r, const double* hX, const double* hU
   }
   AF_TRY(af_mlp_zero_grads(m));
   AF_TRY(af_mlp_step(m, with_r, 1));
-  AF_CUDA(cudaEventRecord(sl.compute_done, st));
-  // download on the copy-out stream while the next step computes into the other slot
+  sl.busy = true;
+  return AF_OK;
+}
+
+// Phase 2: everything queued on the ctx stream so far (the step, and e.g. the caller's all-reduce of the slot's
+// accumulators) gates the download, which runs on the copy-out stream while the next step computes.
+int af_mlp_submit_download_host(af_mlp* m, int with_r, double* hOut, double* hROut, double* const* hGrads,
+                                double* const* hRGrads) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  af_ctx* ctx = m->ctx;
+  DeviceGuard guard(ctx->device);
+  const int k = (int)(m->submitted & 1);
+  af_mlp::Slot& sl = m->slot[k];
+  if (!sl.busy || !m->copy_out) return fail(AF_EINVAL, "af_mlp_submit_download_host without a pending af_mlp_submit_compute_host");
+  const int L = m->L;
+  const int64_t top = m->n * m->sizes[L];
+  AF_CUDA(cudaEventRecord(sl.compute_done, ctx->stream));
   cudaStream_t co = m->copy_out;
   AF_CUDA(cudaStreamWaitEvent(co, sl.compute_done, 0));
   if (hOut) AF_CUDA(cudaMemcpyAsync(hOut, sl.out, (size_t)top * 8, cudaMemcpyDeviceToHost, co));
@@ -678,9 +749,14 @@ int af_mlp_submit_host(af_mlp* m, int with_r, const double* hX, const double* hU
       AF_CUDA(cudaMemcpyAsync(hRGrads[i], sl.rgrad[i], (size_t)m->param_len(i) * 8, cudaMemcpyDeviceToHost, co));
   }
   AF_CUDA(cudaEventRecord(sl.out_done, co));
-  sl.busy = true;
   m->submitted += 1;
   return AF_OK;
+}
+
+int af_mlp_submit_host(af_mlp* m, int with_r, const double* hX, const double* hU, const double* hUR, double* hOut,
+                       double* hROut, double* const* hGrads, double* const* hRGrads) {
+  AF_TRY(af_mlp_submit_compute_host(m, with_r, hX, hU, hUR));
+  return af_mlp_submit_download_host(m, with_r, hOut, hROut, hGrads, hRGrads);
 }
 
 int af_mlp_step_host(af_mlp* m, int with_r, const double* hX, const double* hU, const double* hUR, double* hOut,

@@ -177,7 +177,7 @@ def gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    from autofunc_b200 import api, parallel, synth
+    from autofunc_b200 import _lib, api, parallel, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,7 +190,8 @@ def gpu_arm(args):
     n = args.batch
     K, W = args.steps, args.warmup
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real stream: everything (kernels, NCCL dependencies, events) is ordered on it
+    torch.cuda.set_stream(stream)
     ctx = api.Context(local_rank, stream=stream.cuda_stream)
     api.set_context(ctx)
     ctx.set_gemm_path(2)  # TMA + DMMA or an error; never a silent fallback
@@ -207,15 +208,36 @@ def gpu_arm(args):
     up, upr = plan.upstream(), plan.upstream_r()
     P = 2 * plan.L
     n_params = sum(plan.param_len(i) for i in range(P))
-    slab = parallel.plan_grad_slab(plan, local_rank) if world > 1 else None  # grad | rgrad, contiguous
+
+    # Data parallel (gradient.go:28-30 across ranks).  Default: one NCCL all-reduce over the contiguous
+    # {grad | rgrad} block after the step.  --overlap k: as soon as a layer's accumulators are complete the
+    # library calls back and their all-reduce starts on NCCL's stream while the backward pass continues.
+    pending, views = [], {}
+
+    def on_grad_ready(_user, ptr, count):
+        key = (ptr, count)
+        t = views.get(key)
+        if t is None:
+            t = views[key] = torch.as_tensor(parallel.CudaArrayView(ptr, count), device=f"cuda:{local_rank}")
+        pending.append(dist.all_reduce(t, async_op=True))
+    cb = _lib.GRAD_READY_FN(on_grad_ready)
+    if world > 1 and args.overlap > 0:
+        api.check(ctx.lib.af_mlp_set_grad_ready(plan.h, C.cast(cb, C.c_void_p), None, args.overlap))
+
+    def finish_reduce():
+        if world > 1:
+            if args.overlap <= 0:
+                parallel.allreduce_sum_(parallel.plan_grad_slab(plan, local_rank))  # one collective over grad | rgrad
+            for w in pending:
+                w.wait()  # the step's stream waits for every range's all-reduce
+            pending.clear()
 
     def step():
         plan.zero_grads()
         api.check(ctx.lib.af_fill(ctx.h, up.ptr, 1.0, n_out))  # fresh upstreams every step
         api.check(ctx.lib.af_zero(ctx.h, upr.ptr, n_out))
         plan.step(True, True)
-        if world > 1:
-            parallel.allreduce_sum_(slab)  # gradient.go:28-30 across ranks
+        finish_reduce()
 
     def barrier():
         if world > 1:
@@ -282,24 +304,16 @@ def gpu_arm(args):
     def e2e_step():
         b = sets[e2e_k[0] & 1]
         e2e_k[0] += 1
-        if world == 1:
-            # the reference-facing host-buffer call, pipelined: upload of step k+1 and download of step k-1
-            # overlap the compute of step k; every step still moves its own inputs and results
-            api.check(ctx.lib.af_mlp_submit_host(plan.h, 1, b["hx"].data_ptr(), None, None, b["hout"].data_ptr(),
-                                                 b["hrout"].data_ptr(), b["g_arr"], b["rg_arr"]))
-        else:
-            api.check(ctx.lib.af_upload(ctx.h, plan.input().ptr, b["hx"].data_ptr(), x_host.size))
-            step()
-            api.check(ctx.lib.af_download(ctx.h, b["hout"].data_ptr(), plan.output().ptr, n_out))
-            api.check(ctx.lib.af_download(ctx.h, b["hrout"].data_ptr(), plan.routput().ptr, n_out))
-            for i in range(P):
-                api.check(ctx.lib.af_download(ctx.h, b["hg"][i].data_ptr(), plan.grad(i).ptr, plan.param_len(i)))
-                api.check(ctx.lib.af_download(ctx.h, b["hrg"][i].data_ptr(), plan.rgrad(i).ptr, plan.param_len(i)))
+        # the reference-facing host-buffer call, pipelined: upload of step k+1 and download of step k-1
+        # overlap the compute (and, for N > 1, the all-reduce) of step k; every step moves its own inputs and results
+        api.check(ctx.lib.af_mlp_submit_compute_host(plan.h, 1, b["hx"].data_ptr(), None, None))
+        finish_reduce()
+        api.check(ctx.lib.af_mlp_submit_download_host(plan.h, 1, b["hout"].data_ptr(), b["hrout"].data_ptr(),
+                                                      b["g_arr"], b["rg_arr"]))
 
     def e2e_drain():
-        if world == 1:
-            api.check(ctx.lib.af_mlp_wait(plan.h))
-            api.check(ctx.lib.af_mlp_wait(plan.h))
+        api.check(ctx.lib.af_mlp_wait(plan.h))
+        api.check(ctx.lib.af_mlp_wait(plan.h))
     for _ in range(max(1, min(W, 3))):
         e2e_step()
     e2e_drain()
@@ -370,6 +384,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=1024, help="samples per CPU-oracle step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--big-cfg", type=int, default=None, help="DMMA tile configuration for wide outputs (0 or 2)")
+    ap.add_argument("--overlap", type=int, default=0,
+                    help="N > 1: 0 = one all-reduce after the step (default); k >= 1 = per-layer all-reduces started from the "
+                         "grad-ready hook while the backward pass runs, layer 1's weight gradient in k row chunks")
     ap.add_argument("--trace", action="store_true", help="print the last step's per-launch device times to stderr")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -215,6 +215,23 @@ int af_mlp_submit_host(af_mlp*, int with_r, const double* h_X, const double* h_u
                        const double* h_upstream_r, double* h_out, double* h_rout,
                        double* const* h_grads, double* const* h_rgrads);
 int af_mlp_wait(af_mlp*);
+/* The same step in two phases, for data-parallel callers: _compute_ uploads and runs the step into the next
+ * slot; the caller may then queue work on the ctx stream that the download must wait for (the NCCL
+ * all-reduce of that slot's accumulators); _download_ queues the device-to-host copies behind it.   */
+int af_mlp_submit_compute_host(af_mlp*, int with_r, const double* h_X, const double* h_upstream,
+                               const double* h_upstream_r);
+int af_mlp_submit_download_host(af_mlp*, int with_r, double* h_out, double* h_rout,
+                                double* const* h_grads, double* const* h_rgrads);
+/* Make slot 0 or 1 (input batch, accumulators, outputs) the one af_mlp_step / af_mlp_*_ptr refer to.   */
+int af_mlp_bind_slot(af_mlp*, int slot);
+/* Data-parallel hook.  During af_mlp_step, `fn(user, d_ptr, n_doubles)` is called on the host as soon as
+ * the launches that complete the accumulator range [d_ptr, d_ptr + n_doubles) are on the ctx stream, so the
+ * caller can start that range's all-reduce (gradient.go:28-30 across ranks) while the rest of the backward
+ * pass runs.  Accumulators are laid out one block per layer (gW, gb, rgW, rgb); layer 1's weight gradient --
+ * the largest, and the last to be produced -- is computed in `layer1_chunks` row chunks, each reported
+ * separately.  fn == NULL removes the hook.                                                          */
+typedef void (*af_grad_ready_fn)(void* user, double* d_ptr, int64_t n_doubles);
+int af_mlp_set_grad_ready(af_mlp*, af_grad_ready_fn fn, void* user, int layer1_chunks);
 
 /* dst[r*ld_dst + c] = src[r*ld_src + c]: the copy behind Concat / Slice of packed batches
  * (slices.go:13-119,130-206) when the parts are interleaved per sample.                          */

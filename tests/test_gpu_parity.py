@@ -362,6 +362,42 @@ def test_mlp_pipelined_host_steps_match_blocking_steps(api):
     plan.close()
 
 
+def test_mlp_grad_ready_hook_covers_accumulators_once(api):
+    """af_mlp_set_grad_ready: the ranges reported during a step tile the accumulator block exactly once (so a
+    data-parallel caller all-reduces every gradient once), layer 1's weight gradient arrives in row chunks,
+    and chunking does not change the results."""
+    import ctypes as C
+    from autofunc_b200 import _lib
+    sizes, n = [128, 320, 64, 10], 300
+    onet = ref.MLP(sizes, weight_scale=lambda k: 1 / np.sqrt(k))
+    plan = api.MLPPlan(sizes, n)
+    for i, v in enumerate(onet.variables):
+        plan.set_param(i, v.vector)
+        plan.set_rvector(i, onet.rvec[v])
+    x = onet.make_input(n)
+    want = plan.step_host(x.vector)
+    ranges = []
+    cb = _lib.GRAD_READY_FN(lambda user, ptr, count: ranges.append((ptr, count)))
+    api.check(plan.ctx.lib.af_mlp_set_grad_ready(plan.h, C.cast(cb, C.c_void_p), None, 4))
+    got = plan.step_host(x.vector)
+    api.check(plan.ctx.lib.af_mlp_set_grad_ready(plan.h, None, None, 1))
+    for a, b in zip(want[2] + want[3], got[2] + got[3]):
+        close(b, a, "gradients with chunked layer-1 weight gradient")
+    base = plan.grad(0).ptr
+    end = plan.input().ptr
+    covered = np.zeros((end - base) // 8, dtype=np.int32)
+    for ptr, count in ranges:
+        assert base <= ptr and ptr + 8 * count <= end
+        covered[(ptr - base) // 8:(ptr - base) // 8 + count] += 1
+    assert covered.max() == 1
+    for i in range(2 * plan.L):  # every gradient and R-gradient element is inside exactly one reported range
+        for vec in (plan.grad(i), plan.rgrad(i)):
+            o = (vec.ptr - base) // 8
+            assert (covered[o:o + vec.n] == 1).all()
+    assert len(ranges) > 2 + 2 * 3  # layer-1 weight gradient came in several chunks
+    plan.close()
+
+
 def test_mlp_plan_missing_rvectors(api):
     """Variables absent from the RVector have zero R (variable.go:85-91; arithmetic_test.go:33-34)."""
     sizes, n = [32, 24, 8], 40
