@@ -458,6 +458,43 @@ def test_full_size_properties(api):
     assert np.isfinite(out).all() and np.isfinite(rout).all()
 
 
+def test_hessian_row_magnitudes_match_oracle(api):
+    """README.md:5 use case (BASELINE config 3 at a size the oracle handles): D = sqrt(mean_p (H v_p)^2) from
+    R-gradients, product vs oracle with identical probes; and (Hv) agrees with a finite difference of gradients."""
+    from autofunc_b200 import hessian
+    sizes, n, probes = [24, 32, 16, 6], 20, 3
+    onet = ref.MLP(sizes, weight_scale=lambda k: 1 / np.sqrt(k))
+    plan = api.MLPPlan(sizes, n)
+    for i, v in enumerate(onet.variables):
+        plan.set_param(i, v.vector)
+    x = onet.make_input(n)
+    got = hessian.hessian_row_magnitudes(plan, x.vector, probes, seed=7)
+    acc = [np.zeros(v.vector.size) for v in onet.variables]
+    for p in range(probes):
+        vs = hessian.probe_vectors(plan, 7, p)
+        onet.rvec = {v: vs[i] for i, v in enumerate(onet.variables)}
+        _, _, rgrad = onet.step_r(x, n)
+        for i, v in enumerate(onet.variables):
+            acc[i] += rgrad[v] ** 2 / probes
+    for i in range(len(acc)):
+        close(got[i], np.sqrt(acc[i]), f"row magnitudes of parameter {i}")
+    # Hv against a central difference of the (exact) gradient along v: the R-operator's defining property
+    d = 1e-6
+    base = [v.vector.copy() for v in onet.variables]
+    gs = []
+    for sgn in (1, -1):
+        for v, b0 in zip(onet.variables, base):
+            v.vector[:] = b0 + sgn * d * onet.rvec[v]
+        gs.append(onet.step(x, n)[1])
+    for v, b0 in zip(onet.variables, base):
+        v.vector[:] = b0
+    _, _, rgrad = onet.step_r(x, n)
+    for v in onet.variables:
+        fd = (gs[0][v] - gs[1][v]) / (2 * d)
+        assert np.abs(fd - rgrad[v]).max() < 1e-6 * max(1.0, np.abs(rgrad[v]).max())
+    plan.close()
+
+
 # ---- error behaviour (SURVEY 5: panics with fixed strings -> ShapeError with the same text) -------
 def test_shape_errors(api):
     w = api.Variable(np.zeros(12))
