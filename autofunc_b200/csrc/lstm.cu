@@ -8,8 +8,8 @@
 // does not depend on the recurrence is batched over all T*B rows: the output layer, its backward, and
 // every weight / bias gradient (contraction over T*B samples instead of T launches).
 //
-//   forward  t = 0..T-1 :  G_t = sigmoid(IN_t W4^T + b4)            [af_dense_fwd, 4H x (H+I), n = B]
-//                          s_t = f.s_{t-1} + m.i ; masked = s_t.o   [lstm_cell_fwd_kernel]
+//   forward  t = 0..T-1 :  Z_t = IN_t W4^T (+ R form)               [dual contraction, 4H x (H+I), n = B]
+//                          G_t = sigmoid(Z_t + b4) ; s_t = f.s_{t-1} + m.i ; masked = s_t.o   [lstm_cell_fwd_kernel]
 //            after loop  :  RES = sigmoid(AUG Wout^T + bout)         [af_dense_fwd, n = T*B]
 //   backward before loop:  dOut = sigmoid'(RES) up ; gWout, gbout ; dAUG = dOut Wout
 //            t = T-1..0  :  delta4_t, sg' = sg.f                      [lstm_cell_bwd_kernel]
@@ -39,7 +39,11 @@ __global__ void __launch_bounds__(256) copy2d_kernel(double* __restrict__ dst, l
 //   s = f*sp + m*i            Add(Mul(forget, state), Mul(inMask, inState))   bench/lstm.go:147-150
 //   masked = s*o              Mul(outStateVar, outGate)                       bench/lstm.go:191
 // R forms follow MulR (arithmetic.go:325-329: x*yR + xR*y) and AddR (:58-65).
-__global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(const double* __restrict__ G, const double* __restrict__ RG,
+// On entry G / RG hold the four gates' raw contraction sums (IN W4^T and its R form); the kernel adds
+// the biases (lin_add.go:15-17,37-42), applies the sigmoid and its R form (math_funcs.go:305-309) and
+// stores the activated gates back for the backward pass -- the gate contraction needs no epilogue pass.
+__global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(double* __restrict__ G, double* __restrict__ RG,
+                                                            const double* __restrict__ b4, const double* __restrict__ Rb4,
                                                             const double* __restrict__ INp, const double* __restrict__ RINp,
                                                             double* __restrict__ INn, double* __restrict__ RINn,
                                                             double* __restrict__ AUG, double* __restrict__ RAUG, int B,
@@ -47,16 +51,20 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(const double* __rest
   const int n = B * H;
   for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += gridDim.x * 256) {
     const int b = e / H, j = e - b * H;
-    const double* g = G + (long long)b * 4 * H;
-    const double i = g[j], m = g[H + j], f = g[2 * H + j], o = g[3 * H + j];
+    double* g = G + (long long)b * 4 * H;
+    const double i = sigmoid_f64(g[j] + b4[j]), m = sigmoid_f64(g[H + j] + b4[H + j]);
+    const double f = sigmoid_f64(g[2 * H + j] + b4[2 * H + j]), o = sigmoid_f64(g[3 * H + j] + b4[3 * H + j]);
+    g[j] = i; g[H + j] = m; g[2 * H + j] = f; g[3 * H + j] = o;
     const long long si = (long long)b * ld + j;
     const double sp = INp[si];
     const double s = f * sp + m * i;
     INn[si] = s;
     AUG[si] = s * o;
     if (RG) {
-      const double* rg = RG + (long long)b * 4 * H;
-      const double ri = rg[j], rm = rg[H + j], rf = rg[2 * H + j], ro = rg[3 * H + j];
+      double* rg = RG + (long long)b * 4 * H;
+      const double ri = i * (1 - i) * (rg[j] + Rb4[j]), rm = m * (1 - m) * (rg[H + j] + Rb4[H + j]);
+      const double rf = f * (1 - f) * (rg[2 * H + j] + Rb4[2 * H + j]), ro = o * (1 - o) * (rg[3 * H + j] + Rb4[3 * H + j]);
+      rg[j] = ri; rg[H + j] = rm; rg[2 * H + j] = rf; rg[3 * H + j] = ro;
       const double rsp = RINp[si];
       const double rs = (f * rsp + rf * sp) + (m * ri + rm * i);
       RINn[si] = rs;
@@ -292,11 +300,13 @@ int af_lstm_forward(af_lstm* m, int with_r) {
     double* RINt = m->RIN + t * BC;
     double* Gt = m->G + t * B * 4 * H;
     double* RGt = m->RG + t * B * 4 * H;
-    // all four gates in one fused contraction (R-state of step 0 is identically zero: skip its product)
-    AF_TRY(af_dense_fwd(ctx, m->W4, R ? m->RW4 : nullptr, m->b4, R ? m->Rb4 : nullptr, INt, (R && t > 0) ? RINt : nullptr, Gt,
-                        R ? RGt : nullptr, 4 * H, C, B, 1));
+    // all four gates in one contraction (R-state of step 0 is identically zero: skip its product); bias and
+    // sigmoid are applied by the cell kernel, so a split / stream-K launch needs no separate epilogue pass
+    if (R) AF_TRY(af_lintran_fwd_r(ctx, m->W4, m->RW4, INt, t > 0 ? RINt : nullptr, Gt, RGt, 4 * H, C, B));
+    else AF_TRY(af_lintran_fwd(ctx, m->W4, INt, Gt, 4 * H, C, B));
     lstm_cell_fwd_kernel<<<ew_grid(ctx, B * H), 256, 0, ctx->stream>>>(
-        Gt, R ? RGt : nullptr, INt, RINt, INt + BC, RINt + BC, m->AUG + t * BC, m->RAUG + t * BC, (int)B, (int)H, (int)C);
+        Gt, R ? RGt : nullptr, m->b4, m->Rb4, INt, RINt, INt + BC, RINt + BC, m->AUG + t * BC, m->RAUG + t * BC, (int)B,
+        (int)H, (int)C);
     AF_TRY(after_launch(ctx, "lstm_cell_fwd_kernel", KIND_ELEMENTWISE, (R ? 2.0 : 1.0) * 7 * 8 * B * H));
   }
   // output layer for every step at once (lstm.go:193-194)
