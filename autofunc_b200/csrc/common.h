@@ -86,6 +86,7 @@ struct GemmEpilogue {
   const double* s = nullptr;
   const double* rs = nullptr;
   long long lds = 0;
+  bool prezeroed = false;  // store-type outputs are already zero: a split / stream-K launch may skip its memsets
 };
 // acc0 = A0 B0^T ; acc1 = A0 B1^T + A1 B0^T (dual when `dual`), I x J, contraction Kd
 int gemm_launch(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool dual, long long I, long long J,

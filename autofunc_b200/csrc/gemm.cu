@@ -200,8 +200,8 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
     if (!accumulate) {
       deferred = true;
       const size_t bytes = (size_t)logical.I * logical.J * 8;
-      if (args.out0) AF_CUDA(cudaMemsetAsync(args.out0, 0, bytes, ctx->stream));
-      if (args.out1) AF_CUDA(cudaMemsetAsync(args.out1, 0, bytes, ctx->stream));
+      if (args.out0 && !e.prezeroed) AF_CUDA(cudaMemsetAsync(args.out0, 0, bytes, ctx->stream));
+      if (args.out1 && !e.prezeroed) AF_CUDA(cudaMemsetAsync(args.out1, 0, bytes, ctx->stream));
     }
     args.epi = EPI_ACCUM_ATOMIC;
   }

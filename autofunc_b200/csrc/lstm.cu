@@ -148,6 +148,9 @@ struct af_lstm {
   double *D4, *RD4;      // T x B x 4H
   double *SG[2], *RSG[2];
   int64_t grad_doubles = 0;
+  // CUDA-graph replay of the two time loops (hundreds of short dependent launches): [with_r][fwd/bwd]
+  struct LoopGraph { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; };
+  LoopGraph graphs[2][2];
   int64_t param_len(int idx) const {
     const int k = idx / 2;
     const int64_t rows = k < 4 ? H : O;
@@ -220,6 +223,9 @@ int af_lstm_destroy(af_lstm* m) {
   if (!m) return AF_OK;
   DeviceGuard guard(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  for (auto& a : m->graphs)
+    for (auto& g : a)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
   cudaFree(m->slab);
   delete m;
   return AF_OK;
@@ -285,13 +291,68 @@ int af_lstm_set_inputs(af_lstm* m, const double* d_x) {
   return af_copy_2d(ctx, m->AUG + m->H, m->C, d_x, m->I, TB, m->I);
 }
 
+}  // extern "C"
+
+// Runs `body` eagerly the first time, captures it into a CUDA graph the second time and replays it afterwards.
+template <typename F>
+static int lstm_graphed(af_lstm* m, af_lstm::LoopGraph& g, F body) {
+  af_ctx* ctx = m->ctx;
+  if (ctx->tracing || ctx->stream == nullptr || ctx->stream == cudaStreamLegacy || g.seen < 0) return body();
+  if (g.exec) {
+    AF_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+    ctx->launches += g.launches;
+    return AF_OK;
+  }
+  if (g.seen++ == 0) return body();
+  const int64_t before = ctx->launches;
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    g.seen = -1;  // this stream cannot be captured: stay eager
+    return body();
+  }
+  const int rc = body();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+  if (rc != AF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+  g.launches = ctx->launches - before;
+  ctx->launches = before;
+  const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) { g.exec = nullptr; g.seen = -1; cudaGetLastError(); return body(); }
+  AF_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+  ctx->launches += g.launches;
+  return AF_OK;
+}
+
+static int lstm_forward_launches(af_lstm* m, int with_r);
+static int lstm_backward_launches(af_lstm* m, int with_r);
+
+extern "C" {
+
 int af_lstm_forward(af_lstm* m, int with_r) {
   if (!m) return fail(AF_EINVAL, "null lstm");
+  DeviceGuard guard(m->ctx->device);
+  return lstm_graphed(m, m->graphs[with_r ? 1 : 0][0], [&]() { return lstm_forward_launches(m, with_r); });
+}
+
+int af_lstm_backward(af_lstm* m, int with_r) {
+  if (!m) return fail(AF_EINVAL, "null lstm");
+  DeviceGuard guard(m->ctx->device);
+  return lstm_graphed(m, m->graphs[with_r ? 1 : 0][1], [&]() { return lstm_backward_launches(m, with_r); });
+}
+
+}  // extern "C"
+
+static int lstm_forward_launches(af_lstm* m, int with_r) {
   af_ctx* ctx = m->ctx;
-  DeviceGuard guard(ctx->device);
   const int64_t H = m->H, C = m->C, B = m->B, T = m->T, O = m->O;
   const bool R = with_r != 0;
   const int64_t BC = B * C;
+  // the gate sums of every step are accumulated into zeroed buffers when the contraction is split: clear all
+  // T steps at once instead of two memsets per step
+  AF_CUDA(cudaMemsetAsync(m->G, 0, (size_t)(T * B * 4 * H) * 8, ctx->stream));
+  if (R) AF_CUDA(cudaMemsetAsync(m->RG, 0, (size_t)(T * B * 4 * H) * 8, ctx->stream));
   // initial state is zero (lstm.go:175) with zero R
   AF_CUDA(cudaMemset2DAsync(m->IN, C * 8, 0, H * 8, B, ctx->stream));
   if (R) AF_CUDA(cudaMemset2DAsync(m->RIN, C * 8, 0, H * 8, B, ctx->stream));
@@ -302,8 +363,13 @@ int af_lstm_forward(af_lstm* m, int with_r) {
     double* RGt = m->RG + t * B * 4 * H;
     // all four gates in one contraction (R-state of step 0 is identically zero: skip its product); bias and
     // sigmoid are applied by the cell kernel, so a split / stream-K launch needs no separate epilogue pass
-    if (R) AF_TRY(af_lintran_fwd_r(ctx, m->W4, m->RW4, INt, t > 0 ? RINt : nullptr, Gt, RGt, 4 * H, C, B));
-    else AF_TRY(af_lintran_fwd(ctx, m->W4, INt, Gt, 4 * H, C, B));
+    {
+      GemmOperand A{INt, (R && t > 0) ? RINt : nullptr, LAY_KC, C};
+      GemmOperand Bop{m->W4, R ? m->RW4 : nullptr, LAY_KC, C};
+      GemmEpilogue e;
+      e.epi = EPI_STORE; e.out0 = Gt; e.out1 = R ? RGt : nullptr; e.ldo = 4 * H; e.prezeroed = true;
+      AF_TRY(gemm_launch(ctx, A, Bop, R, B, 4 * H, C, e));
+    }
     lstm_cell_fwd_kernel<<<ew_grid(ctx, B * H), 256, 0, ctx->stream>>>(
         Gt, R ? RGt : nullptr, m->b4, m->Rb4, INt, RINt, INt + BC, RINt + BC, m->AUG + t * BC, m->RAUG + t * BC, (int)B,
         (int)H, (int)C);
@@ -314,10 +380,8 @@ int af_lstm_forward(af_lstm* m, int with_r) {
                       m->RES, R ? m->RRES : nullptr, O, C, T * B, 1);
 }
 
-int af_lstm_backward(af_lstm* m, int with_r) {
-  if (!m) return fail(AF_EINVAL, "null lstm");
+static int lstm_backward_launches(af_lstm* m, int with_r) {
   af_ctx* ctx = m->ctx;
-  DeviceGuard guard(ctx->device);
   const int64_t H = m->H, C = m->C, B = m->B, T = m->T, O = m->O;
   const bool R = with_r != 0;
   const int64_t TB = T * B, BC = B * C;
@@ -354,6 +418,8 @@ int af_lstm_backward(af_lstm* m, int with_r) {
   AF_TRY(colsum_launch(ctx, m->D4, R ? m->RD4 : nullptr, m->gb4, R ? m->rgb4 : nullptr, 4 * H, TB));
   return af_lintran_wgrad_r(ctx, m->D4, R ? m->RD4 : nullptr, m->IN, R ? m->RIN : nullptr, m->gW4, R ? m->rgW4 : nullptr, 4 * H, C, TB);
 }
+
+extern "C" {
 
 // Host-buffer form of one bench iteration (bench/lstm.go:41-48): upload inputs (T x B x I) and the
 // per-step output gradients (T x B x O; h_upstreams_r may be NULL = zeros), zero the accumulators,

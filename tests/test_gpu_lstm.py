@@ -71,6 +71,14 @@ def test_lstm_matches_oracle(api, I, H, O, T, B, scale, with_r):
         close(grads[i], grad[v], f"grad[{i}]")
         if with_r:
             close(rgrads[i], rgrad[v], f"rgrad[{i}]")
+    # second run captures the time loops into CUDA graphs, third replays them: same results
+    for rep in (2, 3):
+        out2, rout2, grads2, rgrads2 = plan.run_host(x, up, upr, with_r=with_r)
+        close(out2.reshape(T, B, O), outs, f"outputs (run {rep})")
+        for i, v in enumerate(net.variables):
+            close(grads2[i], grad[v], f"grad[{i}] (run {rep})")
+            if with_r:
+                close(rgrads2[i], rgrad[v], f"rgrad[{i}] (run {rep})")
     plan.close()
 
 
