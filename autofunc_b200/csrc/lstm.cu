@@ -3,7 +3,7 @@
 //
 // Structure.  The four gate matrices share one input, concat(state, x)
 // (bench/lstm.go:140,188), so they are stored stacked as one (4H) x (H+I) matrix W4 and evaluated by
-// ONE fused contraction per time step (+bias, sigmoid, and the R forms in the epilogue); the cell
+// ONE contraction per time step; bias, sigmoid and their R forms are applied by the cell kernel; the cell
 // algebra (Mul/Add, arithmetic.go:17-96,261-376) is one pointwise kernel per step.  Everything that
 // does not depend on the recurrence is batched over all T*B rows: the output layer, its backward, and
 // every weight / bias gradient (contraction over T*B samples instead of T launches).
