@@ -966,3 +966,760 @@ class LSTMNet:
             out_states[t].propagate_rgradient(sg, sgr, rgrad, grad)
             sg, sgr = grad.pop(in_states[t].variable), rgrad.pop(in_states[t].variable)
         return [o.output() for o in outputs], [o.routput() for o in outputs], grad, rgrad
+
+
+# ======================================================================================
+# SURVEY 8(f) "next" rows: the callers / cost heads either side of the dense path
+# ======================================================================================
+# math_funcs.go: Log, LogSigmoid, Sin, Cos, Norm, Softmax
+# --------------------------------------------------------------------------------------
+class Log(_ElementwiseFunc):  # math_funcs.go:99-189
+    def apply(self, inp):
+        return _LogResult(np.log(inp.output()), inp)
+
+    def apply_r(self, rv, inp):
+        x = inp.output()
+        return _LogRResult(np.log(x), inp.routput() / x, inp)
+
+
+class _LogResult(_UnaryResult):
+    def propagate_gradient(self, upstream, grad):  # math_funcs.go:144-153
+        if not self.input.constant(grad):
+            upstream *= 1 / self.input.output()
+            self.input.propagate_gradient(upstream, grad)
+
+
+class _LogRResult(_UnaryRResult):
+    def propagate_rgradient(self, upstream, upstream_r, rgrad, grad):  # math_funcs.go:173-189
+        if self.input.constant(rgrad, grad):
+            return
+        x, xr = self.input.output(), self.input.routput()
+        u, ur = upstream.copy(), upstream_r.copy()
+        upstream[:] = u / x
+        upstream_r[:] = ur / x - u * xr / (x * x)
+        self.input.propagate_rgradient(upstream, upstream_r, rgrad, grad)
+
+
+class LogSigmoid(_ElementwiseFunc):  # math_funcs.go:376-477
+    @staticmethod
+    def _ls(x):  # math_funcs.go:399-410: the branch avoids the log of a big number
+        with np.errstate(over="ignore"):
+            return np.where(x > 0, -np.log(1 + np.exp(-x)), x - np.log(1 + np.exp(x)))
+
+    def apply(self, inp):
+        return _LogSigmoidResult(self._ls(inp.output()), inp)
+
+    def apply_r(self, rv, inp):
+        x = inp.output()
+        return _LogSigmoidRResult(self._ls(x), inp.routput() / (1 + np.exp(x)), inp)
+
+
+class _LogSigmoidResult(_UnaryResult):
+    def propagate_gradient(self, upstream, grad):  # math_funcs.go:433-440
+        if not self.input.constant(grad):
+            upstream /= 1 + np.exp(self.input.output())
+            self.input.propagate_gradient(upstream, grad)
+
+
+class _LogSigmoidRResult(_UnaryRResult):
+    def propagate_rgradient(self, upstream, upstream_r, rgrad, grad):  # math_funcs.go:460-477
+        if self.input.constant(rgrad, grad):
+            return
+        x, xr = self.input.output(), self.input.routput()
+        u, ur = upstream.copy(), upstream_r.copy()
+        ex = np.exp(x)
+        s = 1 / (1 + ex)
+        upstream[:] = u * s
+        upstream_r[:] = ur * s - u * s * s * ex * xr
+        self.input.propagate_rgradient(upstream, upstream_r, rgrad, grad)
+
+
+class Sin(_ElementwiseFunc):  # math_funcs.go:511-597
+    def apply(self, inp):
+        return _SinResult(np.sin(inp.output()), inp)
+
+    def apply_r(self, rv, inp):
+        x = inp.output()
+        return _SinRResult(np.sin(x), np.cos(x) * inp.routput(), inp)
+
+
+class _SinResult(_UnaryResult):
+    def propagate_gradient(self, upstream, grad):  # math_funcs.go:556-563
+        if not self.input.constant(grad):
+            upstream *= np.cos(self.input.output())
+            self.input.propagate_gradient(upstream, grad)
+
+
+class _SinRResult(_UnaryRResult):
+    def propagate_rgradient(self, upstream, upstream_r, rgrad, grad):  # math_funcs.go:583-597
+        if self.input.constant(rgrad, grad):
+            return
+        c = np.cos(self.input.output())
+        cd = -self.output_vec * self.input.routput()
+        upstream_r[:] = upstream_r * c + upstream * cd
+        upstream *= c
+        self.input.propagate_rgradient(upstream, upstream_r, rgrad, grad)
+
+
+class Cos(_ElementwiseFunc):  # math_funcs.go:599-607
+    def apply(self, inp):
+        return Sin().apply(add_scaler(inp, np.pi / 2))
+
+    def apply_r(self, rv, inp):
+        return Sin().apply_r(rv, add_scaler_r(inp, np.pi / 2))
+
+
+class Tanh(_ElementwiseFunc):
+    """EXTENSION named by BASELINE.json's north_star; the reference has no Tanh.
+    Defined by the same pattern as Sigmoid (math_funcs.go:286-374) with t' = 1 - t^2."""
+
+    def apply(self, inp):
+        return _TanhResult(np.tanh(inp.output()), inp)
+
+    def apply_r(self, rv, inp):
+        t = np.tanh(inp.output())
+        return _TanhRResult(t, (1 - t * t) * inp.routput(), inp)
+
+
+class _TanhResult(_UnaryResult):
+    def propagate_gradient(self, upstream, grad):
+        if not self.input.constant(grad):
+            t = self.output_vec
+            upstream *= 1 - t * t
+            self.input.propagate_gradient(upstream, grad)
+
+
+class _TanhRResult(_UnaryRResult):
+    def propagate_rgradient(self, upstream, upstream_r, rgrad, grad):
+        if self.input.constant(rgrad, grad):
+            return
+        t, tr = self.output_vec, self.routput_vec
+        u = upstream.copy()
+        upstream[:] = (1 - t * t) * u
+        upstream_r[:] = (1 - t * t) * upstream_r - 2 * t * tr * u
+        self.input.propagate_rgradient(upstream, upstream_r, rgrad, grad)
+
+
+class Norm(_ElementwiseFunc):  # math_funcs.go:201-284
+    def apply(self, inp):
+        return _NormResult(vec([np.sqrt(_seq_sum(inp.output() ** 2))]), inp)
+
+    def apply_r(self, rv, inp):
+        x = inp.output()
+        out = np.sqrt(_seq_sum(x ** 2))
+        return _NormRResult(vec([out]), vec([(1 / out) * _seq_sum(x * inp.routput())]), inp)
+
+
+class _NormResult(_UnaryResult):
+    def propagate_gradient(self, u, g):  # math_funcs.go:238-247
+        if not self.constant(g):
+            self.input.propagate_gradient(self.input.output() * (u[0] / self.output_vec[0]), g)
+
+
+class _NormRResult(_UnaryRResult):
+    def propagate_rgradient(self, u, ur, rg, g):  # math_funcs.go:267-284
+        if self.constant(rg, g):
+            return
+        o, ro = self.output_vec[0], self.routput_vec[0]
+        s = u[0] / o
+        sr = -u[0] * ro / (o * o) + ur[0] / o
+        x = self.input.output()
+        self.input.propagate_rgradient(x * s, x * sr + self.input.routput() * s, rg, g)
+
+
+class Softmax(_ElementwiseFunc):  # math_funcs.go:479-509 (whole-vector; composed exactly as the reference)
+    def __init__(self, temperature: float = 0.0):
+        self.temperature = float(temperature)
+
+    def apply(self, inp):
+        scaled = inp
+        if self.temperature != 0 and self.temperature != 1:
+            scaled = scale(inp, 1 / self.temperature)
+        exps = Exp().apply(scaled)
+        return pool(exps, lambda e: scale_first(e, inverse(sum_all(e))))
+
+    def apply_r(self, rv, inp):
+        scaled = inp
+        if self.temperature != 0 and self.temperature != 1:
+            scaled = scale_r(inp, 1 / self.temperature)
+        exps = Exp().apply_r(rv, scaled)
+        # math_funcs.go:506-507 sums the OUTER exps, not the pooled input: kept as written
+        return pool_r(exps, lambda e: scale_first_r(exps, inverse_r(sum_all_r(exps))))
+
+    # the batched form is RFuncBatcher{Softmax} (batcher.go:57-84): one softmax per sample
+    def batch(self, inp, n):
+        return RFuncBatcher(self).batch(inp, n)
+
+    def batch_r(self, rv, inp, n):
+        return RFuncBatcher(self).batch_r(rv, inp, n)
+
+
+# --------------------------------------------------------------------------------------
+# arithmetic.go: AddScaler, Div, ScaleFirst, AddFirst, Inverse, Pow, log-domain sums
+# --------------------------------------------------------------------------------------
+class _AddScaler(_UnaryResult):  # arithmetic.go:184-214
+    def propagate_gradient(self, upstream, grad):
+        self.input.propagate_gradient(upstream, grad)
+
+
+class _AddScalerR(_UnaryRResult):  # arithmetic.go:216-252
+    def propagate_rgradient(self, upstream, upstream_r, rgrad, grad):
+        self.input.propagate_rgradient(upstream, upstream_r, rgrad, grad)
+
+
+def add_scaler(r, f):
+    return _AddScaler(r.output() + f, r)
+
+
+def add_scaler_r(r, f):
+    return _AddScalerR(r.output() + f, r.routput(), r)
+
+
+class _Quotient(_Binary):  # arithmetic.go:378-423
+    def propagate_gradient(self, u, g):
+        den = self.r2.output()
+        if not self.r1.constant(g):
+            self.r1.propagate_gradient(u / den, g)
+        if not self.r2.constant(g):
+            u *= -self.output_vec / den
+            self.r2.propagate_gradient(u, g)
+
+
+def div(a, b):
+    return _Quotient(a.output() / b.output(), a, b)
+
+
+def div_r(a, b):  # arithmetic.go:425-427
+    return mul_r(a, inverse_r(b))
+
+
+class _ScaleFirst:  # arithmetic.go:495-533
+    def __init__(self, inp, scaler):
+        self.input, self.scaler = inp, scaler
+        self.output_vec = inp.output() * scaler.output()[0]
+
+    def output(self):
+        return self.output_vec
+
+    def constant(self, g):
+        return self.input.constant(g) and self.scaler.constant(g)
+
+    def propagate_gradient(self, upstream, grad):
+        if not self.scaler.constant(grad):
+            down = np.zeros(len(self.scaler.output()), dtype=F64)
+            down[0] = np.dot(upstream, self.input.output())
+            self.scaler.propagate_gradient(down, grad)
+        if not self.input.constant(grad):
+            upstream *= self.scaler.output()[0]
+            self.input.propagate_gradient(upstream, grad)
+
+
+class _ScaleFirstR:  # arithmetic.go:535-593
+    def __init__(self, inp, scaler):
+        self.input, self.scaler = inp, scaler
+        f, fr = scaler.output()[0], scaler.routput()[0]
+        self.output_vec = inp.output() * f
+        self.routput_vec = inp.output() * fr + inp.routput() * f
+
+    def output(self):
+        return self.output_vec
+
+    def routput(self):
+        return self.routput_vec
+
+    def constant(self, rg, g):
+        return self.input.constant(rg, g) and self.scaler.constant(rg, g)
+
+    def propagate_rgradient(self, upstream, upstream_r, rgrad, grad):
+        if not self.scaler.constant(rgrad, grad):
+            down = np.zeros(len(self.scaler.output()), dtype=F64)
+            down_r = np.zeros(len(self.scaler.output()), dtype=F64)
+            down[0] = np.dot(upstream, self.input.output())
+            down_r[0] = np.dot(upstream_r, self.input.output()) + np.dot(upstream, self.input.routput())
+            self.scaler.propagate_rgradient(down, down_r, rgrad, grad)
+        if not self.input.constant(rgrad, grad):
+            f, fr = self.scaler.output()[0], self.scaler.routput()[0]
+            upstream_r[:] = upstream_r * f + upstream * fr
+            upstream *= f
+            self.input.propagate_rgradient(upstream, upstream_r, rgrad, grad)
+
+
+def scale_first(inp, scaler):
+    return _ScaleFirst(inp, scaler)
+
+
+def scale_first_r(inp, scaler):
+    return _ScaleFirstR(inp, scaler)
+
+
+class _AddFirst:  # arithmetic.go:595-639
+    def __init__(self, v1, v2):
+        self.input, self.scaler = v1, v2
+        self.output_vec = v1.output() + v2.output()[0]
+
+    def output(self):
+        return self.output_vec
+
+    def constant(self, g):
+        return self.input.constant(g) and self.scaler.constant(g)
+
+    def propagate_gradient(self, upstream, g):
+        if not self.scaler.constant(g):
+            su = np.zeros(len(self.scaler.output()), dtype=F64)
+            su[0] = _seq_sum(upstream)
+            self.scaler.propagate_gradient(su, g)
+        if not self.input.constant(g):
+            self.input.propagate_gradient(upstream, g)
+
+
+class _AddFirstR:  # arithmetic.go:641-694
+    def __init__(self, v1, v2):
+        self.input, self.scaler = v1, v2
+        self.output_vec = v1.output() + v2.output()[0]
+        self.routput_vec = v1.routput() + v2.routput()[0]
+
+    def output(self):
+        return self.output_vec
+
+    def routput(self):
+        return self.routput_vec
+
+    def constant(self, rg, g):
+        return self.input.constant(rg, g) and self.scaler.constant(rg, g)
+
+    def propagate_rgradient(self, upstream, upstream_r, rg, g):
+        if not self.scaler.constant(rg, g):
+            su = np.zeros(len(self.scaler.output()), dtype=F64)
+            sur = np.zeros(len(self.scaler.output()), dtype=F64)
+            su[0], sur[0] = _seq_sum(upstream), _seq_sum(upstream_r)
+            self.scaler.propagate_rgradient(su, sur, rg, g)
+        if not self.input.constant(rg, g):
+            self.input.propagate_rgradient(upstream, upstream_r, rg, g)
+
+
+def add_first(v1, v2):
+    return _AddFirst(v1, v2)
+
+
+def add_first_r(v1, v2):
+    return _AddFirstR(v1, v2)
+
+
+class _Inverse(_UnaryResult):  # arithmetic.go:772-807
+    def propagate_gradient(self, upstream, grad):
+        if not self.input.constant(grad):
+            o = self.output_vec
+            upstream *= -o * o
+            self.input.propagate_gradient(upstream, grad)
+
+
+class _InverseR(_UnaryRResult):  # arithmetic.go:809-867
+    def propagate_rgradient(self, upstream, upstream_r, rgrad, grad):
+        if self.input.constant(rgrad, grad):
+            return
+        o = self.output_vec
+        sq = -(o * o)
+        u = upstream.copy()
+        upstream[:] = sq * u
+        upstream_r[:] = sq * upstream_r + -2 * (sq * o) * self.input.routput() * u
+        self.input.propagate_rgradient(upstream, upstream_r, rgrad, grad)
+
+
+def inverse(r):
+    return _Inverse(1 / r.output(), r)
+
+
+def inverse_r(r):
+    rec = 1 / r.output()
+    return _InverseR(rec, -(rec * rec) * r.routput(), r)
+
+
+class _Pow(_UnaryResult):  # arithmetic.go:869-906
+    power = 1.0
+
+    def constant(self, g):
+        return self.power != 0 and self.input.constant(g)
+
+    def propagate_gradient(self, upstream, grad):
+        if not self.constant(grad):
+            if self.power != 1:
+                upstream *= self.power * np.power(self.input.output(), self.power - 1)
+            self.input.propagate_gradient(upstream, grad)
+
+
+class _PowR(_UnaryRResult):  # arithmetic.go:908-966
+    power = 1.0
+
+    def constant(self, rg, g):
+        return self.power != 0 and self.input.constant(rg, g)
+
+    def propagate_rgradient(self, upstream, upstream_r, rgrad, grad):
+        if not self.constant(rgrad, grad):
+            if self.power != 1:
+                x, xr, p = self.input.output(), self.input.routput(), self.power
+                d1 = p * np.power(x, p - 1)
+                d2 = p * (p - 1) * np.power(x, p - 2) * xr
+                u = upstream.copy()
+                upstream[:] = u * d1
+                upstream_r[:] = upstream_r * d1 + u * d2
+            self.input.propagate_rgradient(upstream, upstream_r, rgrad, grad)
+
+
+def pow_(r, p):
+    res = _Pow(np.power(r.output(), p), r)
+    res.power = float(p)
+    return res
+
+
+def pow_r(r, p):
+    x = r.output()
+    rout = p * np.power(x, p - 1) * r.routput() if p != 0 else np.zeros(len(x), dtype=F64)
+    res = _PowR(np.power(x, p), rout, r)
+    res.power = float(p)
+    return res
+
+
+def _max_abs(x):
+    return float(np.max(np.abs(x))) if len(x) else 0.0
+
+
+def add_log_domain(v1, v2):  # arithmetic.go:1056-1062 (maxVal is the max ABSOLUTE value, a constant)
+    m = max(_max_abs(v1.output()), _max_abs(v2.output()))
+    e1 = Exp().apply(add_scaler(v1, -m))
+    e2 = Exp().apply(add_scaler(v2, -m))
+    return add_scaler(Log().apply(add(e1, e2)), m)
+
+
+def add_log_domain_r(v1, v2):  # arithmetic.go:1065-1072
+    m = max(_max_abs(v1.output()), _max_abs(v2.output()))
+    e1 = Exp().apply_r({}, add_scaler_r(v1, -m))
+    e2 = Exp().apply_r({}, add_scaler_r(v2, -m))
+    return add_scaler_r(Log().apply_r({}, add_r(e1, e2)), m)
+
+
+def sum_all_log_domain(v):  # arithmetic.go:1077-1082
+    m = _max_abs(v.output())
+    return add_scaler(Log().apply(sum_all(Exp().apply(add_scaler(v, -m)))), m)
+
+
+def sum_all_log_domain_r(v):  # arithmetic.go:1085-1090
+    m = _max_abs(v.output())
+    return add_scaler_r(Log().apply_r(None, sum_all_r(Exp().apply_r(None, add_scaler_r(v, -m)))), m)
+
+
+def squared_error(actual, expected):
+    """north_star's "SquaredError": 0.5*||a - y||^2 = Scale(SquaredNorm(Sub(a, y)), .5)."""
+    return scale(SquaredNorm().apply(sub(actual, expected)), 0.5)
+
+
+def squared_error_r(actual, expected):
+    return scale_r(SquaredNorm().apply_r({}, sub_r(actual, expected)), 0.5)
+
+
+def split(n, inp):  # slices.go:310-321
+    if len(inp.output()) % n != 0:
+        raise ValueError("count does not divide input length")
+    size = len(inp.output()) // n
+    return [slice_(inp, i * size, (i + 1) * size) for i in range(n)]
+
+
+def split_r(n, inp):  # slices.go:324-335
+    if len(inp.output()) % n != 0:
+        raise ValueError("count does not divide input length")
+    size = len(inp.output()) // n
+    return [slice_r(inp, i * size, (i + 1) * size) for i in range(n)]
+
+
+# --------------------------------------------------------------------------------------
+# pool.go: Pool / PoolAll (+R) -- the temp-variable protocol
+# --------------------------------------------------------------------------------------
+class _Pooled:  # pool.go:94-136
+    def __init__(self, ins, f):
+        self.inputs = list(ins)
+        self.pool_vars = [Variable(r.output()) for r in ins]
+        for pv, r in zip(self.pool_vars, ins):
+            pv.vector = r.output()  # aliased like &Variable{Vector: in.Output()}
+        self.f_output = f(list(self.pool_vars))
+
+    def output(self):
+        return self.f_output.output()
+
+    def constant(self, g):
+        if not self.f_output.constant(g):
+            return False
+        for pv, r in zip(self.pool_vars, self.inputs):
+            if not self.f_output.constant({pv: np.zeros(0)}) and not r.constant(g):
+                return False
+        return True
+
+    def propagate_gradient(self, upstream, grad):
+        consts = []
+        for pv, r in zip(self.pool_vars, self.inputs):
+            c = self.f_output.constant({pv: np.zeros(0)}) or r.constant(grad)
+            consts.append(c)
+            if not c:
+                grad[pv] = np.zeros(len(pv.vector), dtype=F64)
+        self.f_output.propagate_gradient(upstream, grad)
+        ups = [None] * len(self.pool_vars)
+        for i, pv in enumerate(self.pool_vars):
+            if not consts[i]:
+                ups[i] = grad.pop(pv)
+        for i, c in enumerate(consts):
+            if not c:
+                self.inputs[i].propagate_gradient(ups[i], grad)
+
+
+class _PooledR:  # pool.go:138-195
+    def __init__(self, ins, f):
+        self.inputs = list(ins)
+        self.pool_vars = []
+        pool_res = []
+        for r in ins:
+            pv = Variable(r.output())
+            pv.vector = r.output()
+            self.pool_vars.append(pv)
+            pool_res.append(RVariable(pv, {pv: r.routput()}))
+        self.f_output = f(pool_res)
+
+    def output(self):
+        return self.f_output.output()
+
+    def routput(self):
+        return self.f_output.routput()
+
+    def constant(self, rg, g):
+        if not self.f_output.constant(rg, g):
+            return False
+        for pv, r in zip(self.pool_vars, self.inputs):
+            if not self.f_output.constant({pv: np.zeros(0)}, None) and not r.constant(rg, g):
+                return False
+        return True
+
+    def propagate_rgradient(self, upstream, upstream_r, rgrad, grad):
+        if grad is None:
+            grad = {}
+        consts = []
+        for pv, r in zip(self.pool_vars, self.inputs):
+            c = self.f_output.constant({pv: np.zeros(0)}, None) or r.constant(rgrad, grad)
+            consts.append(c)
+            if not c:
+                grad[pv] = np.zeros(len(pv.vector), dtype=F64)
+                rgrad[pv] = np.zeros(len(pv.vector), dtype=F64)
+        self.f_output.propagate_rgradient(upstream, upstream_r, rgrad, grad)
+        ups, ups_r = [None] * len(consts), [None] * len(consts)
+        for i, pv in enumerate(self.pool_vars):
+            if not consts[i]:
+                ups[i], ups_r[i] = grad.pop(pv), rgrad.pop(pv)
+        for i, c in enumerate(consts):
+            if not c:
+                self.inputs[i].propagate_rgradient(ups[i], ups_r[i], rgrad, grad)
+
+
+def pool(r, f):  # pool.go:21-25
+    return _Pooled([r], lambda ins: f(ins[0]))
+
+
+def pool_r(r, f):  # pool.go:28-32
+    return _PooledR([r], lambda ins: f(ins[0]))
+
+
+def pool_all(ins, f):  # pool.go:38-50
+    return _Pooled(ins, f)
+
+
+def pool_all_r(ins, f):  # pool.go:53-68
+    return _PooledR(ins, f)
+
+
+# --------------------------------------------------------------------------------------
+# fold.go: Fold / FoldR
+# --------------------------------------------------------------------------------------
+class _Fold:  # fold.go:5-84
+    def __init__(self, state, ins, f):
+        self.pool, self.intermediate = [], []
+        for r in ins:
+            self.intermediate.append(state)
+            pv = Variable(state.output())
+            pv.vector = state.output()
+            self.pool.append(pv)
+            state = f(pv, r)
+        self.final = state
+
+    def output(self):
+        return self.final.output()
+
+    def constant(self, g):  # fold.go:35-54
+        if not self.final.constant(g):
+            return False
+        for i in range(len(self.pool) - 1, -1, -1):
+            if not self.intermediate[i].constant(g):
+                return False
+            if i > 0:
+                p = self.pool[i - 1]
+                g[p] = np.zeros(len(p.vector), dtype=F64)
+                c = self.intermediate[i].constant(g)
+                del g[p]
+                if c:
+                    return True
+        return True
+
+    def propagate_gradient(self, u, g):  # fold.go:56-84
+        if not self.pool:
+            self.final.propagate_gradient(u, g)
+            return
+        state_up = u
+        for i in range(len(self.pool), 0, -1):
+            res = self.final if i == len(self.pool) else self.intermediate[i]
+            p = self.pool[i - 1]
+            g[p] = np.zeros(len(p.vector), dtype=F64)
+            if res.constant(g):
+                del g[p]
+                break
+            res.propagate_gradient(state_up, g)
+            state_up = g.pop(p)
+        if self.intermediate:
+            self.intermediate[0].propagate_gradient(state_up, g)
+
+
+class _FoldR:  # fold.go:86-178
+    def __init__(self, state, ins, f):
+        self.pool, self.intermediate = [], []
+        for r in ins:
+            self.intermediate.append(state)
+            pv = Variable(state.output())
+            pv.vector = state.output()
+            self.pool.append(pv)
+            state = f(RVariable(pv, {pv: state.routput()}), r)
+        self.final = state
+
+    def output(self):
+        return self.final.output()
+
+    def routput(self):
+        return self.final.routput()
+
+    def constant(self, rg, g):  # fold.go:113-139
+        if not self.final.constant(rg, g):
+            return False
+        for i in range(len(self.pool) - 1, -1, -1):
+            if not self.intermediate[i].constant(rg, g):
+                return False
+            if i > 0:
+                p = self.pool[i - 1]
+                if g is not None:
+                    g[p] = np.zeros(len(p.vector), dtype=F64)
+                rg[p] = np.zeros(len(p.vector), dtype=F64)
+                c = self.intermediate[i].constant(rg, g)
+                if g is not None:
+                    del g[p]
+                del rg[p]
+                if c:
+                    return True
+        return True
+
+    def propagate_rgradient(self, u, ur, rg, g):  # fold.go:141-178
+        if not self.pool:
+            self.final.propagate_rgradient(u, ur, rg, g)
+            return
+        if g is None:
+            g = {}
+        state_up, state_up_r = u, ur
+        for i in range(len(self.pool), 0, -1):
+            res = self.final if i == len(self.pool) else self.intermediate[i]
+            p = self.pool[i - 1]
+            g[p] = np.zeros(len(p.vector), dtype=F64)
+            rg[p] = np.zeros(len(p.vector), dtype=F64)
+            if res.constant(rg, g):
+                del g[p]
+                del rg[p]
+                break
+            res.propagate_rgradient(state_up, state_up_r, rg, g)
+            state_up, state_up_r = g.pop(p), rg.pop(p)
+        if self.intermediate:
+            self.intermediate[0].propagate_rgradient(state_up, state_up_r, rg, g)
+
+
+def fold(state, ins, f):
+    return _Fold(state, ins, f)
+
+
+def fold_r(state, ins, f):
+    return _FoldR(state, ins, f)
+
+
+# --------------------------------------------------------------------------------------
+# lin_alg.go: MatMulVecs -- LinTran with a computed matrix
+# --------------------------------------------------------------------------------------
+class _MatMul:  # lin_alg.go:9-69
+    def __init__(self, mat, rows, cols, vecs):
+        if len(mat.output()) != rows * cols:
+            raise ValueError("invalid matrix data size")
+        if len(vecs.output()) % cols != 0:
+            raise ValueError("invalid vecs size")
+        n = len(vecs.output()) // cols
+        self.mat_in = mat
+        self.mat_var = Variable(mat.output())
+        self.mat_var.vector = mat.output()
+        self.res = LinTran(self.mat_var, rows, cols).batch(vecs, n)
+
+    def output(self):
+        return self.res.output()
+
+    def constant(self, g):
+        return self.res.constant(g) and self.mat_in.constant(g)
+
+    def propagate_gradient(self, upstream, grad):
+        mat_const = self.mat_in.constant(grad)
+        if not mat_const:
+            grad[self.mat_var] = np.zeros(len(self.mat_var.vector), dtype=F64)
+        self.res.propagate_gradient(upstream, grad)
+        if not mat_const:
+            self.mat_in.propagate_gradient(grad.pop(self.mat_var), grad)
+
+
+class _MatMulR:  # lin_alg.go:71-133
+    def __init__(self, mat, rows, cols, vecs):
+        if len(mat.output()) != rows * cols:
+            raise ValueError("invalid matrix data size")
+        if len(vecs.output()) % cols != 0:
+            raise ValueError("invalid vecs size")
+        n = len(vecs.output()) // cols
+        self.mat_in = mat
+        self.mat_var = Variable(mat.output())
+        self.mat_var.vector = mat.output()
+        self.res = LinTran(self.mat_var, rows, cols).batch_r({self.mat_var: mat.routput()}, vecs, n)
+
+    def output(self):
+        return self.res.output()
+
+    def routput(self):
+        return self.res.routput()
+
+    def constant(self, rg, g):
+        return self.res.constant(rg, g) and self.mat_in.constant(rg, g)
+
+    def propagate_rgradient(self, upstream, upstream_r, rgrad, grad):
+        mat_const = self.mat_in.constant(rgrad, grad)
+        if not mat_const:
+            if grad is None:
+                grad = {}
+            grad[self.mat_var] = np.zeros(len(self.mat_var.vector), dtype=F64)
+            rgrad[self.mat_var] = np.zeros(len(self.mat_var.vector), dtype=F64)
+        self.res.propagate_rgradient(upstream, upstream_r, rgrad, grad)
+        if not mat_const:
+            self.mat_in.propagate_rgradient(grad.pop(self.mat_var), rgrad.pop(self.mat_var), rgrad, grad)
+
+
+def mat_mul_vecs(mat, rows, cols, vecs):
+    return _MatMul(mat, rows, cols, vecs)
+
+
+def mat_mul_vecs_r(mat, rows, cols, vecs):
+    return _MatMulR(mat, rows, cols, vecs)
+
+
+mat_mul_vec, mat_mul_vec_r = mat_mul_vecs, mat_mul_vecs_r
+
+
+def result_len(r) -> int:
+    return len(r.output())
