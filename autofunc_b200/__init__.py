@@ -10,3 +10,7 @@ from .slices import concat, concat_r, slice_, slice_r, repeat, repeat_r, concat_
 from . import api as _api  # noqa: E402
 for _n in ("concat", "concat_r", "slice_", "slice_r", "repeat", "repeat_r", "concat_batched", "concat_batched_r"):
     setattr(_api, _n, globals()[_n])  # the operator namespace tests and callers use is `api`
+from . import funcs as _funcs  # noqa: E402
+from .funcs import *  # noqa: F401,F403,E402
+for _n in _funcs.__all__:
+    setattr(_api, _n, getattr(_funcs, _n))

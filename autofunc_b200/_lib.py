@@ -67,6 +67,32 @@ PROTOTYPES = {
     "af_square_bwd_r": (INT, [P, D, D, D, D, I64]),
     "af_sum_all": (INT, [P, D, D, D, D, I64]),
     "af_fill": (INT, [P, D, C.c_double, I64]),
+    "af_log_fwd_r": (INT, [P, D, D, D, D, I64]),
+    "af_log_bwd_r": (INT, [P, D, D, D, D, I64]),
+    "af_logsigmoid_fwd_r": (INT, [P, D, D, D, D, I64]),
+    "af_logsigmoid_bwd_r": (INT, [P, D, D, D, D, I64]),
+    "af_sin_fwd_r": (INT, [P, D, D, D, D, I64]),
+    "af_sin_bwd_r": (INT, [P, D, D, D, D, I64]),
+    "af_tanh_fwd_r": (INT, [P, D, D, D, D, I64]),
+    "af_tanh_bwd_r": (INT, [P, D, D, D, D, I64]),
+    "af_inverse_fwd_r": (INT, [P, D, D, D, D, I64]),
+    "af_inverse_bwd_r": (INT, [P, D, D, D, D, I64]),
+    "af_pow_fwd_r": (INT, [P, D, D, C.c_double, D, D, I64]),
+    "af_pow_bwd_r": (INT, [P, D, D, C.c_double, D, D, I64]),
+    "af_div": (INT, [P, D, D, D, I64]),
+    "af_div_bwd": (INT, [P, D, D, D, D, D, I64]),
+    "af_add_scaler": (INT, [P, D, C.c_double, D, I64]),
+    "af_add_dev": (INT, [P, D, D, C.c_double, D, I64]),
+    "af_scale_dev": (INT, [P, D, D, D, D, D, D, I64]),
+    "af_fill_dev": (INT, [P, D, D, I64]),
+    "af_dot": (INT, [P, D, D, D, D, D, I64]),
+    "af_max_abs": (INT, [P, D, D, INT, I64]),
+    "af_norm_fwd_r": (INT, [P, D, D, D, D, I64]),
+    "af_norm_bwd_r": (INT, [P, D, D, D, D, D, D, D, D, I64]),
+    "af_softmax_fwd_r": (INT, [P, D, D, C.c_double, D, D, I64, I64]),
+    "af_softmax_bwd_r": (INT, [P, D, D, C.c_double, D, D, I64, I64]),
+    "af_sqerr_fwd_r": (INT, [P, D, D, D, D, D, D, I64]),
+    "af_sqerr_bwd_r": (INT, [P, D, D, D, D, D, D, C.c_double, D, D, I64]),
     "af_dense_fwd": (INT, [P, D, D, D, D, D, D, D, D, I64, I64, I64, INT]),
     "af_dense_igrad": (INT, [P, D, D, D, D, D, D, D, D, I64, I64, I64]),
     "af_mlp_create": (INT, [P, C.POINTER(I64), INT, I64, C.POINTER(P)]),

@@ -146,6 +146,13 @@ class DeviceVec:
         check(self.ctx.lib.af_copy(self.ctx.h, v.ptr, self.ptr, self.n))
         return v
 
+    def __iadd__(self, other):  # `grad[v] += upstream` (variable.go:45) when the map's vectors live in HBM
+        o = other if isinstance(other, DeviceVec) else self.ctx.upload(other)
+        if o.n != self.n:
+            raise ShapeError(_lib.AF_ESHAPE, "vector sizes do not match")
+        check(self.ctx.lib.af_axpy(self.ctx.h, 1.0, o.ptr, self.ptr, self.n))
+        return self
+
 
 _default_ctx: Context | None = None
 
@@ -173,31 +180,77 @@ def _p(v: "DeviceVec | None"):
 class Variable:
     """variable.go:19-21.  `.vector` is the host value (numpy float64); a device copy is cached and
     refreshed when the host value changes -- call `set()` / `mark_dirty()` after mutating large
-    vectors in place (vectors up to 64Ki entries are compared automatically)."""
+    vectors in place (vectors up to 64Ki entries are compared automatically).
+
+    The device copy can also be the authoritative one: pool variables wrap a Result's output without
+    leaving HBM (`from_device`, the analogue of `&Variable{Vector: in.Output()}` at pool.go:42,
+    fold.go:24, lin_alg.go:37), and `add_scaled_device` is gradient.go:40-52's Axpy on the device.
+    `.vector` then downloads lazily, the first time a host caller looks."""
 
     __hash__ = object.__hash__
     _AUTO_CHECK = 1 << 16
 
     def __init__(self, v):
-        self.vector = np.array(v, dtype=F64).reshape(-1)
+        self._vector = np.array(v, dtype=F64).reshape(-1)
+        self.size = self._vector.size
         self._dev: DeviceVec | None = None
         self._snapshot: np.ndarray | None = None
+        self._host_stale = False
+
+    @classmethod
+    def from_device(cls, d: DeviceVec) -> "Variable":
+        v = cls.__new__(cls)
+        v._vector, v.size, v._dev, v._snapshot, v._host_stale = None, d.n, d, None, True
+        return v
+
+    @property
+    def vector(self) -> np.ndarray:
+        if self._host_stale:
+            h = self._dev.numpy()
+            if self._vector is None:
+                self._vector = h
+            else:
+                self._vector[:] = h
+            self._host_stale = False
+            self._snapshot = self._vector.copy() if self.size <= self._AUTO_CHECK else None
+        return self._vector
+
+    @vector.setter
+    def vector(self, arr) -> None:
+        self._vector = np.array(arr, dtype=F64).reshape(-1)
+        self.size = self._vector.size
+        self._dev, self._host_stale = None, False
+
+    def __len__(self):
+        return self.size
 
     def set(self, arr) -> None:
         self.vector[:] = arr
         self._dev = None
 
     def mark_dirty(self) -> None:
+        _ = self.vector  # pull a device-side update down before the host copy becomes authoritative
         self._dev = None
 
     def device(self) -> DeviceVec:
-        small = self.vector.size <= self._AUTO_CHECK
-        if self._dev is not None and small and not np.array_equal(self._snapshot, self.vector):
+        if self._host_stale:
+            return self._dev
+        small = self.size <= self._AUTO_CHECK
+        if self._dev is not None and small and not np.array_equal(self._snapshot, self._vector):
             self._dev = None
         if self._dev is None:
-            self._dev = context().upload(self.vector)
-            self._snapshot = self.vector.copy() if small else None
+            self._dev = context().upload(self._vector)
+            self._snapshot = self._vector.copy() if small else None
         return self._dev
+
+    def add_scaled_device(self, scale: float, g: DeviceVec) -> None:
+        """v += scale * g without leaving HBM (gradient.go:40-52)."""
+        d = self.device()
+        if g.n != d.n:
+            raise ShapeError(_lib.AF_ESHAPE, "vector sizes do not match")
+        ctx = context()
+        check(ctx.lib.af_axpy(ctx.h, float(scale), g.ptr, d.ptr, d.n))
+        self._host_stale = True
 
     # Result interface ------------------------------------------------------------------
     def output(self):
@@ -208,7 +261,7 @@ class Variable:
 
     def propagate_gradient(self, upstream, grad):  # variable.go:43-47
         if self in grad:
-            grad[self] += _host(upstream)
+            grad[self] += upstream if isinstance(grad[self], DeviceVec) else _host(upstream)
 
     # device-side protocol
     def _d(self):
@@ -220,7 +273,7 @@ class Variable:
 
     # wire format (variable.go:24-37,61-68)
     def serialize(self) -> bytes:
-        return np.uint64(self.vector.size).astype("<u8").tobytes() + self.vector.astype("<f8").tobytes()
+        return np.uint64(self.size).astype("<u8").tobytes() + self.vector.astype("<f8").tobytes()
 
     @staticmethod
     def deserialize(b: bytes) -> "Variable":
@@ -234,15 +287,19 @@ class RVariable:
     def __init__(self, v: Variable, rv: dict):
         self.variable = v
         self._has_r = v in rv
-        self.routput_vec = np.asarray(rv[v], dtype=F64) if self._has_r else None
-        self._rdev: DeviceVec | None = None
+        r = rv[v] if self._has_r else None
+        self._rdev: DeviceVec | None = r if isinstance(r, DeviceVec) else None
+        self.routput_vec = np.asarray(r, dtype=F64) if (self._has_r and self._rdev is None) else None
 
     def output(self):
         return self.variable.vector
 
     def routput(self):
-        if self.routput_vec is None:  # variable.go:85-91: fresh zeros
-            self.routput_vec = np.zeros(self.variable.vector.size, dtype=F64)
+        if self.routput_vec is None:
+            if self._rdev is not None:
+                self.routput_vec = self._rdev.numpy()
+            else:  # variable.go:85-91: fresh zeros
+                self.routput_vec = np.zeros(self.variable.size, dtype=F64)
         return self.routput_vec
 
     def constant(self, rg, g):  # variable.go:102-111
@@ -253,10 +310,11 @@ class RVariable:
         return self.variable not in g
 
     def propagate_rgradient(self, upstream, upstream_r, rgrad, grad):  # variable.go:113-123
-        if grad is not None and self.variable in grad:
-            grad[self.variable] += _host(upstream)
-        if self.variable in rgrad:
-            rgrad[self.variable] += _host(upstream_r)
+        v = self.variable
+        if grad is not None and v in grad:
+            grad[v] += upstream if isinstance(grad[v], DeviceVec) else _host(upstream)
+        if v in rgrad:
+            rgrad[v] += upstream_r if isinstance(rgrad[v], DeviceVec) else _host(upstream_r)
 
     def _d(self):
         return self.variable.device()
@@ -278,7 +336,7 @@ class RVariable:
 
 
 def new_gradient(variables):  # gradient.go:13-19
-    return {v: np.zeros(v.vector.size, dtype=F64) for v in variables}
+    return {v: np.zeros(v.size, dtype=F64) for v in variables}
 
 
 new_rgradient = new_gradient
@@ -291,8 +349,90 @@ def gradient_add(g, g1):  # gradient.go:28-30
 
 def gradient_add_to_vars(g, scale):  # gradient.go:40-52
     for v, gv in g.items():
-        v.vector += scale * gv
-        v.mark_dirty()
+        if isinstance(gv, DeviceVec):
+            v.add_scaled_device(scale, gv)
+        else:
+            v.vector += scale * gv
+            v.mark_dirty()
+
+
+def gradient_zero(g):  # gradient.go:22-24,100-106
+    for gv in g.values():
+        if isinstance(gv, DeviceVec):
+            check(gv.ctx.lib.af_zero(gv.ctx.h, gv.ptr, gv.n))
+        else:
+            gv[:] = 0
+
+
+def gradient_scale(g, f):  # gradient.go:33-36,122-126
+    for gv in g.values():
+        if isinstance(gv, DeviceVec):
+            check(gv.ctx.lib.af_scale(gv.ctx.h, gv.ptr, float(f), gv.n))
+        else:
+            gv *= f
+
+
+def gradient_copy(g):  # gradient.go:54-57,128-136
+    if isinstance(g, DeviceGradient):
+        return DeviceGradient._from_items((k, v.copy()) for k, v in g.items())
+    return {k: v.copy() for k, v in g.items()}
+
+
+class DeviceGradient(dict):
+    """A Gradient / RGradient (gradient.go:11,62) whose vectors stay in HBM: backward passes accumulate
+    straight into them (no per-call flush to the host), `add_to_vars` is the SGD step on the device, and
+    nothing is downloaded until `host()` is asked for.  Keys are Variables, values DeviceVecs."""
+
+    def __init__(self, variables=()):
+        super().__init__()
+        for v in variables:
+            self[v] = context().zeros(v.size)
+
+    @classmethod
+    def _from_items(cls, items):
+        g = cls()
+        for k, v in items:
+            g[k] = v
+        return g
+
+    def zero(self):
+        gradient_zero(self)
+
+    def scale(self, f):
+        gradient_scale(self, f)
+
+    def add(self, g1):
+        gradient_add(self, g1)
+
+    def add_to_vars(self, scale):
+        gradient_add_to_vars(self, scale)
+
+    def copy(self):
+        return gradient_copy(self)
+
+    def host(self):
+        return {k: _host(v) for k, v in self.items()}
+
+
+new_device_gradient = new_device_rgradient = DeviceGradient
+
+
+class _TempGrad:
+    """Placeholder a device node inserts as `grad[tmp]` for the reference's temp-variable protocol
+    (pool.go:114-136, fold.go:64-80, lin_alg.go:57-68).  Device nodes accumulate into the session's
+    HBM accumulator for `tmp`; a foreign host Result that does `grad[tmp] += upstream` materialises a
+    host vector here; `_Session.take` returns the sum of both as a DeviceVec."""
+
+    def __init__(self, n):
+        self.n, self.host = n, None
+
+    def __len__(self):
+        return self.n
+
+    def __iadd__(self, x):
+        x = np.asarray(x, dtype=F64)
+        self.host = x.copy() if self.host is None else self.host + x
+        return self
 
 
 def _host(x) -> np.ndarray:
@@ -311,12 +451,28 @@ class _Session:
         self.acc: dict[tuple[int, int], tuple[dict, Variable, DeviceVec]] = {}
 
     def accumulator(self, gmap, v) -> DeviceVec:
+        cur = gmap.get(v)
+        if isinstance(cur, DeviceVec):  # DeviceGradient: the map's own vector is the accumulator
+            return cur
         key = (id(gmap), id(v))
         ent = self.acc.get(key)
         if ent is None:
-            ent = (gmap, v, context().zeros(v.vector.size))
+            ent = (gmap, v, context().zeros(v.size))
             self.acc[key] = ent
         return ent[2]
+
+    def take(self, gmap, v) -> DeviceVec:
+        """Remove temp variable `v` from `gmap` and return everything accumulated for it, on the device."""
+        ent = self.acc.pop((id(gmap), id(v)), None)
+        cur = gmap.pop(v)
+        d = ent[2] if ent is not None else None
+        host = cur.host if isinstance(cur, _TempGrad) else cur
+        if isinstance(host, DeviceVec):
+            d = host if d is None else d.__iadd__(host)
+        elif host is not None:
+            up = context().upload(host)
+            d = up if d is None else d.__iadd__(up)
+        return d if d is not None else context().zeros(v.size)
 
     def accumulate(self, gmap, v, dU: DeviceVec | None):
         if dU is None:
@@ -328,7 +484,9 @@ class _Session:
     def flush(self):
         for gmap, v, a in self.acc.values():
             if v in gmap:
-                gmap[v] += a.numpy()
+                cur = gmap[v]
+                cur += a if isinstance(cur, DeviceVec) else a.numpy()
+                gmap[v] = cur
         self.acc.clear()
 
 
@@ -488,8 +646,8 @@ class LinAdd:
 
     def _n(self, inp, n):
         got = _in_len(inp)
-        if got != n * self.var.vector.size:
-            raise ShapeError(_lib.AF_ESHAPE, "input length should be %d but got %d" % (n * self.var.vector.size, got))
+        if got != n * self.var.size:
+            raise ShapeError(_lib.AF_ESHAPE, "input length should be %d but got %d" % (n * self.var.size, got))
 
     def apply(self, inp):
         return self.batch(inp, 1)
@@ -502,7 +660,7 @@ class LinAdd:
         ctx = context()
         x = _in_d(inp)
         y = ctx.empty(x.n)
-        check(ctx.lib.af_bias_fwd(ctx.h, x.ptr, self.var.device().ptr, y.ptr, self.var.vector.size, n))
+        check(ctx.lib.af_bias_fwd(ctx.h, x.ptr, self.var.device().ptr, y.ptr, self.var.size, n))
         return _LinAddResult(self.var, inp, n, y)
 
     def batch_r(self, rv, inp, n):
@@ -512,7 +670,7 @@ class LinAdd:
         x, xr = _in_d(inp), _in_dr(inp)
         y, ry = ctx.empty(x.n), ctx.empty(x.n)
         check(ctx.lib.af_bias_fwd_r(ctx.h, x.ptr, _p(xr), rvar._d().ptr, _p(rvar._dr()), y.ptr, ry.ptr,
-                                    self.var.vector.size, n))
+                                    self.var.size, n))
         return _LinAddRResult(rvar, inp, n, y, ry)
 
 
@@ -550,7 +708,7 @@ class _LinAddRResult(_DeviceResult):
         gacc = sess.accumulator(grad, v) if (grad is not None and v in grad) else None
         racc = sess.accumulator(rgrad, v) if v in rgrad else None
         if gacc is not None or racc is not None:
-            check(ctx.lib.af_bias_grad_r(ctx.h, dU.ptr, dUR.ptr, _p(gacc), _p(racc), v.vector.size, self.n))
+            check(ctx.lib.af_bias_grad_r(ctx.h, dU.ptr, dUR.ptr, _p(gacc), _p(racc), v.size, self.n))
         if not self.input.constant(rgrad, grad):
             _down_r(self.input, sess, dU, dUR, rgrad, grad)
 
@@ -848,7 +1006,7 @@ class _SumAll(_UnaryResult):
     def _fill(self, src: DeviceVec, n: int) -> DeviceVec:
         ctx = context()
         out = ctx.empty(n)
-        check(ctx.lib.af_fill(ctx.h, out.ptr, float(src.numpy()[0]), n))
+        check(ctx.lib.af_fill_dev(ctx.h, out.ptr, src.ptr, n))  # the upstream scalar never leaves the device
         return out
 
     def _bwd(self, sess, dU, grad):  # arithmetic.go:987-995
@@ -919,7 +1077,7 @@ class DenseSigmoid:
 
     def __init__(self, weights: Variable, biases: Variable, rows: int, cols: int, activation: bool = True):
         self.w, self.b, self.rows, self.cols, self.activation = weights, biases, int(rows), int(cols), activation
-        if weights.vector.size != rows * cols or biases.vector.size != rows:
+        if weights.size != rows * cols or biases.size != rows:
             raise ShapeError(_lib.AF_ESHAPE, "parameter sizes do not match rows x cols")
 
     def _check(self, inp, n):
@@ -1024,7 +1182,7 @@ def fuse_dense(layers):
     while i < len(layers):
         a = layers[i]
         if (isinstance(a, LinTran) and i + 1 < len(layers) and isinstance(layers[i + 1], LinAdd)
-                and layers[i + 1].var.vector.size == a.rows):
+                and layers[i + 1].var.size == a.rows):
             act = i + 2 < len(layers) and isinstance(layers[i + 2], Sigmoid)
             out.append(DenseSigmoid(a.data, layers[i + 1].var, a.rows, a.cols, activation=act))
             i += 3 if act else 2

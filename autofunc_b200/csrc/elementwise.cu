@@ -3,35 +3,10 @@
 // in flight per thread, grid sized to a multiple of the SM count.  Each computes the value form
 // and the R form in the same pass where the reference walks the vectors twice.
 #include "common.h"
+#include "ew.cuh"
 
 namespace af {
 namespace {
-
-constexpr int kEwThreads = 256;
-constexpr int kEwUnroll = 4;
-
-template <typename F>
-__global__ void __launch_bounds__(kEwThreads) ew_kernel(long long n, F f) {
-  const long long stride = (long long)gridDim.x * kEwThreads;
-  long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x;
-  for (; i + (kEwUnroll - 1) * stride < n; i += kEwUnroll * stride) {
-#pragma unroll
-    for (int u = 0; u < kEwUnroll; ++u) f(i + u * stride);
-  }
-  for (; i < n; i += stride) f(i);
-}
-
-// `bpe` = algorithmic bytes per element (each distinct vector read or written once)
-template <typename F>
-int ew_launch(af_ctx* ctx, long long n, const char* what, int bpe, F f) {
-  if (n <= 0) return AF_OK;
-  long long blocks = (n + (long long)kEwThreads * kEwUnroll - 1) / ((long long)kEwThreads * kEwUnroll);
-  const long long cap = (long long)ctx->sm_count * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  ew_kernel<<<(unsigned)blocks, kEwThreads, 0, ctx->stream>>>(n, f);
-  return after_launch(ctx, what, KIND_ELEMENTWISE, (double)n * bpe);
-}
 
 __device__ __forceinline__ double sigm(double x) { return 1.0 / (1.0 + exp(-x)); }
 
@@ -120,12 +95,6 @@ int colsum_launch(af_ctx* ctx, const double* U, const double* UR, double* gb, do
 }  // namespace af
 
 using namespace af;
-
-#define AF_CHECK_CTX(ctx) \
-  if (!(ctx)) return af::fail(AF_EINVAL, "null context"); \
-  af::DeviceGuard _guard((ctx)->device)
-#define AF_NEED(p) \
-  if (!(p)) return af::fail(AF_EINVAL, "null pointer argument: " #p)
 
 extern "C" {
 

@@ -157,6 +157,67 @@ int af_sum_all(af_ctx*, const double* d_x, const double* d_xR, double* d_out, do
 /* fill (SumAll backward broadcast, arithmetic.go:990-993)                                      */
 int af_fill(af_ctx*, double* d_x, double value, int64_t len);
 
+/* ---- the functions and cost heads either side of the dense path -------- */
+/* Conventions: every *_fwd_r computes the value form, and the R form too when the R output pointer is
+ * non-NULL (a NULL R input means identically zero, variable.go:85-91).  Every *_bwd_r overwrites the
+ * upstreams in place as the reference does (result.go:24-29); d_UR may be NULL for the non-R form.
+ * Scalars the reference reads on the host (scaler.Output()[0], MaxAbs(), SumAll's upstream) are device
+ * scalars passed by pointer, so chains of these calls never synchronise the stream.                  */
+/* Log (math_funcs.go:99-189): O = log X, RO = RX / X; bwd U <- U/X, UR <- UR/X - U RX / X^2          */
+int af_log_fwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_O, double* d_RO, int64_t len);
+int af_log_bwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_U, double* d_UR, int64_t len);
+/* LogSigmoid (math_funcs.go:376-477): branch on the sign of x as :399-410; RO = RX / (1 + e^x)        */
+int af_logsigmoid_fwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_O, double* d_RO, int64_t len);
+int af_logsigmoid_bwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_U, double* d_UR, int64_t len);
+/* Sin (math_funcs.go:511-597); Cos is Sin(AddScaler(x, pi/2)) (:599-607)                              */
+int af_sin_fwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_O, double* d_RO, int64_t len);
+int af_sin_bwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_U, double* d_UR, int64_t len);
+/* Tanh: EXTENSION named by BASELINE.json's north_star (the reference has none); Sigmoid's contract.   */
+int af_tanh_fwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_T, double* d_RT, int64_t len);
+int af_tanh_bwd_r(af_ctx*, const double* d_T, const double* d_RT, double* d_U, double* d_UR, int64_t len);
+/* Inverse (arithmetic.go:772-867): O = 1/X, RO = -O^2 RX; bwd takes the forward OUTPUT d_O.           */
+int af_inverse_fwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_O, double* d_RO, int64_t len);
+int af_inverse_bwd_r(af_ctx*, const double* d_O, const double* d_RX, double* d_U, double* d_UR, int64_t len);
+/* Pow (arithmetic.go:869-966)                                                                         */
+int af_pow_fwd_r(af_ctx*, const double* d_X, const double* d_RX, double p, double* d_O, double* d_RO, int64_t len);
+int af_pow_bwd_r(af_ctx*, const double* d_X, const double* d_RX, double p, double* d_U, double* d_UR, int64_t len);
+/* Div (arithmetic.go:378-423): O = A/B; bwd DA = U/B, DB = U(-O/B) (either may be NULL).  DivR is
+ * MulR(a, InverseR(b)) in the reference (:425-427) and is composed the same way by the caller.        */
+int af_div(af_ctx*, const double* d_A, const double* d_B, double* d_O, int64_t len);
+int af_div_bwd(af_ctx*, const double* d_U, const double* d_O, const double* d_B, double* d_DA, double* d_DB, int64_t len);
+/* AddScaler (arithmetic.go:184-252): O = X + f                                                        */
+int af_add_scaler(af_ctx*, const double* d_X, double f, double* d_O, int64_t len);
+/* O = X + sign * d_f[0]: AddFirst (arithmetic.go:595-694) and the "- maxVal" of the log-domain sums   */
+int af_add_dev(af_ctx*, const double* d_X, const double* d_f, double sign, double* d_O, int64_t len);
+/* O = X d_f[0]; RO = X d_fR[0] + RX d_f[0]: ScaleFirst forward and (on the upstreams) backward
+ * (arithmetic.go:495-593).  O may alias X and RO may alias RX.                                         */
+int af_scale_dev(af_ctx*, const double* d_X, const double* d_RX, const double* d_f, const double* d_fR,
+                 double* d_O, double* d_RO, int64_t len);
+/* x[i] = d_value[0]: SumAll's backward broadcast (arithmetic.go:987-995,1035-1047)                    */
+int af_fill_dev(af_ctx*, double* d_x, const double* d_value, int64_t len);
+/* *d_out = sum a.b (+ sum c.d when c, d non-NULL): DotFast (arithmetic.go:523,571-573)                */
+int af_dot(af_ctx*, const double* d_a, const double* d_b, const double* d_c, const double* d_d, double* d_out, int64_t len);
+/* *d_out = max |x| (linalg MaxAbs, arithmetic.go:1057,1078); combine != 0: max with the value already there */
+int af_max_abs(af_ctx*, const double* d_x, double* d_out, int combine, int64_t len);
+/* Norm (math_funcs.go:201-284): out = ||X||, outR = <X,RX>/out; bwd D = X u/o, DR = X(-u ro/o^2 + uR/o) + RX u/o */
+int af_norm_fwd_r(af_ctx*, const double* d_X, const double* d_RX, double* d_out, double* d_outR, int64_t len);
+int af_norm_bwd_r(af_ctx*, const double* d_X, const double* d_RX, const double* d_o, const double* d_ro,
+                  const double* d_u, const double* d_uR, double* d_D, double* d_DR, int64_t len);
+/* Softmax of every row of an n x len packed batch = RFuncBatcher{&Softmax{T}} (math_funcs.go:479-509,
+ * batcher.go:57-84) as ONE kernel per direction; temperature 0 means 1 (:481-485).  No max-subtraction,
+ * like the reference.  bwd_r is in place on U, UR and needs only the forward outputs Y, RY.            */
+int af_softmax_fwd_r(af_ctx*, const double* d_X, const double* d_RX, double temperature, double* d_Y, double* d_RY,
+                     int64_t len, int64_t n);
+int af_softmax_bwd_r(af_ctx*, const double* d_Y, const double* d_RY, double temperature, double* d_U, double* d_UR,
+                     int64_t len, int64_t n);
+/* Squared-error cost head (north_star's "SquaredError"): c = .5 ||A - Y||^2, the reference's
+ * Scale(SquaredNorm(Sub(a, y)), .5) (math_funcs.go:191-199, arithmetic.go:105,436,696,972) as one
+ * reduction; bwd: upstream (d_u, d_uR device scalars) -> upstream on A (sign = +1) or on Y (sign = -1). */
+int af_sqerr_fwd_r(af_ctx*, const double* d_A, const double* d_RA, const double* d_Y, const double* d_RY,
+                   double* d_out, double* d_outR, int64_t len);
+int af_sqerr_bwd_r(af_ctx*, const double* d_A, const double* d_RA, const double* d_Y, const double* d_RY,
+                   const double* d_u, const double* d_uR, double sign, double* d_G, double* d_GR, int64_t len);
+
 /* ---- fused dense layer: LinTran -> LinAdd -> Sigmoid in one kernel per direction ---------- */
 /* Forward with R (G1+G2+E1+E2):  S = sigmoid(X W^T + b) ; RS = S(1-S)(X RW^T + RX W^T + Rb).
  * activation: 0 = none (S = pre-activation), 1 = sigmoid.  d_b/d_Rb/d_RW/d_RX/d_RS may be NULL
