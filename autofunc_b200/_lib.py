@@ -109,6 +109,8 @@ PROTOTYPES = {
     "af_mlp_upstream_ptr": (D, [P]),
     "af_mlp_upstream_r_ptr": (D, [P]),
     "af_mlp_zero_grads": (INT, [P]),
+    "af_mlp_add_to_vars": (INT, [P, C.c_double]),
+    "af_mlp_get_param": (INT, [P, INT, H, I64]),
     "af_mlp_step": (INT, [P, INT, INT]),
     "af_mlp_set_graph": (INT, [P, INT]),
     "af_mlp_step_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),
@@ -132,6 +134,7 @@ PROTOTYPES = {
     "af_lstm_upstream_r_ptr": (D, [P]),
     "af_lstm_grad_slab": (I64, [P, C.POINTER(D)]),
     "af_lstm_zero_grads": (INT, [P]),
+    "af_lstm_add_to_vars": (INT, [P, C.c_double]),
     "af_lstm_set_inputs": (INT, [P, D]),
     "af_lstm_forward": (INT, [P, INT]),
     "af_lstm_backward": (INT, [P, INT]),

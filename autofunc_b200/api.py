@@ -1248,6 +1248,15 @@ class MLPPlan:
     def zero_grads(self):
         check(self.ctx.lib.af_mlp_zero_grads(self.h))
 
+    def add_to_vars(self, scale: float):
+        """Gradient.AddToVars (gradient.go:40-52) on the device: param += scale * grad."""
+        check(self.ctx.lib.af_mlp_add_to_vars(self.h, float(scale)))
+
+    def get_param(self, idx) -> np.ndarray:
+        out = np.empty(self.param_len(idx), dtype=F64)
+        check(self.ctx.lib.af_mlp_get_param(self.h, idx, out.ctypes.data, out.size))
+        return out
+
     def step(self, with_r=True, backprop=True):
         check(self.ctx.lib.af_mlp_step(self.h, int(with_r), int(backprop)))
 

@@ -527,6 +527,18 @@ int af_mlp_zero_grads(af_mlp* m) {
   return AF_OK;
 }
 
+// Gradient.AddToVars (gradient.go:40-52) for the plan's own parameters: param_i += scale * grad_i, in HBM.
+int af_mlp_add_to_vars(af_mlp* m, double scale) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  for (int i = 0; i < 2 * m->L; ++i) AF_TRY(af_axpy(m->ctx, scale, m->grad[i], m->param[i], m->param_len(i)));
+  return AF_OK;
+}
+
+int af_mlp_get_param(af_mlp* m, int index, double* h, int64_t len) {
+  AF_TRY(mlp_index_ok(m, index, len)); AF_NEED(h);
+  return af_download(m->ctx, h, m->param[index], len);
+}
+
 static int mlp_step_launches(af_mlp* m, int with_r, int backprop);
 
 static int mlp_pipeline_init(af_mlp* m);

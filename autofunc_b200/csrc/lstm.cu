@@ -280,6 +280,15 @@ int af_lstm_zero_grads(af_lstm* m) {
   return AF_OK;
 }
 
+// Gradient.AddToVars (gradient.go:40-52) for the plan's own parameters, in HBM
+int af_lstm_add_to_vars(af_lstm* m, double scale) {
+  if (!m) return fail(AF_EINVAL, "null lstm");
+  AF_TRY(af_axpy(m->ctx, scale, m->gW4, m->W4, 4 * m->H * m->C));
+  AF_TRY(af_axpy(m->ctx, scale, m->gb4, m->b4, 4 * m->H));
+  AF_TRY(af_axpy(m->ctx, scale, m->gWout, m->Wout, m->O * m->C));
+  return af_axpy(m->ctx, scale, m->gbout, m->bout, m->O);
+}
+
 // inputs: T x B x I (time-major, lane-major within a step: the packing seqfunc.MapBatcher produces,
 // seqfunc/map.go:262-270).  Device pointer.
 int af_lstm_set_inputs(af_lstm* m, const double* d_x) {

@@ -65,6 +65,13 @@ class LSTMPlan:
     def zero_grads(self):
         check(self.ctx.lib.af_lstm_zero_grads(self.h))
 
+    def add_to_vars(self, scale: float):
+        """Gradient.AddToVars (gradient.go:40-52) on the device: param += scale * grad."""
+        check(self.ctx.lib.af_lstm_add_to_vars(self.h, float(scale)))
+
+    def param(self, idx):
+        return self._vec(self.ctx.lib.af_lstm_param_ptr(self.h, idx), self.param_len(idx))
+
     def set_inputs(self, d_x: DeviceVec):
         check(self.ctx.lib.af_lstm_set_inputs(self.h, d_x.ptr))
 

@@ -250,6 +250,10 @@ double* af_mlp_routput_ptr(af_mlp*);
 double* af_mlp_upstream_ptr(af_mlp*);           /* n x sizes[L]: outGrad  (bench/mlp.go:118-126) */
 double* af_mlp_upstream_r_ptr(af_mlp*);         /* n x sizes[L]: outRGrad */
 int af_mlp_zero_grads(af_mlp*);
+/* Gradient.AddToVars (gradient.go:40-52) on the plan's own parameters: param_i += scale * grad_i, in HBM
+ * (a training loop that never downloads the gradient).                                  */
+int af_mlp_add_to_vars(af_mlp*, double scale);
+int af_mlp_get_param(af_mlp*, int index, double* h_value, int64_t len);      /* sync */
 /* One iteration of bench/mlp.go:52-54 on resident data: ApplyR, then PropagateRGradient with
  * non-nil grad, accumulating into grad/rgrad.  with_r == 0 runs bench/mlp.go:36-38 instead
  * (Apply + PropagateGradient).  The upstream buffers are consumed (clobbered), as the reference
@@ -321,6 +325,7 @@ double* af_lstm_upstream_r_ptr(af_lstm*);
 /* The contiguous {grad | rgrad} block (for one data-parallel all-reduce): returns its length in doubles. */
 int64_t af_lstm_grad_slab(af_lstm*, double** d_first);
 int af_lstm_zero_grads(af_lstm*);
+int af_lstm_add_to_vars(af_lstm*, double scale);                /* gradient.go:40-52, in HBM */
 int af_lstm_set_inputs(af_lstm*, const double* d_x);          /* device T x B x I */
 int af_lstm_forward(af_lstm*, int with_r);                   /* Reset + T x StepTime (lstm.go:42-45) */
 int af_lstm_backward(af_lstm*, int with_r);                  /* PropagateGradient (lstm.go:215-234); consumes upstreams */

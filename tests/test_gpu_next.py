@@ -335,3 +335,109 @@ def test_device_gradient_map_semantics(api):
     assert np.allclose(a.vector, [5.0, 10.0, 15.0])  # lazily downloaded after the device-side update
     a.set([1.0, 1.0, 1.0])  # host write wins again
     assert np.allclose(api.add(a, a).output(), 2.0)
+
+
+def test_mlp_plan_training_loop_in_hbm_matches_oracle(api):
+    """af_mlp_step + af_mlp_add_to_vars: K gradient-ascent steps on the bench objective (outGrad = 1,
+    bench/mlp.go:118-126) without the gradient ever leaving the device, vs the oracle's host loop."""
+    sizes, n, lr, steps = [40, 64, 24, 10], 96, 0.01, 4
+    onet = ref.MLP(sizes, weight_scale=lambda k: 1 / np.sqrt(k))
+    x = onet.make_input(n)
+    plan = api.MLPPlan(sizes, n)
+    for i, v in enumerate(onet.variables):
+        plan.set_param(i, v.vector)
+        plan.set_rvector(i, None)
+    ctx = api.context()
+    api.check(ctx.lib.af_upload(ctx.h, plan.input().ptr, x.vector.ctypes.data, x.vector.size))
+    for _ in range(steps):
+        plan.zero_grads()
+        api.check(ctx.lib.af_fill(ctx.h, plan.upstream().ptr, 1.0, n * sizes[-1]))
+        plan.step(with_r=False, backprop=True)
+        plan.add_to_vars(lr)
+        _, grad = onet.step(x, n)
+        ref.gradient_add_to_vars(grad, lr)
+    for i, v in enumerate(onet.variables):
+        close(plan.get_param(i), v.vector, f"param {i} after {steps} steps")
+    plan.close()
+
+
+def test_lstm_plan_add_to_vars(api):
+    from autofunc_b200.lstm import LSTMPlan
+    I, H, O, T, B = 6, 16, 4, 5, 3
+    onet = ref.LSTMNet(I, H, O, weight_scale=0.3)
+    plan = LSTMPlan(I, H, O, T, B)
+    for i, v in enumerate(onet.variables):
+        plan.set_param(i, v.vector)
+    xs = ref.splitmix_uniform(3, T * B * I, 0.0, 1.0)
+    ups = ref.splitmix_uniform(4, T * B * O, 0.0, 1.0)
+    _, _, grads, _ = plan.run_host(xs, ups, with_r=False)
+    plan.add_to_vars(-0.125)
+    for i, v in enumerate(onet.variables):
+        close(plan.param(i).numpy(), v.vector - 0.125 * grads[i], f"lstm param {i}")
+    plan.close()
+
+
+def test_packed_map_rbatcher_matches_host_path_and_oracle(api):
+    """seqfunc.MapRBatcher over a list packed time-major in HBM (no per-timestep host copies) equals the host
+    joinTime/appendSplit path and the oracle's vector-by-vector application (seqfunc/test/map_test.go:88-120);
+    the sequence gradient arrives packed in one Variable."""
+    from autofunc_b200 import seq
+    sizes = [4, 6, 2]
+    onet = ref.MLP(sizes, weight_scale=lambda k: 1 / np.sqrt(k))
+    pvars = [api.Variable(v.vector) for v in onet.variables]
+    prv = {pv: onet.rvec[ov] for pv, ov in zip(pvars, onet.variables)}
+    layers = api.fuse_dense([api.LinTran(pvars[0], 6, 4), api.LinAdd(pvars[1]), api.Sigmoid(),
+                             api.LinTran(pvars[2], 2, 6), api.LinAdd(pvars[3]), api.Sigmoid()])
+    lens = [3, 1, 0, 2, 5]
+    seqs = [[ref.splitmix_uniform(700 + 10 * l + t, 4) for t in range(n)] for l, n in enumerate(lens)]
+    rseqs = [[ref.splitmix_uniform(750 + 10 * l + t, 4) for t in range(n)] for l, n in enumerate(lens)]
+    ups = [[ref.splitmix_uniform(800 + 10 * l + t, 2) for t in range(n)] for l, n in enumerate(lens)]
+    uprs = [[ref.splitmix_uniform(850 + 10 * l + t, 2) for t in range(n)] for l, n in enumerate(lens)]
+    plens, widths, flat = seq.PackedSeqs.pack_host(seqs)
+    _, _, rflat = seq.PackedSeqs.pack_host(rseqs)
+    xin = api.Variable(flat)
+    rv = dict(prv)
+    rv[xin] = rflat
+    res = seq.MapRBatcher(layers).apply_seqs_r(rv, seq.PackedVarResult(xin, plens, widths, rv))
+    # oracle: every vector on its own
+    per = ref.ComposedRFunc(list(onet.layers))
+    ograd, orgrad = ref.new_gradient(onet.variables), ref.new_rgradient(onet.variables)
+    xg = [[None] * n for n in lens]
+    xrg = [[None] * n for n in lens]
+    outs, routs = res.output_seqs(), res.routput_seqs()
+    for l, s in enumerate(seqs):
+        assert len(outs[l]) == len(s)
+        for t, v in enumerate(s):
+            xv = ref.Variable(v)
+            orv = dict(onet.rvec)
+            orv[xv] = rseqs[l][t]
+            r = per.apply_r(orv, ref.RVariable(xv, orv))
+            close(outs[l][t], r.output(), f"lane {l} t {t}")
+            close(routs[l][t], r.routput(), f"lane {l} t {t} R")
+            g1, rg1 = {xv: np.zeros(4)}, {xv: np.zeros(4)}
+            g1.update(ograd)
+            rg1.update(orgrad)
+            r.propagate_rgradient(ups[l][t].copy(), uprs[l][t].copy(), rg1, g1)
+            xg[l][t], xrg[l][t] = g1[xv], rg1[xv]
+    grad, rgrad = api.new_gradient(pvars + [xin]), api.new_rgradient(pvars + [xin])
+    res.propagate_rgradient(ups, uprs, rgrad, grad)
+    for i, (pv, ov) in enumerate(zip(pvars, onet.variables)):
+        close(grad[pv], ograd[ov], f"grad[{i}]")
+        close(rgrad[pv], orgrad[ov], f"rgrad[{i}]")
+    shape = seq.PackedSeqs(plens, widths, api.context().upload(flat))
+    for got, want, what in ((shape.unpack_host(grad[xin]), xg, "input grad"), (shape.unpack_host(rgrad[xin]), xrg, "input rgrad")):
+        for l in range(len(lens)):
+            for t in range(lens[l]):
+                close(got[l][t], want[l][t], f"{what} lane {l} t {t}")
+    assert set(grad) == set(pvars + [xin])  # temporaries deleted again (map_batcher.go:136-137)
+    # the host joinTime path gives the same sequences
+    res_h = seq.MapRBatcher(layers).apply_seqs_r(prv, seq.ConstRResult(seqs))
+    for l in range(len(lens)):
+        for t in range(lens[l]):
+            close(outs[l][t], res_h.output_seqs()[l][t], f"host path lane {l} t {t}")
+    # non-R mapping over a constant packed list, device-resident gradient map
+    res2 = seq.MapBatcher(layers).apply_seqs(seq.PackedConstResult.from_host(seqs))
+    dg = api.DeviceGradient(pvars)
+    res2.propagate_gradient(ups, dg)
+    for i, (pv, ov) in enumerate(zip(pvars, onet.variables)):
+        close(dg.host()[pv], ograd[ov], f"device grad[{i}]")
