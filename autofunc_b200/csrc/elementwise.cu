@@ -81,7 +81,8 @@ __global__ void sum_final_kernel(const double* __restrict__ part, int nparts, do
 int colsum_launch(af_ctx* ctx, const double* U, const double* UR, double* gb, double* rgb, long long len, long long n) {
   if (len <= 0 || n <= 0 || (!gb && !rgb)) return AF_OK;
   const long long colblocks = (len + 31) / 32;
-  long long want = (2ll * ctx->sm_count + colblocks - 1) / colblocks;
+  // 8 resident CTAs per SM: with two row loads in flight per thread that is what it takes to cover the HBM latency
+  long long want = (8ll * ctx->sm_count + colblocks - 1) / colblocks;
   long long maxsplit = (n + 63) / 64;
   if (want > maxsplit) want = maxsplit;
   if (want < 1) want = 1;
@@ -101,18 +102,20 @@ extern "C" {
 int af_bias_fwd(af_ctx* ctx, const double* X, const double* b, double* Y, int64_t len, int64_t n) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(b); AF_NEED(Y);
   if (len < 0 || n < 0) return fail(AF_ESHAPE, "negative length");
-  return ew_launch(ctx, len * n, "bias_fwd", 16, [=] __device__(long long i) { Y[i] = X[i] + b[i % len]; });
+  return ew_launch(ctx, len * n, "bias_fwd", 16, EwIn<1>{{X}}, EwOut<1>{{Y}},
+                   [=] __device__(long long i, const double* x, double* y) { y[0] = x[0] + b[i % len]; });
 }
 
 int af_bias_fwd_r(af_ctx* ctx, const double* X, const double* RX, const double* b, const double* Rb, double* Y,
                   double* RY, int64_t len, int64_t n) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(b); AF_NEED(Y); AF_NEED(RY);
   if (len < 0 || n < 0) return fail(AF_ESHAPE, "negative length");
-  return ew_launch(ctx, len * n, "bias_fwd_r", 32, [=] __device__(long long i) {
-    const long long c = i % len;
-    Y[i] = X[i] + b[c];
-    RY[i] = (RX ? RX[i] : 0.0) + (Rb ? Rb[c] : 0.0);
-  });
+  return ew_launch(ctx, len * n, "bias_fwd_r", 32, EwIn<2>{{X, RX}}, EwOut<2>{{Y, RY}},
+                   [=] __device__(long long i, const double* x, double* y) {
+                     const long long c = i % len;
+                     y[0] = x[0] + b[c];
+                     y[1] = x[1] + (Rb ? Rb[c] : 0.0);
+                   });
 }
 
 int af_bias_grad(af_ctx* ctx, const double* U, double* gb, int64_t len, int64_t n) {
@@ -129,122 +132,132 @@ int af_bias_grad_r(af_ctx* ctx, const double* U, const double* UR, double* gb, d
 
 int af_sigmoid_fwd(af_ctx* ctx, const double* X, double* S, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(S);
-  return ew_launch(ctx, len, "sigmoid_fwd", 16, [=] __device__(long long i) { S[i] = sigm(X[i]); });
+  return ew_launch(ctx, len, "sigmoid_fwd", 16, EwIn<1>{{X}}, EwOut<1>{{S}},
+                   [=] __device__(long long, const double* x, double* y) { y[0] = sigm(x[0]); });
 }
 
 int af_sigmoid_fwd_r(af_ctx* ctx, const double* X, const double* RX, double* S, double* RS, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(S); AF_NEED(RS);
-  return ew_launch(ctx, len, "sigmoid_fwd_r", 32, [=] __device__(long long i) {
-    const double s = sigm(X[i]);
-    S[i] = s;
-    RS[i] = s * (1 - s) * (RX ? RX[i] : 0.0);
-  });
+  return ew_launch(ctx, len, "sigmoid_fwd_r", 32, EwIn<2>{{X, RX}}, EwOut<2>{{S, RS}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     const double s = sigm(x[0]);
+                     y[0] = s;
+                     y[1] = s * (1 - s) * x[1];
+                   });
 }
 
 int af_sigmoid_bwd(af_ctx* ctx, const double* S, double* U, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(S); AF_NEED(U);
-  return ew_launch(ctx, len, "sigmoid_bwd", 24, [=] __device__(long long i) {
-    const double x = S[i];
-    U[i] *= x * (1 - x);
-  });
+  return ew_launch(ctx, len, "sigmoid_bwd", 24, EwIn<2>{{S, U}}, EwOut<1>{{U}},
+                   [=] __device__(long long, const double* x, double* y) { y[0] = x[1] * (x[0] * (1 - x[0])); });
 }
 
 int af_sigmoid_bwd_r(af_ctx* ctx, const double* S, const double* RS, double* U, double* UR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(S); AF_NEED(RS); AF_NEED(U); AF_NEED(UR);
-  return ew_launch(ctx, len, "sigmoid_bwd_r", 48, [=] __device__(long long i) {
-    const double x = S[i], xr = RS[i], p = U[i], pr = UR[i];
-    U[i] = x * (1 - x) * p;
-    UR[i] = xr * (1 - x) * p - x * xr * p + x * (1 - x) * pr;
-  });
+  return ew_launch(ctx, len, "sigmoid_bwd_r", 48, EwIn<4>{{S, RS, U, UR}}, EwOut<2>{{U, UR}},
+                   [=] __device__(long long, const double* v, double* y) {
+                     const double x = v[0], xr = v[1], p = v[2], pr = v[3];
+                     y[0] = x * (1 - x) * p;
+                     y[1] = xr * (1 - x) * p - x * xr * p + x * (1 - x) * pr;
+                   });
 }
 
 int af_exp_fwd(af_ctx* ctx, const double* X, double* E, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(E);
-  return ew_launch(ctx, len, "exp_fwd", 16, [=] __device__(long long i) { E[i] = exp(X[i]); });
+  return ew_launch(ctx, len, "exp_fwd", 16, EwIn<1>{{X}}, EwOut<1>{{E}},
+                   [=] __device__(long long, const double* x, double* y) { y[0] = exp(x[0]); });
 }
 
 int af_exp_fwd_r(af_ctx* ctx, const double* X, const double* RX, double* E, double* RE, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(E); AF_NEED(RE);
-  return ew_launch(ctx, len, "exp_fwd_r", 32, [=] __device__(long long i) {
-    const double e = exp(X[i]);
-    E[i] = e;
-    RE[i] = e * (RX ? RX[i] : 0.0);
-  });
+  return ew_launch(ctx, len, "exp_fwd_r", 32, EwIn<2>{{X, RX}}, EwOut<2>{{E, RE}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     const double e = exp(x[0]);
+                     y[0] = e;
+                     y[1] = e * x[1];
+                   });
 }
 
 int af_exp_bwd(af_ctx* ctx, const double* E, double* U, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(E); AF_NEED(U);
-  return ew_launch(ctx, len, "exp_bwd", 24, [=] __device__(long long i) { U[i] *= E[i]; });
+  return ew_launch(ctx, len, "exp_bwd", 24, EwIn<2>{{E, U}}, EwOut<1>{{U}},
+                   [=] __device__(long long, const double* x, double* y) { y[0] = x[1] * x[0]; });
 }
 
 int af_exp_bwd_r(af_ctx* ctx, const double* E, const double* RE, double* U, double* UR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(E); AF_NEED(RE); AF_NEED(U); AF_NEED(UR);
-  return ew_launch(ctx, len, "exp_bwd_r", 48, [=] __device__(long long i) {
-    const double u = U[i], x = E[i], xr = RE[i];
-    U[i] = u * x;
-    UR[i] = UR[i] * x + u * xr;
-  });
+  return ew_launch(ctx, len, "exp_bwd_r", 48, EwIn<4>{{E, RE, U, UR}}, EwOut<2>{{U, UR}},
+                   [=] __device__(long long, const double* v, double* y) {
+                     const double x = v[0], xr = v[1], u = v[2];
+                     y[0] = u * x;
+                     y[1] = v[3] * x + u * xr;
+                   });
 }
 
 int af_add(af_ctx* ctx, const double* a, const double* b, double* out, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(a); AF_NEED(b); AF_NEED(out);
-  return ew_launch(ctx, len, "add", 24, [=] __device__(long long i) { out[i] = a[i] + b[i]; });
+  return ew_launch(ctx, len, "add", 24, EwIn<2>{{a, b}}, EwOut<1>{{out}},
+                   [=] __device__(long long, const double* x, double* y) { y[0] = x[0] + x[1]; });
 }
 
 int af_sub(af_ctx* ctx, const double* a, const double* b, double* out, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(a); AF_NEED(b); AF_NEED(out);
-  return ew_launch(ctx, len, "sub", 24, [=] __device__(long long i) { out[i] = a[i] - b[i]; });
+  return ew_launch(ctx, len, "sub", 24, EwIn<2>{{a, b}}, EwOut<1>{{out}},
+                   [=] __device__(long long, const double* x, double* y) { y[0] = x[0] - x[1]; });
 }
 
 int af_mul(af_ctx* ctx, const double* a, const double* b, double* out, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(a); AF_NEED(b); AF_NEED(out);
-  return ew_launch(ctx, len, "mul", 24, [=] __device__(long long i) { out[i] = a[i] * b[i]; });
+  return ew_launch(ctx, len, "mul", 24, EwIn<2>{{a, b}}, EwOut<1>{{out}},
+                   [=] __device__(long long, const double* x, double* y) { y[0] = x[0] * x[1]; });
 }
 
 int af_mul_r(af_ctx* ctx, const double* a, const double* aR, const double* b, const double* bR, double* out,
              int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(a); AF_NEED(b); AF_NEED(out);
-  return ew_launch(ctx, len, "mul_r", 40, [=] __device__(long long i) {
-    out[i] = a[i] * (bR ? bR[i] : 0.0) + (aR ? aR[i] : 0.0) * b[i];
-  });
+  return ew_launch(ctx, len, "mul_r", 40, EwIn<4>{{a, aR, b, bR}}, EwOut<1>{{out}},
+                   [=] __device__(long long, const double* x, double* y) { y[0] = x[0] * x[3] + x[1] * x[2]; });
 }
 
 int af_mul_bwd(af_ctx* ctx, const double* U, const double* UR, const double* o, const double* oR, double* D,
                double* DR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(U); AF_NEED(o); AF_NEED(D);
-  return ew_launch(ctx, len, "mul_bwd", 56, [=] __device__(long long i) {
-    const double x = U[i], oo = o[i];
-    if (DR) DR[i] = x * (oR ? oR[i] : 0.0) + (UR ? UR[i] : 0.0) * oo;
-    D[i] = x * oo;
-  });
+  return ew_launch(ctx, len, "mul_bwd", 56, EwIn<4>{{U, DR ? UR : nullptr, o, DR ? oR : nullptr}}, EwOut<2>{{D, DR}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     y[1] = x[0] * x[3] + x[1] * x[2];
+                     y[0] = x[0] * x[2];
+                   });
 }
 
 int af_scale(af_ctx* ctx, double* x, double f, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(x);
-  return ew_launch(ctx, len, "scale", 16, [=] __device__(long long i) { x[i] *= f; });
+  return ew_launch(ctx, len, "scale", 16, EwIn<1>{{x}}, EwOut<1>{{x}},
+                   [=] __device__(long long, const double* v, double* y) { y[0] = v[0] * f; });
 }
 
 int af_axpy(af_ctx* ctx, double f, const double* x, double* y, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(x); AF_NEED(y);
-  return ew_launch(ctx, len, "axpy", 24, [=] __device__(long long i) { y[i] += f * x[i]; });
+  return ew_launch(ctx, len, "axpy", 24, EwIn<2>{{x, y}}, EwOut<1>{{y}},
+                   [=] __device__(long long, const double* v, double* o) { o[0] = v[1] + f * v[0]; });
 }
 
 int af_square_fwd_r(af_ctx* ctx, const double* X, const double* RX, double* O, double* RO, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(O);
-  return ew_launch(ctx, len, "square_fwd_r", 32, [=] __device__(long long i) {
-    const double x = X[i];
-    O[i] = x * x;
-    if (RO) RO[i] = 2 * x * (RX ? RX[i] : 0.0);
-  });
+  return ew_launch(ctx, len, "square_fwd_r", 32, EwIn<2>{{X, RO ? RX : nullptr}}, EwOut<2>{{O, RO}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     y[0] = x[0] * x[0];
+                     y[1] = 2 * x[0] * x[1];
+                   });
 }
 
 int af_square_bwd_r(af_ctx* ctx, const double* X, const double* RX, double* U, double* UR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(U);
-  return ew_launch(ctx, len, "square_bwd_r", 48, [=] __device__(long long i) {
-    const double x = X[i], u = U[i];
-    if (UR) UR[i] = 2 * (UR[i] * x + u * (RX ? RX[i] : 0.0));
-    U[i] = u * (x * 2);
-  });
+  return ew_launch(ctx, len, "square_bwd_r", 48, EwIn<4>{{X, UR ? RX : nullptr, U, UR}}, EwOut<2>{{U, UR}},
+                   [=] __device__(long long, const double* v, double* y) {
+                     const double x = v[0], u = v[2];
+                     y[1] = 2 * (v[3] * x + u * v[1]);
+                     y[0] = u * (x * 2);
+                   });
 }
 
 int af_sum_all(af_ctx* ctx, const double* x, const double* xR, double* out, double* outR, int64_t len) {
@@ -263,7 +276,8 @@ int af_sum_all(af_ctx* ctx, const double* x, const double* xR, double* out, doub
 
 int af_fill(af_ctx* ctx, double* x, double value, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(x);
-  return ew_launch(ctx, len, "fill", 8, [=] __device__(long long i) { x[i] = value; });
+  return ew_launch(ctx, len, "fill", 8, EwIn<1>{{nullptr}}, EwOut<1>{{x}},
+                   [=] __device__(long long, const double*, double* y) { y[0] = value; });
 }
 
 }  // extern "C"

@@ -9,17 +9,25 @@
 #include "common.h"
 #include "ew.cuh"
 
+#include <algorithm>
+
 namespace af {
 namespace {
 
-__device__ __forceinline__ double rd(const double* p, long long i) { return p ? p[i] : 0.0; }
+__device__ __forceinline__ double rd(const double* p, long long i) { return p ? p[i] : 0.0; }  // NULL R operand = 0
 
 // ---- row-wise softmax ----------------------------------------------------------------------------
-// A group of G threads owns one row (G = 32: one warp, rows up to ~1k entries; G = 256: one block).
+// A group of G threads owns one row: G = 8 / 16 / 32 lanes of a warp for short rows (several rows per warp, so a
+// 10-class head still issues full coalesced warps), G = 256 (one block) for long ones.  Each thread keeps its first
+// kRowCache exponentials in registers, so rows up to G * kRowCache entries are read from HBM once and exp() is
+// evaluated once; only the excess of longer rows is recomputed from L2.
+constexpr int kRowCache = 8;
+
 template <int G>
 __device__ __forceinline__ double group_sum(double v, double* sm) {
-  v = warp_sum(v);
-  if (G == 32) return v;
+#pragma unroll
+  for (int o = (G < 32 ? G : 32) / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (G <= 32) return v;
   const int w = threadIdx.x >> 5;
   __syncthreads();  // sm may still be read by the previous reduction
   if ((threadIdx.x & 31) == 0) sm[w] = v;
@@ -38,27 +46,49 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const double* __restri
                                                           long long len, long long n) {
   __shared__ double sm[8];
   const int lane = threadIdx.x % G;
-  const long long row = (long long)blockIdx.x * (256 / G) + threadIdx.x / G;
-  const bool live = row < n;  // G == 256: whole block shares `live`; G == 32: whole warp does
-  if (G == 32 && !live) return;
+  constexpr int RPB = 256 / G;  // rows per block pass; the block walks the rows persistently
+  for (long long row0 = (long long)blockIdx.x * RPB; row0 < n; row0 += (long long)gridDim.x * RPB) {
+  const long long row = row0 + threadIdx.x / G;
+  const bool live = row < n;  // a dead group still takes part in the shuffles / barriers (its sums are zero)
   const double* x = X + row * len;
   const double* xr = RX ? RX + row * len : nullptr;
+  double ev[kRowCache], erv[kRowCache];
   double s = 0.0, sr = 0.0;
-  if (live)
-    for (long long k = lane; k < len; k += G) {
+  if (live) {
+#pragma unroll
+    for (int j = 0; j < kRowCache; ++j) {
+      const long long k = lane + (long long)j * G;
+      ev[j] = erv[j] = 0.0;
+      if (k < len) {
+        ev[j] = exp(x[k] * invT);
+        s += ev[j];
+        if (RY) { erv[j] = ev[j] * (rd(xr, k) * invT); sr += erv[j]; }
+      }
+    }
+    for (long long k = lane + (long long)kRowCache * G; k < len; k += G) {
       const double e = exp(x[k] * invT);
       s += e;
       if (RY) sr += e * (rd(xr, k) * invT);
     }
+  }
   s = group_sum<G>(s, sm);
   if (RY) sr = group_sum<G>(sr, sm);
-  if (!live) return;
+  if (!live) continue;
   const double inv = 1.0 / s;
   const double invR = -(inv * inv) * sr;
-  for (long long k = lane; k < len; k += G) {
+#pragma unroll
+  for (int j = 0; j < kRowCache; ++j) {
+    const long long k = lane + (long long)j * G;
+    if (k < len) {
+      Y[row * len + k] = ev[j] * inv;
+      if (RY) RY[row * len + k] = ev[j] * invR + erv[j] * inv;
+    }
+  }
+  for (long long k = lane + (long long)kRowCache * G; k < len; k += G) {
     const double e = exp(x[k] * invT);
     Y[row * len + k] = e * inv;
     if (RY) RY[row * len + k] = e * invR + (e * (rd(xr, k) * invT)) * inv;
+  }
   }
 }
 
@@ -70,32 +100,61 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const double* __restri
                                                           long long len, long long n) {
   __shared__ double sm[8];
   const int lane = threadIdx.x % G;
-  const long long row = (long long)blockIdx.x * (256 / G) + threadIdx.x / G;
+  constexpr int RPB = 256 / G;
+  for (long long row0 = (long long)blockIdx.x * RPB; row0 < n; row0 += (long long)gridDim.x * RPB) {
+  const long long row = row0 + threadIdx.x / G;
   const bool live = row < n;
-  if (G == 32 && !live) return;
   const long long o = row * len;
+  double uv[kRowCache], yv[kRowCache], urv[kRowCache], ryv[kRowCache];
   double a = 0.0, b = 0.0;  // <u,y> ; <uR,y> + <u,yR>
-  if (live)
-    for (long long k = lane; k < len; k += G) {
+  if (live) {
+#pragma unroll
+    for (int j = 0; j < kRowCache; ++j) {
+      const long long k = lane + (long long)j * G;
+      uv[j] = yv[j] = urv[j] = ryv[j] = 0.0;
+      if (k < len) {
+        uv[j] = U[o + k]; yv[j] = Y[o + k];
+        a += uv[j] * yv[j];
+        if (UR) { urv[j] = UR[o + k]; ryv[j] = rd(RY, o + k); b += urv[j] * yv[j] + uv[j] * ryv[j]; }
+      }
+    }
+    for (long long k = lane + (long long)kRowCache * G; k < len; k += G) {
       const double u = U[o + k], y = Y[o + k];
       a += u * y;
       if (UR) b += UR[o + k] * y + u * rd(RY, o + k);
     }
+  }
   a = group_sum<G>(a, sm);
   if (UR) b = group_sum<G>(b, sm);
-  if (!live) return;
-  for (long long k = lane; k < len; k += G) {
+  if (!live) continue;
+#pragma unroll
+  for (int j = 0; j < kRowCache; ++j) {
+    const long long k = lane + (long long)j * G;
+    if (k < len) {
+      if (UR) UR[o + k] = invT * (ryv[j] * (uv[j] - a) + yv[j] * (urv[j] - b));
+      U[o + k] = invT * (yv[j] * (uv[j] - a));
+    }
+  }
+  for (long long k = lane + (long long)kRowCache * G; k < len; k += G) {
     const double u = U[o + k], y = Y[o + k];
     if (UR) UR[o + k] = invT * (rd(RY, o + k) * (u - a) + y * (UR[o + k] - b));
     U[o + k] = invT * (y * (u - a));
   }
+  }
 }
 
-template <typename K32, typename K256>
-void row_launch(af_ctx* ctx, long long len, long long n, K32 k32, K256 k256) {
-  if (len <= 1024) k32((unsigned)((n + 7) / 8));
-  else k256((unsigned)n);
-}
+// group width for a row length: the smallest sub-warp that covers the row in <= 2 strides, a full warp up to
+// 32 * kRowCache entries, one block beyond that
+// one block pass per 256/G rows (measured: capping the grid and walking rows persistently is slower -- a block's rows
+// then serialise on the load -> reduce -> store dependency; softmax_bwd rows of 1024: 4.5 vs 2.4 TB/s)
+#define AF_ROW_GRID(G) (unsigned)((n + 256 / (G) - 1) / (256 / (G)))
+#define AF_ROW_DISPATCH(KERNEL, ...)                                                              \
+  do {                                                                                            \
+    if (len <= 16) KERNEL<8><<<AF_ROW_GRID(8), 256, 0, ctx->stream>>>(__VA_ARGS__);               \
+    else if (len <= 32) KERNEL<16><<<AF_ROW_GRID(16), 256, 0, ctx->stream>>>(__VA_ARGS__);        \
+    else if (len <= 32 * kRowCache) KERNEL<32><<<AF_ROW_GRID(32), 256, 0, ctx->stream>>>(__VA_ARGS__); \
+    else KERNEL<256><<<AF_ROW_GRID(256), 256, 0, ctx->stream>>>(__VA_ARGS__);                     \
+  } while (0)
 
 }  // namespace
 }  // namespace af
@@ -107,154 +166,172 @@ extern "C" {
 // ---- Log (math_funcs.go:99-189) --------------------------------------------------------------------
 int af_log_fwd_r(af_ctx* ctx, const double* X, const double* RX, double* O, double* RO, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(O);
-  return ew_launch(ctx, len, "log_fwd_r", RO ? 32 : 16, [=] __device__(long long i) {
-    const double x = X[i];
-    O[i] = log(x);
-    if (RO) RO[i] = rd(RX, i) / x;
-  });
+  return ew_launch(ctx, len, "log_fwd_r", RO ? 32 : 16, EwIn<2>{{X, RO ? RX : nullptr}}, EwOut<2>{{O, RO}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     y[0] = log(x[0]);
+                     y[1] = x[1] / x[0];
+                   });
 }
 
 int af_log_bwd_r(af_ctx* ctx, const double* X, const double* RX, double* U, double* UR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(U);
-  return ew_launch(ctx, len, "log_bwd_r", UR ? 48 : 24, [=] __device__(long long i) {
-    const double x = X[i], u = U[i];
-    if (UR) UR[i] = UR[i] / x - u * rd(RX, i) / (x * x);
-    U[i] = UR ? u / x : u * (1 / x);  // math_funcs.go:150 multiplies by 1/x, :184 divides
-  });
+  const bool r = UR != nullptr;
+  return ew_launch(ctx, len, "log_bwd_r", r ? 48 : 24, EwIn<4>{{X, r ? RX : nullptr, U, UR}}, EwOut<2>{{U, UR}},
+                   [=] __device__(long long, const double* v, double* y) {
+                     const double x = v[0], u = v[2];
+                     y[1] = v[3] / x - u * v[1] / (x * x);
+                     y[0] = r ? u / x : u * (1 / x);  // math_funcs.go:150 multiplies by 1/x, :184 divides
+                   });
 }
 
 // ---- LogSigmoid (math_funcs.go:376-477) -------------------------------------------------------------
 int af_logsigmoid_fwd_r(af_ctx* ctx, const double* X, const double* RX, double* O, double* RO, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(O);
-  return ew_launch(ctx, len, "logsigmoid_fwd_r", RO ? 32 : 16, [=] __device__(long long i) {
-    const double x = X[i];
-    O[i] = x > 0 ? -log(1 + exp(-x)) : x - log(1 + exp(x));
-    if (RO) RO[i] = rd(RX, i) / (1 + exp(x));
-  });
+  const bool r = RO != nullptr;
+  return ew_launch(ctx, len, "logsigmoid_fwd_r", r ? 32 : 16, EwIn<2>{{X, r ? RX : nullptr}}, EwOut<2>{{O, RO}},
+                   [=] __device__(long long, const double* v, double* y) {
+                     const double x = v[0];
+                     y[0] = x > 0 ? -log(1 + exp(-x)) : x - log(1 + exp(x));
+                     if (r) y[1] = v[1] / (1 + exp(x));
+                   });
 }
 
 int af_logsigmoid_bwd_r(af_ctx* ctx, const double* X, const double* RX, double* U, double* UR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(U);
-  return ew_launch(ctx, len, "logsigmoid_bwd_r", UR ? 48 : 24, [=] __device__(long long i) {
-    const double u = U[i], ex = exp(X[i]);
-    if (UR) {
-      const double s = 1 / (1 + ex);
-      UR[i] = UR[i] * s - u * s * s * ex * rd(RX, i);
-      U[i] = u * s;
-    } else {
-      U[i] = u / (1 + ex);
-    }
-  });
+  const bool r = UR != nullptr;
+  return ew_launch(ctx, len, "logsigmoid_bwd_r", r ? 48 : 24, EwIn<4>{{X, r ? RX : nullptr, U, UR}}, EwOut<2>{{U, UR}},
+                   [=] __device__(long long, const double* v, double* y) {
+                     const double u = v[2], ex = exp(v[0]);
+                     if (r) {
+                       const double s = 1 / (1 + ex);
+                       y[1] = v[3] * s - u * s * s * ex * v[1];
+                       y[0] = u * s;
+                     } else {
+                       y[0] = u / (1 + ex);
+                     }
+                   });
 }
 
 // ---- Sin (math_funcs.go:511-597); Cos = Sin(AddScaler(x, pi/2)) on the host side --------------------
 int af_sin_fwd_r(af_ctx* ctx, const double* X, const double* RX, double* O, double* RO, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(O);
-  return ew_launch(ctx, len, "sin_fwd_r", RO ? 32 : 16, [=] __device__(long long i) {
-    double s, c;
-    sincos(X[i], &s, &c);
-    O[i] = s;
-    if (RO) RO[i] = c * rd(RX, i);
-  });
+  return ew_launch(ctx, len, "sin_fwd_r", RO ? 32 : 16, EwIn<2>{{X, RO ? RX : nullptr}}, EwOut<2>{{O, RO}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     double s, c;
+                     sincos(x[0], &s, &c);
+                     y[0] = s;
+                     y[1] = c * x[1];
+                   });
 }
 
 int af_sin_bwd_r(af_ctx* ctx, const double* X, const double* RX, double* U, double* UR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(U);
-  return ew_launch(ctx, len, "sin_bwd_r", UR ? 48 : 24, [=] __device__(long long i) {
-    double s, c;
-    sincos(X[i], &s, &c);
-    const double u = U[i];
-    if (UR) UR[i] = UR[i] * c + u * (-s * rd(RX, i));
-    U[i] = u * c;
-  });
+  return ew_launch(ctx, len, "sin_bwd_r", UR ? 48 : 24, EwIn<4>{{X, UR ? RX : nullptr, U, UR}}, EwOut<2>{{U, UR}},
+                   [=] __device__(long long, const double* v, double* y) {
+                     double s, c;
+                     sincos(v[0], &s, &c);
+                     const double u = v[2];
+                     y[1] = v[3] * c + u * (-s * v[1]);
+                     y[0] = u * c;
+                   });
 }
 
 // ---- Tanh: extension named by the north star, same contract as Sigmoid (T, RT kept by the caller) ----
 int af_tanh_fwd_r(af_ctx* ctx, const double* X, const double* RX, double* T, double* RT, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(T);
-  return ew_launch(ctx, len, "tanh_fwd_r", RT ? 32 : 16, [=] __device__(long long i) {
-    const double t = tanh(X[i]);
-    T[i] = t;
-    if (RT) RT[i] = (1 - t * t) * rd(RX, i);
-  });
+  return ew_launch(ctx, len, "tanh_fwd_r", RT ? 32 : 16, EwIn<2>{{X, RT ? RX : nullptr}}, EwOut<2>{{T, RT}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     const double t = tanh(x[0]);
+                     y[0] = t;
+                     y[1] = (1 - t * t) * x[1];
+                   });
 }
 
 int af_tanh_bwd_r(af_ctx* ctx, const double* T, const double* RT, double* U, double* UR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(T); AF_NEED(U);
-  return ew_launch(ctx, len, "tanh_bwd_r", UR ? 48 : 24, [=] __device__(long long i) {
-    const double t = T[i], u = U[i];
-    if (UR) UR[i] = (1 - t * t) * UR[i] - 2 * t * rd(RT, i) * u;
-    U[i] = (1 - t * t) * u;
-  });
+  return ew_launch(ctx, len, "tanh_bwd_r", UR ? 48 : 24, EwIn<4>{{T, UR ? RT : nullptr, U, UR}}, EwOut<2>{{U, UR}},
+                   [=] __device__(long long, const double* v, double* y) {
+                     const double t = v[0], u = v[2];
+                     y[1] = (1 - t * t) * v[3] - 2 * t * v[1] * u;
+                     y[0] = (1 - t * t) * u;
+                   });
 }
 
 // ---- Inverse (arithmetic.go:772-867) ------------------------------------------------------------------
 int af_inverse_fwd_r(af_ctx* ctx, const double* X, const double* RX, double* O, double* RO, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(O);
-  return ew_launch(ctx, len, "inverse_fwd_r", RO ? 32 : 16, [=] __device__(long long i) {
-    const double r = 1 / X[i];
-    O[i] = r;
-    if (RO) RO[i] = -(r * r) * rd(RX, i);
-  });
+  return ew_launch(ctx, len, "inverse_fwd_r", RO ? 32 : 16, EwIn<2>{{X, RO ? RX : nullptr}}, EwOut<2>{{O, RO}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     const double r = 1 / x[0];
+                     y[0] = r;
+                     y[1] = -(r * r) * x[1];
+                   });
 }
 
 // O = the forward output 1/x
 int af_inverse_bwd_r(af_ctx* ctx, const double* O, const double* RX, double* U, double* UR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(O); AF_NEED(U);
-  return ew_launch(ctx, len, "inverse_bwd_r", UR ? 48 : 24, [=] __device__(long long i) {
-    const double o = O[i], u = U[i], sq = -(o * o);
-    if (UR) UR[i] = sq * UR[i] + -2 * (sq * o) * rd(RX, i) * u;
-    U[i] = sq * u;
-  });
+  return ew_launch(ctx, len, "inverse_bwd_r", UR ? 48 : 24, EwIn<4>{{O, UR ? RX : nullptr, U, UR}}, EwOut<2>{{U, UR}},
+                   [=] __device__(long long, const double* v, double* y) {
+                     const double o = v[0], u = v[2], sq = -(o * o);
+                     y[1] = sq * v[3] + -2 * (sq * o) * v[1] * u;
+                     y[0] = sq * u;
+                   });
 }
 
 // ---- Pow (arithmetic.go:869-966) ----------------------------------------------------------------------
 int af_pow_fwd_r(af_ctx* ctx, const double* X, const double* RX, double p, double* O, double* RO, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(O);
-  return ew_launch(ctx, len, "pow_fwd_r", RO ? 32 : 16, [=] __device__(long long i) {
-    const double x = X[i];
-    O[i] = pow(x, p);
-    if (RO) RO[i] = p != 0 ? p * pow(x, p - 1) * rd(RX, i) : 0.0;
-  });
+  const bool r = RO != nullptr;
+  return ew_launch(ctx, len, "pow_fwd_r", r ? 32 : 16, EwIn<2>{{X, r ? RX : nullptr}}, EwOut<2>{{O, RO}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     y[0] = pow(x[0], p);
+                     if (r) y[1] = p != 0 ? p * pow(x[0], p - 1) * x[1] : 0.0;
+                   });
 }
 
 int af_pow_bwd_r(af_ctx* ctx, const double* X, const double* RX, double p, double* U, double* UR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(U);
   if (p == 1) return AF_OK;  // arithmetic.go:898,952: upstream passes through untouched
-  return ew_launch(ctx, len, "pow_bwd_r", UR ? 48 : 24, [=] __device__(long long i) {
-    const double x = X[i], u = U[i];
-    const double d1 = p * pow(x, p - 1);
-    if (UR) UR[i] = UR[i] * d1 + u * (p * (p - 1) * pow(x, p - 2) * rd(RX, i));
-    U[i] = u * d1;
-  });
+  const bool r = UR != nullptr;
+  return ew_launch(ctx, len, "pow_bwd_r", r ? 48 : 24, EwIn<4>{{X, r ? RX : nullptr, U, UR}}, EwOut<2>{{U, UR}},
+                   [=] __device__(long long, const double* v, double* y) {
+                     const double x = v[0], u = v[2];
+                     const double d1 = p * pow(x, p - 1);
+                     if (r) y[1] = v[3] * d1 + u * (p * (p - 1) * pow(x, p - 2) * v[1]);
+                     y[0] = u * d1;
+                   });
 }
 
 // ---- Div (arithmetic.go:378-423; DivR is MulR(a, InverseR(b)) and needs no kernel of its own) --------
 int af_div(af_ctx* ctx, const double* A, const double* B, double* O, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(A); AF_NEED(B); AF_NEED(O);
-  return ew_launch(ctx, len, "div", 24, [=] __device__(long long i) { O[i] = A[i] / B[i]; });
+  return ew_launch(ctx, len, "div", 24, EwIn<2>{{A, B}}, EwOut<1>{{O}},
+                   [=] __device__(long long, const double* x, double* y) { y[0] = x[0] / x[1]; });
 }
 
 // DA = U / B (numerator's upstream), DB = U * (-O / B) (denominator's); either may be NULL
 int af_div_bwd(af_ctx* ctx, const double* U, const double* O, const double* B, double* DA, double* DB, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(U); AF_NEED(O); AF_NEED(B);
-  return ew_launch(ctx, len, "div_bwd", 40, [=] __device__(long long i) {
-    const double u = U[i], b = B[i];
-    if (DA) DA[i] = u / b;
-    if (DB) DB[i] = u * (-O[i] / b);
-  });
+  return ew_launch(ctx, len, "div_bwd", 40, EwIn<3>{{U, O, B}}, EwOut<2>{{DA, DB}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     y[0] = x[0] / x[2];
+                     y[1] = x[0] * (-x[1] / x[2]);
+                   });
 }
 
 // ---- scalar-broadcast ops: AddScaler, ScaleFirst, AddFirst, SumAll backward ---------------------------
 int af_add_scaler(af_ctx* ctx, const double* X, double f, double* O, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(O);
-  return ew_launch(ctx, len, "add_scaler", 16, [=] __device__(long long i) { O[i] = X[i] + f; });
+  return ew_launch(ctx, len, "add_scaler", 16, EwIn<1>{{X}}, EwOut<1>{{O}},
+                   [=] __device__(long long, const double* x, double* y) { y[0] = x[0] + f; });
 }
 
 // O = X + sign * f[0] with f on the device (AddFirst, arithmetic.go:595-612; the "- maxVal" of the log-domain sums)
 int af_add_dev(af_ctx* ctx, const double* X, const double* d_f, double sign, double* O, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(d_f); AF_NEED(O);
-  return ew_launch(ctx, len, "add_dev", 16, [=] __device__(long long i) { O[i] = X[i] + sign * d_f[0]; });
+  return ew_launch(ctx, len, "add_dev", 16, EwIn<1>{{X}}, EwOut<1>{{O}},
+                   [=] __device__(long long, const double* x, double* y) { y[0] = x[0] + sign * d_f[0]; });
 }
 
 // O = X * f[0];  RO = X * fR[0] + RX * f[0]   (ScaleFirst forward and, applied to the upstreams, its backward:
@@ -262,17 +339,19 @@ int af_add_dev(af_ctx* ctx, const double* X, const double* d_f, double sign, dou
 int af_scale_dev(af_ctx* ctx, const double* X, const double* RX, const double* d_f, const double* d_fR, double* O,
                  double* RO, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(d_f); AF_NEED(O);
-  return ew_launch(ctx, len, "scale_dev", RO ? 32 : 16, [=] __device__(long long i) {
-    const double x = X[i], f = d_f[0];
-    if (RO) RO[i] = x * (d_fR ? d_fR[0] : 0.0) + rd(RX, i) * f;
-    O[i] = x * f;
-  });
+  return ew_launch(ctx, len, "scale_dev", RO ? 32 : 16, EwIn<2>{{X, RO ? RX : nullptr}}, EwOut<2>{{O, RO}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     const double f = d_f[0];
+                     y[1] = x[0] * (d_fR ? d_fR[0] : 0.0) + x[1] * f;
+                     y[0] = x[0] * f;
+                   });
 }
 
 // x[i] = value[0]: SumAll's backward broadcast (arithmetic.go:987-995,1035-1047) without a host round trip
 int af_fill_dev(af_ctx* ctx, double* x, const double* d_value, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(x); AF_NEED(d_value);
-  return ew_launch(ctx, len, "fill_dev", 8, [=] __device__(long long i) { x[i] = d_value[0]; });
+  return ew_launch(ctx, len, "fill_dev", 8, EwIn<1>{{nullptr}}, EwOut<1>{{x}},
+                   [=] __device__(long long, const double*, double* y) { y[0] = d_value[0]; });
 }
 
 // out[0] = sum a.b (+ sum c.d when c, d are given): DotFast at arithmetic.go:523,571-573
@@ -315,11 +394,12 @@ int af_norm_bwd_r(af_ctx* ctx, const double* X, const double* RX, const double* 
                   const double* d_u, const double* d_uR, double* D, double* DR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(X); AF_NEED(d_o); AF_NEED(d_u); AF_NEED(D);
   if (DR) { AF_NEED(d_ro); AF_NEED(d_uR); }
-  return ew_launch(ctx, len, "norm_bwd_r", DR ? 32 : 16, [=] __device__(long long i) {
-    const double o = d_o[0], u = d_u[0], s = u / o, x = X[i];
-    if (DR) DR[i] = x * (-u * d_ro[0] / (o * o) + d_uR[0] / o) + rd(RX, i) * s;
-    D[i] = x * s;
-  });
+  return ew_launch(ctx, len, "norm_bwd_r", DR ? 32 : 16, EwIn<2>{{X, DR ? RX : nullptr}}, EwOut<2>{{D, DR}},
+                   [=] __device__(long long, const double* x, double* y) {
+                     const double o = d_o[0], u = d_u[0], s = u / o;
+                     if (DR) y[1] = x[0] * (-u * d_ro[0] / (o * o) + d_uR[0] / o) + x[1] * s;
+                     y[0] = x[0] * s;
+                   });
 }
 
 // ---- Softmax, one per row of an n x len packed batch (math_funcs.go:479-509 under RFuncBatcher) --------
@@ -329,9 +409,7 @@ int af_softmax_fwd_r(af_ctx* ctx, const double* X, const double* RX, double temp
   if (len < 0 || n < 0) return fail(AF_ESHAPE, "negative length");
   if (len == 0 || n == 0) return AF_OK;
   const double invT = (temperature != 0 && temperature != 1) ? 1 / temperature : 1.0;
-  row_launch(ctx, len, n,
-             [&](unsigned g) { softmax_fwd_kernel<32><<<g, 256, 0, ctx->stream>>>(X, RX, Y, RY, invT, len, n); },
-             [&](unsigned g) { softmax_fwd_kernel<256><<<g, 256, 0, ctx->stream>>>(X, RX, Y, RY, invT, len, n); });
+  AF_ROW_DISPATCH(softmax_fwd_kernel, X, RX, Y, RY, invT, len, n);
   return after_launch(ctx, "softmax_fwd_kernel", KIND_REDUCE, 8.0 * len * n * (RY ? 4 : 2));
 }
 
@@ -341,9 +419,7 @@ int af_softmax_bwd_r(af_ctx* ctx, const double* Y, const double* RY, double temp
   if (len < 0 || n < 0) return fail(AF_ESHAPE, "negative length");
   if (len == 0 || n == 0) return AF_OK;
   const double invT = (temperature != 0 && temperature != 1) ? 1 / temperature : 1.0;
-  row_launch(ctx, len, n,
-             [&](unsigned g) { softmax_bwd_kernel<32><<<g, 256, 0, ctx->stream>>>(Y, RY, U, UR, invT, len, n); },
-             [&](unsigned g) { softmax_bwd_kernel<256><<<g, 256, 0, ctx->stream>>>(Y, RY, U, UR, invT, len, n); });
+  AF_ROW_DISPATCH(softmax_bwd_kernel, Y, RY, U, UR, invT, len, n);
   return after_launch(ctx, "softmax_bwd_kernel", KIND_REDUCE, 8.0 * len * n * (UR ? 6 : 3));
 }
 
@@ -371,11 +447,12 @@ int af_sqerr_bwd_r(af_ctx* ctx, const double* A, const double* RA, const double*
                    const double* d_uR, double sign, double* G, double* GR, int64_t len) {
   AF_CHECK_CTX(ctx); AF_NEED(A); AF_NEED(Y); AF_NEED(d_u); AF_NEED(G);
   if (GR) AF_NEED(d_uR);
-  return ew_launch(ctx, len, "sqerr_bwd_r", GR ? 48 : 24, [=] __device__(long long i) {
-    const double d = A[i] - Y[i], u = d_u[0] * 0.5;
-    if (GR) GR[i] = sign * (2 * ((d_uR[0] * 0.5) * d + u * (rd(RA, i) - rd(RY, i))));
-    G[i] = sign * (u * (d * 2));
-  });
+  return ew_launch(ctx, len, "sqerr_bwd_r", GR ? 48 : 24, EwIn<4>{{A, Y, GR ? RA : nullptr, GR ? RY : nullptr}},
+                   EwOut<2>{{G, GR}}, [=] __device__(long long, const double* x, double* y) {
+                     const double d = x[0] - x[1], u = d_u[0] * 0.5;
+                     if (GR) y[1] = sign * (2 * ((d_uR[0] * 0.5) * d + u * (x[2] - x[3])));
+                     y[0] = sign * (u * (d * 2));
+                   });
 }
 
 }  // extern "C"

@@ -88,6 +88,14 @@ def lintran_config(ctx, steps):
         api.check(L.af_axpy(h, 1.0, D.ptr, gX.ptr, n * cols))
         api.check(L.af_axpy(h, 1.0, DR.ptr, rgX.ptr, n * cols))
     ms = timed(step, steps)
+    if os.environ.get("AF_TRACE"):
+        cap = 256
+        kinds, work, msa, cnt = (C.c_int * cap)(), (C.c_double * cap)(), (C.c_float * cap)(), C.c_int(0)
+        api.check(ctx.lib.af_trace_begin(ctx.h, cap))
+        step()
+        api.check(ctx.lib.af_trace_end(ctx.h, cap, kinds, work, msa, C.byref(cnt)))
+        for i in range(cnt.value):
+            print(f"  [{i:2d}] kind={kinds[i]} work={work[i]:.4g} {msa[i] * 1e3:7.1f} us", file=sys.stderr)
     algo_bytes = 8 * 8 * rows * cols  # W, RW read twice + gW, rgW read-modify-write
     print(json.dumps({"config": "C1 lintran 1024x2048 n=10 fwd+Grad+RGrad", "ms_per_step": ms, "us_per_step": ms * 1e3,
                       "algorithmic_GBps": algo_bytes / ms / 1e6, "samples_per_s": n / ms * 1e3}), flush=True)
