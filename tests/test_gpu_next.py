@@ -442,3 +442,44 @@ def test_packed_map_rbatcher_matches_host_path_and_oracle(api):
     res2.propagate_gradient(ups, dg)
     for i, (pv, ov) in enumerate(zip(pvars, onet.variables)):
         close(dg.host()[pv], ograd[ov], f"device grad[{i}]")
+
+
+def test_map_batcher_output_on_reference_seq_fixtures(api):
+    """seqfunc/test/map_test.go:88-120 (TestMapBatcherOutput) on the reference's own TestSeqs / TranMatrix fixtures
+    (tests/golden/reference_fixtures.json): mapping the Batcher over the lanes -- through the host joinTime path AND
+    the packed device path -- equals applying the Func vector by vector; gradients/R-gradients of TranMatrix equal the
+    oracle's per-vector sums."""
+    import json
+    import os
+    from autofunc_b200 import seq
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_fixtures.json")))["seqfunc/test/map_test.go"]
+    tv = [np.array(v) for v in G["TestVars"]]
+    lanes = [[0, 1, 2], [2, 0, 3], [1], [3], [0, 3]]  # map_test.go:28-34
+    seqs = [[tv[i] for i in lane] for lane in lanes]
+    M, RM = np.array(G["TranMatrix"]), np.array(G["rv_TranMatrix"])
+    pm = api.Variable(M)
+    plt = api.LinTran(pm, 4, 4)
+    om = ref.Variable(M)
+    olt = ref.LinTran(om, 4, 4)
+    expected = [[olt.apply(ref.Variable(v)).output() for v in s] for s in seqs]
+    for res in (seq.MapBatcher(plt).apply_seqs(seq.ConstResult(seqs)),
+                seq.MapBatcher(plt).apply_seqs(seq.PackedConstResult.from_host(seqs))):
+        got = res.output_seqs()
+        assert [len(s) for s in got] == [len(s) for s in expected]
+        for l, s in enumerate(expected):
+            for t, v in enumerate(s):
+                assert np.max(np.abs(got[l][t] - v)) <= 1e-5  # the reference's tolerance
+                close(got[l][t], v, f"lane {l} t {t}")
+    ups = [[ref.splitmix_uniform(60 + 7 * l + t, 4) for t in range(len(s))] for l, s in enumerate(seqs)]
+    uprs = [[ref.splitmix_uniform(90 + 7 * l + t, 4) for t in range(len(s))] for l, s in enumerate(seqs)]
+    og, org = {om: np.zeros(16)}, {om: np.zeros(16)}
+    for l, s in enumerate(seqs):
+        for t, v in enumerate(s):
+            r = olt.apply_r({om: RM}, ref.RVariable(ref.Variable(v), {}))
+            r.propagate_rgradient(ups[l][t].copy(), uprs[l][t].copy(), org, og)
+    for inp in (seq.ConstRResult(seqs), seq.PackedConstResult.from_host(seqs)):
+        res = seq.MapRBatcher(plt).apply_seqs_r({pm: RM}, inp)
+        g, rg = api.new_gradient([pm]), api.new_rgradient([pm])
+        res.propagate_rgradient(ups, uprs, rg, g)
+        close(g[pm], og[om], "TranMatrix gradient")
+        close(rg[pm], org[om], "TranMatrix R-gradient")

@@ -5,7 +5,11 @@
   C3  Hessian-vector step on a 4 x (2048->2048) MLP, n=4096
   C4  bench/lstm.go     LSTM H=512, T=128, B=256 (I=30, O=10), forward + BPTT + R
   C5  one rank's share of 4 x (8192->8192), n=8192 (the 8-GPU shard of n=65536)
-Inputs resident, CUDA events, 3 warm-ups.  One JSON line per config on stdout."""
+Inputs resident, CUDA events, 3 warm-ups.  One JSON line per config on stdout.
+
+Under torchrun (WORLD_SIZE > 1) every rank runs the same per-GPU problem on its own shard of the batch (weak scaling)
+and each step ends with the NCCL sum all-reduce of the parameter-gradient accumulators ({grad | rgrad} slab); the
+time is the max over ranks and the rates are whole-job aggregates."""
 import ctypes as C
 import json
 import os
@@ -21,17 +25,44 @@ from autofunc_b200 import api, synth
 from autofunc_b200.lstm import LSTMPlan
 
 
+RANK, WORLD, LOCAL = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+
+
+def reduce_slab(ptr, n):
+    """Gradient.Add across ranks (gradient.go:28-30): NCCL sum all-reduce of a device range, on the step's stream."""
+    if WORLD > 1:
+        import torch.distributed as dist
+        from autofunc_b200 import parallel
+        dist.all_reduce(torch.as_tensor(parallel.CudaArrayView(ptr, n), device=f"cuda:{LOCAL}"))
+
+
 def timed(fn, steps, warmup=3):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         fn()
     e1.record()
     e1.synchronize()
-    return e0.elapsed_time(e1) / steps
+    ms = e0.elapsed_time(e1) / steps
+    if WORLD > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def emit(d):
+    if RANK == 0:
+        d["n_gpus"] = WORLD
+        print(json.dumps(d), flush=True)
 
 
 def mlp_config(ctx, name, sizes, n, steps, flops):
@@ -40,16 +71,18 @@ def mlp_config(ctx, name, sizes, n, steps, flops):
     for i, (p, r) in enumerate(zip(params, rvecs)):
         plan.set_param(i, p)
         plan.set_rvector(i, r)
-    x = synth.mlp_input(sizes, n)
+    x = synth.mlp_input(sizes, n, seed=124 + 7919 * RANK)
     ctx.lib.af_upload(ctx.h, plan.input().ptr, x.ctypes.data, x.size)
     n_out = n * sizes[-1]
     up, upr = plan.upstream(), plan.upstream_r()
+    slab_ptr, slab_n = plan.grad(0).ptr, (plan.input().ptr - plan.grad(0).ptr) // 8
 
     def step():
         plan.zero_grads()
         api.check(ctx.lib.af_fill(ctx.h, up.ptr, 1.0, n_out))
         api.check(ctx.lib.af_zero(ctx.h, upr.ptr, n_out))
         plan.step(True, True)
+        reduce_slab(slab_ptr, slab_n)
     ms = timed(step, steps)
     if os.environ.get("AF_TRACE"):
         cap = 256
@@ -60,8 +93,8 @@ def mlp_config(ctx, name, sizes, n, steps, flops):
         for i in range(cnt.value):
             print(f"  [{i:2d}] kind={kinds[i]} work={work[i]:.4g} {msa[i] * 1e3:7.1f} us", file=sys.stderr)
     plan.close()
-    print(json.dumps({"config": name, "sizes": sizes, "n": n, "ms_per_step": ms, "samples_per_s": n / ms * 1e3,
-                      "tflops_executed": flops / ms / 1e9}), flush=True)
+    emit({"config": name, "sizes": sizes, "n_per_gpu": n, "ms_per_step": ms, "samples_per_s": WORLD * n / ms * 1e3,
+          "tflops_executed": WORLD * flops / ms / 1e9, "allreduce_MB": slab_n * 8 / 1e6 if WORLD > 1 else 0})
 
 
 def executed_flops(sizes, n):
@@ -87,6 +120,8 @@ def lintran_config(ctx, steps):
         api.check(L.af_lintran_igrad_r(h, d["U"].ptr, d["UR"].ptr, d["W"].ptr, d["RW"].ptr, D.ptr, DR.ptr, rows, cols, n))
         api.check(L.af_axpy(h, 1.0, D.ptr, gX.ptr, n * cols))
         api.check(L.af_axpy(h, 1.0, DR.ptr, rgX.ptr, n * cols))
+        reduce_slab(gW.ptr, rows * cols)   # the parameter's accumulators; X's gradients stay with their shard
+        reduce_slab(rgW.ptr, rows * cols)
     ms = timed(step, steps)
     if os.environ.get("AF_TRACE"):
         cap = 256
@@ -97,8 +132,8 @@ def lintran_config(ctx, steps):
         for i in range(cnt.value):
             print(f"  [{i:2d}] kind={kinds[i]} work={work[i]:.4g} {msa[i] * 1e3:7.1f} us", file=sys.stderr)
     algo_bytes = 8 * 8 * rows * cols  # W, RW read twice + gW, rgW read-modify-write
-    print(json.dumps({"config": "C1 lintran 1024x2048 n=10 fwd+Grad+RGrad", "ms_per_step": ms, "us_per_step": ms * 1e3,
-                      "algorithmic_GBps": algo_bytes / ms / 1e6, "samples_per_s": n / ms * 1e3}), flush=True)
+    emit({"config": "C1 lintran 1024x2048 n=10 fwd+Grad+RGrad", "n_per_gpu": n, "ms_per_step": ms, "us_per_step": ms * 1e3,
+          "algorithmic_GBps": WORLD * algo_bytes / ms / 1e6, "samples_per_s": WORLD * n / ms * 1e3})
 
 
 def lstm_config(ctx, I, H, O, T, B, steps):
@@ -117,6 +152,8 @@ def lstm_config(ctx, I, H, O, T, B, steps):
         api.check(ctx.lib.af_zero(ctx.h, upr.ptr, upr.n))
         plan.forward(True)
         plan.backward(True)
+        reduce_slab(slab.ptr, slab.n)
+    slab = plan.grad_slab()
     ms = timed(step, steps)
     if os.environ.get("AF_TRACE"):
         cap = 4096
@@ -134,15 +171,19 @@ def lstm_config(ctx, I, H, O, T, B, steps):
             print(f"  kind={k} work={w:.4g} launches={c} total={t:.3f} ms avg={t / c * 1e3:.1f} us rate={w * c / t / 1e9 if t else 0:.2f} (TF/s or TB/s)", file=sys.stderr)
     flops = 18.0 * (4 * H + O) * (H + I) * T * B
     plan.close()
-    print(json.dumps({"config": f"C4 lstm I={I} H={H} O={O} T={T} B={B} fwd+BPTT+R", "ms_per_step": ms,
-                      "sequences_per_s": B / ms * 1e3, "tflops_reference_count": flops / ms / 1e9}), flush=True)
+    emit({"config": f"C4 lstm I={I} H={H} O={O} T={T} B={B} fwd+BPTT+R", "lanes_per_gpu": B, "ms_per_step": ms,
+          "sequences_per_s": WORLD * B / ms * 1e3, "tflops_reference_count": WORLD * flops / ms / 1e9})
 
 
 def main():
     which = set(sys.argv[1:]) or {"c1", "c2", "c3", "c4"}
+    torch.cuda.set_device(LOCAL)
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
     stream = torch.cuda.Stream()  # a real stream (the legacy default stream cannot be graph-captured)
     torch.cuda.set_stream(stream)
-    ctx = api.Context(0, stream=stream.cuda_stream)
+    ctx = api.Context(LOCAL, stream=stream.cuda_stream)
     api.set_context(ctx)
     if "c1" in which:
         lintran_config(ctx, 50)
@@ -157,6 +198,10 @@ def main():
     if "c5" in which:
         s = [8192] * 5
         mlp_config(ctx, "C5 shard 4x(8192->8192) n=8192 (1/8 of n=65536)", s, 8192, 2, executed_flops(s, 8192))
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
