@@ -112,6 +112,7 @@ PROTOTYPES = {
     "af_mlp_add_to_vars": (INT, [P, C.c_double]),
     "af_mlp_get_param": (INT, [P, INT, H, I64]),
     "af_mlp_step": (INT, [P, INT, INT]),
+    "af_mlp_step_fresh": (INT, [P, INT]),
     "af_mlp_set_graph": (INT, [P, INT]),
     "af_mlp_step_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),
     "af_mlp_submit_host": (INT, [P, INT, H, H, H, H, H, C.POINTER(H), C.POINTER(H)]),

@@ -1252,6 +1252,10 @@ class MLPPlan:
         """Gradient.AddToVars (gradient.go:40-52) on the device: param += scale * grad."""
         check(self.ctx.lib.af_mlp_add_to_vars(self.h, float(scale)))
 
+    def step_fresh(self, with_r=True):
+        """One bench iteration in one call: fresh accumulators, outGrad = 1 / outRGrad = 0, forward + backward."""
+        check(self.ctx.lib.af_mlp_step_fresh(self.h, int(with_r)))
+
     def get_param(self, idx) -> np.ndarray:
         out = np.empty(self.param_len(idx), dtype=F64)
         check(self.ctx.lib.af_mlp_get_param(self.h, idx, out.ctypes.data, out.size))

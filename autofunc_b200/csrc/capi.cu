@@ -106,6 +106,7 @@ int af_ctx_destroy(af_ctx* ctx) {
   DeviceGuard guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->barrier_word) cudaFree(ctx->barrier_word);
   for (cudaEvent_t ev : ctx->trace_events) cudaEventDestroy(ev);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -164,6 +165,10 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
   }
   if (!strcmp(name, "small_n")) {
     ctx->small_n_off = value == 0;
+    return AF_OK;
+  }
+  if (!strcmp(name, "small_mlp")) {
+    ctx->small_mlp_off = value == 0;
     return AF_OK;
   }
   return fail(AF_EINVAL, std::string("unknown option ") + name);
@@ -568,10 +573,51 @@ int af_mlp_set_graph(af_mlp* m, int enable) {
   return AF_OK;
 }
 
+static bool mlp_small_ok(af_mlp* m) {
+  return !m->grad_ready && small_mlp_applicable(m->ctx, m->L, m->sizes.data(), m->n);
+}
+// fresh: the accumulators start this step at zero (stored, not read-modify-written);
+// unit_upstream: outGrad = 1, outRGrad = 0 (bench/mlp.go:118-126) generated in registers
+static int mlp_small_step(af_mlp* m, int with_r, int backprop, bool fresh, bool unit_upstream) {
+  std::vector<const double*> rv(2 * m->L);
+  for (int i = 0; i < 2 * m->L; ++i) rv[i] = m->has_rvec[i] ? m->rvec[i] : nullptr;
+  return small_mlp_launch(m->ctx, m->L, m->sizes.data(), m->n, m->param.data(), rv.data(), m->grad.data(),
+                          m->rgrad.data(), m->act.data(), m->ract.data(), m->delta.data(), m->rdelta.data(), with_r != 0,
+                          backprop != 0, fresh, unit_upstream);
+}
+
+// One iteration of the reference benchmark (bench/mlp.go:43-57 with :118-126): fresh accumulators, upstream from the
+// host (or outGrad = 1 / outRGrad = 0 when NULL), forward + backward.  The inputs are already in act[0].
+static int mlp_fresh_step(af_mlp* m, int with_r, const double* hU, const double* hUR) {
+  af_ctx* ctx = m->ctx;
+  cudaStream_t st = ctx->stream;
+  const int L = m->L;
+  const int64_t top = m->n * m->sizes[L];
+  const bool unit = !hU && !hUR;
+  if (unit && mlp_small_ok(m)) return mlp_small_step(m, with_r, 1, true, true);
+  if (hU) AF_CUDA(cudaMemcpyAsync(m->delta[L], hU, (size_t)top * 8, cudaMemcpyHostToDevice, st));
+  else AF_TRY(af_fill(ctx, m->delta[L], 1.0, top));  // bench/mlp.go:120-123
+  if (with_r) {
+    if (hUR) AF_CUDA(cudaMemcpyAsync(m->rdelta[L], hUR, (size_t)top * 8, cudaMemcpyHostToDevice, st));
+    else AF_CUDA(cudaMemsetAsync(m->rdelta[L], 0, (size_t)top * 8, st));  // bench/mlp.go:124
+  }
+  if (mlp_small_ok(m)) return mlp_small_step(m, with_r, 1, true, false);
+  AF_TRY(af_mlp_zero_grads(m));
+  return af_mlp_step(m, with_r, 1);
+}
+
+int af_mlp_step_fresh(af_mlp* m, int with_r) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  DeviceGuard guard(m->ctx->device);
+  return mlp_fresh_step(m, with_r, nullptr, nullptr);
+}
+
 int af_mlp_step(af_mlp* m, int with_r, int backprop) {
   if (!m) return fail(AF_EINVAL, "null mlp");
   af_ctx* ctx = m->ctx;
   DeviceGuard guard(ctx->device);
+  // a handful of samples: the whole step is one persistent kernel (small_mlp.cu), no graph needed
+  if (mlp_small_ok(m)) return mlp_small_step(m, with_r, backprop, false, false);
   // the legacy default stream cannot be captured
   if (!m->use_graph || m->grad_ready || ctx->tracing || ctx->stream == nullptr || ctx->stream == cudaStreamLegacy)
     return mlp_step_launches(m, with_r, backprop);
@@ -725,14 +771,7 @@ int af_mlp_submit_compute_host(af_mlp* m, int with_r, const double* hX, const do
   cudaStream_t st = ctx->stream;
   AF_CUDA(cudaStreamWaitEvent(st, sl.in_ready, 0));
   mlp_bind_slot(m, k);
-  if (hU) AF_CUDA(cudaMemcpyAsync(m->delta[L], hU, (size_t)top * 8, cudaMemcpyHostToDevice, st));
-  else AF_TRY(af_fill(ctx, m->delta[L], 1.0, top));
-  if (with_r) {
-    if (hUR) AF_CUDA(cudaMemcpyAsync(m->rdelta[L], hUR, (size_t)top * 8, cudaMemcpyHostToDevice, st));
-    else AF_CUDA(cudaMemsetAsync(m->rdelta[L], 0, (size_t)top * 8, st));
-  }
-  AF_TRY(af_mlp_zero_grads(m));
-  AF_TRY(af_mlp_step(m, with_r, 1));
+  AF_TRY(mlp_fresh_step(m, with_r, hU, hUR));
   sl.busy = true;
   return AF_OK;
 }
@@ -783,14 +822,7 @@ int af_mlp_step_host(af_mlp* m, int with_r, const double* hX, const double* hU, 
   const int L = m->L;
   const int64_t top = m->n * m->sizes[L];
   AF_CUDA(cudaMemcpyAsync(m->act[0], hX, (size_t)(m->n * m->sizes[0]) * 8, cudaMemcpyHostToDevice, st));
-  if (hU) AF_CUDA(cudaMemcpyAsync(m->delta[L], hU, (size_t)top * 8, cudaMemcpyHostToDevice, st));
-  else AF_TRY(af_fill(ctx, m->delta[L], 1.0, top));  // bench/mlp.go:120-123
-  if (with_r) {
-    if (hUR) AF_CUDA(cudaMemcpyAsync(m->rdelta[L], hUR, (size_t)top * 8, cudaMemcpyHostToDevice, st));
-    else AF_CUDA(cudaMemsetAsync(m->rdelta[L], 0, (size_t)top * 8, st));  // bench/mlp.go:124
-  }
-  AF_TRY(af_mlp_zero_grads(m));
-  AF_TRY(af_mlp_step(m, with_r, 1));
+  AF_TRY(mlp_fresh_step(m, with_r, hU, hUR));
   if (hOut) AF_CUDA(cudaMemcpyAsync(hOut, m->act[L], (size_t)top * 8, cudaMemcpyDeviceToHost, st));
   if (hROut && with_r) AF_CUDA(cudaMemcpyAsync(hROut, m->ract[L], (size_t)top * 8, cudaMemcpyDeviceToHost, st));
   for (int i = 0; i < 2 * L; ++i) {

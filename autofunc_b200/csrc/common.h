@@ -19,6 +19,9 @@ struct af_ctx {
   int gemm_path = 0;  // 0 auto, 1 generic, 2 require DMMA
   int big_cfg = 2;    // tile configuration for wide outputs: 0 = 128x64 x 8 warps, 2 = 64x64 x 2 CTAs/SM (default, fastest measured), 3 = 128x64 x 16 warps
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
+  bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu
+  unsigned* barrier_word = nullptr;  // grid-barrier counter of the persistent small-batch kernel
+  unsigned barrier_base = 0;         // its value once every launch queued so far has finished
   int64_t launches = 0;
   // driver entry point, resolved at run time so the library loads on hosts without libcuda
   void* encode_tiled = nullptr;
@@ -100,5 +103,12 @@ int small_wgrad_launch(af_ctx* ctx, const double* U, const double* UR, const dou
                        double* rgW, long long rows, long long cols, long long n);
 int small_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, long long rows,
                        long long cols, long long n, const GemmEpilogue& e, bool dual);
+
+// whole-step persistent kernel for an MLP plan with n <= 8 samples (small_mlp.cu)
+bool small_mlp_applicable(af_ctx* ctx, int L, const int64_t* sizes, int64_t n);
+int small_mlp_launch(af_ctx* ctx, int L, const int64_t* sizes, int64_t n, double* const* param, const double* const* rvec,
+                     double* const* grad, double* const* rgrad, double* const* act, double* const* ract,
+                     double* const* delta, double* const* rdelta, bool with_r, bool backprop, bool fresh,
+                     bool unit_upstream);
 
 }  // namespace af

@@ -70,7 +70,9 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
 /* Tuning knobs (measurement / A-B runs).  "big_cfg": tile configuration of the DMMA kernel for outputs
  * wider than 16 columns: 0 = 128x64 tile, one CTA per SM; 2 = 64x64 tile, two CTAs per SM.
  * "small_n": 1 (default) = batches of <= 16 samples use the streaming Gemv/Ger kernels, 0 = they go
- * through the tensor-core kernel (transposed narrow tiles + split-K).                               */
+ * through the tensor-core kernel (transposed narrow tiles + split-K).
+ * "small_mlp": 1 (default) = af_mlp_step with <= 4 samples runs as ONE persistent cooperative kernel
+ * (all layers, both directions, grid barriers between phases); 0 = the per-kernel CUDA graph.          */
 int af_set_option(af_ctx* ctx, const char* name, int value);
 
 int af_malloc(af_ctx* ctx, int64_t n_doubles, double** d_out);
@@ -261,6 +263,12 @@ int af_mlp_get_param(af_mlp*, int index, double* h_value, int64_t len);      /* 
 int af_mlp_step(af_mlp*, int with_r, int backprop);
 /* Replay the step from a CUDA graph (captured on the second call of a configuration).  On by default for
  * batches <= 256, where the ~25 short kernels of a step are launch-bound.                          */
+/* One iteration of the reference benchmark as ONE call (bench/mlp.go:43-57 with the fresh Gradient maps of
+ * :33-35 and outGrad = 1 / outRGrad = 0 of :118-126): equivalent to af_mlp_zero_grads + fill the upstreams +
+ * af_mlp_step(with_r, 1).  For batches of <= 4 samples the persistent kernel stores the accumulators instead of
+ * read-modify-writing them and generates the upstream in registers, so the zeroing passes disappear.  After a
+ * non-R fresh step the R accumulators are unspecified (the reference has no RGradient map in Run()).       */
+int af_mlp_step_fresh(af_mlp*, int with_r);
 int af_mlp_set_graph(af_mlp*, int enable);
 /* Host-buffer form (the reference-facing call): uploads h_X (n x sizes[0]), h_upstream /
  * h_upstream_r (n x sizes[L]; NULL => ones / zeros as in bench/mlp.go:118-126), zeroes the

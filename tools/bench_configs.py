@@ -77,11 +77,8 @@ def mlp_config(ctx, name, sizes, n, steps, flops):
     up, upr = plan.upstream(), plan.upstream_r()
     slab_ptr, slab_n = plan.grad(0).ptr, (plan.input().ptr - plan.grad(0).ptr) // 8
 
-    def step():
-        plan.zero_grads()
-        api.check(ctx.lib.af_fill(ctx.h, up.ptr, 1.0, n_out))
-        api.check(ctx.lib.af_zero(ctx.h, upr.ptr, n_out))
-        plan.step(True, True)
+    def step():  # one bench iteration: fresh accumulators, outGrad = 1, outRGrad = 0, RunR(backProp=true)
+        plan.step_fresh(True)
         reduce_slab(slab_ptr, slab_n)
     ms = timed(step, steps)
     if os.environ.get("AF_TRACE"):
