@@ -21,7 +21,8 @@ __device__ __forceinline__ double rd(const double* p, long long i) { return p ? 
 // 10-class head still issues full coalesced warps), G = 256 (one block) for long ones.  Each thread keeps its first
 // kRowCache exponentials in registers, so rows up to G * kRowCache entries are read from HBM once and exp() is
 // evaluated once; only the excess of longer rows is recomputed from L2.
-constexpr int kRowCache = 8;
+constexpr int kRowCache = 8;  // forward: exponentials (and their R forms) per thread
+constexpr int kBwdCache = 4;  // backward keeps four vectors per entry, so half as many entries (registers)
 
 template <int G>
 __device__ __forceinline__ double group_sum(double v, double* sm) {
@@ -46,9 +47,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const double* __restri
                                                           long long len, long long n) {
   __shared__ double sm[8];
   const int lane = threadIdx.x % G;
-  constexpr int RPB = 256 / G;  // rows per block pass; the block walks the rows persistently
-  for (long long row0 = (long long)blockIdx.x * RPB; row0 < n; row0 += (long long)gridDim.x * RPB) {
-  const long long row = row0 + threadIdx.x / G;
+  const long long row = (long long)blockIdx.x * (256 / G) + threadIdx.x / G;
   const bool live = row < n;  // a dead group still takes part in the shuffles / barriers (its sums are zero)
   const double* x = X + row * len;
   const double* xr = RX ? RX + row * len : nullptr;
@@ -73,7 +72,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const double* __restri
   }
   s = group_sum<G>(s, sm);
   if (RY) sr = group_sum<G>(sr, sm);
-  if (!live) continue;
+  if (!live) return;
   const double inv = 1.0 / s;
   const double invR = -(inv * inv) * sr;
 #pragma unroll
@@ -89,7 +88,6 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const double* __restri
     Y[row * len + k] = e * inv;
     if (RY) RY[row * len + k] = e * invR + (e * (rd(xr, k) * invT)) * inv;
   }
-  }
 }
 
 // in place: U <- invT * y (u - <u,y>);  UR <- invT * [ yR (u - <u,y>) + y (uR - <uR,y> - <u,yR>) ]
@@ -100,16 +98,14 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const double* __restri
                                                           long long len, long long n) {
   __shared__ double sm[8];
   const int lane = threadIdx.x % G;
-  constexpr int RPB = 256 / G;
-  for (long long row0 = (long long)blockIdx.x * RPB; row0 < n; row0 += (long long)gridDim.x * RPB) {
-  const long long row = row0 + threadIdx.x / G;
+  const long long row = (long long)blockIdx.x * (256 / G) + threadIdx.x / G;
   const bool live = row < n;
   const long long o = row * len;
-  double uv[kRowCache], yv[kRowCache], urv[kRowCache], ryv[kRowCache];
+  double uv[kBwdCache], yv[kBwdCache], urv[kBwdCache], ryv[kBwdCache];
   double a = 0.0, b = 0.0;  // <u,y> ; <uR,y> + <u,yR>
   if (live) {
 #pragma unroll
-    for (int j = 0; j < kRowCache; ++j) {
+    for (int j = 0; j < kBwdCache; ++j) {
       const long long k = lane + (long long)j * G;
       uv[j] = yv[j] = urv[j] = ryv[j] = 0.0;
       if (k < len) {
@@ -118,7 +114,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const double* __restri
         if (UR) { urv[j] = UR[o + k]; ryv[j] = rd(RY, o + k); b += urv[j] * yv[j] + uv[j] * ryv[j]; }
       }
     }
-    for (long long k = lane + (long long)kRowCache * G; k < len; k += G) {
+    for (long long k = lane + (long long)kBwdCache * G; k < len; k += G) {
       const double u = U[o + k], y = Y[o + k];
       a += u * y;
       if (UR) b += UR[o + k] * y + u * rd(RY, o + k);
@@ -126,20 +122,19 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const double* __restri
   }
   a = group_sum<G>(a, sm);
   if (UR) b = group_sum<G>(b, sm);
-  if (!live) continue;
+  if (!live) return;
 #pragma unroll
-  for (int j = 0; j < kRowCache; ++j) {
+  for (int j = 0; j < kBwdCache; ++j) {
     const long long k = lane + (long long)j * G;
     if (k < len) {
       if (UR) UR[o + k] = invT * (ryv[j] * (uv[j] - a) + yv[j] * (urv[j] - b));
       U[o + k] = invT * (yv[j] * (uv[j] - a));
     }
   }
-  for (long long k = lane + (long long)kRowCache * G; k < len; k += G) {
+  for (long long k = lane + (long long)kBwdCache * G; k < len; k += G) {
     const double u = U[o + k], y = Y[o + k];
     if (UR) UR[o + k] = invT * (rd(RY, o + k) * (u - a) + y * (UR[o + k] - b));
     U[o + k] = invT * (y * (u - a));
-  }
   }
 }
 

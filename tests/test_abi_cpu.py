@@ -93,3 +93,15 @@ def test_synth_generator_matches_oracle_generator():
         assert np.array_equal(p, v.vector)
     for r, v in zip(rvecs, net.variables):
         assert np.array_equal(r, net.rvec[v])
+
+
+def test_go_shim_binds_only_declared_symbols():
+    """go/b200/*.go cannot be compiled here (no Go toolchain): at least every C.af_* it calls must be an entry point
+    the header declares, and every header struct it names must exist."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    declared = set(_declared_symbols()) | {"af_ctx", "af_mlp", "af_lstm"}
+    used = set()
+    for f in os.listdir(os.path.join(root, "go", "b200")):
+        if f.endswith(".go"):
+            used |= set(re.findall(r"\bC\.(af_[a-z0-9_]+)\b", open(os.path.join(root, "go", "b200", f)).read()))
+    assert used and not (used - declared), f"go shim calls undeclared entry points: {sorted(used - declared)}"

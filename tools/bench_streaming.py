@@ -16,7 +16,8 @@ from autofunc_b200 import api
 
 def main():
     n = int(os.environ.get("AF_STREAM_N", 1 << 26))  # 64 Mi doubles = 512 MiB per vector
-    steps = 10
+    steps = int(os.environ.get('AF_STREAM_STEPS', 10))
+    warm = int(os.environ.get('AF_STREAM_WARM', 30))
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = api.Context(0, stream=stream.cuda_stream)
@@ -57,7 +58,7 @@ def main():
     for name, bpe, call in cases:
         for v in bufs:  # the backward kernels overwrite their operands in place: restore (device to device)
             api.check(L.af_copy(h, v.ptr, pristine.ptr, n))
-        for _ in range(30):  # ~15 ms of back-to-back launches: clocks are up before the timed region
+        for _ in range(warm):  # ~15 ms of back-to-back launches: clocks are up before the timed region
             api.check(call())
         for v in bufs:
             api.check(L.af_copy(h, v.ptr, pristine.ptr, n))
