@@ -594,14 +594,22 @@ static int mlp_fresh_step(af_mlp* m, int with_r, const double* hU, const double*
   const int L = m->L;
   const int64_t top = m->n * m->sizes[L];
   const bool unit = !hU && !hUR;
-  if (unit && mlp_small_ok(m)) return mlp_small_step(m, with_r, 1, true, true);
+  if (unit && mlp_small_ok(m)) {
+    const int rc = mlp_small_step(m, with_r, 1, true, true);
+    if (rc != AF_ENOTSUP) return rc;
+    ctx->small_mlp_off = true;  // cooperative launch refused: per-kernel path from now on
+  }
   if (hU) AF_CUDA(cudaMemcpyAsync(m->delta[L], hU, (size_t)top * 8, cudaMemcpyHostToDevice, st));
   else AF_TRY(af_fill(ctx, m->delta[L], 1.0, top));  // bench/mlp.go:120-123
   if (with_r) {
     if (hUR) AF_CUDA(cudaMemcpyAsync(m->rdelta[L], hUR, (size_t)top * 8, cudaMemcpyHostToDevice, st));
     else AF_CUDA(cudaMemsetAsync(m->rdelta[L], 0, (size_t)top * 8, st));  // bench/mlp.go:124
   }
-  if (mlp_small_ok(m)) return mlp_small_step(m, with_r, 1, true, false);
+  if (mlp_small_ok(m)) {
+    const int rc = mlp_small_step(m, with_r, 1, true, false);
+    if (rc != AF_ENOTSUP) return rc;
+    ctx->small_mlp_off = true;
+  }
   AF_TRY(af_mlp_zero_grads(m));
   return af_mlp_step(m, with_r, 1);
 }
@@ -617,7 +625,11 @@ int af_mlp_step(af_mlp* m, int with_r, int backprop) {
   af_ctx* ctx = m->ctx;
   DeviceGuard guard(ctx->device);
   // a handful of samples: the whole step is one persistent kernel (small_mlp.cu), no graph needed
-  if (mlp_small_ok(m)) return mlp_small_step(m, with_r, backprop, false, false);
+  if (mlp_small_ok(m)) {
+    const int rc = mlp_small_step(m, with_r, backprop, false, false);
+    if (rc != AF_ENOTSUP) return rc;
+    ctx->small_mlp_off = true;  // cooperative launch refused: per-kernel path from now on
+  }
   // the legacy default stream cannot be captured
   if (!m->use_graph || m->grad_ready || ctx->tracing || ctx->stream == nullptr || ctx->stream == cudaStreamLegacy)
     return mlp_step_launches(m, with_r, backprop);

@@ -308,7 +308,15 @@ int launch_variant(af_ctx* ctx, SmallMlpArgs& a, double bytes) {
   a.bar_base = ctx->barrier_base;
   ctx->barrier_base += barriers * (unsigned)grid;
   void* params[] = {(void*)&a};
-  AF_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(kThreads * G), params, 0, ctx->stream));
+  const cudaError_t le =
+      cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(kThreads * G), params, 0, ctx->stream);
+  if (le != cudaSuccess) {
+    // the grid cannot be made co-resident here (SMs held by another client, stream being captured, ...): nothing was
+    // launched; tell the caller to take the per-kernel path instead
+    ctx->barrier_base = a.bar_base;
+    cudaGetLastError();
+    return fail(AF_ENOTSUP, std::string("cooperative launch of small_mlp_step_kernel refused: ") + cudaGetErrorString(le));
+  }
   return after_launch(ctx, "small_mlp_step_kernel", KIND_SMALL_N, bytes);
 }
 

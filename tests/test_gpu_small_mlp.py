@@ -116,3 +116,21 @@ def test_small_mlp_absent_rvectors_forward_only_and_ab(api):
         close(grads2[i], grads[i], f"A/B grad[{i}]")
         close(rgrads2[i], rgrads[i], f"A/B rgrad[{i}]")
     plan.close()
+
+
+def test_odd_widths_fall_back_to_the_per_kernel_path(api):
+    """Odd contraction lengths cannot use 16-byte row accesses: the plan takes the generic per-kernel path, same numbers."""
+    sizes, n = [7, 9, 5], 2
+    onet = ref.MLP(sizes, weight_scale=lambda k: 1 / np.sqrt(k))
+    x = onet.make_input(n)
+    ores, ograd, orgrad = onet.step_r(x, n)
+    plan = _plan(api, onet, sizes, n)
+    before = plan.ctx.launch_count()
+    out, rout, grads, rgrads = plan.step_host(x.vector)
+    assert plan.ctx.launch_count() - before > 1
+    close(out, ores.output(), "Output")
+    close(rout, ores.routput(), "ROutput")
+    for i, v in enumerate(onet.variables):
+        close(grads[i], ograd[v], f"grad[{i}]")
+        close(rgrads[i], orgrad[v], f"rgrad[{i}]")
+    plan.close()
