@@ -20,6 +20,8 @@ struct af_ctx {
   int big_cfg = 2;    // tile configuration for wide outputs: 0 = 128x64 x 8 warps, 2 = 64x64 x 2 CTAs/SM (default, fastest measured), 3 = 128x64 x 16 warps
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu
+  bool pdl = false;      // inside a dependent-kernel chain (LSTM time loops): launch with programmatic stream serialization
+  bool pdl_off = true;   // opt-in (af_set_option "pdl" 1): measured 24.6 vs 24.25 ms on the C4 LSTM, so off by default
   unsigned* barrier_word = nullptr;  // grid-barrier counter of the persistent small-batch kernel
   unsigned barrier_base = 0;         // its value once every launch queued so far has finished
   int64_t launches = 0;
@@ -59,6 +61,29 @@ enum : int { KIND_GEMM_DUAL = 0, KIND_GEMM_SINGLE = 1, KIND_GEMM_GENERIC = 2, KI
 // after a kernel launch: count it, surface launch errors, and (when tracing) record an event.
 // `work` is the launch's ALGORITHMIC work: flops for contractions, bytes for streaming kernels.
 int after_launch(af_ctx* ctx, const char* what, int kind, double work);
+
+// Kernel launch that may carry the programmatic-dependent-launch attribute: the kernel may then start while its
+// predecessor in the stream drains, and MUST execute griddepcontrol.wait before touching the predecessor's output
+// (pdl_wait() below).  Only kernels written that way are launched with `pdl` = true.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#ifdef __CUDACC__
+// wait for the predecessor grid (no-op without the launch attribute), then let the successor start launching: it
+// waits on us the same way, so triggering early is always safe
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
 
 struct DeviceGuard {
   int prev = -1;

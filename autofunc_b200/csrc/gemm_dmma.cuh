@@ -307,6 +307,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();  // everything above overlapped the predecessor's tail; its output is visible from here on
 
   // Producer role: lane 0 of warp 0 keeps kStages-1 units in flight.  It is folded into a consumer
   // warp (not an extra warp) because registers are allocated per SM sub-partition: an extra warp would put

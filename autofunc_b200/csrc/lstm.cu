@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(double* __restrict__
                                                             double* __restrict__ INn, double* __restrict__ RINn,
                                                             double* __restrict__ AUG, double* __restrict__ RAUG, int B,
                                                             int H, int ld) {
+  pdl_wait();
   const int n = B * H;
   for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += gridDim.x * 256) {
     const int b = e / H, j = e - b * H;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(
     const double* __restrict__ DAUG, const double* __restrict__ RDAUG, const double* __restrict__ SG,
     const double* __restrict__ RSG, double* __restrict__ SGn, double* __restrict__ RSGn, double* __restrict__ D4,
     double* __restrict__ RD4, int B, int H, int ld) {
+  pdl_wait();
   const int n = B * H;
   for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += gridDim.x * 256) {
     const int b = e / H, j = e - b * H;
@@ -365,7 +367,11 @@ static int lstm_forward_launches(af_lstm* m, int with_r) {
   // initial state is zero (lstm.go:175) with zero R
   AF_CUDA(cudaMemset2DAsync(m->IN, C * 8, 0, H * 8, B, ctx->stream));
   if (R) AF_CUDA(cudaMemset2DAsync(m->RIN, C * 8, 0, H * 8, B, ctx->stream));
+  // the time loop is a chain of dependent kernels (contraction -> cell -> contraction ...): programmatic dependent
+  // launch lets each kernel's launch and prologue overlap its predecessor's tail
+  struct PdlScope { af_ctx* c; explicit PdlScope(af_ctx* c_) : c(c_) { c->pdl = true; } ~PdlScope() { c->pdl = false; } };
   for (int64_t t = 0; t < T; ++t) {
+    PdlScope pdl_scope(ctx);
     double* INt = m->IN + t * BC;
     double* RINt = m->RIN + t * BC;
     double* Gt = m->G + t * B * 4 * H;
@@ -379,9 +385,9 @@ static int lstm_forward_launches(af_lstm* m, int with_r) {
       e.epi = EPI_STORE; e.out0 = Gt; e.out1 = R ? RGt : nullptr; e.ldo = 4 * H; e.prezeroed = true;
       AF_TRY(gemm_launch(ctx, A, Bop, R, B, 4 * H, C, e));
     }
-    lstm_cell_fwd_kernel<<<ew_grid(ctx, B * H), 256, 0, ctx->stream>>>(
-        Gt, R ? RGt : nullptr, m->b4, m->Rb4, INt, RINt, INt + BC, RINt + BC, m->AUG + t * BC, m->RAUG + t * BC, (int)B,
-        (int)H, (int)C);
+    AF_CUDA(launch_kernel(lstm_cell_fwd_kernel, dim3(ew_grid(ctx, B * H)), dim3(256), 0, ctx->stream, ctx->pdl && !ctx->pdl_off,
+                          Gt, R ? RGt : nullptr, m->b4, m->Rb4, INt, RINt, INt + BC, RINt + BC, m->AUG + t * BC,
+                          m->RAUG + t * BC, (int)B, (int)H, (int)C));
     AF_TRY(after_launch(ctx, "lstm_cell_fwd_kernel", KIND_ELEMENTWISE, (R ? 2.0 : 1.0) * 7 * 8 * B * H));
   }
   // output layer for every step at once (lstm.go:193-194)
@@ -404,13 +410,15 @@ static int lstm_backward_launches(af_lstm* m, int with_r) {
   AF_CUDA(cudaMemsetAsync(m->SG[0], 0, (size_t)(B * H) * 8, ctx->stream));
   if (R) AF_CUDA(cudaMemsetAsync(m->RSG[0], 0, (size_t)(B * H) * 8, ctx->stream));
   int cur = 0;
+  struct PdlScope { af_ctx* c; explicit PdlScope(af_ctx* c_) : c(c_) { c->pdl = true; } ~PdlScope() { c->pdl = false; } };
   for (int64_t t = T - 1; t >= 0; --t) {
+    PdlScope pdl_scope(ctx);
     double* D4t = m->D4 + t * B * 4 * H;
     double* RD4t = m->RD4 + t * B * 4 * H;
-    lstm_cell_bwd_kernel<<<ew_grid(ctx, B * H), 256, 0, ctx->stream>>>(
-        m->G + t * B * 4 * H, R ? m->RG + t * B * 4 * H : nullptr, m->IN + t * BC, m->RIN + t * BC, m->IN + (t + 1) * BC,
-        m->RIN + (t + 1) * BC, m->DAUG + t * BC, m->RDAUG + t * BC, m->SG[cur], m->RSG[cur], m->SG[cur ^ 1], m->RSG[cur ^ 1], D4t,
-        RD4t, (int)B, (int)H, (int)C);
+    AF_CUDA(launch_kernel(lstm_cell_bwd_kernel, dim3(ew_grid(ctx, B * H)), dim3(256), 0, ctx->stream, ctx->pdl && !ctx->pdl_off,
+                          m->G + t * B * 4 * H, R ? m->RG + t * B * 4 * H : nullptr, m->IN + t * BC, m->RIN + t * BC,
+                          m->IN + (t + 1) * BC, m->RIN + (t + 1) * BC, m->DAUG + t * BC, m->RDAUG + t * BC, m->SG[cur],
+                          m->RSG[cur], m->SG[cur ^ 1], m->RSG[cur ^ 1], D4t, RD4t, (int)B, (int)H, (int)C));
     AF_TRY(after_launch(ctx, "lstm_cell_bwd_kernel", KIND_ELEMENTWISE, (R ? 2.0 : 1.0) * 13 * 8 * B * H));
     if (t > 0) {
       // stateGrad += delta4 W4[:, :H]  (the four gates' inputGradient, lin_tran.go:272-359, restricted to the

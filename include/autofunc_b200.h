@@ -71,6 +71,11 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * wider than 16 columns: 0 = 128x64 tile, one CTA per SM; 2 = 64x64 tile, two CTAs per SM.
  * "small_n": 1 (default) = batches of <= 16 samples use the streaming Gemv/Ger kernels, 0 = they go
  * through the tensor-core kernel (transposed narrow tiles + split-K).
+ * "pdl": 1 = the LSTM time loops launch their dependent kernel chain (contraction -> cell -> ...) with
+ * programmatic dependent launch (each kernel's launch and prologue overlap its predecessor's tail); 0 (default) =
+ * plain launches -- measured 24.6 ms vs 24.25 ms on the C4 LSTM: the stream-K contraction already keeps every CTA
+ * slot busy until its end, so the early-launched successor only competes for the slots.  Takes effect for graphs
+ * captured afterwards.
  * "small_mlp": 1 (default) = af_mlp_step with <= 4 samples runs as ONE persistent cooperative kernel
  * (all layers, both directions, grid barriers between phases); 0 = the per-kernel CUDA graph.          */
 int af_set_option(af_ctx* ctx, const char* name, int value);
