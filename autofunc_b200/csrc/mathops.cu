@@ -138,6 +138,136 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const double* __restri
   }
 }
 
+// ---- staged row-wise softmax: rows up to kSoftChunk entries ------------------------------------------
+// A block stages a contiguous chunk of WHOLE rows (up to kSoftChunk doubles per vector) in shared memory with one
+// coalesced cooperative load -- every thread has 8 independent loads per vector in flight, whatever the row length --
+// then groups of G threads reduce and rescale their rows in place in shared memory, and the block stores the chunk
+// back coalesced.  Each vector crosses HBM exactly once, exp() is evaluated once, and a 10-class head moves full
+// 256-byte warp transactions instead of 80-byte rows.
+constexpr int kSoftChunk = 2048;
+
+template <int G>
+__device__ __forceinline__ double staged_group_sum(double v, double* red, int row_in_pass) {
+#pragma unroll
+  for (int o = (G < 32 ? G : 32) / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (G <= 32) return v;
+  // G == 256: one row per pass, the whole block reduces
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i];
+  return t;
+}
+
+__device__ __forceinline__ void stage_in(double* dst, const double* __restrict__ src, long long base, int elems) {
+  // 8 x 256 = kSoftChunk: fully unrolled so the loads are all issued before the first use
+#pragma unroll
+  for (int u = 0; u < kSoftChunk / 256; ++u) {
+    const int e = threadIdx.x + u * 256;
+    if (e < elems) dst[e] = src ? src[base + e] : 0.0;
+  }
+}
+__device__ __forceinline__ void stage_out(double* __restrict__ dst, const double* src, long long base, int elems) {
+#pragma unroll
+  for (int u = 0; u < kSoftChunk / 256; ++u) {
+    const int e = threadIdx.x + u * 256;
+    if (e < elems) dst[base + e] = src[e];
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) softmax_fwd_staged_kernel(const double* __restrict__ X, const double* __restrict__ RX,
+                                                                 double* __restrict__ Y, double* __restrict__ RY,
+                                                                 double invT, int len, long long n, int rows_per_chunk) {
+  extern __shared__ double sm_soft[];
+  double* sx = sm_soft;                 // x -> e -> y
+  double* sr = sm_soft + kSoftChunk;    // xR -> eR -> yR
+  __shared__ double red[8];
+  const long long row0 = (long long)blockIdx.x * rows_per_chunk;
+  const int nrows = (int)min((long long)rows_per_chunk, n - row0);
+  const int elems = nrows * len;
+  const long long base = row0 * len;
+  stage_in(sx, X, base, elems);
+  if (RY) stage_in(sr, RX, base, elems);
+  __syncthreads();
+  constexpr int P = 256 / G;  // rows per pass
+  const int lane = threadIdx.x % G, sub = threadIdx.x / G;
+  for (int r0 = 0; r0 < nrows; r0 += P) {  // uniform trip count: dead groups still take part in the reductions
+    const int r = r0 + sub;
+    const bool live = r < nrows;
+    double* x = sx + r * len;
+    double* xr = sr + r * len;
+    double s = 0.0, srsum = 0.0;
+    if (live)
+      for (int k = lane; k < len; k += G) {
+        const double e = exp(x[k] * invT);
+        x[k] = e;
+        s += e;
+        if (RY) { const double er = e * (xr[k] * invT); xr[k] = er; srsum += er; }
+      }
+    s = staged_group_sum<G>(s, red, sub);
+    if (RY) srsum = staged_group_sum<G>(srsum, red, sub);
+    if (live) {
+      const double inv = 1.0 / s, invR = -(inv * inv) * srsum;
+      for (int k = lane; k < len; k += G) {
+        const double e = x[k];
+        if (RY) xr[k] = e * invR + xr[k] * inv;
+        x[k] = e * inv;
+      }
+    }
+  }
+  __syncthreads();
+  stage_out(Y, sx, base, elems);
+  if (RY) stage_out(RY, sr, base, elems);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) softmax_bwd_staged_kernel(const double* __restrict__ Y, const double* __restrict__ RY,
+                                                                 double* __restrict__ U, double* __restrict__ UR, double invT,
+                                                                 int len, long long n, int rows_per_chunk) {
+  extern __shared__ double sm_soft[];
+  double* su = sm_soft;
+  double* sy = sm_soft + kSoftChunk;
+  double* sur = sm_soft + 2 * kSoftChunk;
+  double* sry = sm_soft + 3 * kSoftChunk;
+  __shared__ double red[8];
+  const long long row0 = (long long)blockIdx.x * rows_per_chunk;
+  const int nrows = (int)min((long long)rows_per_chunk, n - row0);
+  const int elems = nrows * len;
+  const long long base = row0 * len;
+  stage_in(su, U, base, elems);
+  stage_in(sy, Y, base, elems);
+  if (UR) { stage_in(sur, UR, base, elems); stage_in(sry, RY, base, elems); }
+  __syncthreads();
+  constexpr int P = 256 / G;
+  const int lane = threadIdx.x % G, sub = threadIdx.x / G;
+  for (int r0 = 0; r0 < nrows; r0 += P) {
+    const int r = r0 + sub;
+    const bool live = r < nrows;
+    const int o = r * len;
+    double a = 0.0, b = 0.0;  // <u,y> ; <uR,y> + <u,yR>
+    if (live)
+      for (int k = lane; k < len; k += G) {
+        const double u = su[o + k], y = sy[o + k];
+        a += u * y;
+        if (UR) b += sur[o + k] * y + u * sry[o + k];
+      }
+    a = staged_group_sum<G>(a, red, sub);
+    if (UR) b = staged_group_sum<G>(b, red, sub);
+    if (live)
+      for (int k = lane; k < len; k += G) {
+        const double u = su[o + k], y = sy[o + k];
+        if (UR) sur[o + k] = invT * (sry[o + k] * (u - a) + y * (sur[o + k] - b));
+        su[o + k] = invT * (y * (u - a));
+      }
+  }
+  __syncthreads();
+  stage_out(U, su, base, elems);
+  if (UR) stage_out(UR, sur, base, elems);
+}
+
 // group width for a row length: the smallest sub-warp that covers the row in <= 2 strides, a full warp up to
 // 32 * kRowCache entries, one block beyond that
 // one block pass per 256/G rows (measured: capping the grid and walking rows persistently is slower -- a block's rows
@@ -149,6 +279,26 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const double* __restri
     else if (len <= 32) KERNEL<16><<<AF_ROW_GRID(16), 256, 0, ctx->stream>>>(__VA_ARGS__);        \
     else if (len <= 32 * kRowCache) KERNEL<32><<<AF_ROW_GRID(32), 256, 0, ctx->stream>>>(__VA_ARGS__); \
     else KERNEL<256><<<AF_ROW_GRID(256), 256, 0, ctx->stream>>>(__VA_ARGS__);                     \
+  } while (0)
+
+// group width for the staged kernels: 4 / 8 / 16 / 32 lanes per row up to 256 entries (about 2-8 entries per lane), the whole block beyond; the
+// bwd variant needs 64 KB of dynamic shared memory (opt-in attribute, set once per instantiation)
+#define AF_STAGED_LAUNCH(KERNEL, G, SMEM, ...)                                                     \
+  do {                                                                                             \
+    static bool configured = false;                                                                \
+    if (!configured) {                                                                             \
+      AF_CUDA(cudaFuncSetAttribute(KERNEL<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSoftChunk * 8)); \
+      configured = true;                                                                           \
+    }                                                                                              \
+    KERNEL<G><<<grid, 256, SMEM, ctx->stream>>>(__VA_ARGS__);                                      \
+  } while (0)
+#define AF_STAGED_DISPATCH(KERNEL, SMEM, ...)                                  \
+  do {                                                                         \
+    if (len <= 12) AF_STAGED_LAUNCH(KERNEL, 4, SMEM, __VA_ARGS__);             \
+    else if (len <= 16) AF_STAGED_LAUNCH(KERNEL, 8, SMEM, __VA_ARGS__);        \
+    else if (len <= 32) AF_STAGED_LAUNCH(KERNEL, 16, SMEM, __VA_ARGS__);       \
+    else if (len <= 256) AF_STAGED_LAUNCH(KERNEL, 32, SMEM, __VA_ARGS__);      \
+    else AF_STAGED_LAUNCH(KERNEL, 256, SMEM, __VA_ARGS__);                     \
   } while (0)
 
 }  // namespace
@@ -404,6 +554,13 @@ int af_softmax_fwd_r(af_ctx* ctx, const double* X, const double* RX, double temp
   if (len < 0 || n < 0) return fail(AF_ESHAPE, "negative length");
   if (len == 0 || n == 0) return AF_OK;
   const double invT = (temperature != 0 && temperature != 1) ? 1 / temperature : 1.0;
+  if (len <= kSoftChunk) {
+    const int rpc = (int)(kSoftChunk / len);
+    const unsigned grid = (unsigned)((n + rpc - 1) / rpc);
+    const size_t smem = (size_t)(RY ? 2 : 1) * kSoftChunk * 8;
+    AF_STAGED_DISPATCH(softmax_fwd_staged_kernel, smem, X, RX, Y, RY, invT, (int)len, (long long)n, rpc);
+    return after_launch(ctx, "softmax_fwd_staged_kernel", KIND_REDUCE, 8.0 * len * n * (RY ? 4 : 2));
+  }
   AF_ROW_DISPATCH(softmax_fwd_kernel, X, RX, Y, RY, invT, len, n);
   return after_launch(ctx, "softmax_fwd_kernel", KIND_REDUCE, 8.0 * len * n * (RY ? 4 : 2));
 }
@@ -414,6 +571,13 @@ int af_softmax_bwd_r(af_ctx* ctx, const double* Y, const double* RY, double temp
   if (len < 0 || n < 0) return fail(AF_ESHAPE, "negative length");
   if (len == 0 || n == 0) return AF_OK;
   const double invT = (temperature != 0 && temperature != 1) ? 1 / temperature : 1.0;
+  if (len <= kSoftChunk) {
+    const int rpc = (int)(kSoftChunk / len);
+    const unsigned grid = (unsigned)((n + rpc - 1) / rpc);
+    const size_t smem = (size_t)(UR ? 4 : 2) * kSoftChunk * 8;
+    AF_STAGED_DISPATCH(softmax_bwd_staged_kernel, smem, Y, RY, U, UR, invT, (int)len, (long long)n, rpc);
+    return after_launch(ctx, "softmax_bwd_staged_kernel", KIND_REDUCE, 8.0 * len * n * (UR ? 6 : 3));
+  }
   AF_ROW_DISPATCH(softmax_bwd_kernel, Y, RY, U, UR, invT, len, n);
   return after_launch(ctx, "softmax_bwd_kernel", KIND_REDUCE, 8.0 * len * n * (UR ? 6 : 3));
 }

@@ -96,6 +96,9 @@ class MapBatcher:
         self.b = b
 
     def apply_seqs(self, r):
+        """seqfunc/map_batcher.go:26-48.  A packed device list (anything with `.packed()`) never touches the host."""
+        if hasattr(r, "packed"):
+            return _map_packed(self.b, r, None, False)
         seqs = r.output_seqs()
         res = _MapBatcherResult(r, [[] for _ in seqs])
         for t in range(max_sequence_len(seqs)):
@@ -135,6 +138,8 @@ class MapRBatcher:
         return MapBatcher(self.b).apply_seqs(r)
 
     def apply_seqs_r(self, rv, r):  # map_batcher.go:76-99
+        if hasattr(r, "packed"):
+            return _map_packed(self.b, r, rv, True)
         seqs, rseqs = r.output_seqs(), r.routput_seqs()
         res = _MapBatcherRResult(r, [[] for _ in seqs], [[] for _ in seqs])
         for t in range(max_sequence_len(seqs)):
@@ -421,26 +426,3 @@ def _map_packed(b, r, rv, with_r):
         off += d.n
     return _PackedMapResult(r, shape, pool, results, shape.like(widths, out),
                             shape.like(widths, out_r) if with_r else None)
-
-
-_host_apply_seqs = MapBatcher.apply_seqs
-_host_apply_seqs_r = MapRBatcher.apply_seqs_r
-
-
-def _apply_seqs(self, r):
-    """seqfunc/map_batcher.go:26-48.  A packed device list (anything with `.packed()`) never touches the host."""
-    if hasattr(r, "packed"):
-        return _map_packed(self.b, r, None, False)
-    return _host_apply_seqs(self, r)
-
-
-def _apply_seqs_r(self, rv, r):
-    """seqfunc/map_batcher.go:76-99."""
-    if hasattr(r, "packed"):
-        return _map_packed(self.b, r, rv, True)
-    return _host_apply_seqs_r(self, rv, r)
-
-
-MapBatcher.apply_seqs = _apply_seqs
-MapRBatcher.apply_seqs = _apply_seqs
-MapRBatcher.apply_seqs_r = _apply_seqs_r
