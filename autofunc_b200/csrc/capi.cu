@@ -278,7 +278,7 @@ static int wgrad_impl(af_ctx* ctx, const double* U, const double* UR, const doub
   if (rows * cols == 0 || n == 0) return AF_OK;
   const bool dual = rgW != nullptr;
   if (!gW && !rgW) return AF_OK;
-  if (small_n_applicable(ctx, rows, cols, n, {X, RX, gW, rgW}))  // Ger branch, lin_tran.go:187-196,223-241
+  if (small_n_applicable(ctx, rows, cols, n, {X, RX, gW, rgW}, 16))  // Ger branch, lin_tran.go:187-196,223-241
     return small_wgrad_launch(ctx, U, dual ? UR : nullptr, X, dual ? RX : nullptr, gW, rgW, rows, cols, n);
   GemmOperand A{U, dual ? UR : nullptr, LAY_RC, rows};
   GemmOperand B{X, dual ? RX : nullptr, LAY_RC, cols};

@@ -121,7 +121,8 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool du
                 long long Kd, const GemmEpilogue& e);
 
 // small-batch (n <= 16) streaming kernels, small_n.cu: the reference's Gemv / Ger branch
-bool small_n_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs);
+bool small_n_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs,
+                        int nmax = 8);
 int small_fwd_launch(af_ctx* ctx, const double* W, const double* RW, const double* X, const double* RX, long long rows,
                      long long cols, long long n, const GemmEpilogue& e, bool dual);
 int small_wgrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* X, const double* RX, double* gW,

@@ -1,6 +1,7 @@
 // Small-batch LinTran kernels: the reference's own n == 1 branch (Gemv / Ger instead of Gemm,
-// lin_tran.go:90-99, 138-152, 187-196, 223-241, 285-288, 329-334), generalised to n <= 8 samples (9..16 take the
-// tensor-core kernel with transposed narrow tiles, which measured faster there).
+// lin_tran.go:90-99, 138-152, 187-196, 223-241, 285-288, 329-334), generalised to n <= 8 samples (n <= 16 for the
+// weight gradient; the other passes of 9..16 take the tensor-core kernel with transposed narrow tiles, which
+// measured faster there).
 //
 // With a handful of samples the six contractions are HBM-bound streaming passes over the weight
 // matrix, not tensor-core work: the algorithmic traffic is W, RW read once per forward and once per
@@ -176,9 +177,13 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 }  // namespace
 
-bool small_n_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs) {
+// nmax: 8 for the forward and input-gradient passes; 16 for the weight gradient, whose rank-n update streams faster
+// than the transposed tensor-core tiles up to there (C1, n = 10: 29.6 vs 41.0 us; the other two passes measured
+// 52 vs 27 and 44 vs 26 us, so they keep the tensor-core path for n = 9..16)
+bool small_n_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs,
+                        int nmax) {
   if (ctx->gemm_path == 1 || ctx->small_n_off) return false;
-  if (n < 1 || n > 8 || (cols & 1) || rows < 1 || cols < 2 || rows > (1 << 30) || cols > (1 << 30)) return false;
+  if (n < 1 || n > nmax || (cols & 1) || rows < 1 || cols < 2 || rows > (1 << 30) || cols > (1 << 30)) return false;
   for (const void* p : ptrs)
     if (p && !aligned16(p)) return false;
   return true;
@@ -197,7 +202,8 @@ int small_fwd_launch(af_ctx* ctx, const double* W, const double* RW, const doubl
   const double* rw = dual ? RW : nullptr;
   const double* rx = dual ? RX : nullptr;
   if (n <= 2) small_fwd_kernel<2><<<blocks, kSmallThreads, 0, ctx->stream>>>(W, rw, X, rx, (int)rows, (int)cols, (int)n, wpr, a);
-  else small_fwd_kernel<8><<<blocks, kSmallThreads, 0, ctx->stream>>>(W, rw, X, rx, (int)rows, (int)cols, (int)n, wpr, a);
+  else if (n <= 8) small_fwd_kernel<8><<<blocks, kSmallThreads, 0, ctx->stream>>>(W, rw, X, rx, (int)rows, (int)cols, (int)n, wpr, a);
+  else small_fwd_kernel<16><<<blocks, kSmallThreads, 0, ctx->stream>>>(W, rw, X, rx, (int)rows, (int)cols, (int)n, wpr, a);
   const int products = 1 + (dual ? (rw ? 1 : 0) + (rx ? 1 : 0) : 0);
   return after_launch(ctx, "small_fwd_kernel", KIND_SMALL_N, 8.0 * rows * cols * (rw ? 2 : 1) + 0.0 * products);
 }
@@ -206,7 +212,8 @@ int small_wgrad_launch(af_ctx* ctx, const double* U, const double* UR, const dou
                        double* rgW, long long rows, long long cols, long long n) {
   dim3 grid((unsigned)((cols / 2 + kSmallThreads - 1) / kSmallThreads), (unsigned)rows);
   if (n <= 2) small_wgrad_kernel<2><<<grid, kSmallThreads, 0, ctx->stream>>>(U, UR, X, RX, gW, rgW, (int)rows, (int)cols, (int)n);
-  else small_wgrad_kernel<8><<<grid, kSmallThreads, 0, ctx->stream>>>(U, UR, X, RX, gW, rgW, (int)rows, (int)cols, (int)n);
+  else if (n <= 8) small_wgrad_kernel<8><<<grid, kSmallThreads, 0, ctx->stream>>>(U, UR, X, RX, gW, rgW, (int)rows, (int)cols, (int)n);
+  else small_wgrad_kernel<16><<<grid, kSmallThreads, 0, ctx->stream>>>(U, UR, X, RX, gW, rgW, (int)rows, (int)cols, (int)n);
   return after_launch(ctx, "small_wgrad_kernel", KIND_SMALL_N, 16.0 * rows * cols * ((gW ? 1 : 0) + (rgW ? 1 : 0)));
 }
 
@@ -231,7 +238,8 @@ int small_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const dou
   small_igrad_kernel<NM><<<grid, kSmallThreads, (size_t)2 * NM * mchunk * 8, ctx->stream>>>(U, ur, W, rw, D, DR, (int)rows, \
                                                                                             (int)cols, (int)n, mchunk)
   if (n <= 2) AF_SMALL_IGRAD(2);
-  else AF_SMALL_IGRAD(8);
+  else if (n <= 8) AF_SMALL_IGRAD(8);
+  else AF_SMALL_IGRAD(16);
 #undef AF_SMALL_IGRAD
   AF_TRY(after_launch(ctx, "small_igrad_kernel", KIND_SMALL_N, 8.0 * rows * cols * (rw ? 2 : 1)));
   if (e.epi == EPI_STORE) return AF_OK;
