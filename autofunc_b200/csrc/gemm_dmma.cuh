@@ -207,7 +207,7 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 //                    swapped operands + transposed store, its 10-row weight gradient)
 template <int CFG> struct TileCfg;
 template <> struct TileCfg<0> { static constexpr int WI = 4, WJ = 2, TI = 4, TJ = 4, STAGES = 4, MIN_CTAS = 1, PREFETCH = 1; };
-template <> struct TileCfg<1> { static constexpr int WI = 8, WJ = 1, TI = 1, TJ = 2, STAGES = 4, MIN_CTAS = 1, PREFETCH = 1; };
+template <> struct TileCfg<1> { static constexpr int WI = 8, WJ = 1, TI = 1, TJ = 2, STAGES = 4, MIN_CTAS = 2, PREFETCH = 1; };
 //   CFG 2 "paired" : 2x2 warps of 32x32 ->  64 x 64, 3 stages, TWO CTAs per SM: the two CTAs drift out of
 //                    phase, so one CTA's epilogue / pipeline fill overlaps the other's DMMA stream
 template <> struct TileCfg<2> { static constexpr int WI = 2, WJ = 2, TI = 4, TJ = 4, STAGES = 3, MIN_CTAS = 2, PREFETCH = 1; };

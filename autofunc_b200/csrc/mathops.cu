@@ -285,10 +285,10 @@ __global__ void __launch_bounds__(256) softmax_bwd_staged_kernel(const double* _
 // bwd variant needs 64 KB of dynamic shared memory (opt-in attribute, set once per instantiation)
 #define AF_STAGED_LAUNCH(KERNEL, G, SMEM, ...)                                                     \
   do {                                                                                             \
-    static bool configured = false;                                                                \
-    if (!configured) {                                                                             \
+    static unsigned long long configured = 0; /* one bit per device: the attribute is per device and function */ \
+    if (!(configured >> (ctx->device & 63) & 1ull)) {                                              \
       AF_CUDA(cudaFuncSetAttribute(KERNEL<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSoftChunk * 8)); \
-      configured = true;                                                                           \
+      configured |= 1ull << (ctx->device & 63);                                                    \
     }                                                                                              \
     KERNEL<G><<<grid, 256, SMEM, ctx->stream>>>(__VA_ARGS__);                                      \
   } while (0)
