@@ -277,6 +277,29 @@ def gpu_arm(args):
     ms_total = float(ms_total.item())
     value = world * n * K / (ms_total * 1e-3)
 
+    # ---- the reference benchmark's other two modes (bench/mlp.go:29-41): Run(b, false) and Run(b, true) ----
+    def timed_mode(with_r, backprop):
+        def one():
+            plan.zero_grads()
+            api.check(ctx.lib.af_fill(ctx.h, up.ptr, 1.0, n_out))
+            plan.step(with_r, backprop)
+            if backprop:
+                finish_reduce()
+        for _ in range(3):
+            one()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(max(3, K // 2)):
+            one()
+        a1.record(stream)
+        barrier()
+        t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * n * max(3, K // 2) / (float(t.item()) * 1e-3)
+    other_modes = {"fwd_only_samples_per_s": timed_mode(False, False), "fwd_gradient_samples_per_s": timed_mode(False, True)}
+
     # ---- roofline of the dominant kernel (the dual TMA+DMMA contraction), from the live trace ----
     gemm_ms = sum(ms_arr[i] for i in range(count.value) if kinds[i] == 0)
     gemm_flops = sum(work[i] for i in range(count.value) if kinds[i] == 0)
@@ -358,6 +381,7 @@ def gpu_arm(args):
                          "whole_step_tflops": flops_per_sample(LAYER_SIZES) * n * K / (ms_total * 1e-3) / 1e12},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
+            "other_modes": other_modes,  # Run(b,false) / Run(b,true) of bench/mlp.go:29-41, resident, same batch
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
         }
         if world == 1 and not args.no_cpu_baseline:
