@@ -129,3 +129,35 @@ def matmulvec_test_func(ns, mat_var):
         def apply_r(self, rv, inp):
             return ns.mat_mul_vec_r(ns.RVariable(mat_var, rv), 3, 4, inp)
     return M()
+
+
+class RandomNetFixture:
+    """A randomly shaped batched network chaining every family of node: LinTran/LinAdd/Sigmoid, MatMulVecs with a
+    computed matrix, Pool, a batched Softmax head and the squared-error cost; b and t are absent from the RVector."""
+
+    def __init__(self, ns, seed):
+        import numpy as np
+        rng = np.random.default_rng(seed)
+        n, k, m = int(rng.integers(1, 4)), int(rng.integers(2, 5)), int(rng.integers(2, 5))
+        w = ns.Variable(rng.uniform(-1, 1, m * k))
+        b = ns.Variable(rng.uniform(-1, 1, m))
+        q = ns.Variable(rng.uniform(0.5, 1.5, m * m))
+        t = ns.Variable(rng.uniform(0, 1, n * m))
+        x = ns.Variable(rng.uniform(-1, 1, n * k))
+        self.variables, self.input = [w, b, q, t, x], x
+        self.rv = {v: rng.uniform(-1, 1, len(v.vector)) for v in (w, q, x)}
+
+        class Net:
+            def apply(self, inp):
+                h = ns.Sigmoid().apply(ns.LinAdd(b).batch(ns.LinTran(w, m, k).batch(inp, n), n))
+                mixed = ns.mat_mul_vecs(ns.mul(q, q), m, m, h)
+                p = ns.pool(mixed, lambda z: ns.add(z, ns.scale(z, 0.5)))
+                return ns.squared_error(ns.Softmax(1.5).batch(p, n), t)
+
+            def apply_r(self, r, inp):
+                rb, rq, rt = (ns.RVariable(v, r) for v in (b, q, t))
+                h = ns.Sigmoid().apply_r(r, ns.LinAdd(b).batch_r(r, ns.LinTran(w, m, k).batch_r(r, inp, n), n))
+                mixed = ns.mat_mul_vecs_r(ns.mul_r(rq, rq), m, m, h)
+                p = ns.pool_r(mixed, lambda z: ns.add_r(z, ns.scale_r(z, 0.5)))
+                return ns.squared_error_r(ns.Softmax(1.5).batch_r(r, p, n), rt)
+        self.func = Net()

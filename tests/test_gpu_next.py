@@ -483,3 +483,10 @@ def test_map_batcher_output_on_reference_seq_fixtures(api):
         res.propagate_rgradient(ups, uprs, rg, g)
         close(g[pm], og[om], "TranMatrix gradient")
         close(rg[pm], org[om], "TranMatrix R-gradient")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_networks_pass_the_reference_acceptance_procedure(api, seed):
+    """functest.RFuncChecker.FullCheck on the product for the same random networks the oracle is checked on."""
+    f = fx.RandomNetFixture(api, seed)
+    assert RFuncChecker(api, f.func, f.variables, f.input, f.rv).full_check() == []

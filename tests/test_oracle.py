@@ -175,3 +175,11 @@ def test_matmulvec_output_and_checks():  # test/lin_alg_test.go:55-73
 def test_squared_error_is_half_squared_distance():
     a, y = ref.Variable([1, -2, 3]), ref.Variable([0.5, 0.5, 0.5])
     assert abs(ref.squared_error(a, y).output()[0] - 0.5 * np.sum((a.vector - y.vector) ** 2)) < 1e-15
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_networks_pass_the_reference_acceptance_procedure(seed):
+    """The reference's checker (functest.RFuncChecker.FullCheck) on randomly shaped batched networks that chain every
+    family of node the product implements (tests/fixtures.py: RandomNetFixture)."""
+    f = fx.RandomNetFixture(ref, seed)
+    assert RFuncChecker(ref, f.func, f.variables, f.input, f.rv).full_check() == []
