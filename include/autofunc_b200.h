@@ -3,7 +3,7 @@
  *
  * This is the drop-in boundary.  The reference has no FFI of its own: the path sits
  * behind the Go interfaces Func/RFunc (func.go:7-27), Batcher/RBatcher (batcher.go:5-29) and
- * Result/RResult (result.go:10-77).  A Go (cgo) shim -- go/b200/*.go, shown in INTEGRATION.md --
+ * Result/RResult (result.go:10-77).  A Go (cgo) shim -- the package go/b200, shown in INTEGRATION.md --
  * implements those interfaces by calling the entry points below; each entry point cites the
  * reference routine it replaces.
  *

@@ -105,3 +105,23 @@ def test_go_shim_binds_only_declared_symbols():
         if f.endswith(".go"):
             used |= set(re.findall(r"\bC\.(af_[a-z0-9_]+)\b", open(os.path.join(root, "go", "b200", f)).read()))
     assert used and not (used - declared), f"go shim calls undeclared entry points: {sorted(used - declared)}"
+
+
+def _compile_c_example(tmp_path):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(str(tmp_path), "mlp_step")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(root, "include"),
+           os.path.join(root, "examples", "mlp_step.c"), "-L" + os.path.dirname(_lib.LIB_PATH), "-lautofunc_b200",
+           "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH), "-lm", "-o", exe]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_client_links(lib, tmp_path):
+    """The boundary is a C ABI: the header must compile as pedantic C99 and a C program must link against the library
+    with nothing but -lautofunc_b200 (no CUDA, torch or C++ runtime on the link line)."""
+    exe = _compile_c_example(tmp_path)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode != 0 and "af_ctx_create" in r.stderr  # fails loudly without a GPU: no CPU fallback

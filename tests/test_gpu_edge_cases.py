@@ -123,3 +123,13 @@ def test_c_abi_rejects_bad_arguments_loudly(api):
     assert L.af_softmax_fwd_r(h, v.ptr, None, 0.0, v.ptr, None, -3, 2) == api._lib.AF_ESHAPE
     assert L.af_sigmoid_fwd(None, v.ptr, v.ptr, 8) == api._lib.AF_EINVAL
     assert L.af_mlp_step(None, 1, 1) == api._lib.AF_EINVAL
+
+
+def test_plain_c_client_of_the_abi(api, tmp_path):
+    """examples/mlp_step.c: a C99 program drives one bench iteration through the C ABI from host buffers and checks
+    accumulation, linearity of the R-operator in the R-vector, and AddToVars on the device."""
+    import subprocess
+    from tests.test_abi_cpu import _compile_c_example
+    r = subprocess.run([_compile_c_example(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "mlp_step ok" in r.stdout
