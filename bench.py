@@ -55,28 +55,48 @@ def workload_name(batch):
 # CPU arm: the oracle (numpy + OpenBLAS threads) -- the only place bench.py executes oracle/
 # ------------------------------------------------------------------------------------------------
 def cpu_threads():
+    """Threads the BLAS pool runs with inside run_cpu_oracle (= every core this process may use)."""
     try:
-        from threadpoolctl import threadpool_info
-        n = [p.get("num_threads", 0) for p in threadpool_info() if p.get("user_api") == "blas"]
+        from threadpoolctl import threadpool_info, threadpool_limits
+        with threadpool_limits(limits=host_cores(), user_api="blas"):
+            n = [p.get("num_threads", 0) for p in threadpool_info() if p.get("user_api") == "blas"]
         if n:
             return max(n)
     except Exception:
         pass
-    return os.cpu_count() or 1
+    return host_cores()
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def run_cpu_oracle(n, steps, warmup):
+    """The CPU arm uses every host thread it can: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would
+    throttle OpenBLAS to one thread, so the BLAS pool is sized explicitly."""
     from oracle import autofunc_ref as ref
-    net = ref.MLP(LAYER_SIZES)
-    x = net.make_input(n)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        net.step_r(x, n)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    return times
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=host_cores(), user_api="blas")
+    except Exception:
+        limiter = None
+    try:
+        net = ref.MLP(LAYER_SIZES)
+        x = net.make_input(n)
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            net.step_r(x, n)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+        return times
+    finally:
+        if limiter is not None:
+            limiter.restore_original_limits()
 
 
 def reference_arm(args):
