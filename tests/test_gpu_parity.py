@@ -507,3 +507,27 @@ def test_shape_errors(api):
         api.mul(api.Variable(np.zeros(3)), api.Variable(np.zeros(4)))
     with pytest.raises(api.ShapeError, match="input count does not divide input length"):
         api.Sigmoid().batch(api.Variable(np.zeros(5)), 2)
+
+
+@pytest.mark.parametrize("sizes,scaled", [([1000, 2000, 512, 10], False), ([1000, 2000, 512, 10], True),
+                                          ([2048, 2048, 2048, 2048, 2048], True)])
+def test_bench_configuration_matches_oracle_at_full_size(api, sizes, scaled):
+    """BASELINE configs[1] exactly as bench.py runs it -- 1000-2000-512-10, n = 4096, RunR with backProp -- and
+    configs[2] (the Hessian-vector step on 4 x (2048 -> 2048), n = 4096) against the oracle directly (numpy finishes
+    these sizes in seconds): Output, ROutput and every gradient / R-gradient vector."""
+    n = 4096
+    ws = (lambda k: 1 / np.sqrt(k)) if scaled else None   # None = bench/mlp.go's U[-1,1) init (saturated sigmoids)
+    onet = ref.MLP(sizes, weight_scale=ws)
+    x = onet.make_input(n)
+    ores, ograd, orgrad = onet.step_r(x, n)
+    plan = api.MLPPlan(sizes, n)
+    for i, v in enumerate(onet.variables):
+        plan.set_param(i, v.vector)
+        plan.set_rvector(i, onet.rvec[v])
+    out, rout, grads, rgrads = plan.step_host(x.vector)
+    close(out, ores.output(), "Output")
+    close(rout, ores.routput(), "ROutput")
+    for i, v in enumerate(onet.variables):
+        close(grads[i], ograd[v], f"grad[{i}]")
+        close(rgrads[i], orgrad[v], f"rgrad[{i}]")
+    plan.close()
