@@ -20,6 +20,7 @@ struct af_ctx {
   int big_cfg = 2;    // tile configuration for wide outputs: 0 = 128x64 x 8 warps, 2 = 64x64 x 2 CTAs/SM (default, fastest measured), 3 = 128x64 x 16 warps
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu
+  bool lstm_split_off = true;   // opt-in (af_set_option "lstm_split" 1): two concurrent half-batch kernel chains; measured 24.6 vs 24.2 ms
   bool pdl = false;      // inside a dependent-kernel chain (LSTM time loops): launch with programmatic stream serialization
   bool pdl_off = true;   // opt-in (af_set_option "pdl" 1): measured 24.6 vs 24.25 ms on the C4 LSTM, so off by default
   unsigned* barrier_word = nullptr;  // grid-barrier counter of the persistent small-batch kernel

@@ -150,6 +150,11 @@ struct af_lstm {
   double *D4, *RD4;      // T x B x 4H
   double *SG[2], *RSG[2];
   int64_t grad_doubles = 0;
+  // The lanes are independent through the whole recurrence, so the time loops run the two halves of the batch as two
+  // concurrent kernel chains (main stream + side stream, forked and joined with events -- also inside the captured
+  // graphs): while one half is in a kernel's tail or launch gap the other half's contraction has the SMs.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // CUDA-graph replay of the two time loops (hundreds of short dependent launches): [with_r][fwd/bwd]
   struct LoopGraph { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; };
   LoopGraph graphs[2][2];
@@ -228,6 +233,9 @@ int af_lstm_destroy(af_lstm* m) {
   for (auto& a : m->graphs)
     for (auto& g : a)
       if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (m->side) cudaStreamDestroy(m->side);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
   cudaFree(m->slab);
   delete m;
   return AF_OK;
@@ -355,6 +363,41 @@ int af_lstm_backward(af_lstm* m, int with_r) {
 
 }  // extern "C"
 
+// number of independent lane groups the time loops run concurrently (1 = single chain)
+static int lstm_lane_groups(af_lstm* m) {
+  af_ctx* ctx = m->ctx;
+  if (ctx->lstm_split_off || ctx->tracing || m->B < 128 || (m->B & 1)) return 1;
+  if (ctx->stream == nullptr || ctx->stream == cudaStreamLegacy) return 1;
+  if (!m->side) {
+    if (cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      return 1;
+    }
+  }
+  return 2;
+}
+// run body(group, first lane, lanes) for every lane group, group 1 on the side stream
+template <typename F>
+static int lstm_for_groups(af_lstm* m, int groups, F body) {
+  af_ctx* ctx = m->ctx;
+  if (groups == 1) return body(0, (int64_t)0, m->B);
+  cudaStream_t main_stream = ctx->stream;
+  AF_CUDA(cudaEventRecord(m->ev_fork, main_stream));
+  AF_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+  const int64_t half = m->B / 2;
+  int rc = AF_OK;
+  for (int g = 0; g < 2 && rc == AF_OK; ++g) {
+    ctx->stream = g == 0 ? main_stream : m->side;
+    rc = body(g, g * half, half);
+  }
+  ctx->stream = main_stream;
+  AF_CUDA(cudaEventRecord(m->ev_join, m->side));
+  AF_CUDA(cudaStreamWaitEvent(main_stream, m->ev_join, 0));
+  return rc;
+}
+
 static int lstm_forward_launches(af_lstm* m, int with_r) {
   af_ctx* ctx = m->ctx;
   const int64_t H = m->H, C = m->C, B = m->B, T = m->T, O = m->O;
@@ -367,29 +410,31 @@ static int lstm_forward_launches(af_lstm* m, int with_r) {
   // initial state is zero (lstm.go:175) with zero R
   AF_CUDA(cudaMemset2DAsync(m->IN, C * 8, 0, H * 8, B, ctx->stream));
   if (R) AF_CUDA(cudaMemset2DAsync(m->RIN, C * 8, 0, H * 8, B, ctx->stream));
-  // the time loop is a chain of dependent kernels (contraction -> cell -> contraction ...): programmatic dependent
-  // launch lets each kernel's launch and prologue overlap its predecessor's tail
+  // the time loop is a chain of dependent kernels (contraction -> cell -> contraction ...), one chain per lane group
   struct PdlScope { af_ctx* c; explicit PdlScope(af_ctx* c_) : c(c_) { c->pdl = true; } ~PdlScope() { c->pdl = false; } };
-  for (int64_t t = 0; t < T; ++t) {
-    PdlScope pdl_scope(ctx);
-    double* INt = m->IN + t * BC;
-    double* RINt = m->RIN + t * BC;
-    double* Gt = m->G + t * B * 4 * H;
-    double* RGt = m->RG + t * B * 4 * H;
-    // all four gates in one contraction (R-state of step 0 is identically zero: skip its product); bias and
-    // sigmoid are applied by the cell kernel, so a split / stream-K launch needs no separate epilogue pass
-    {
-      GemmOperand A{INt, (R && t > 0) ? RINt : nullptr, LAY_KC, C};
-      GemmOperand Bop{m->W4, R ? m->RW4 : nullptr, LAY_KC, C};
-      GemmEpilogue e;
-      e.epi = EPI_STORE; e.out0 = Gt; e.out1 = R ? RGt : nullptr; e.ldo = 4 * H; e.prezeroed = true;
-      AF_TRY(gemm_launch(ctx, A, Bop, R, B, 4 * H, C, e));
+  AF_TRY(lstm_for_groups(m, lstm_lane_groups(m), [&](int, int64_t b0, int64_t nb) -> int {
+    for (int64_t t = 0; t < T; ++t) {
+      PdlScope pdl_scope(ctx);
+      double* INt = m->IN + t * BC + b0 * C;
+      double* RINt = m->RIN + t * BC + b0 * C;
+      double* Gt = m->G + (t * B + b0) * 4 * H;
+      double* RGt = m->RG + (t * B + b0) * 4 * H;
+      // all four gates in one contraction (R-state of step 0 is identically zero: skip its product); bias and
+      // sigmoid are applied by the cell kernel, so a split / stream-K launch needs no separate epilogue pass
+      {
+        GemmOperand A{INt, (R && t > 0) ? RINt : nullptr, LAY_KC, C};
+        GemmOperand Bop{m->W4, R ? m->RW4 : nullptr, LAY_KC, C};
+        GemmEpilogue e;
+        e.epi = EPI_STORE; e.out0 = Gt; e.out1 = R ? RGt : nullptr; e.ldo = 4 * H; e.prezeroed = true;
+        AF_TRY(gemm_launch(ctx, A, Bop, R, nb, 4 * H, C, e));
+      }
+      AF_CUDA(launch_kernel(lstm_cell_fwd_kernel, dim3(ew_grid(ctx, nb * H)), dim3(256), 0, ctx->stream,
+                            ctx->pdl && !ctx->pdl_off, Gt, R ? RGt : nullptr, m->b4, m->Rb4, INt, RINt, INt + BC, RINt + BC,
+                            m->AUG + t * BC + b0 * C, m->RAUG + t * BC + b0 * C, (int)nb, (int)H, (int)C));
+      AF_TRY(after_launch(ctx, "lstm_cell_fwd_kernel", KIND_ELEMENTWISE, (R ? 2.0 : 1.0) * 7 * 8 * nb * H));
     }
-    AF_CUDA(launch_kernel(lstm_cell_fwd_kernel, dim3(ew_grid(ctx, B * H)), dim3(256), 0, ctx->stream, ctx->pdl && !ctx->pdl_off,
-                          Gt, R ? RGt : nullptr, m->b4, m->Rb4, INt, RINt, INt + BC, RINt + BC, m->AUG + t * BC,
-                          m->RAUG + t * BC, (int)B, (int)H, (int)C));
-    AF_TRY(after_launch(ctx, "lstm_cell_fwd_kernel", KIND_ELEMENTWISE, (R ? 2.0 : 1.0) * 7 * 8 * B * H));
-  }
+    return AF_OK;
+  }));
   // output layer for every step at once (lstm.go:193-194)
   return af_dense_fwd(ctx, m->Wout, R ? m->RWout : nullptr, m->bout, R ? m->Rbout : nullptr, m->AUG, R ? m->RAUG : nullptr,
                       m->RES, R ? m->RRES : nullptr, O, C, T * B, 1);
@@ -409,28 +454,32 @@ static int lstm_backward_launches(af_lstm* m, int with_r) {
                         R ? m->RDAUG : nullptr, O, C, TB));
   AF_CUDA(cudaMemsetAsync(m->SG[0], 0, (size_t)(B * H) * 8, ctx->stream));
   if (R) AF_CUDA(cudaMemsetAsync(m->RSG[0], 0, (size_t)(B * H) * 8, ctx->stream));
-  int cur = 0;
   struct PdlScope { af_ctx* c; explicit PdlScope(af_ctx* c_) : c(c_) { c->pdl = true; } ~PdlScope() { c->pdl = false; } };
-  for (int64_t t = T - 1; t >= 0; --t) {
-    PdlScope pdl_scope(ctx);
-    double* D4t = m->D4 + t * B * 4 * H;
-    double* RD4t = m->RD4 + t * B * 4 * H;
-    AF_CUDA(launch_kernel(lstm_cell_bwd_kernel, dim3(ew_grid(ctx, B * H)), dim3(256), 0, ctx->stream, ctx->pdl && !ctx->pdl_off,
-                          m->G + t * B * 4 * H, R ? m->RG + t * B * 4 * H : nullptr, m->IN + t * BC, m->RIN + t * BC,
-                          m->IN + (t + 1) * BC, m->RIN + (t + 1) * BC, m->DAUG + t * BC, m->RDAUG + t * BC, m->SG[cur],
-                          m->RSG[cur], m->SG[cur ^ 1], m->RSG[cur ^ 1], D4t, RD4t, (int)B, (int)H, (int)C));
-    AF_TRY(after_launch(ctx, "lstm_cell_bwd_kernel", KIND_ELEMENTWISE, (R ? 2.0 : 1.0) * 13 * 8 * B * H));
-    if (t > 0) {
-      // stateGrad += delta4 W4[:, :H]  (the four gates' inputGradient, lin_tran.go:272-359, restricted to the
-      // state columns: the x columns go to a Variable that is not in the gradient maps)
-      GemmOperand A{D4t, R ? RD4t : nullptr, LAY_KC, 4 * H};
-      GemmOperand Bop{m->W4, R ? m->RW4 : nullptr, LAY_RC, C};
-      GemmEpilogue e;
-      e.epi = EPI_ACCUM; e.out0 = m->SG[cur ^ 1]; e.out1 = R ? m->RSG[cur ^ 1] : nullptr; e.ldo = H;
-      AF_TRY(gemm_launch(ctx, A, Bop, R, B, H, 4 * H, e));
+  AF_TRY(lstm_for_groups(m, lstm_lane_groups(m), [&](int, int64_t b0, int64_t nb) -> int {
+    int cur = 0;
+    for (int64_t t = T - 1; t >= 0; --t) {
+      PdlScope pdl_scope(ctx);
+      double* D4t = m->D4 + (t * B + b0) * 4 * H;
+      double* RD4t = m->RD4 + (t * B + b0) * 4 * H;
+      const int64_t go = (t * B + b0) * 4 * H, io = t * BC + b0 * C, so = b0 * H;
+      AF_CUDA(launch_kernel(lstm_cell_bwd_kernel, dim3(ew_grid(ctx, nb * H)), dim3(256), 0, ctx->stream,
+                            ctx->pdl && !ctx->pdl_off, m->G + go, R ? m->RG + go : nullptr, m->IN + io, m->RIN + io,
+                            m->IN + io + BC, m->RIN + io + BC, m->DAUG + io, m->RDAUG + io, m->SG[cur] + so, m->RSG[cur] + so,
+                            m->SG[cur ^ 1] + so, m->RSG[cur ^ 1] + so, D4t, RD4t, (int)nb, (int)H, (int)C));
+      AF_TRY(after_launch(ctx, "lstm_cell_bwd_kernel", KIND_ELEMENTWISE, (R ? 2.0 : 1.0) * 13 * 8 * nb * H));
+      if (t > 0) {
+        // stateGrad += delta4 W4[:, :H]  (the four gates' inputGradient, lin_tran.go:272-359, restricted to the
+        // state columns: the x columns go to a Variable that is not in the gradient maps)
+        GemmOperand A{D4t, R ? RD4t : nullptr, LAY_KC, 4 * H};
+        GemmOperand Bop{m->W4, R ? m->RW4 : nullptr, LAY_RC, C};
+        GemmEpilogue e;
+        e.epi = EPI_ACCUM; e.out0 = m->SG[cur ^ 1] + so; e.out1 = R ? m->RSG[cur ^ 1] + so : nullptr; e.ldo = H;
+        AF_TRY(gemm_launch(ctx, A, Bop, R, nb, H, 4 * H, e));
+      }
+      cur ^= 1;
     }
-    cur ^= 1;
-  }
+    return AF_OK;
+  }));
   // gate weight / bias gradients over all T*B rows at once (lstm.go's per-step dataGradient calls add up)
   AF_TRY(colsum_launch(ctx, m->D4, R ? m->RD4 : nullptr, m->gb4, R ? m->rgb4 : nullptr, 4 * H, TB));
   return af_lintran_wgrad_r(ctx, m->D4, R ? m->RD4 : nullptr, m->IN, R ? m->RIN : nullptr, m->gW4, R ? m->rgW4 : nullptr, 4 * H, C, TB);

@@ -71,6 +71,10 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * wider than 16 columns: 0 = 128x64 tile, one CTA per SM; 2 = 64x64 tile, two CTAs per SM.
  * "small_n": 1 (default) = batches of <= 16 samples use the streaming Gemv/Ger kernels, 0 = they go
  * through the tensor-core kernel (transposed narrow tiles + split-K).
+ * "lstm_split": 1 = the LSTM time loops run the two halves of the lane batch as two concurrent kernel chains on
+ * two streams (lanes are independent through the recurrence); 0 (default) = one chain -- measured 24.6 vs 24.2 ms on
+ * the C4 LSTM: the half-batch contractions lose more efficiency than the overlap of tails and launch gaps returns.
+ * Takes effect for graphs captured afterwards.
  * "pdl": 1 = the LSTM time loops launch their dependent kernel chain (contraction -> cell -> ...) with
  * programmatic dependent launch (each kernel's launch and prologue overlap its predecessor's tail); 0 (default) =
  * plain launches -- measured 24.6 ms vs 24.25 ms on the C4 LSTM: the stream-K contraction already keeps every CTA
