@@ -317,6 +317,8 @@ static int igrad_impl(af_ctx* ctx, const double* U, const double* UR, const doub
   e.out0 = D; e.out1 = DR; e.ldo = cols; e.s = S; e.rs = RS; e.lds = cols;
   if (rows > 0 && small_n_applicable(ctx, rows, cols, n, {W, RW, D, DR}))  // Gemv T branch, lin_tran.go:285-288,329-334
     return small_igrad_launch(ctx, U, UR, W, RW, rows, cols, n, e, dual);
+  if (few_rows_igrad_applicable(ctx, rows, cols, n, {W, RW, D, DR, S, RS}))  // <= 16 output rows: a streaming pass, not a GEMM
+    return few_rows_igrad_launch(ctx, U, UR, W, RW, rows, cols, n, e, dual);
   if (rows == 0) {
     int saved = ctx->gemm_path;
     ctx->gemm_path = 1;

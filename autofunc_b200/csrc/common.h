@@ -131,6 +131,11 @@ int small_wgrad_launch(af_ctx* ctx, const double* U, const double* UR, const dou
 int small_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, long long rows,
                        long long cols, long long n, const GemmEpilogue& e, bool dual);
 
+// input gradient through a layer with at most 16 output rows and a large batch (streaming, small_n.cu)
+bool few_rows_igrad_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs);
+int few_rows_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, long long rows,
+                          long long cols, long long n, const GemmEpilogue& e, bool dual);
+
 // whole-step persistent kernel for an MLP plan with n <= 8 samples (small_mlp.cu)
 bool small_mlp_applicable(af_ctx* ctx, int L, const int64_t* sizes, int64_t n);
 int small_mlp_launch(af_ctx* ctx, int L, const int64_t* sizes, int64_t n, double* const* param, const double* const* rvec,

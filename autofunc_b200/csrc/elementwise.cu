@@ -23,7 +23,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const double* __restrict__ 
   if (r1 > n) r1 = n;
   double a0 = 0.0, a1 = 0.0;
   if (c < len) {
-    for (long long r = r0 + ty; r < r1; r += 8) {
+    long long r = r0 + ty;
+    if (gb && rgb) {  // the common case, unrolled: eight independent loads in flight per thread
+      const double* u = U + c;
+      const double* ur = UR + c;
+      for (; r + 24 < r1; r += 32) {
+        const double x0 = u[r * len], x1 = u[(r + 8) * len], x2 = u[(r + 16) * len], x3 = u[(r + 24) * len];
+        const double y0 = ur[r * len], y1 = ur[(r + 8) * len], y2 = ur[(r + 16) * len], y3 = ur[(r + 24) * len];
+        a0 += (x0 + x1) + (x2 + x3);
+        a1 += (y0 + y1) + (y2 + y3);
+      }
+    }
+    for (; r < r1; r += 8) {
       if (gb) a0 += U[r * len + c];
       if (rgb) a1 += UR[r * len + c];
     }

@@ -173,6 +173,52 @@ __global__ void __launch_bounds__(kSmallThreads) small_igrad_kernel(const double
   }
 }
 
+// ---- input gradient through a layer with FEW OUTPUT ROWS (the 10-class head of the bench network) ----------
+// D[i][k] = sum_{m < M} U[i][m] W[m][k] with M <= 16: a contraction of length M is no tensor-core work (one k-tile,
+// 11 % pipe utilisation measured), it is a streaming pass over the n x K outputs.  Thread = (sample, column pair);
+// W / RW (M x K, a few tens of KB) come from L1, the epilogue (sigmoid backward of the layer below, or plain store)
+// is applied in registers, so HBM sees S, RS once and D, DR once.
+constexpr int kFewRowsSpt = 4;  // samples per thread: every W / RW load from L1 is reused for four samples
+
+template <bool DUAL>
+__global__ void __launch_bounds__(256) few_rows_igrad_kernel(const double* __restrict__ U, const double* __restrict__ UR,
+                                                             const double* __restrict__ W, const double* __restrict__ RW,
+                                                             int rows, int cols, long long n, const GemmArgs p) {
+  const int half = cols / 2;
+  const bool vec_ok = (p.ldo & 1) == 0 && (p.epi != EPI_SIGMOID_BWD || (p.lds & 1) == 0);
+  const long long groups = (n + kFewRowsSpt - 1) / kFewRowsSpt;
+  const long long total = groups * half;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const long long ig = idx / half;
+    const int k = 2 * (int)(idx - ig * half);
+    const long long i0 = ig * kFewRowsSpt;
+    double2 d[kFewRowsSpt], dr[kFewRowsSpt];
+#pragma unroll
+    for (int q = 0; q < kFewRowsSpt; ++q) d[q] = dr[q] = make_double2(0.0, 0.0);
+#pragma unroll 2
+    for (int m = 0; m < rows; ++m) {
+      const double2 wv = ld2(W + (long long)m * cols + k);
+      double2 rwv = make_double2(0.0, 0.0);
+      if (DUAL && RW) rwv = ld2(RW + (long long)m * cols + k);
+#pragma unroll
+      for (int q = 0; q < kFewRowsSpt; ++q) {
+        if (i0 + q < n) {
+          const double um = U[(i0 + q) * rows + m];
+          d[q].x = fma(um, wv.x, d[q].x); d[q].y = fma(um, wv.y, d[q].y);
+          if (DUAL) {
+            const double urm = UR ? UR[(i0 + q) * rows + m] : 0.0;
+            dr[q].x = fma(urm, wv.x, fma(um, rwv.x, dr[q].x));
+            dr[q].y = fma(urm, wv.y, fma(um, rwv.y, dr[q].y));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kFewRowsSpt; ++q)
+      if (i0 + q < n) epi_pair<DUAL>(p, vec_ok, i0 + q, k, d[q].x, d[q].y, dr[q].x, dr[q].y);
+  }
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -247,6 +293,28 @@ int small_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const dou
   a.I = (int)n; a.J = (int)cols; a.epi = e.epi; a.out0 = D; a.out1 = DR; a.ldo = e.ldo;
   a.s = e.s; a.rs = e.rs; a.lds = e.lds;
   return gemm_deferred_epilogue(ctx, a, dual);
+}
+
+bool few_rows_igrad_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs) {
+  if (ctx->gemm_path == 1 || ctx->small_n_off) return false;
+  if (rows < 1 || rows > 16 || n <= 16 || (cols & 1) || cols < 2 || cols > (1 << 30)) return false;
+  for (const void* p : ptrs)
+    if (p && !aligned16(p)) return false;
+  return true;
+}
+
+int few_rows_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, long long rows,
+                          long long cols, long long n, const GemmEpilogue& e, bool dual) {
+  GemmArgs a{};
+  a.I = (int)n; a.J = (int)cols; a.Kd = (int)rows; a.epi = e.epi; a.out0 = e.out0; a.out1 = dual ? e.out1 : nullptr;
+  a.ldo = e.ldo; a.s = e.s; a.rs = e.rs; a.lds = e.lds;
+  const long long total = (n + kFewRowsSpt - 1) / kFewRowsSpt * (cols / 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 8ll * ctx->sm_count) blocks = 8ll * ctx->sm_count;
+  if (dual) few_rows_igrad_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(U, UR, W, RW, (int)rows, (int)cols, n, a);
+  else few_rows_igrad_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(U, nullptr, W, nullptr, (int)rows, (int)cols, n, a);
+  const double out_vectors = (dual ? 2.0 : 1.0) * (e.epi == EPI_SIGMOID_BWD ? 2.0 : 1.0);
+  return after_launch(ctx, "few_rows_igrad_kernel", KIND_SMALL_N, 8.0 * n * cols * out_vectors);
 }
 
 }  // namespace af

@@ -317,11 +317,11 @@ def gpu_arm(args):
     launches = ctx.launch_count() - launches0
     if args.trace and rank == 0:
         per_step = count.value // K
-        names = {0: "gemm_dual", 1: "gemm_single", 2: "gemm_generic", 3: "elementwise", 4: "reduce"}
+        names = {0: "gemm_dual", 1: "gemm_single", 2: "gemm_generic", 3: "elementwise", 4: "reduce", 5: "streaming"}
         for i in range(count.value - per_step, count.value):
             rate = work[i] / (ms_arr[i] * 1e-3) / 1e12 if ms_arr[i] > 0 else 0.0
             unit = "TFLOP/s" if kinds[i] < 3 else "TB/s"
-            print(f"trace[{i - (count.value - per_step):2d}] {names[kinds[i]]:12s} {ms_arr[i] * 1e3:9.1f} us  work {work[i]:.4g}  {rate:7.2f} {unit}",
+            print(f"trace[{i - (count.value - per_step):2d}] {names.get(kinds[i], str(kinds[i])):12s} {ms_arr[i] * 1e3:9.1f} us  work {work[i]:.4g}  {rate:7.2f} {unit}",
                   file=sys.stderr)
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
