@@ -1,0 +1,613 @@
+// C++ host-side tests of the drop-in (include/autofunc_b200.hpp): the reference's own Go tests for the path,
+// restated test for test (file:line cited at each), plus a `run` mode that pytest drives with seeded inputs to compare
+// the C++ host path with the CPU oracle at 1e-12 + 1e-10|ref| (tests/test_gpu_cpp_host.py).
+//
+//   host_tests selftest [name-substring]      run the restated reference tests (needs a B200)
+//   host_tests run <case> <in.bin> <out.bin> <args...>
+//
+// Files are sequences of vectors in the reference's Variable wire format (variable.go:24-37).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <iterator>
+#include <string>
+#include <vector>
+
+#include "autofunc_b200.hpp"
+#include "functest.hpp"
+
+using namespace autofunc;
+using functest::RFuncChecker;
+using linalg::Vector;
+
+namespace {
+
+struct TestFailure : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+void Fatalf(const std::string& msg) { throw TestFailure(msg); }
+
+std::string Show(const Vector& v) {
+  std::string s = "[";
+  for (size_t i = 0; i < v.size(); i++) s += (i ? " " : "") + std::to_string(v[i]);
+  return s + "]";
+}
+
+void ExpectFullCheck(RFuncChecker c) {
+  std::vector<std::string> errs = c.FullCheck();
+  if (errs.empty()) return;
+  std::string all = std::to_string(errs.size()) + " FullCheck errors; first: " + errs[0];
+  Fatalf(all);
+}
+
+void ExpectPanic(const std::string& want, const std::function<void()>& fn) {
+  try {
+    fn();
+  } catch (const Panic& p) {
+    if (std::string(p.what()) != want) Fatalf("expected panic \"" + want + "\" but got \"" + p.what() + "\"");
+    return;
+  }
+  Fatalf("expected panic \"" + want + "\" but nothing was thrown");
+}
+
+template <class T, class... A>
+std::shared_ptr<T> New(A&&... a) {
+  return std::make_shared<T>(std::forward<A>(a)...);
+}
+
+// ---- fixtures: test/lin_tran_test.go:12-53 ----------------------------------------------------------------
+struct LinTranFixture {
+  std::shared_ptr<LinTran> mat1 = New<LinTran>(NewVariable({1, 2, 3, 3, 4, 5, -6, 1, 7, 8, -10, 4}), 3, 4);
+  std::shared_ptr<LinTran> mat2 = New<LinTran>(NewVariable({4, 2, 3}), 1, 3);
+  VariablePtr vec = NewVariable({4, 3, 2, 1});
+  VariablePtr vec2 = NewVariable({5, 1, -3, 2, 1, 2, 3, 4});
+  std::vector<VariablePtr> vars{mat1->Data, mat2->Data, vec, vec2};
+  RVector rv{
+      {mat1->Data.get(),
+       {0.40350, 0.75874, 0.87843, 0.86287, 0.97869, 0.27141, 0.84472, 0.43952, 0.49841, 0.46748, 0.71821, 0.57590}},
+      {mat2->Data.get(), {0.45823, 0.66692, 0.14662}},
+      {vec.get(), {0, -1, 3, -7}},
+      {vec2.get(), {1, 3, -2, 3, -3, 2, 1, 7}},
+  };
+};
+
+// test/lin_tran_test.go:55-63
+struct LinTranBatchTest : RFunc {
+  std::shared_ptr<LinTran> m1, m2;
+  LinTranBatchTest(std::shared_ptr<LinTran> a, std::shared_ptr<LinTran> b) : m1(std::move(a)), m2(std::move(b)) {}
+  ResultPtr Apply(ResultPtr v) override { return m2->Batch(m1->Batch(v, 2), 2); }
+  RResultPtr ApplyR(const RVector& rv, RResultPtr v) override { return m2->BatchR(rv, m1->BatchR(rv, v, 2), 2); }
+};
+
+void TestLinTranOutput() {  // test/lin_tran_test.go:65-73
+  LinTranFixture f;
+  Vector actual = f.mat1->Apply(f.vec)->Output();
+  if (actual != Vector{19, 20, 36}) Fatalf("expected [19 20 36] got " + Show(actual));
+  RResultPtr r = f.mat1->ApplyR(f.rv, NewRVariable(f.vec, f.rv));
+  if (r->Output() != Vector{19, 20, 36}) Fatalf("ApplyR: expected [19 20 36] got " + Show(r->Output()));
+}
+
+void TestLinTran() {  // test/lin_tran_test.go:75-83
+  LinTranFixture f;
+  ExpectFullCheck(RFuncChecker(New<ComposedRFunc>(ComposedRFunc{f.mat1, f.mat2}), f.vars, f.vec, f.rv));
+}
+
+void TestLinTranBatchOutput() {  // test/lin_tran_test.go:85-97
+  LinTranFixture f;
+  Vector actual = LinTranBatchTest(f.mat1, f.mat2).Apply(f.vec2)->Output();
+  if (actual != Vector{349, 131}) Fatalf("expected [349 131] got " + Show(actual));
+}
+
+void TestLinTranBatch() {  // test/lin_tran_test.go:99-107
+  LinTranFixture f;
+  ExpectFullCheck(RFuncChecker(New<LinTranBatchTest>(f.mat1, f.mat2), f.vars, f.vec2, f.rv));
+}
+
+void TestLinAdd() {  // test/lin_add_test.go:11-30
+  VariablePtr v1 = NewVariable({1, 3, 2, 1}), v2 = NewVariable({5, -3, 5, 4});
+  RVector rv{{v1.get(), {0.5, -10, 5, 3.14}}, {v2.get(), {0, 5, -15, -30}}};
+  ExpectFullCheck(RFuncChecker(New<ComposedRFunc>(ComposedRFunc{New<LinAdd>(v1), New<LinAdd>(v2)}), {v1, v2}, v2, rv));
+}
+
+// ---- test/math_funcs_test.go:13-100 ----------------------------------------------------------------------------
+struct MathFixture {
+  VariablePtr vec = NewVariable({1, -0.5, 0.3, 0.7}), vecPos = NewVariable({1, 0.5, 0.3, 0.7});
+  std::vector<VariablePtr> vars{vec, vecPos};
+  RVector rv{{vec.get(), {0.5, -10, 5, 3.14}}};
+  void Check(std::shared_ptr<RFunc> f, bool positive = false) {
+    ExpectFullCheck(RFuncChecker(std::move(f), vars, positive ? vecPos : vec, rv));
+  }
+};
+void TestExp() { MathFixture().Check(New<Exp>()); }
+void TestLog() { MathFixture().Check(New<Log>(), true); }
+void TestSquaredNorm() { MathFixture().Check(New<SquaredNorm>()); }
+void TestSigmoid() {
+  MathFixture().Check(New<ComposedRFunc>(ComposedRFunc{New<Sigmoid>(), New<Sigmoid>(), New<Sigmoid>()}));
+}
+void TestLogSigmoid() {
+  MathFixture().Check(New<ComposedRFunc>(ComposedRFunc{New<LogSigmoid>(), New<LogSigmoid>(), New<LogSigmoid>()}));
+}
+void TestSoftmax() { MathFixture().Check(New<Softmax>()); }
+void TestSoftmax3() { MathFixture().Check(New<Softmax>(3)); }
+void TestSin() { MathFixture().Check(New<Sin>()); }
+void TestTanh() { MathFixture().Check(New<Tanh>()); }  // extension; Sigmoid's contract
+
+// ---- test/slices_test.go:11-120 --------------------------------------------------------------------------------
+struct SlicesFixture {
+  VariablePtr v1 = NewVariable({1, 2, -4, 3, -2}), v2 = NewVariable({4, -2, 3, -0.5, 0.3}),
+              v3 = NewVariable({0.99196, 0.48826, 0.51066, 0.66715, 0.44423});
+  std::vector<VariablePtr> vars{v1, v2, v3};
+  // vector 2 intentionally left out (slices_test.go:30-31)
+  RVector rv{{v1.get(), {0.340162, -0.325063, 0.179612, 0.056463, -0.812274}},
+             {v3.get(), {0.59824, -0.63322, 0.13379, 0.99559, 0.53748}}};
+};
+struct ConcatTestFunc : RFunc {
+  SlicesFixture* f;
+  explicit ConcatTestFunc(SlicesFixture* fx) : f(fx) {}
+  ResultPtr Apply(ResultPtr r) override { return Concat({f->v1, r, f->v3}); }
+  RResultPtr ApplyR(const RVector&, RResultPtr r) override {
+    return ConcatR({NewRVariable(f->v1, f->rv), r, NewRVariable(f->v3, f->rv)});
+  }
+};
+struct SliceTestFunc : RFunc {
+  bool WrapInput;
+  explicit SliceTestFunc(bool w) : WrapInput(w) {}
+  ResultPtr Apply(ResultPtr r) override {
+    if (WrapInput) r = Add(r, Scale(r, 0));
+    return Slice(r, 1, 3);
+  }
+  RResultPtr ApplyR(const RVector&, RResultPtr r) override {
+    if (WrapInput) r = AddR(r, ScaleR(r, 0));
+    return SliceR(r, 1, 3);
+  }
+};
+struct RepeatTestFunc : RFunc {
+  ResultPtr Apply(ResultPtr r) override { return Repeat(Add(Add(r, Scale(r, 0)), r), 3); }
+  RResultPtr ApplyR(const RVector&, RResultPtr r) override { return RepeatR(AddR(AddR(r, ScaleR(r, 0)), r), 3); }
+};
+void TestConcat() {
+  SlicesFixture f;
+  ExpectFullCheck(RFuncChecker(New<ConcatTestFunc>(&f), f.vars, f.v2, f.rv));
+}
+void TestSlice() {
+  SlicesFixture f;
+  ExpectFullCheck(RFuncChecker(New<SliceTestFunc>(false), f.vars, f.v1, f.rv));
+}
+void TestWrappedSlice() {
+  SlicesFixture f;
+  ExpectFullCheck(RFuncChecker(New<SliceTestFunc>(true), f.vars, f.v1, f.rv));
+}
+void TestRepeat() {
+  SlicesFixture f;
+  ExpectFullCheck(RFuncChecker(New<RepeatTestFunc>(), f.vars, f.v1, f.rv));
+}
+
+// ---- the hot subset of test/arithmetic_test.go:12-77 (same fixtures; vector 2 absent from the RVector) ------------
+struct ArithmeticTestFunc : RFunc {
+  VariablePtr v1, v2, v3, v4;
+  const RVector* rv;
+  ResultPtr Apply(ResultPtr r) override {
+    ResultPtr sq1 = Square(Mul(Scale(Add(r, v1), -0.2), v2));
+    ResultPtr sum1 = AddScaler(Add(Mul(sq1, v3), Scale(v4, -0.5)), 2);
+    return Scale(Sub(SumAll(Mul(sum1, sum1)), SumAll(Sub(sq1, v1))), 0.05);
+  }
+  RResultPtr ApplyR(const RVector&, RResultPtr r) override {
+    RResultPtr r1 = NewRVariable(v1, *rv), r2 = NewRVariable(v2, *rv), r3 = NewRVariable(v3, *rv),
+               r4 = NewRVariable(v4, *rv);
+    RResultPtr sq1 = SquareR(MulR(ScaleR(AddR(r, r1), -0.2), r2));
+    RResultPtr sum1 = AddScalerR(AddR(MulR(sq1, r3), ScaleR(r4, -0.5)), 2);
+    return ScaleR(SubR(SumAllR(MulR(sum1, sum1)), SumAllR(SubR(sq1, r1))), 0.05);
+  }
+};
+void TestArithmetic() {
+  auto f = New<ArithmeticTestFunc>();
+  f->v1 = NewVariable({1, 2, -4, 3, -2});
+  f->v2 = NewVariable({4, -2, 3, -0.5, 0.3});
+  f->v3 = NewVariable({0.99196, 0.48826, 0.51066, 0.66715, 0.44423});
+  f->v4 = NewVariable({0.509893, 0.874112, -0.080468, 0.372740, -0.172097});
+  RVector rv{{f->v1.get(), {0.340162, -0.325063, 0.179612, 0.056463, -0.812274}},
+             {f->v3.get(), {0.59824, -0.63322, 0.13379, 0.99559, 0.53748}},
+             {f->v4.get(), {4.2222, 5.2762, -7.5762, 2.3420, -1.8927}}};
+  f->rv = &rv;
+  ExpectFullCheck(RFuncChecker(f, {f->v1, f->v2, f->v3, f->v4}, f->v4, rv));
+}
+
+// ---- test/variable_test.go:12-35 ---------------------------------------------------------------------------------
+void TestVariableSerialize() {
+  Vector x(17);
+  uint64_t s = 88172645463325252ull;
+  for (double& e : x) {
+    s ^= s << 13, s ^= s >> 7, s ^= s << 17;
+    e = (double)(int64_t)s / 9.2e18;
+  }
+  VariablePtr v = NewVariable(x);
+  std::string data = v->Serialize() + NewVariable({1.5, -2.5})->Serialize();
+  size_t pos = 0;
+  VariablePtr a = Variable::Deserialize(data, &pos), b = Variable::Deserialize(data, &pos);
+  if (a->Vector != x) Fatalf("round trip changed the vector");
+  if (b->Vector != Vector{1.5, -2.5} || pos != data.size()) Fatalf("second variable did not round-trip");
+  if (data.size() != 8 + 17 * 8 + 8 + 2 * 8 || (unsigned char)data[0] != 17) Fatalf("wire format is not LE u64 count + f64s");
+}
+
+// ---- batcher.go:34-111: the batched form of a Func equals the per-sample form (seqfunc TestMapBatcherOutput's idea) --
+struct Net {
+  std::vector<VariablePtr> vars;
+  ComposedRBatcher layers;
+  std::shared_ptr<ComposedRFunc> func = New<ComposedRFunc>();
+  RVector rv;
+};
+double Uniform(uint64_t* s) {
+  *s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = *s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0) * 2 - 1;
+}
+Vector RandomVector(size_t n, uint64_t* s, double scale = 1) {
+  Vector v(n);
+  for (double& e : v) e = scale * Uniform(s);
+  return v;
+}
+Net MakeNet(const std::vector<int>& sizes, uint64_t seed, bool biasesInRV = true) {
+  Net net;
+  uint64_t s = seed;
+  for (size_t l = 0; l + 1 < sizes.size(); l++) {
+    int in = sizes[l], out = sizes[l + 1];
+    VariablePtr w = NewVariable(RandomVector((size_t)in * out, &s, 1 / std::sqrt((double)in)));
+    VariablePtr b = NewVariable(RandomVector((size_t)out, &s));
+    net.vars.push_back(w);
+    net.vars.push_back(b);
+    auto lt = New<LinTran>(w, out, in);
+    auto la = New<LinAdd>(b);
+    auto sg = New<Sigmoid>();
+    net.layers.push_back(lt);
+    net.layers.push_back(la);
+    net.layers.push_back(sg);
+    net.func->push_back(lt);
+    net.func->push_back(la);
+    net.func->push_back(sg);
+    net.rv[w.get()] = RandomVector(w->Vector.size(), &s);
+    if (biasesInRV) net.rv[b.get()] = RandomVector(b->Vector.size(), &s);
+  }
+  return net;
+}
+void ExpectClose(const Vector& a, const Vector& b, const std::string& what, double rtol = 1e-10, double atol = 1e-12) {
+  if (a.size() != b.size()) Fatalf(what + ": lengths differ");
+  for (size_t i = 0; i < a.size(); i++)
+    if (!(std::fabs(a[i] - b[i]) <= atol + rtol * std::fabs(b[i])))
+      Fatalf(what + ": entry " + std::to_string(i) + ": " + std::to_string(a[i]) + " vs " + std::to_string(b[i]));
+}
+
+void TestRFuncBatcherMatchesBatch() {
+  Net net = MakeNet({5, 7, 3}, 11);
+  const int n = 4;
+  uint64_t s = 99;
+  VariablePtr x = NewVariable(RandomVector(5 * n, &s));
+  net.rv[x.get()] = RandomVector(5 * n, &s);
+  std::vector<VariablePtr> vars = net.vars;
+  vars.push_back(x);
+  Vector up = RandomVector(3 * n, &s), upR = RandomVector(3 * n, &s);
+  auto run = [&](RBatcher& b, Vector* out, Vector* outR, Gradient* g, RGradient* rg) {
+    RResultPtr r = b.BatchR(net.rv, NewRVariable(x, net.rv), n);
+    *out = r->Output();
+    *outR = r->ROutput();
+    *g = NewGradient(vars);
+    *rg = NewRGradient(vars);
+    r->PropagateRGradient(up, upR, *rg, g);
+  };
+  Vector o1, r1, o2, r2;
+  Gradient g1, g2;
+  RGradient rg1, rg2;
+  run(net.layers, &o1, &r1, &g1, &rg1);
+  RFuncBatcher naive(net.func);  // batcher.go:57-84: Slice, ApplyR per sample, Concat
+  run(naive, &o2, &r2, &g2, &rg2);
+  ExpectClose(o2, o1, "output");
+  ExpectClose(r2, r1, "r-output");
+  for (auto& v : vars) {
+    ExpectClose(g2[v.get()], g1[v.get()], "gradient");
+    ExpectClose(rg2[v.get()], rg1[v.get()], "r-gradient");
+  }
+  // non-R: FuncBatcher vs ComposedBatcher
+  ResultPtr a = net.layers.Batch(x, n), b = FuncBatcher(net.func).Batch(x, n);
+  ExpectClose(b->Output(), a->Output(), "Batch output");
+  Gradient ga = NewGradient(vars), gb = NewGradient(vars);
+  a->PropagateGradient(up, ga);
+  b->PropagateGradient(up, gb);
+  for (auto& v : vars) ExpectClose(gb[v.get()], ga[v.get()], "Batch gradient");
+}
+
+// The fused layer, the whole-network plan and the operator chain are the same function (bench/mlp.go:75-83).
+void TestFusedAndPlanMatchOperators() {
+  std::vector<int> sizes{24, 40, 16, 10};
+  const int n = 33;
+  Net net = MakeNet(sizes, 5, /*biasesInRV=*/false);  // biases absent from the RVector: zero R (variable.go:85-91)
+  uint64_t s = 7;
+  VariablePtr x = NewVariable(RandomVector((size_t)sizes[0] * n, &s));
+  Vector up = RandomVector((size_t)sizes.back() * n, &s), upR = RandomVector((size_t)sizes.back() * n, &s);
+  auto run = [&](RBatcher& b, Vector* out, Vector* outR, Gradient* g, RGradient* rg) {
+    RResultPtr r = b.BatchR(net.rv, NewRVariable(x, net.rv), n);
+    *out = r->Output();
+    *outR = r->ROutput();
+    *g = NewGradient(net.vars);
+    *rg = NewRGradient(net.vars);
+    r->PropagateRGradient(up, upR, *rg, g);
+  };
+  Vector o1, r1, o2, r2;
+  Gradient g1, g2;
+  RGradient rg1, rg2;
+  run(net.layers, &o1, &r1, &g1, &rg1);
+  ComposedRBatcher fused = b200::FuseDense(net.layers);
+  if (fused.size() != sizes.size() - 1) Fatalf("FuseDense did not fuse every {LinTran, LinAdd, Sigmoid} triple");
+  run(fused, &o2, &r2, &g2, &rg2);
+  ExpectClose(o2, o1, "fused output");
+  ExpectClose(r2, r1, "fused r-output");
+  for (auto& v : net.vars) {
+    ExpectClose(g2[v.get()], g1[v.get()], "fused gradient");
+    ExpectClose(rg2[v.get()], rg1[v.get()], "fused r-gradient");
+  }
+  b200::MLP plan(std::vector<int64_t>(sizes.begin(), sizes.end()), n);
+  plan.SetParams(net.vars, net.rv);
+  Gradient g3 = NewGradient(net.vars);
+  RGradient rg3 = NewRGradient(net.vars);
+  for (auto& kv : g3) kv.second.assign(kv.second.size(), 1.0);  // gradients ACCUMULATE (variable.go:45)
+  auto res = plan.StepR(net.vars, x->Vector, up, upR, rg3, &g3);
+  ExpectClose(res.first, o1, "plan output");
+  ExpectClose(res.second, r1, "plan r-output");
+  for (auto& v : net.vars) {
+    Vector want = g1[v.get()];
+    for (double& e : want) e += 1.0;
+    ExpectClose(g3[v.get()], want, "plan gradient (accumulated onto ones)");
+    ExpectClose(rg3[v.get()], rg1[v.get()], "plan r-gradient");
+  }
+}
+
+// result.go:62-65: grad == nil; lin_tran.go:374-386: only map keys receive gradient; Constant prunes the recursion.
+void TestNilGradientAndPruning() {
+  Net net = MakeNet({6, 8, 4}, 3);
+  const int n = 5;
+  uint64_t s = 17;
+  VariablePtr x = NewVariable(RandomVector(6 * n, &s));
+  Vector up = RandomVector(4 * n, &s), upR = RandomVector(4 * n, &s);
+  RResultPtr r = net.layers.BatchR(net.rv, NewRVariable(x, net.rv), n);
+  Gradient g = NewGradient(net.vars);
+  RGradient rg = NewRGradient(net.vars);
+  r->PropagateRGradient(up, upR, rg, &g);
+  RGradient rgOnly = NewRGradient({net.vars[2], net.vars[3]});  // last layer only
+  r = net.layers.BatchR(net.rv, NewRVariable(x, net.rv), n);
+  int64_t before = b200::Context::Default().LaunchCount();
+  r->PropagateRGradient(up, upR, rgOnly, nullptr);
+  int64_t launches = b200::Context::Default().LaunchCount() - before;
+  if (rgOnly.size() != 2) Fatalf("PropagateRGradient added keys to the map");
+  ExpectClose(rgOnly[net.vars[2].get()], rg[net.vars[2].get()], "nil-grad r-gradient W2");
+  ExpectClose(rgOnly[net.vars[3].get()], rg[net.vars[3].get()], "nil-grad r-gradient b2");
+  // sigmoid backward + column sums + weight gradient of layer 2, two accumulator memsets: the first layer is constant
+  // w.r.t. {W2, b2}, so neither an input gradient nor anything of layer 1 may run.
+  if (launches > 6) Fatalf("pruned backward pass launched " + std::to_string(launches) + " kernels");
+  RGradient none;
+  if (!r->Constant(none, nullptr) || r->Constant(rgOnly, nullptr) || r->Constant(none, &g) ||
+      r->Constant(NewRGradient({x}), nullptr))
+    Fatalf("Constant() is wrong");
+}
+
+// lin_tran.go:26-27,52-54; batcher.go:41; arithmetic.go:265: the reference's panic texts
+void TestPanics() {
+  LinTranFixture f;
+  ExpectPanic("input length should be 4 but got 8", [&] { f.mat1->Apply(f.vec2); });
+  ExpectPanic("input length should be 12 but got 8", [&] { f.mat1->Batch(f.vec2, 3); });
+  ExpectPanic("input length should be 4 but got 8", [&] { f.mat1->ApplyR(f.rv, NewRVariable(f.vec2, f.rv)); });
+  ExpectPanic("input count does not divide input length", [&] { Sigmoid().Batch(f.vec2, 3); });
+  ExpectPanic("vector sizes do not match", [&] { Add(f.vec, f.vec2); });
+  ExpectPanic("vector sizes do not match", [&] { MulR(NewRVariable(f.vec, f.rv), NewRVariable(f.vec2, f.rv)); });
+  ExpectPanic("invalid upstream size", [&] {
+    Gradient g = NewGradient(f.vars);
+    f.mat1->Apply(f.vec)->PropagateGradient({1, 2}, g);
+  });
+}
+
+// A foreign host-only Result in the middle of a device chain (the drop-in must coexist with the reference's own nodes).
+struct HostDouble : Result {
+  ResultPtr in;
+  Vector out;
+  explicit HostDouble(ResultPtr r) : in(std::move(r)), out(in->Output()) {
+    for (double& e : out) e *= 2;
+  }
+  const Vector& Output() override { return out; }
+  bool Constant(const Gradient& g) override { return in->Constant(g); }
+  void PropagateGradient(Vector up, Gradient& g) override {
+    for (double& e : up) e *= 2;
+    in->PropagateGradient(std::move(up), g);
+  }
+};
+void TestForeignHostResultInChain() {
+  LinTranFixture f;
+  Gradient g1 = NewGradient(f.vars), g2 = NewGradient(f.vars);
+  ResultPtr a = f.mat2->Apply(New<HostDouble>(f.mat1->Apply(f.vec)));
+  ResultPtr b = f.mat2->Apply(Scale(f.mat1->Apply(f.vec), 2));
+  if (a->Output() != b->Output()) Fatalf("outputs differ: " + Show(a->Output()) + " vs " + Show(b->Output()));
+  a->PropagateGradient({1}, g1);
+  b->PropagateGradient({1}, g2);
+  for (auto& v : f.vars) ExpectClose(g1[v.get()], g2[v.get()], "gradient through a host node");
+}
+
+struct NamedTest {
+  const char* name;
+  void (*fn)();
+};
+#define T(x) {#x, x}
+const NamedTest kTests[] = {
+    T(TestLinTranOutput), T(TestLinTran), T(TestLinTranBatchOutput), T(TestLinTranBatch), T(TestLinAdd), T(TestExp),
+    T(TestLog), T(TestSquaredNorm), T(TestSigmoid), T(TestLogSigmoid), T(TestSoftmax), T(TestSoftmax3), T(TestSin),
+    T(TestTanh), T(TestConcat), T(TestSlice), T(TestWrappedSlice), T(TestRepeat), T(TestArithmetic),
+    T(TestVariableSerialize), T(TestRFuncBatcherMatchesBatch), T(TestFusedAndPlanMatchOperators),
+    T(TestNilGradientAndPruning), T(TestPanics), T(TestForeignHostResultInChain),
+};
+#undef T
+
+int SelfTest(const std::string& filter) {
+  int failed = 0, ran = 0;
+  for (const NamedTest& t : kTests) {
+    if (!filter.empty() && std::string(t.name).find(filter) == std::string::npos) continue;
+    ran++;
+    try {
+      t.fn();
+      std::printf("PASS %s\n", t.name);
+    } catch (const std::exception& e) {
+      failed++;
+      std::printf("FAIL %s: %s\n", t.name, e.what());
+    }
+  }
+  std::printf("%d tests, %d failed; %lld kernel launches\n", ran, failed,
+              (long long)b200::Context::Default().LaunchCount());
+  return failed == 0 && ran > 0 ? 0 : 1;
+}
+
+// ---- run mode: seeded inputs from pytest, outputs back for the oracle comparison -------------------------------
+std::vector<Vector> ReadVectors(const std::string& path) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in) throw std::runtime_error("cannot open " + path);
+  std::string bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  std::vector<Vector> out;
+  size_t pos = 0;
+  while (pos < bytes.size()) out.push_back(Variable::Deserialize(bytes, &pos)->Vector);
+  return out;
+}
+void WriteVectors(const std::string& path, const std::vector<Vector>& vs) {
+  std::ofstream out(path, std::ios::binary);
+  for (const Vector& v : vs) {
+    std::string s = Variable(v).Serialize();
+    out.write(s.data(), (std::streamsize)s.size());
+  }
+  if (!out) throw std::runtime_error("cannot write " + path);
+}
+
+// mlp <mode> <n> <s0> ... <sL>   in: W0 b0 ... | RW0 Rb0 ... | X U UR    out: out rout g... rg...
+std::vector<Vector> RunMLP(const std::vector<std::string>& a, const std::vector<Vector>& in) {
+  std::string mode = a.at(0);
+  int n = std::stoi(a.at(1));
+  std::vector<int64_t> sizes;
+  for (size_t i = 2; i < a.size(); i++) sizes.push_back(std::stoll(a[i]));
+  size_t P = 2 * (sizes.size() - 1);
+  if (in.size() != 2 * P + 3) throw std::runtime_error("mlp: expected 2P+3 input vectors");
+  std::vector<VariablePtr> vars;
+  RVector rv;
+  ComposedRBatcher layers;
+  for (size_t i = 0; i < P; i++) {
+    vars.push_back(NewVariable(in[i]));
+    rv[vars[i].get()] = in[P + i];
+  }
+  for (size_t l = 0; l + 1 < sizes.size(); l++) {
+    layers.push_back(New<LinTran>(vars[2 * l], (int)sizes[l + 1], (int)sizes[l]));
+    layers.push_back(New<LinAdd>(vars[2 * l + 1]));
+    layers.push_back(New<Sigmoid>());
+  }
+  VariablePtr x = NewVariable(in[2 * P]);
+  const Vector &up = in[2 * P + 1], &upR = in[2 * P + 2];
+  Gradient g = NewGradient(vars);
+  RGradient rg = NewRGradient(vars);
+  std::vector<Vector> out;
+  if (mode == "plan") {
+    b200::MLP plan(sizes, n);
+    plan.SetParams(vars, rv);
+    auto r = plan.StepR(vars, x->Vector, up, upR, rg, &g);
+    out = {r.first, r.second};
+  } else if (mode == "nonr") {
+    ResultPtr r = layers.Batch(x, n);
+    out = {r->Output()};
+    r->PropagateGradient(up, g);
+    for (auto& v : vars) out.push_back(g[v.get()]);
+    return out;
+  } else {
+    ComposedRBatcher net = mode == "fused" ? b200::FuseDense(layers) : layers;
+    RResultPtr r = net.BatchR(rv, NewRVariable(x, rv), n);
+    out = {r->Output(), r->ROutput()};
+    r->PropagateRGradient(up, upR, rg, mode == "nilgrad" ? nullptr : &g);
+  }
+  for (auto& v : vars) out.push_back(g[v.get()]);
+  for (auto& v : vars) out.push_back(rg[v.get()]);
+  return out;
+}
+
+// lintran <rows> <cols> <n>   (bench/lintran.go:60-90: the input is a variable too)
+// in: W RW X RX U UR    out: Y RY gW rgW gX rgX
+std::vector<Vector> RunLinTran(const std::vector<std::string>& a, const std::vector<Vector>& in) {
+  int rows = std::stoi(a.at(0)), cols = std::stoi(a.at(1)), n = std::stoi(a.at(2));
+  VariablePtr w = NewVariable(in.at(0)), x = NewVariable(in.at(2));
+  RVector rv{{w.get(), in.at(1)}, {x.get(), in.at(3)}};
+  LinTran lt(w, rows, cols);
+  RResultPtr r = lt.BatchR(rv, NewRVariable(x, rv), n);
+  Gradient g = NewGradient({w, x});
+  RGradient rg = NewRGradient({w, x});
+  std::vector<Vector> out{r->Output(), r->ROutput()};
+  r->PropagateRGradient(in.at(4), in.at(5), rg, &g);
+  out.insert(out.end(), {g[w.get()], rg[w.get()], g[x.get()], rg[x.get()]});
+  return out;
+}
+
+// lstm <I> <H> <O> <T> <B>   in: 10 params | 10 R-vectors | inputs upstreams upstreamsR   out: out rout 10 g 10 rg
+std::vector<Vector> RunLSTM(const std::vector<std::string>& a, const std::vector<Vector>& in) {
+  b200::LSTM net(std::stoll(a.at(0)), std::stoll(a.at(1)), std::stoll(a.at(2)), std::stoll(a.at(3)), std::stoll(a.at(4)));
+  std::vector<VariablePtr> vars;
+  RVector rv;
+  for (int i = 0; i < 10; i++) {
+    vars.push_back(NewVariable(in.at(i)));
+    rv[vars[i].get()] = in.at(10 + i);
+  }
+  net.SetParams(vars, rv);
+  Gradient g = NewGradient(vars);
+  RGradient rg = NewRGradient(vars);
+  auto r = net.RunR(vars, in.at(20), in.at(21), in.at(22), rg, &g);
+  std::vector<Vector> out{r.first, r.second};
+  for (auto& v : vars) out.push_back(g[v.get()]);
+  for (auto& v : vars) out.push_back(rg[v.get()]);
+  return out;
+}
+
+// arith <n> <m> <k>: a composite over Add/Repeat/Sigmoid/Exp/Scale/Mul/Sub/Square/SumAll/Slice/Concat
+// in: X (n*m) B (m) RX RB U UR (1 + k)   out: out rout gX gB rgX rgB
+std::vector<Vector> RunArith(const std::vector<std::string>& a, const std::vector<Vector>& in) {
+  int n = std::stoi(a.at(0)), k = std::stoi(a.at(2));
+  VariablePtr x = NewVariable(in.at(0)), b = NewVariable(in.at(1));
+  RVector rv{{x.get(), in.at(2)}, {b.get(), in.at(3)}};
+  RResultPtr rx = NewRVariable(x, rv), rb = NewRVariable(b, rv);
+  RResultPtr h = AddR(rx, RepeatR(rb, n));
+  RResultPtr gte = MulR(Sigmoid().ApplyR(rv, h), Exp().ApplyR(rv, ScaleR(rx, 0.5)));
+  RResultPtr o = ConcatR({SumAllR(SquareR(SubR(gte, rx))), SliceR(gte, 1, 1 + k)});
+  Gradient g = NewGradient({x, b});
+  RGradient rg = NewRGradient({x, b});
+  std::vector<Vector> out{o->Output(), o->ROutput()};
+  o->PropagateRGradient(in.at(4), in.at(5), rg, &g);
+  out.insert(out.end(), {g[x.get()], g[b.get()], rg[x.get()], rg[b.get()]});
+  return out;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  std::vector<std::string> args(argv + 1, argv + argc);
+  try {
+    if (!args.empty() && args[0] == "selftest") return SelfTest(args.size() > 1 ? args[1] : "");
+    if (args.size() >= 4 && args[0] == "run") {
+      std::vector<Vector> in = ReadVectors(args[2]);
+      std::vector<std::string> rest(args.begin() + 4, args.end());
+      std::vector<Vector> out;
+      if (args[1] == "mlp") out = RunMLP(rest, in);
+      else if (args[1] == "lintran") out = RunLinTran(rest, in);
+      else if (args[1] == "lstm") out = RunLSTM(rest, in);
+      else if (args[1] == "arith") out = RunArith(rest, in);
+      else throw std::runtime_error("unknown case " + args[1]);
+      WriteVectors(args[3], out);
+      std::printf("run ok: %lld kernel launches\n", (long long)b200::Context::Default().LaunchCount());
+      return 0;
+    }
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "host_tests: %s\n", e.what());
+    return 2;
+  }
+  std::fprintf(stderr, "usage: host_tests selftest [filter] | run <case> <in> <out> <args...>\n");
+  return 64;
+}
