@@ -198,7 +198,7 @@ class Session {
     auto key = std::make_pair((const void*)&m, (const void*)v);
     auto it = acc_.find(key);
     if (it != acc_.end()) return it->second.acc;
-    Entry e{&m, v, DevVec::Zeros(len)};
+    Entry e{&m, v, DevVec::Zeros(len), false};
     acc_.emplace(key, e);
     return e.acc;
   }
@@ -206,17 +206,27 @@ class Session {
     Dev a = Accumulator(m, v, u->n);
     check(af_axpy(ctx(), 1.0, u->p, a->p, a->n));
   }
+  // Make `acc` the accumulator for (m, v) and keep it out of Flush: the map's vector for v lives in HBM
+  // (DeviceGradient below), so backward passes accumulate straight into it and nothing is copied to the host.
+  void Seed(Gradient& m, Variable* v, Dev acc) {
+    acc_[std::make_pair((const void*)&m, (const void*)v)] = Entry{&m, v, std::move(acc), true};
+  }
   void Flush() {
-    for (auto& kv : acc_) {
-      Entry& e = kv.second;
+    for (auto it0 = acc_.begin(); it0 != acc_.end();) {
+      Entry& e = it0->second;
+      if (e.resident) {
+        ++it0;
+        continue;
+      }
       auto it = e.map->find(e.v);
-      if (it == e.map->end()) continue;
-      linalg::Vector h = e.acc->Download();
-      linalg::Vector& dst = it->second;
-      if (dst.size() != h.size()) throw Panic("vector sizes do not match");
-      for (size_t i = 0; i < h.size(); i++) dst[i] += h[i];
+      if (it != e.map->end()) {
+        linalg::Vector h = e.acc->Download();
+        linalg::Vector& dst = it->second;
+        if (dst.size() != h.size()) throw Panic("vector sizes do not match");
+        for (size_t i = 0; i < h.size(); i++) dst[i] += h[i];
+      }
+      it0 = acc_.erase(it0);
     }
-    acc_.clear();
   }
 
  private:
@@ -224,6 +234,7 @@ class Session {
     Gradient* map;
     Variable* v;
     Dev acc;
+    bool resident = false;
   };
   std::map<std::pair<const void*, const void*>, Entry> acc_;
 };
@@ -295,6 +306,7 @@ class Variable : public Result {
   // after mutating a larger one in place call MarkDirty().
   b200::Dev dev() override {
     const size_t kAuto = 1 << 16;
+    if (host_stale_) return dev_;
     if (dev_ && Vector.size() <= kAuto && snapshot_ != Vector) dev_.reset();
     if (dev_ && (size_t)dev_->n != Vector.size()) dev_.reset();
     if (!dev_) {
@@ -304,6 +316,20 @@ class Variable : public Result {
     return dev_;
   }
   void MarkDirty() { dev_.reset(); }
+  // Vector += scale * g without leaving HBM (gradient.go:40-52's Axpy on the device copy).  The device copy is then
+  // the authoritative one: call Sync() before reading or writing `Vector` on the host again.
+  void AddScaledDevice(double scale, const b200::Dev& g) {
+    b200::Dev d = dev();
+    if (g->n != d->n) throw Panic("vector sizes do not match");
+    b200::check(af_axpy(b200::ctx(), scale, g->p, d->p, d->n));
+    host_stale_ = true;
+  }
+  void Sync() {
+    if (!host_stale_) return;
+    Vector = dev_->Download();
+    if (Vector.size() <= (size_t)(1 << 16)) snapshot_ = Vector;
+    host_stale_ = false;
+  }
   void bwd(b200::Session& s, b200::Dev u, Gradient& grad) override {
     if (grad.find(this) != grad.end()) s.Accumulate(grad, this, u);
   }
@@ -341,6 +367,7 @@ class Variable : public Result {
  private:
   b200::Dev dev_;
   linalg::Vector snapshot_;
+  bool host_stale_ = false;
 };
 
 inline VariablePtr NewVariable(linalg::Vector v) { return std::make_shared<Variable>(std::move(v)); }
@@ -567,6 +594,61 @@ class DeviceRResult : public RResult {
   linalg::Vector host_, host_r_;
   bool have_ = false, have_r_ = false;
 };
+
+// a Gradient / RGradient whose vectors live in HBM (gradient.go:11-57 on the device), so a
+// training loop never downloads a gradient.  `Keys()` is the map handed to Propagate* (its host vectors stay empty:
+// only the keys matter, as everywhere in the reference); the sums land in the device vectors.  Device chains only:
+// a foreign host-only Result below a DeviceGradient pass would find the empty host vectors.
+class DeviceGradient {
+ public:
+  explicit DeviceGradient(const std::vector<VariablePtr>& vars) {  // gradient.go:13-19
+    for (auto& v : vars) {
+      keys_[v.get()] = linalg::Vector();
+      vecs_[v.get()] = DevVec::Zeros((int64_t)v->Vector.size());
+    }
+  }
+  Gradient& Keys() { return keys_; }
+  Dev operator[](const VariablePtr& v) { return vecs_.at(v.get()); }
+  linalg::Vector Host(const VariablePtr& v) { return vecs_.at(v.get())->Download(); }
+  void Zero() {  // gradient.go:22-24
+    for (auto& kv : vecs_) check(af_zero(ctx(), kv.second->p, kv.second->n));
+  }
+  void Scale(double f) {  // gradient.go:33-36
+    for (auto& kv : vecs_) check(af_scale(ctx(), kv.second->p, f, kv.second->n));
+  }
+  void Add(DeviceGradient& o) {  // gradient.go:28-30
+    for (auto& kv : vecs_) check(af_axpy(ctx(), 1.0, o.vecs_.at(kv.first)->p, kv.second->p, kv.second->n));
+  }
+  void AddToVars(double scale) {  // gradient.go:40-52
+    for (auto& kv : vecs_) kv.first->AddScaledDevice(scale, kv.second);
+  }
+  void SeedInto(Session& s) {
+    for (auto& kv : vecs_) s.Seed(keys_, kv.first, kv.second);
+  }
+
+ private:
+  Gradient keys_;
+  std::unordered_map<Variable*, Dev> vecs_;
+};
+
+// out.PropagateGradient(upstream, grad) / out.PropagateRGradient(upstream, upstreamR, rgrad, grad) with the maps in HBM.
+inline void PropagateGradient(Result& out, const linalg::Vector& upstream, DeviceGradient& grad) {
+  if ((int64_t)upstream.size() != out.len()) throw Panic("invalid upstream size");
+  Session s;
+  grad.SeedInto(s);
+  out.bwd(s, DevVec::Upload(upstream), grad.Keys());
+  s.Flush();
+}
+inline void PropagateRGradient(RResult& out, const linalg::Vector& upstream, const linalg::Vector& upstreamR,
+                               DeviceGradient& rgrad, DeviceGradient* grad) {
+  if ((int64_t)upstream.size() != out.len() || (int64_t)upstreamR.size() != out.len())
+    throw Panic("invalid upstream size");
+  Session s;
+  rgrad.SeedInto(s);
+  if (grad) grad->SeedInto(s);
+  out.bwdR(s, DevVec::Upload(upstream), DevVec::Upload(upstreamR), rgrad.Keys(), grad ? &grad->Keys() : nullptr);
+  s.Flush();
+}
 
 inline bool InGrad(const Gradient* g, Variable* v) { return g != nullptr && g->find(v) != g->end(); }
 inline Dev AccOrNull(Session& s, Gradient* g, Variable* v) {

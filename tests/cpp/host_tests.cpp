@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "autofunc_b200.hpp"
+#include "autofunc_b200_seq.hpp"
 #include "functest.hpp"
 
 using namespace autofunc;
@@ -434,6 +435,125 @@ void TestForeignHostResultInChain() {
   for (auto& v : f.vars) ExpectClose(g1[v.get()], g2[v.get()], "gradient through a host node");
 }
 
+// ---- seqfunc/test/map_test.go:11-51 fixtures -------------------------------------------------------------------
+struct SeqFixture {
+  VariablePtr tran = NewVariable({0.35771, 0.87735, 0.82339, -0.11739, -0.56811, 0.56496, 0.41425, 0.14371, -0.82190,
+                                  0.24597, -0.23267, 0.50681, -0.82619, -0.59787, -0.76291, -0.96163});
+  std::vector<VariablePtr> vars{NewVariable({1, -3, 2, 0.5}), NewVariable({3, -3, 0, 0.5}), NewVariable({2, -3, 2, -0.5}),
+                                NewVariable({0, -3, -5, 0.5}), NewVariable({-2, 0.5, 3}), tran};
+  seqfunc::VarSeqs seqs{{vars[0], vars[1], vars[2]}, {vars[2], vars[0], vars[3]}, {vars[1]}, {vars[3]},
+                        {vars[0], vars[3]}};
+  RVector rv{{vars[0].get(), {-1, 1, 0.33, -0.33}},
+             {vars[3].get(), {2, 0.33, -5, 0.33}},
+             {vars[4].get(), {1, 2, 3}},
+             {tran.get(),
+              {-0.31895, -0.47222, 0.58130, 0.54394, -0.99254, -0.42368, -0.56713, 0.15739, 0.28701, 0.92360, -0.33617,
+               -0.42437, -0.56957, -0.97235, 0.66386, 0.22420}}};
+  std::shared_ptr<LinTran> linTran = New<LinTran>(tran, 4, 4);
+};
+
+void TestMapBatcherOutput() {  // seqfunc/test/map_test.go:88-120: the batched map equals the per-vector map
+  SeqFixture f;
+  seqfunc::MapBatcher mb(f.linTran);
+  const seqfunc::Seqs actual = mb.ApplySeqs(New<seqfunc::VarResult>(f.seqs))->OutputSeqs();
+  if (actual.size() != f.seqs.size()) Fatalf("lane count differs");
+  for (size_t i = 0; i < f.seqs.size(); i++) {
+    if (actual[i].size() != f.seqs[i].size()) Fatalf("sequence length differs");
+    for (size_t j = 0; j < f.seqs[i].size(); j++)
+      ExpectClose(actual[i][j], f.linTran->Apply(f.seqs[i][j])->Output(), "mapped vector", 0, 1e-5);
+  }
+}
+
+// seqfunc/test/map_test.go:122-142 (TestMapBatcher / TestMapRBatcher) by the property the checker would establish:
+// outputs, R-outputs, gradients and R-gradients of the batched map equal the sums over the per-vector applications.
+void TestMapRBatcher() {
+  SeqFixture f;
+  auto net = New<ComposedRBatcher>(ComposedRBatcher{f.linTran, New<Sigmoid>()});
+  seqfunc::MapRBatcher mb(net);
+  seqfunc::RResultPtr res = mb.ApplySeqsR(f.rv, New<seqfunc::VarRResult>(f.rv, f.seqs));
+  uint64_t s = 5;
+  seqfunc::Seqs up, upR;
+  for (auto& seq : f.seqs) {
+    up.emplace_back();
+    upR.emplace_back();
+    for (size_t j = 0; j < seq.size(); j++) {
+      up.back().push_back(RandomVector(4, &s));
+      upR.back().push_back(RandomVector(4, &s));
+    }
+  }
+  Gradient g = NewGradient(f.vars), gWant = NewGradient(f.vars);
+  RGradient rg = NewRGradient(f.vars), rgWant = NewRGradient(f.vars);
+  res->PropagateRGradient(up, upR, rg, &g);
+  if (g.size() != f.vars.size() || rg.size() != f.vars.size()) Fatalf("pool variables were left in the maps");
+  for (size_t i = 0; i < f.seqs.size(); i++)
+    for (size_t j = 0; j < f.seqs[i].size(); j++) {
+      RResultPtr one = net->BatchR(f.rv, NewRVariable(f.seqs[i][j], f.rv), 1);
+      ExpectClose(res->OutputSeqs()[i][j], one->Output(), "output");
+      ExpectClose(res->ROutputSeqs()[i][j], one->ROutput(), "r-output");
+      one->PropagateRGradient(up[i][j], upR[i][j], rgWant, &gWant);
+    }
+  for (auto& v : f.vars) {
+    ExpectClose(g[v.get()], gWant[v.get()], "gradient", 1e-10, 1e-12);
+    ExpectClose(rg[v.get()], rgWant[v.get()], "r-gradient", 1e-10, 1e-12);
+  }
+  // nil Gradient (map_batcher.go:120-123) and the non-R map
+  RGradient rg2 = NewRGradient(f.vars);
+  mb.ApplySeqsR(f.rv, New<seqfunc::VarRResult>(f.rv, f.seqs))->PropagateRGradient(up, upR, rg2, nullptr);
+  for (auto& v : f.vars) ExpectClose(rg2[v.get()], rgWant[v.get()], "nil-grad r-gradient", 1e-10, 1e-12);
+  Gradient g3 = NewGradient(f.vars);
+  mb.ApplySeqs(New<seqfunc::VarResult>(f.seqs))->PropagateGradient(up, g3);
+  for (auto& v : f.vars) ExpectClose(g3[v.get()], gWant[v.get()], "non-R gradient", 1e-10, 1e-12);
+}
+
+// gradient.go:11-57 with the maps in HBM: same numbers as the host maps, AddToVars without a download
+void TestDeviceGradient() {
+  Net net = MakeNet({6, 9, 4}, 21);
+  const int n = 5;
+  uint64_t s = 31;
+  VariablePtr x = NewVariable(RandomVector(6 * n, &s));
+  Vector up = RandomVector(4 * n, &s), upR = RandomVector(4 * n, &s);
+  Gradient g = NewGradient(net.vars);
+  RGradient rg = NewRGradient(net.vars);
+  net.layers.BatchR(net.rv, NewRVariable(x, net.rv), n)->PropagateRGradient(up, upR, rg, &g);
+  b200::DeviceGradient dg(net.vars), drg(net.vars);
+  RResultPtr r = net.layers.BatchR(net.rv, NewRVariable(x, net.rv), n);
+  b200::PropagateRGradient(*r, up, upR, drg, &dg);
+  b200::PropagateRGradient(*r, up, upR, drg, &dg);  // accumulates (variable.go:45)
+  for (auto& v : net.vars) {
+    Vector want = g[v.get()], wantR = rg[v.get()];
+    for (double& e : want) e *= 2;
+    for (double& e : wantR) e *= 2;
+    ExpectClose(dg.Host(v), want, "device gradient");
+    ExpectClose(drg.Host(v), wantR, "device r-gradient");
+    if (!dg.Keys()[v.get()].empty()) Fatalf("a device gradient pass wrote to the host map");
+  }
+  dg.Scale(0.5);
+  std::vector<Vector> before;
+  for (auto& v : net.vars) before.push_back(v->Vector);
+  dg.AddToVars(-0.1);
+  ResultPtr after = net.layers.Batch(x, n);  // uses the updated device copies
+  for (size_t i = 0; i < net.vars.size(); i++) {
+    net.vars[i]->Sync();
+    Vector want = before[i];
+    for (size_t k = 0; k < want.size(); k++) want[k] += -0.1 * g[net.vars[i].get()][k];
+    ExpectClose(net.vars[i]->Vector, want, "AddToVars on the device");
+  }
+  std::vector<VariablePtr> fresh;
+  for (auto& v : net.vars) fresh.push_back(NewVariable(v->Vector));
+  ComposedRBatcher again;
+  for (size_t l = 0; l < 2; l++) {
+    again.push_back(New<LinTran>(fresh[2 * l], l == 0 ? 9 : 4, l == 0 ? 6 : 9));
+    again.push_back(New<LinAdd>(fresh[2 * l + 1]));
+    again.push_back(New<Sigmoid>());
+  }
+  ExpectClose(after->Output(), again.Batch(x, n)->Output(), "forward pass after the device update");
+  dg.Zero();
+  b200::PropagateGradient(*after, up, dg);
+  Gradient g2 = NewGradient(fresh);
+  again.Batch(x, n)->PropagateGradient(up, g2);
+  for (size_t i = 0; i < fresh.size(); i++) ExpectClose(dg.Host(net.vars[i]), g2[fresh[i].get()], "non-R device gradient");
+}
+
 struct NamedTest {
   const char* name;
   void (*fn)();
@@ -444,7 +564,8 @@ const NamedTest kTests[] = {
     T(TestLog), T(TestSquaredNorm), T(TestSigmoid), T(TestLogSigmoid), T(TestSoftmax), T(TestSoftmax3), T(TestSin),
     T(TestTanh), T(TestConcat), T(TestSlice), T(TestWrappedSlice), T(TestRepeat), T(TestArithmetic),
     T(TestVariableSerialize), T(TestRFuncBatcherMatchesBatch), T(TestFusedAndPlanMatchOperators),
-    T(TestNilGradientAndPruning), T(TestPanics), T(TestForeignHostResultInChain),
+    T(TestNilGradientAndPruning), T(TestPanics), T(TestForeignHostResultInChain), T(TestMapBatcherOutput),
+    T(TestMapRBatcher), T(TestDeviceGradient),
 };
 #undef T
 
