@@ -211,6 +211,29 @@ class Session {
   void Seed(Gradient& m, Variable* v, Dev acc) {
     acc_[std::make_pair((const void*)&m, (const void*)v)] = Entry{&m, v, std::move(acc), true};
   }
+  // The temp-variable protocol of pool.go:114-136 / lin_alg.go:57-68 / fold.go:62-84 inside a device backward pass:
+  // remove temp variable `v` from `m` and return everything accumulated for it -- the device accumulator plus
+  // whatever a foreign host node added to the host vector -- without leaving HBM.
+  Dev Take(Gradient& m, Variable* v) {
+    Dev d;
+    auto it = acc_.find(std::make_pair((const void*)&m, (const void*)v));
+    if (it != acc_.end()) {
+      d = it->second.acc;
+      acc_.erase(it);
+    }
+    auto mit = m.find(v);
+    if (mit == m.end()) throw Panic("temporary variable is missing from the gradient map", AF_EINVAL);
+    linalg::Vector host = std::move(mit->second);
+    m.erase(mit);
+    bool any = false;
+    for (double x : host) any = any || x != 0.0;
+    if (any) {
+      Dev up = DevVec::Upload(host);
+      if (d) check(af_axpy(ctx(), 1.0, up->p, d->p, d->n));
+      else d = up;
+    }
+    return d ? d : DevVec::Zeros((int64_t)host.size());
+  }
   void Flush() {
     for (auto it0 = acc_.begin(); it0 != acc_.end();) {
       Entry& e = it0->second;
@@ -316,6 +339,14 @@ class Variable : public Result {
     return dev_;
   }
   void MarkDirty() { dev_.reset(); }
+  // `&Variable{Vector: in.Output()}` (pool.go:42, fold.go:24, lin_alg.go:37) sharing the Result's device buffer, so
+  // pooling a device node costs no upload.
+  static std::shared_ptr<Variable> Wrap(Result& r) {
+    auto v = std::make_shared<Variable>(r.Output());
+    v->dev_ = r.dev();
+    if (v->Vector.size() <= (size_t)(1 << 16)) v->snapshot_ = v->Vector;
+    return v;
+  }
   // Vector += scale * g without leaving HBM (gradient.go:40-52's Axpy on the device copy).  The device copy is then
   // the authoritative one: call Sync() before reading or writing `Vector` on the host again.
   void AddScaledDevice(double scale, const b200::Dev& g) {
@@ -382,6 +413,14 @@ class RVariable : public RResult {
     has_r_ = it != rv.end();
     if (has_r_) r_ = &it->second;
   }
+  // &RVariable{Variable: v, ROutputVec: rOutput} (pool.go:58-61, fold.go:110-113, seqfunc/map_batcher.go:85-88);
+  // rdev, when given, is the device copy of rOutput.
+  RVariable(VariablePtr v, linalg::Vector rOutput, b200::Dev rdev = nullptr)
+      : Var(std::move(v)), has_r_(true), own_r_(std::move(rOutput)), rdev_(std::move(rdev)) {
+    r_ = &own_r_;
+  }
+  RVariable(const RVariable&) = delete;
+  RVariable& operator=(const RVariable&) = delete;
   const linalg::Vector& Output() override { return Var->Vector; }
   const linalg::Vector& ROutput() override {
     if (has_r_) return *r_;
@@ -421,7 +460,7 @@ class RVariable : public RResult {
  private:
   bool has_r_ = false;
   const linalg::Vector* r_ = nullptr;  // aliases the RVector's entry, as the reference's slice does
-  linalg::Vector zero_;
+  linalg::Vector own_r_, zero_;
   b200::Dev rdev_;
 };
 using RVariablePtr = std::shared_ptr<RVariable>;

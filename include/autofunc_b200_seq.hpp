@@ -192,7 +192,6 @@ class MapBatcherRResult : public RResult {
  public:
   RResultPtr Input;
   std::vector<VariablePtr> Pool;
-  std::vector<RVector> PoolRV;  // keeps each timestep's joined R-vector alive (the Go RVariable owns its slice)
   std::vector<autofunc::RResultPtr> Results;
   Seqs Output, ROutput;
   const Seqs& OutputSeqs() override { return Output; }
@@ -230,14 +229,10 @@ class MapRBatcher : public RFunc {
     res->Output.resize(in.size());
     res->ROutput.resize(in.size());
     size_t maxLen = maxSequenceLen(in);
-    res->PoolRV.reserve(maxLen);
     int n;
     for (size_t t = 0; t < maxLen; t++) {
       VariablePtr v = NewVariable(joinTime(in, t, &n));
-      res->PoolRV.emplace_back();
-      RVector& own = res->PoolRV.back();
-      own[v.get()] = joinTime(inR, t, &n);
-      RVariablePtr inVar = NewRVariable(v, own);  // RVariable{Variable: joined, ROutputVec: joinedR}
+      auto inVar = std::make_shared<RVariable>(v, joinTime(inR, t, &n));  // RVariable{joined, ROutputVec: joinedR}
       autofunc::RResultPtr output = B->BatchR(rv, inVar, n);
       res->Pool.push_back(v);
       res->Results.push_back(output);
