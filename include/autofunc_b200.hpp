@@ -11,9 +11,13 @@
 //   Func / RFunc / Composed(R)Func      func.go:7-45
 //   Batcher / RBatcher / Composed(R)Batcher / FuncBatcher / RFuncBatcher   batcher.go:5-111
 //   LinTran, LinAdd                     lin_tran.go, lin_add.go
-//   Sigmoid, Exp, Log, LogSigmoid, Sin, Softmax, SquaredNorm               math_funcs.go
-//   Add, Sub, Mul, Scale, AddScaler, Square, SumAll (+R forms)              arithmetic.go
-//   Concat, Slice, Repeat (+R forms)    slices.go
+//   Sigmoid, Exp, Log, LogSigmoid, Sin, Cos, Norm, Softmax, SquaredNorm     math_funcs.go
+//   Add, Sub, Mul, Div, Scale, AddScaler, Square, Inverse, Pow, SumAll, ScaleFirst, AddFirst, AddLogDomain,
+//   SumAllLogDomain (+R forms); SquaredError (the north star's cost head)   arithmetic.go
+//   Concat, Slice, Repeat, Split (+R forms)                                 slices.go
+//   Pool, PoolAll, PoolSplit (+R forms)                                     pool.go
+//   Fold, FoldR                                                             fold.go
+//   MatMulVec(s), MatMulVec(s)R                                             lin_alg.go:14-133
 //   b200::DenseSigmoid, b200::FuseDense, b200::MLP, b200::LSTM             the fused / whole-network fast paths
 //
 // A Go `panic(msg)` is a thrown autofunc::Panic carrying the same message.  Go's nil-able `Gradient` argument of
@@ -31,6 +35,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <initializer_list>
+#include <iterator>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -211,10 +218,12 @@ class Session {
   void Seed(Gradient& m, Variable* v, Dev acc) {
     acc_[std::make_pair((const void*)&m, (const void*)v)] = Entry{&m, v, std::move(acc), true};
   }
-  // The temp-variable protocol of pool.go:114-136 / lin_alg.go:57-68 / fold.go:62-84 inside a device backward pass:
-  // remove temp variable `v` from `m` and return everything accumulated for it -- the device accumulator plus
-  // whatever a foreign host node added to the host vector -- without leaving HBM.
-  Dev Take(Gradient& m, Variable* v) {
+  // The temp-variable protocol of pool.go:114-136 / lin_alg.go:57-68 / fold.go:62-84 inside a device backward pass.
+  // The caller inserted `m[v]` as an EMPTY vector (a zero vector that has not been materialised: every host-side
+  // `+=` in this header treats an empty destination as zeros of the source's length), ran the inner backward pass,
+  // and now removes v from m and takes everything accumulated for it -- the device accumulator plus whatever a
+  // foreign host node added to the host vector -- without leaving HBM.  `len` sizes the all-zero answer.
+  Dev Take(Gradient& m, Variable* v, int64_t len) {
     Dev d;
     auto it = acc_.find(std::make_pair((const void*)&m, (const void*)v));
     if (it != acc_.end()) {
@@ -225,14 +234,17 @@ class Session {
     if (mit == m.end()) throw Panic("temporary variable is missing from the gradient map", AF_EINVAL);
     linalg::Vector host = std::move(mit->second);
     m.erase(mit);
-    bool any = false;
-    for (double x : host) any = any || x != 0.0;
-    if (any) {
+    if (!host.empty()) {
+      if ((int64_t)host.size() != len) throw Panic("vector sizes do not match");
       Dev up = DevVec::Upload(host);
       if (d) check(af_axpy(ctx(), 1.0, up->p, d->p, d->n));
       else d = up;
     }
-    return d ? d : DevVec::Zeros((int64_t)host.size());
+    return d ? d : DevVec::Zeros(len);
+  }
+  // Drop whatever is still keyed by map `m` (a node-local Gradient{} that stood in for a nil one, pool.go:164-166).
+  void Forget(Gradient& m) {
+    for (auto it = acc_.begin(); it != acc_.end();) it = it->second.map == &m ? acc_.erase(it) : std::next(it);
   }
   void Flush() {
     for (auto it0 = acc_.begin(); it0 != acc_.end();) {
@@ -245,6 +257,7 @@ class Session {
       if (it != e.map->end()) {
         linalg::Vector h = e.acc->Download();
         linalg::Vector& dst = it->second;
+        if (dst.empty()) dst.assign(h.size(), 0.0);  // an unmaterialised zero vector (see Take)
         if (dst.size() != h.size()) throw Panic("vector sizes do not match");
         for (size_t i = 0; i < h.size(); i++) dst[i] += h[i];
       }
@@ -314,16 +327,21 @@ class Variable : public Result {
 
   explicit Variable(linalg::Vector v) : Vector(std::move(v)) {}
 
-  const linalg::Vector& Output() override { return Vector; }               // variable.go:39
+  const linalg::Vector& Output() override {  // variable.go:39
+    Sync();
+    return Vector;
+  }
   bool Constant(const Gradient& g) override {                               // variable.go:49-52
     return g.find(this) == g.end();
   }
   void PropagateGradient(linalg::Vector upstream, Gradient& grad) override {  // variable.go:43-47
     auto it = grad.find(this);
     if (it == grad.end()) return;
+    if (it->second.empty()) it->second.assign(upstream.size(), 0.0);  // an unmaterialised zero vector (Session::Take)
     if (it->second.size() != upstream.size()) throw Panic("vector sizes do not match");
     for (size_t i = 0; i < upstream.size(); i++) it->second[i] += upstream[i];
   }
+  int64_t len() override { return host_stale_ ? dev_->n : (int64_t)Vector.size(); }
 
   // The device copy is cached.  Vectors of up to 64Ki entries are compared with the snapshot taken at upload;
   // after mutating a larger one in place call MarkDirty().
@@ -339,12 +357,13 @@ class Variable : public Result {
     return dev_;
   }
   void MarkDirty() { dev_.reset(); }
-  // `&Variable{Vector: in.Output()}` (pool.go:42, fold.go:24, lin_alg.go:37) sharing the Result's device buffer, so
-  // pooling a device node costs no upload.
-  static std::shared_ptr<Variable> Wrap(Result& r) {
-    auto v = std::make_shared<Variable>(r.Output());
-    v->dev_ = r.dev();
-    if (v->Vector.size() <= (size_t)(1 << 16)) v->snapshot_ = v->Vector;
+  // `&Variable{Vector: in.Output()}` (pool.go:42, fold.go:24, lin_alg.go:37) sharing the producing node's device
+  // buffer: pooling a device node costs neither an upload nor a download.  `Vector` is filled on the first Output()
+  // (or Sync()); until then len() and dev() are the device copy's.
+  static std::shared_ptr<Variable> Wrap(b200::Dev d) {
+    auto v = std::make_shared<Variable>(linalg::Vector());
+    v->dev_ = std::move(d);
+    v->host_stale_ = true;
     return v;
   }
   // Vector += scale * g without leaving HBM (gradient.go:40-52's Axpy on the device copy).  The device copy is then
@@ -421,10 +440,21 @@ class RVariable : public RResult {
   }
   RVariable(const RVariable&) = delete;
   RVariable& operator=(const RVariable&) = delete;
-  const linalg::Vector& Output() override { return Var->Vector; }
+  // &RVariable{Variable: pool, ROutputVec: in.ROutput()} with the R-output still in HBM (nullptr == identically zero)
+  static std::shared_ptr<RVariable> Wrap(VariablePtr v, b200::Dev rdev) {
+    auto r = std::make_shared<RVariable>(std::move(v), linalg::Vector(), rdev);
+    r->has_r_ = rdev != nullptr;
+    r->own_stale_ = rdev != nullptr;
+    return r;
+  }
+  const linalg::Vector& Output() override { return Var->Output(); }
   const linalg::Vector& ROutput() override {
+    if (own_stale_) {
+      own_r_ = rdev_->Download();
+      own_stale_ = false;
+    }
     if (has_r_) return *r_;
-    if (zero_.size() != Var->Vector.size()) zero_.assign(Var->Vector.size(), 0.0);
+    if ((int64_t)zero_.size() != Var->len()) zero_.assign((size_t)Var->len(), 0.0);
     return zero_;
   }
   bool Constant(const RGradient& rg, const Gradient* g) override {  // variable.go:102-111
@@ -435,6 +465,7 @@ class RVariable : public RResult {
   void PropagateRGradient(linalg::Vector upstream, linalg::Vector upstreamR, RGradient& rgrad,
                           Gradient* grad) override {  // variable.go:113-123
     auto add = [](linalg::Vector& dst, const linalg::Vector& src) {
+      if (dst.empty()) dst.assign(src.size(), 0.0);  // an unmaterialised zero vector (Session::Take)
       if (dst.size() != src.size()) throw Panic("vector sizes do not match");
       for (size_t i = 0; i < src.size(); i++) dst[i] += src[i];
     };
@@ -445,7 +476,7 @@ class RVariable : public RResult {
     auto it = rgrad.find(Var.get());
     if (it != rgrad.end()) add(it->second, upstreamR);
   }
-  int64_t len() override { return (int64_t)Var->Vector.size(); }
+  int64_t len() override { return Var->len(); }
   b200::Dev dev() override { return Var->dev(); }
   b200::Dev devR() override {
     if (!has_r_) return nullptr;
@@ -458,7 +489,7 @@ class RVariable : public RResult {
   }
 
  private:
-  bool has_r_ = false;
+  bool has_r_ = false, own_stale_ = false;
   const linalg::Vector* r_ = nullptr;  // aliases the RVector's entry, as the reference's slice does
   linalg::Vector own_r_, zero_;
   b200::Dev rdev_;
@@ -472,7 +503,7 @@ inline RVariablePtr NewRVariable(VariablePtr v, const RVector& rv) {
 // gradient.go:13-19
 inline Gradient NewGradient(const std::vector<VariablePtr>& vars) {
   Gradient g;
-  for (auto& v : vars) g[v.get()] = linalg::Vector(v->Vector.size(), 0.0);
+  for (auto& v : vars) g[v.get()] = linalg::Vector((size_t)v->len(), 0.0);
   return g;
 }
 inline RGradient NewRGradient(const std::vector<VariablePtr>& vars) { return NewGradient(vars); }
@@ -643,7 +674,7 @@ class DeviceGradient {
   explicit DeviceGradient(const std::vector<VariablePtr>& vars) {  // gradient.go:13-19
     for (auto& v : vars) {
       keys_[v.get()] = linalg::Vector();
-      vecs_[v.get()] = DevVec::Zeros((int64_t)v->Vector.size());
+      vecs_[v.get()] = DevVec::Zeros(v->len());
     }
   }
   Gradient& Keys() { return keys_; }
@@ -691,7 +722,7 @@ inline void PropagateRGradient(RResult& out, const linalg::Vector& upstream, con
 
 inline bool InGrad(const Gradient* g, Variable* v) { return g != nullptr && g->find(v) != g->end(); }
 inline Dev AccOrNull(Session& s, Gradient* g, Variable* v) {
-  return InGrad(g, v) ? s.Accumulator(*g, v, (int64_t)v->Vector.size()) : nullptr;
+  return InGrad(g, v) ? s.Accumulator(*g, v, v->len()) : nullptr;
 }
 
 }  // namespace b200
@@ -716,6 +747,8 @@ class LinTran : public RFunc, public RBatcher {
   }
   ResultPtr Batch(ResultPtr in, int n) override;                       // lin_tran.go:50-62
   RResultPtr BatchR(const RVector& v, RResultPtr in, int n) override;  // lin_tran.go:64-77
+  // BatchR with the matrix's RVariable already built (MatMulVecsR: RVector{v: mat.ROutput()} with the R-vector in HBM)
+  RResultPtr BatchRWith(RVariablePtr rdata, RResultPtr in, int n);
 
  private:
   void checkLen(int64_t got, int n) const {
@@ -790,8 +823,11 @@ inline ResultPtr LinTran::Batch(ResultPtr in, int n) {
 }
 
 inline RResultPtr LinTran::BatchR(const RVector& v, RResultPtr in, int n) {
+  return BatchRWith(NewRVariable(Data, v), std::move(in), n);
+}
+
+inline RResultPtr LinTran::BatchRWith(RVariablePtr rdata, RResultPtr in, int n) {
   checkLen(in->len(), n);
-  RVariablePtr rdata = NewRVariable(Data, v);
   b200::Dev x = in->dev(), xr = in->devR();
   b200::Dev y = b200::DevVec::Empty((int64_t)n * Rows), ry = b200::DevVec::Empty((int64_t)n * Rows);
   b200::check(af_lintran_fwd_r(b200::ctx(), rdata->dev()->p, b200::ptr(rdata->devR()), x->p, b200::ptr(xr), y->p,
@@ -813,7 +849,7 @@ class LinAdd : public RFunc, public RBatcher {
 
  private:
   void checkLen(int64_t got, int n) const {
-    int64_t want = (int64_t)Var->Vector.size() * n;
+    int64_t want = Var->len() * n;
     if (want != got) throw Panic(Sprintf("input length should be %lld but got %lld", want, got));
   }
 };
@@ -827,7 +863,7 @@ class LinAddResult : public DeviceResult {
   bool Constant(const Gradient& g) override { return in_->Constant(g) && var_->Constant(g); }
   void bwd(Session& s, Dev u, Gradient& grad) override {  // lin_add.go:66-73
     if (!var_->Constant(grad)) {
-      Dev acc = s.Accumulator(grad, var_.get(), (int64_t)var_->Vector.size());
+      Dev acc = s.Accumulator(grad, var_.get(), var_->len());
       check(af_bias_grad(ctx(), u->p, acc->p, acc->n, n_));
     }
     if (!in_->Constant(grad)) in_->bwd(s, u, grad);
@@ -850,7 +886,7 @@ class LinAddRResult : public DeviceRResult {
     Variable* v = rvar_->Var.get();
     Dev gacc = AccOrNull(s, grad, v), racc = AccOrNull(s, &rgrad, v);
     if (gacc || racc)
-      check(af_bias_grad_r(ctx(), u->p, uR->p, mptr(gacc), mptr(racc), (int64_t)v->Vector.size(), n_));
+      check(af_bias_grad_r(ctx(), u->p, uR->p, mptr(gacc), mptr(racc), v->len(), n_));
     if (!in_->Constant(rgrad, grad)) in_->bwdR(s, u, uR, rgrad, grad);
   }
 
@@ -866,7 +902,7 @@ inline ResultPtr LinAdd::Batch(ResultPtr in, int n) {
   checkLen(in->len(), n);
   b200::Dev x = in->dev();
   b200::Dev y = b200::DevVec::Empty(x->n);
-  b200::check(af_bias_fwd(b200::ctx(), x->p, Var->dev()->p, y->p, (int64_t)Var->Vector.size(), n));
+  b200::check(af_bias_fwd(b200::ctx(), x->p, Var->dev()->p, y->p, Var->len(), n));
   return std::make_shared<b200::LinAddResult>(Var, in, n, y);
 }
 
@@ -876,7 +912,7 @@ inline RResultPtr LinAdd::BatchR(const RVector& v, RResultPtr in, int n) {
   b200::Dev x = in->dev(), xr = in->devR();
   b200::Dev y = b200::DevVec::Empty(x->n), ry = b200::DevVec::Empty(x->n);
   b200::check(af_bias_fwd_r(b200::ctx(), x->p, b200::ptr(xr), rvar->dev()->p, b200::ptr(rvar->devR()), y->p, ry->p,
-                            (int64_t)Var->Vector.size(), n));
+                            Var->len(), n));
   return std::make_shared<b200::LinAddRResult>(rvar, in, n, y, ry);
 }
 
@@ -1530,6 +1566,698 @@ class RFuncBatcher : public RBatcher {
 };
 
 // =================================================================================================
+// SURVEY 8(f) rank 3, either side of the path: Cos, Norm, Inverse, Pow, Div, ScaleFirst, AddFirst, the log-domain
+// sums, the squared-error head (math_funcs.go:201-284,599-607; arithmetic.go:378-427,495-694,772-966,1049-1090)
+// =================================================================================================
+namespace b200 {
+
+// Inverse's backward pass reads the forward OUTPUT and the INPUT's R-vector (arithmetic.go:800-807,851-867).
+inline const UnaryKernels* InverseKernels() {
+  static const UnaryKernels k{af_inverse_fwd_r, af_inverse_bwd_r, true};
+  return &k;
+}
+
+class PowResult : public DeviceResult {
+ public:
+  PowResult(ResultPtr in, double p, Dev x, Dev out) : DeviceResult(std::move(out)), in_(std::move(in)), x_(std::move(x)), p_(p) {}
+  bool Constant(const Gradient& g) override { return p_ != 0 && in_->Constant(g); }  // arithmetic.go:892-894
+  void bwd(Session& s, Dev u, Gradient& grad) override {                             // arithmetic.go:896-906
+    if (Constant(grad)) return;
+    check(af_pow_bwd_r(ctx(), x_->p, nullptr, p_, u->p, nullptr, u->n));
+    in_->bwd(s, u, grad);
+  }
+
+ private:
+  ResultPtr in_;
+  Dev x_;
+  double p_;
+};
+class PowRResult : public DeviceRResult {
+ public:
+  PowRResult(RResultPtr in, double p, Dev x, Dev xr, Dev out, Dev outR)
+      : DeviceRResult(std::move(out), std::move(outR)), in_(std::move(in)), x_(std::move(x)), xr_(std::move(xr)), p_(p) {}
+  bool Constant(const RGradient& rg, const Gradient* g) override { return p_ != 0 && in_->Constant(rg, g); }  // :944-946
+  void bwdR(Session& s, Dev u, Dev uR, RGradient& rgrad, Gradient* grad) override {                            // :948-966
+    if (Constant(rgrad, grad)) return;
+    check(af_pow_bwd_r(ctx(), x_->p, ptr(xr_), p_, u->p, uR->p, u->n));
+    in_->bwdR(s, u, uR, rgrad, grad);
+  }
+
+ private:
+  RResultPtr in_;
+  Dev x_, xr_;
+  double p_;
+};
+
+class QuotientResult : public DeviceResult {
+ public:
+  QuotientResult(ResultPtr num, ResultPtr denom, Dev b, Dev out)
+      : DeviceResult(std::move(out)), num_(std::move(num)), denom_(std::move(denom)), b_(std::move(b)) {}
+  bool Constant(const Gradient& g) override { return num_->Constant(g) && denom_->Constant(g); }
+  void bwd(Session& s, Dev u, Gradient& grad) override {  // arithmetic.go:407-423
+    bool na = !num_->Constant(grad), nb = !denom_->Constant(grad);
+    if (!na && !nb) return;
+    Dev da = na ? DevVec::Empty(u->n) : nullptr, db = nb ? DevVec::Empty(u->n) : nullptr;
+    check(af_div_bwd(ctx(), u->p, d_->p, b_->p, mptr(da), mptr(db), u->n));
+    if (na) num_->bwd(s, da, grad);
+    if (nb) denom_->bwd(s, db, grad);
+  }
+
+ private:
+  ResultPtr num_, denom_;
+  Dev b_;
+};
+
+// ScaleFirst (arithmetic.go:495-593): the scaler is read where it lives, on the device.
+class ScaleFirstResult : public DeviceResult {
+ public:
+  ScaleFirstResult(ResultPtr in, ResultPtr scaler, Dev x, Dev f, Dev out)
+      : DeviceResult(std::move(out)), in_(std::move(in)), scaler_(std::move(scaler)), x_(std::move(x)), f_(std::move(f)) {}
+  bool Constant(const Gradient& g) override { return in_->Constant(g) && scaler_->Constant(g); }
+  void bwd(Session& s, Dev u, Gradient& grad) override {  // arithmetic.go:520-533
+    if (!scaler_->Constant(grad)) {
+      Dev down = DevVec::Zeros(scaler_->len());
+      check(af_dot(ctx(), u->p, x_->p, nullptr, nullptr, down->p, u->n));
+      scaler_->bwd(s, down, grad);
+    }
+    if (!in_->Constant(grad)) {  // after the scaler's branch, so the upstream can be scaled in place
+      check(af_scale_dev(ctx(), u->p, nullptr, f_->p, nullptr, u->p, nullptr, u->n));
+      in_->bwd(s, u, grad);
+    }
+  }
+
+ private:
+  ResultPtr in_, scaler_;
+  Dev x_, f_;
+};
+class ScaleFirstRResult : public DeviceRResult {
+ public:
+  ScaleFirstRResult(RResultPtr in, RResultPtr scaler, Dev x, Dev xr, Dev f, Dev fr, Dev out, Dev outR)
+      : DeviceRResult(std::move(out), std::move(outR)), in_(std::move(in)), scaler_(std::move(scaler)), x_(std::move(x)),
+        xr_(std::move(xr)), f_(std::move(f)), fr_(std::move(fr)) {}
+  bool Constant(const RGradient& rg, const Gradient* g) override { return in_->Constant(rg, g) && scaler_->Constant(rg, g); }
+  void bwdR(Session& s, Dev u, Dev uR, RGradient& rgrad, Gradient* grad) override {  // arithmetic.go:567-593
+    if (!scaler_->Constant(rgrad, grad)) {
+      Dev down = DevVec::Zeros(scaler_->len()), downR = DevVec::Zeros(scaler_->len());
+      check(af_dot(ctx(), u->p, x_->p, nullptr, nullptr, down->p, u->n));
+      check(af_dot(ctx(), uR->p, x_->p, xr_ ? u->p : nullptr, ptr(xr_), downR->p, u->n));
+      scaler_->bwdR(s, down, downR, rgrad, grad);
+    }
+    if (!in_->Constant(rgrad, grad)) {
+      check(af_scale_dev(ctx(), u->p, uR->p, f_->p, ptr(fr_), u->p, uR->p, u->n));
+      in_->bwdR(s, u, uR, rgrad, grad);
+    }
+  }
+
+ private:
+  RResultPtr in_, scaler_;
+  Dev x_, xr_, f_, fr_;
+};
+
+// AddFirst (arithmetic.go:595-694)
+class AddFirstResult : public DeviceResult {
+ public:
+  AddFirstResult(ResultPtr in, ResultPtr scaler, Dev out)
+      : DeviceResult(std::move(out)), in_(std::move(in)), scaler_(std::move(scaler)) {}
+  bool Constant(const Gradient& g) override { return in_->Constant(g) && scaler_->Constant(g); }
+  void bwd(Session& s, Dev u, Gradient& grad) override {  // arithmetic.go:627-639
+    if (!scaler_->Constant(grad)) {
+      Dev su = DevVec::Zeros(scaler_->len());
+      check(af_sum_all(ctx(), u->p, nullptr, su->p, nullptr, u->n));
+      scaler_->bwd(s, su, grad);
+    }
+    if (!in_->Constant(grad)) in_->bwd(s, u, grad);
+  }
+
+ private:
+  ResultPtr in_, scaler_;
+};
+class AddFirstRResult : public DeviceRResult {
+ public:
+  AddFirstRResult(RResultPtr in, RResultPtr scaler, Dev out, Dev outR)
+      : DeviceRResult(std::move(out), std::move(outR)), in_(std::move(in)), scaler_(std::move(scaler)) {}
+  bool Constant(const RGradient& rg, const Gradient* g) override { return in_->Constant(rg, g) && scaler_->Constant(rg, g); }
+  void bwdR(Session& s, Dev u, Dev uR, RGradient& rgrad, Gradient* grad) override {  // arithmetic.go:680-694
+    if (!scaler_->Constant(rgrad, grad)) {
+      Dev su = DevVec::Zeros(scaler_->len()), suR = DevVec::Zeros(scaler_->len());
+      check(af_sum_all(ctx(), u->p, uR->p, su->p, suR->p, u->n));
+      scaler_->bwdR(s, su, suR, rgrad, grad);
+    }
+    if (!in_->Constant(rgrad, grad)) in_->bwdR(s, u, uR, rgrad, grad);
+  }
+
+ private:
+  RResultPtr in_, scaler_;
+};
+
+class NormResult : public DeviceResult {
+ public:
+  NormResult(ResultPtr in, Dev x, Dev out) : DeviceResult(std::move(out)), in_(std::move(in)), x_(std::move(x)) {}
+  bool Constant(const Gradient& g) override { return in_->Constant(g); }
+  void bwd(Session& s, Dev u, Gradient& grad) override {  // math_funcs.go:238-247
+    if (in_->Constant(grad)) return;
+    Dev d = DevVec::Empty(x_->n);
+    check(af_norm_bwd_r(ctx(), x_->p, nullptr, d_->p, nullptr, u->p, nullptr, d->p, nullptr, x_->n));
+    in_->bwd(s, d, grad);
+  }
+
+ private:
+  ResultPtr in_;
+  Dev x_;
+};
+class NormRResult : public DeviceRResult {
+ public:
+  NormRResult(RResultPtr in, Dev x, Dev xr, Dev out, Dev outR)
+      : DeviceRResult(std::move(out), std::move(outR)), in_(std::move(in)), x_(std::move(x)), xr_(std::move(xr)) {}
+  bool Constant(const RGradient& rg, const Gradient* g) override { return in_->Constant(rg, g); }
+  void bwdR(Session& s, Dev u, Dev uR, RGradient& rgrad, Gradient* grad) override {  // math_funcs.go:267-284
+    if (in_->Constant(rgrad, grad)) return;
+    Dev d = DevVec::Empty(x_->n), dr = DevVec::Empty(x_->n);
+    check(af_norm_bwd_r(ctx(), x_->p, ptr(xr_), d_->p, dr_->p, u->p, uR->p, d->p, dr->p, x_->n));
+    in_->bwdR(s, d, dr, rgrad, grad);
+  }
+
+ private:
+  RResultPtr in_;
+  Dev x_, xr_;
+};
+
+class SquaredErrorResult : public DeviceResult {
+ public:
+  SquaredErrorResult(ResultPtr a, ResultPtr y, Dev da, Dev dy, Dev out)
+      : DeviceResult(std::move(out)), a_(std::move(a)), y_(std::move(y)), da_(std::move(da)), dy_(std::move(dy)) {}
+  bool Constant(const Gradient& g) override { return a_->Constant(g) && y_->Constant(g); }
+  void bwd(Session& s, Dev u, Gradient& grad) override {
+    ResultPtr who[2] = {a_, y_};
+    for (int i = 0; i < 2; i++) {
+      if (who[i]->Constant(grad)) continue;
+      Dev g = DevVec::Empty(da_->n);
+      check(af_sqerr_bwd_r(ctx(), da_->p, nullptr, dy_->p, nullptr, u->p, nullptr, i == 0 ? 1.0 : -1.0, g->p, nullptr, da_->n));
+      who[i]->bwd(s, g, grad);
+    }
+  }
+
+ private:
+  ResultPtr a_, y_;
+  Dev da_, dy_;
+};
+class SquaredErrorRResult : public DeviceRResult {
+ public:
+  SquaredErrorRResult(RResultPtr a, RResultPtr y, Dev da, Dev dar, Dev dy, Dev dyr, Dev out, Dev outR)
+      : DeviceRResult(std::move(out), std::move(outR)), a_(std::move(a)), y_(std::move(y)), da_(std::move(da)),
+        dar_(std::move(dar)), dy_(std::move(dy)), dyr_(std::move(dyr)) {}
+  bool Constant(const RGradient& rg, const Gradient* g) override { return a_->Constant(rg, g) && y_->Constant(rg, g); }
+  void bwdR(Session& s, Dev u, Dev uR, RGradient& rgrad, Gradient* grad) override {
+    RResultPtr who[2] = {a_, y_};
+    for (int i = 0; i < 2; i++) {
+      if (who[i]->Constant(rgrad, grad)) continue;
+      Dev g = DevVec::Empty(da_->n), gr = DevVec::Empty(da_->n);
+      check(af_sqerr_bwd_r(ctx(), da_->p, ptr(dar_), dy_->p, ptr(dyr_), u->p, uR->p, i == 0 ? 1.0 : -1.0, g->p, gr->p,
+                           da_->n));
+      who[i]->bwdR(s, g, gr, rgrad, grad);
+    }
+  }
+
+ private:
+  RResultPtr a_, y_;
+  Dev da_, dar_, dy_, dyr_;
+};
+
+// out = x + sign * m[0] with the upstream passing through untouched: the "- maxVal" / "+ maxVal" steps of the log-domain
+// sums (arithmetic.go:1056-1090; maxVal is a constant of the graph, kept on the device).
+inline ResultPtr Shift(ResultPtr in, const Dev& m, double sign) {
+  Dev x = in->dev();
+  Dev out = DevVec::Empty(x->n);
+  check(af_add_dev(ctx(), x->p, m->p, sign, out->p, x->n));
+  return std::make_shared<ScaledResult>(std::move(in), 1.0, out);
+}
+inline RResultPtr ShiftR(RResultPtr in, const Dev& m, double sign) {
+  Dev x = in->dev(), xr = in->devR();
+  Dev out = DevVec::Empty(x->n);
+  check(af_add_dev(ctx(), x->p, m->p, sign, out->p, x->n));
+  return std::make_shared<ScaledRResult>(std::move(in), 1.0, out, xr ? xr : DevVec::Zeros(x->n));
+}
+inline Dev MaxAbs(std::initializer_list<Dev> xs) {  // linalg.Vector.MaxAbs over all the vectors
+  Dev m = DevVec::Zeros(1);
+  int i = 0;
+  for (const Dev& x : xs) check(af_max_abs(ctx(), x->p, m->p, i++ > 0, x->n));
+  return m;
+}
+
+}  // namespace b200
+
+// math_funcs.go:599-607: Cos(x) = Sin(x + pi/2)
+struct Cos : RFunc {
+  ResultPtr Apply(ResultPtr in) override { return Sin().Apply(AddScaler(std::move(in), 3.14159265358979323846 / 2)); }
+  RResultPtr ApplyR(const RVector& v, RResultPtr in) override {
+    return Sin().ApplyR(v, AddScalerR(std::move(in), 3.14159265358979323846 / 2));
+  }
+};
+
+// math_funcs.go:201-284
+struct Norm : RFunc {
+  ResultPtr Apply(ResultPtr in) override {
+    b200::Dev x = in->dev(), o = b200::DevVec::Empty(1);
+    b200::check(af_norm_fwd_r(b200::ctx(), x->p, nullptr, o->p, nullptr, x->n));
+    return std::make_shared<b200::NormResult>(std::move(in), x, o);
+  }
+  RResultPtr ApplyR(const RVector&, RResultPtr in) override {
+    b200::Dev x = in->dev(), xr = in->devR(), o = b200::DevVec::Empty(1), ro = b200::DevVec::Empty(1);
+    b200::check(af_norm_fwd_r(b200::ctx(), x->p, b200::ptr(xr), o->p, ro->p, x->n));
+    return std::make_shared<b200::NormRResult>(std::move(in), x, xr, o, ro);
+  }
+};
+
+// arithmetic.go:772-867
+inline ResultPtr Inverse(ResultPtr in) {
+  b200::Dev x = in->dev(), o = b200::DevVec::Empty(x->n);
+  b200::check(af_inverse_fwd_r(b200::ctx(), x->p, nullptr, o->p, nullptr, x->n));
+  return std::make_shared<b200::UnaryResult>(b200::InverseKernels(), std::move(in), o, o);
+}
+inline RResultPtr InverseR(RResultPtr in) {
+  b200::Dev x = in->dev(), xr = in->devR(), o = b200::DevVec::Empty(x->n), ro = b200::DevVec::Empty(x->n);
+  b200::check(af_inverse_fwd_r(b200::ctx(), x->p, b200::ptr(xr), o->p, ro->p, x->n));
+  return std::make_shared<b200::UnaryRResult>(b200::InverseKernels(), std::move(in), o, xr, o, ro);
+}
+// arithmetic.go:869-966
+inline ResultPtr Pow(ResultPtr in, double p) {
+  b200::Dev x = in->dev(), o = b200::DevVec::Empty(x->n);
+  b200::check(af_pow_fwd_r(b200::ctx(), x->p, nullptr, p, o->p, nullptr, x->n));
+  return std::make_shared<b200::PowResult>(std::move(in), p, x, o);
+}
+inline RResultPtr PowR(RResultPtr in, double p) {
+  b200::Dev x = in->dev(), xr = in->devR(), o = b200::DevVec::Empty(x->n), ro = b200::DevVec::Empty(x->n);
+  b200::check(af_pow_fwd_r(b200::ctx(), x->p, b200::ptr(xr), p, o->p, ro->p, x->n));
+  return std::make_shared<b200::PowRResult>(std::move(in), p, x, xr, o, ro);
+}
+// arithmetic.go:378-427
+inline ResultPtr Div(ResultPtr a, ResultPtr b) {
+  b200::SameLen(a->len(), b->len());
+  b200::Dev x = a->dev(), y = b->dev(), o = b200::DevVec::Empty(x->n);
+  b200::check(af_div(b200::ctx(), x->p, y->p, o->p, x->n));
+  return std::make_shared<b200::QuotientResult>(std::move(a), std::move(b), y, o);
+}
+inline RResultPtr DivR(RResultPtr a, RResultPtr b) { return MulR(std::move(a), InverseR(std::move(b))); }
+// arithmetic.go:495-593: `in` scaled by the first (only) component of `scaler`
+inline ResultPtr ScaleFirst(ResultPtr in, ResultPtr scaler) {
+  b200::Dev x = in->dev(), f = scaler->dev(), o = b200::DevVec::Empty(x->n);
+  b200::check(af_scale_dev(b200::ctx(), x->p, nullptr, f->p, nullptr, o->p, nullptr, x->n));
+  return std::make_shared<b200::ScaleFirstResult>(std::move(in), std::move(scaler), x, f, o);
+}
+inline RResultPtr ScaleFirstR(RResultPtr in, RResultPtr scaler) {
+  b200::Dev x = in->dev(), xr = in->devR(), f = scaler->dev(), fr = scaler->devR();
+  b200::Dev o = b200::DevVec::Empty(x->n), ro = b200::DevVec::Empty(x->n);
+  b200::check(af_scale_dev(b200::ctx(), x->p, b200::ptr(xr), f->p, b200::ptr(fr), o->p, ro->p, x->n));
+  return std::make_shared<b200::ScaleFirstRResult>(std::move(in), std::move(scaler), x, xr, f, fr, o, ro);
+}
+// arithmetic.go:595-694: the first component of v2 added to every component of v1
+inline ResultPtr AddFirst(ResultPtr v1, ResultPtr v2) {
+  b200::Dev x = v1->dev(), o = b200::DevVec::Empty(x->n);
+  b200::check(af_add_dev(b200::ctx(), x->p, v2->dev()->p, 1.0, o->p, x->n));
+  return std::make_shared<b200::AddFirstResult>(std::move(v1), std::move(v2), o);
+}
+inline RResultPtr AddFirstR(RResultPtr v1, RResultPtr v2) {
+  b200::Dev x = v1->dev(), xr = b200::ZerosIfNull(v1->devR(), x->n), fr = v2->devR();
+  b200::Dev o = b200::DevVec::Empty(x->n), ro;
+  b200::check(af_add_dev(b200::ctx(), x->p, v2->dev()->p, 1.0, o->p, x->n));
+  if (fr) {
+    ro = b200::DevVec::Empty(x->n);
+    b200::check(af_add_dev(b200::ctx(), xr->p, fr->p, 1.0, ro->p, x->n));
+  } else {
+    ro = xr->Copy();
+  }
+  return std::make_shared<b200::AddFirstRResult>(std::move(v1), std::move(v2), o, ro);
+}
+// arithmetic.go:1049-1072: log(exp(v1) + exp(v2)) without overflow
+inline ResultPtr AddLogDomain(ResultPtr v1, ResultPtr v2) {
+  b200::SameLen(v1->len(), v2->len());
+  b200::Dev m = b200::MaxAbs({v1->dev(), v2->dev()});
+  ResultPtr e1 = Exp().Apply(b200::Shift(std::move(v1), m, -1.0)), e2 = Exp().Apply(b200::Shift(std::move(v2), m, -1.0));
+  return b200::Shift(Log().Apply(Add(e1, e2)), m, 1.0);
+}
+inline RResultPtr AddLogDomainR(RResultPtr v1, RResultPtr v2) {
+  static const RVector none;
+  b200::SameLen(v1->len(), v2->len());
+  b200::Dev m = b200::MaxAbs({v1->dev(), v2->dev()});
+  RResultPtr e1 = Exp().ApplyR(none, b200::ShiftR(std::move(v1), m, -1.0));
+  RResultPtr e2 = Exp().ApplyR(none, b200::ShiftR(std::move(v2), m, -1.0));
+  return b200::ShiftR(Log().ApplyR(none, AddR(e1, e2)), m, 1.0);
+}
+// arithmetic.go:1074-1090: log(sum(exp(v)))
+inline ResultPtr SumAllLogDomain(ResultPtr v) {
+  b200::Dev m = b200::MaxAbs({v->dev()});
+  return b200::Shift(Log().Apply(SumAll(Exp().Apply(b200::Shift(std::move(v), m, -1.0)))), m, 1.0);
+}
+inline RResultPtr SumAllLogDomainR(RResultPtr v) {
+  static const RVector none;
+  b200::Dev m = b200::MaxAbs({v->dev()});
+  return b200::ShiftR(Log().ApplyR(none, SumAllR(Exp().ApplyR(none, b200::ShiftR(std::move(v), m, -1.0)))), m, 1.0);
+}
+// north_star's "SquaredError": .5 ||actual - expected||^2 = Scale(SquaredNorm(Sub(a, y)), .5) of the reference in one
+// reduction forward and one elementwise pass backward.
+inline ResultPtr SquaredError(ResultPtr actual, ResultPtr expected) {
+  b200::SameLen(actual->len(), expected->len());
+  b200::Dev a = actual->dev(), y = expected->dev(), o = b200::DevVec::Empty(1);
+  b200::check(af_sqerr_fwd_r(b200::ctx(), a->p, nullptr, y->p, nullptr, o->p, nullptr, a->n));
+  return std::make_shared<b200::SquaredErrorResult>(std::move(actual), std::move(expected), a, y, o);
+}
+inline RResultPtr SquaredErrorR(RResultPtr actual, RResultPtr expected) {
+  b200::SameLen(actual->len(), expected->len());
+  b200::Dev a = actual->dev(), ar = actual->devR(), y = expected->dev(), yr = expected->devR();
+  b200::Dev o = b200::DevVec::Empty(1), ro = b200::DevVec::Empty(1);
+  b200::check(af_sqerr_fwd_r(b200::ctx(), a->p, b200::ptr(ar), y->p, b200::ptr(yr), o->p, ro->p, a->n));
+  return std::make_shared<b200::SquaredErrorRResult>(std::move(actual), std::move(expected), a, ar, y, yr, o, ro);
+}
+
+// slices.go:310-335
+inline std::vector<ResultPtr> Split(int n, ResultPtr in) {
+  if (n <= 0 || in->len() % n != 0) throw Panic("count does not divide input length");
+  int64_t each = in->len() / n;
+  std::vector<ResultPtr> parts;
+  for (int i = 0; i < n; i++) parts.push_back(Slice(in, i * each, (i + 1) * each));
+  return parts;
+}
+inline std::vector<RResultPtr> SplitR(int n, RResultPtr in) {
+  if (n <= 0 || in->len() % n != 0) throw Panic("count does not divide input length");
+  int64_t each = in->len() / n;
+  std::vector<RResultPtr> parts;
+  for (int i = 0; i < n; i++) parts.push_back(SliceR(in, i * each, (i + 1) * each));
+  return parts;
+}
+
+// =================================================================================================
+// Pool / PoolAll / PoolSplit (pool.go), Fold (fold.go), MatMulVecs (lin_alg.go:14-133): graph logic around the
+// temp-variable protocol -- insert grad[tmp], propagate, read, delete.  The pool variable shares the producing node's
+// device buffer (Variable::Wrap) and what accumulates for it is taken from the backward pass's device accumulators
+// (Session::Take), so neither direction leaves HBM; a foreign host node in the chain still works (it adds into the
+// map's host vector, which Take folds in).
+// =================================================================================================
+namespace b200 {
+
+inline VariablePtr PoolVar(Result& r) { return Variable::Wrap(r.dev()); }
+inline RVariablePtr PoolRVar(RResult& r) { return RVariable::Wrap(Variable::Wrap(r.dev()), r.devR()); }
+// Gradient{v: linalg.Vector{}} at pool.go:107,117,159,174
+inline Gradient Marker(Variable* v) {
+  Gradient g;
+  g[v] = linalg::Vector();
+  return g;
+}
+
+class PooledResult : public DeviceResult {
+ public:
+  PooledResult(std::vector<ResultPtr> ins, std::vector<VariablePtr> vars, ResultPtr out)
+      : DeviceResult(out->dev()), ins_(std::move(ins)), vars_(std::move(vars)), out_(std::move(out)) {}
+  bool Constant(const Gradient& g) override {  // pool.go:102-112
+    if (!out_->Constant(g)) return false;
+    for (size_t i = 0; i < vars_.size(); i++)
+      if (!out_->Constant(Marker(vars_[i].get())) && !ins_[i]->Constant(g)) return false;
+    return true;
+  }
+  void bwd(Session& s, Dev u, Gradient& grad) override {  // pool.go:114-136
+    std::vector<bool> constant(vars_.size());
+    for (size_t i = 0; i < vars_.size(); i++) {
+      constant[i] = out_->Constant(Marker(vars_[i].get())) || ins_[i]->Constant(grad);
+      if (!constant[i]) grad[vars_[i].get()] = linalg::Vector();
+    }
+    out_->bwd(s, std::move(u), grad);
+    std::vector<Dev> ups(vars_.size());
+    for (size_t i = 0; i < vars_.size(); i++)
+      if (!constant[i]) ups[i] = s.Take(grad, vars_[i].get(), vars_[i]->len());
+    for (size_t i = 0; i < vars_.size(); i++)
+      if (!constant[i]) ins_[i]->bwd(s, ups[i], grad);
+  }
+
+ private:
+  std::vector<ResultPtr> ins_;
+  std::vector<VariablePtr> vars_;
+  ResultPtr out_;
+};
+
+class PooledRResult : public DeviceRResult {
+ public:
+  PooledRResult(std::vector<RResultPtr> ins, std::vector<VariablePtr> vars, RResultPtr out)
+      : DeviceRResult(out->dev(), out->devR()), ins_(std::move(ins)), vars_(std::move(vars)), out_(std::move(out)) {}
+  bool Constant(const RGradient& rg, const Gradient* g) override {  // pool.go:150-160
+    if (!out_->Constant(rg, g)) return false;
+    for (size_t i = 0; i < vars_.size(); i++)
+      if (!out_->Constant(Marker(vars_[i].get()), nullptr) && !ins_[i]->Constant(rg, g)) return false;
+    return true;
+  }
+  void bwdR(Session& s, Dev u, Dev uR, RGradient& rgrad, Gradient* grad) override {  // pool.go:162-195
+    Gradient temp;
+    if (grad == nullptr) grad = &temp;  // pool.go:164-166
+    std::vector<bool> constant(vars_.size());
+    for (size_t i = 0; i < vars_.size(); i++) {
+      constant[i] = out_->Constant(Marker(vars_[i].get()), nullptr) || ins_[i]->Constant(rgrad, grad);
+      if (!constant[i]) (*grad)[vars_[i].get()] = linalg::Vector(), rgrad[vars_[i].get()] = linalg::Vector();
+    }
+    out_->bwdR(s, std::move(u), std::move(uR), rgrad, grad);
+    std::vector<Dev> ups(vars_.size()), upsR(vars_.size());
+    for (size_t i = 0; i < vars_.size(); i++)
+      if (!constant[i]) {
+        ups[i] = s.Take(*grad, vars_[i].get(), vars_[i]->len());
+        upsR[i] = s.Take(rgrad, vars_[i].get(), vars_[i]->len());
+      }
+    for (size_t i = 0; i < vars_.size(); i++)
+      if (!constant[i]) ins_[i]->bwdR(s, ups[i], upsR[i], rgrad, grad);
+    if (grad == &temp) s.Forget(temp);
+  }
+
+ private:
+  std::vector<RResultPtr> ins_;
+  std::vector<VariablePtr> vars_;
+  RResultPtr out_;
+};
+
+class FoldResult : public DeviceResult {
+ public:
+  FoldResult(std::vector<VariablePtr> pool, std::vector<ResultPtr> inter, ResultPtr final)
+      : DeviceResult(final->dev()), pool_(std::move(pool)), inter_(std::move(inter)), final_(std::move(final)) {}
+  bool Constant(const Gradient& cg) override {  // fold.go:35-54 (the map is borrowed for the temporary, as in Go)
+    Gradient& g = const_cast<Gradient&>(cg);
+    if (!final_->Constant(g)) return false;
+    for (size_t i = pool_.size(); i-- > 0;) {
+      if (!inter_[i]->Constant(g)) return false;
+      if (i > 0) {
+        Variable* p = pool_[i - 1].get();
+        g[p] = linalg::Vector();
+        bool c = inter_[i]->Constant(g);
+        g.erase(p);
+        if (c) return true;
+      }
+    }
+    return true;
+  }
+  void bwd(Session& s, Dev u, Gradient& g) override {  // fold.go:56-84
+    if (pool_.empty()) return final_->bwd(s, std::move(u), g);
+    Dev stateUp = std::move(u);
+    for (size_t i = pool_.size(); i > 0; i--) {
+      Result& res = i == pool_.size() ? *final_ : *inter_[i];
+      Variable* p = pool_[i - 1].get();
+      g[p] = linalg::Vector();
+      if (res.Constant(g)) {
+        g.erase(p);
+        break;
+      }
+      res.bwd(s, stateUp, g);
+      stateUp = s.Take(g, p, p->len());
+    }
+    inter_[0]->bwd(s, stateUp, g);
+  }
+
+ private:
+  std::vector<VariablePtr> pool_;
+  std::vector<ResultPtr> inter_;
+  ResultPtr final_;
+};
+
+class FoldRResult : public DeviceRResult {
+ public:
+  FoldRResult(std::vector<VariablePtr> pool, std::vector<RResultPtr> inter, RResultPtr final)
+      : DeviceRResult(final->dev(), final->devR()), pool_(std::move(pool)), inter_(std::move(inter)),
+        final_(std::move(final)) {}
+  bool Constant(const RGradient& crg, const Gradient* cg) override {  // fold.go:113-139
+    RGradient& rg = const_cast<RGradient&>(crg);
+    Gradient* g = const_cast<Gradient*>(cg);
+    if (!final_->Constant(rg, g)) return false;
+    for (size_t i = pool_.size(); i-- > 0;) {
+      if (!inter_[i]->Constant(rg, g)) return false;
+      if (i > 0) {
+        Variable* p = pool_[i - 1].get();
+        if (g != nullptr) (*g)[p] = linalg::Vector();
+        rg[p] = linalg::Vector();
+        bool c = inter_[i]->Constant(rg, g);
+        if (g != nullptr) g->erase(p);
+        rg.erase(p);
+        if (c) return true;
+      }
+    }
+    return true;
+  }
+  void bwdR(Session& s, Dev u, Dev uR, RGradient& rg, Gradient* g) override {  // fold.go:141-178
+    if (pool_.empty()) return final_->bwdR(s, std::move(u), std::move(uR), rg, g);
+    Gradient temp;
+    if (g == nullptr) g = &temp;  // fold.go:147-149
+    Dev stateUp = std::move(u), stateUpR = std::move(uR);
+    for (size_t i = pool_.size(); i > 0; i--) {
+      RResult& res = i == pool_.size() ? *final_ : *inter_[i];
+      Variable* p = pool_[i - 1].get();
+      (*g)[p] = linalg::Vector();
+      rg[p] = linalg::Vector();
+      if (res.Constant(rg, g)) {
+        g->erase(p);
+        rg.erase(p);
+        break;
+      }
+      res.bwdR(s, stateUp, stateUpR, rg, g);
+      stateUp = s.Take(*g, p, p->len());
+      stateUpR = s.Take(rg, p, p->len());
+    }
+    inter_[0]->bwdR(s, stateUp, stateUpR, rg, g);
+    if (g == &temp) s.Forget(temp);
+  }
+
+ private:
+  std::vector<VariablePtr> pool_;
+  std::vector<RResultPtr> inter_;
+  RResultPtr final_;
+};
+
+class MatMulResult : public DeviceResult {
+ public:
+  MatMulResult(ResultPtr mat, VariablePtr matVar, ResultPtr res)
+      : DeviceResult(res->dev()), mat_(std::move(mat)), matVar_(std::move(matVar)), res_(std::move(res)) {}
+  bool Constant(const Gradient& g) override { return res_->Constant(g) && mat_->Constant(g); }  // lin_alg.go:53-55
+  void bwd(Session& s, Dev u, Gradient& grad) override {                                        // lin_alg.go:57-69
+    bool matConst = mat_->Constant(grad);
+    if (!matConst) grad[matVar_.get()] = linalg::Vector();
+    res_->bwd(s, std::move(u), grad);
+    if (!matConst) mat_->bwd(s, s.Take(grad, matVar_.get(), matVar_->len()), grad);
+  }
+
+ private:
+  ResultPtr mat_;
+  VariablePtr matVar_;
+  ResultPtr res_;
+};
+
+class MatMulRResult : public DeviceRResult {
+ public:
+  MatMulRResult(RResultPtr mat, VariablePtr matVar, RResultPtr res)
+      : DeviceRResult(res->dev(), res->devR()), mat_(std::move(mat)), matVar_(std::move(matVar)), res_(std::move(res)) {}
+  bool Constant(const RGradient& rg, const Gradient* g) override { return res_->Constant(rg, g) && mat_->Constant(rg, g); }
+  void bwdR(Session& s, Dev u, Dev uR, RGradient& rgrad, Gradient* grad) override {  // lin_alg.go:113-133
+    bool matConst = mat_->Constant(rgrad, grad);
+    Gradient temp;
+    if (!matConst) {
+      if (grad == nullptr) grad = &temp;
+      (*grad)[matVar_.get()] = linalg::Vector();
+      rgrad[matVar_.get()] = linalg::Vector();
+    }
+    res_->bwdR(s, std::move(u), std::move(uR), rgrad, grad);
+    if (!matConst) {
+      Dev d = s.Take(*grad, matVar_.get(), matVar_->len()), dr = s.Take(rgrad, matVar_.get(), matVar_->len());
+      mat_->bwdR(s, d, dr, rgrad, grad);
+    }
+    if (grad == &temp) s.Forget(temp);
+  }
+
+ private:
+  RResultPtr mat_;
+  VariablePtr matVar_;
+  RResultPtr res_;
+};
+
+}  // namespace b200
+
+// pool.go:38-68
+inline ResultPtr PoolAll(std::vector<ResultPtr> ins, const std::function<ResultPtr(const std::vector<ResultPtr>&)>& f) {
+  std::vector<VariablePtr> vars;
+  std::vector<ResultPtr> pooled;
+  for (auto& r : ins) {
+    vars.push_back(b200::PoolVar(*r));
+    pooled.push_back(vars.back());
+  }
+  ResultPtr out = f(pooled);
+  return std::make_shared<b200::PooledResult>(std::move(ins), std::move(vars), std::move(out));
+}
+inline RResultPtr PoolAllR(std::vector<RResultPtr> ins,
+                           const std::function<RResultPtr(const std::vector<RResultPtr>&)>& f) {
+  std::vector<VariablePtr> vars;
+  std::vector<RResultPtr> pooled;
+  for (auto& r : ins) {
+    RVariablePtr rv = b200::PoolRVar(*r);
+    vars.push_back(rv->Var);
+    pooled.push_back(rv);
+  }
+  RResultPtr out = f(pooled);
+  return std::make_shared<b200::PooledRResult>(std::move(ins), std::move(vars), std::move(out));
+}
+// pool.go:21-32
+inline ResultPtr Pool(ResultPtr r, const std::function<ResultPtr(ResultPtr)>& f) {
+  return PoolAll({std::move(r)}, [&](const std::vector<ResultPtr>& in) { return f(in[0]); });
+}
+inline RResultPtr PoolR(RResultPtr r, const std::function<RResultPtr(RResultPtr)>& f) {
+  return PoolAllR({std::move(r)}, [&](const std::vector<RResultPtr>& in) { return f(in[0]); });
+}
+// pool.go:70-91
+inline ResultPtr PoolSplit(int n, ResultPtr r, const std::function<ResultPtr(const std::vector<ResultPtr>&)>& f) {
+  return Pool(std::move(r), [&](ResultPtr in) { return f(Split(n, std::move(in))); });
+}
+inline RResultPtr PoolSplitR(int n, RResultPtr r, const std::function<RResultPtr(const std::vector<RResultPtr>&)>& f) {
+  return PoolR(std::move(r), [&](RResultPtr in) { return f(SplitR(n, std::move(in))); });
+}
+
+// fold.go:19-30,93-107: the recurrent state never leaves HBM between timesteps
+inline ResultPtr Fold(ResultPtr state, const std::vector<ResultPtr>& ins,
+                      const std::function<ResultPtr(ResultPtr state, ResultPtr in)>& f) {
+  std::vector<VariablePtr> pool;
+  std::vector<ResultPtr> inter;
+  for (auto& in : ins) {
+    inter.push_back(state);
+    pool.push_back(b200::PoolVar(*state));
+    state = f(pool.back(), in);
+  }
+  return std::make_shared<b200::FoldResult>(std::move(pool), std::move(inter), std::move(state));
+}
+inline RResultPtr FoldR(RResultPtr state, const std::vector<RResultPtr>& ins,
+                        const std::function<RResultPtr(RResultPtr state, RResultPtr in)>& f) {
+  std::vector<VariablePtr> pool;
+  std::vector<RResultPtr> inter;
+  for (auto& in : ins) {
+    inter.push_back(state);
+    RVariablePtr pr = b200::PoolRVar(*state);
+    pool.push_back(pr->Var);
+    state = f(pr, in);
+  }
+  return std::make_shared<b200::FoldRResult>(std::move(pool), std::move(inter), std::move(state));
+}
+
+// lin_alg.go:14-133: LinTran whose matrix is itself a Result; reuses the six LinTran kernels verbatim
+inline ResultPtr MatMulVecs(ResultPtr mat, int rows, int cols, ResultPtr vecs) {
+  if (mat->len() != (int64_t)rows * cols) throw Panic("invalid matrix data size");  // lin_alg.go:29-31
+  if (cols <= 0 || vecs->len() % cols != 0) throw Panic("invalid vecs size");        // lin_alg.go:32-34
+  int n = (int)(vecs->len() / cols);
+  VariablePtr v = b200::PoolVar(*mat);
+  ResultPtr res = LinTran(v, rows, cols).Batch(std::move(vecs), n);
+  return std::make_shared<b200::MatMulResult>(std::move(mat), std::move(v), std::move(res));
+}
+inline RResultPtr MatMulVecsR(RResultPtr mat, int rows, int cols, RResultPtr vecs) {
+  if (mat->len() != (int64_t)rows * cols) throw Panic("invalid matrix data size");  // lin_alg.go:85-87
+  if (cols <= 0 || vecs->len() % cols != 0) throw Panic("invalid vecs size");        // lin_alg.go:88-90
+  int n = (int)(vecs->len() / cols);
+  RVariablePtr mr = b200::PoolRVar(*mat);
+  RResultPtr res = LinTran(mr->Var, rows, cols).BatchRWith(mr, std::move(vecs), n);  // RVector{v: mat.ROutput()}
+  return std::make_shared<b200::MatMulRResult>(std::move(mat), mr->Var, std::move(res));
+}
+inline ResultPtr MatMulVec(ResultPtr mat, int rows, int cols, ResultPtr vec) {  // lin_alg.go:16-18
+  return MatMulVecs(std::move(mat), rows, cols, std::move(vec));
+}
+inline RResultPtr MatMulVecR(RResultPtr mat, int rows, int cols, RResultPtr vec) {  // lin_alg.go:74-76
+  return MatMulVecsR(std::move(mat), rows, cols, std::move(vec));
+}
+
+// =================================================================================================
 // b200 fast paths: fused dense layer, whole-network MLP plan, LSTM plan
 // =================================================================================================
 namespace b200 {
@@ -1543,7 +2271,7 @@ class DenseSigmoid : public RFunc, public RBatcher {
 
   DenseSigmoid(VariablePtr w, VariablePtr b, int rows, int cols, bool activation = true)
       : Weights(std::move(w)), Biases(std::move(b)), Rows(rows), Cols(cols), Activation(activation) {
-    if ((int64_t)Weights->Vector.size() != (int64_t)rows * cols || (int64_t)Biases->Vector.size() != rows)
+    if (Weights->len() != (int64_t)rows * cols || Biases->len() != rows)
       throw Panic("parameter sizes do not match rows x cols");
   }
   ResultPtr Apply(ResultPtr in) override { return Batch(std::move(in), 1); }
@@ -1657,7 +2385,7 @@ inline ComposedRBatcher FuseDense(const ComposedRBatcher& layers) {
   while (i < layers.size()) {
     auto* lt = dynamic_cast<LinTran*>(layers[i].get());
     auto* la = i + 1 < layers.size() ? dynamic_cast<LinAdd*>(layers[i + 1].get()) : nullptr;
-    if (lt && la && (int64_t)la->Var->Vector.size() == lt->Rows) {
+    if (lt && la && la->Var->len() == lt->Rows) {
       bool act = i + 2 < layers.size() && dynamic_cast<Sigmoid*>(layers[i + 2].get()) != nullptr;
       out.push_back(std::make_shared<DenseSigmoid>(lt->Data, la->Var, lt->Rows, lt->Cols, act));
       i += act ? 3 : 2;

@@ -295,6 +295,120 @@ int af_fill_dev(af_ctx* c, double* x, const double* v, int64_t n) {
 }
 int af_fill(af_ctx* c, double* x, double v, int64_t n) { return af_fill_dev(c, x, &v, n); }
 
+// arithmetic.go:772-867.  The backward pass reads the forward OUTPUT o = 1/x and the input's R-vector.
+EW_FWD(af_inverse_fwd_r, o = 1 / x; ro = -(o * o) * xr)
+EW_BWD(af_inverse_bwd_r, const double sq = -(s * s); nu = sq * u; nur = sq * ur + -2 * (sq * s) * sr * u)
+// arithmetic.go:869-966
+int af_pow_fwd_r(af_ctx* c, const double* X, const double* RX, double p, double* O, double* RO, int64_t len) {
+  CTX(c);
+  for (int64_t i = 0; i < len; i++) {
+    O[i] = std::pow(X[i], p);
+    if (RO) RO[i] = p != 0 ? p * std::pow(X[i], p - 1) * (RX ? RX[i] : 0) : 0.0;  // :925-930
+  }
+  return AF_OK;
+}
+int af_pow_bwd_r(af_ctx* c, const double* X, const double* RX, double p, double* U, double* UR, int64_t len) {
+  CTX(c);
+  if (p == 1) return AF_OK;  // :898,952
+  for (int64_t i = 0; i < len; i++) {
+    const double u = U[i], d1 = p * std::pow(X[i], p - 1);
+    if (UR) UR[i] = UR[i] * d1 + u * (p * (p - 1) * std::pow(X[i], p - 2) * (RX ? RX[i] : 0));  // :955-961
+    U[i] = u * d1;
+  }
+  return AF_OK;
+}
+// arithmetic.go:378-423
+int af_div(af_ctx* c, const double* A, const double* B, double* O, int64_t n) {
+  CTX(c);
+  for (int64_t i = 0; i < n; i++) O[i] = A[i] / B[i];
+  return AF_OK;
+}
+int af_div_bwd(af_ctx* c, const double* U, const double* O, const double* B, double* DA, double* DB, int64_t n) {
+  CTX(c);
+  for (int64_t i = 0; i < n; i++) {
+    if (DA) DA[i] = U[i] / B[i];              // :409-415
+    if (DB) DB[i] = U[i] * (-O[i] / B[i]);    // :416-421
+  }
+  return AF_OK;
+}
+// arithmetic.go:595-612 (AddFirst) and the "- maxVal" / "+ maxVal" of :1056-1090
+int af_add_dev(af_ctx* c, const double* X, const double* f, double sign, double* O, int64_t n) {
+  CTX(c);
+  for (int64_t i = 0; i < n; i++) O[i] = X[i] + sign * f[0];
+  return AF_OK;
+}
+// arithmetic.go:503-510,544-553 forward; :583-592 on the upstreams.  Outputs may alias inputs.
+int af_scale_dev(af_ctx* c, const double* X, const double* RX, const double* f, const double* fR, double* O,
+                 double* RO, int64_t n) {
+  CTX(c);
+  for (int64_t i = 0; i < n; i++) {
+    const double x = X[i], xr = RX ? RX[i] : 0;
+    if (RO) RO[i] = x * (fR ? fR[0] : 0) + xr * f[0];
+    O[i] = x * f[0];
+  }
+  return AF_OK;
+}
+// DotFast at arithmetic.go:523,571-573
+int af_dot(af_ctx* c, const double* a, const double* b, const double* cc, const double* d, double* out, int64_t n) {
+  CTX(c);
+  if ((cc == nullptr) != (d == nullptr)) return fail(AF_EINVAL, "af_dot: c and d must be given together");
+  double s = 0;
+  for (int64_t i = 0; i < n; i++) s += a[i] * b[i] + (cc ? cc[i] * d[i] : 0);
+  *out = s;
+  return AF_OK;
+}
+// linalg.Vector.MaxAbs at arithmetic.go:1057,1078
+int af_max_abs(af_ctx* c, const double* x, double* out, int combine, int64_t n) {
+  CTX(c);
+  double m = 0;
+  for (int64_t i = 0; i < n; i++) m = std::fmax(m, std::fabs(x[i]));
+  *out = combine ? std::fmax(*out, m) : m;
+  return AF_OK;
+}
+// math_funcs.go:201-284
+int af_norm_fwd_r(af_ctx* c, const double* X, const double* RX, double* out, double* outR, int64_t n) {
+  CTX(c);
+  double ss = 0, xr = 0;
+  for (int64_t i = 0; i < n; i++) ss += X[i] * X[i], xr += X[i] * (RX ? RX[i] : 0);
+  *out = std::sqrt(ss);
+  if (outR) *outR = (1 / *out) * xr;  // :222-224
+  return AF_OK;
+}
+int af_norm_bwd_r(af_ctx* c, const double* X, const double* RX, const double* o, const double* ro, const double* u,
+                  const double* uR, double* D, double* DR, int64_t n) {
+  CTX(c);
+  for (int64_t i = 0; i < n; i++) {
+    const double s = u[0] / o[0];
+    if (DR) DR[i] = X[i] * (-u[0] * ro[0] / (o[0] * o[0]) + uR[0] / o[0]) + (RX ? RX[i] : 0) * s;  // :267-284
+    D[i] = X[i] * s;                                                                              // :238-247
+  }
+  return AF_OK;
+}
+// Scale(SquaredNorm(Sub(a, y)), .5): math_funcs.go:191-199, arithmetic.go:105-182,436-493,696-770,972-1047
+int af_sqerr_fwd_r(af_ctx* c, const double* A, const double* RA, const double* Y, const double* RY, double* out,
+                   double* outR, int64_t n) {
+  CTX(c);
+  double s = 0, sr = 0;
+  for (int64_t i = 0; i < n; i++) {
+    const double d = A[i] - Y[i];
+    s += d * d;
+    sr += 2 * d * ((RA ? RA[i] : 0) - (RY ? RY[i] : 0));
+  }
+  *out = 0.5 * s;
+  if (outR) *outR = 0.5 * sr;
+  return AF_OK;
+}
+int af_sqerr_bwd_r(af_ctx* c, const double* A, const double* RA, const double* Y, const double* RY, const double* u,
+                   const double* uR, double sign, double* G, double* GR, int64_t n) {
+  CTX(c);
+  for (int64_t i = 0; i < n; i++) {
+    const double d = A[i] - Y[i], dr = (RA ? RA[i] : 0) - (RY ? RY[i] : 0), hu = 0.5 * u[0];
+    if (GR) GR[i] = sign * (2 * ((0.5 * uR[0]) * d + hu * dr));
+    G[i] = sign * (hu * (2 * d));
+  }
+  return AF_OK;
+}
+
 // ---- Softmax rows (math_funcs.go:479-509; no max-subtraction, like the reference) -------------------------------
 int af_softmax_fwd_r(af_ctx* c, const double* X, const double* RX, double t, double* Y, double* RY, int64_t len,
                      int64_t n) {

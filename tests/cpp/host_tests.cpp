@@ -60,6 +60,72 @@ std::shared_ptr<T> New(A&&... a) {
   return std::make_shared<T>(std::forward<A>(a)...);
 }
 
+// ---- shared helpers ------------------------------------------------------------------------------------------------
+struct Net {
+  std::vector<VariablePtr> vars;
+  ComposedRBatcher layers;
+  std::shared_ptr<ComposedRFunc> func = New<ComposedRFunc>();
+  RVector rv;
+};
+double Uniform(uint64_t* s) {
+  *s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = *s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0) * 2 - 1;
+}
+Vector RandomVector(size_t n, uint64_t* s, double scale = 1) {
+  Vector v(n);
+  for (double& e : v) e = scale * Uniform(s);
+  return v;
+}
+Net MakeNet(const std::vector<int>& sizes, uint64_t seed, bool biasesInRV = true) {
+  Net net;
+  uint64_t s = seed;
+  for (size_t l = 0; l + 1 < sizes.size(); l++) {
+    int in = sizes[l], out = sizes[l + 1];
+    VariablePtr w = NewVariable(RandomVector((size_t)in * out, &s, 1 / std::sqrt((double)in)));
+    VariablePtr b = NewVariable(RandomVector((size_t)out, &s));
+    net.vars.push_back(w);
+    net.vars.push_back(b);
+    auto lt = New<LinTran>(w, out, in);
+    auto la = New<LinAdd>(b);
+    auto sg = New<Sigmoid>();
+    net.layers.push_back(lt);
+    net.layers.push_back(la);
+    net.layers.push_back(sg);
+    net.func->push_back(lt);
+    net.func->push_back(la);
+    net.func->push_back(sg);
+    net.rv[w.get()] = RandomVector(w->Vector.size(), &s);
+    if (biasesInRV) net.rv[b.get()] = RandomVector(b->Vector.size(), &s);
+  }
+  return net;
+}
+void ExpectClose(const Vector& a, const Vector& b, const std::string& what, double rtol = 1e-10, double atol = 1e-12) {
+  if (a.size() != b.size()) Fatalf(what + ": lengths differ");
+  for (size_t i = 0; i < a.size(); i++)
+    if (!(std::fabs(a[i] - b[i]) <= atol + rtol * std::fabs(b[i])))
+      Fatalf(what + ": entry " + std::to_string(i) + ": " + std::to_string(a[i]) + " vs " + std::to_string(b[i]));
+}
+
+
+// A foreign host-only Result in the middle of a device chain (the drop-in must coexist with the reference's own nodes).
+struct HostDouble : Result {
+  ResultPtr in;
+  Vector out;
+  explicit HostDouble(ResultPtr r) : in(std::move(r)), out(in->Output()) {
+    for (double& e : out) e *= 2;
+  }
+  const Vector& Output() override { return out; }
+  bool Constant(const Gradient& g) override { return in->Constant(g); }
+  void PropagateGradient(Vector up, Gradient& g) override {
+    for (double& e : up) e *= 2;
+    in->PropagateGradient(std::move(up), g);
+  }
+};
+
 // ---- fixtures: test/lin_tran_test.go:12-53 ----------------------------------------------------------------
 struct LinTranFixture {
   std::shared_ptr<LinTran> mat1 = New<LinTran>(NewVariable({1, 2, 3, 3, 4, 5, -6, 1, 7, 8, -10, 4}), 3, 4);
@@ -187,34 +253,258 @@ void TestRepeat() {
   ExpectFullCheck(RFuncChecker(New<RepeatTestFunc>(), f.vars, f.v1, f.rv));
 }
 
-// ---- the hot subset of test/arithmetic_test.go:12-77 (same fixtures; vector 2 absent from the RVector) ------------
-struct ArithmeticTestFunc : RFunc {
-  VariablePtr v1, v2, v3, v4;
-  const RVector* rv;
+// ---- test/arithmetic_test.go:12-110 (vector 2 intentionally absent from the RVector) -----------------------------
+struct ArithmeticFixture {
+  VariablePtr v1 = NewVariable({1, 2, -4, 3, -2}), v2 = NewVariable({4, -2, 3, -0.5, 0.3}),
+              v3 = NewVariable({0.99196, 0.48826, 0.51066, 0.66715, 0.44423}),
+              v4 = NewVariable({0.509893, 0.874112, -0.080468, 0.372740, -0.172097});
+  std::vector<VariablePtr> vars{v1, v2, v3, v4};
+  RVector rv{{v1.get(), {0.340162, -0.325063, 0.179612, 0.056463, -0.812274}},
+             {v3.get(), {0.59824, -0.63322, 0.13379, 0.99559, 0.53748}},
+             {v4.get(), {4.2222, 5.2762, -7.5762, 2.3420, -1.8927}}};
+};
+struct ArithmeticTestFunc : RFunc {  // test/arithmetic_test.go:45-69
+  ArithmeticFixture* f;
+  explicit ArithmeticTestFunc(ArithmeticFixture* fx) : f(fx) {}
   ResultPtr Apply(ResultPtr r) override {
-    ResultPtr sq1 = Square(Mul(Scale(Add(r, v1), -0.2), v2));
-    ResultPtr sum1 = AddScaler(Add(Mul(sq1, v3), Scale(v4, -0.5)), 2);
-    return Scale(Sub(SumAll(Mul(sum1, sum1)), SumAll(Sub(sq1, v1))), 0.05);
+    ResultPtr sq1 = Square(Mul(Scale(Add(r, f->v1), -2), f->v2));
+    ResultPtr sum1 = AddScaler(Add(Mul(sq1, f->v3), Scale(f->v4, -0.5)), 2);
+    ResultPtr powed = Div(Pow(Pow(Inverse(sum1), 2), 1 / 3.0), sum1);
+    ResultPtr allSum = SumAll(AddFirst(powed, f->v1));
+    allSum = Sub(allSum, SumAllLogDomain(f->v2));
+    return ScaleFirst(AddLogDomain(f->v1, f->v2), allSum);
   }
-  RResultPtr ApplyR(const RVector&, RResultPtr r) override {
-    RResultPtr r1 = NewRVariable(v1, *rv), r2 = NewRVariable(v2, *rv), r3 = NewRVariable(v3, *rv),
-               r4 = NewRVariable(v4, *rv);
-    RResultPtr sq1 = SquareR(MulR(ScaleR(AddR(r, r1), -0.2), r2));
+  RResultPtr ApplyR(const RVector& v, RResultPtr r) override {
+    RResultPtr r1 = NewRVariable(f->v1, v), r2 = NewRVariable(f->v2, v), r3 = NewRVariable(f->v3, v),
+               r4 = NewRVariable(f->v4, v);
+    RResultPtr sq1 = SquareR(MulR(ScaleR(AddR(r, r1), -2), r2));
     RResultPtr sum1 = AddScalerR(AddR(MulR(sq1, r3), ScaleR(r4, -0.5)), 2);
-    return ScaleR(SubR(SumAllR(MulR(sum1, sum1)), SumAllR(SubR(sq1, r1))), 0.05);
+    RResultPtr powed = DivR(PowR(PowR(InverseR(sum1), 2), 1 / 3.0), sum1);
+    RResultPtr allSum = SumAllR(AddFirstR(powed, r1));
+    allSum = SubR(allSum, SumAllLogDomainR(r2));
+    return ScaleFirstR(AddLogDomainR(r1, r2), allSum);
   }
 };
-void TestArithmetic() {
-  auto f = New<ArithmeticTestFunc>();
-  f->v1 = NewVariable({1, 2, -4, 3, -2});
-  f->v2 = NewVariable({4, -2, 3, -0.5, 0.3});
-  f->v3 = NewVariable({0.99196, 0.48826, 0.51066, 0.66715, 0.44423});
-  f->v4 = NewVariable({0.509893, 0.874112, -0.080468, 0.372740, -0.172097});
-  RVector rv{{f->v1.get(), {0.340162, -0.325063, 0.179612, 0.056463, -0.812274}},
-             {f->v3.get(), {0.59824, -0.63322, 0.13379, 0.99559, 0.53748}},
-             {f->v4.get(), {4.2222, 5.2762, -7.5762, 2.3420, -1.8927}}};
-  f->rv = &rv;
-  ExpectFullCheck(RFuncChecker(f, {f->v1, f->v2, f->v3, f->v4}, f->v4, rv));
+void TestArithmetic() {  // test/arithmetic_test.go:71-79
+  ArithmeticFixture f;
+  ExpectFullCheck(RFuncChecker(New<ArithmeticTestFunc>(&f), f.vars, f.v4, f.rv));
+}
+void TestAddLogDomainOutput() {  // test/arithmetic_test.go:81-97
+  ArithmeticFixture f;
+  Vector expected;
+  for (size_t i = 0; i < f.v1->Vector.size(); i++) expected.push_back(std::log(std::exp(f.v1->Vector[i]) + std::exp(f.v2->Vector[i])));
+  ExpectClose(AddLogDomain(f.v1, f.v2)->Output(), expected, "AddLogDomain", 0, 1e-5);
+}
+void TestSumAllLogDomainOutput() {  // test/arithmetic_test.go:99-110
+  VariablePtr in = NewVariable({3, 3.5, -1, 2});
+  double sum = 0;
+  for (double x : in->Vector) sum += std::exp(x);
+  ExpectClose(SumAllLogDomain(in)->Output(), {std::log(sum)}, "SumAllLogDomain", 0, 1e-8);
+}
+void TestCosOutput() {  // test/math_funcs_test.go:102-111
+  uint64_t s = 1234;
+  for (int i = 0; i < 10; i++) {
+    double arg = Uniform(&s) * 10;
+    ExpectClose(Cos().Apply(NewVariable({arg}))->Output(), {std::cos(arg)}, "Cos", 0, 1e-5);
+  }
+}
+void TestNormOutput() {  // test/math_funcs_test.go:113-120
+  ExpectClose(Norm().Apply(NewVariable({3, 4}))->Output(), {5.0}, "Norm", 0, 1e-5);
+}
+void TestNorm() { MathFixture().Check(New<Norm>()); }  // test/math_funcs_test.go:122-130
+// Division and the squared-error head against their reference compositions (arithmetic.go:425-427; math_funcs.go:191-199)
+struct DivTestFunc : RFunc {
+  ArithmeticFixture* f;
+  explicit DivTestFunc(ArithmeticFixture* fx) : f(fx) {}
+  ResultPtr Apply(ResultPtr r) override { return Div(Mul(r, f->v3), AddScaler(Square(f->v2), 1)); }
+  RResultPtr ApplyR(const RVector& v, RResultPtr r) override {
+    return DivR(MulR(r, NewRVariable(f->v3, v)), AddScalerR(SquareR(NewRVariable(f->v2, v)), 1));
+  }
+};
+struct SquaredErrorTestFunc : RFunc {
+  ArithmeticFixture* f;
+  bool composed;
+  SquaredErrorTestFunc(ArithmeticFixture* fx, bool c) : f(fx), composed(c) {}
+  ResultPtr Apply(ResultPtr r) override {
+    ResultPtr a = Mul(r, f->v3), y = Add(f->v1, f->v4);
+    return composed ? Scale(SquaredNorm().Apply(Sub(a, y)), 0.5) : SquaredError(a, y);
+  }
+  RResultPtr ApplyR(const RVector& v, RResultPtr r) override {
+    RResultPtr a = MulR(r, NewRVariable(f->v3, v)), y = AddR(NewRVariable(f->v1, v), NewRVariable(f->v4, v));
+    return composed ? ScaleR(SquaredNorm().ApplyR(v, SubR(a, y)), 0.5) : SquaredErrorR(a, y);
+  }
+};
+void TestDiv() {
+  ArithmeticFixture f;
+  ExpectFullCheck(RFuncChecker(New<DivTestFunc>(&f), f.vars, f.v4, f.rv));
+}
+void TestSquaredError() {
+  ArithmeticFixture f;
+  ExpectFullCheck(RFuncChecker(New<SquaredErrorTestFunc>(&f, false), f.vars, f.v2, f.rv));
+  f.rv[f.v2.get()] = {0.3, -0.1, 0.7, 0.2, -0.9};
+  Gradient g1 = NewGradient(f.vars), g2 = NewGradient(f.vars);
+  RGradient rg1 = NewRGradient(f.vars), rg2 = NewRGradient(f.vars);
+  RResultPtr fused = SquaredErrorTestFunc(&f, false).ApplyR(f.rv, NewRVariable(f.v2, f.rv));
+  RResultPtr chain = SquaredErrorTestFunc(&f, true).ApplyR(f.rv, NewRVariable(f.v2, f.rv));
+  ExpectClose(fused->Output(), chain->Output(), "cost");
+  ExpectClose(fused->ROutput(), chain->ROutput(), "r-cost");
+  fused->PropagateRGradient({1.5}, {-0.25}, rg1, &g1);
+  chain->PropagateRGradient({1.5}, {-0.25}, rg2, &g2);
+  for (auto& v : f.vars) {
+    ExpectClose(g1[v.get()], g2[v.get()], "squared-error gradient");
+    ExpectClose(rg1[v.get()], rg2[v.get()], "squared-error r-gradient");
+  }
+}
+
+// ---- test/pool_test.go:11-42 --------------------------------------------------------------------------------------
+struct PoolTestFunc : RFunc {
+  ResultPtr Apply(ResultPtr r) override {
+    return Pool(r, [](ResultPtr pooled) { return Pow(Exp().Apply(AddScaler(pooled, 2)), 0.5); });
+  }
+  RResultPtr ApplyR(const RVector& v, RResultPtr r) override {
+    return PoolR(r, [&](RResultPtr pooled) { return PowR(Exp().ApplyR(v, AddScalerR(pooled, 2)), 0.5); });
+  }
+};
+void TestPool() {
+  VariablePtr var = NewVariable({1, -2, 3, -4, 5});
+  RVector rv{{var.get(), {1, -1, 2, -2, 3}}};
+  auto f = New<ComposedRFunc>(ComposedRFunc{New<Sigmoid>(), New<Exp>(), New<PoolTestFunc>()});
+  ExpectFullCheck(RFuncChecker(f, {var}, var, rv));
+}
+// Pool's purpose (pool.go:5-20): a pooled input used k times is back-propagated through ONCE, and on the device the
+// pool variable's gradient never visits the host.
+void TestPoolPropagatesOnce() {
+  Net net = MakeNet({6, 5}, 41);
+  uint64_t s = 43;
+  VariablePtr x = NewVariable(RandomVector(6, &s));
+  auto uses = [](ResultPtr p) { return Add(Mul(p, p), Add(Square(p), Scale(p, 3))); };  // p appears five times
+  ResultPtr pooled = Pool(net.layers.Batch(x, 1), uses), plain = uses(net.layers.Batch(x, 1));
+  ExpectClose(pooled->Output(), plain->Output(), "pooled output");
+  Gradient g1 = NewGradient(net.vars), g2 = NewGradient(net.vars);
+  Vector up = RandomVector(5, &s);
+  int64_t before = b200::Context::Default().LaunchCount();
+  pooled->PropagateGradient(up, g1);
+  int64_t pooledLaunches = b200::Context::Default().LaunchCount() - before;
+  before = b200::Context::Default().LaunchCount();
+  plain->PropagateGradient(up, g2);
+  int64_t plainLaunches = b200::Context::Default().LaunchCount() - before;
+  for (auto& v : net.vars) ExpectClose(g1[v.get()], g2[v.get()], "pooled gradient");
+  if (g1.size() != net.vars.size()) Fatalf("the pool variable was left in the gradient map");
+  if (pooledLaunches >= plainLaunches)
+    Fatalf("pooling did not save work: " + std::to_string(pooledLaunches) + " vs " + std::to_string(plainLaunches));
+}
+// PoolAll / PoolSplit with a constant input, an unused pool variable, a nil Gradient and a foreign host node inside f
+void TestPoolAllEdgeCases() {
+  ArithmeticFixture f;
+  auto body = [&](const std::vector<RResultPtr>& in) { return AddR(MulR(in[0], in[1]), ScaleR(in[0], 2)); };  // in[2] unused
+  auto build = [&] {
+    return PoolAllR({MulR(NewRVariable(f.v1, f.rv), NewRVariable(f.v3, f.rv)), SquareR(NewRVariable(f.v2, f.rv)),
+                     NewRVariable(f.v4, f.rv)},
+                    body);
+  };
+  RResultPtr direct = body({MulR(NewRVariable(f.v1, f.rv), NewRVariable(f.v3, f.rv)), SquareR(NewRVariable(f.v2, f.rv)),
+                            NewRVariable(f.v4, f.rv)});
+  RResultPtr pooled = build();
+  ExpectClose(pooled->Output(), direct->Output(), "PoolAllR output");
+  ExpectClose(pooled->ROutput(), direct->ROutput(), "PoolAllR r-output");
+  Vector up{1, -2, 0.5, 3, -1}, upR{0.1, 0.2, -0.3, 0.4, 0.5};
+  Gradient g1 = NewGradient(f.vars), g2 = NewGradient(f.vars);
+  RGradient rg1 = NewRGradient(f.vars), rg2 = NewRGradient(f.vars), rg3 = NewRGradient({f.v1});
+  pooled->PropagateRGradient(up, upR, rg1, &g1);
+  direct->PropagateRGradient(up, upR, rg2, &g2);
+  for (auto& v : f.vars) {
+    ExpectClose(g1[v.get()], g2[v.get()], "PoolAllR gradient");
+    ExpectClose(rg1[v.get()], rg2[v.get()], "PoolAllR r-gradient");
+  }
+  for (double e : g1[f.v4.get()])
+    if (e != 0) Fatalf("an unused pool input received gradient");
+  build()->PropagateRGradient(up, upR, rg3, nullptr);  // nil Gradient (pool.go:164-166), v2's branch constant
+  if (rg3.size() != 1) Fatalf("pool variables were left in the r-gradient map");
+  ExpectClose(rg3[f.v1.get()], rg2[f.v1.get()], "PoolAllR nil-grad r-gradient");
+  RGradient none;
+  if (!pooled->Constant(none, nullptr) || pooled->Constant(rg3, nullptr) || !pooled->Constant(NewRGradient({f.v4}), nullptr))
+    Fatalf("pooledRResult.Constant is wrong");
+  // a host-only node inside the pooled function adds into the temporary's HOST vector; Session::Take folds it in
+  ResultPtr a = Pool(Scale(f.v1, 0.5), [](ResultPtr p) { return Add(New<HostDouble>(p), Square(p)); });
+  ResultPtr b = Add(Scale(Scale(f.v1, 0.5), 2), Square(Scale(f.v1, 0.5)));
+  Gradient ga = NewGradient(f.vars), gb = NewGradient(f.vars);
+  a->PropagateGradient(up, ga);
+  b->PropagateGradient(up, gb);
+  ExpectClose(a->Output(), b->Output(), "pool with host node: output");
+  ExpectClose(ga[f.v1.get()], gb[f.v1.get()], "pool with host node: gradient");
+  ResultPtr sp = PoolSplit(5, Scale(f.v2, 2), [](const std::vector<ResultPtr>& parts) { return Mul(parts[1], parts[3]); });
+  ExpectClose(sp->Output(), {-4 * -1.0}, "PoolSplit output");
+  Gradient gs = NewGradient(f.vars);
+  sp->PropagateGradient({1}, gs);
+  ExpectClose(gs[f.v2.get()], {0, -2, 0, -8, 0}, "PoolSplit gradient");
+}
+
+// ---- test/fold_test.go:12-65 --------------------------------------------------------------------------------------
+struct FoldTestFunc : RFunc {
+  VariablePtr initState;
+  explicit FoldTestFunc(VariablePtr s) : initState(std::move(s)) {}
+  ResultPtr Apply(ResultPtr in) override {
+    return Fold(initState, Split((int)(in->len() / 2), in), [](ResultPtr state, ResultPtr x) { return Mul(Inverse(state), x); });
+  }
+  RResultPtr ApplyR(const RVector& rv, RResultPtr in) override {
+    return FoldR(NewRVariable(initState, rv), SplitR((int)(in->len() / 2), in),
+                 [](RResultPtr state, RResultPtr x) { return MulR(InverseR(state), x); });
+  }
+};
+void TestFoldOut() {
+  VariablePtr in = NewVariable({1, 2, 2.5, 1.5, 3, 0.5}), init = NewVariable({2, 1});
+  ExpectClose(FoldTestFunc(init).Apply(in)->Output(), {0.6, 2.0 / 3.0}, "Fold output", 0, 1e-5);
+}
+void TestFold() {
+  std::vector<VariablePtr> vars{NewVariable({1, 2, 2.5, 1.5, 3, 0.5}), NewVariable({2, 1})};
+  RVector rv;
+  uint64_t s = 77;
+  for (auto& v : vars) rv[v.get()] = RandomVector(v->Vector.size(), &s);
+  ExpectFullCheck(RFuncChecker(New<FoldTestFunc>(vars[1]), vars, vars[0], rv));
+  // an empty input list returns the state itself (fold.go:57-60)
+  Gradient g = NewGradient(vars);
+  ResultPtr r = Fold(vars[1], {}, [](ResultPtr st, ResultPtr) { return st; });
+  r->PropagateGradient({1, 2}, g);
+  ExpectClose(g[vars[1].get()], {1, 2}, "empty fold");
+  // a fold whose state stops depending on the past (fold.go:70-73): the loop breaks, nothing older is touched
+  ResultPtr cut = Fold(vars[1], Split(3, vars[0]), [](ResultPtr, ResultPtr x) { return Scale(x, 2); });
+  Gradient g2 = NewGradient(vars);
+  cut->PropagateGradient({1, 1}, g2);
+  ExpectClose(g2[vars[0].get()], {0, 0, 0, 0, 2, 2}, "fold cut off from its past");
+  ExpectClose(g2[vars[1].get()], {0, 0}, "fold cut off from its past: initial state");
+  if (g2.size() != 2) Fatalf("fold left a pool variable in the map");
+}
+
+// ---- test/lin_alg_test.go:12-22,56-74 -----------------------------------------------------------------------------
+struct MatMulVecTest : RFunc {
+  LinTranFixture* f;
+  explicit MatMulVecTest(LinTranFixture* fx) : f(fx) {}
+  ResultPtr Apply(ResultPtr in) override { return MatMulVec(f->mat1->Data, 3, 4, in); }
+  RResultPtr ApplyR(const RVector& rv, RResultPtr in) override { return MatMulVecR(NewRVariable(f->mat1->Data, rv), 3, 4, in); }
+};
+void TestMatMulVecOutput() {
+  LinTranFixture f;
+  ExpectClose(MatMulVecTest(&f).Apply(f.vec)->Output(), {19, 20, 36}, "MatMulVec", 0, 1e-5);
+}
+void TestMatMulVecChecks() {
+  LinTranFixture f;
+  ExpectFullCheck(RFuncChecker(New<MatMulVecTest>(&f), f.vars, f.vec, f.rv));
+}
+// MatMulVecs with a COMPUTED matrix (the case LinTran cannot express) and several vectors, against the operator chain
+struct MatMulVecsComputed : RFunc {
+  LinTranFixture* f;
+  explicit MatMulVecsComputed(LinTranFixture* fx) : f(fx) {}
+  ResultPtr Apply(ResultPtr in) override { return MatMulVecs(Square(Scale(f->mat1->Data, 0.5)), 3, 4, in); }
+  RResultPtr ApplyR(const RVector& rv, RResultPtr in) override {
+    return MatMulVecsR(SquareR(ScaleR(NewRVariable(f->mat1->Data, rv), 0.5)), 3, 4, in);
+  }
+};
+void TestMatMulVecsComputedMatrix() {
+  LinTranFixture f;
+  ExpectFullCheck(RFuncChecker(New<MatMulVecsComputed>(&f), f.vars, f.vec2, f.rv));
+  ExpectPanic("invalid matrix data size", [&] { MatMulVecs(f.vec, 3, 4, f.vec); });
+  ExpectPanic("invalid vecs size", [&] { MatMulVecs(f.mat1->Data, 3, 4, f.mat2->Data); });
+  ExpectPanic("count does not divide input length", [&] { Split(3, f.vec); });
 }
 
 // ---- test/variable_test.go:12-35 ---------------------------------------------------------------------------------
@@ -235,55 +525,6 @@ void TestVariableSerialize() {
 }
 
 // ---- batcher.go:34-111: the batched form of a Func equals the per-sample form (seqfunc TestMapBatcherOutput's idea) --
-struct Net {
-  std::vector<VariablePtr> vars;
-  ComposedRBatcher layers;
-  std::shared_ptr<ComposedRFunc> func = New<ComposedRFunc>();
-  RVector rv;
-};
-double Uniform(uint64_t* s) {
-  *s += 0x9E3779B97F4A7C15ull;
-  uint64_t z = *s;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (double)(z >> 11) * (1.0 / 9007199254740992.0) * 2 - 1;
-}
-Vector RandomVector(size_t n, uint64_t* s, double scale = 1) {
-  Vector v(n);
-  for (double& e : v) e = scale * Uniform(s);
-  return v;
-}
-Net MakeNet(const std::vector<int>& sizes, uint64_t seed, bool biasesInRV = true) {
-  Net net;
-  uint64_t s = seed;
-  for (size_t l = 0; l + 1 < sizes.size(); l++) {
-    int in = sizes[l], out = sizes[l + 1];
-    VariablePtr w = NewVariable(RandomVector((size_t)in * out, &s, 1 / std::sqrt((double)in)));
-    VariablePtr b = NewVariable(RandomVector((size_t)out, &s));
-    net.vars.push_back(w);
-    net.vars.push_back(b);
-    auto lt = New<LinTran>(w, out, in);
-    auto la = New<LinAdd>(b);
-    auto sg = New<Sigmoid>();
-    net.layers.push_back(lt);
-    net.layers.push_back(la);
-    net.layers.push_back(sg);
-    net.func->push_back(lt);
-    net.func->push_back(la);
-    net.func->push_back(sg);
-    net.rv[w.get()] = RandomVector(w->Vector.size(), &s);
-    if (biasesInRV) net.rv[b.get()] = RandomVector(b->Vector.size(), &s);
-  }
-  return net;
-}
-void ExpectClose(const Vector& a, const Vector& b, const std::string& what, double rtol = 1e-10, double atol = 1e-12) {
-  if (a.size() != b.size()) Fatalf(what + ": lengths differ");
-  for (size_t i = 0; i < a.size(); i++)
-    if (!(std::fabs(a[i] - b[i]) <= atol + rtol * std::fabs(b[i])))
-      Fatalf(what + ": entry " + std::to_string(i) + ": " + std::to_string(a[i]) + " vs " + std::to_string(b[i]));
-}
-
 void TestRFuncBatcherMatchesBatch() {
   Net net = MakeNet({5, 7, 3}, 11);
   const int n = 4;
@@ -410,20 +651,6 @@ void TestPanics() {
   });
 }
 
-// A foreign host-only Result in the middle of a device chain (the drop-in must coexist with the reference's own nodes).
-struct HostDouble : Result {
-  ResultPtr in;
-  Vector out;
-  explicit HostDouble(ResultPtr r) : in(std::move(r)), out(in->Output()) {
-    for (double& e : out) e *= 2;
-  }
-  const Vector& Output() override { return out; }
-  bool Constant(const Gradient& g) override { return in->Constant(g); }
-  void PropagateGradient(Vector up, Gradient& g) override {
-    for (double& e : up) e *= 2;
-    in->PropagateGradient(std::move(up), g);
-  }
-};
 void TestForeignHostResultInChain() {
   LinTranFixture f;
   Gradient g1 = NewGradient(f.vars), g2 = NewGradient(f.vars);
@@ -563,6 +790,9 @@ const NamedTest kTests[] = {
     T(TestLinTranOutput), T(TestLinTran), T(TestLinTranBatchOutput), T(TestLinTranBatch), T(TestLinAdd), T(TestExp),
     T(TestLog), T(TestSquaredNorm), T(TestSigmoid), T(TestLogSigmoid), T(TestSoftmax), T(TestSoftmax3), T(TestSin),
     T(TestTanh), T(TestConcat), T(TestSlice), T(TestWrappedSlice), T(TestRepeat), T(TestArithmetic),
+    T(TestAddLogDomainOutput), T(TestSumAllLogDomainOutput), T(TestCosOutput), T(TestNormOutput), T(TestNorm),
+    T(TestDiv), T(TestSquaredError), T(TestPool), T(TestPoolPropagatesOnce), T(TestPoolAllEdgeCases), T(TestFoldOut),
+    T(TestFold), T(TestMatMulVecOutput), T(TestMatMulVecChecks), T(TestMatMulVecsComputedMatrix),
     T(TestVariableSerialize), T(TestRFuncBatcherMatchesBatch), T(TestFusedAndPlanMatchOperators),
     T(TestNilGradientAndPruning), T(TestPanics), T(TestForeignHostResultInChain), T(TestMapBatcherOutput),
     T(TestMapRBatcher), T(TestDeviceGradient),
@@ -706,6 +936,32 @@ std::vector<Vector> RunArith(const std::vector<std::string>& a, const std::vecto
   return out;
 }
 
+// next <rows> <cols> <n>: a composite over SURVEY 8(f) rank 3 -- MatMulVecs with a computed matrix, Pool, Div, batched
+// Softmax, Fold, Inverse, the squared-error head, Norm, the log-domain sums, Pow, AddFirst, ScaleFirst, Cos.
+// in: M (rows*cols) V (cols*n) B (rows) RM RV RB U UR (2*rows + 1)   out: out rout gM gV gB rgM rgV rgB
+std::vector<Vector> RunNext(const std::vector<std::string>& a, const std::vector<Vector>& in) {
+  int rows = std::stoi(a.at(0)), cols = std::stoi(a.at(1)), n = std::stoi(a.at(2));
+  VariablePtr M = NewVariable(in.at(0)), V = NewVariable(in.at(1)), B = NewVariable(in.at(2));
+  RVector rv{{M.get(), in.at(3)}, {V.get(), in.at(4)}, {B.get(), in.at(5)}};
+  RResultPtr rM = NewRVariable(M, rv), rV = NewRVariable(V, rv), rB = NewRVariable(B, rv);
+  RResultPtr y = MatMulVecsR(AddScalerR(SquareR(rM), 1), rows, cols, rV);
+  RResultPtr p = PoolR(y, [](RResultPtr q) { return DivR(q, AddScalerR(SquareR(q), 1)); });
+  RResultPtr sm = Softmax().BatchR(rv, p, n);
+  RResultPtr folded = FoldR(rB, SplitR(n, sm), [](RResultPtr state, RResultPtr x) {
+    return MulR(InverseR(AddScalerR(SquareR(state), 1)), AddR(x, state));
+  });
+  RResultPtr cost = SquaredErrorR(folded, rB), nrm = Norm().ApplyR(rv, p), lse = SumAllLogDomainR(folded);
+  RResultPtr pw = PowR(AddScalerR(SquareR(folded), 1), 0.3);
+  RResultPtr o = ConcatR({ScaleFirstR(AddFirstR(pw, nrm), lse), cost, Cos().ApplyR(rv, AddLogDomainR(folded, rB))});
+  Gradient g = NewGradient({M, V, B});
+  RGradient rg = NewRGradient({M, V, B});
+  std::vector<Vector> out{o->Output(), o->ROutput()};
+  o->PropagateRGradient(in.at(6), in.at(7), rg, &g);
+  if (g.size() != 3 || rg.size() != 3) throw std::runtime_error("temporary variables were left in the gradient maps");
+  out.insert(out.end(), {g[M.get()], g[V.get()], g[B.get()], rg[M.get()], rg[V.get()], rg[B.get()]});
+  return out;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -720,6 +976,7 @@ int main(int argc, char** argv) {
       else if (args[1] == "lintran") out = RunLinTran(rest, in);
       else if (args[1] == "lstm") out = RunLSTM(rest, in);
       else if (args[1] == "arith") out = RunArith(rest, in);
+      else if (args[1] == "next") out = RunNext(rest, in);
       else throw std::runtime_error("unknown case " + args[1]);
       WriteVectors(args[3], out);
       std::printf("run ok: %lld kernel launches\n", (long long)b200::Context::Default().LaunchCount());

@@ -132,6 +132,34 @@ def check_arith(ref, exe, tmp, n, m, k, seed=0):
         close(a, w_, f"arith {what}")
 
 
+def check_next(ref, exe, tmp, rows, cols, n, seed=0):
+    """SURVEY 8(f) rank 3 through the C++ host layer: host_tests.cpp RunNext, node for node on the oracle."""
+    M = ref.Variable(ref.splitmix_uniform(601 + seed, rows * cols))
+    V = ref.Variable(ref.splitmix_uniform(602 + seed, cols * n))
+    B = ref.Variable(ref.splitmix_uniform(603 + seed, rows))
+    rv = {M: ref.splitmix_uniform(604 + seed, rows * cols), V: ref.splitmix_uniform(605 + seed, cols * n),
+          B: ref.splitmix_uniform(606 + seed, rows)}
+    m = 2 * rows + 1
+    up, upr = ref.splitmix_uniform(607 + seed, m), ref.splitmix_uniform(608 + seed, m)
+    got = run_case(exe, tmp, "next", [M.vector, V.vector, B.vector, rv[M], rv[V], rv[B], up, upr], [rows, cols, n])
+    rM, rV, rB = ref.RVariable(M, rv), ref.RVariable(V, rv), ref.RVariable(B, rv)
+    y = ref.mat_mul_vecs_r(ref.add_scaler_r(ref.square_r(rM), 1), rows, cols, rV)
+    p = ref.pool_r(y, lambda q: ref.div_r(q, ref.add_scaler_r(ref.square_r(q), 1)))
+    sm = ref.Softmax().batch_r(rv, p, n)
+    folded = ref.fold_r(rB, ref.split_r(n, sm), lambda state, x: ref.mul_r(
+        ref.inverse_r(ref.add_scaler_r(ref.square_r(state), 1)), ref.add_r(x, state)))
+    cost, nrm, lse = ref.squared_error_r(folded, rB), ref.Norm().apply_r(rv, p), ref.sum_all_log_domain_r(folded)
+    pw = ref.pow_r(ref.add_scaler_r(ref.square_r(folded), 1), 0.3)
+    o = ref.concat_r(ref.scale_first_r(ref.add_first_r(pw, nrm), lse), cost,
+                     ref.Cos().apply_r(rv, ref.add_log_domain_r(folded, rB)))
+    g, rg = ref.new_gradient([M, V, B]), ref.new_rgradient([M, V, B])
+    out, rout = o.output().copy(), o.routput().copy()
+    o.propagate_rgradient(up.copy(), upr.copy(), rg, g)
+    names = ["out", "rout", "gM", "gV", "gB", "rgM", "rgV", "rgB"]
+    for a, w_, what in zip(got, [out, rout, g[M], g[V], g[B], rg[M], rg[V], rg[B]], names):
+        close(a, w_, f"next {rows}x{cols} n={n} {what}")
+
+
 def check_lstm(ref, exe, tmp, I, H, O, T, B, scale=0.5):
     from tests.test_gpu_lstm import _oracle
     net = ref.LSTMNet(I, H, O, weight_scale=scale)

@@ -20,7 +20,7 @@ def exe(tmp_path_factory):
 def test_reference_tests_pass_on_the_cpp_host_layer(exe):
     r = subprocess.run([exe, "selftest"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "0 failed" in r.stdout and len(re.findall(r"^PASS ", r.stdout, re.M)) >= 25
+    assert "0 failed" in r.stdout and len(re.findall(r"^PASS ", r.stdout, re.M)) >= 43
 
 
 @pytest.mark.parametrize("mode", ["ops", "fused", "plan", "nonr", "nilgrad"])
@@ -33,6 +33,13 @@ def test_cpp_lintran_and_arithmetic_match_numpy_oracle(exe, tmp_path):
     cpp_host.check_lintran(ref, exe, str(tmp_path), 6, 11, 10)
     cpp_host.check_lintran(ref, exe, str(tmp_path), 1, 1, 1, seed=5)
     cpp_host.check_arith(ref, exe, str(tmp_path), 4, 6, 3)
+
+
+def test_cpp_pool_fold_matmul_and_cost_heads_match_numpy_oracle(exe, tmp_path):
+    """SURVEY 8(f) rank 3 through the C++ host layer (MatMulVecs, Pool, Fold, Div, Pow, Inverse, Norm, Softmax, the
+    log-domain sums, squared error): the temp-variable protocol and the gating, checked where no GPU exists."""
+    cpp_host.check_next(ref, exe, str(tmp_path), 5, 7, 4)
+    cpp_host.check_next(ref, exe, str(tmp_path), 1, 1, 1, seed=9)
 
 
 def test_cpp_host_fails_loudly_without_the_gpu_library(tmp_path):

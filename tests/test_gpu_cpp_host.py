@@ -24,7 +24,7 @@ def exe(tmp_path_factory):
 def test_reference_tests_pass_on_the_gpu_through_cpp(exe):
     r = subprocess.run([exe, "selftest"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "0 failed" in r.stdout and len(re.findall(r"^PASS ", r.stdout, re.M)) >= 25
+    assert "0 failed" in r.stdout and len(re.findall(r"^PASS ", r.stdout, re.M)) >= 43
     launches = int(re.search(r"(\d+) kernel launches", r.stdout).group(1))
     assert launches > 1000  # the work ran as CUDA kernels of this library
 
@@ -44,6 +44,14 @@ def test_cpp_lintran_c1_shape_matches_oracle(exe, tmp_path):
 
 def test_cpp_arithmetic_and_slices_match_oracle(exe, tmp_path):
     cpp_host.check_arith(ref, exe, str(tmp_path), 33, 70, 40)
+
+
+def test_cpp_pool_fold_matmul_and_cost_heads_match_oracle(exe, tmp_path):
+    """SURVEY 8(f) rank 3 through the C++ host layer on the device: MatMulVecs with a computed matrix (the six LinTran
+    kernels), Pool / Fold with the temporaries in HBM, Softmax rows, Norm, squared error, the log-domain sums."""
+    cpp_host.check_next(ref, exe, str(tmp_path), 24, 40, 16)
+    cpp_host.check_next(ref, exe, str(tmp_path), 10, 64, 130, seed=4)
+    cpp_host.check_next(ref, exe, str(tmp_path), 3, 5, 2, seed=7)   # odd pitches: the generic contraction kernel
 
 
 def test_cpp_lstm_plan_matches_oracle(exe, tmp_path):
