@@ -32,6 +32,11 @@ PROTOTYPES = {
     "af_set_option": (INT, [P, C.c_char_p, INT]),
     "af_trace_begin": (INT, [P, INT]),
     "af_trace_end": (INT, [P, INT, C.POINTER(INT), C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(INT)]),
+    "af_graph_begin": (INT, [P]),
+    "af_graph_end": (INT, [P, C.POINTER(P)]),
+    "af_graph_launch": (INT, [P]),
+    "af_graph_launches": (I64, [P]),
+    "af_graph_destroy": (INT, [P]),
     "af_malloc": (INT, [P, I64, C.POINTER(D)]),
     "af_free": (INT, [P, D]),
     "af_upload": (INT, [P, D, H, I64]),

@@ -95,6 +95,12 @@ class Context:
     def set_gemm_path(self, mode: int) -> None:
         check(self.lib.af_set_gemm_path(self.h, mode))
 
+    def record(self) -> "Graph":
+        """`with ctx.record() as g:` records every ABI-level launch issued on this context inside the block into a
+        CUDA graph instead of running it; `g.launch()` replays the sequence (same buffers, same sizes) as one
+        submission.  For launch-bound chains: the reference's own benchmarks run n = 1 and n = 10."""
+        return Graph(self)
+
     def trim(self) -> None:
         self.sync()
         for fl in self._pool.values():
@@ -107,6 +113,47 @@ class Context:
             self.trim()
             self._closed = True
             self.lib.af_ctx_destroy(self.h)
+
+
+class Graph:
+    """A recorded launch sequence (af_graph_begin / af_graph_end / af_graph_launch)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx, self.h = ctx, None
+
+    def __enter__(self):
+        check(self.ctx.lib.af_graph_begin(self.ctx.h))
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is not None:  # abandon the recording, let the exception through
+            self.ctx.lib.af_graph_end(self.ctx.h, None)
+            return False
+        h = C.c_void_p()
+        check(self.ctx.lib.af_graph_end(self.ctx.h, C.byref(h)))
+        self.h = h
+        return False
+
+    @property
+    def launches(self) -> int:
+        return int(self.ctx.lib.af_graph_launches(self.h)) if self.h else 0
+
+    def launch(self) -> None:
+        if self.h is None:
+            raise AutofuncError(_lib.AF_EINVAL, "the graph was not recorded")
+        check(self.ctx.lib.af_graph_launch(self.h))
+
+    def close(self) -> None:
+        if self.h is not None:
+            self.ctx.lib.af_graph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if not self.ctx._closed:
+                self.close()
+        except Exception:
+            pass
 
 
 class DeviceVec:

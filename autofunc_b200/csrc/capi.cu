@@ -45,6 +45,9 @@ using namespace af;
   af::DeviceGuard _guard((ctx)->device)
 #define AF_NEED(p) \
   if (!(p)) return af::fail(AF_EINVAL, "null pointer argument: " #p)
+// entry points that synchronise, allocate or manage graphs of their own cannot be part of a recorded sequence
+#define AF_NOT_RECORDING(ctx, what) \
+  if ((ctx)->recording) return af::fail(AF_EINVAL, what ": not allowed between af_graph_begin and af_graph_end")
 
 static int check_dims(int64_t rows, int64_t cols, int64_t n) {
   if (rows < 0 || cols < 0 || n < 0) return fail(AF_ESHAPE, "negative dimension");
@@ -115,7 +118,78 @@ int af_ctx_destroy(af_ctx* ctx) {
 
 int af_sync(af_ctx* ctx) {
   AF_CHECK_CTX(ctx);
+  AF_NOT_RECORDING(ctx, "af_sync");
   AF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return AF_OK;
+}
+
+// ---- recorded launch sequences (CUDA graphs) ---------------------------------------------------------
+struct af_graph {
+  af_ctx* ctx = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+};
+
+int af_graph_begin(af_ctx* ctx) {
+  AF_CHECK_CTX(ctx);
+  if (ctx->recording) return fail(AF_EINVAL, "af_graph_begin: already recording");
+  if (ctx->tracing) return fail(AF_EINVAL, "af_graph_begin: a launch trace is active");
+  if (ctx->stream == nullptr || ctx->stream == cudaStreamLegacy)
+    return fail(AF_ENOTSUP, "af_graph_begin: the legacy default stream cannot be captured");
+  AF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+  ctx->recording = true;
+  ctx->record_start = ctx->launches;
+  return AF_OK;
+}
+
+int af_graph_end(af_ctx* ctx, af_graph** out) {
+  AF_CHECK_CTX(ctx);
+  if (!ctx->recording) return fail(AF_EINVAL, "af_graph_end: not recording");
+  ctx->recording = false;
+  const int64_t launches = ctx->launches - ctx->record_start;
+  ctx->launches = ctx->record_start;  // nothing ran
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+  if (ce != cudaSuccess) {
+    if (graph) cudaGraphDestroy(graph);
+    return cuda_fail(ce, "cudaStreamEndCapture");
+  }
+  if (!out) {  // the caller abandons the recording
+    if (graph) cudaGraphDestroy(graph);
+    return AF_OK;
+  }
+  af_graph* g = new af_graph();
+  g->ctx = ctx;
+  g->launches = launches;
+  const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    delete g;
+    return cuda_fail(ie, "cudaGraphInstantiate");
+  }
+  *out = g;
+  return AF_OK;
+}
+
+int af_graph_launch(af_graph* g) {
+  if (!g) return fail(AF_EINVAL, "null graph");
+  af_ctx* ctx = g->ctx;
+  DeviceGuard guard(ctx->device);
+  AF_NOT_RECORDING(ctx, "af_graph_launch");
+  if (ctx->tracing) return fail(AF_EINVAL, "af_graph_launch: a launch trace is active (replays carry no per-launch events)");
+  AF_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+  ctx->launches += g->launches;
+  return AF_OK;
+}
+
+int64_t af_graph_launches(af_graph* g) { return g ? g->launches : 0; }
+
+int af_graph_destroy(af_graph* g) {
+  if (!g) return AF_OK;
+  DeviceGuard guard(g->ctx->device);
+  cudaStreamSynchronize(g->ctx->stream);
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  delete g;
   return AF_OK;
 }
 
@@ -125,6 +199,7 @@ int64_t af_launch_count(af_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int af_trace_begin(af_ctx* ctx, int capacity) {
   AF_CHECK_CTX(ctx);
+  AF_NOT_RECORDING(ctx, "af_trace_begin");
   if (capacity < 1) return fail(AF_EINVAL, "trace capacity must be positive");
   while ((int)ctx->trace_events.size() < capacity + 1) {
     cudaEvent_t ev;
@@ -193,6 +268,7 @@ int af_malloc(af_ctx* ctx, int64_t n, double** out) {
   AF_CHECK_CTX(ctx); AF_NEED(out);
   if (n < 0) return fail(AF_ESHAPE, "negative allocation size");
   *out = nullptr;
+  AF_NOT_RECORDING(ctx, "af_malloc");
   AF_CUDA(cudaMalloc(out, (size_t)(n > 0 ? n : 1) * sizeof(double)));
   return AF_OK;
 }
@@ -200,6 +276,7 @@ int af_malloc(af_ctx* ctx, int64_t n, double** out) {
 int af_free(af_ctx* ctx, double* p) {
   AF_CHECK_CTX(ctx);
   if (!p) return AF_OK;
+  AF_NOT_RECORDING(ctx, "af_free");
   AF_CUDA(cudaStreamSynchronize(ctx->stream));
   AF_CUDA(cudaFree(p));
   return AF_OK;
@@ -209,6 +286,7 @@ int af_upload(af_ctx* ctx, double* dst, const double* src, int64_t n) {
   AF_CHECK_CTX(ctx);
   if (n <= 0) return AF_OK;
   AF_NEED(dst); AF_NEED(src);
+  AF_NOT_RECORDING(ctx, "af_upload");
   AF_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   AF_CUDA(cudaStreamSynchronize(ctx->stream));
   return AF_OK;
@@ -218,6 +296,7 @@ int af_download(af_ctx* ctx, double* dst, const double* src, int64_t n) {
   AF_CHECK_CTX(ctx);
   if (n <= 0) return AF_OK;
   AF_NEED(dst); AF_NEED(src);
+  AF_NOT_RECORDING(ctx, "af_download");
   AF_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   AF_CUDA(cudaStreamSynchronize(ctx->stream));
   return AF_OK;
@@ -427,6 +506,7 @@ extern "C" {
 
 int af_mlp_create(af_ctx* ctx, const int64_t* sizes, int n_layers, int64_t batch, af_mlp** out) {
   AF_CHECK_CTX(ctx); AF_NEED(sizes); AF_NEED(out);
+  AF_NOT_RECORDING(ctx, "af_mlp_create");
   if (n_layers < 1 || batch < 1) return fail(AF_ESHAPE, "need at least one layer and one sample");
   for (int i = 0; i <= n_layers; ++i)
     if (sizes[i] < 1) return fail(AF_ESHAPE, "layer widths must be positive");
@@ -627,6 +707,7 @@ static int mlp_fresh_step(af_mlp* m, int with_r, const double* hU, const double*
 int af_mlp_step_fresh(af_mlp* m, int with_r) {
   if (!m) return fail(AF_EINVAL, "null mlp");
   DeviceGuard guard(m->ctx->device);
+  AF_NOT_RECORDING(m->ctx, "af_mlp_step_fresh (plans replay graphs of their own)");
   return mlp_fresh_step(m, with_r, nullptr, nullptr);
 }
 
@@ -634,6 +715,7 @@ int af_mlp_step(af_mlp* m, int with_r, int backprop) {
   if (!m) return fail(AF_EINVAL, "null mlp");
   af_ctx* ctx = m->ctx;
   DeviceGuard guard(ctx->device);
+  AF_NOT_RECORDING(ctx, "af_mlp_step (plans replay graphs of their own)");
   // a handful of samples: the whole step is one persistent kernel (small_mlp.cu), no graph needed
   if (mlp_small_ok(m)) {
     const int rc = mlp_small_step(m, with_r, backprop, false, false);
@@ -781,6 +863,7 @@ int af_mlp_submit_compute_host(af_mlp* m, int with_r, const double* hX, const do
   AF_NEED(hX);
   af_ctx* ctx = m->ctx;
   DeviceGuard guard(ctx->device);
+  AF_NOT_RECORDING(ctx, "af_mlp_submit_compute_host");
   AF_TRY(mlp_pipeline_init(m));
   while (m->submitted - m->waited >= 2) AF_TRY(af_mlp_wait(m));  // at most two steps in flight
   const int k = (int)(m->submitted & 1);

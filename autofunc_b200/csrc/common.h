@@ -26,6 +26,9 @@ struct af_ctx {
   unsigned* barrier_word = nullptr;  // grid-barrier counter of the persistent small-batch kernel
   unsigned barrier_base = 0;         // its value once every launch queued so far has finished
   int64_t launches = 0;
+  // af_graph_begin / af_graph_end: launches on `stream` are being recorded into a CUDA graph, not executed
+  bool recording = false;
+  int64_t record_start = 0;
   // driver entry point, resolved at run time so the library loads on hosts without libcuda
   void* encode_tiled = nullptr;
   double* scratch = nullptr;  // small device scratch (reductions)

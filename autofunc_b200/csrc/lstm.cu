@@ -187,6 +187,7 @@ int af_copy_2d(af_ctx* ctx, double* d_dst, int64_t ld_dst, const double* d_src, 
 int af_lstm_create(af_ctx* ctx, int64_t I, int64_t H, int64_t O, int64_t T, int64_t B, af_lstm** out) {
   if (!ctx || !out) return fail(AF_EINVAL, "null argument");
   if (I < 1 || H < 1 || O < 1 || T < 1 || B < 1) return fail(AF_ESHAPE, "LSTM dimensions must be positive");
+  if (ctx->recording) return fail(AF_EINVAL, "af_lstm_create: not allowed between af_graph_begin and af_graph_end");
   DeviceGuard guard(ctx->device);
   af_lstm* m = new af_lstm();
   m->ctx = ctx; m->I = I; m->H = H; m->O = O; m->T = T; m->B = B; m->C = H + I;
@@ -351,12 +352,14 @@ extern "C" {
 
 int af_lstm_forward(af_lstm* m, int with_r) {
   if (!m) return fail(AF_EINVAL, "null lstm");
+  if (m->ctx->recording) return fail(AF_EINVAL, "af_lstm_forward: plans replay graphs of their own and cannot be recorded");
   DeviceGuard guard(m->ctx->device);
   return lstm_graphed(m, m->graphs[with_r ? 1 : 0][0], [&]() { return lstm_forward_launches(m, with_r); });
 }
 
 int af_lstm_backward(af_lstm* m, int with_r) {
   if (!m) return fail(AF_EINVAL, "null lstm");
+  if (m->ctx->recording) return fail(AF_EINVAL, "af_lstm_backward: plans replay graphs of their own and cannot be recorded");
   DeviceGuard guard(m->ctx->device);
   return lstm_graphed(m, m->graphs[with_r ? 1 : 0][1], [&]() { return lstm_backward_launches(m, with_r); });
 }

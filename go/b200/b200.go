@@ -423,3 +423,19 @@ func (m *MLP) StepR(vars []*autofunc.Variable, input, outGrad, outRGrad linalg.V
 	}
 	return
 }
+
+// Graph is a recorded launch sequence (af_graph_*): every C.af_* launch issued between Record and End is captured
+// into a CUDA graph instead of running; Launch replays the sequence -- same buffers, same sizes -- as one
+// submission.  For launch-bound chains: the reference's own benchmarks run n = 1 (bench/mlp.go:36) and n = 10
+// (bench/lintran.go:13-17).  Run the sequence once eagerly first.
+type Graph struct{ h *C.af_graph }
+
+func Record() *Graph {
+	check(C.af_graph_begin(context()))
+	return &Graph{}
+}
+
+func (g *Graph) End()          { check(C.af_graph_end(context(), &g.h)) }
+func (g *Graph) Launch()       { check(C.af_graph_launch(g.h)) }
+func (g *Graph) Launches() int { return int(C.af_graph_launches(g.h)) }
+func (g *Graph) Close()        { C.af_graph_destroy(g.h); g.h = nil }

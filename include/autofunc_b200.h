@@ -229,6 +229,24 @@ int af_sqerr_fwd_r(af_ctx*, const double* d_A, const double* d_RA, const double*
 int af_sqerr_bwd_r(af_ctx*, const double* d_A, const double* d_RA, const double* d_Y, const double* d_RY,
                    const double* d_u, const double* d_uR, double sign, double* d_G, double* d_GR, int64_t len);
 
+/* ---- recorded launch sequences (CUDA graphs) --------------------------------------------------
+ * The operator-level calls above are one kernel launch each; with a handful of samples (the
+ * reference's own benchmarks run n = 1 and n = 10, bench/mlp.go:36, bench/lintran.go:13-17) a chain
+ * of them is bound by launch gaps, not by HBM.  Between af_graph_begin and af_graph_end every
+ * launch issued on the context is RECORDED instead of executed; af_graph_launch replays the whole
+ * sequence -- same buffers, same sizes -- as one submission.  Run the sequence once eagerly first
+ * (first calls size internal scratch and set kernel attributes).  Calls that synchronise, allocate
+ * or manage graphs of their own (af_sync, af_malloc, af_free, af_upload, af_download, af_mlp_*
+ * steps, af_lstm_*) fail with AF_EINVAL while recording; af_graph_end must still be called
+ * (out == NULL abandons the recording).  af_launch_count advances by the recorded number of
+ * launches on every replay.                                                                     */
+typedef struct af_graph af_graph;
+int af_graph_begin(af_ctx*);
+int af_graph_end(af_ctx*, af_graph** out);
+int af_graph_launch(af_graph*);
+int64_t af_graph_launches(af_graph*);
+int af_graph_destroy(af_graph*);
+
 /* ---- fused dense layer: LinTran -> LinAdd -> Sigmoid in one kernel per direction ---------- */
 /* Forward with R (G1+G2+E1+E2):  S = sigmoid(X W^T + b) ; RS = S(1-S)(X RW^T + RX W^T + Rb).
  * activation: 0 = none (S = pre-activation), 1 = sigmoid.  d_b/d_Rb/d_RW/d_RX/d_RS may be NULL

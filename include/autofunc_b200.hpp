@@ -182,6 +182,30 @@ class DevVec {
   Dev owner_;
 };
 
+// A recorded launch sequence (af_graph_*): ABI-level calls issued between construction and End() are captured into a
+// CUDA graph; Launch() replays them -- same buffers, same sizes -- as one submission.  Host-layer nodes allocate their
+// outputs per call, so record explicit-buffer (af_*) sequences, after one eager warm-up run of the same sequence.
+class Graph {
+ public:
+  Graph() { check(af_graph_begin(ctx())); }
+  Graph(const Graph&) = delete;
+  Graph& operator=(const Graph&) = delete;
+  ~Graph() {
+    if (!ended_) af_graph_end(ctx(), nullptr);
+    af_graph_destroy(g_);
+  }
+  void End() {
+    ended_ = true;
+    check(af_graph_end(ctx(), &g_));
+  }
+  void Launch() { check(af_graph_launch(g_)); }
+  int64_t Launches() const { return af_graph_launches(g_); }
+
+ private:
+  af_graph* g_ = nullptr;
+  bool ended_ = false;
+};
+
 inline const double* ptr(const Dev& v) { return v ? v->p : nullptr; }  // NULL R operand == identically zero
 inline double* mptr(const Dev& v) { return v ? v->p : nullptr; }
 inline Dev ZerosIfNull(const Dev& v, int64_t n) { return v ? v : DevVec::Zeros(n); }

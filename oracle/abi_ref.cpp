@@ -8,7 +8,8 @@
 // reference file:line it restates; parity status as in oracle/autofunc_ref.py (pinned on the reference's KATs and
 // FullCheck at 1e-5; below that defined by the oracle).
 //
-// Covered: every entry point the host layer calls except the LSTM plan (af_lstm_* return AF_ENOTSUP).
+// Covered: every entry point the host layer calls except the LSTM plan and recorded graphs (af_lstm_*, af_graph_*
+// return AF_ENOTSUP).
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -571,6 +572,13 @@ double* af_mlp_output_ptr(af_mlp* m) { return m->act.back().data(); }
 double* af_mlp_routput_ptr(af_mlp* m) { return m->ract.back().data(); }
 double* af_mlp_grad_ptr(af_mlp* m, int i) { return m->grad[i].data(); }
 double* af_mlp_rgrad_ptr(af_mlp* m, int i) { return m->rgrad[i].data(); }
+
+// ---- recorded launch sequences: a CUDA-graph facility of the product, nothing to restate on a CPU -----------------
+int af_graph_begin(af_ctx*) { return fail(AF_ENOTSUP, "the CPU restatement of the ABI records no graphs"); }
+int af_graph_end(af_ctx*, af_graph**) { return fail(AF_ENOTSUP, "no graphs"); }
+int af_graph_launch(af_graph*) { return fail(AF_ENOTSUP, "no graphs"); }
+int64_t af_graph_launches(af_graph*) { return 0; }
+int af_graph_destroy(af_graph*) { return AF_OK; }
 
 // ---- LSTM plan: not restated here (oracle/autofunc_ref.py LSTMNet is the checker for it) ---------------------------
 int af_lstm_create(af_ctx*, int64_t, int64_t, int64_t, int64_t, int64_t, af_lstm**) {

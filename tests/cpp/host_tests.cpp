@@ -13,6 +13,7 @@
 #include <functional>
 #include <iostream>
 #include <iterator>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -781,6 +782,47 @@ void TestDeviceGradient() {
   for (size_t i = 0; i < fresh.size(); i++) ExpectClose(dg.Host(net.vars[i]), g2[fresh[i].get()], "non-R device gradient");
 }
 
+// af_graph_*: an explicit-buffer ABI sequence recorded once and replayed (bench/lintran.go's step at n = 10 is bound by
+// launch gaps).  The CPU restatement of the ABI records nothing (AF_ENOTSUP): the test is then vacuous.
+void TestRecordedGraph() {
+  using b200::Dev;
+  using b200::DevVec;
+  const int rows = 6, cols = 8, n = 3;
+  uint64_t s = 3;
+  Vector w = RandomVector(rows * cols, &s), x = RandomVector(cols * n, &s), u = RandomVector(rows * n, &s);
+  Dev W = DevVec::Upload(w), X = DevVec::Upload(x), U = DevVec::Upload(u);
+  Dev Y = DevVec::Zeros(rows * n), gW = DevVec::Zeros(rows * cols), D = DevVec::Zeros(cols * n);
+  auto step = [&] {
+    b200::check(af_lintran_fwd(b200::ctx(), W->p, X->p, Y->p, rows, cols, n));
+    b200::check(af_lintran_wgrad(b200::ctx(), U->p, X->p, gW->p, rows, cols, n));
+    b200::check(af_lintran_igrad(b200::ctx(), U->p, W->p, D->p, rows, cols, n));
+  };
+  step();  // eager warm-up; gW holds one step
+  Vector y1 = Y->Download(), g1 = gW->Download(), d1 = D->Download();
+  std::unique_ptr<b200::Graph> g;
+  try {
+    g.reset(new b200::Graph());
+  } catch (const Panic& p) {
+    if (p.code == AF_ENOTSUP) return;
+    throw;
+  }
+  int64_t before = b200::Context::Default().LaunchCount();
+  step();
+  g->End();
+  if (b200::Context::Default().LaunchCount() != before) Fatalf("recording counted launches");
+  ExpectClose(gW->Download(), g1, "recording must not execute");
+  g->Launch();
+  g->Launch();
+  if (b200::Context::Default().LaunchCount() != before + 2 * g->Launches() || g->Launches() < 3) Fatalf("replay launch count");
+  Vector want = g1;
+  for (double& e : want) e *= 3;
+  ExpectClose(gW->Download(), want, "replayed weight gradient accumulates");
+  ExpectClose(Y->Download(), y1, "replayed output");
+  ExpectClose(D->Download(), d1, "replayed input gradient");
+  b200::Graph g2;  // refused calls leave the recording abandonable
+  ExpectPanic("af_sync: not allowed between af_graph_begin and af_graph_end", [&] { b200::Context::Default().Sync(); });
+}
+
 struct NamedTest {
   const char* name;
   void (*fn)();
@@ -795,7 +837,7 @@ const NamedTest kTests[] = {
     T(TestFold), T(TestMatMulVecOutput), T(TestMatMulVecChecks), T(TestMatMulVecsComputedMatrix),
     T(TestVariableSerialize), T(TestRFuncBatcherMatchesBatch), T(TestFusedAndPlanMatchOperators),
     T(TestNilGradientAndPruning), T(TestPanics), T(TestForeignHostResultInChain), T(TestMapBatcherOutput),
-    T(TestMapRBatcher), T(TestDeviceGradient),
+    T(TestMapRBatcher), T(TestDeviceGradient), T(TestRecordedGraph),
 };
 #undef T
 
