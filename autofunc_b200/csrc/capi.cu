@@ -238,6 +238,11 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->big_cfg = value;
     return AF_OK;
   }
+  if (!strcmp(name, "persist_tiles")) {
+    if (value < 0 || value > 2) return fail(AF_EINVAL, "persist_tiles must be 0, 1 or 2");
+    ctx->persist_tiles = value;
+    return AF_OK;
+  }
   if (!strcmp(name, "small_n")) {
     ctx->small_n_off = value == 0;
     return AF_OK;

@@ -192,15 +192,26 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
     const double c = 1.03 * (sk_units + cf * segs) + cd;
     if (cfg != 0 && (c < best * 0.98 || (must_defer && mode == 0))) { best = c; mode = 2; }
   }
+  // Persistent whole tiles: a launch of several waves of one-tile CTAs pays every CTA's prologue (barrier setup,
+  // pipeline fill) and epilogue in the open (ncu: tensor pipe 85 % of elapsed vs 92 % for the 296-CTA stream-K
+  // launches).  Give each of <= `slots` CTAs m whole tiles instead: the TMA ring runs on into the next tile while the
+  // current one is stored, the epilogue stays fused (no atomics, no zeroing, no deferred pass).
+  long long tiles_per_cta = 0;
+  if (mode == 0 && ctx->persist_tiles && cfg != 0 && tiles > slots) {
+    tiles_per_cta = (tiles + slots - 1) / slots;
+    mode = 3;
+  }
   bool deferred = false;
   long long units_per_cta = kt_total, units_per_tile = kt_total;
-  if (mode == 1) {
+  if (mode == 3) {
+    units_per_cta = tiles_per_cta * kt_total;
+  } else if (mode == 1) {
     units_per_cta = (kt_total + best_s - 1) / best_s;
     units_per_tile = units_per_cta * best_s;
   } else if (mode == 2) {
     units_per_cta = sk_units;
   }
-  if (mode != 0) {
+  if (mode == 1 || mode == 2) {
     if (!accumulate) {
       deferred = true;
       const size_t bytes = (size_t)logical.I * logical.J * 8;
@@ -213,6 +224,12 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   args.units_per_tile = (int)units_per_tile;
   args.total_units = tiles * units_per_tile;
   dim3 grid((unsigned)((args.total_units + units_per_cta - 1) / units_per_cta), 1, 1);
+  if (mode == 3 && ctx->persist_tiles == 2 && tiles_per_cta * (tiles_per_cta - 1) <= tiles) {
+    // wave order: CTA c takes tiles c, c + grid, ...; the first `wave_rem` CTAs have m tiles, the rest m - 1
+    // (m (m - 1) <= tiles guarantees that the first m - 1 rounds are complete)
+    args.wave_tiles = (int)tiles_per_cta;
+    args.wave_rem = (int)(tiles - (tiles_per_cta - 1) * (long long)grid.x);
+  }
 
   CUtensorMap maps[4];
   AF_TRY(make_map(ctx, &maps[0], A.p0, A.layout, I, Kd, A.ld, bm));

@@ -61,6 +61,10 @@ struct GemmArgs {
   int units_per_cta;       // contiguous (tile, k-tile) units per CTA; == kt_total for one tile per CTA
   int units_per_tile;      // == kt_total (stream-K, one tile per CTA) or splits * units_per_cta (aligned split-K)
   long long total_units;
+  int wave_tiles;     // > 0 (persistent whole tiles, wave order): CTA c works on tiles c, c + grid, c + 2 grid, ... so that
+                      // the CTAs running at one moment are on neighbouring tiles (L2 reuse); position q = c * m + s of
+                      // the tile sequence is tile s * grid + c with m = wave_tiles
+  int wave_rem;       // the first wave_rem CTAs have m tiles, the others m - 1
   int transpose_out;  // write element (i,j) at out[j*ldo + i] (operands were swapped by the host)
   double* out0;
   double* out1;
@@ -294,8 +298,11 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int kt0 = (int)(u0 - (long long)tile0 * p.units_per_tile);
   // aligned split-K pads every tile to a multiple of units_per_cta: clip the padding
   if (p.units_per_tile != kt_total && nun > kt_total - kt0) nun = kt_total - kt0;
+  if (MULTI && p.wave_tiles > 0) nun = (p.wave_tiles - ((int)blockIdx.x < p.wave_rem ? 0 : 1)) * kt_total;
   if (nun <= 0) return;
   const bool has_a1 = DUAL && p.has_a1, has_b1 = DUAL && p.has_b1;
+  // sequence position -> output tile (identity unless the launch is wave-ordered)
+  auto tile_of = [&](int q) { return (MULTI && p.wave_tiles > 0) ? (q % p.wave_tiles) * (int)gridDim.x + q / p.wave_tiles : q; };
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -314,7 +321,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // three warps on one sub-partition and cap every thread at 168 registers, spilling accumulators.
   const uint32_t tx_bytes = L::kABytes + L::kBBytes + (has_a1 ? L::kABytes : 0) + (has_b1 ? L::kBBytes : 0);
   // the producer walks the unit sequence incrementally (no divisions in the loop)
-  int p_kt = kt0, p_tj = tile0 % p.tiles_j, p_ti = tile0 / p.tiles_j;
+  int p_kt = kt0, p_q = tile0, p_tj = tile_of(tile0) % p.tiles_j, p_ti = tile_of(tile0) / p.tiles_j;
   auto produce = [&](int t) {
     const int s = t % kStages;
     const uint32_t ph = (t / kStages) & 1;
@@ -330,7 +337,11 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     ++p_kt;
     if (MULTI && p_kt == kt_total) {
       p_kt = 0;
-      if (++p_tj == p.tiles_j) { p_tj = 0; ++p_ti; }
+      ++p_q;
+      if (p.wave_tiles > 0) {
+        const int tl = tile_of(p_q);
+        p_tj = tl % p.tiles_j; p_ti = tl / p.tiles_j;
+      } else if (++p_tj == p.tiles_j) { p_tj = 0; ++p_ti; }
     }
   };
   if (threadIdx.x == 0) {
@@ -405,7 +416,8 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // registers -> global for the tile that just ended (or was interrupted by the end of this CTA's range)
   const bool vec_ok = !p.transpose_out && ((p.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.out0) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.out1) & 15) == 0);
-  auto flush = [&](int tile) {
+  auto flush = [&](int q) {
+    const int tile = tile_of(q);
     const int i0 = (tile / p.tiles_j) * BM, j0 = (tile % p.tiles_j) * BN;
 #pragma unroll
     for (int t = 0; t < TI; ++t) {

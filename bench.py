@@ -217,6 +217,8 @@ def gpu_arm(args):
     ctx.set_gemm_path(2)  # TMA + DMMA or an error; never a silent fallback
     if args.big_cfg is not None:
         api.check(ctx.lib.af_set_option(ctx.h, b"big_cfg", args.big_cfg))
+    if args.persist_tiles is not None:
+        api.check(ctx.lib.af_set_option(ctx.h, b"persist_tiles", args.persist_tiles))
     plan = api.MLPPlan(LAYER_SIZES, n, ctx)
     params, rvecs = synth.mlp_params(LAYER_SIZES)
     for i, (p, r) in enumerate(zip(params, rvecs)):
@@ -463,6 +465,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=1024, help="samples per CPU-oracle step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--big-cfg", type=int, default=None, help="DMMA tile configuration for wide outputs (0 or 2)")
+    ap.add_argument("--persist-tiles", type=int, default=None,
+                    help="multi-wave contractions as persistent CTAs over whole tiles: 0 off, 1 contiguous, 2 wave order")
     ap.add_argument("--overlap", type=int, default=0,
                     help="N > 1: 0 = one all-reduce after the step (default); k >= 1 = per-layer all-reduces started from the "
                          "grad-ready hook while the backward pass runs, layer 1's weight gradient in k row chunks")
