@@ -733,6 +733,92 @@ void TestMapRBatcher() {
   for (auto& v : f.vars) ExpectClose(g3[v.get()], gWant[v.get()], "non-R gradient", 1e-10, 1e-12);
 }
 
+// a sequence list packed time-major in ONE variable, two maps chained device to device (the second
+// map reads the first one's packed output: no host list in between), gradients for the packed variable and the shared
+// parameter against the per-vector applications.
+void TestPackedSeqsDevicePath() {
+  SeqFixture f;
+  seqfunc::Seqs host, hostR;
+  for (auto& seq : f.seqs) {
+    host.emplace_back();
+    hostR.emplace_back();
+    for (auto& v : seq) {
+      host.back().push_back(v->Vector);
+      auto it = f.rv.find(v.get());
+      hostR.back().push_back(it != f.rv.end() ? it->second : Vector(v->Vector.size(), 0.0));
+    }
+  }
+  std::vector<size_t> lens;
+  std::vector<int64_t> widths;
+  Vector flat, flatR;
+  seqfunc::PackedSeqs::PackHost(hostR, &lens, &widths, &flatR);
+  seqfunc::PackedSeqs::PackHost(host, &lens, &widths, &flat);
+  VariablePtr packedVar = NewVariable(flat);
+  RVector rv = f.rv;
+  rv[packedVar.get()] = flatR;
+  auto net1 = New<ComposedRBatcher>(ComposedRBatcher{f.linTran, New<Sigmoid>()});
+  auto net2 = New<ComposedRBatcher>(ComposedRBatcher{f.linTran, New<Tanh>()});
+  auto input = New<seqfunc::PackedVarRResult>(rv, packedVar, lens, widths);
+  seqfunc::RResultPtr mid = seqfunc::MapRBatcher(net1).ApplySeqsR(rv, input);
+  seqfunc::RResultPtr res = seqfunc::MapRBatcher(net2).ApplySeqsR(rv, mid);
+  if (res->packed()->data->n != (int64_t)flat.size() || !res->packed()->SameShape(*input->packed())) Fatalf("packed output shape");
+  uint64_t s = 9;
+  seqfunc::Seqs up, upR;
+  for (auto& seq : f.seqs) {
+    up.emplace_back();
+    upR.emplace_back();
+    for (size_t j = 0; j < seq.size(); j++) {
+      up.back().push_back(RandomVector(4, &s));
+      upR.back().push_back(RandomVector(4, &s));
+    }
+  }
+  std::vector<VariablePtr> vars{packedVar, f.tran};
+  Gradient g = NewGradient(vars);
+  RGradient rg = NewRGradient(vars);
+  res->PropagateRGradient(up, upR, rg, &g);
+  if (g.size() != 2 || rg.size() != 2) Fatalf("pool variables were left in the maps");
+  // the same thing vector by vector
+  seqfunc::Seqs wantG(f.seqs.size()), wantRG(f.seqs.size());
+  Gradient gT = NewGradient({f.tran});
+  RGradient rgT = NewRGradient({f.tran});
+  for (size_t i = 0; i < f.seqs.size(); i++)
+    for (size_t j = 0; j < f.seqs[i].size(); j++) {
+      VariablePtr x = NewVariable(host[i][j]);
+      RVector rvx = f.rv;
+      rvx[x.get()] = hostR[i][j];
+      RResultPtr one = net2->BatchR(rvx, net1->BatchR(rvx, NewRVariable(x, rvx), 1), 1);
+      ExpectClose(res->OutputSeqs()[i][j], one->Output(), "output");
+      ExpectClose(res->ROutputSeqs()[i][j], one->ROutput(), "r-output");
+      Gradient gx = NewGradient({x, f.tran});
+      RGradient rgx = NewRGradient({x, f.tran});
+      one->PropagateRGradient(up[i][j], upR[i][j], rgx, &gx);
+      wantG[i].push_back(gx[x.get()]);
+      wantRG[i].push_back(rgx[x.get()]);
+      for (size_t k = 0; k < 16; k++) gT[f.tran.get()][k] += gx[f.tran.get()][k], rgT[f.tran.get()][k] += rgx[f.tran.get()][k];
+    }
+  Vector wantFlat, wantFlatR;
+  seqfunc::PackedSeqs::PackHost(wantG, &lens, &widths, &wantFlat);
+  seqfunc::PackedSeqs::PackHost(wantRG, &lens, &widths, &wantFlatR);
+  ExpectClose(g[packedVar.get()], wantFlat, "gradient of the packed list");
+  ExpectClose(rg[packedVar.get()], wantFlatR, "r-gradient of the packed list");
+  ExpectClose(g[f.tran.get()], gT[f.tran.get()], "parameter gradient");
+  ExpectClose(rg[f.tran.get()], rgT[f.tran.get()], "parameter r-gradient");
+  // the same backward pass with the maps in HBM (b200::DeviceGradient) and packed upstreams: nothing visits the host
+  b200::DeviceGradient dg(vars), drg(vars);
+  seqfunc::Packed pu = seqfunc::PackedSeqs::FromHost(up), puR = seqfunc::PackedSeqs::FromHost(upR);
+  seqfunc::PropagateRGradient(*res, *pu, *puR, drg, &dg);
+  ExpectClose(dg.Host(packedVar), wantFlat, "device gradient of the packed list");
+  ExpectClose(drg.Host(f.tran), rgT[f.tran.get()], "device parameter r-gradient");
+  // non-R map over the same packed variable, host upstream lists
+  Gradient g2 = NewGradient(vars);
+  seqfunc::ResultPtr r2 = seqfunc::MapBatcher(net2).ApplySeqs(
+      seqfunc::MapBatcher(net1).ApplySeqs(New<seqfunc::PackedVarResult>(packedVar, lens, widths)));
+  r2->PropagateGradient(up, g2);
+  ExpectClose(g2[packedVar.get()], wantFlat, "non-R gradient of the packed list");
+  ExpectClose(g2[f.tran.get()], gT[f.tran.get()], "non-R parameter gradient");
+  ExpectPanic("upstream sequence shape mismatch", [&] { r2->PropagateGradient({{Vector(4, 0.0)}}, g2); });
+}
+
 // gradient.go:11-57 with the maps in HBM: same numbers as the host maps, AddToVars without a download
 void TestDeviceGradient() {
   Net net = MakeNet({6, 9, 4}, 21);
@@ -837,7 +923,7 @@ const NamedTest kTests[] = {
     T(TestFold), T(TestMatMulVecOutput), T(TestMatMulVecChecks), T(TestMatMulVecsComputedMatrix),
     T(TestVariableSerialize), T(TestRFuncBatcherMatchesBatch), T(TestFusedAndPlanMatchOperators),
     T(TestNilGradientAndPruning), T(TestPanics), T(TestForeignHostResultInChain), T(TestMapBatcherOutput),
-    T(TestMapRBatcher), T(TestDeviceGradient), T(TestRecordedGraph),
+    T(TestMapRBatcher), T(TestPackedSeqsDevicePath), T(TestDeviceGradient), T(TestRecordedGraph),
 };
 #undef T
 
