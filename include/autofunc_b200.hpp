@@ -1562,6 +1562,94 @@ inline RResultPtr RepeatR(RResultPtr in, int n) {
   return std::make_shared<b200::RepeatRResult>(std::move(in), n, out, outR);
 }
 
+// Per-sample concatenation of packed batches: sample i of the result is [a_i | b_i | ...] -- what Concat produces under
+// a batcher (batcher.go:57-84) and the layout bench/lstm.go:140,188 builds per lane; one strided copy per part.
+namespace b200 {
+inline std::vector<int64_t> BatchedWidths(const std::vector<int64_t>& lens, int n) {
+  std::vector<int64_t> w;
+  for (int64_t l : lens) {
+    if (n <= 0 || l % n != 0) throw Panic("input count does not divide input length");  // batcher.go:41
+    w.push_back(l / n);
+  }
+  return w;
+}
+inline Dev BatchedPart(const Dev& u, int64_t off, int64_t w, int64_t total, int n) {
+  Dev out = DevVec::Empty((int64_t)n * w);
+  if (out->n > 0) check(af_copy_2d(ctx(), out->p, w, u->p + off, total, n, w));
+  return out;
+}
+class ConcatBatchedResult : public DeviceResult {
+ public:
+  ConcatBatchedResult(std::vector<ResultPtr> ins, std::vector<int64_t> widths, int n, Dev out)
+      : DeviceResult(std::move(out)), ins_(std::move(ins)), widths_(std::move(widths)), n_(n) {}
+  bool Constant(const Gradient& g) override {
+    for (auto& r : ins_)
+      if (!r->Constant(g)) return false;
+    return true;
+  }
+  void bwd(Session& s, Dev u, Gradient& grad) override {
+    int64_t total = d_->n / (n_ > 0 ? n_ : 1), off = 0;
+    for (size_t i = 0; i < ins_.size(); off += widths_[i], i++)
+      if (!ins_[i]->Constant(grad)) ins_[i]->bwd(s, BatchedPart(u, off, widths_[i], total, n_), grad);
+  }
+
+ private:
+  std::vector<ResultPtr> ins_;
+  std::vector<int64_t> widths_;
+  int n_;
+};
+class ConcatBatchedRResult : public DeviceRResult {
+ public:
+  ConcatBatchedRResult(std::vector<RResultPtr> ins, std::vector<int64_t> widths, int n, Dev out, Dev outR)
+      : DeviceRResult(std::move(out), std::move(outR)), ins_(std::move(ins)), widths_(std::move(widths)), n_(n) {}
+  bool Constant(const RGradient& rg, const Gradient* g) override {
+    for (auto& r : ins_)
+      if (!r->Constant(rg, g)) return false;
+    return true;
+  }
+  void bwdR(Session& s, Dev u, Dev uR, RGradient& rgrad, Gradient* grad) override {
+    int64_t total = d_->n / (n_ > 0 ? n_ : 1), off = 0;
+    for (size_t i = 0; i < ins_.size(); off += widths_[i], i++)
+      if (!ins_[i]->Constant(rgrad, grad))
+        ins_[i]->bwdR(s, BatchedPart(u, off, widths_[i], total, n_), BatchedPart(uR, off, widths_[i], total, n_), rgrad, grad);
+  }
+
+ private:
+  std::vector<RResultPtr> ins_;
+  std::vector<int64_t> widths_;
+  int n_;
+};
+}  // namespace b200
+
+inline ResultPtr ConcatBatched(int n, std::vector<ResultPtr> ins) {
+  std::vector<int64_t> lens;
+  for (auto& r : ins) lens.push_back(r->len());
+  std::vector<int64_t> widths = b200::BatchedWidths(lens, n);
+  int64_t total = 0;
+  for (int64_t w : widths) total += w;
+  b200::Dev out = b200::DevVec::Empty((int64_t)n * total);
+  int64_t off = 0;
+  for (size_t i = 0; i < ins.size(); off += widths[i], i++)
+    if (widths[i] > 0) b200::check(af_copy_2d(b200::ctx(), out->p + off, total, ins[i]->dev()->p, widths[i], n, widths[i]));
+  return std::make_shared<b200::ConcatBatchedResult>(std::move(ins), std::move(widths), n, out);
+}
+inline RResultPtr ConcatBatchedR(int n, std::vector<RResultPtr> ins) {
+  std::vector<int64_t> lens;
+  for (auto& r : ins) lens.push_back(r->len());
+  std::vector<int64_t> widths = b200::BatchedWidths(lens, n);
+  int64_t total = 0;
+  for (int64_t w : widths) total += w;
+  b200::Dev out = b200::DevVec::Empty((int64_t)n * total), outR = b200::DevVec::Zeros((int64_t)n * total);
+  int64_t off = 0;
+  for (size_t i = 0; i < ins.size(); off += widths[i], i++) {
+    if (widths[i] == 0) continue;
+    b200::check(af_copy_2d(b200::ctx(), out->p + off, total, ins[i]->dev()->p, widths[i], n, widths[i]));
+    b200::Dev xr = ins[i]->devR();
+    if (xr) b200::check(af_copy_2d(b200::ctx(), outR->p + off, total, xr->p, widths[i], n, widths[i]));
+  }
+  return std::make_shared<b200::ConcatBatchedRResult>(std::move(ins), std::move(widths), n, out, outR);
+}
+
 // batcher.go:34-84: the naive adaptor -- split the packed input, apply F per sample, concatenate.
 class FuncBatcher : public Batcher {
  public:

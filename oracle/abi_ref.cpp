@@ -93,6 +93,14 @@ int af_copy(af_ctx* c, double* d, const double* s, int64_t n) {
   return AF_OK;
 }
 
+// slices.go:13-119,130-206 on packed batches: rows x cols block copy between pitched buffers
+int af_copy_2d(af_ctx* c, double* dst, int64_t ld_dst, const double* src, int64_t ld_src, int64_t rows, int64_t cols) {
+  CTX(c);
+  for (int64_t r = 0; r < rows; r++)
+    if (cols > 0) std::memmove(dst + r * ld_dst, src + r * ld_src, (size_t)cols * 8);
+  return AF_OK;
+}
+
 // ---- LinTran (lin_tran.go) ------------------------------------------------------------------------------------
 int af_lintran_fwd_r(af_ctx* c, const double* W, const double* RW, const double* X, const double* RX, double* Y,
                      double* RY, int64_t rows, int64_t cols, int64_t n) {

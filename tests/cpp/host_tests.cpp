@@ -254,6 +254,30 @@ void TestRepeat() {
   ExpectFullCheck(RFuncChecker(New<RepeatTestFunc>(), f.vars, f.v1, f.rv));
 }
 
+// Concat under a batcher (batcher.go:57-84): per-sample concatenation of packed batches, by the reference's checker and
+// against Slice / Concat applied sample by sample
+struct ConcatBatchedTestFunc : RFunc {
+  VariablePtr other;
+  const RVector* rv;
+  ResultPtr Apply(ResultPtr r) override { return Mul(ConcatBatched(2, {r, other}), ConcatBatched(2, {other, r})); }
+  RResultPtr ApplyR(const RVector&, RResultPtr r) override {
+    RResultPtr o = NewRVariable(other, *rv);
+    return MulR(ConcatBatchedR(2, {r, o}), ConcatBatchedR(2, {o, r}));
+  }
+};
+void TestConcatBatched() {
+  VariablePtr x = NewVariable({1, -2, 0.5, 3}), other = NewVariable({0.3, -0.7, 2, 1.5, -1, 0.25});
+  RVector rv{{x.get(), {0.5, 1, -1, 2}}};  // `other` absent: zero R
+  auto f = New<ConcatBatchedTestFunc>();
+  f->other = other;
+  f->rv = &rv;
+  ExpectFullCheck(RFuncChecker(f, {x, other}, x, rv));
+  ExpectClose(ConcatBatched(2, {x, other})->Output(), {1, -2, 0.3, -0.7, 2, 0.5, 3, 1.5, -1, 0.25}, "layout");
+  ExpectClose(ConcatBatched(2, {x, other})->Output(),
+              Concat({Slice(x, 0, 2), Slice(other, 0, 3), Slice(x, 2, 4), Slice(other, 3, 6)})->Output(), "vs Concat of Slices");
+  ExpectPanic("input count does not divide input length", [&] { ConcatBatched(4, {x, other}); });
+}
+
 // ---- test/arithmetic_test.go:12-110 (vector 2 intentionally absent from the RVector) -----------------------------
 struct ArithmeticFixture {
   VariablePtr v1 = NewVariable({1, 2, -4, 3, -2}), v2 = NewVariable({4, -2, 3, -0.5, 0.3}),
@@ -917,7 +941,7 @@ struct NamedTest {
 const NamedTest kTests[] = {
     T(TestLinTranOutput), T(TestLinTran), T(TestLinTranBatchOutput), T(TestLinTranBatch), T(TestLinAdd), T(TestExp),
     T(TestLog), T(TestSquaredNorm), T(TestSigmoid), T(TestLogSigmoid), T(TestSoftmax), T(TestSoftmax3), T(TestSin),
-    T(TestTanh), T(TestConcat), T(TestSlice), T(TestWrappedSlice), T(TestRepeat), T(TestArithmetic),
+    T(TestTanh), T(TestConcat), T(TestSlice), T(TestWrappedSlice), T(TestRepeat), T(TestConcatBatched), T(TestArithmetic),
     T(TestAddLogDomainOutput), T(TestSumAllLogDomainOutput), T(TestCosOutput), T(TestNormOutput), T(TestNorm),
     T(TestDiv), T(TestSquaredError), T(TestPool), T(TestPoolPropagatesOnce), T(TestPoolAllEdgeCases), T(TestFoldOut),
     T(TestFold), T(TestMatMulVecOutput), T(TestMatMulVecChecks), T(TestMatMulVecsComputedMatrix),
@@ -1046,6 +1070,51 @@ std::vector<Vector> RunLSTM(const std::vector<std::string>& a, const std::vector
   return out;
 }
 
+// lstmops <I> <H> <O> <T> <B>: bench/lstm.go's network assembled from the drop-in's OPERATORS (lstmBlock.Apply
+// :139-151, lstmNet.StepTime :163-196), batched over B lanes the way a Batcher sees them, R-operator carried through;
+// BPTT by propagating every step's output through the whole graph.  Same files as `lstm`, so the oracle's LSTMNet and
+// the fused plan are the references.   in: 10 params | 10 R-vectors | inputs upstreams upstreamsR
+std::vector<Vector> RunLSTMOps(const std::vector<std::string>& a, const std::vector<Vector>& in) {
+  const int I = std::stoi(a.at(0)), H = std::stoi(a.at(1)), O = std::stoi(a.at(2)), T = std::stoi(a.at(3)), B = std::stoi(a.at(4));
+  const int C = H + I;
+  std::vector<VariablePtr> p;  // W_in b_in W_ingate b_ingate W_forget b_forget W_outgate b_outgate W_out b_out
+  RVector rv;
+  for (int i = 0; i < 10; i++) {
+    p.push_back(NewVariable(in.at(i)));
+    rv[p[i].get()] = in.at(10 + i);
+  }
+  Sigmoid sig;
+  auto gate = [&](int k, RResultPtr x, int rows) {
+    return sig.BatchR(rv, LinAdd(p[2 * k + 1]).BatchR(rv, LinTran(p[2 * k], rows, C).BatchR(rv, x, B), B), B);
+  };
+  RResultPtr state = NewRVariable(NewVariable(Vector((size_t)B * H, 0.0)), rv);  // lstm.go:175, zero R
+  std::vector<RResultPtr> results;
+  for (int t = 0; t < T; t++) {
+    Vector xt(in.at(20).begin() + (long)t * B * I, in.at(20).begin() + (long)(t + 1) * B * I);
+    RResultPtr sample = NewRVariable(NewVariable(xt), rv);
+    RResultPtr joined = ConcatBatchedR(B, {state, sample});                                       // :140,188
+    RResultPtr inState = gate(0, joined, H), inMask = gate(1, joined, H), forgetMask = gate(2, joined, H);
+    RResultPtr outState = AddR(MulR(forgetMask, state), MulR(inMask, inState));                    // :147-150
+    RResultPtr masked = MulR(outState, gate(3, joined, H));                                        // :189-191
+    results.push_back(gate(4, ConcatBatchedR(B, {masked, sample}), O));                            // :193-194
+    state = outState;
+  }
+  Gradient g = NewGradient(p);
+  RGradient rg = NewRGradient(p);
+  Vector out, rout;
+  for (int t = 0; t < T; t++) {
+    out.insert(out.end(), results[t]->Output().begin(), results[t]->Output().end());
+    rout.insert(rout.end(), results[t]->ROutput().begin(), results[t]->ROutput().end());
+    Vector up(in.at(21).begin() + (long)t * B * O, in.at(21).begin() + (long)(t + 1) * B * O);
+    Vector upR(in.at(22).begin() + (long)t * B * O, in.at(22).begin() + (long)(t + 1) * B * O);
+    results[t]->PropagateRGradient(up, upR, rg, &g);
+  }
+  std::vector<Vector> res{out, rout};
+  for (auto& v : p) res.push_back(g[v.get()]);
+  for (auto& v : p) res.push_back(rg[v.get()]);
+  return res;
+}
+
 // arith <n> <m> <k>: a composite over Add/Repeat/Sigmoid/Exp/Scale/Mul/Sub/Square/SumAll/Slice/Concat
 // in: X (n*m) B (m) RX RB U UR (1 + k)   out: out rout gX gB rgX rgB
 std::vector<Vector> RunArith(const std::vector<std::string>& a, const std::vector<Vector>& in) {
@@ -1103,6 +1172,7 @@ int main(int argc, char** argv) {
       if (args[1] == "mlp") out = RunMLP(rest, in);
       else if (args[1] == "lintran") out = RunLinTran(rest, in);
       else if (args[1] == "lstm") out = RunLSTM(rest, in);
+      else if (args[1] == "lstmops") out = RunLSTMOps(rest, in);
       else if (args[1] == "arith") out = RunArith(rest, in);
       else if (args[1] == "next") out = RunNext(rest, in);
       else throw std::runtime_error("unknown case " + args[1]);

@@ -160,7 +160,9 @@ def check_next(ref, exe, tmp, rows, cols, n, seed=0):
         close(a, w_, f"next {rows}x{cols} n={n} {what}")
 
 
-def check_lstm(ref, exe, tmp, I, H, O, T, B, scale=0.5):
+def check_lstm(ref, exe, tmp, I, H, O, T, B, scale=0.5, case="lstm"):
+    """case "lstm": the fused plan (b200::LSTM); case "lstmops": bench/lstm.go's network assembled from the C++ host
+    layer's operators.  Both against the oracle's LSTMNet, lane by lane."""
     from tests.test_gpu_lstm import _oracle
     net = ref.LSTMNet(I, H, O, weight_scale=scale)
     x = ref.splitmix_uniform(501, T * B * I, 0, 1).reshape(T, B, I)
@@ -168,7 +170,7 @@ def check_lstm(ref, exe, tmp, I, H, O, T, B, scale=0.5):
     upr = ref.splitmix_uniform(503, T * B * O).reshape(T, B, O)
     outs, routs, grad, rgrad = _oracle(net, x, up, upr, True)
     inputs = [v.vector for v in net.variables] + [net.rvec[v] for v in net.variables] + [x, up, upr]
-    got = run_case(exe, tmp, "lstm", inputs, [I, H, O, T, B])
+    got = run_case(exe, tmp, case, inputs, [I, H, O, T, B])
     close(got[0], outs.reshape(-1), "lstm outputs")
     close(got[1], routs.reshape(-1), "lstm r-outputs")
     for i, v in enumerate(net.variables):

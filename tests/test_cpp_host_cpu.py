@@ -20,7 +20,7 @@ def exe(tmp_path_factory):
 def test_reference_tests_pass_on_the_cpp_host_layer(exe):
     r = subprocess.run([exe, "selftest"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "0 failed" in r.stdout and len(re.findall(r"^PASS ", r.stdout, re.M)) >= 45
+    assert "0 failed" in r.stdout and len(re.findall(r"^PASS ", r.stdout, re.M)) >= 46
 
 
 @pytest.mark.parametrize("mode", ["ops", "fused", "plan", "nonr", "nilgrad"])
@@ -40,6 +40,13 @@ def test_cpp_pool_fold_matmul_and_cost_heads_match_numpy_oracle(exe, tmp_path):
     log-domain sums, squared error): the temp-variable protocol and the gating, checked where no GPU exists."""
     cpp_host.check_next(ref, exe, str(tmp_path), 5, 7, 4)
     cpp_host.check_next(ref, exe, str(tmp_path), 1, 1, 1, seed=9)
+
+
+def test_cpp_lstm_from_operators_matches_numpy_oracle(exe, tmp_path):
+    """bench/lstm.go:139-196 built from the C++ host layer's operators (ConcatBatched, LinTran, LinAdd, Sigmoid, Mul,
+    Add), batched over the lanes, BPTT + R-operator through the operator graph -- against the oracle's LSTMNet."""
+    cpp_host.check_lstm(ref, exe, str(tmp_path), 3, 5, 2, 3, 2, case="lstmops")
+    cpp_host.check_lstm(ref, exe, str(tmp_path), 6, 8, 4, 4, 3, case="lstmops")
 
 
 def test_cpp_host_fails_loudly_without_the_gpu_library(tmp_path):

@@ -24,7 +24,7 @@ def exe(tmp_path_factory):
 def test_reference_tests_pass_on_the_gpu_through_cpp(exe):
     r = subprocess.run([exe, "selftest"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "0 failed" in r.stdout and len(re.findall(r"^PASS ", r.stdout, re.M)) >= 45
+    assert "0 failed" in r.stdout and len(re.findall(r"^PASS ", r.stdout, re.M)) >= 46
     launches = int(re.search(r"(\d+) kernel launches", r.stdout).group(1))
     assert launches > 1000  # the work ran as CUDA kernels of this library
 
@@ -52,6 +52,14 @@ def test_cpp_pool_fold_matmul_and_cost_heads_match_oracle(exe, tmp_path):
     cpp_host.check_next(ref, exe, str(tmp_path), 24, 40, 16)
     cpp_host.check_next(ref, exe, str(tmp_path), 10, 64, 130, seed=4)
     cpp_host.check_next(ref, exe, str(tmp_path), 3, 5, 2, seed=7)   # odd pitches: the generic contraction kernel
+
+
+def test_cpp_lstm_from_operators_matches_oracle(exe, tmp_path):
+    """bench/lstm.go:139-196 assembled from the C++ operators on the device (the reference's benchmark network running on
+    the drop-in's LinTran / LinAdd / Sigmoid / Mul / Add / Concat), against the oracle -- the same files the fused plan
+    is checked with below."""
+    cpp_host.check_lstm(ref, exe, str(tmp_path), 6, 8, 4, 4, 3, case="lstmops")
+    cpp_host.check_lstm(ref, exe, str(tmp_path), 30, 100, 10, 5, 3, scale=1.0, case="lstmops")
 
 
 def test_cpp_lstm_plan_matches_oracle(exe, tmp_path):
