@@ -14,7 +14,7 @@
 //   Sigmoid, Exp, Log, LogSigmoid, Sin, Cos, Norm, Softmax, SquaredNorm     math_funcs.go
 //   Add, Sub, Mul, Div, Scale, AddScaler, Square, Inverse, Pow, SumAll, ScaleFirst, AddFirst, AddLogDomain,
 //   SumAllLogDomain (+R forms); SquaredError (the north star's cost head)   arithmetic.go
-//   Concat, Slice, Repeat, Split (+R forms)                                 slices.go
+//   Concat, Slice, Repeat, Split, ConcatBatched (+R forms)                  slices.go (ConcatBatched: Concat under a batcher)
 //   Pool, PoolAll, PoolSplit (+R forms)                                     pool.go
 //   Fold, FoldR                                                             fold.go
 //   MatMulVec(s), MatMulVec(s)R                                             lin_alg.go:14-133
@@ -409,7 +409,8 @@ class Variable : public Result {
   }
 
   // Wire format (variable.go:24-37,61-68): little-endian u64 count, then little-endian f64s.
-  std::string Serialize() const {
+  std::string Serialize() {
+    Sync();  // a variable updated or produced on the device is written with its current contents
     std::string out(8 + 8 * Vector.size(), '\0');
     uint64_t n = Vector.size();
     for (int i = 0; i < 8; i++) out[i] = (char)((n >> (8 * i)) & 0xff);
