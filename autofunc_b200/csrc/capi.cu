@@ -243,6 +243,11 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->persist_tiles = value;
     return AF_OK;
   }
+  if (!strcmp(name, "sk_bias")) {
+    if (value < 50 || value > 200) return fail(AF_EINVAL, "sk_bias is a percentage between 50 and 200");
+    ctx->sk_bias = ctx->sk_bias_long = value;
+    return AF_OK;
+  }
   if (!strcmp(name, "small_n")) {
     ctx->small_n_off = value == 0;
     return AF_OK;

@@ -19,6 +19,9 @@ struct af_ctx {
   int gemm_path = 0;  // 0 auto, 1 generic, 2 require DMMA
   int big_cfg = 2;    // tile configuration for wide outputs: 0 = 128x64 x 8 warps, 2 = 64x64 x 2 CTAs/SM (default, fastest measured), 3 = 128x64 x 16 warps
   int persist_tiles = 0;  // multi-wave one-tile-per-CTA launches as persistent CTAs over whole tiles: 0 off, 1 contiguous tile ranges, 2 wave-ordered (tile = slot + step * grid)
+  // stream-K's cost in the work-decomposition model, percent, for short (< 64 k-tiles per CTA) and long unit ranges
+  // (af_set_option "sk_bias" sets both: A/B of the model's threshold)
+  int sk_bias = 103, sk_bias_long = 96;
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu
   bool lstm_split_off = true;   // opt-in (af_set_option "lstm_split" 1): two concurrent half-batch kernel chains; measured 24.6 vs 24.2 ms

@@ -189,7 +189,13 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
       if (c < best * 0.98) { best = c; mode = 1; best_s = sp; }
     }
     const double segs = 1.0 + (double)(sk_units - 1) / kt_total;
-    const double c = 1.03 * (sk_units + cf * segs) + cd;
+    // measured (profiles/r01s4_sk_bias_ab.txt): ranges of >= 64 k-tiles amortise a segment's fixed cost better than the
+    // model's cf says (bench weight gradient 1082 -> 1065 us, MLP n = 1024 step 1.371 -> 1.326 ms as stream-K), short
+    // ranges do not (the LSTM's per-step contractions, 15 k-tiles per CTA: 24.3 -> 26.2 ms)
+    // (accumulating outputs only: store-type launches also pay the zeroing and the deferred pass, and C3's forward /
+    // input-gradient launches lose 0.3 % when they flip)
+    const int bias = (accumulate && sk_units >= 64) ? ctx->sk_bias_long : ctx->sk_bias;
+    const double c = bias * 0.01 * (sk_units + cf * segs) + cd;
     if (cfg != 0 && (c < best * 0.98 || (must_defer && mode == 0))) { best = c; mode = 2; }
   }
   // Persistent whole tiles: a launch of several waves of one-tile CTAs pays every CTA's prologue (barrier setup,

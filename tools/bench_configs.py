@@ -189,7 +189,7 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = api.Context(LOCAL, stream=stream.cuda_stream)
     api.set_context(ctx)
-    for opt in ("pdl", "small_mlp", "small_n", "lstm_split", "persist_tiles"):  # A/B switches: AF_OPT_PDL=0 etc.
+    for opt in ("pdl", "small_mlp", "small_n", "lstm_split", "persist_tiles", "sk_bias"):  # A/B switches: AF_OPT_PDL=0 etc.
         v = os.environ.get("AF_OPT_" + opt.upper())
         if v is not None:
             api.check(ctx.lib.af_set_option(ctx.h, opt.encode(), int(v)))
