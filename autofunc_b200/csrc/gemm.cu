@@ -192,9 +192,10 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
     // measured (profiles/r01s4_sk_bias_ab.txt): ranges of >= 64 k-tiles amortise a segment's fixed cost better than the
     // model's cf says (bench weight gradient 1082 -> 1065 us, MLP n = 1024 step 1.371 -> 1.326 ms as stream-K), short
     // ranges do not (the LSTM's per-step contractions, 15 k-tiles per CTA: 24.3 -> 26.2 ms)
-    // (accumulating outputs only: store-type launches also pay the zeroing and the deferred pass, and C3's forward /
-    // input-gradient launches lose 0.3 % when they flip)
-    const int bias = (accumulate && sk_units >= 64) ? ctx->sk_bias_long : ctx->sk_bias;
+    // (store-type launches also pay the zeroing and the deferred pass: they lean only while the last-wave loss is
+    // large -- under four waves of tiles, e.g. 512 tiles = 1.73 waves at n = 1024; C3's 6.9-wave forward / input-
+    // gradient launches lose 0.3 % when they flip)
+    const int bias = (sk_units >= 64 && (accumulate || tiles < 4 * slots)) ? ctx->sk_bias_long : ctx->sk_bias;
     const double c = bias * 0.01 * (sk_units + cf * segs) + cd;
     if (cfg != 0 && (c < best * 0.98 || (must_defer && mode == 0))) { best = c; mode = 2; }
   }
