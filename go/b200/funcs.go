@@ -67,7 +67,7 @@ func (f ewFunc) bwd(src, srcR, u, uR *devVec) {
 }
 
 func (f ewFunc) ApplyR(_ autofunc.RVector, in autofunc.RResult) autofunc.RResult {
-	x, xR := inputDev(in)
+	x, xR := inputDevR(in)
 	o, oR := newDev(x.n), newDev(x.n)
 	f.fwd(x, xR, o, oR)
 	return &ewRResult{f: f, in: in, x: x, xR: xR, o: o, oR: oR}
@@ -94,9 +94,7 @@ func (r *ewRResult) Constant(rg autofunc.RGradient, g autofunc.Gradient) bool {
 	return r.in.Constant(rg, g)
 }
 func (r *ewRResult) PropagateRGradient(u, uR linalg.Vector, rg autofunc.RGradient, g autofunc.Gradient) {
-	s := &session{acc: map[[2]uintptr]*sessionEntry{}}
-	r.bwdR(s, upload(u), upload(uR), rg, g)
-	s.flush()
+	propagateR(r, u, uR, rg, g)
 }
 func (r *ewRResult) bwdR(s *session, u, uR *devVec, rg autofunc.RGradient, g autofunc.Gradient) {
 	if r.in.Constant(rg, g) {
@@ -107,7 +105,7 @@ func (r *ewRResult) bwdR(s *session, u, uR *devVec, rg autofunc.RGradient, g aut
 	} else {
 		r.f.bwd(r.x, r.xR, u, uR)
 	}
-	down(r.in, s, u, uR, rg, g)
+	downR(r.in, s, u, uR, rg, g)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -121,7 +119,7 @@ func (s *Softmax) ApplyR(rv autofunc.RVector, in autofunc.RResult) autofunc.RRes
 }
 
 func (s *Softmax) BatchR(_ autofunc.RVector, in autofunc.RResult, n int) autofunc.RResult {
-	x, xR := inputDev(in)
+	x, xR := inputDevR(in)
 	if n < 1 || x.n%n != 0 {
 		panic("input count does not divide input length")
 	}
@@ -145,16 +143,14 @@ func (r *softmaxRResult) Constant(rg autofunc.RGradient, g autofunc.Gradient) bo
 	return r.in.Constant(rg, g)
 }
 func (r *softmaxRResult) PropagateRGradient(u, uR linalg.Vector, rg autofunc.RGradient, g autofunc.Gradient) {
-	s := &session{acc: map[[2]uintptr]*sessionEntry{}}
-	r.bwdR(s, upload(u), upload(uR), rg, g)
-	s.flush()
+	propagateR(r, u, uR, rg, g)
 }
 func (r *softmaxRResult) bwdR(s *session, u, uR *devVec, rg autofunc.RGradient, g autofunc.Gradient) {
 	if r.in.Constant(rg, g) {
 		return
 	}
 	check(C.af_softmax_bwd_r(context(), r.y.p, r.yR.p, C.double(r.t), u.p, uR.p, C.int64_t(r.y.n/r.rows), C.int64_t(r.rows)))
-	down(r.in, s, u, uR, rg, g)
+	downR(r.in, s, u, uR, rg, g)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -162,8 +158,8 @@ func (r *softmaxRResult) bwdR(s *session, u, uR *devVec, rg autofunc.RGradient, 
 // (math_funcs.go:191-199, arithmetic.go:144,466) as one reduction.  funcs.py: squared_error_r.
 // ---------------------------------------------------------------------------------------------
 func SquaredErrorR(actual, expected autofunc.RResult) autofunc.RResult {
-	a, aR := inputDev(actual)
-	y, yR := inputDev(expected)
+	a, aR := inputDevR(actual)
+	y, yR := inputDevR(expected)
 	if a.n != y.n {
 		panic("vector sizes do not match") // arithmetic.go:265
 	}
@@ -185,9 +181,7 @@ func (r *sqErrRResult) Constant(rg autofunc.RGradient, g autofunc.Gradient) bool
 	return r.actual.Constant(rg, g) && r.expected.Constant(rg, g)
 }
 func (r *sqErrRResult) PropagateRGradient(u, uR linalg.Vector, rg autofunc.RGradient, g autofunc.Gradient) {
-	s := &session{acc: map[[2]uintptr]*sessionEntry{}}
-	r.bwdR(s, upload(u), upload(uR), rg, g)
-	s.flush()
+	propagateR(r, u, uR, rg, g)
 }
 func (r *sqErrRResult) bwdR(s *session, u, uR *devVec, rg autofunc.RGradient, g autofunc.Gradient) {
 	for _, side := range []struct {
@@ -200,7 +194,7 @@ func (r *sqErrRResult) bwdR(s *session, u, uR *devVec, rg autofunc.RGradient, g 
 		d, dR := newDev(r.a.n), newDev(r.a.n)
 		check(C.af_sqerr_bwd_r(context(), r.a.p, ptr(r.aR), r.y.p, ptr(r.yR), u.p, uR.p, C.double(side.sign),
 			d.p, dR.p, C.int64_t(r.a.n)))
-		down(side.in, s, d, dR, rg, g)
+		downR(side.in, s, d, dR, rg, g)
 	}
 }
 
@@ -223,5 +217,5 @@ func (m *MLP) AddToVars(scale float64) { check(C.af_mlp_add_to_vars(m.h, C.doubl
 
 // Param downloads parameter i (W0, b0, W1, b1, ...) after device-side updates.
 func (m *MLP) Param(i int, dst linalg.Vector) {
-	check(C.af_mlp_get_param(m.h, C.int(i), (*C.double)(&dst[0]), C.int64_t(len(dst))))
+	check(C.af_mlp_get_param(m.h, C.int(i), hostPtr(dst), C.int64_t(len(dst))))
 }

@@ -95,16 +95,75 @@ def test_synth_generator_matches_oracle_generator():
         assert np.array_equal(r, net.rvec[v])
 
 
+def _split_args(text, start):
+    """Arguments of the call whose opening parenthesis is at text[start]; returns (args, index after the ')')."""
+    depth, args, cur, i = 0, [], [], start
+    while True:
+        ch = text[i]
+        if ch in "([{":
+            depth += 1
+            if depth > 1:
+                cur.append(ch)
+        elif ch in ")]}":
+            depth -= 1
+            if depth == 0:
+                break
+            cur.append(ch)
+        elif ch == "," and depth == 1:
+            args.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+        i += 1
+    last = "".join(cur).strip()
+    if last or args:
+        args.append(last)
+    return args, i + 1
+
+
+def _header_arity():
+    text = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER_PATH).read(), flags=re.S)
+    arity = {}
+    for m in re.finditer(r"\b(af_[a-z0-9_]+)\s*\(", text):
+        args, _ = _split_args(text, m.end() - 1)
+        arity[m.group(1)] = 0 if args in ([], ["void"]) else len(args)
+    return arity
+
+
+def _go_sources():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "go", "b200")
+    return {f: open(os.path.join(root, f)).read() for f in sorted(os.listdir(root)) if f.endswith(".go")}
+
+
 def test_go_shim_binds_only_declared_symbols():
     """go/b200/*.go cannot be compiled here (no Go toolchain): at least every C.af_* it calls must be an entry point
     the header declares, and every header struct it names must exist."""
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     declared = set(_declared_symbols()) | {"af_ctx", "af_mlp", "af_lstm", "af_graph"}
     used = set()
-    for f in os.listdir(os.path.join(root, "go", "b200")):
-        if f.endswith(".go"):
-            used |= set(re.findall(r"\bC\.(af_[a-z0-9_]+)\b", open(os.path.join(root, "go", "b200", f)).read()))
+    for src in _go_sources().values():
+        used |= set(re.findall(r"\bC\.(af_[a-z0-9_]+)\b", src))
     assert used and not (used - declared), f"go shim calls undeclared entry points: {sorted(used - declared)}"
+
+
+def test_go_shim_calls_match_the_prototypes():
+    """A lint in place of the Go compiler: every C.af_*(...) call passes as many arguments as the header's prototype
+    takes, brackets balance in every file, and no forward or backward method falls back to the reference's CPU
+    operators (the shim computes nothing on the host)."""
+    arity = _header_arity()
+    assert arity["af_lintran_fwd_r"] == 10 and arity["af_last_error"] == 0 and arity["af_dense_fwd"] == 13
+    calls = 0
+    for name, src in _go_sources().items():
+        code = re.sub(r"//[^\n]*", "", src)
+        code = re.sub(r"/\*.*?\*/", "", code, flags=re.S)
+        for o, c in ("()", "[]", "{}"):
+            assert code.count(o) == code.count(c), f"{name}: unbalanced {o}{c}"
+        for m in re.finditer(r"\bC\.(af_[a-z0-9_]+)\(", code):
+            args, _ = _split_args(code, m.end() - 1)
+            assert len(args) == arity[m.group(1)], f"{name}: {m.group(1)} called with {len(args)} arguments, prototype has {arity[m.group(1)]}"
+            calls += 1
+        for cpu_op in ("autofunc.LinTran{", "autofunc.LinAdd{", "autofunc.Sigmoid{", "autofunc.FuncBatcher{", "autofunc.ComposedFunc{"):
+            assert cpu_op not in code, f"{name}: constructs the reference's CPU operator {cpu_op}...}}"
+    assert calls > 60
 
 
 def _compile_c_example(tmp_path):
