@@ -332,6 +332,17 @@ def gpu_arm(args):
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_total = float(ms_total.item())
     value = world * n * K / (ms_total * 1e-3)
+    if args.profile_step:
+        # launch-list runs (ncu --metrics gpu__time_duration.sum): nothing but the W + K steps of the timed workload is
+        # launched, so the listed kernels ARE the step and a kernel's share of the list is its share of the step
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_total / K, "steps": K,
+                              "warmup": W, "profile_step": True, "gpu_launches": int(launches)}), flush=True)
+        plan.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
 
     # ---- the reference benchmark's other two modes (bench/mlp.go:29-41): Run(b, false) and Run(b, true) ----
     def timed_mode(with_r, backprop):
@@ -476,6 +487,9 @@ def main():
     ap.add_argument("--overlap-steps", type=int, default=0,
                     help="N > 1: 0 (default) = blocking all-reduce at the end of every step; 1 = double-buffered accumulators, "
                          "the all-reduce of step k overlaps the compute of step k+1 (measured slower: 5.22 vs 5.17 ms at 8 GPUs)")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run only the warm-up and timed steps (no other modes, peak measurement, end-to-end or CPU legs): "
+                         "the command to put under ncu for a launch list of the step")
     ap.add_argument("--trace", action="store_true", help="print the last step's per-launch device times to stderr")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
