@@ -56,6 +56,10 @@ class Context:
         self.device = device
         self._pool: dict[int, list[int]] = {}
         self._closed = False
+        # A/B runs of the tuning knobs over unmodified callers (tests, tools): AF_OPTIONS="sk_rotate=1,big_cfg=0"
+        for item in filter(None, os.environ.get("AF_OPTIONS", "").split(",")):
+            name, _, value = item.partition("=")
+            check(self.lib.af_set_option(self.h, name.strip().encode(), int(value)))
 
     # size-bucketed free lists: operators allocate their outputs per call as the reference does
     # with make() (lin_tran.go:81), but cudaMalloc/cudaFree would synchronise the stream

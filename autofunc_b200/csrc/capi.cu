@@ -248,6 +248,11 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->sk_bias = ctx->sk_bias_long = value;
     return AF_OK;
   }
+  if (!strcmp(name, "sk_rotate")) {
+    if (value != 0 && value != 1) return fail(AF_EINVAL, "sk_rotate must be 0 or 1");
+    ctx->sk_rotate = value;
+    return AF_OK;
+  }
   if (!strcmp(name, "small_n")) {
     ctx->small_n_off = value == 0;
     return AF_OK;

@@ -22,6 +22,9 @@ struct af_ctx {
   // stream-K's cost in the work-decomposition model, percent, for short (< 64 k-tiles per CTA) and long unit ranges
   // (af_set_option "sk_bias" sets both: A/B of the model's threshold)
   int sk_bias = 103, sk_bias_long = 96;
+  // stream-K launches with long unit ranges walk each tile segment's k-tiles in rotated order (gemm_dmma.cuh: seg_start)
+  // so that all CTAs sweep k in lockstep and share operand panels in L2 (af_set_option "sk_rotate" 0/1: A/B)
+  int sk_rotate = 1;
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu
   bool lstm_split_off = true;   // opt-in (af_set_option "lstm_split" 1): two concurrent half-batch kernel chains; measured 24.6 vs 24.2 ms

@@ -217,6 +217,7 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
     units_per_tile = units_per_cta * best_s;
   } else if (mode == 2) {
     units_per_cta = sk_units;
+    args.rotate = (ctx->sk_rotate && sk_units >= 64) ? 1 : 0;
   }
   if (mode == 1 || mode == 2) {
     if (!accumulate) {

@@ -221,6 +221,8 @@ def gpu_arm(args):
         api.check(ctx.lib.af_set_option(ctx.h, b"persist_tiles", args.persist_tiles))
     if args.sk_bias is not None:
         api.check(ctx.lib.af_set_option(ctx.h, b"sk_bias", args.sk_bias))
+    if args.sk_rotate is not None:
+        api.check(ctx.lib.af_set_option(ctx.h, b"sk_rotate", args.sk_rotate))
     plan = api.MLPPlan(LAYER_SIZES, n, ctx)
     params, rvecs = synth.mlp_params(LAYER_SIZES)
     for i, (p, r) in enumerate(zip(params, rvecs)):
@@ -479,6 +481,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--big-cfg", type=int, default=None, help="DMMA tile configuration for wide outputs (0 or 2)")
     ap.add_argument("--sk-bias", type=int, default=None, help="stream-K cost in the decomposition model, percent (default: 103 for short unit ranges, 96 for long ones)")
+    ap.add_argument("--sk-rotate", type=int, default=None,
+                    help="stream-K launches walk each tile segment's k-tiles in rotated order so CTAs sweep k in lockstep (L2 reuse): 0 / 1")
     ap.add_argument("--persist-tiles", type=int, default=None,
                     help="multi-wave contractions as persistent CTAs over whole tiles: 0 off, 1 contiguous, 2 wave order")
     ap.add_argument("--overlap", type=int, default=0,
