@@ -35,6 +35,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "streamk_walk.h"
+
 namespace af {
 
 constexpr int kBK = 16;
@@ -327,16 +329,9 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // which a segment's k-tiles are accumulated is free, so with p.rotate a segment [b, b + len) that starts at local
   // time tau (units since the CTA's start; all CTAs of a stream-K launch start together) begins at k-tile b + r and
   // wraps, with r chosen so that k-tile == tau (mod kt_total) for as long as possible: whole tiles are then swept
-  // in lockstep by every CTA and a panel's k-slice is fetched from DRAM once for all the tiles that use it.
-  auto seg_start = [&](int b, int len, int tau) -> int {
-    if (!MULTI || !p.rotate) return b;
-    const int r1 = ((tau - b) % kt_total + kt_total) % kt_total;  // aligned before the wrap, for len - r1 units
-    const int r2 = (r1 + len) % kt_total;                          // aligned after the wrap, for r2 units
-    int r = 0, span = 0;
-    if (r1 < len) { r = r1; span = len - r1; }
-    if (r2 < len && r2 > span) r = r2;
-    return b + r;
-  };
+  // in lockstep by every CTA and a panel's k-slice is fetched from DRAM once for all the tiles that use it
+  // (streamk_walk.h: sk_seg_start).
+  auto seg_start = [&](int b, int len, int tau) -> int { return sk_seg_start(b, len, tau, kt_total, MULTI && p.rotate); };
   int p_q = tile0, p_tj = tile_of(tile0) % p.tiles_j, p_ti = tile_of(tile0) / p.tiles_j;
   int p_b = kt0, p_len = (kt_total - kt0 < nun) ? kt_total - kt0 : nun, p_done = 0, p_tau = 0;  // current segment (MULTI)
   int p_kt = seg_start(p_b, p_len, 0);
