@@ -80,6 +80,11 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * plain launches -- measured 24.6 ms vs 24.25 ms on the C4 LSTM: the stream-K contraction already keeps every CTA
  * slot busy until its end, so the early-launched successor only competes for the slots.  Takes effect for graphs
  * captured afterwards.
+ * "sk_rotate": 1 (default) = stream-K contraction launches whose CTAs own >= 64 k-tiles accumulate each tile segment's
+ * k-tiles in rotated order, so that all CTAs sweep k in lockstep and share operand panels in L2 (DRAM reads of the bench
+ * weight gradient 2.44 GB -> 0.46 GB, same time); 0 = every segment ascending from its first k-tile.
+ * "sk_bias": stream-K's cost in the work-decomposition model, percent (A/B of the model's threshold).
+ * "persist_tiles": 1 | 2 = multi-wave one-tile-per-CTA launches as persistent CTAs over whole tiles (measured slower; 0).
  * "small_mlp": 1 (default) = af_mlp_step with <= 4 samples runs as ONE persistent cooperative kernel
  * (all layers, both directions, grid barriers between phases); 0 = the per-kernel CUDA graph.          */
 int af_set_option(af_ctx* ctx, const char* name, int value);
