@@ -1,5 +1,7 @@
-"""Builds the C++ part of the checker: oracle/abi_ref.cpp -> oracle/_build/libautofunc_b200_ref.so (git-ignored).
-TEST INFRASTRUCTURE: called by tests/ and by __graft_entry__.build() (building the checker is not using it)."""
+"""Builds the C++ parts of the checker into oracle/_build/ (git-ignored): oracle/abi_ref.cpp -> libautofunc_b200_ref.so
+(CPU restatement of the C ABI for the C++ host tests) and oracle/native_ref.cpp -> libnative_ref.so (the "oracle-native"
+CPU baseline: the reference's Gemm-per-call-site structure with a blocked OpenMP Gemm).
+TEST INFRASTRUCTURE: called by tests/, bench.py's CPU legs and __graft_entry__.build() (building the checker is not using it)."""
 from __future__ import annotations
 
 import os
@@ -21,5 +23,20 @@ def build_abi_ref() -> str:
     return REF_LIB
 
 
+NATIVE_LIB = os.path.join(OUT_DIR, "libnative_ref.so")
+
+
+def build_native_ref() -> str:
+    src = os.path.join(HERE, "native_ref.cpp")
+    if os.path.exists(NATIVE_LIB) and os.path.getmtime(NATIVE_LIB) >= os.path.getmtime(src):
+        return NATIVE_LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    # no -march: the library is built in one container and timed on another host (and gonum's own kernels are SSE2)
+    subprocess.run(["g++", "-std=c++17", "-O3", "-fopenmp", "-Wall", "-Wextra", "-Werror", "-fPIC", "-shared", src, "-o", NATIVE_LIB],
+                   check=True, capture_output=True, text=True)
+    return NATIVE_LIB
+
+
 if __name__ == "__main__":
     print(build_abi_ref())
+    print(build_native_ref())

@@ -183,3 +183,21 @@ def test_random_networks_pass_the_reference_acceptance_procedure(seed):
     family of node the product implements (tests/fixtures.py: RandomNetFixture)."""
     f = fx.RandomNetFixture(ref, seed)
     assert RFuncChecker(ref, f.func, f.variables, f.input, f.rv).full_check() == []
+
+
+@pytest.mark.parametrize("sizes,n,scaled", [([7, 5, 3], 4, False), ([100, 130, 66, 10], 37, True), ([1000, 2000, 512, 10], 16, False)])
+def test_native_like_cpu_baseline_matches_the_numpy_oracle(sizes, n, scaled):
+    """oracle/native_ref.cpp (SURVEY 8d "oracle-native": one blocked OpenMP Gemm per lin_tran.go call site, the CPU
+    baseline that stands in for the reference's default gonum backend) computes the same step as the numpy oracle."""
+    from oracle import native
+    net = ref.MLP(sizes, weight_scale=(lambda k: 1 / np.sqrt(k)) if scaled else None)
+    x = net.make_input(n)
+    res, grad, rgrad = net.step_r(x, n)
+    out, rout, grads, rgrads = native.mlp_step_r(sizes, n, [v.vector for v in net.variables],
+                                                 [net.rvec[v] for v in net.variables], x.vector)
+
+    def close(a, b):
+        return bool(np.all(np.abs(a - b) <= 1e-12 + 1e-10 * np.abs(b)))
+    assert close(out, res.output()) and close(rout, res.routput())
+    for i, v in enumerate(net.variables):
+        assert close(grads[i], grad[v]) and close(rgrads[i], rgrad[v]), i
