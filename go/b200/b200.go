@@ -10,7 +10,7 @@
 // the same logic; every method cites the api.py routine it transliterates.
 //
 // Files: b200.go (context, device vectors, backward session, LinTran, DenseSigmoid, MLP plan,
-// recorded graphs), ops.go (LinAdd, Sigmoid, Exp, Add/Mul/Scale), funcs.go (SURVEY 8f functions).
+// recorded graphs), ops.go (LinAdd, Sigmoid, Exp, Add/Mul/Scale), funcs.go (SURVEY 8f functions), lstm.go (the LSTM plan).
 //
 // Build (on a machine with Go >= 1.21, CUDA 12.9 and a B200):
 //   CGO_CFLAGS="-I${REPO}/include" CGO_LDFLAGS="-L${REPO}/autofunc_b200 -lautofunc_b200" go build ./go/b200
