@@ -580,7 +580,11 @@ func (m *MLP) StepR(vars []*autofunc.Variable, input, outGrad, outRGrad linalg.V
 	out, outR = make(linalg.Vector, nOut), make(linalg.Vector, nOut)
 	tmpG := make([]linalg.Vector, len(vars))
 	tmpRG := make([]linalg.Vector, len(vars))
-	pg, prg := newCPtrArray(len(vars)), newCPtrArray(len(vars))
+	nParams := 2 * (len(m.Sizes) - 1)
+	if len(vars) != nParams {
+		panic(fmt.Sprintf("b200.MLP: expected %d variables (W0, b0, W1, b1, ...) but got %d", nParams, len(vars)))
+	}
+	pg, prg := newCPtrArray(nParams), newCPtrArray(nParams) // the library reads 2L entries; NULL entries are skipped
 	defer pg.free()
 	defer prg.free()
 	var pin runtime.Pinner
