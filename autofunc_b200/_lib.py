@@ -12,7 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUTOFUNC_B200_LIB") or os.path.join(_HERE, "libautofunc_b200.so")  # override: A/B builds only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "autofunc_b200.h")
 
-AF_OK, AF_ESHAPE, AF_ECUDA, AF_ENOMEM, AF_EINVAL, AF_ENOTSUP = 0, -1, -2, -3, -4, -5
+AF_OK, AF_ESHAPE, AF_ECUDA, AF_ENOMEM, AF_EINVAL, AF_ENOTSUP, AF_ENCCL = 0, -1, -2, -3, -4, -5, -6
+AF_DP_OFF, AF_DP_BLOCKING, AF_DP_OVERLAP, AF_DP_DEFERRED = 0, 1, 2, 3
+AF_DP_ID_BYTES = 128
 
 P = C.c_void_p          # opaque handles and device pointers
 D = C.c_void_p          # device double*
@@ -126,6 +128,22 @@ PROTOTYPES = {
     "af_mlp_submit_download_host": (INT, [P, INT, H, H, C.POINTER(H), C.POINTER(H)]),
     "af_mlp_bind_slot": (INT, [P, INT]),
     "af_mlp_set_grad_ready": (INT, [P, C.c_void_p, C.c_void_p, INT]),
+    "af_dp_unique_id": (INT, [C.c_void_p]),
+    "af_dp_init": (INT, [P, INT, INT, C.c_void_p]),
+    "af_dp_init_local": (INT, [C.POINTER(P), INT]),
+    "af_dp_destroy": (INT, [P]),
+    "af_dp_info": (INT, [P, C.POINTER(INT), C.POINTER(INT), C.POINTER(INT)]),
+    "af_dp_group_begin": (INT, []),
+    "af_dp_group_end": (INT, []),
+    "af_dp_calls": (I64, [P]),
+    "af_allreduce_sum": (INT, [P, D, I64]),
+    "af_mlp_set_dp": (INT, [P, INT]),
+    "af_mlp_step_dp": (INT, [P, INT]),
+    "af_mlp_step_fresh_dp": (INT, [P, INT]),
+    "af_mlp_dp_join": (INT, [P]),
+    "af_mlp_grad_slab": (I64, [P, C.POINTER(D)]),
+    "af_mlp_set_host_shard": (INT, [P, INT]),
+    "af_lstm_step_dp": (INT, [P, INT]),
     "af_copy_2d": (INT, [P, D, I64, D, I64, I64, I64]),
     "af_lstm_create": (INT, [P, I64, I64, I64, I64, I64, C.POINTER(P)]),
     "af_lstm_destroy": (INT, [P]),

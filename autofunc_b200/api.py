@@ -96,6 +96,26 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.af_launch_count(self.h))
 
+    def set_option(self, name: str, value: int) -> None:
+        check(self.lib.af_set_option(self.h, name.encode(), int(value)))
+
+    # ---- data parallelism (af_dp_*): Gradient.Add across ranks, NCCL behind the C ABI ----
+    def dp_init(self, nranks: int, rank: int, unique_id: bytes) -> None:
+        """Join the communicator identified by `unique_id` (the 128 bytes rank 0 got from parallel.dp_unique_id())."""
+        buf = C.create_string_buffer(bytes(unique_id), _lib.AF_DP_ID_BYTES)
+        check(self.lib.af_dp_init(self.h, int(nranks), int(rank), buf))
+
+    def dp_info(self) -> tuple[int, int, int]:
+        n, r, v = C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.af_dp_info(self.h, C.byref(n), C.byref(r), C.byref(v)))
+        return n.value, r.value, v.value
+
+    def dp_calls(self) -> int:
+        return int(self.lib.af_dp_calls(self.h))
+
+    def allreduce_sum(self, v: "DeviceVec") -> None:
+        check(self.lib.af_allreduce_sum(self.h, v.ptr, len(v)))
+
     def set_gemm_path(self, mode: int) -> None:
         check(self.lib.af_set_gemm_path(self.h, mode))
 
@@ -328,7 +348,12 @@ class Variable:
 
     @staticmethod
     def deserialize(b: bytes) -> "Variable":
+        # DeserializeVariable (variable.go:24-37) returns an error on a short read; so does this
+        if len(b) < 8:
+            raise ValueError(f"serialized Variable is truncated: {len(b)} bytes, the length prefix alone takes 8")
         n = int(np.frombuffer(b[:8], dtype="<u8")[0])
+        if (len(b) - 8) // 8 < n:
+            raise ValueError(f"serialized Variable is truncated: the prefix announces {n} values, {(len(b) - 8) // 8} present")
         return Variable(np.frombuffer(b[8:8 + 8 * n], dtype="<f8").copy())
 
 
@@ -1306,6 +1331,29 @@ class MLPPlan:
     def step_fresh(self, with_r=True):
         """One bench iteration in one call: fresh accumulators, outGrad = 1 / outRGrad = 0, forward + backward."""
         check(self.ctx.lib.af_mlp_step_fresh(self.h, int(with_r)))
+
+    # ---- data parallel (gradient.go:28-30 across the context's communicator) ----
+    def set_dp(self, mode: int):
+        check(self.ctx.lib.af_mlp_set_dp(self.h, int(mode)))
+
+    def step_dp(self, with_r=True):
+        """af_mlp_step(with_r, backprop) from accumulators the caller zeroed, then the sum over ranks."""
+        check(self.ctx.lib.af_mlp_step_dp(self.h, int(with_r)))
+
+    def step_fresh_dp(self, with_r=True):
+        check(self.ctx.lib.af_mlp_step_fresh_dp(self.h, int(with_r)))
+
+    def dp_join(self):
+        check(self.ctx.lib.af_mlp_dp_join(self.h))
+
+    def set_host_shard(self, enable=True):
+        check(self.ctx.lib.af_mlp_set_host_shard(self.h, int(bool(enable))))
+
+    def grad_slab(self):
+        """The contiguous {grad | rgrad} block of the bound slot (layer blocks gW, gb, rgW, rgb adjacent)."""
+        p = C.c_void_p()
+        n = self.ctx.lib.af_mlp_grad_slab(self.h, C.byref(p))
+        return self._vec(p.value, int(n))
 
     def get_param(self, idx) -> np.ndarray:
         out = np.empty(self.param_len(idx), dtype=F64)

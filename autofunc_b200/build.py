@@ -11,12 +11,23 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libautofunc_b200.so")
-SOURCES = ["capi.cu", "gemm.cu", "elementwise.cu", "mathops.cu", "lstm.cu", "small_n.cu", "small_mlp.cu"]
+SOURCES = ["capi.cu", "gemm.cu", "elementwise.cu", "mathops.cu", "lstm.cu", "small_n.cu", "small_mlp.cu", "dp.cu"]
 HEADERS = ["common.h", "ew.cuh", "gemm_dmma.cuh", "streamk_walk.h", os.path.join("..", "..", "include", "autofunc_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
     "-Xcompiler", "-fPIC",
 ]
+
+
+def kernel_source_sha() -> str:
+    """sha256 (first 16 hex digits) of the contraction kernel's sources: profiles/roofline_traffic.json carries the value
+    of the build it was measured on, and bench.py reports `roofline.traffic` only while it still matches."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("gemm_dmma.cuh", "gemm.cu", "streamk_walk.h"):
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 def _nvcc() -> str:
@@ -61,7 +72,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 2) or 1) as pool:
         list(pool.map(run, jobs))
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
-    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs])
+    # -ldl: dp.cu resolves libnccl with dlopen at af_dp_* time (the library itself links neither NCCL nor torch)
+    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-ldl"])
     return LIB
 
 

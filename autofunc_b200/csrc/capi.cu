@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.h"
@@ -108,6 +109,7 @@ int af_ctx_destroy(af_ctx* ctx) {
   if (!ctx) return AF_OK;
   DeviceGuard guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  af_dp_destroy(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->barrier_word) cudaFree(ctx->barrier_word);
   for (cudaEvent_t ev : ctx->trace_events) cudaEventDestroy(ev);
@@ -233,6 +235,18 @@ int af_trace_end(af_ctx* ctx, int capacity, int* h_kind, double* h_work, float* 
 
 int af_set_option(af_ctx* ctx, const char* name, int value) {
   if (!ctx || !name) return fail(AF_EINVAL, "null argument");
+  ctx->option_epoch += 1;  // plan-owned graphs captured under the old settings are re-captured
+  if (!strcmp(name, "dp_max_ctas")) {
+    if (value < 0 || value > 64) return fail(AF_EINVAL, "dp_max_ctas must lie in [0, 64]");
+    if (ctx->comm) return fail(AF_EINVAL, "dp_max_ctas must be set before af_dp_init");
+    ctx->dp_max_ctas = value;
+    return AF_OK;
+  }
+  if (!strcmp(name, "dp_reserve_sms")) {
+    if (value < -1 || value >= ctx->sm_count) return fail(AF_EINVAL, "dp_reserve_sms must lie in [-1, sm_count)");
+    ctx->dp_reserve_sms = value;
+    return AF_OK;
+  }
   if (!strcmp(name, "big_cfg")) {
     if (value != 0 && value != 2) return fail(AF_EINVAL, "big_cfg must be 0 (128x64, 8 warps, 1 CTA/SM) or 2 (64x64, 4 warps, 2 CTAs/SM)");
     ctx->big_cfg = value;
@@ -275,6 +289,7 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
 int af_set_gemm_path(af_ctx* ctx, int mode) {
   if (!ctx) return fail(AF_EINVAL, "null context");
   if (mode < 0 || mode > 2) return fail(AF_EINVAL, "gemm path must be 0, 1 or 2");
+  ctx->option_epoch += 1;
   ctx->gemm_path = mode;
   return AF_OK;
 }
@@ -476,6 +491,7 @@ struct af_mlp {
   std::vector<double*> act, ract;      // L+1: act[0] = input
   std::vector<double*> delta, rdelta;  // L+1: delta[L] = upstream buffer
   int64_t total_params = 0;
+  int64_t gr_doubles = 0;  // length of the contiguous {grad | rgrad} block (padded sub-buffers, layer blocks adjacent)
   int64_t param_len(int idx) const {
     const int l = idx / 2;
     return (idx & 1) ? sizes[l + 1] : sizes[l] * sizes[l + 1];
@@ -493,8 +509,8 @@ struct af_mlp {
   int bound_slot = 0;
   // CUDA-graph replay of the step (small batches are launch-bound: ~25 short kernels per step).  One graph
   // per (with_r, backprop, slot); captured on the second call of a configuration, dropped whenever the set
-  // of present R-vectors changes.
-  struct StepGraph { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; };
+  // of present R-vectors changes or an option of the context changes (epoch).
+  struct StepGraph { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; int64_t epoch = 0; };
   StepGraph graphs[2][2][2];
   bool use_graph = false;
   // data-parallel hook: called (on the host, at enqueue time) as soon as the launches that complete a range of
@@ -506,6 +522,13 @@ struct af_mlp {
   double* alt = nullptr;  // backing store of slot 1
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   int64_t submitted = 0, waited = 0;
+  // data parallelism inside the library (dp.cu): mode AF_DP_*, per-layer "block complete" events on the ctx stream,
+  // per-slot "reduced" events on the communicator's stream
+  int dp_mode = AF_DP_OFF;
+  bool host_shard = false;
+  std::vector<cudaEvent_t> dp_layer_ev, dp_fence_ev;
+  cudaEvent_t dp_done[2] = {nullptr, nullptr};
+  bool dp_pending[2] = {false, false};
 };
 static void mlp_drop_graphs(af_mlp* m) {
   for (auto& a : m->graphs)
@@ -561,6 +584,7 @@ int af_mlp_create(af_ctx* ctx, const int64_t* sizes, int n_layers, int64_t batch
   for (int l = 0; l <= n_layers; ++l) m->ract.push_back(next());
   for (int l = 0; l <= n_layers; ++l) m->delta.push_back(next());
   for (int l = 0; l <= n_layers; ++l) m->rdelta.push_back(next());
+  m->gr_doubles = m->act[0] - m->grad[0];
   m->has_rvec.assign(P, false);
   m->use_graph = batch <= 256;  // launch-bound regime
   for (int i = 0; i < P; ++i) m->total_params += m->param_len(i);
@@ -571,12 +595,17 @@ int af_mlp_create(af_ctx* ctx, const int64_t* sizes, int n_layers, int64_t batch
 int af_mlp_destroy(af_mlp* m) {
   if (!m) return AF_OK;
   DeviceGuard guard(m->ctx->device);
+  if (m->ctx->dp_stream) cudaStreamSynchronize(m->ctx->dp_stream);
   cudaStreamSynchronize(m->ctx->stream);
   if (m->copy_in) { cudaStreamSynchronize(m->copy_in); cudaStreamDestroy(m->copy_in); }
   if (m->copy_out) { cudaStreamSynchronize(m->copy_out); cudaStreamDestroy(m->copy_out); }
   for (auto& sl : m->slot)
     for (cudaEvent_t ev : {sl.in_ready, sl.compute_done, sl.out_done})
       if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : m->dp_layer_ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : m->dp_fence_ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : m->dp_done)
+    if (ev) cudaEventDestroy(ev);
   mlp_drop_graphs(m);
   if (m->alt) cudaFree(m->alt);
   cudaFree(m->slab);
@@ -627,19 +656,40 @@ double* af_mlp_output_ptr(af_mlp* m) { return m ? m->act[m->L] : nullptr; }
 double* af_mlp_routput_ptr(af_mlp* m) { return m ? m->ract[m->L] : nullptr; }
 double* af_mlp_upstream_ptr(af_mlp* m) { return m ? m->delta[m->L] : nullptr; }
 double* af_mlp_upstream_r_ptr(af_mlp* m) { return m ? m->rdelta[m->L] : nullptr; }
+int64_t af_mlp_grad_slab(af_mlp* m, double** d_first) {
+  if (!m) return 0;
+  if (d_first) *d_first = m->grad[0];
+  return m->gr_doubles;
+}
+
+// the ctx stream waits for the slot's outstanding reduces (AF_DP_DEFERRED leaves them running past the step)
+static int mlp_dp_join_slot(af_mlp* m, int k) {
+  if (!m->dp_pending[k]) return AF_OK;
+  AF_CUDA(cudaStreamWaitEvent(m->ctx->stream, m->dp_done[k], 0));
+  m->dp_pending[k] = false;
+  return AF_OK;
+}
+
+int af_mlp_dp_join(af_mlp* m) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  DeviceGuard guard(m->ctx->device);
+  AF_TRY(mlp_dp_join_slot(m, 0));
+  return mlp_dp_join_slot(m, 1);
+}
 
 int af_mlp_zero_grads(af_mlp* m) {
   if (!m) return fail(AF_EINVAL, "null mlp");
   DeviceGuard guard(m->ctx->device);
+  AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
   // grad and rgrad blocks are adjacent in the slab
-  const size_t bytes = (size_t)(m->act[0] - m->grad[0]) * 8;
-  AF_CUDA(cudaMemsetAsync(m->grad[0], 0, bytes, m->ctx->stream));
+  AF_CUDA(cudaMemsetAsync(m->grad[0], 0, (size_t)m->gr_doubles * 8, m->ctx->stream));
   return AF_OK;
 }
 
 // Gradient.AddToVars (gradient.go:40-52) for the plan's own parameters: param_i += scale * grad_i, in HBM.
 int af_mlp_add_to_vars(af_mlp* m, double scale) {
   if (!m) return fail(AF_EINVAL, "null mlp");
+  AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
   for (int i = 0; i < 2 * m->L; ++i) AF_TRY(af_axpy(m->ctx, scale, m->grad[i], m->param[i], m->param_len(i)));
   return AF_OK;
 }
@@ -649,7 +699,12 @@ int af_mlp_get_param(af_mlp* m, int index, double* h, int64_t len) {
   return af_download(m->ctx, h, m->param[index], len);
 }
 
-static int mlp_step_launches(af_mlp* m, int with_r, int backprop);
+static int mlp_forward_launches(af_mlp* m, int with_r);
+static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap);
+static int mlp_step_launches(af_mlp* m, int with_r, int backprop) {
+  AF_TRY(mlp_forward_launches(m, with_r));
+  return backprop ? mlp_backward_launches(m, with_r, false) : AF_OK;
+}
 
 static int mlp_pipeline_init(af_mlp* m);
 static void mlp_bind_slot(af_mlp* m, int k);
@@ -659,6 +714,21 @@ int af_mlp_set_grad_ready(af_mlp* m, af_grad_ready_fn fn, void* user, int layer1
   m->grad_ready = fn;
   m->grad_ready_user = user;
   m->grad_ready_chunks = layer1_chunks < 1 ? 1 : layer1_chunks;
+  return AF_OK;
+}
+
+int af_mlp_set_dp(af_mlp* m, int mode) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  if (mode < AF_DP_OFF || mode > AF_DP_DEFERRED) return fail(AF_EINVAL, "dp mode must be AF_DP_OFF .. AF_DP_DEFERRED");
+  DeviceGuard guard(m->ctx->device);
+  AF_TRY(af_mlp_dp_join(m));
+  m->dp_mode = mode;
+  return AF_OK;
+}
+
+int af_mlp_set_host_shard(af_mlp* m, int enable) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  m->host_shard = enable != 0;
   return AF_OK;
 }
 
@@ -691,39 +761,77 @@ static int mlp_small_step(af_mlp* m, int with_r, int backprop, bool fresh, bool 
                           backprop != 0, fresh, unit_upstream);
 }
 
-// One iteration of the reference benchmark (bench/mlp.go:43-57 with :118-126): fresh accumulators, upstream from the
-// host (or outGrad = 1 / outRGrad = 0 when NULL), forward + backward.  The inputs are already in act[0].
-static int mlp_fresh_step(af_mlp* m, int with_r, const double* hU, const double* hUR) {
+// upstream of a fresh step: from the host, or outGrad = 1 / outRGrad = 0 (bench/mlp.go:118-126)
+static int mlp_load_upstream(af_mlp* m, int with_r, const double* hU, const double* hUR) {
   af_ctx* ctx = m->ctx;
   cudaStream_t st = ctx->stream;
   const int L = m->L;
   const int64_t top = m->n * m->sizes[L];
-  const bool unit = !hU && !hUR;
-  if (unit && mlp_small_ok(m)) {
-    const int rc = mlp_small_step(m, with_r, 1, true, true);
-    if (rc != AF_ENOTSUP) return rc;
-    ctx->small_mlp_off = true;  // cooperative launch refused: per-kernel path from now on
-  }
   if (hU) AF_CUDA(cudaMemcpyAsync(m->delta[L], hU, (size_t)top * 8, cudaMemcpyHostToDevice, st));
   else AF_TRY(af_fill(ctx, m->delta[L], 1.0, top));  // bench/mlp.go:120-123
   if (with_r) {
     if (hUR) AF_CUDA(cudaMemcpyAsync(m->rdelta[L], hUR, (size_t)top * 8, cudaMemcpyHostToDevice, st));
     else AF_CUDA(cudaMemsetAsync(m->rdelta[L], 0, (size_t)top * 8, st));  // bench/mlp.go:124
   }
-  if (mlp_small_ok(m)) {
-    const int rc = mlp_small_step(m, with_r, 1, true, false);
-    if (rc != AF_ENOTSUP) return rc;
-    ctx->small_mlp_off = true;
+  return AF_OK;
+}
+
+// One iteration of the reference benchmark (bench/mlp.go:43-57 with :118-126): fresh accumulators, upstream from the
+// host (or outGrad = 1 / outRGrad = 0 when NULL), forward + backward.  The inputs are already in act[0].
+// dp: sum the accumulators across the context's communicator afterwards (Gradient.Add across ranks), scheduled per
+// the plan's dp mode.
+static int mlp_fresh_step(af_mlp* m, int with_r, const double* hU, const double* hUR, bool dp) {
+  af_ctx* ctx = m->ctx;
+  dp = dp && dp_active(ctx);
+  const int mode = dp ? (m->dp_mode != AF_DP_OFF ? m->dp_mode : AF_DP_OVERLAP) : AF_DP_OFF;
+  const bool unit = !hU && !hUR;
+  const bool captured = m->use_graph && !m->grad_ready && !ctx->tracing && ctx->stream != nullptr && ctx->stream != cudaStreamLegacy;
+  if (mode >= AF_DP_OVERLAP && !captured && !mlp_small_ok(m) && !m->grad_ready) {
+    // the previous step's reduce may still be running (deferred join): only the accumulators depend on it, so the
+    // forward pass goes first and the join sits in front of the zeroing
+    if (mode == AF_DP_DEFERRED) AF_TRY(mlp_forward_launches(m, with_r));
+    AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
+    AF_TRY(mlp_load_upstream(m, with_r, hU, hUR));
+    AF_CUDA(cudaMemsetAsync(m->grad[0], 0, (size_t)m->gr_doubles * 8, ctx->stream));
+    if (mode != AF_DP_DEFERRED) AF_TRY(mlp_forward_launches(m, with_r));
+    AF_TRY(mlp_backward_launches(m, with_r, true));
+    if (mode == AF_DP_OVERLAP) AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
+    return AF_OK;
   }
-  AF_TRY(af_mlp_zero_grads(m));
-  return af_mlp_step(m, with_r, 1);
+  AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
+  int rc = AF_ENOTSUP;
+  if (unit && mlp_small_ok(m)) {
+    rc = mlp_small_step(m, with_r, 1, true, true);
+    if (rc == AF_ENOTSUP) ctx->small_mlp_off = true;  // cooperative launch refused: per-kernel path from now on
+  }
+  if (rc == AF_ENOTSUP) {
+    AF_TRY(mlp_load_upstream(m, with_r, hU, hUR));
+    if (mlp_small_ok(m)) {
+      rc = mlp_small_step(m, with_r, 1, true, false);
+      if (rc == AF_ENOTSUP) ctx->small_mlp_off = true;
+    }
+  }
+  if (rc == AF_ENOTSUP) {
+    AF_TRY(af_mlp_zero_grads(m));
+    rc = af_mlp_step(m, with_r, 1);
+  }
+  AF_TRY(rc);
+  if (dp) AF_TRY(dp_allreduce(ctx, m->grad[0], m->gr_doubles, ctx->stream));
+  return AF_OK;
 }
 
 int af_mlp_step_fresh(af_mlp* m, int with_r) {
   if (!m) return fail(AF_EINVAL, "null mlp");
   DeviceGuard guard(m->ctx->device);
   AF_NOT_RECORDING(m->ctx, "af_mlp_step_fresh (plans replay graphs of their own)");
-  return mlp_fresh_step(m, with_r, nullptr, nullptr);
+  return mlp_fresh_step(m, with_r, nullptr, nullptr, false);
+}
+
+int af_mlp_step_fresh_dp(af_mlp* m, int with_r) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  DeviceGuard guard(m->ctx->device);
+  AF_NOT_RECORDING(m->ctx, "af_mlp_step_fresh_dp (plans replay graphs of their own)");
+  return mlp_fresh_step(m, with_r, nullptr, nullptr, true);
 }
 
 int af_mlp_step(af_mlp* m, int with_r, int backprop) {
@@ -731,6 +839,7 @@ int af_mlp_step(af_mlp* m, int with_r, int backprop) {
   af_ctx* ctx = m->ctx;
   DeviceGuard guard(ctx->device);
   AF_NOT_RECORDING(ctx, "af_mlp_step (plans replay graphs of their own)");
+  if (backprop) AF_TRY(mlp_dp_join_slot(m, m->bound_slot));  // the step accumulates into the slot's gradients
   // a handful of samples: the whole step is one persistent kernel (small_mlp.cu), no graph needed
   if (mlp_small_ok(m)) {
     const int rc = mlp_small_step(m, with_r, backprop, false, false);
@@ -741,6 +850,11 @@ int af_mlp_step(af_mlp* m, int with_r, int backprop) {
   if (!m->use_graph || m->grad_ready || ctx->tracing || ctx->stream == nullptr || ctx->stream == cudaStreamLegacy)
     return mlp_step_launches(m, with_r, backprop);
   af_mlp::StepGraph& g = m->graphs[with_r ? 1 : 0][backprop ? 1 : 0][m->bound_slot];
+  if (g.exec && g.epoch != ctx->option_epoch) {  // an option changed since the capture: the decomposition may differ
+    cudaGraphExecDestroy(g.exec);
+    g = af_mlp::StepGraph();
+    g.seen = 1;  // kernel attributes are set; capture again right away
+  }
   if (g.exec) {
     AF_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
     ctx->launches += g.launches;
@@ -759,6 +873,7 @@ int af_mlp_step(af_mlp* m, int with_r, int backprop) {
   if (rc != AF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
   if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
   g.launches = ctx->launches - before;
+  g.epoch = ctx->option_epoch;
   ctx->launches = before;
   const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
   cudaGraphDestroy(graph);
@@ -768,7 +883,30 @@ int af_mlp_step(af_mlp* m, int with_r, int backprop) {
   return AF_OK;
 }
 
-static int mlp_step_launches(af_mlp* m, int with_r, int backprop) {
+// af_mlp_step(with_r, 1) from accumulators the caller zeroed, then the sum over ranks (per the plan's dp mode)
+int af_mlp_step_dp(af_mlp* m, int with_r) {
+  if (!m) return fail(AF_EINVAL, "null mlp");
+  af_ctx* ctx = m->ctx;
+  DeviceGuard guard(ctx->device);
+  AF_NOT_RECORDING(ctx, "af_mlp_step_dp (plans replay graphs of their own)");
+  const bool dp = dp_active(ctx);
+  const int mode = dp ? (m->dp_mode != AF_DP_OFF ? m->dp_mode : AF_DP_OVERLAP) : AF_DP_OFF;
+  const bool captured = m->use_graph && !m->grad_ready && !ctx->tracing && ctx->stream != nullptr && ctx->stream != cudaStreamLegacy;
+  if (mode >= AF_DP_OVERLAP && !captured && !mlp_small_ok(m) && !m->grad_ready) {
+    AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
+    AF_TRY(mlp_forward_launches(m, with_r));
+    AF_TRY(mlp_backward_launches(m, with_r, true));
+    if (mode == AF_DP_OVERLAP) AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
+    return AF_OK;
+  }
+  AF_TRY(af_mlp_step(m, with_r, 1));
+  if (dp) AF_TRY(dp_allreduce(ctx, m->grad[0], m->gr_doubles, ctx->stream));
+  return AF_OK;
+}
+
+}  // extern "C"
+
+static int mlp_forward_launches(af_mlp* m, int with_r) {
   af_ctx* ctx = m->ctx;
   const int L = m->L;
   const int64_t n = m->n;
@@ -781,48 +919,130 @@ static int mlp_step_launches(af_mlp* m, int with_r, int backprop) {
     AF_TRY(af_dense_fwd(ctx, m->param[2 * l], rv(2 * l), m->param[2 * l + 1], rv(2 * l + 1), m->act[l], RX,
                         m->act[l + 1], R ? m->ract[l + 1] : nullptr, m->sizes[l + 1], m->sizes[l], n, 1));
   }
-  if (!backprop) return AF_OK;
-  // backward: top sigmoid (math_funcs.go:326-333 / 357-374) on the caller's upstream, in place
+  return AF_OK;
+}
+
+// Backward pass.  dp_overlap = false: the reference's order, layer by layer from the top (bias gradient, weight
+// gradient, input gradient).  dp_overlap = true (data parallel, AF_DP_OVERLAP / AF_DP_DEFERRED): the input-gradient
+// chain -- the only true dependency chain -- runs first; the weight / bias gradients follow, blocks under 1 MB first
+// (their all-reduce rides with a neighbour's), then the large layers largest first, and every completed run of adjacent
+// layer blocks is all-reduced on the communicator's stream while the remaining contractions run (stream-K launches are
+// sized for sm_count - reserved SMs meanwhile).  The results are identical: every product reads the same operands.
+static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap) {
+  af_ctx* ctx = m->ctx;
+  const int L = m->L;
+  const int64_t n = m->n;
+  const bool R = with_r != 0;
+  auto rv = [&](int idx) -> const double* { return (R && m->has_rvec[idx]) ? m->rvec[idx] : nullptr; };
+  // top sigmoid (math_funcs.go:326-333 / 357-374) on the caller's upstream, in place
   const int64_t top = n * m->sizes[L];
   if (R) AF_TRY(af_sigmoid_bwd_r(ctx, m->act[L], m->ract[L], m->delta[L], m->rdelta[L], top));
   else AF_TRY(af_sigmoid_bwd(ctx, m->act[L], m->delta[L], top));
-  for (int l = L - 1; l >= 0; --l) {
+  auto input_gradient = [&](int l) -> int {  // lin_tran.go:420-423 with the sigmoid backward of the layer below fused in
+    return af_dense_igrad(ctx, m->delta[l + 1], R ? m->rdelta[l + 1] : nullptr, m->param[2 * l], rv(2 * l), m->act[l],
+                          R ? m->ract[l] : nullptr, m->delta[l], R ? m->rdelta[l] : nullptr, m->sizes[l + 1], m->sizes[l], n);
+  };
+  auto block_end = [&](int l) -> double* { return l + 1 < L ? m->grad[2 * l + 2] : m->grad[0] + m->gr_doubles; };
+  if (!dp_overlap) {
+    for (int l = L - 1; l >= 0; --l) {
+      const int64_t rows = m->sizes[l + 1], cols = m->sizes[l];
+      const double* U = m->delta[l + 1];
+      const double* UR = R ? m->rdelta[l + 1] : nullptr;
+      // lin_add.go:94-104 batched: gb += colsum(U), rgb += colsum(UR)
+      AF_TRY(colsum_launch(ctx, U, UR, m->grad[2 * l + 1], R ? m->rgrad[2 * l + 1] : nullptr, rows, n));
+      // lin_tran.go:410-418
+      const double* RX = (R && l > 0) ? m->ract[l] : nullptr;
+      double* gW = m->grad[2 * l];
+      double* rgW = R ? m->rgrad[2 * l] : nullptr;
+      const int chunks = (m->grad_ready && l == 0 && m->grad_ready_chunks > 1) ? m->grad_ready_chunks : 1;
+      if (chunks == 1) {
+        AF_TRY(af_lintran_wgrad_r(ctx, U, UR, m->act[l], RX, gW, rgW, rows, cols, n));
+        if (m->grad_ready)  // the whole layer block gW_l .. rgb_l is complete
+          m->grad_ready(m->grad_ready_user, gW, block_end(l) - gW);
+      } else {
+        // row chunks of the weight gradient (rows of W = columns of U): each chunk's all-reduce can start while
+        // the next chunk is being computed
+        m->grad_ready(m->grad_ready_user, m->grad[2 * l + 1], m->param_len(2 * l + 1));
+        if (R) m->grad_ready(m->grad_ready_user, m->rgrad[2 * l + 1], m->param_len(2 * l + 1));
+        const int64_t step_rows = ((rows + chunks - 1) / chunks + 63) / 64 * 64;
+        for (int64_t r0 = 0; r0 < rows; r0 += step_rows) {
+          const int64_t rc = rows - r0 < step_rows ? rows - r0 : step_rows;
+          GemmOperand A{U + r0, UR ? UR + r0 : nullptr, LAY_RC, rows};
+          GemmOperand Bop{m->act[l], RX, LAY_RC, cols};
+          GemmEpilogue e;
+          e.epi = EPI_ACCUM; e.out0 = gW + r0 * cols; e.out1 = rgW ? rgW + r0 * cols : nullptr; e.ldo = cols;
+          AF_TRY(gemm_launch(ctx, A, Bop, rgW != nullptr, rc, cols, n, e));
+          m->grad_ready(m->grad_ready_user, gW + r0 * cols, rc * cols);
+          if (rgW) m->grad_ready(m->grad_ready_user, rgW + r0 * cols, rc * cols);
+        }
+      }
+      // lin_tran.go:420-423: the input Variable is not in the gradient maps, so layer 1 stops here
+      if (l > 0) AF_TRY(input_gradient(l));
+    }
+    return AF_OK;
+  }
+
+  // ---- data-parallel order ----
+  const int slot = m->bound_slot;
+  while ((int)m->dp_layer_ev.size() < L) {
+    cudaEvent_t ev, fe;
+    AF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    m->dp_layer_ev.push_back(ev);
+    AF_CUDA(cudaEventCreateWithFlags(&fe, cudaEventDisableTiming));
+    m->dp_fence_ev.push_back(fe);
+  }
+  if (!m->dp_done[slot]) AF_CUDA(cudaEventCreateWithFlags(&m->dp_done[slot], cudaEventDisableTiming));
+  for (int l = L - 1; l >= 1; --l) AF_TRY(input_gradient(l));
+  std::vector<int> order;
+  const int64_t small_block = 1 << 17;  // doubles (1 MB): a collective this short is all latency
+  for (int l = L - 1; l >= 0; --l)
+    if (block_end(l) - m->grad[2 * l] < small_block) order.push_back(l);
+  std::vector<int> large;
+  for (int l = 0; l < L; ++l)
+    if (block_end(l) - m->grad[2 * l] >= small_block) large.push_back(l);
+  std::stable_sort(large.begin(), large.end(), [&](int a, int b) {
+    return (block_end(a) - m->grad[2 * a]) > (block_end(b) - m->grad[2 * b]);
+  });
+  const size_t n_small = order.size();
+  order.insert(order.end(), large.begin(), large.end());
+  std::vector<char> done(L, 0), reduced(L, 0);
+  int issued = 0;
+  auto reduce_run = [&](int l) -> int {  // the maximal run of complete, not yet reduced, adjacent blocks around l
+    int lo = l, hi = l;
+    while (lo > 0 && done[lo - 1] && !reduced[lo - 1]) --lo;
+    while (hi + 1 < L && done[hi + 1] && !reduced[hi + 1]) ++hi;
+    for (int k = lo; k <= hi; ++k) reduced[k] = 1;
+    cudaEvent_t ev = m->dp_layer_ev[issued % L], fence = m->dp_fence_ev[issued % L];
+    AF_CUDA(cudaEventRecord(ev, ctx->stream));
+    AF_CUDA(cudaStreamWaitEvent(ctx->dp_stream, ev, 0));
+    // Launch fence.  The collective's CTAs need whole SMs (640 threads x 96 registers) and the next contraction on the
+    // ctx stream would fill every SM before a cross-stream launch gets through -- the collective would then wait for
+    // that kernel's end (measured in round 1: "overlap" no faster than blocking).  So the ctx stream itself waits
+    // for an event the communicator's stream records right before the collective: the collective is launched
+    // in-stream behind it, the next contraction only after the event has crossed streams, and takes the other SMs.
+    AF_CUDA(cudaEventRecord(fence, ctx->dp_stream));
+    AF_TRY(dp_allreduce(ctx, m->grad[2 * lo], block_end(hi) - m->grad[2 * lo], ctx->dp_stream));
+    AF_CUDA(cudaStreamWaitEvent(ctx->stream, fence, 0));
+    ++issued;
+    ctx->reserved_sms = ctx->dp_reserve_sms >= 0 ? ctx->dp_reserve_sms : ctx->dp_max_ctas;
+    return AF_OK;
+  };
+  struct ReserveScope { af_ctx* c; ~ReserveScope() { c->reserved_sms = 0; } } reserve_scope{ctx};
+  for (size_t q = 0; q < order.size(); ++q) {
+    const int l = order[q];
     const int64_t rows = m->sizes[l + 1], cols = m->sizes[l];
     const double* U = m->delta[l + 1];
     const double* UR = R ? m->rdelta[l + 1] : nullptr;
-    // lin_add.go:94-104 batched: gb += colsum(U), rgb += colsum(UR)
     AF_TRY(colsum_launch(ctx, U, UR, m->grad[2 * l + 1], R ? m->rgrad[2 * l + 1] : nullptr, rows, n));
-    // lin_tran.go:410-418
-    const double* RX = (R && l > 0) ? m->ract[l] : nullptr;
-    double* gW = m->grad[2 * l];
-    double* rgW = R ? m->rgrad[2 * l] : nullptr;
-    const int chunks = (m->grad_ready && l == 0 && m->grad_ready_chunks > 1) ? m->grad_ready_chunks : 1;
-    if (chunks == 1) {
-      AF_TRY(af_lintran_wgrad_r(ctx, U, UR, m->act[l], RX, gW, rgW, rows, cols, n));
-      if (m->grad_ready)  // the whole layer block gW_l .. rgb_l is complete
-        m->grad_ready(m->grad_ready_user, gW, (l + 1 < L ? m->grad[2 * l + 2] : m->act[0]) - gW);
-    } else {
-      // row chunks of the weight gradient (rows of W = columns of U): each chunk's all-reduce can start while
-      // the next chunk is being computed
-      m->grad_ready(m->grad_ready_user, m->grad[2 * l + 1], m->param_len(2 * l + 1));
-      if (R) m->grad_ready(m->grad_ready_user, m->rgrad[2 * l + 1], m->param_len(2 * l + 1));
-      const int64_t step_rows = ((rows + chunks - 1) / chunks + 63) / 64 * 64;
-      for (int64_t r0 = 0; r0 < rows; r0 += step_rows) {
-        const int64_t rc = rows - r0 < step_rows ? rows - r0 : step_rows;
-        GemmOperand A{U + r0, UR ? UR + r0 : nullptr, LAY_RC, rows};
-        GemmOperand Bop{m->act[l], RX, LAY_RC, cols};
-        GemmEpilogue e;
-        e.epi = EPI_ACCUM; e.out0 = gW + r0 * cols; e.out1 = rgW ? rgW + r0 * cols : nullptr; e.ldo = cols;
-        AF_TRY(gemm_launch(ctx, A, Bop, rgW != nullptr, rc, cols, n, e));
-        m->grad_ready(m->grad_ready_user, gW + r0 * cols, rc * cols);
-        if (rgW) m->grad_ready(m->grad_ready_user, rgW + r0 * cols, rc * cols);
-      }
-    }
-    // lin_tran.go:420-423: the input Variable is not in the gradient maps, so layer 1 stops here
-    if (l > 0)
-      AF_TRY(af_dense_igrad(ctx, U, UR, m->param[2 * l], rv(2 * l), m->act[l], R ? m->ract[l] : nullptr, m->delta[l],
-                            R ? m->rdelta[l] : nullptr, rows, cols, n));
+    AF_TRY(af_lintran_wgrad_r(ctx, U, UR, m->act[l], (R && l > 0) ? m->ract[l] : nullptr, m->grad[2 * l],
+                              R ? m->rgrad[2 * l] : nullptr, rows, cols, n));
+    done[l] = 1;
+    if (q >= n_small) AF_TRY(reduce_run(l));
   }
+  for (int l = 0; l < L; ++l)  // runs made of small blocks only
+    if (done[l] && !reduced[l]) AF_TRY(reduce_run(l));
+  AF_CUDA(cudaEventRecord(m->dp_done[slot], ctx->dp_stream));
+  m->dp_pending[slot] = true;
   return AF_OK;
 }
 
@@ -831,7 +1051,7 @@ static int mlp_pipeline_init(af_mlp* m) {
   if (m->copy_in) return AF_OK;
   const int L = m->L, P = 2 * L;
   auto pad = [](int64_t x) { return (x + 31) / 32 * 32; };
-  const int64_t gr_doubles = m->act[0] - m->grad[0];  // grad | rgrad, padded, adjacent
+  const int64_t gr_doubles = m->gr_doubles;  // grad | rgrad, padded, adjacent
   const int64_t x_doubles = pad(m->n * m->sizes[0]), o_doubles = pad(m->n * m->sizes[L]);
   AF_CUDA(cudaMalloc(&m->alt, (size_t)(gr_doubles + x_doubles + 2 * o_doubles) * 8));
   AF_CUDA(cudaStreamCreateWithFlags(&m->copy_in, cudaStreamNonBlocking));
@@ -861,6 +1081,36 @@ static void mlp_bind_slot(af_mlp* m, int k) {
   m->act[m->L] = sl.out; m->ract[m->L] = sl.rout;
 }
 
+// device-to-host copies of a step's results on `st`.  With af_mlp_set_host_shard on a data-parallel plan only this
+// rank's 1/nranks of the reduced {grad | rgrad} block crosses to the host (the ranks' host buffers together hold the
+// reduced gradient exactly once).
+static int mlp_download(af_mlp* m, int with_r, double* hOut, double* hROut, double* const* hGrads, double* const* hRGrads,
+                        cudaStream_t st) {
+  const int L = m->L;
+  const int64_t top = m->n * m->sizes[L];
+  if (hOut) AF_CUDA(cudaMemcpyAsync(hOut, m->act[L], (size_t)top * 8, cudaMemcpyDeviceToHost, st));
+  if (hROut && with_r) AF_CUDA(cudaMemcpyAsync(hROut, m->ract[L], (size_t)top * 8, cudaMemcpyDeviceToHost, st));
+  int64_t lo = 0, hi = m->gr_doubles;
+  if (m->host_shard && dp_active(m->ctx)) {
+    lo = m->gr_doubles * m->ctx->dp_rank / m->ctx->dp_nranks;
+    hi = m->gr_doubles * (m->ctx->dp_rank + 1) / m->ctx->dp_nranks;
+  }
+  auto part = [&](double* h, const double* d, int64_t len) -> int {
+    if (!h) return AF_OK;
+    const int64_t off = d - m->grad[0];
+    const int64_t a = off > lo ? off : lo, b = off + len < hi ? off + len : hi;
+    if (a < b) AF_CUDA(cudaMemcpyAsync(h + (a - off), d + (a - off), (size_t)(b - a) * 8, cudaMemcpyDeviceToHost, st));
+    return AF_OK;
+  };
+  for (int i = 0; i < 2 * L; ++i) {
+    if (hGrads) AF_TRY(part(hGrads[i], m->grad[i], m->param_len(i)));
+    if (with_r && hRGrads) AF_TRY(part(hRGrads[i], m->rgrad[i], m->param_len(i)));
+  }
+  return AF_OK;
+}
+
+extern "C" {
+
 int af_mlp_wait(af_mlp* m) {
   if (!m) return fail(AF_EINVAL, "null mlp");
   if (m->waited >= m->submitted) return AF_OK;
@@ -883,15 +1133,13 @@ int af_mlp_submit_compute_host(af_mlp* m, int with_r, const double* hX, const do
   while (m->submitted - m->waited >= 2) AF_TRY(af_mlp_wait(m));  // at most two steps in flight
   const int k = (int)(m->submitted & 1);
   af_mlp::Slot& sl = m->slot[k];
-  const int L = m->L;
-  const int64_t top = m->n * m->sizes[L];
   // the slot's previous user has fully drained (out_done waited above)
   AF_CUDA(cudaMemcpyAsync(sl.x, hX, (size_t)(m->n * m->sizes[0]) * 8, cudaMemcpyHostToDevice, m->copy_in));
   AF_CUDA(cudaEventRecord(sl.in_ready, m->copy_in));
   cudaStream_t st = ctx->stream;
   AF_CUDA(cudaStreamWaitEvent(st, sl.in_ready, 0));
   mlp_bind_slot(m, k);
-  AF_TRY(mlp_fresh_step(m, with_r, hU, hUR));
+  AF_TRY(mlp_fresh_step(m, with_r, hU, hUR, m->dp_mode != AF_DP_OFF));
   sl.busy = true;
   return AF_OK;
 }
@@ -906,19 +1154,13 @@ int af_mlp_submit_download_host(af_mlp* m, int with_r, double* hOut, double* hRO
   const int k = (int)(m->submitted & 1);
   af_mlp::Slot& sl = m->slot[k];
   if (!sl.busy || !m->copy_out) return fail(AF_EINVAL, "af_mlp_submit_download_host without a pending af_mlp_submit_compute_host");
-  const int L = m->L;
-  const int64_t top = m->n * m->sizes[L];
   AF_CUDA(cudaEventRecord(sl.compute_done, ctx->stream));
   cudaStream_t co = m->copy_out;
   AF_CUDA(cudaStreamWaitEvent(co, sl.compute_done, 0));
-  if (hOut) AF_CUDA(cudaMemcpyAsync(hOut, sl.out, (size_t)top * 8, cudaMemcpyDeviceToHost, co));
-  if (hROut && with_r) AF_CUDA(cudaMemcpyAsync(hROut, sl.rout, (size_t)top * 8, cudaMemcpyDeviceToHost, co));
-  for (int i = 0; i < 2 * L; ++i) {
-    if (hGrads && hGrads[i])
-      AF_CUDA(cudaMemcpyAsync(hGrads[i], sl.grad[i], (size_t)m->param_len(i) * 8, cudaMemcpyDeviceToHost, co));
-    if (with_r && hRGrads && hRGrads[i])
-      AF_CUDA(cudaMemcpyAsync(hRGrads[i], sl.rgrad[i], (size_t)m->param_len(i) * 8, cudaMemcpyDeviceToHost, co));
-  }
+  // a deferred reduce of this slot gates the download, not the ctx stream (which joins when it next touches the slot)
+  if (m->dp_pending[k]) AF_CUDA(cudaStreamWaitEvent(co, m->dp_done[k], 0));
+  if (m->bound_slot != k) mlp_bind_slot(m, k);
+  AF_TRY(mlp_download(m, with_r, hOut, hROut, hGrads, hRGrads, co));
   AF_CUDA(cudaEventRecord(sl.out_done, co));
   m->submitted += 1;
   return AF_OK;
@@ -939,18 +1181,10 @@ int af_mlp_step_host(af_mlp* m, int with_r, const double* hX, const double* hU, 
   while (m->waited < m->submitted) AF_TRY(af_mlp_wait(m));
   if (m->copy_in) mlp_bind_slot(m, 0);
   cudaStream_t st = ctx->stream;
-  const int L = m->L;
-  const int64_t top = m->n * m->sizes[L];
   AF_CUDA(cudaMemcpyAsync(m->act[0], hX, (size_t)(m->n * m->sizes[0]) * 8, cudaMemcpyHostToDevice, st));
-  AF_TRY(mlp_fresh_step(m, with_r, hU, hUR));
-  if (hOut) AF_CUDA(cudaMemcpyAsync(hOut, m->act[L], (size_t)top * 8, cudaMemcpyDeviceToHost, st));
-  if (hROut && with_r) AF_CUDA(cudaMemcpyAsync(hROut, m->ract[L], (size_t)top * 8, cudaMemcpyDeviceToHost, st));
-  for (int i = 0; i < 2 * L; ++i) {
-    if (hGrads && hGrads[i])
-      AF_CUDA(cudaMemcpyAsync(hGrads[i], m->grad[i], (size_t)m->param_len(i) * 8, cudaMemcpyDeviceToHost, st));
-    if (with_r && hRGrads && hRGrads[i])
-      AF_CUDA(cudaMemcpyAsync(hRGrads[i], m->rgrad[i], (size_t)m->param_len(i) * 8, cudaMemcpyDeviceToHost, st));
-  }
+  AF_TRY(mlp_fresh_step(m, with_r, hU, hUR, m->dp_mode != AF_DP_OFF));
+  AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
+  AF_TRY(mlp_download(m, with_r, hOut, hROut, hGrads, hRGrads, st));
   AF_CUDA(cudaStreamSynchronize(st));
   return AF_OK;
 }

@@ -46,6 +46,18 @@ struct af_ctx {
   std::vector<int> trace_kind;
   std::vector<double> trace_work;
   size_t trace_used = 0;
+  // bumped by af_set_option / af_set_gemm_path: plan-owned CUDA graphs captured under an older epoch are re-captured
+  int64_t option_epoch = 0;
+  // ---- data parallelism (dp.cu): one NCCL communicator per context, its own high-priority stream ----
+  void* comm = nullptr;           // ncclComm_t
+  int dp_rank = 0, dp_nranks = 1;
+  cudaStream_t dp_stream = nullptr;
+  int dp_max_ctas = 8;            // CTA cap of the communicator (af_set_option "dp_max_ctas", before af_dp_init)
+  // SMs left to a collective that runs beside the contractions: stream-K launches are sized for
+  // (sm_count - reserved_sms) SMs while > 0 (set by the plans around their overlapped all-reduces)
+  int reserved_sms = 0;
+  int dp_reserve_sms = -1;        // af_set_option "dp_reserve_sms"; -1 = dp_max_ctas
+  int64_t dp_calls = 0;           // collectives issued through this context (bench.py reports it)
 };
 
 namespace af {
@@ -107,6 +119,12 @@ struct DeviceGuard {
     if (prev >= 0) cudaSetDevice(prev);
   }
 };
+
+// ---- data parallelism (dp.cu) ----------------------------------------------------------------
+// sum all-reduce of d_ptr[0..n) across the context's communicator, enqueued on `stream` (Gradient.Add across ranks,
+// gradient.go:28-30,108-120).  No-op when the context has no communicator or a single rank.
+int dp_allreduce(af_ctx* ctx, double* d_ptr, long long n, cudaStream_t stream);
+inline bool dp_active(const af_ctx* ctx) { return ctx->comm != nullptr && ctx->dp_nranks > 1; }
 
 // ---- contraction front end (gemm.cu) --------------------------------------------------------
 struct GemmOperand {

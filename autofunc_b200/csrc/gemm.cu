@@ -3,6 +3,7 @@
 #include "common.h"
 #include "gemm_dmma.cuh"
 
+#include <atomic>
 #include <utility>
 
 namespace af {
@@ -57,10 +58,13 @@ template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI>
 int launch_dmma_impl(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3 grid) {
   auto kern = gemm_dmma_kernel<ALAY, BLAY, NACC, CFG, MULTI>;
   const int smem = (int)GemmSmem<NACC, CFG>::kTotal;
-  static unsigned long long configured = 0;  // per template instantiation; the attribute is per device AND function
-  if (!(configured >> (ctx->device & 63) & 1ull)) {
+  // per template instantiation; the attribute is per device AND function.  Contexts on different devices may be driven
+  // by different host threads: a device's bit is published only after its attribute call has returned (two threads may
+  // both make the call, which is harmless).
+  static std::atomic<unsigned long long> configured{0};
+  if (!(configured.load(std::memory_order_acquire) >> (ctx->device & 63) & 1ull)) {
     AF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured |= 1ull << (ctx->device & 63);
+    configured.fetch_or(1ull << (ctx->device & 63), std::memory_order_release);
   }
   const cudaError_t le = launch_kernel(kern, grid, dim3(GemmSmem<NACC, CFG>::kThreads), (size_t)smem, ctx->stream,
                                        ctx->pdl && !ctx->pdl_off, maps[0], maps[1], maps[2], maps[3], args);
@@ -165,7 +169,8 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   const long long tiles = tiles_i * tiles_j;
   // the narrow configuration streams the long operand and is latency-bound (ncu: 12 % warps active, tensor pipe 34 %,
   // stalls = long_scoreboard / wait with one CTA per SM): two CTAs per SM (80 KB of stages each) double the bytes in flight
-  const int slots = ctx->sm_count * (cfg == 0 ? 1 : 2);
+  // (while a plan keeps an all-reduce in flight beside its contractions the collective's CTAs own `reserved_sms` SMs)
+  const int slots = (ctx->sm_count - ctx->reserved_sms) * (cfg == 0 ? 1 : 2);
   args.kt_total = kt_total;
   args.tiles_j = (int)tiles_j;
   args.total_units = tiles * kt_total;

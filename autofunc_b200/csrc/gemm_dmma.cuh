@@ -179,16 +179,29 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Bounded wait: try_wait suspends the thread for a hardware-chosen slice per attempt; after kMbarSpinFast failed attempts
+// the loop backs off with nanosleep, and after kMbarSpinLimit (seconds of wall time -- a healthy wait on a TMA tile lasts
+// microseconds) the thread traps: a TMA that faulted or a descriptor that never completes surfaces as a launch failure
+// (AF_ECUDA at the next call) instead of hanging the GPU.
+constexpr uint32_t kMbarSpinFast = 1u << 12, kMbarSpinLimit = 1u << 24;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
-      ".reg .pred P1;\n"
+      ".reg .pred P1, P2;\n"
+      ".reg .u32 spins;\n"
+      "mov.u32 spins, 0;\n"
       "AF_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
       "@P1 bra AF_DONE;\n"
-      "bra AF_WAIT;\n"
+      "add.u32 spins, spins, 1;\n"
+      "setp.lt.u32 P2, spins, %2;\n"
+      "@P2 bra AF_WAIT;\n"
+      "nanosleep.u32 128;\n"
+      "setp.lt.u32 P2, spins, %3;\n"
+      "@P2 bra AF_WAIT;\n"
+      "trap;\n"
       "AF_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
+      "}\n" ::"r"(bar), "r"(parity), "n"(kMbarSpinFast), "n"(kMbarSpinLimit)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

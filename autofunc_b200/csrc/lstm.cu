@@ -156,7 +156,7 @@ struct af_lstm {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // CUDA-graph replay of the two time loops (hundreds of short dependent launches): [with_r][fwd/bwd]
-  struct LoopGraph { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; };
+  struct LoopGraph { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; int64_t epoch = 0; };
   LoopGraph graphs[2][2];
   int64_t param_len(int idx) const {
     const int k = idx / 2;
@@ -318,6 +318,11 @@ template <typename F>
 static int lstm_graphed(af_lstm* m, af_lstm::LoopGraph& g, F body) {
   af_ctx* ctx = m->ctx;
   if (ctx->tracing || ctx->stream == nullptr || ctx->stream == cudaStreamLegacy || g.seen < 0) return body();
+  if (g.exec && g.epoch != ctx->option_epoch) {  // an option changed since the capture: the decomposition may differ
+    cudaGraphExecDestroy(g.exec);
+    g = af_lstm::LoopGraph();
+    g.seen = 1;
+  }
   if (g.exec) {
     AF_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
     ctx->launches += g.launches;
@@ -336,6 +341,7 @@ static int lstm_graphed(af_lstm* m, af_lstm::LoopGraph& g, F body) {
   if (rc != AF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
   if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
   g.launches = ctx->launches - before;
+  g.epoch = ctx->option_epoch;
   ctx->launches = before;
   const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
   cudaGraphDestroy(graph);
@@ -493,6 +499,17 @@ extern "C" {
 // Host-buffer form of one bench iteration (bench/lstm.go:41-48): upload inputs (T x B x I) and the
 // per-step output gradients (T x B x O; h_upstreams_r may be NULL = zeros), zero the accumulators,
 // forward, BPTT, download outputs and every gradient (10 host pointers each, reference order).
+// One data-parallel iteration on resident inputs / upstreams: fresh accumulators, forward, BPTT, then the sum of the
+// ranks' {grad | rgrad} blocks (Gradient.Add across ranks, gradient.go:28-30) in order on the ctx stream.
+int af_lstm_step_dp(af_lstm* m, int with_r) {
+  if (!m) return fail(AF_EINVAL, "null lstm");
+  AF_TRY(af_lstm_zero_grads(m));
+  AF_TRY(af_lstm_forward(m, with_r));
+  AF_TRY(af_lstm_backward(m, with_r));
+  DeviceGuard guard(m->ctx->device);
+  return dp_allreduce(m->ctx, m->gW4, m->grad_doubles, m->ctx->stream);
+}
+
 int af_lstm_run_host(af_lstm* m, int with_r, const double* h_x, const double* h_up, const double* h_upr, double* h_out,
                      double* h_rout, double* const* h_grads, double* const* h_rgrads) {
   if (!m || !h_x || !h_up) return fail(AF_EINVAL, "null argument");
@@ -500,9 +517,11 @@ int af_lstm_run_host(af_lstm* m, int with_r, const double* h_x, const double* h_
   DeviceGuard guard(ctx->device);
   cudaStream_t st = ctx->stream;
   const int64_t TB = m->T * m->B;
-  // stage x through D4 (free until the backward pass) so it can be scattered into IN / AUG
-  AF_CUDA(cudaMemcpyAsync(m->D4, h_x, (size_t)(TB * m->I) * 8, cudaMemcpyHostToDevice, st));
-  AF_TRY(af_lstm_set_inputs(m, m->D4));
+  // x_t is the tail of both concatenations, concat(state, x) and concat(masked, x) (lstm.go:140,193): a strided copy
+  // puts it straight into IN's x columns (no staging buffer -- any input width fits), AUG's come from there on the device
+  AF_CUDA(cudaMemcpy2DAsync(m->IN + m->H, (size_t)m->C * 8, h_x, (size_t)m->I * 8, (size_t)m->I * 8, (size_t)TB,
+                            cudaMemcpyHostToDevice, st));
+  AF_TRY(af_copy_2d(ctx, m->AUG + m->H, m->C, m->IN + m->H, m->C, TB, m->I));
   AF_CUDA(cudaMemcpyAsync(m->UP, h_up, (size_t)(TB * m->O) * 8, cudaMemcpyHostToDevice, st));
   if (with_r) {
     if (h_upr) AF_CUDA(cudaMemcpyAsync(m->RUP, h_upr, (size_t)(TB * m->O) * 8, cudaMemcpyHostToDevice, st));

@@ -6,6 +6,7 @@
 // backward kernels overwrite the upstreams in place as the reference does (result.go:24-29).  Scalars that the
 // reference reads on the host (`scaler.Output()[0]`, `MaxAbs()`, the upstream of a SumAll) stay on the device and are
 // passed BY POINTER, so a chain of these ops never synchronises the stream.
+#include <atomic>
 #include "common.h"
 #include "ew.cuh"
 
@@ -285,10 +286,11 @@ __global__ void __launch_bounds__(256) softmax_bwd_staged_kernel(const double* _
 // bwd variant needs 64 KB of dynamic shared memory (opt-in attribute, set once per instantiation)
 #define AF_STAGED_LAUNCH(KERNEL, G, SMEM, ...)                                                     \
   do {                                                                                             \
-    static unsigned long long configured = 0; /* one bit per device: the attribute is per device and function */ \
-    if (!(configured >> (ctx->device & 63) & 1ull)) {                                              \
+    /* one bit per device (the attribute is per device and function), published after the call returns */ \
+    static std::atomic<unsigned long long> configured{0};                                          \
+    if (!(configured.load(std::memory_order_acquire) >> (ctx->device & 63) & 1ull)) {              \
       AF_CUDA(cudaFuncSetAttribute(KERNEL<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSoftChunk * 8)); \
-      configured |= 1ull << (ctx->device & 63);                                                    \
+      configured.fetch_or(1ull << (ctx->device & 63), std::memory_order_release);                  \
     }                                                                                              \
     KERNEL<G><<<grid, 256, SMEM, ctx->stream>>>(__VA_ARGS__);                                      \
   } while (0)

@@ -81,6 +81,10 @@ class LSTMPlan:
     def backward(self, with_r=True):
         check(self.ctx.lib.af_lstm_backward(self.h, int(with_r)))
 
+    def step_dp(self, with_r=True):
+        """Fresh accumulators, forward, BPTT, then the sum of the ranks' {grad | rgrad} blocks (af_lstm_step_dp)."""
+        check(self.ctx.lib.af_lstm_step_dp(self.h, int(with_r)))
+
     def run_host(self, x, upstreams, upstreams_r=None, with_r=True, out=None, rout=None, grads=None, rgrads=None):
         """x: T x B x I, upstreams: T x B x O (host arrays).  Returns (out, rout, grads, rgrads)."""
         n_out = self.T * self.B * self.O

@@ -3,7 +3,10 @@ of sample rows; parameters and R-vectors are replicated; after the local step th
 and R-gradients are summed across ranks -- the multi-device form of Gradient.Add (gradient.go:28-30,
 108-120; the reference's gradient is a SUM over samples, never a mean).
 
-torch.distributed is the transport (NCCL over NVLink on GPUs, gloo on CPU for tests)."""
+On GPUs the collective lives BEHIND the C ABI (af_dp_init / af_allreduce_sum / af_mlp_step_dp, csrc/dp.cu: NCCL over
+NVLink, resolved inside the library); the host side only has to ship the 128-byte communicator id from rank 0 to the
+other ranks -- dp_unique_id() + any broadcast (torch.distributed in bench.py, a file or socket elsewhere).  The torch
+helpers below (allreduce_sum_, plan_grad_slab) are the gloo path of the CPU tests and the round-1 A/B transport."""
 from __future__ import annotations
 
 import os
@@ -11,6 +14,38 @@ import os
 
 def env_rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def dp_unique_id() -> bytes:
+    """Rank 0's half of the rendezvous: af_dp_unique_id (ncclGetUniqueId behind the ABI)."""
+    import ctypes as C
+
+    from . import _lib
+    buf = C.create_string_buffer(_lib.AF_DP_ID_BYTES)
+    _lib.check(_lib.load().af_dp_unique_id(buf))
+    return buf.raw
+
+
+def dp_init_torch(ctx, device_index: int):
+    """Create ctx's communicator with torch.distributed (already initialised, any backend) as the id courier."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = f"cuda:{device_index}" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(dp_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, 0)
+    ctx.dp_init(world, rank, bytes(t.cpu().numpy().tobytes()))
+
+
+def dp_init_local(contexts) -> None:
+    """One process, several devices: af_dp_init_local (ncclCommInitAll) over one Context per device."""
+    import ctypes as C
+
+    from . import _lib
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    _lib.check(_lib.load().af_dp_init_local(arr, len(contexts)))
 
 
 def shard_rows(n_total: int, world: int, rank: int) -> tuple[int, int]:

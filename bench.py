@@ -6,10 +6,12 @@ float64, samples/sec.
     python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU)
     python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference
 
-One "step" = one pass of the hot path over one batch of synthetic inputs: zero the accumulators,
-fresh outGrad = 1 / outRGrad = 0 (bench/mlp.go:118-126), ApplyR, PropagateRGradient with non-nil
-grad; for N > 1 each rank owns `batch` samples (weak scaling) and the step ends with one NCCL
-sum all-reduce of {grad, rgrad}.  Prints ONE JSON line on rank 0.
+One "step" = one pass of the hot path over one batch of synthetic inputs: fresh accumulators, fresh
+outGrad = 1 / outRGrad = 0 (bench/mlp.go:118-126), ApplyR, PropagateRGradient with non-nil grad; for
+N > 1 each rank owns `batch` samples (weak scaling) and the step includes the sum of {grad, rgrad}
+over the ranks (Gradient.Add, gradient.go:28-30) -- issued INSIDE the library (af_mlp_step_fresh_dp:
+NCCL behind the C ABI, csrc/dp.cu); torch.distributed only launches the ranks, ships the 128-byte
+communicator id and takes the max of the ranks' timings.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -29,8 +31,10 @@ if ROOT not in sys.path:
 import numpy as np
 
 LAYER_SIZES = [1000, 2000, 512, 10]  # bench/mlp.go:17-20
+C5_SIZES = [8192] * 5                # BASELINE configs[4]: 4 x (8192 -> 8192)
 METRIC = "mlp_fwd_gradient_rgradient_samples_per_sec"
 UNIT = "samples/s"
+DP_MODES = {"blocking": 1, "overlap": 2, "deferred": 3}
 
 
 def flops_per_sample(sizes, with_r=True):
@@ -54,19 +58,6 @@ def workload_name(batch):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (numpy + OpenBLAS threads) -- the only place bench.py executes oracle/
 # ------------------------------------------------------------------------------------------------
-def cpu_threads():
-    """Threads the BLAS pool runs with inside run_cpu_oracle (= every core this process may use)."""
-    try:
-        from threadpoolctl import threadpool_info, threadpool_limits
-        with threadpool_limits(limits=host_cores(), user_api="blas"):
-            n = [p.get("num_threads", 0) for p in threadpool_info() if p.get("user_api") == "blas"]
-        if n:
-            return max(n)
-    except Exception:
-        pass
-    return host_cores()
-
-
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -74,15 +65,42 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def run_cpu_oracle(n, steps, warmup):
-    """The CPU arm uses every host thread it can: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would
-    throttle OpenBLAS to one thread, so the BLAS pool is sized explicitly."""
-    from oracle import autofunc_ref as ref
+def _blas_limit(threads):
     try:
         from threadpoolctl import threadpool_limits
-        limiter = threadpool_limits(limits=host_cores(), user_api="blas")
+        return threadpool_limits(limits=threads, user_api="blas")
     except Exception:
-        limiter = None
+        return None
+
+
+def cpu_thread_sweep(n):
+    """The stated CPU baseline is the oracle's BEST thread count, not its default: one step of the workload at every
+    power-of-two fraction of the host's cores (OpenBLAS often peaks below the hyper-thread count)."""
+    from oracle import autofunc_ref as ref
+    net = ref.MLP(LAYER_SIZES)
+    x = net.make_input(n)
+    cores = host_cores()
+    cands = sorted({max(1, cores >> s) for s in range(0, 4)}, reverse=True)
+    sweep = {}
+    for t in cands:
+        lim = _blas_limit(t)
+        try:
+            net.step_r(x, n)  # warm (thread pool resize, page faults)
+            t0 = time.perf_counter()
+            net.step_r(x, n)
+            sweep[t] = n / (time.perf_counter() - t0)
+        finally:
+            if lim is not None:
+                lim.restore_original_limits()
+    best = max(sweep, key=sweep.get)
+    return best, {str(k): v for k, v in sweep.items()}
+
+
+def run_cpu_oracle(n, steps, warmup, threads):
+    """The CPU arm uses the host threads it is told to: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would
+    throttle OpenBLAS to one thread, so the BLAS pool is sized explicitly."""
+    from oracle import autofunc_ref as ref
+    limiter = _blas_limit(threads)
     try:
         net = ref.MLP(LAYER_SIZES)
         x = net.make_input(n)
@@ -126,21 +144,22 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n = args.cpu_batch
-    times = run_cpu_oracle(n, args.steps, args.warmup)
+    n = args.cpu_batch or args.batch  # the SAME configuration as the GPU arm: n = 4096 per step
+    threads, sweep = cpu_thread_sweep(n)
+    times = run_cpu_oracle(n, args.steps, args.warmup, threads)
     total = sum(times)
     value = n * len(times) / total
-    cores = cpu_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.batch), "layer_sizes": LAYER_SIZES, "batch_per_gpu": args.batch,
                    "global_batch": args.batch * args.gpus},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{len(times)} steps of {n} samples each (bounded sample of the n={args.batch} workload); "
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{len(times)} steps of {n} samples each (the GPU arm's own batch); "
                                    "CPU restatement of the reference (oracle/autofunc_ref.py, numpy + OpenBLAS): "
-                                   "the reference is pure Go and no Go toolchain exists on this box"},
+                                   "the reference is pure Go and no Go toolchain exists on this box",
+                         "host_cores": host_cores(), "thread_sweep_samples_per_s": sweep},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     try:
@@ -224,7 +243,7 @@ def gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    from autofunc_b200 import _lib, api, parallel, synth
+    from autofunc_b200 import _lib, api, build as af_build, parallel, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,19 +256,23 @@ def gpu_arm(args):
     n = args.batch
     K, W = args.steps, args.warmup
 
-    stream = torch.cuda.Stream()  # a real stream: everything (kernels, NCCL dependencies, events) is ordered on it
+    stream = torch.cuda.Stream()  # a real stream: kernels, copies and the timing events are ordered on it
     torch.cuda.set_stream(stream)
     ctx = api.Context(local_rank, stream=stream.cuda_stream)
     api.set_context(ctx)
     ctx.set_gemm_path(2)  # TMA + DMMA or an error; never a silent fallback
-    if args.big_cfg is not None:
-        api.check(ctx.lib.af_set_option(ctx.h, b"big_cfg", args.big_cfg))
-    if args.persist_tiles is not None:
-        api.check(ctx.lib.af_set_option(ctx.h, b"persist_tiles", args.persist_tiles))
-    if args.sk_bias is not None:
-        api.check(ctx.lib.af_set_option(ctx.h, b"sk_bias", args.sk_bias))
-    if args.sk_rotate is not None:
-        api.check(ctx.lib.af_set_option(ctx.h, b"sk_rotate", args.sk_rotate))
+    for name in ("big_cfg", "persist_tiles", "sk_bias", "sk_rotate", "dp_max_ctas", "dp_reserve_sms"):
+        v = getattr(args, name)
+        if v is not None:
+            ctx.set_option(name, v)
+    dp_info = None
+    if world > 1:
+        # the communicator lives inside libautofunc_b200 (af_dp_init); torch only carries its 128-byte id
+        parallel.dp_init_torch(ctx, local_rank)
+        nr, rk, ver = ctx.dp_info()
+        assert (nr, rk) == (world, rank)
+        dp_info = {"transport": "NCCL behind the C ABI (af_dp_init / af_mlp_step_fresh_dp, csrc/dp.cu)",
+                   "nccl_version": ver, "mode": args.dp_mode, "max_ctas": args.dp_max_ctas if args.dp_max_ctas is not None else 8}
     plan = api.MLPPlan(LAYER_SIZES, n, ctx)
     params, rvecs = synth.mlp_params(LAYER_SIZES)
     for i, (p, r) in enumerate(zip(params, rvecs)):
@@ -258,72 +281,43 @@ def gpu_arm(args):
     x_host = synth.mlp_input(LAYER_SIZES, n, seed=124 + 7919 * rank)
     ctx.lib.af_upload(ctx.h, plan.input().ptr, x_host.ctypes.data, x_host.size)
     n_out = n * LAYER_SIZES[-1]
-    up, upr = plan.upstream(), plan.upstream_r()
     P = 2 * plan.L
     n_params = sum(plan.param_len(i) for i in range(P))
-
-    # Data parallel (gradient.go:28-30 across ranks).  Default: one NCCL all-reduce over the contiguous
-    # {grad | rgrad} block after the step.  --overlap k: as soon as a layer's accumulators are complete the
-    # library calls back and their all-reduce starts on NCCL's stream while the backward pass continues.
-    pending, views = [], {}
-
-    def on_grad_ready(_user, ptr, count):
-        key = (ptr, count)
-        t = views.get(key)
-        if t is None:
-            t = views[key] = torch.as_tensor(parallel.CudaArrayView(ptr, count), device=f"cuda:{local_rank}")
-        pending.append(dist.all_reduce(t, async_op=True))
-    cb = _lib.GRAD_READY_FN(on_grad_ready)
-    if world > 1 and args.overlap > 0:
-        api.check(ctx.lib.af_mlp_set_grad_ready(plan.h, C.cast(cb, C.c_void_p), None, args.overlap))
-
-    def finish_reduce():
-        if world > 1:
-            if args.overlap <= 0:
-                parallel.allreduce_sum_(parallel.plan_grad_slab(plan, local_rank))  # one collective over grad | rgrad
-            for w in pending:
-                w.wait()  # the step's stream waits for every range's all-reduce
-            pending.clear()
-
-    # --overlap-steps 1 (opt-in; measured slower): the accumulators are double-buffered (the plan's two slots), step k's
-    # all-reduce runs on NCCL's stream while step k+1 computes into the other slot, and a slot is only reused once its
-    # all-reduce has finished.  Every step still reduces its own gradients inside the timed region (drain() below).
-    overlap_steps = world > 1 and args.overlap_steps and args.overlap <= 0
-    slot_slab, slot_pending, step_k = [None, None], [None, None], [0]
-    if overlap_steps:
-        for sl in (1, 0):  # ends bound to slot 0
-            api.check(ctx.lib.af_mlp_bind_slot(plan.h, sl))
-            ctx.lib.af_upload(ctx.h, plan.input().ptr, x_host.ctypes.data, x_host.size)
-            slot_slab[sl] = parallel.plan_grad_slab(plan, local_rank)
-
-    def drain():
-        for sl in (0, 1):
-            if slot_pending[sl] is not None:
-                slot_pending[sl].wait()
-                slot_pending[sl] = None
+    plan.set_dp(DP_MODES[args.dp_mode] if world > 1 else 0)
+    slab = plan.grad_slab()
+    slab_t = torch.as_tensor(parallel.CudaArrayView(slab.ptr, len(slab)), device=f"cuda:{local_rank}")
 
     def step():
-        if overlap_steps:
-            sl = step_k[0] & 1
-            step_k[0] += 1
-            if slot_pending[sl] is not None:
-                slot_pending[sl].wait()  # the compute stream waits for the all-reduce of step k-2 before zeroing its slab
-                slot_pending[sl] = None
-            api.check(ctx.lib.af_mlp_bind_slot(plan.h, sl))
-        plan.zero_grads()
-        api.check(ctx.lib.af_fill(ctx.h, up.ptr, 1.0, n_out))  # fresh upstreams every step
-        api.check(ctx.lib.af_zero(ctx.h, upr.ptr, n_out))
-        plan.step(True, True)
-        if overlap_steps:
-            slot_pending[sl] = dist.all_reduce(slot_slab[sl], async_op=True)
-        else:
-            finish_reduce()
+        # one bench iteration as ONE library call: fresh accumulators, outGrad = 1 / outRGrad = 0, ApplyR,
+        # PropagateRGradient, and (N > 1) the sum over ranks scheduled per the plan's dp mode
+        plan.step_fresh_dp(True)
+
+    def drain():
+        plan.dp_join()  # deferred mode: the last step's reduce completes inside the timed region
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- warm-up, and (N > 1) the checksum identity of the data-parallel reduce:
+    #      sum(reduced block) on every rank == sum over ranks of sum(local block)
+    dp_check = None
+    if world > 1:
+        plan.step_fresh(True)  # local step, no reduce
+        local = torch.stack([slab_t.sum(), slab_t.abs().sum()])
+        dist.all_reduce(local)
+        step()
+        drain()
+        got = slab_t.sum()
+        rel = float((got - local[0]).abs() / local[1])
+        lo, hi = got.clone(), got.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dp_check = {"identity": "sum(all-reduced {grad|rgrad}) == sum over ranks of sum(local {grad|rgrad})",
+                    "rel_err_vs_sum_abs": rel, "ranks_identical": bool(float(lo) == float(hi)), "ok": rel < 1e-10}
+        if not dp_check["ok"] or not dp_check["ranks_identical"]:
+            raise SystemExit(f"bench.py: data-parallel checksum identity violated: {dp_check}")
     for _ in range(W):
         step()
     drain()
@@ -332,6 +326,7 @@ def gpu_arm(args):
     kinds, work, ms_arr = (C.c_int * cap)(), (C.c_double * cap)(), (C.c_float * cap)()
     count = C.c_int(0)
     launches0 = ctx.launch_count()
+    dp_calls0 = ctx.dp_calls()
     sampler = ClockSampler(local_rank)
     sampler.start()
     api.check(ctx.lib.af_trace_begin(ctx.h, cap))
@@ -339,15 +334,13 @@ def gpu_arm(args):
     e0.record(stream)
     for _ in range(K):
         step()
-    drain()  # the last all-reduces complete inside the timed region
+    drain()
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
-    if overlap_steps:
-        api.check(ctx.lib.af_mlp_bind_slot(plan.h, 0))
-        overlap_steps = False  # the remaining sections use the blocking all-reduce
     api.check(ctx.lib.af_trace_end(ctx.h, cap, kinds, work, ms_arr, C.byref(count)))
     launches = ctx.launch_count() - launches0
+    dp_calls = ctx.dp_calls() - dp_calls0
     if args.trace and rank == 0:
         per_step = count.value // K
         names = {0: "gemm_dual", 1: "gemm_single", 2: "gemm_generic", 3: "elementwise", 4: "reduce", 5: "streaming"}
@@ -356,10 +349,14 @@ def gpu_arm(args):
             unit = "TFLOP/s" if kinds[i] < 3 else "TB/s"
             print(f"trace[{i - (count.value - per_step):2d}] {names.get(kinds[i], str(kinds[i])):12s} {ms_arr[i] * 1e3:9.1f} us  work {work[i]:.4g}  {rate:7.2f} {unit}",
                   file=sys.stderr)
-    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_total = float(ms_total.item())
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = world * n * K / (ms_total * 1e-3)
     if args.profile_step:
         # launch-list runs (ncu --metrics gpu__time_duration.sum): nothing but the W + K steps of the timed workload is
@@ -373,28 +370,41 @@ def gpu_arm(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- the reference benchmark's other two modes (bench/mlp.go:29-41): Run(b, false) and Run(b, true) ----
-    def timed_mode(with_r, backprop):
-        def one():
-            plan.zero_grads()
-            api.check(ctx.lib.af_fill(ctx.h, up.ptr, 1.0, n_out))
-            plan.step(with_r, backprop)
-            if backprop:
-                finish_reduce()
+    def timed(fn, reps, after=None):
+        """device time of `reps` calls of fn on the ctx stream, max over ranks, ms per call"""
         for _ in range(3):
-            one()
+            fn()
+        if after:
+            after()
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record(stream)
-        for _ in range(max(3, K // 2)):
-            one()
+        for _ in range(reps):
+            fn()
+        if after:
+            after()
         a1.record(stream)
         barrier()
-        t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * n * max(3, K // 2) / (float(t.item()) * 1e-3)
-    other_modes = {"fwd_only_samples_per_s": timed_mode(False, False), "fwd_gradient_samples_per_s": timed_mode(False, True)}
+        return max_over_ranks(a0.elapsed_time(a1)) / reps
+
+    # ---- the reference benchmark's other two modes (bench/mlp.go:29-41): Run(b, false) and Run(b, true) ----
+    reps = max(3, K // 2)
+    other_modes = {"fwd_only_samples_per_s": world * n / (timed(lambda: plan.step(False, False), reps) * 1e-3),
+                   "fwd_gradient_samples_per_s": world * n / (timed(lambda: plan.step_fresh_dp(False), reps, drain) * 1e-3)}
+
+    # ---- (N > 1) what the reduce costs: the same step without it, the collective alone, and the other schedules ----
+    dp_report = None
+    if world > 1:
+        local_ms = timed(lambda: plan.step_fresh(True), K)
+        ar_ms = timed(lambda: ctx.allreduce_sum(slab), K)
+        modes = {}
+        for name, code in DP_MODES.items():
+            plan.set_dp(code)
+            modes[name] = world * n / (timed(step, K, drain) * 1e-3)
+        plan.set_dp(DP_MODES[args.dp_mode])
+        dp_report = dict(dp_info, allreduce_bytes=len(slab) * 8, allreduce_alone_ms=ar_ms,
+                         step_without_reduce_ms=local_ms, exposed_ms_per_step=ms_total / K - local_ms,
+                         collectives_per_step=dp_calls / K, samples_per_s_by_mode=modes, check=dp_check)
 
     # ---- roofline of the dominant kernel (the dual TMA+DMMA contraction), from the live trace ----
     gemm_ms = sum(ms_arr[i] for i in range(count.value) if kinds[i] == 0)
@@ -406,7 +416,7 @@ def gpu_arm(args):
     # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
     def pinned(count_):
         return torch.empty(count_, dtype=torch.float64).pin_memory()
-    # two sets of pinned host buffers: the N=1 path keeps two steps in flight (af_mlp_submit_host)
+    # two sets of pinned host buffers: two steps are in flight (af_mlp_submit_host)
     sets = []
     for _ in range(2):
         hx = pinned(x_host.size)
@@ -416,19 +426,21 @@ def gpu_arm(args):
         HP = C.c_void_p * P
         sets.append(dict(hx=hx, hout=pinned(n_out), hrout=pinned(n_out), hg=hg, hrg=hrg,
                          g_arr=HP(*[t.data_ptr() for t in hg]), rg_arr=HP(*[t.data_ptr() for t in hrg])))
+    # N > 1: the reduced gradient is the same on every rank, so each rank copies back only its 1/N of the block
+    # (af_mlp_set_host_shard): the host receives the full reduced gradient once per step, not N times
+    if world > 1:
+        plan.set_host_shard(True)
     h2d = x_host.size * 8
-    d2h = 2 * n_out * 8 + 2 * n_params * 8
+    d2h = 2 * n_out * 8 + (len(slab) * 8 // world if world > 1 else 2 * n_params * 8)
     e2e_k = [0]
 
     def e2e_step():
         b = sets[e2e_k[0] & 1]
         e2e_k[0] += 1
-        # the reference-facing host-buffer call, pipelined: upload of step k+1 and download of step k-1
-        # overlap the compute (and, for N > 1, the all-reduce) of step k; every step moves its own inputs and results
-        api.check(ctx.lib.af_mlp_submit_compute_host(plan.h, 1, b["hx"].data_ptr(), None, None))
-        finish_reduce()
-        api.check(ctx.lib.af_mlp_submit_download_host(plan.h, 1, b["hout"].data_ptr(), b["hrout"].data_ptr(),
-                                                      b["g_arr"], b["rg_arr"]))
+        # the reference-facing host-buffer call, pipelined: upload of step k+1 and download of step k-1 overlap the
+        # compute (and, for N > 1, the reduce) of step k; every step moves its own inputs and results
+        api.check(ctx.lib.af_mlp_submit_host(plan.h, 1, b["hx"].data_ptr(), None, None, b["hout"].data_ptr(),
+                                             b["hrout"].data_ptr(), b["g_arr"], b["rg_arr"]))
 
     def e2e_drain():
         api.check(ctx.lib.af_mlp_wait(plan.h))
@@ -442,17 +454,38 @@ def gpu_arm(args):
         e2e_step()
     e2e_drain()
     torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * K / float(e2e_s.item())
+    e2e_value = world * n * K / max_over_ranks(time.perf_counter() - t0)
+    plan.set_host_shard(False)
+    api.check(ctx.lib.af_mlp_bind_slot(plan.h, 0))
+
+    # ---- (N > 1) strong scaling: the same global problems split N ways ----
+    strong = None
+    if world > 1 and not args.no_strong:
+        strong = {}
+        try:
+            strong["mlp_global_4096"] = strong_mlp(torch, dist, ctx, api, parallel, synth, world, rank, local_rank, stream,
+                                                   LAYER_SIZES, 4096, K, args.dp_mode, max_over_ranks, barrier)
+        except Exception as e:
+            strong["mlp_global_4096"] = {"error": repr(e)[:300]}
+        plan.close()
+        plan = None
+        try:
+            strong["c5_global_65536"] = strong_mlp(torch, dist, ctx, api, parallel, synth, world, rank, local_rank, stream,
+                                                   C5_SIZES, 65536, 2, args.dp_mode, max_over_ranks, barrier, device_init=True)
+        except Exception as e:
+            strong["c5_global_65536"] = {"error": repr(e)[:300]}
 
     if rank == 0:
-        traffic = None
+        traffic, traffic_note = None, None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                if tj.get("kernel_source_sha") == af_build.kernel_source_sha():
+                    traffic = tj.get("dram_bytes_per_launch")
+                else:
+                    traffic_note = ("null: profiles/roofline_traffic.json was captured on kernel sources "
+                                    f"{tj.get('kernel_source_sha')}, this build is {af_build.kernel_source_sha()}")
             except Exception:
                 traffic = None
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
@@ -462,9 +495,13 @@ def gpu_arm(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n), "layer_sizes": LAYER_SIZES, "batch_per_gpu": n,
                        "global_batch": n * world, "parallelism": f"dp{world}",
-                       "allreduce": ("overlapped with the next step's compute (double-buffered accumulators)"
-                                     if (world > 1 and args.overlap_steps and args.overlap <= 0) else
-                                     "none" if world == 1 else "blocking, end of step"),
+                       "allreduce": "none" if world == 1 else
+                                    {"blocking": "one all-reduce of {grad|rgrad} after the backward pass, on the step's stream",
+                                     "overlap": "per-layer all-reduces on the communicator's stream beside the remaining weight-gradient "
+                                                "contractions (largest layer first), joined at the end of every step",
+                                     "deferred": "as overlap, the tail of the reduce joined before the NEXT step's accumulators are "
+                                                 "zeroed (it overlaps that step's forward pass); all reduces complete inside the "
+                                                 "timed region"}[args.dp_mode],
                        "l2": "no flush: each step streams ~%.0f MB of activations/upstreams (> 126 MB L2)" %
                              (n * sum(LAYER_SIZES) * 8 * 4 / 1e6),
                        "flops_per_sample": flops_per_sample(LAYER_SIZES)},
@@ -477,28 +514,88 @@ def gpu_arm(args):
                          "other_kernels_ms_per_step": other_ms / K,
                          "peak_source": "cuBLAS Dgemm 8192^3 (torch.matmul f64, best of 6) measured in this run; "
                                         "MEASURED_PEAKS.json has no FP64 entry",
-                         "whole_step_tflops": flops_per_sample(LAYER_SIZES) * n * K / (ms_total * 1e-3) / 1e12},
+                         "whole_step_tflops": flops_per_sample(LAYER_SIZES) * n * K / (ms_total * 1e-3) / 1e12 * world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "other_modes": other_modes,  # Run(b,false) / Run(b,true) of bench/mlp.go:29-41, resident, same batch
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
         }
+        if traffic_note:
+            line["roofline"]["traffic_note"] = traffic_note
+        if world > 1:
+            line["e2e"]["note"] = ("per rank: every rank uploads its own batch and downloads its outputs plus its 1/N of the "
+                                   "all-reduced {grad|rgrad} block (af_mlp_set_host_shard)")
+            line["data_parallel"] = dp_report
+            if strong is not None:
+                line["strong_scaling"] = strong
         if world == 1 and not args.no_cpu_baseline:
-            times = run_cpu_oracle(args.cpu_batch, 3, 1)
+            nb = args.cpu_batch or n
+            threads, sweep = cpu_thread_sweep(nb)
+            times = run_cpu_oracle(nb, 3, 1, threads)
             line["cpu_baseline"] = {
-                "value": args.cpu_batch * len(times) / sum(times), "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-                "sample": f"3 steps of {args.cpu_batch} samples (same network, same step); oracle/autofunc_ref.py "
-                          "(numpy + OpenBLAS, all host threads) -- CPU restatement, Go unavailable"}
+                "value": nb * len(times) / sum(times), "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"3 steps of {nb} samples (same network, same step, same batch); oracle/autofunc_ref.py "
+                          "(numpy + OpenBLAS at its best thread count) -- CPU restatement, Go unavailable",
+                "host_cores": host_cores(), "thread_sweep_samples_per_s": sweep}
             try:  # the weaker of the two CPU baselines SURVEY 8(d) names, for the record
-                line["other_cpu_baselines"] = {"oracle_native": run_cpu_native(min(args.cpu_batch, 256), 2, 1)}
+                line["other_cpu_baselines"] = {"oracle_native": run_cpu_native(min(nb, 256), 2, 1)}
             except Exception as e:
                 line["other_cpu_baselines"] = {"oracle_native": {"unavailable": str(e)[:200]}}
         print(json.dumps(line), flush=True)
-    plan.close()
+    if plan is not None:
+        plan.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def strong_mlp(torch, dist, ctx, api, parallel, synth, world, rank, local_rank, stream, sizes, n_global, steps, dp_mode,
+               max_over_ranks, barrier, device_init=False):
+    """Strong scaling: a FIXED global batch split over the ranks (parallel.shard_rows), the same data-parallel step."""
+    start, count = parallel.shard_rows(n_global, world, rank)
+    plan = api.MLPPlan(sizes, count, ctx)
+    try:
+        P = 2 * plan.L
+        if device_init:
+            # C5's parameters are 4 x 537 MB (+ R-vectors): filled on the device (timing only; values U[-1,1)/sqrt(K))
+            for i in range(P):
+                for ptr_of in (ctx.lib.af_mlp_param_ptr, ctx.lib.af_mlp_rvector_ptr):
+                    t = torch.as_tensor(parallel.CudaArrayView(ptr_of(plan.h, i), plan.param_len(i)), device=f"cuda:{local_rank}")
+                    with torch.cuda.stream(stream):
+                        t.uniform_(-1.0, 1.0)
+                        if i % 2 == 0 and ptr_of is ctx.lib.af_mlp_param_ptr:
+                            t.mul_(1.0 / np.sqrt(sizes[i // 2]))
+            xt = torch.as_tensor(parallel.CudaArrayView(plan.input().ptr, count * sizes[0]), device=f"cuda:{local_rank}")
+            with torch.cuda.stream(stream):
+                xt.uniform_(-1.0, 1.0)
+        else:
+            params, rvecs = synth.mlp_params(sizes)
+            for i, (p, r) in enumerate(zip(params, rvecs)):
+                plan.set_param(i, p)
+                plan.set_rvector(i, r)
+            x = synth.mlp_input(sizes, n_global).reshape(n_global, sizes[0])[start:start + count]
+            x = np.ascontiguousarray(x).reshape(-1)
+            ctx.lib.af_upload(ctx.h, plan.input().ptr, x.ctypes.data, x.size)
+        plan.set_dp(DP_MODES[dp_mode])
+        for _ in range(1 if device_init else 3):
+            plan.step_fresh_dp(True)
+        plan.dp_join()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(steps):
+            plan.step_fresh_dp(True)
+        plan.dp_join()
+        a1.record(stream)
+        barrier()
+        ms = max_over_ranks(a0.elapsed_time(a1)) / steps
+        return {"layer_sizes": sizes, "global_batch": n_global, "batch_per_gpu": count, "n_gpus": world, "steps": steps,
+                "ms_per_step": ms, "samples_per_s": n_global / (ms * 1e-3),
+                "tflops_reference_count": flops_per_sample(sizes) * n_global / (ms * 1e-3) / 1e12,
+                "allreduce_bytes": len(plan.grad_slab()) * 8, "scaling": "strong"}
+    finally:
+        plan.close()
 
 
 def main():
@@ -508,20 +605,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
-    ap.add_argument("--cpu-batch", type=int, default=1024, help="samples per CPU-oracle step (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="samples per CPU-oracle step (0 = the GPU arm's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--big-cfg", type=int, default=None, help="DMMA tile configuration for wide outputs (0 or 2)")
-    ap.add_argument("--sk-bias", type=int, default=None, help="stream-K cost in the decomposition model, percent (default: 103 for short unit ranges, 96 for long ones)")
-    ap.add_argument("--sk-rotate", type=int, default=None,
+    ap.add_argument("--big-cfg", dest="big_cfg", type=int, default=None, help="DMMA tile configuration for wide outputs (0 or 2)")
+    ap.add_argument("--sk-bias", dest="sk_bias", type=int, default=None, help="stream-K cost in the decomposition model, percent (default: 103 for short unit ranges, 96 for long ones)")
+    ap.add_argument("--sk-rotate", dest="sk_rotate", type=int, default=None,
                     help="stream-K launches walk each tile segment's k-tiles in rotated order so CTAs sweep k in lockstep (L2 reuse): 0 / 1")
-    ap.add_argument("--persist-tiles", type=int, default=None,
+    ap.add_argument("--persist-tiles", dest="persist_tiles", type=int, default=None,
                     help="multi-wave contractions as persistent CTAs over whole tiles: 0 off, 1 contiguous, 2 wave order")
-    ap.add_argument("--overlap", type=int, default=0,
-                    help="N > 1: 0 = one all-reduce after the step (default); k >= 1 = per-layer all-reduces started from the "
-                         "grad-ready hook while the backward pass runs, layer 1's weight gradient in k row chunks")
-    ap.add_argument("--overlap-steps", type=int, default=0,
-                    help="N > 1: 0 (default) = blocking all-reduce at the end of every step; 1 = double-buffered accumulators, "
-                         "the all-reduce of step k overlaps the compute of step k+1 (measured slower: 5.22 vs 5.17 ms at 8 GPUs)")
+    ap.add_argument("--dp-mode", dest="dp_mode", default="overlap", choices=sorted(DP_MODES),
+                    help="N > 1: how the library schedules the sum over ranks (include/autofunc_b200.h AF_DP_*)")
+    ap.add_argument("--dp-max-ctas", dest="dp_max_ctas", type=int, default=None, help="CTA cap of the library's NCCL communicator (default 8)")
+    ap.add_argument("--dp-reserve-sms", dest="dp_reserve_sms", type=int, default=None,
+                    help="SMs left to the overlapped all-reduce when sizing stream-K launches (default = dp_max_ctas)")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling block (n = 4096 and C5 n = 65536 split N ways)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run only the warm-up and timed steps (no other modes, peak measurement, end-to-end or CPU legs): "
                          "the command to put under ncu for a launch list of the step")

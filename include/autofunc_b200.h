@@ -37,9 +37,11 @@ extern "C" {
 #define AF_ENOMEM (-3)
 #define AF_EINVAL (-4)
 #define AF_ENOTSUP (-5)
+#define AF_ENCCL (-6)    /* the collective library failed or is missing (data-parallel entry points only) */
 
 typedef struct af_ctx af_ctx;
 typedef struct af_mlp af_mlp;
+typedef struct af_lstm af_lstm;
 
 /* ---- context / memory ------------------------------------------------------------------- */
 int af_ctx_create(int device, af_ctx** out);
@@ -86,7 +88,11 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * "sk_bias": stream-K's cost in the work-decomposition model, percent (A/B of the model's threshold).
  * "persist_tiles": 1 | 2 = multi-wave one-tile-per-CTA launches as persistent CTAs over whole tiles (measured slower; 0).
  * "small_mlp": 1 (default) = af_mlp_step with <= 4 samples runs as ONE persistent cooperative kernel
- * (all layers, both directions, grid barriers between phases); 0 = the per-kernel CUDA graph.          */
+ * (all layers, both directions, grid barriers between phases); 0 = the per-kernel CUDA graph.
+ * "dp_max_ctas": CTA cap of the context's communicator (ncclConfig_t.maxCTAs; default 8, 0 = NCCL's own choice); read by
+ * af_dp_init.  "dp_reserve_sms": SMs the plans leave to an all-reduce that runs beside their contractions (default =
+ * dp_max_ctas): stream-K launches issued while a reduce is in flight are sized for sm_count - dp_reserve_sms SMs.
+ * Plan-owned CUDA graphs captured before a change of any option are re-captured.                        */
 int af_set_option(af_ctx* ctx, const char* name, int value);
 
 int af_malloc(af_ctx* ctx, int64_t n_doubles, double** d_out);
@@ -338,6 +344,61 @@ int af_mlp_bind_slot(af_mlp*, int slot);
 typedef void (*af_grad_ready_fn)(void* user, double* d_ptr, int64_t n_doubles);
 int af_mlp_set_grad_ready(af_mlp*, af_grad_ready_fn fn, void* user, int layer1_chunks);
 
+/* ---- data parallelism: Gradient.Add across ranks (gradient.go:28-30,108-120) ---------------------
+ * The path shards over the batch: rank r holds its rows of X; parameters and R-vectors are
+ * replicated; the parameter gradients and R-gradients are SUMS over samples, so the sum of the ranks'
+ * accumulators is the full-batch gradient.  One af_ctx = one device = one rank; the transport is NCCL
+ * (ncclAllReduce, ncclDouble, ncclSum) over NVLink / NVSwitch, resolved at run time (the library loads on
+ * hosts without NCCL; the entry points below then return AF_ENCCL).
+ *   several processes, one device each : rank 0 calls af_dp_unique_id and ships the 128 bytes to the other
+ *                                        ranks by any means; every rank calls af_dp_init.
+ *   one process, several devices       : af_dp_init_local over the contexts (one per device).  Calls that
+ *                                        issue collectives must then come from one host thread per context,
+ *                                        or be bracketed by af_dp_group_begin / af_dp_group_end.          */
+#define AF_DP_ID_BYTES 128
+int af_dp_unique_id(void* id128);
+int af_dp_init(af_ctx*, int nranks, int rank, const void* id128);
+int af_dp_init_local(af_ctx* const* ctxs, int n);
+int af_dp_destroy(af_ctx*);
+int af_dp_info(af_ctx*, int* nranks, int* rank, int* nccl_version);   /* any pointer may be NULL */
+int af_dp_group_begin(void);
+int af_dp_group_end(void);
+int64_t af_dp_calls(af_ctx*);   /* collectives issued through ctx so far */
+/* d_ptr[0..n) <- sum over ranks, in place, in order on the ctx stream (asynchronous).                   */
+int af_allreduce_sum(af_ctx*, double* d_ptr, int64_t n);
+/* Plan level.  A data-parallel step = a step from FRESH (zeroed) accumulators followed by the sum of
+ * every rank's {grad | rgrad} block; how the reduce is scheduled is the plan's dp mode:
+ *   AF_DP_BLOCKING  one all-reduce of the whole block on the ctx stream after the backward pass
+ *   AF_DP_OVERLAP   (default) the backward pass runs its critical chain (input gradients) first, then the weight
+ *                   gradients largest layer first; each layer block's all-reduce starts on the communicator's own
+ *                   stream as soon as the block is complete and runs beside the remaining contractions on
+ *                   "dp_max_ctas" SMs; the ctx stream joins at the end of the step
+ *   AF_DP_DEFERRED  as AF_DP_OVERLAP, but the join is deferred to the next use of the accumulators by the library
+ *                   (af_mlp_zero_grads, the next fresh step -- which runs its forward pass first --, af_mlp_add_to_vars,
+ *                   any host download) or af_mlp_dp_join: the tail of the reduce overlaps the next forward pass.
+ * af_mlp_step_dp: af_mlp_step(with_r, backprop = 1) + the reduce; the caller zeroed the accumulators.
+ * af_mlp_step_fresh_dp: af_mlp_step_fresh + the reduce.  The host-buffer forms (af_mlp_step_host,
+ * af_mlp_submit_*_host) reduce whenever the plan's mode is not AF_DP_OFF.  Without a communicator (or with one
+ * rank) every form degenerates to its local step.                                                       */
+#define AF_DP_OFF 0
+#define AF_DP_BLOCKING 1
+#define AF_DP_OVERLAP 2
+#define AF_DP_DEFERRED 3
+int af_mlp_set_dp(af_mlp*, int mode);
+int af_mlp_step_dp(af_mlp*, int with_r);
+int af_mlp_step_fresh_dp(af_mlp*, int with_r);
+int af_mlp_dp_join(af_mlp*);    /* the ctx stream waits for the plan's outstanding reduces */
+/* The contiguous {grad | rgrad} block of the bound slot: returns its length in doubles.                 */
+int64_t af_mlp_grad_slab(af_mlp*, double** d_first);
+/* Host downloads of a data-parallel plan.  enable != 0: the host-buffer forms copy back only the part of the
+ * all-reduced {grad | rgrad} block this rank owns -- elements [rank * S / nranks, (rank + 1) * S / nranks) of the
+ * block in parameter order (gW0, gb0, rgW0, rgb0, gW1, ...), written at their usual offsets inside h_grads[i] /
+ * h_rgrads[i] -- so the reduced gradient crosses to the host once per step instead of once per rank.      */
+int af_mlp_set_host_shard(af_mlp*, int enable);
+/* One data-parallel LSTM iteration on resident data: zero the accumulators, forward, BPTT, one all-reduce of
+ * the {grad | rgrad} block on the ctx stream (the step is ~100x longer than its reduce).                  */
+int af_lstm_step_dp(af_lstm*, int with_r);
+
 /* dst[r*ld_dst + c] = src[r*ld_src + c]: the copy behind Concat / Slice of packed batches
  * (slices.go:13-119,130-206) when the parts are interleaved per sample.                          */
 int af_copy_2d(af_ctx*, double* d_dst, int64_t ld_dst, const double* d_src, int64_t ld_src, int64_t rows, int64_t cols);
@@ -349,7 +410,6 @@ int af_copy_2d(af_ctx*, double* d_dst, int64_t ld_dst, const double* d_src, int6
  * OutputWeights is O x (H+I) over concat(masked, x) (lstm.go:193).  Sequences are time-major and
  * lane-major within a step: T x B x I inputs, T x B x O outputs / upstreams (the packing
  * seqfunc.MapBatcher produces, seqfunc/map.go:262-284).                                           */
-typedef struct af_lstm af_lstm;
 int af_lstm_create(af_ctx*, int64_t input_size, int64_t hidden_size, int64_t output_size, int64_t time_steps,
                    int64_t lanes, af_lstm** out);
 int af_lstm_destroy(af_lstm*);

@@ -184,3 +184,40 @@ def test_header_is_plain_c_and_a_c_client_links(lib, tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run([exe], capture_output=True, text=True)
         assert r.returncode != 0 and "af_ctx_create" in r.stderr  # fails loudly without a GPU: no CPU fallback
+
+
+def test_variable_deserialize_rejects_truncated_buffers():
+    """DeserializeVariable (variable.go:24-37) returns an error on a short read."""
+    from autofunc_b200 import api
+    b = api.Variable(np.arange(4, dtype=np.float64)).serialize()
+    for cut in (0, 7, 8, len(b) - 1):
+        with pytest.raises(ValueError, match="truncated"):
+            api.Variable.deserialize(b[:cut])
+    assert np.array_equal(api.Variable.deserialize(b + b"tail").vector, np.arange(4.0))  # trailing bytes belong to the caller
+
+
+def test_dp_entry_points_without_a_gpu(lib):
+    """The data-parallel ABI is part of the boundary: it loads without NCCL at link time (dlopen at call time), rejects
+    bad arguments, and the 128-byte communicator id comes from the collective library, not from torch."""
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "nccl" not in out and "torch" not in out
+    assert lib.af_allreduce_sum(None, None, 4) == _lib.AF_EINVAL
+    assert lib.af_dp_init(None, 2, 0, None) == _lib.AF_EINVAL
+    assert lib.af_dp_calls(None) == 0
+    buf = C.create_string_buffer(_lib.AF_DP_ID_BYTES)
+    rc = lib.af_dp_unique_id(buf)
+    assert rc in (_lib.AF_OK, _lib.AF_ENCCL)  # AF_ENCCL: no libnccl.so.2 on this host -- a loud, typed failure
+    if rc == _lib.AF_OK:
+        assert any(buf.raw)
+    else:
+        assert b"nccl" in lib.af_last_error().lower()
+
+
+def test_roofline_traffic_is_tied_to_the_kernel_sources():
+    """bench.py reports roofline.traffic only while profiles/roofline_traffic.json matches the contraction sources."""
+    import json
+    sha = af_build.kernel_source_sha()
+    assert re.fullmatch(r"[0-9a-f]{16}", sha)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tj = json.load(open(os.path.join(root, "profiles", "roofline_traffic.json")))
+    assert "dram_bytes_per_launch" in tj and "kernel_source_sha" in tj

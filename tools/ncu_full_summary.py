@@ -63,7 +63,11 @@ def main():
         print(f"# dual contractions: {len(dual)} launches, {t:.3f} ms, mean DRAM bytes per launch {mean:.0f}, "
               f"time-weighted tensor pipe active {w:.1f} % of elapsed")
         if traffic_json:
-            json.dump({"source": title, "dram_bytes_per_launch": mean, "launches": launches}, open(traffic_json, "w"), indent=1)
+            import os
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            from autofunc_b200.build import kernel_source_sha
+            json.dump({"source": title, "kernel_source_sha": kernel_source_sha(), "dram_bytes_per_launch": mean,
+                       "launches": launches}, open(traffic_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
