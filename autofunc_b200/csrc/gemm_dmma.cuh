@@ -179,30 +179,47 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: try_wait suspends the thread for a hardware-chosen slice per attempt; after kMbarSpinFast failed attempts
-// the loop backs off with nanosleep, and after kMbarSpinLimit (seconds of wall time -- a healthy wait on a TMA tile lasts
-// microseconds) the thread traps: a TMA that faulted or a descriptor that never completes surfaces as a launch failure
-// (AF_ECUDA at the next call) instead of hanging the GPU.
-constexpr uint32_t kMbarSpinFast = 1u << 12, kMbarSpinLimit = 1u << 24;
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait: try_wait suspends the thread for a hardware-chosen slice per attempt (the back-off); after kMbarSpinLimit
+// failed attempts (seconds of wall time -- a healthy wait on a TMA tile lasts microseconds) the thread traps: a TMA that
+// faulted or a descriptor that never completes surfaces as a launch failure (AF_ECUDA at the next call) instead of hanging
+// the GPU.  The shape of the loop matters: a first version with nanosleep and two exits made ptxas wrap every wait of the
+// main loop in BSSY / BSYNC convergence barriers and cost 2.4 % of the bench step (863 k vs 884 k samples/s, A/B in
+// profiles/r02_mbar_wait_ab.txt).
+constexpr uint32_t kMbarSpinLimit = 1u << 26;
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
   asm volatile(
       "{\n"
-      ".reg .pred P1, P2;\n"
-      ".reg .u32 spins;\n"
-      "mov.u32 spins, 0;\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// the retry loop lives in its own function so that the hot path is one TRYWAIT and a not-taken branch
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  for (uint32_t left = kMbarSpinLimit; left != 0; --left)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef AF_UNBOUNDED_MBAR_WAIT  // A/B builds only: the round-1 wait loop
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
       "AF_WAIT:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
       "@P1 bra AF_DONE;\n"
-      "add.u32 spins, spins, 1;\n"
-      "setp.lt.u32 P2, spins, %2;\n"
-      "@P2 bra AF_WAIT;\n"
-      "nanosleep.u32 128;\n"
-      "setp.lt.u32 P2, spins, %3;\n"
-      "@P2 bra AF_WAIT;\n"
-      "trap;\n"
+      "bra AF_WAIT;\n"
       "AF_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity), "n"(kMbarSpinFast), "n"(kMbarSpinLimit)
+      "}\n" ::"r"(bar), "r"(parity)
       : "memory");
+  return;
+#endif
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(

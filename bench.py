@@ -287,7 +287,17 @@ def gpu_arm(args):
     slab = plan.grad_slab()
     slab_t = torch.as_tensor(parallel.CudaArrayView(slab.ptr, len(slab)), device=f"cuda:{local_rank}")
 
+    up, upr = plan.upstream(), plan.upstream_r()
+
+    def legacy_step():  # round 1's call sequence for the same iteration (A/B of the fresh-step entry point; N = 1 only)
+        plan.zero_grads()
+        api.check(ctx.lib.af_fill(ctx.h, up.ptr, 1.0, n_out))
+        api.check(ctx.lib.af_zero(ctx.h, upr.ptr, n_out))
+        plan.step(True, True)
+
     def step():
+        if args.legacy_step and world == 1:
+            return legacy_step()
         # one bench iteration as ONE library call: fresh accumulators, outGrad = 1 / outRGrad = 0, ApplyR,
         # PropagateRGradient, and (N > 1) the sum over ranks scheduled per the plan's dp mode
         plan.step_fresh_dp(True)
@@ -622,6 +632,7 @@ def main():
     ap.add_argument("--profile-step", action="store_true",
                     help="run only the warm-up and timed steps (no other modes, peak measurement, end-to-end or CPU legs): "
                          "the command to put under ncu for a launch list of the step")
+    ap.add_argument("--legacy-step", action="store_true", help="N = 1: zero_grads + fill + zero + af_mlp_step (four calls) instead of af_mlp_step_fresh_dp")
     ap.add_argument("--trace", action="store_true", help="print the last step's per-launch device times to stderr")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

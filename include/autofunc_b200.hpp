@@ -33,6 +33,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <array>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -124,6 +125,20 @@ class Context {
 };
 
 inline af_ctx* ctx() { return Context::Default().h; }
+
+// Data parallelism, one process per device (LOCAL_RANK picks the device above): rank 0 calls DPUniqueID, the 128 bytes
+// travel to the other ranks by the host's own means, every rank calls DPInit.  The gradient sum itself is
+// af_allreduce_sum / MLP::StepFreshDP / LSTM::StepDP -- Gradient.Add (gradient.go:28-30,108-120) across ranks.
+namespace b200 {
+using DPId = std::array<unsigned char, AF_DP_ID_BYTES>;
+inline DPId DPUniqueID() {
+  DPId id{};
+  check(af_dp_unique_id(id.data()));
+  return id;
+}
+inline void DPInit(int nranks, int rank, const DPId& id) { check(af_dp_init(ctx(), nranks, rank, id.data())); }
+inline void DPDestroy() { check(af_dp_destroy(ctx())); }
+}  // namespace b200
 
 class DevVec;
 using Dev = std::shared_ptr<DevVec>;
@@ -2583,6 +2598,13 @@ class MLP {
   }
   // Resident form: one bench iteration with fresh accumulators, nothing crosses PCIe.
   void StepFresh(bool withR) { check(af_mlp_step_fresh(h_, withR ? 1 : 0)); }
+  // Data parallel (Gradient.Add across ranks, gradient.go:28-30; the context joined a communicator with b200::DPInit):
+  // SetDP picks the schedule of the reduce (AF_DP_*) for the host-buffer steps; the *DP forms always reduce.
+  void SetDP(int mode) { check(af_mlp_set_dp(h_, mode)); }
+  void StepFreshDP(bool withR) { check(af_mlp_step_fresh_dp(h_, withR ? 1 : 0)); }
+  void StepDP(bool withR) { check(af_mlp_step_dp(h_, withR ? 1 : 0)); }  // accumulators zeroed by the caller
+  void DPJoin() { check(af_mlp_dp_join(h_)); }
+  void SetHostShard(bool on) { check(af_mlp_set_host_shard(h_, on ? 1 : 0)); }
   void AddToVars(double scale) { check(af_mlp_add_to_vars(h_, scale)); }  // gradient.go:40-52 in HBM
   Dev Input() { return DevVec::Wrap(af_mlp_input_ptr(h_), Batch * Sizes[0]); }
   Dev Output() { return DevVec::Wrap(af_mlp_output_ptr(h_), Batch * Sizes.back()); }
@@ -2661,6 +2683,9 @@ class LSTM {
     }
     return {std::move(out), std::move(outR)};
   }
+  // Data parallel over the lanes: fresh accumulators, forward, BPTT on resident inputs / upstreams, then the sum of
+  // the ranks' {grad | rgrad} blocks (af_lstm_step_dp).
+  void StepDP(bool withR) { check(af_lstm_step_dp(h_, withR ? 1 : 0)); }
 
  private:
   af_lstm* h_ = nullptr;

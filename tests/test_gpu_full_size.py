@@ -61,9 +61,8 @@ def _plan_for(net, I, H, O, T, B):
     return plan
 
 
-# scale 1.0 is bench/lstm.go:108,113 as written (U[-1,1) weights: with 542 inputs the gates saturate, which is what the
-# reference benchmark computes); 0.05 keeps the gates in their active range so every term of the R-backward matters
-@pytest.mark.parametrize("I,O,scale,lanes", [(30, 10, 0.05, 8), (30, 10, 1.0, 4), (512, 512, 0.03, 4)])
+# 0.05 / 0.03 keep the gates in their active range, so every term of the R-backward matters and the map is well conditioned
+@pytest.mark.parametrize("I,O,scale,lanes", [(30, 10, 0.05, 8), (512, 512, 0.03, 4)])
 def test_c4_lstm_h512_t128_matches_oracle(api, I, O, scale, lanes):
     H, T, B = 512, 128, lanes
     net = ref.LSTMNet(I, H, O, weight_scale=scale)
@@ -80,6 +79,52 @@ def test_c4_lstm_h512_t128_matches_oracle(api, I, O, scale, lanes):
             close(grads[i], grad[v], f"grad[{i}] (run {rep})")
             close(rgrads[i], rgrad[v], f"rgrad[{i}] (run {rep})")
     plan.close()
+
+
+def test_c4_lstm_reference_init_is_chaotic_and_matches_within_its_conditioning(api):
+    """bench/lstm.go:108,113 exactly as written -- U[-1,1) weights -- at H = 512: the pre-activations have a standard
+    deviation of ~8, most gates saturate and the few that do not make the recurrence CHAOTIC: perturbing the oracle's own
+    weights by one unit in the last place moves the oracle's outputs by up to 4e-3 and its R-outputs by 1e10 after 128
+    steps (measured; the first step at which the 1-ulp twin leaves the 1e-10 band is t ~ 35).  No two correct float64
+    implementations with different summation orders (gonum's blocked Dgemm vs OpenBLAS vs DMMA tiles) agree to 1e-10
+    there, the reference with itself included.  So this configuration is pinned two ways:
+      (a) strictly, at 1e-12 + 1e-10 |ref|, on the steps before the oracle's own 1-ulp twin leaves that band;
+      (b) on all 128 steps within the map's conditioning: |gpu - ref| <= tol + 1024 max|ref_twin - ref|, the maximum taken
+          over the steps so far (outputs; the divergence grows along the sequence) or over the vector (gradients)."""
+    I, H, O, T, B = 30, 512, 10, 128, 4
+    x = ref.splitmix_uniform(601, T * B * I, 0, 1).reshape(T, B, I)
+    up = ref.splitmix_uniform(602, T * B * O, 0, 1).reshape(T, B, O)
+    net = ref.LSTMNet(I, H, O, weight_scale=1.0)
+    twin = ref.LSTMNet(I, H, O, weight_scale=1.0)
+    for v in twin.variables:  # one unit in the last place, random sign
+        v.vector *= 1 + 2.2e-16 * np.sign(ref.splitmix_uniform(9, len(v.vector)))
+    with np.errstate(over="ignore"):  # exp(-z) overflows to inf for saturated gates: sigmoid = 0, as in Go
+        outs, routs, grad, rgrad = _oracle_lanes(net, x, up, None)
+        outs2, routs2, grad2, rgrad2 = _oracle_lanes(twin, x, up, None)
+    plan = _plan_for(net, I, H, O, T, B)
+    out, rout, grads, rgrads = plan.run_host(x, up, None)
+    out, rout = out.reshape(T, B, O), rout.reshape(T, B, O)
+    plan.close()
+    tol = lambda want: ATOL + RTOL * np.abs(want)
+    sens = np.abs(outs2 - outs) > tol(outs)
+    rsens = np.abs(routs2 - routs) > tol(routs)
+    t_ok = int(min(np.argmax(sens.any(axis=(1, 2))) if sens.any() else T, np.argmax(rsens.any(axis=(1, 2))) if rsens.any() else T))
+    assert t_ok >= 8, f"the oracle's 1-ulp twin already diverges at step {t_ok}"
+    close(out[:t_ok], outs[:t_ok], f"outputs, steps < {t_ok}")
+    close(rout[:t_ok], routs[:t_ok], f"R-outputs, steps < {t_ok}")
+
+    def within_conditioning(got, want, twin_val, what, by_step=False):
+        err = np.abs(np.asarray(got) - want)
+        d = np.abs(twin_val - want)
+        spread = np.maximum.accumulate(d.max(axis=(1, 2)))[:, None, None] if by_step else d.max()
+        bad = err > tol(want) + 1024 * spread
+        assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} beyond the map's conditioning; worst {err.max():.3e}"
+    within_conditioning(out, outs, outs2, "outputs, all steps", by_step=True)
+    within_conditioning(rout, routs, routs2, "R-outputs, all steps", by_step=True)
+    for i, v in enumerate(net.variables):
+        within_conditioning(grads[i], grad[v], grad2[twin.variables[i]], f"grad[{i}]")
+        within_conditioning(rgrads[i], rgrad[v], rgrad2[twin.variables[i]], f"rgrad[{i}]")
+    assert np.isfinite(out).all() and np.isfinite(rout).all()
 
 
 def test_c4_lstm_full_batch_256_lanes_against_oracle_lanes(api):
