@@ -275,6 +275,10 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->lstm_split_off = value == 0;
     return AF_OK;
   }
+  if (!strcmp(name, "lstm_fused")) {
+    ctx->lstm_fused_off = value == 0;
+    return AF_OK;
+  }
   if (!strcmp(name, "pdl")) {
     ctx->pdl_off = value == 0;
     return AF_OK;

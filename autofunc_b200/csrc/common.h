@@ -28,6 +28,7 @@ struct af_ctx {
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu
   bool lstm_split_off = true;   // opt-in (af_set_option "lstm_split" 1): two concurrent half-batch kernel chains; measured 24.6 vs 24.2 ms
+  bool lstm_fused_off = false;  // A/B switch (af_set_option "lstm_fused" 0): the per-kernel LSTM steps of round 1
   bool pdl = false;      // inside a dependent-kernel chain (LSTM time loops): launch with programmatic stream serialization
   bool pdl_off = true;   // opt-in (af_set_option "pdl" 1): measured 24.6 vs 24.25 ms on the C4 LSTM, so off by default
   unsigned* barrier_word = nullptr;  // grid-barrier counter of the persistent small-batch kernel
@@ -148,6 +149,12 @@ struct GemmEpilogue {
 // acc0 = A0 B0^T ; acc1 = A0 B1^T + A1 B0^T (dual when `dual`), I x J, contraction Kd
 int gemm_launch(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool dual, long long I, long long J,
                 long long Kd, const GemmEpilogue& e);
+
+// TMA descriptors (gemm.cu).  layout LAY_KC: element (r,k) at p[r*ld + k] -> box {16, tile_rows}; LAY_RC: element (r,k) at
+// p[k*ld + r] -> box {16, 16}.  gemm_make_gate_map: the stacked LSTM gate matrix as the 4-D tensor of a forward-step tile.
+int gemm_make_map(af_ctx* ctx, CUtensorMap* map, const double* p, int layout, long long rows, long long kd, long long ld,
+                  int tile_rows);
+int gemm_make_gate_map(af_ctx* ctx, CUtensorMap* map, const double* w4, long long H, long long C);
 
 // small-batch (n <= 16) streaming kernels, small_n.cu: the reference's Gemv / Ger branch
 bool small_n_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs,

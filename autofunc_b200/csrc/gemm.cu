@@ -27,6 +27,13 @@ bool tma_compatible(const double* p, long long ld, long long rows, long long kd)
 // RC: element (r,k) at p[k*ld + r] -> dims {R, Kd}, box {16, 16}
 int make_map(af_ctx* ctx, CUtensorMap* map, const double* p, int layout, long long rows, long long kd, long long ld,
              int tile_rows) {
+  return gemm_make_map(ctx, map, p, layout, rows, kd, ld, tile_rows);
+}
+
+}  // namespace
+
+int gemm_make_map(af_ctx* ctx, CUtensorMap* map, const double* p, int layout, long long rows, long long kd, long long ld,
+                  int tile_rows) {
   cuuint64_t dims[2];
   cuuint32_t box[2];
   if (layout == LAY_KC) {
@@ -45,6 +52,25 @@ int make_map(af_ctx* ctx, CUtensorMap* map, const double* p, int layout, long lo
   if (r != CUDA_SUCCESS) return fail(AF_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return AF_OK;
 }
+
+// The stacked LSTM gate matrix W4 (4H x C, gate-major rows: bench/lstm.go's four H x C matrices one after another) as a
+// 3-D tensor {k, unit, gate} with box {16, 16, 4}: one box = the 64 rows {4 gates} x {16 units} of a forward-step tile
+// (gemm_dmma_kernel SPECIAL = 1), landing in shared memory as 64 consecutive 128-byte lines exactly like a KC tile.
+// Only the first H columns (the state part of concat(state, x)) are mapped.
+int gemm_make_gate_map(af_ctx* ctx, CUtensorMap* map, const double* w4, long long H, long long C) {
+  cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)H, 4};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 8, (cuuint64_t)H * C * 8};
+  cuuint32_t box[3] = {kBK, 16, 4};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(w4), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AF_ECUDA, "cuTensorMapEncodeTiled (gate map) failed with CUresult " + std::to_string((int)r));
+  return AF_OK;
+}
+
+namespace {
 
 // algorithmic flops of one launch: 2 I J Kd per product that the reference would also compute
 double gemm_flops(const GemmArgs& a, bool dual) {

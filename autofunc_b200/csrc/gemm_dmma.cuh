@@ -54,6 +54,25 @@ enum : int {
   EPI_ACCUM_ATOMIC = 5,  // out += acc with red.global.add.f64 (split-K)
 };
 
+// Operands of the fused LSTM step epilogues (SPECIAL = 1 / 2 below; lstm_step.cu).  Everything is one time step's
+// slice; `ld` is the row pitch of the [state | x] buffers IN / AUG / DAUG (= H + I), gate buffers have pitch 4H.
+struct LstmStepArgs {
+  int H, ld;
+  // forward (bench/lstm.go:139-151,183-191): G / RG hold x W_x^T + b (and the R form) on entry, the activated gates
+  // on exit; INp = state entering the step, INn = state leaving it, AUG = masked state (input of the output layer)
+  double* G; double* RG;
+  const double* INp; const double* RINp;
+  double* INn; double* RINn; double* AUG; double* RAUG;
+  // backward (bench/lstm.go:215-234): the contraction adds delta4_t W_h to SGF (= sg f of step t), and the epilogue
+  // runs the cell backward of step t - 1 on the completed state gradient: Gm / RGm = gates of step t - 1,
+  // INm / INt = state entering / leaving step t - 1, DAUGm = gradient toward its masked state; it writes
+  // delta4_{t-1} to D4m / RD4m and the new sg f back to SGF / RSGF (pitch H)
+  const double* Gm; const double* RGm;
+  const double* INm; const double* RINm; const double* INt; const double* RINt;
+  const double* DAUGm; const double* RDAUGm;
+  double* SGF; double* RSGF; double* D4m; double* RD4m;
+};
+
 struct GemmArgs {
   int I, J, Kd;
   int has_a1, has_b1;  // R operands present (NULL R-vector == zero, variable.go:85-91)
@@ -77,12 +96,75 @@ struct GemmArgs {
   const double* s;
   const double* rs;
   long long lds;
+  LstmStepArgs lstm;
 };
 
 // ---------------------------------------------------------------------------------------------
 // epilogue element functions (shared by the DMMA kernel and the generic kernel)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double sigmoid_f64(double z) { return 1.0 / (1.0 + exp(-z)); }
+
+// ---- LSTM cell algebra, one (lane, hidden unit) element; shared by the fused step epilogues and the stand-alone
+//      cell kernels of lstm.cu so that both paths evaluate the same expressions in the same order -------------------
+// forward: zi..zo = the four gates' pre-activations (contraction + x projection + bias), rz* their R forms
+//   s = f sp + m i            Add(Mul(forget, state), Mul(inMask, inState))   bench/lstm.go:147-150
+//   masked = s o              Mul(outStateVar, outGate)                       bench/lstm.go:191
+// R forms follow MulR (arithmetic.go:325-329: x yR + xR y), AddR (:58-65) and the sigmoid's (math_funcs.go:305-309).
+struct LstmCellFwd {
+  double i, m, f, o, s, masked;
+  double ri, rm, rf, ro, rs, rmasked;
+};
+template <bool R>
+__device__ __forceinline__ LstmCellFwd lstm_cell_fwd(double zi, double zm, double zf, double zo, double sp, double rzi,
+                                                     double rzm, double rzf, double rzo, double rsp) {
+  LstmCellFwd c;
+  c.i = sigmoid_f64(zi); c.m = sigmoid_f64(zm); c.f = sigmoid_f64(zf); c.o = sigmoid_f64(zo);
+  c.s = c.f * sp + c.m * c.i;
+  c.masked = c.s * c.o;
+  if (R) {
+    c.ri = c.i * (1 - c.i) * rzi; c.rm = c.m * (1 - c.m) * rzm;
+    c.rf = c.f * (1 - c.f) * rzf; c.ro = c.o * (1 - c.o) * rzo;
+    c.rs = (c.f * rsp + c.rf * sp) + (c.m * c.ri + c.rm * c.i);
+    c.rmasked = c.s * c.ro + c.rs * c.o;
+  }
+  return c;
+}
+// backward (bench/lstm.go:215-234 with the node backwards of arithmetic.go:34-49,288-306 / 79-96,349-376 and
+// math_funcs.go:326-333 / 357-374 inlined):  carry = state gradient arriving from step t + 1
+//   sg  = carry + dmask o                 (grad[outStateVar] added to stateGrad, lstm.go:227-228)
+//   do  = dmask s                         -> delta_o = sigmoid'(o) do
+//   dm  = sg i ; di = sg m ; df = sg sp   -> delta_* = sigmoid'(gate) d*
+//   sgf = sg f                            (Mul(forget, state) toward the state)
+struct LstmCellBwd {
+  double di, dm, df, d_o, sgf;
+  double rdi, rdm, rdf, rd_o, rsgf;
+};
+template <bool R>
+__device__ __forceinline__ LstmCellBwd lstm_cell_bwd(double i, double m, double f, double o, double sp, double s,
+                                                     double dmask, double carry, double ri, double rm, double rf, double ro,
+                                                     double rsp, double rs, double rdmask, double rcarry) {
+  LstmCellBwd c;
+  const double sg = carry + dmask * o;
+  const double d_o = dmask * s, d_m = sg * i, d_i = sg * m, d_f = sg * sp;
+  c.di = i * (1 - i) * d_i;
+  c.dm = m * (1 - m) * d_m;
+  c.df = f * (1 - f) * d_f;
+  c.d_o = o * (1 - o) * d_o;
+  c.sgf = sg * f;
+  if (R) {
+    // downstreamR = u otherR + uR other (arithmetic.go:358-362)
+    const double rsg = rcarry + (dmask * ro + rdmask * o);
+    const double rd_o = dmask * rs + rdmask * s;
+    const double rd_m = sg * ri + rsg * i, rd_i = sg * rm + rsg * m, rd_f = sg * rsp + rsg * sp;
+    // sigmoid R-backward, operand order of math_funcs.go:369-370
+    c.rdi = ri * (1 - i) * d_i - i * ri * d_i + i * (1 - i) * rd_i;
+    c.rdm = rm * (1 - m) * d_m - m * rm * d_m + m * (1 - m) * rd_m;
+    c.rdf = rf * (1 - f) * d_f - f * rf * d_f + f * (1 - f) * rd_f;
+    c.rd_o = ro * (1 - o) * d_o - o * ro * d_o + o * (1 - o) * rd_o;
+    c.rsgf = sg * rf + rsg * f;
+  }
+  return c;
+}
 
 template <bool DUAL>
 __device__ __forceinline__ void epi_transform(const GemmArgs& p, long long i, int j, double& v0, double& v1) {
@@ -227,6 +309,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// thread-block cluster helpers (SPECIAL = 2: split-K over a cluster, partial tiles exchanged through DSMEM)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local` (a shared::cta address of this CTA's window) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local, uint32_t rank) {
+  uint32_t a;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(local), "r"(rank));
+  return a;
+}
+__device__ __forceinline__ void dsmem_st_f64(uint32_t addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -269,6 +376,11 @@ struct GemmSmem {
   static constexpr int kThreads = kWarps * 32;
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   static constexpr uint32_t kTotal = kBarOffset + 2 * kStages * 8 + 1024;  // + alignment slack
+  // SPECIAL = 2: exchange buffer of the cluster split-K, [source CTA][value][lane] doubles, after the barriers
+  static constexpr int kSplit = 4;
+  static constexpr uint32_t kXchgOffset = kBarOffset + 128;
+  static constexpr uint32_t kXchgBytes = kSplit * NACC * T::TI * T::TJ * 2 * 32 * 8;
+  static constexpr uint32_t kTotalCluster = kXchgOffset + kXchgBytes + 1024;
   static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "swizzle atoms must stay 1024-byte aligned");
   static_assert((T::TI == 1 || (T::TI * 8) % 16 == 0) && (T::TJ == 1 || (T::TJ * 8) % 16 == 0), "frag_addr assumes 16-row alignment");
 };
@@ -310,8 +422,17 @@ __device__ __forceinline__ uint32_t frag_addr(uint32_t base, int t) {
 // prefetch run across tile boundaries, so a new tile's pipeline fill overlaps the previous tile's math.
 // MULTI = false: the CTA's range lies inside one tile (one tile per CTA, or aligned split-K): one segment, one
 // epilogue after the loop -- the leanest code.  MULTI = true: stream-K, the range may span tiles.
-template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI>
-__global__ void __launch_bounds__(TileCfg<CFG>::WI * TileCfg<CFG>::WJ * 32, TileCfg<CFG>::MIN_CTAS)
+// SPECIAL (lstm_step.cu; one tile per CTA / aligned split only, CFG 2):
+//   1  LSTM forward step.  B is the stacked gate matrix read through a 3-D tensor map {k, unit, gate} so that the 64 rows
+//      of a tile are {4 gates} x {16 hidden units}, and warp column wj's accumulator block u covers gate u of units
+//      8 wj .. 8 wj + 7: every thread's accumulators then hold all four gates of its (lane, unit) elements and the epilogue is the whole cell (bias + x projection read from G, sigmoids, Mul / Add,
+//      new state, masked state) -- the step is ONE kernel, nothing is accumulated atomically, no gate buffer is zeroed.
+//   2  LSTM backward step.  The contraction over the 4H gate rows is split over a CLUSTER of kSplit CTAs (aligned
+//      split-K: CTA r of the cluster takes k-tiles [r kt/4, (r+1) kt/4)); every CTA sends warp w's partial accumulators
+//      to CTA w through distributed shared memory, and CTA w adds the four partials in rank order (deterministic, no
+//      atomics, no zeroing) and runs the cell backward of the previous time step on its 32 x 32 quarter of the tile.
+template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI, int SPECIAL = 0>
+__global__ void __launch_bounds__(TileCfg<CFG>::WI * TileCfg<CFG>::WJ * 32, SPECIAL == 2 ? 1 : TileCfg<CFG>::MIN_CTAS)
 gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs p) {
   using L = GemmSmem<NACC, CFG>;
@@ -374,9 +495,14 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int k0 = p_kt * kBK, i0 = p_ti * BM, j0 = p_tj * BN;
     mbar_expect_tx(full, tx_bytes);
     tma_load_tile<ALAY, BM>(st + L::kA0, &tmA0, full, i0, k0);
-    tma_load_tile<BLAY, BN>(st + L::kB0, &tmB0, full, j0, k0);
+    if (SPECIAL == 1) {  // rows of the tile = {4 gates} x {16 hidden units}: box {16 k, 16 units, 4 gates}
+      tma_load_3d(st + L::kB0, &tmB0, full, k0, p_tj * 16, 0);
+      if (has_b1) tma_load_3d(st + L::kB1, &tmB1, full, k0, p_tj * 16, 0);
+    } else {
+      tma_load_tile<BLAY, BN>(st + L::kB0, &tmB0, full, j0, k0);
+      if (has_b1) tma_load_tile<BLAY, BN>(st + L::kB1, &tmB1, full, j0, k0);
+    }
     if (has_a1) tma_load_tile<ALAY, BM>(st + L::kA1, &tmA1, full, i0, k0);
-    if (has_b1) tma_load_tile<BLAY, BN>(st + L::kB1, &tmB1, full, j0, k0);
     ++p_kt;
     if (MULTI) {
       if (p_kt == p_b + p_len) p_kt = p_b;  // wrap inside the segment (a rotated walk; otherwise the segment ends here)
@@ -407,7 +533,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       fa[s] = frag_base<ALAY>(wi0, g, kj ^ ms[s]);
-      fb[s] = frag_base<BLAY>(wj0, g, kj ^ ms[s]);
+      fb[s] = frag_base<BLAY>(SPECIAL == 1 ? (warp % T::WJ) * 8 : wj0, g, kj ^ ms[s]);
     }
   }
 
@@ -431,14 +557,15 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
     for (int t = 0; t < TI; ++t) a0[buf][t] = lds_f64(st + L::kA0 + frag_addr<ALAY>(fa[ks], t));
 #pragma unroll
-    for (int u = 0; u < TJ; ++u) b0[buf][u] = lds_f64(st + L::kB0 + frag_addr<BLAY>(fb[ks], u));
+    for (int u = 0; u < TJ; ++u) b0[buf][u] = lds_f64(st + L::kB0 + (SPECIAL == 1 ? fb[ks] + u * 2048 : frag_addr<BLAY>(fb[ks], u)));
     if (has_a1) {
 #pragma unroll
       for (int t = 0; t < TI; ++t) a1[buf][DUAL ? t : 0] = lds_f64(st + L::kA1 + frag_addr<ALAY>(fa[ks], t));
     }
     if (has_b1) {
 #pragma unroll
-      for (int u = 0; u < TJ; ++u) b1[buf][DUAL ? u : 0] = lds_f64(st + L::kB1 + frag_addr<BLAY>(fb[ks], u));
+      for (int u = 0; u < TJ; ++u)
+        b1[buf][DUAL ? u : 0] = lds_f64(st + L::kB1 + (SPECIAL == 1 ? fb[ks] + u * 2048 : frag_addr<BLAY>(fb[ks], u)));
     }
   };
   auto mma_step = [&](int buf) {
@@ -468,16 +595,144 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   auto flush = [&](int q) {
     const int tile = tile_of(q);
     const int i0 = (tile / p.tiles_j) * BM, j0 = (tile % p.tiles_j) * BN;
+    if constexpr (SPECIAL == 1) {
+      // ---- LSTM forward cell (see LstmStepArgs): accumulator block u of this thread IS gate u of its two units ----
+      static_assert(SPECIAL != 1 || (TJ == 4 && T::WJ == 2 && BLAY == LAY_KC), "the gate layout assumes 4 blocks of 8 units per warp");
+      const LstmStepArgs& c = p.lstm;
+      const int H = c.H;
+      const int unit = (tile % p.tiles_j) * 16 + (warp % T::WJ) * 8 + 2 * j4;  // and unit + 1
 #pragma unroll
-    for (int t = 0; t < TI; ++t) {
-      const long long i = i0 + wi0 + 8 * t + g;
+      for (int t = 0; t < TI; ++t) {
+        const long long i = i0 + wi0 + 8 * t + g;
+        if (i < p.I) {
+          double* gp = c.G + i * 4 * H + unit;
+          const long long si = i * c.ld + unit;
+          double2 z[4], rz[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double2 x = *reinterpret_cast<const double2*>(gp + u * H);  // x W_x^T + b of gate u
+            z[u] = make_double2(acc0[t][u][0] + x.x, acc0[t][u][1] + x.y);
+            if (DUAL) {
+              const double2 rx = *reinterpret_cast<const double2*>(c.RG + i * 4 * H + unit + u * H);
+              rz[u] = make_double2(acc1[DUAL ? t : 0][u][0] + rx.x, acc1[DUAL ? t : 0][u][1] + rx.y);
+            } else {
+              rz[u] = make_double2(0.0, 0.0);
+            }
+          }
+          const double2 sp = *reinterpret_cast<const double2*>(c.INp + si);
+          const double2 rsp = DUAL ? *reinterpret_cast<const double2*>(c.RINp + si) : make_double2(0.0, 0.0);
+          const LstmCellFwd a = lstm_cell_fwd<DUAL>(z[0].x, z[1].x, z[2].x, z[3].x, sp.x, rz[0].x, rz[1].x, rz[2].x, rz[3].x, rsp.x);
+          const LstmCellFwd b = lstm_cell_fwd<DUAL>(z[0].y, z[1].y, z[2].y, z[3].y, sp.y, rz[0].y, rz[1].y, rz[2].y, rz[3].y, rsp.y);
+          *reinterpret_cast<double2*>(gp) = make_double2(a.i, b.i);
+          *reinterpret_cast<double2*>(gp + H) = make_double2(a.m, b.m);
+          *reinterpret_cast<double2*>(gp + 2 * H) = make_double2(a.f, b.f);
+          *reinterpret_cast<double2*>(gp + 3 * H) = make_double2(a.o, b.o);
+          *reinterpret_cast<double2*>(c.INn + si) = make_double2(a.s, b.s);
+          *reinterpret_cast<double2*>(c.AUG + si) = make_double2(a.masked, b.masked);
+          if (DUAL) {
+            double* rgp = c.RG + i * 4 * H + unit;
+            *reinterpret_cast<double2*>(rgp) = make_double2(a.ri, b.ri);
+            *reinterpret_cast<double2*>(rgp + H) = make_double2(a.rm, b.rm);
+            *reinterpret_cast<double2*>(rgp + 2 * H) = make_double2(a.rf, b.rf);
+            *reinterpret_cast<double2*>(rgp + 3 * H) = make_double2(a.ro, b.ro);
+            *reinterpret_cast<double2*>(c.RINn + si) = make_double2(a.rs, b.rs);
+            *reinterpret_cast<double2*>(c.RAUG + si) = make_double2(a.rmasked, b.rmasked);
+          }
+        }
+      }
+      return;
+    }
+    if constexpr (SPECIAL == 2) {
+      // ---- cluster split-K: exchange the partial tiles through DSMEM, then the LSTM cell backward ----
+      static_assert(SPECIAL != 2 || (kConsumerWarps == L::kSplit && TI == L::kSplit), "one quarter per warp, one t per warp");
+      constexpr int NV1 = TI * TJ * 2, NV = NACC * NV1;
+      const LstmStepArgs& c = p.lstm;
+      const uint32_t xchg = base + L::kXchgOffset;
+      const uint32_t rank = cluster_ctarank();
+      cluster_sync();  // every CTA of the cluster is running and past its main loop: exchange buffers may be written
+      {
+        // warp w holds the partial sums of quarter w of the tile: they go to CTA w, slot `rank`, as [value][lane]
+        const uint32_t dst = dsmem_addr(xchg, (uint32_t)warp) + (rank * NV * 32 + lane) * 8;
+#pragma unroll
+        for (int t = 0; t < TI; ++t)
+#pragma unroll
+          for (int u = 0; u < TJ; ++u)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int v = (t * TJ + u) * 2 + e;
+              dsmem_st_f64(dst + v * 256, acc0[t][u][e]);
+              if (DUAL) dsmem_st_f64(dst + (NV1 + v) * 256, acc1[DUAL ? t : 0][u][e]);
+            }
+      }
+      cluster_sync();  // all partials have landed (release / acquire at cluster scope)
+      // this CTA finishes quarter `rank`; its warp w takes the rows t == w of that quarter's fragments
+      const int H = c.H;
+      const int t = warp;
+      const long long i = i0 + (int)(rank / T::WJ) * (TI * 8) + 8 * t + g;
       if (i < p.I) {
 #pragma unroll
         for (int u = 0; u < TJ; ++u) {
-          const int j = j0 + wj0 + 8 * u + 2 * j4;
-          if (j < p.J)
-            epi_pair<DUAL>(p, vec_ok, i, j, acc0[t][u][0], acc0[t][u][1], DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0,
-                           DUAL ? acc1[DUAL ? t : 0][u][1] : 0.0);
+          const int j = j0 + (int)(rank % T::WJ) * (TJ * 8) + 8 * u + 2 * j4;  // and j + 1
+          if (j >= p.J) continue;
+          double s0[2], s1[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int v = (t * TJ + u) * 2 + e;
+            double a = 0.0, r = 0.0;
+#pragma unroll
+            for (int src = 0; src < L::kSplit; ++src) {  // rank order: the sum is the same on every run
+              a += lds_f64(xchg + ((src * NV + v) * 32 + lane) * 8);
+              if (DUAL) r += lds_f64(xchg + ((src * NV + NV1 + v) * 32 + lane) * 8);
+            }
+            s0[e] = a; s1[e] = r;
+          }
+          const long long ei = i * H + j, gi = i * 4 * H + j, si = i * c.ld + j;
+          const double2 carry = *reinterpret_cast<const double2*>(c.SGF + ei);
+          const double2 gI = *reinterpret_cast<const double2*>(c.Gm + gi), gM = *reinterpret_cast<const double2*>(c.Gm + gi + H);
+          const double2 gF = *reinterpret_cast<const double2*>(c.Gm + gi + 2 * H), gO = *reinterpret_cast<const double2*>(c.Gm + gi + 3 * H);
+          const double2 sp = *reinterpret_cast<const double2*>(c.INm + si), sn = *reinterpret_cast<const double2*>(c.INt + si);
+          const double2 dm = *reinterpret_cast<const double2*>(c.DAUGm + si);
+          double2 rcarry, rI, rM, rF, rO, rsp, rsn, rdm;
+          rcarry = rI = rM = rF = rO = rsp = rsn = rdm = make_double2(0.0, 0.0);
+          if (DUAL) {
+            rcarry = *reinterpret_cast<const double2*>(c.RSGF + ei);
+            rI = *reinterpret_cast<const double2*>(c.RGm + gi); rM = *reinterpret_cast<const double2*>(c.RGm + gi + H);
+            rF = *reinterpret_cast<const double2*>(c.RGm + gi + 2 * H); rO = *reinterpret_cast<const double2*>(c.RGm + gi + 3 * H);
+            rsp = *reinterpret_cast<const double2*>(c.RINm + si); rsn = *reinterpret_cast<const double2*>(c.RINt + si);
+            rdm = *reinterpret_cast<const double2*>(c.RDAUGm + si);
+          }
+          const LstmCellBwd a = lstm_cell_bwd<DUAL>(gI.x, gM.x, gF.x, gO.x, sp.x, sn.x, dm.x, carry.x + s0[0], rI.x, rM.x, rF.x, rO.x,
+                                                    rsp.x, rsn.x, rdm.x, rcarry.x + s1[0]);
+          const LstmCellBwd b = lstm_cell_bwd<DUAL>(gI.y, gM.y, gF.y, gO.y, sp.y, sn.y, dm.y, carry.y + s0[1], rI.y, rM.y, rF.y, rO.y,
+                                                    rsp.y, rsn.y, rdm.y, rcarry.y + s1[1]);
+          *reinterpret_cast<double2*>(c.D4m + gi) = make_double2(a.di, b.di);
+          *reinterpret_cast<double2*>(c.D4m + gi + H) = make_double2(a.dm, b.dm);
+          *reinterpret_cast<double2*>(c.D4m + gi + 2 * H) = make_double2(a.df, b.df);
+          *reinterpret_cast<double2*>(c.D4m + gi + 3 * H) = make_double2(a.d_o, b.d_o);
+          *reinterpret_cast<double2*>(c.SGF + ei) = make_double2(a.sgf, b.sgf);
+          if (DUAL) {
+            *reinterpret_cast<double2*>(c.RD4m + gi) = make_double2(a.rdi, b.rdi);
+            *reinterpret_cast<double2*>(c.RD4m + gi + H) = make_double2(a.rdm, b.rdm);
+            *reinterpret_cast<double2*>(c.RD4m + gi + 2 * H) = make_double2(a.rdf, b.rdf);
+            *reinterpret_cast<double2*>(c.RD4m + gi + 3 * H) = make_double2(a.rd_o, b.rd_o);
+            *reinterpret_cast<double2*>(c.RSGF + ei) = make_double2(a.rsgf, b.rsgf);
+          }
+        }
+      }
+      return;
+    }
+    if constexpr (SPECIAL == 0) {
+#pragma unroll
+      for (int t = 0; t < TI; ++t) {
+        const long long i = i0 + wi0 + 8 * t + g;
+        if (i < p.I) {
+#pragma unroll
+          for (int u = 0; u < TJ; ++u) {
+            const int j = j0 + wj0 + 8 * u + 2 * j4;
+            if (j < p.J)
+              epi_pair<DUAL>(p, vec_ok, i, j, acc0[t][u][0], acc0[t][u][1], DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0,
+                             DUAL ? acc1[DUAL ? t : 0][u][1] : 0.0);
+          }
         }
       }
     }

@@ -21,6 +21,11 @@
 #include "gemm_dmma.cuh"
 
 namespace af {
+bool lstm_fused_applicable(af_ctx* ctx, long long H, long long C, long long B);
+int lstm_fwd_step_launch(af_ctx* ctx, const double* W4, const double* RW4, const LstmStepArgs& st, bool with_r, bool r_state,
+                         long long nb);
+int lstm_bwd_step_launch(af_ctx* ctx, const double* D4, const double* RD4, const double* W4, const double* RW4,
+                         const LstmStepArgs& st, bool with_r, long long nb);
 int colsum_launch(af_ctx* ctx, const double* U, const double* UR, double* gb, double* rgb, long long len, long long n);
 
 namespace {
@@ -53,23 +58,24 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(double* __restrict__
   for (int e = blockIdx.x * 256 + threadIdx.x; e < n; e += gridDim.x * 256) {
     const int b = e / H, j = e - b * H;
     double* g = G + (long long)b * 4 * H;
-    const double i = sigmoid_f64(g[j] + b4[j]), m = sigmoid_f64(g[H + j] + b4[H + j]);
-    const double f = sigmoid_f64(g[2 * H + j] + b4[2 * H + j]), o = sigmoid_f64(g[3 * H + j] + b4[3 * H + j]);
-    g[j] = i; g[H + j] = m; g[2 * H + j] = f; g[3 * H + j] = o;
     const long long si = (long long)b * ld + j;
-    const double sp = INp[si];
-    const double s = f * sp + m * i;
-    INn[si] = s;
-    AUG[si] = s * o;
+    double rz[4] = {0.0, 0.0, 0.0, 0.0};
+    double* rg = RG ? RG + (long long)b * 4 * H : nullptr;
     if (RG) {
-      double* rg = RG + (long long)b * 4 * H;
-      const double ri = i * (1 - i) * (rg[j] + Rb4[j]), rm = m * (1 - m) * (rg[H + j] + Rb4[H + j]);
-      const double rf = f * (1 - f) * (rg[2 * H + j] + Rb4[2 * H + j]), ro = o * (1 - o) * (rg[3 * H + j] + Rb4[3 * H + j]);
-      rg[j] = ri; rg[H + j] = rm; rg[2 * H + j] = rf; rg[3 * H + j] = ro;
-      const double rsp = RINp[si];
-      const double rs = (f * rsp + rf * sp) + (m * ri + rm * i);
-      RINn[si] = rs;
-      RAUG[si] = s * ro + rs * o;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rz[u] = rg[u * H + j] + Rb4[u * H + j];
+    }
+    const double z0 = g[j] + b4[j], z1 = g[H + j] + b4[H + j], z2 = g[2 * H + j] + b4[2 * H + j], z3 = g[3 * H + j] + b4[3 * H + j];
+    if (RG) {
+      const LstmCellFwd c = lstm_cell_fwd<true>(z0, z1, z2, z3, INp[si], rz[0], rz[1], rz[2], rz[3], RINp[si]);
+      g[j] = c.i; g[H + j] = c.m; g[2 * H + j] = c.f; g[3 * H + j] = c.o;
+      INn[si] = c.s; AUG[si] = c.masked;
+      rg[j] = c.ri; rg[H + j] = c.rm; rg[2 * H + j] = c.rf; rg[3 * H + j] = c.ro;
+      RINn[si] = c.rs; RAUG[si] = c.rmasked;
+    } else {
+      const LstmCellFwd c = lstm_cell_fwd<false>(z0, z1, z2, z3, INp[si], 0.0, 0.0, 0.0, 0.0, 0.0);
+      g[j] = c.i; g[H + j] = c.m; g[2 * H + j] = c.f; g[3 * H + j] = c.o;
+      INn[si] = c.s; AUG[si] = c.masked;
     }
   }
 }
@@ -94,29 +100,17 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(
     const int b = e / H, j = e - b * H;
     const long long gi = (long long)b * 4 * H, si = (long long)b * ld + j;
     const double i = G[gi + j], m = G[gi + H + j], f = G[gi + 2 * H + j], o = G[gi + 3 * H + j];
-    const double sp = INp[si], s = INn[si];
-    const double dmask = DAUG[si];
-    const double sg = SG[e] + dmask * o;
-    const double d_o = dmask * s, d_m = sg * i, d_i = sg * m, d_f = sg * sp;
-    D4[gi + j] = i * (1 - i) * d_i;
-    D4[gi + H + j] = m * (1 - m) * d_m;
-    D4[gi + 2 * H + j] = f * (1 - f) * d_f;
-    D4[gi + 3 * H + j] = o * (1 - o) * d_o;
-    SGn[e] = sg * f;
     if (RG) {
-      const double ri = RG[gi + j], rm = RG[gi + H + j], rf = RG[gi + 2 * H + j], ro = RG[gi + 3 * H + j];
-      const double rsp = RINp[si], rs = RINn[si];
-      const double rdmask = RDAUG[si];
-      // downstreamR = u*otherR + uR*other (arithmetic.go:358-362)
-      const double rsg = RSG[e] + (dmask * ro + rdmask * o);
-      const double rd_o = dmask * rs + rdmask * s;
-      const double rd_m = sg * ri + rsg * i, rd_i = sg * rm + rsg * m, rd_f = sg * rsp + rsg * sp;
-      // sigmoid R-backward, operand order of math_funcs.go:369-370
-      RD4[gi + j] = ri * (1 - i) * d_i - i * ri * d_i + i * (1 - i) * rd_i;
-      RD4[gi + H + j] = rm * (1 - m) * d_m - m * rm * d_m + m * (1 - m) * rd_m;
-      RD4[gi + 2 * H + j] = rf * (1 - f) * d_f - f * rf * d_f + f * (1 - f) * rd_f;
-      RD4[gi + 3 * H + j] = ro * (1 - o) * d_o - o * ro * d_o + o * (1 - o) * rd_o;
-      RSGn[e] = sg * rf + rsg * f;
+      const LstmCellBwd c = lstm_cell_bwd<true>(i, m, f, o, INp[si], INn[si], DAUG[si], SG[e], RG[gi + j], RG[gi + H + j],
+                                                RG[gi + 2 * H + j], RG[gi + 3 * H + j], RINp[si], RINn[si], RDAUG[si], RSG[e]);
+      D4[gi + j] = c.di; D4[gi + H + j] = c.dm; D4[gi + 2 * H + j] = c.df; D4[gi + 3 * H + j] = c.d_o;
+      SGn[e] = c.sgf;
+      RD4[gi + j] = c.rdi; RD4[gi + H + j] = c.rdm; RD4[gi + 2 * H + j] = c.rdf; RD4[gi + 3 * H + j] = c.rd_o;
+      RSGn[e] = c.rsgf;
+    } else {
+      const LstmCellBwd c = lstm_cell_bwd<false>(i, m, f, o, INp[si], INn[si], DAUG[si], SG[e], 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0);
+      D4[gi + j] = c.di; D4[gi + H + j] = c.dm; D4[gi + 2 * H + j] = c.df; D4[gi + 3 * H + j] = c.d_o;
+      SGn[e] = c.sgf;
     }
   }
 }
@@ -412,10 +406,23 @@ static int lstm_forward_launches(af_lstm* m, int with_r) {
   const int64_t H = m->H, C = m->C, B = m->B, T = m->T, O = m->O;
   const bool R = with_r != 0;
   const int64_t BC = B * C;
-  // the gate sums of every step are accumulated into zeroed buffers when the contraction is split: clear all
-  // T steps at once instead of two memsets per step
-  AF_CUDA(cudaMemsetAsync(m->G, 0, (size_t)(T * B * 4 * H) * 8, ctx->stream));
-  if (R) AF_CUDA(cudaMemsetAsync(m->RG, 0, (size_t)(T * B * 4 * H) * 8, ctx->stream));
+  const bool fused = lstm_fused_applicable(ctx, H, C, B);
+  if (fused) {
+    // The x part of concat(state, x) (lstm.go:140) does not depend on the recurrence: project it for all T x B rows at
+    // once, bias included, straight into the gate buffers -- G = X W4[:, H:]^T + b4 (and the R form; x has no R-vector) --
+    // so that the recurrent contraction is K = H (aligned) and the step's epilogue finds its addend where it will store
+    // the activated gates.
+    GemmOperand A{m->IN + H, nullptr, LAY_KC, C};
+    GemmOperand Bop{m->W4 + H, R ? m->RW4 + H : nullptr, LAY_KC, C};
+    GemmEpilogue e;
+    e.epi = EPI_BIAS; e.out0 = m->G; e.out1 = R ? m->RG : nullptr; e.ldo = 4 * H; e.bias0 = m->b4; e.bias1 = R ? m->Rb4 : nullptr;
+    AF_TRY(gemm_launch(ctx, A, Bop, R, T * B, 4 * H, m->I, e));
+  } else {
+    // the gate sums of every step are accumulated into zeroed buffers when the contraction is split: clear all
+    // T steps at once instead of two memsets per step
+    AF_CUDA(cudaMemsetAsync(m->G, 0, (size_t)(T * B * 4 * H) * 8, ctx->stream));
+    if (R) AF_CUDA(cudaMemsetAsync(m->RG, 0, (size_t)(T * B * 4 * H) * 8, ctx->stream));
+  }
   // initial state is zero (lstm.go:175) with zero R
   AF_CUDA(cudaMemset2DAsync(m->IN, C * 8, 0, H * 8, B, ctx->stream));
   if (R) AF_CUDA(cudaMemset2DAsync(m->RIN, C * 8, 0, H * 8, B, ctx->stream));
@@ -428,6 +435,16 @@ static int lstm_forward_launches(af_lstm* m, int with_r) {
       double* RINt = m->RIN + t * BC + b0 * C;
       double* Gt = m->G + (t * B + b0) * 4 * H;
       double* RGt = m->RG + (t * B + b0) * 4 * H;
+      if (fused) {
+        // ONE kernel per step: gate contraction over the state + bias + sigmoids + cell algebra (lstm_step.cu)
+        LstmStepArgs st{};
+        st.H = (int)H; st.ld = (int)C;
+        st.G = Gt; st.RG = R ? RGt : nullptr;
+        st.INp = INt; st.RINp = RINt; st.INn = INt + BC; st.RINn = RINt + BC;
+        st.AUG = m->AUG + t * BC + b0 * C; st.RAUG = m->RAUG + t * BC + b0 * C;
+        AF_TRY(lstm_fwd_step_launch(ctx, m->W4, R ? m->RW4 : nullptr, st, R, t > 0, nb));
+        continue;
+      }
       // all four gates in one contraction (R-state of step 0 is identically zero: skip its product); bias and
       // sigmoid are applied by the cell kernel, so a split / stream-K launch needs no separate epilogue pass
       {
@@ -464,6 +481,7 @@ static int lstm_backward_launches(af_lstm* m, int with_r) {
   AF_CUDA(cudaMemsetAsync(m->SG[0], 0, (size_t)(B * H) * 8, ctx->stream));
   if (R) AF_CUDA(cudaMemsetAsync(m->RSG[0], 0, (size_t)(B * H) * 8, ctx->stream));
   struct PdlScope { af_ctx* c; explicit PdlScope(af_ctx* c_) : c(c_) { c->pdl = true; } ~PdlScope() { c->pdl = false; } };
+  const bool fused = lstm_fused_applicable(ctx, H, C, B);
   AF_TRY(lstm_for_groups(m, lstm_lane_groups(m), [&](int, int64_t b0, int64_t nb) -> int {
     int cur = 0;
     for (int64_t t = T - 1; t >= 0; --t) {
@@ -471,11 +489,30 @@ static int lstm_backward_launches(af_lstm* m, int with_r) {
       double* D4t = m->D4 + (t * B + b0) * 4 * H;
       double* RD4t = m->RD4 + (t * B + b0) * 4 * H;
       const int64_t go = (t * B + b0) * 4 * H, io = t * BC + b0 * C, so = b0 * H;
-      AF_CUDA(launch_kernel(lstm_cell_bwd_kernel, dim3(ew_grid(ctx, nb * H)), dim3(256), 0, ctx->stream,
-                            ctx->pdl && !ctx->pdl_off, m->G + go, R ? m->RG + go : nullptr, m->IN + io, m->RIN + io,
-                            m->IN + io + BC, m->RIN + io + BC, m->DAUG + io, m->RDAUG + io, m->SG[cur] + so, m->RSG[cur] + so,
-                            m->SG[cur ^ 1] + so, m->RSG[cur ^ 1] + so, D4t, RD4t, (int)nb, (int)H, (int)C));
-      AF_TRY(after_launch(ctx, "lstm_cell_bwd_kernel", KIND_ELEMENTWISE, (R ? 2.0 : 1.0) * 13 * 8 * nb * H));
+      if (!fused || t == T - 1) {
+        // (fused path: only the last time step, whose incoming state gradient is zero, runs the stand-alone cell kernel;
+        // it leaves sg f in SG[1], which the fused steps then update in place)
+        AF_CUDA(launch_kernel(lstm_cell_bwd_kernel, dim3(ew_grid(ctx, nb * H)), dim3(256), 0, ctx->stream,
+                              ctx->pdl && !ctx->pdl_off, m->G + go, R ? m->RG + go : nullptr, m->IN + io, m->RIN + io,
+                              m->IN + io + BC, m->RIN + io + BC, m->DAUG + io, m->RDAUG + io, m->SG[cur] + so, m->RSG[cur] + so,
+                              m->SG[cur ^ 1] + so, m->RSG[cur ^ 1] + so, D4t, RD4t, (int)nb, (int)H, (int)C));
+        AF_TRY(after_launch(ctx, "lstm_cell_bwd_kernel", KIND_ELEMENTWISE, (R ? 2.0 : 1.0) * 13 * 8 * nb * H));
+      }
+      if (fused) {
+        if (t > 0) {
+          // ONE kernel: stateGrad += delta4_t W4[:, :H] over a cluster of 4 CTAs (split-K through distributed shared
+          // memory), then the cell backward of step t - 1 in the epilogue (lstm_step.cu)
+          LstmStepArgs st{};
+          st.H = (int)H; st.ld = (int)C;
+          st.Gm = m->G + go - B * 4 * H; st.RGm = R ? m->RG + go - B * 4 * H : nullptr;
+          st.INm = m->IN + io - BC; st.RINm = m->RIN + io - BC; st.INt = m->IN + io; st.RINt = m->RIN + io;
+          st.DAUGm = m->DAUG + io - BC; st.RDAUGm = m->RDAUG + io - BC;
+          st.SGF = m->SG[1] + so; st.RSGF = m->RSG[1] + so;
+          st.D4m = D4t - B * 4 * H; st.RD4m = RD4t - B * 4 * H;
+          AF_TRY(lstm_bwd_step_launch(ctx, D4t, R ? RD4t : nullptr, m->W4, R ? m->RW4 : nullptr, st, R, nb));
+        }
+        continue;
+      }
       if (t > 0) {
         // stateGrad += delta4 W4[:, :H]  (the four gates' inputGradient, lin_tran.go:272-359, restricted to the
         // state columns: the x columns go to a Variable that is not in the gradient maps)

@@ -29,11 +29,11 @@ RANK, WORLD, LOCAL = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WO
 
 
 def reduce_slab(ptr, n):
-    """Gradient.Add across ranks (gradient.go:28-30): NCCL sum all-reduce of a device range, on the step's stream."""
+    """Gradient.Add across ranks (gradient.go:28-30): the library's own collective (af_allreduce_sum: NCCL behind the C
+    ABI, csrc/dp.cu) over a device range, in order on the step's stream."""
     if WORLD > 1:
-        import torch.distributed as dist
-        from autofunc_b200 import parallel
-        dist.all_reduce(torch.as_tensor(parallel.CudaArrayView(ptr, n), device=f"cuda:{LOCAL}"))
+        ctx = api.context()
+        api.check(ctx.lib.af_allreduce_sum(ctx.h, ptr, n))
 
 
 def timed(fn, steps, warmup=3):
@@ -189,7 +189,10 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = api.Context(LOCAL, stream=stream.cuda_stream)
     api.set_context(ctx)
-    for opt in ("pdl", "small_mlp", "small_n", "lstm_split", "persist_tiles", "sk_bias"):  # A/B switches: AF_OPT_PDL=0 etc.
+    if WORLD > 1:
+        from autofunc_b200 import parallel
+        parallel.dp_init_torch(ctx, LOCAL)  # torch.distributed only ships the communicator id
+    for opt in ("pdl", "small_mlp", "small_n", "lstm_split", "lstm_fused", "persist_tiles", "sk_bias"):  # A/B switches: AF_OPT_PDL=0 etc.
         v = os.environ.get("AF_OPT_" + opt.upper())
         if v is not None:
             api.check(ctx.lib.af_set_option(ctx.h, opt.encode(), int(v)))
@@ -203,6 +206,8 @@ def main():
         mlp_config(ctx, "C3 hessian-vector 4x(2048->2048) n=4096", s, 4096, 5, executed_flops(s, 4096))
     if "c4" in which:
         lstm_config(ctx, 30, 512, 10, 128, 256, 3)
+    if "c4a" in which:  # the aligned variant SURVEY 8 asks for next to the reference's I = 30, O = 10
+        lstm_config(ctx, 512, 512, 512, 128, 256, 3)
     if "c5" in which:
         s = [8192] * 5
         mlp_config(ctx, "C5 shard 4x(8192->8192) n=8192 (1/8 of n=65536)", s, 8192, 2, executed_flops(s, 8192))
