@@ -171,6 +171,12 @@ bool few_rows_igrad_applicable(af_ctx* ctx, long long rows, long long cols, long
 int few_rows_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, long long rows,
                           long long cols, long long n, const GemmEpilogue& e, bool dual);
 
+// forward through a layer with at most 32 input columns and a large batch (streaming, small_n.cu): Y = X W^T + b
+bool few_cols_fwd_applicable(af_ctx* ctx, long long rows, long long cols, long long n);
+int few_cols_fwd_launch(af_ctx* ctx, const double* X, long long ldx, const double* W, const double* RW, long long ldw,
+                        const double* b, const double* Rb, double* Y, double* RY, long long ldy, long long rows, long long cols,
+                        long long n);
+
 // whole-step persistent kernel for an MLP plan with n <= 8 samples (small_mlp.cu)
 bool small_mlp_applicable(af_ctx* ctx, int L, const int64_t* sizes, int64_t n);
 int small_mlp_launch(af_ctx* ctx, int L, const int64_t* sizes, int64_t n, double* const* param, const double* const* rvec,

@@ -93,7 +93,7 @@ int launch_dmma_impl(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args,
     configured.fetch_or(1ull << (ctx->device & 63), std::memory_order_release);
   }
   const cudaError_t le = launch_kernel(kern, grid, dim3(GemmSmem<NACC, CFG>::kThreads), (size_t)smem, ctx->stream,
-                                       ctx->pdl && !ctx->pdl_off, maps[0], maps[1], maps[2], maps[3], args);
+                                       ctx->pdl && !ctx->pdl_off, maps[0], maps[1], maps[2], maps[3], args, SpecialArgs<0>{});
   if (le != cudaSuccess) return cuda_fail(le, "gemm_dmma_kernel launch");
   return after_launch(ctx, "gemm_dmma_kernel", NACC == 2 ? KIND_GEMM_DUAL : KIND_GEMM_SINGLE, gemm_flops(args, NACC == 2));
 }

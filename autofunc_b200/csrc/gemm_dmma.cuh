@@ -96,8 +96,12 @@ struct GemmArgs {
   const double* s;
   const double* rs;
   long long lds;
-  LstmStepArgs lstm;
 };
+// extra kernel parameter of the SPECIAL variants (empty for the plain contraction: its parameter block stays as small as
+// it was -- appending the LSTM operands to GemmArgs itself cost the bench's 2048-CTA forward launch 7 %)
+template <int SPECIAL> struct SpecialArgs {};
+template <> struct SpecialArgs<1> { LstmStepArgs lstm; };
+template <> struct SpecialArgs<2> { LstmStepArgs lstm; };
 
 // ---------------------------------------------------------------------------------------------
 // epilogue element functions (shared by the DMMA kernel and the generic kernel)
@@ -301,7 +305,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return;
 #endif
-  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+  if (__builtin_expect(!mbar_try_wait(bar, parity), 0)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -358,6 +362,10 @@ template <> struct TileCfg<2> { static constexpr int WI = 2, WJ = 2, TI = 4, TJ 
 //   CFG 3 "wide"   : 4x4 warps of 32x16 -> 128 x 64 with FOUR warps per sub-partition (<= 128 registers):
 //                    latency is hidden by warp count instead of register double-buffering
 template <> struct TileCfg<3> { static constexpr int WI = 4, WJ = 4, TI = 4, TJ = 2, STAGES = 4, MIN_CTAS = 1, PREFETCH = 0; };
+//   CFG 4 "step"   : 4x2 warps of 16x32 ->  64 x 64 with EIGHT warps: the LSTM time steps (lstm_step.cu) are 128-tile
+//                    launches, one CTA per SM -- two warps per sub-partition cover each other's barrier waits and fragment
+//                    loads (with CFG 2's four warps the same launch ran at 60 % of the pipe: 82 vs 50 us per step)
+template <> struct TileCfg<4> { static constexpr int WI = 4, WJ = 2, TI = 2, TJ = 4, STAGES = 3, MIN_CTAS = 1, PREFETCH = 1; };
 
 template <int NACC, int CFG>
 struct GemmSmem {
@@ -379,7 +387,7 @@ struct GemmSmem {
   // SPECIAL = 2: exchange buffer of the cluster split-K, [source CTA][value][lane] doubles, after the barriers
   static constexpr int kSplit = 4;
   static constexpr uint32_t kXchgOffset = kBarOffset + 128;
-  static constexpr uint32_t kXchgBytes = kSplit * NACC * T::TI * T::TJ * 2 * 32 * 8;
+  static constexpr uint32_t kXchgBytes = kSplit * (kWarps / kSplit) * NACC * T::TI * T::TJ * 2 * 32 * 8;
   static constexpr uint32_t kTotalCluster = kXchgOffset + kXchgBytes + 1024;
   static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "swizzle atoms must stay 1024-byte aligned");
   static_assert((T::TI == 1 || (T::TI * 8) % 16 == 0) && (T::TJ == 1 || (T::TJ * 8) % 16 == 0), "frag_addr assumes 16-row alignment");
@@ -434,7 +442,8 @@ __device__ __forceinline__ uint32_t frag_addr(uint32_t base, int t) {
 template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI, int SPECIAL = 0>
 __global__ void __launch_bounds__(TileCfg<CFG>::WI * TileCfg<CFG>::WJ * 32, SPECIAL == 2 ? 1 : TileCfg<CFG>::MIN_CTAS)
 gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs p) {
+                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs p,
+                 const SpecialArgs<SPECIAL> sp) {
   using L = GemmSmem<NACC, CFG>;
   using T = TileCfg<CFG>;
   constexpr bool DUAL = (NACC == 2);
@@ -598,7 +607,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if constexpr (SPECIAL == 1) {
       // ---- LSTM forward cell (see LstmStepArgs): accumulator block u of this thread IS gate u of its two units ----
       static_assert(SPECIAL != 1 || (TJ == 4 && T::WJ == 2 && BLAY == LAY_KC), "the gate layout assumes 4 blocks of 8 units per warp");
-      const LstmStepArgs& c = p.lstm;
+      const LstmStepArgs& c = sp.lstm;
       const int H = c.H;
       const int unit = (tile % p.tiles_j) * 16 + (warp % T::WJ) * 8 + 2 * j4;  // and unit + 1
 #pragma unroll
@@ -644,15 +653,18 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     if constexpr (SPECIAL == 2) {
       // ---- cluster split-K: exchange the partial tiles through DSMEM, then the LSTM cell backward ----
-      static_assert(SPECIAL != 2 || (kConsumerWarps == L::kSplit && TI == L::kSplit), "one quarter per warp, one t per warp");
-      constexpr int NV1 = TI * TJ * 2, NV = NACC * NV1;
-      const LstmStepArgs& c = p.lstm;
+      // The tile is cut into kSplit "quarters" of NQ consecutive warps each; CTA q of the cluster finishes quarter q.
+      constexpr int NQ = kConsumerWarps / L::kSplit;     // warps per quarter
+      constexpr int NV1 = TI * TJ * 2, NV = NACC * NV1;  // accumulator values per thread (one / both accumulators)
+      constexpr int PER = NQ * NV1 / kConsumerWarps;     // values of one accumulator each warp finishes
+      static_assert(SPECIAL != 2 || (kConsumerWarps % L::kSplit == 0 && PER >= 2 && PER % 2 == 0 && NV1 % PER == 0), "quarter layout");
+      const LstmStepArgs& c = sp.lstm;
       const uint32_t xchg = base + L::kXchgOffset;
       const uint32_t rank = cluster_ctarank();
       cluster_sync();  // every CTA of the cluster is running and past its main loop: exchange buffers may be written
       {
-        // warp w holds the partial sums of quarter w of the tile: they go to CTA w, slot `rank`, as [value][lane]
-        const uint32_t dst = dsmem_addr(xchg, (uint32_t)warp) + (rank * NV * 32 + lane) * 8;
+        // this warp's partial sums go to the CTA that owns its quarter: slot [source rank][warp within quarter][value][lane]
+        const uint32_t dst = dsmem_addr(xchg, (uint32_t)(warp / NQ)) + (((rank * NQ + (warp % NQ)) * NV) * 32 + lane) * 8;
 #pragma unroll
         for (int t = 0; t < TI; ++t)
 #pragma unroll
@@ -665,58 +677,60 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
       }
       cluster_sync();  // all partials have landed (release / acquire at cluster scope)
-      // this CTA finishes quarter `rank`; its warp w takes the rows t == w of that quarter's fragments
       const int H = c.H;
-      const int t = warp;
-      const long long i = i0 + (int)(rank / T::WJ) * (TI * 8) + 8 * t + g;
-      if (i < p.I) {
+      const int first = warp * PER;                 // this warp's chunk of the quarter's NQ x NV1 values
+      const int sub = first / NV1;                  // which warp of the quarter produced them
+      const int sw = (int)rank * NQ + sub;          // ... and its position in the tile
+      const int sw_i0 = (sw / T::WJ) * (TI * 8), sw_j0 = (sw % T::WJ) * (TJ * 8);
 #pragma unroll
-        for (int u = 0; u < TJ; ++u) {
-          const int j = j0 + (int)(rank % T::WJ) * (TJ * 8) + 8 * u + 2 * j4;  // and j + 1
-          if (j >= p.J) continue;
-          double s0[2], s1[2];
+      for (int x = 0; x < PER; x += 2) {
+        const int v = first % NV1 + x;              // even: the pair (e = 0, 1) of one 8 x 8 block
+        const int t = v / (TJ * 2), u = (v / 2) % TJ;
+        const long long i = i0 + sw_i0 + 8 * t + g;
+        const int j = j0 + sw_j0 + 8 * u + 2 * j4;  // and j + 1
+        if (i >= p.I || j >= p.J) continue;
+        double s0[2], s1[2];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int v = (t * TJ + u) * 2 + e;
-            double a = 0.0, r = 0.0;
+        for (int e = 0; e < 2; ++e) {
+          double a = 0.0, r = 0.0;
 #pragma unroll
-            for (int src = 0; src < L::kSplit; ++src) {  // rank order: the sum is the same on every run
-              a += lds_f64(xchg + ((src * NV + v) * 32 + lane) * 8);
-              if (DUAL) r += lds_f64(xchg + ((src * NV + NV1 + v) * 32 + lane) * 8);
-            }
-            s0[e] = a; s1[e] = r;
+          for (int src = 0; src < L::kSplit; ++src) {  // rank order: the sum is the same on every run
+            const uint32_t slot = xchg + (((src * NQ + sub) * NV + v + e) * 32 + lane) * 8;
+            a += lds_f64(slot);
+            if (DUAL) r += lds_f64(slot + NV1 * 256);
           }
-          const long long ei = i * H + j, gi = i * 4 * H + j, si = i * c.ld + j;
-          const double2 carry = *reinterpret_cast<const double2*>(c.SGF + ei);
-          const double2 gI = *reinterpret_cast<const double2*>(c.Gm + gi), gM = *reinterpret_cast<const double2*>(c.Gm + gi + H);
-          const double2 gF = *reinterpret_cast<const double2*>(c.Gm + gi + 2 * H), gO = *reinterpret_cast<const double2*>(c.Gm + gi + 3 * H);
-          const double2 sp = *reinterpret_cast<const double2*>(c.INm + si), sn = *reinterpret_cast<const double2*>(c.INt + si);
-          const double2 dm = *reinterpret_cast<const double2*>(c.DAUGm + si);
-          double2 rcarry, rI, rM, rF, rO, rsp, rsn, rdm;
-          rcarry = rI = rM = rF = rO = rsp = rsn = rdm = make_double2(0.0, 0.0);
-          if (DUAL) {
-            rcarry = *reinterpret_cast<const double2*>(c.RSGF + ei);
-            rI = *reinterpret_cast<const double2*>(c.RGm + gi); rM = *reinterpret_cast<const double2*>(c.RGm + gi + H);
-            rF = *reinterpret_cast<const double2*>(c.RGm + gi + 2 * H); rO = *reinterpret_cast<const double2*>(c.RGm + gi + 3 * H);
-            rsp = *reinterpret_cast<const double2*>(c.RINm + si); rsn = *reinterpret_cast<const double2*>(c.RINt + si);
-            rdm = *reinterpret_cast<const double2*>(c.RDAUGm + si);
-          }
-          const LstmCellBwd a = lstm_cell_bwd<DUAL>(gI.x, gM.x, gF.x, gO.x, sp.x, sn.x, dm.x, carry.x + s0[0], rI.x, rM.x, rF.x, rO.x,
-                                                    rsp.x, rsn.x, rdm.x, rcarry.x + s1[0]);
-          const LstmCellBwd b = lstm_cell_bwd<DUAL>(gI.y, gM.y, gF.y, gO.y, sp.y, sn.y, dm.y, carry.y + s0[1], rI.y, rM.y, rF.y, rO.y,
-                                                    rsp.y, rsn.y, rdm.y, rcarry.y + s1[1]);
-          *reinterpret_cast<double2*>(c.D4m + gi) = make_double2(a.di, b.di);
-          *reinterpret_cast<double2*>(c.D4m + gi + H) = make_double2(a.dm, b.dm);
-          *reinterpret_cast<double2*>(c.D4m + gi + 2 * H) = make_double2(a.df, b.df);
-          *reinterpret_cast<double2*>(c.D4m + gi + 3 * H) = make_double2(a.d_o, b.d_o);
-          *reinterpret_cast<double2*>(c.SGF + ei) = make_double2(a.sgf, b.sgf);
-          if (DUAL) {
-            *reinterpret_cast<double2*>(c.RD4m + gi) = make_double2(a.rdi, b.rdi);
-            *reinterpret_cast<double2*>(c.RD4m + gi + H) = make_double2(a.rdm, b.rdm);
-            *reinterpret_cast<double2*>(c.RD4m + gi + 2 * H) = make_double2(a.rdf, b.rdf);
-            *reinterpret_cast<double2*>(c.RD4m + gi + 3 * H) = make_double2(a.rd_o, b.rd_o);
-            *reinterpret_cast<double2*>(c.RSGF + ei) = make_double2(a.rsgf, b.rsgf);
-          }
+          s0[e] = a; s1[e] = r;
+        }
+        const long long ei = i * H + j, gi = i * 4 * H + j, si = i * c.ld + j;
+        const double2 carry = *reinterpret_cast<const double2*>(c.SGF + ei);
+        const double2 gI = *reinterpret_cast<const double2*>(c.Gm + gi), gM = *reinterpret_cast<const double2*>(c.Gm + gi + H);
+        const double2 gF = *reinterpret_cast<const double2*>(c.Gm + gi + 2 * H), gO = *reinterpret_cast<const double2*>(c.Gm + gi + 3 * H);
+        const double2 sp = *reinterpret_cast<const double2*>(c.INm + si), sn = *reinterpret_cast<const double2*>(c.INt + si);
+        const double2 dm = *reinterpret_cast<const double2*>(c.DAUGm + si);
+        double2 rcarry, rI, rM, rF, rO, rsp, rsn, rdm;
+        rcarry = rI = rM = rF = rO = rsp = rsn = rdm = make_double2(0.0, 0.0);
+        if (DUAL) {
+          rcarry = *reinterpret_cast<const double2*>(c.RSGF + ei);
+          rI = *reinterpret_cast<const double2*>(c.RGm + gi); rM = *reinterpret_cast<const double2*>(c.RGm + gi + H);
+          rF = *reinterpret_cast<const double2*>(c.RGm + gi + 2 * H); rO = *reinterpret_cast<const double2*>(c.RGm + gi + 3 * H);
+          rsp = *reinterpret_cast<const double2*>(c.RINm + si); rsn = *reinterpret_cast<const double2*>(c.RINt + si);
+          rdm = *reinterpret_cast<const double2*>(c.RDAUGm + si);
+        }
+        const LstmCellBwd a = lstm_cell_bwd<DUAL>(gI.x, gM.x, gF.x, gO.x, sp.x, sn.x, dm.x, carry.x + s0[0], rI.x, rM.x, rF.x, rO.x,
+                                                  rsp.x, rsn.x, rdm.x, rcarry.x + s1[0]);
+        const LstmCellBwd b = lstm_cell_bwd<DUAL>(gI.y, gM.y, gF.y, gO.y, sp.y, sn.y, dm.y, carry.y + s0[1], rI.y, rM.y, rF.y, rO.y,
+                                                  rsp.y, rsn.y, rdm.y, rcarry.y + s1[1]);
+        *reinterpret_cast<double2*>(c.D4m + gi) = make_double2(a.di, b.di);
+        *reinterpret_cast<double2*>(c.D4m + gi + H) = make_double2(a.dm, b.dm);
+        *reinterpret_cast<double2*>(c.D4m + gi + 2 * H) = make_double2(a.df, b.df);
+        *reinterpret_cast<double2*>(c.D4m + gi + 3 * H) = make_double2(a.d_o, b.d_o);
+        *reinterpret_cast<double2*>(c.SGF + ei) = make_double2(a.sgf, b.sgf);
+        if (DUAL) {
+          *reinterpret_cast<double2*>(c.RD4m + gi) = make_double2(a.rdi, b.rdi);
+          *reinterpret_cast<double2*>(c.RD4m + gi + H) = make_double2(a.rdm, b.rdm);
+          *reinterpret_cast<double2*>(c.RD4m + gi + 2 * H) = make_double2(a.rdf, b.rdf);
+          *reinterpret_cast<double2*>(c.RD4m + gi + 3 * H) = make_double2(a.rd_o, b.rd_o);
+          *reinterpret_cast<double2*>(c.RSGF + ei) = make_double2(a.rsgf, b.rsgf);
         }
       }
       return;

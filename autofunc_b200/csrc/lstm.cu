@@ -412,11 +412,16 @@ static int lstm_forward_launches(af_lstm* m, int with_r) {
     // once, bias included, straight into the gate buffers -- G = X W4[:, H:]^T + b4 (and the R form; x has no R-vector) --
     // so that the recurrent contraction is K = H (aligned) and the step's epilogue finds its addend where it will store
     // the activated gates.
-    GemmOperand A{m->IN + H, nullptr, LAY_KC, C};
-    GemmOperand Bop{m->W4 + H, R ? m->RW4 + H : nullptr, LAY_KC, C};
-    GemmEpilogue e;
-    e.epi = EPI_BIAS; e.out0 = m->G; e.out1 = R ? m->RG : nullptr; e.ldo = 4 * H; e.bias0 = m->b4; e.bias1 = R ? m->Rb4 : nullptr;
-    AF_TRY(gemm_launch(ctx, A, Bop, R, T * B, 4 * H, m->I, e));
+    if (few_cols_fwd_applicable(ctx, 4 * H, m->I, T * B)) {  // I <= 32 (the reference's I = 30): a streaming pass
+      AF_TRY(few_cols_fwd_launch(ctx, m->IN + H, C, m->W4 + H, R ? m->RW4 + H : nullptr, C, m->b4, R ? m->Rb4 : nullptr, m->G,
+                                 R ? m->RG : nullptr, 4 * H, 4 * H, m->I, T * B));
+    } else {
+      GemmOperand A{m->IN + H, nullptr, LAY_KC, C};
+      GemmOperand Bop{m->W4 + H, R ? m->RW4 + H : nullptr, LAY_KC, C};
+      GemmEpilogue e;
+      e.epi = EPI_BIAS; e.out0 = m->G; e.out1 = R ? m->RG : nullptr; e.ldo = 4 * H; e.bias0 = m->b4; e.bias1 = R ? m->Rb4 : nullptr;
+      AF_TRY(gemm_launch(ctx, A, Bop, R, T * B, 4 * H, m->I, e));
+    }
   } else {
     // the gate sums of every step are accumulated into zeroed buffers when the contraction is split: clear all
     // T steps at once instead of two memsets per step

@@ -22,7 +22,7 @@ namespace af {
 
 namespace {
 
-constexpr int kCfg = 2;  // 64 x 64 tiles, 4 warps of 32 x 32
+constexpr int kCfg = 4;  // 64 x 64 tiles, 8 warps of 16 x 32 (TileCfg<4>: two warps per SM sub-partition with one CTA per SM)
 
 template <typename Kern>
 int set_smem_once(af_ctx* ctx, Kern kern, int smem, std::atomic<unsigned long long>& configured) {
@@ -34,13 +34,13 @@ int set_smem_once(af_ctx* ctx, Kern kern, int smem, std::atomic<unsigned long lo
 }
 
 template <int NACC>
-int launch_fwd(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, unsigned grid) {
+int launch_fwd(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, const LstmStepArgs& st, unsigned grid) {
   auto kern = gemm_dmma_kernel<LAY_KC, LAY_KC, NACC, kCfg, false, 1>;
   const int smem = (int)GemmSmem<NACC, kCfg>::kTotal;
   static std::atomic<unsigned long long> configured{0};
   AF_TRY(set_smem_once(ctx, kern, smem, configured));
   const cudaError_t le = launch_kernel(kern, dim3(grid), dim3(GemmSmem<NACC, kCfg>::kThreads), (size_t)smem, ctx->stream,
-                                       ctx->pdl && !ctx->pdl_off, maps[0], maps[1], maps[2], maps[3], args);
+                                       ctx->pdl && !ctx->pdl_off, maps[0], maps[1], maps[2], maps[3], args, SpecialArgs<1>{st});
   if (le != cudaSuccess) return cuda_fail(le, "lstm forward step launch");
   const int products = 1 + (NACC == 2 ? (args.has_a1 ? 1 : 0) + (args.has_b1 ? 1 : 0) : 0);
   return after_launch(ctx, "gemm_dmma_kernel<lstm fwd step>", NACC == 2 ? KIND_GEMM_DUAL : KIND_GEMM_SINGLE,
@@ -48,7 +48,7 @@ int launch_fwd(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, unsig
 }
 
 template <int NACC>
-int launch_bwd(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, unsigned grid) {
+int launch_bwd(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, const LstmStepArgs& st, unsigned grid) {
   auto kern = gemm_dmma_kernel<LAY_KC, LAY_RC, NACC, kCfg, false, 2>;
   const int smem = (int)GemmSmem<NACC, kCfg>::kTotalCluster;
   static std::atomic<unsigned long long> configured{0};
@@ -62,7 +62,7 @@ int launch_bwd(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, unsig
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = (ctx->pdl && !ctx->pdl_off) ? 2 : 1;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], args);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], args, SpecialArgs<2>{st});
   if (le != cudaSuccess) return cuda_fail(le, "lstm backward step launch (cluster of 4)");
   const int products = 1 + (NACC == 2 ? (args.has_a1 ? 1 : 0) + (args.has_b1 ? 1 : 0) : 0);
   return after_launch(ctx, "gemm_dmma_kernel<lstm bwd step>", NACC == 2 ? KIND_GEMM_DUAL : KIND_GEMM_SINGLE,
@@ -97,13 +97,12 @@ int lstm_fwd_step_launch(af_ctx* ctx, const double* W4, const double* RW4, const
   args.units_per_cta = args.kt_total; args.units_per_tile = args.kt_total;
   const long long tiles = ((nb + 63) / 64) * args.tiles_j;
   args.total_units = tiles * args.kt_total;
-  args.lstm = st;
   CUtensorMap maps[4];
   AF_TRY(gemm_make_map(ctx, &maps[0], st.INp, LAY_KC, nb, H, C, 64));
   if (args.has_a1) AF_TRY(gemm_make_map(ctx, &maps[1], st.RINp, LAY_KC, nb, H, C, 64)); else maps[1] = maps[0];
   AF_TRY(gemm_make_gate_map(ctx, &maps[2], W4, H, C));
   if (args.has_b1) AF_TRY(gemm_make_gate_map(ctx, &maps[3], RW4, H, C)); else maps[3] = maps[2];
-  return with_r ? launch_fwd<2>(ctx, maps, args, (unsigned)tiles) : launch_fwd<1>(ctx, maps, args, (unsigned)tiles);
+  return with_r ? launch_fwd<2>(ctx, maps, args, st, (unsigned)tiles) : launch_fwd<1>(ctx, maps, args, st, (unsigned)tiles);
 }
 
 // One backward step on `nb` lanes: SGF += D4 W4[:, :H], then the cell backward of the previous time step (LstmStepArgs).
@@ -125,14 +124,13 @@ int lstm_bwd_step_launch(af_ctx* ctx, const double* D4, const double* RD4, const
   args.units_per_tile = args.kt_total;
   const long long tiles = ((nb + 63) / 64) * args.tiles_j;
   args.total_units = tiles * args.kt_total;
-  args.lstm = st;
   CUtensorMap maps[4];
   AF_TRY(gemm_make_map(ctx, &maps[0], D4, LAY_KC, nb, 4 * H, 4 * H, 64));
   if (with_r) AF_TRY(gemm_make_map(ctx, &maps[1], RD4, LAY_KC, nb, 4 * H, 4 * H, 64)); else maps[1] = maps[0];
   AF_TRY(gemm_make_map(ctx, &maps[2], W4, LAY_RC, H, 4 * H, C, 64));
   if (with_r) AF_TRY(gemm_make_map(ctx, &maps[3], RW4, LAY_RC, H, 4 * H, C, 64)); else maps[3] = maps[2];
   const unsigned grid = (unsigned)(tiles * split);
-  return with_r ? launch_bwd<2>(ctx, maps, args, grid) : launch_bwd<1>(ctx, maps, args, grid);
+  return with_r ? launch_bwd<2>(ctx, maps, args, st, grid) : launch_bwd<1>(ctx, maps, args, st, grid);
 }
 
 }  // namespace af

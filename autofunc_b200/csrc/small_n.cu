@@ -317,4 +317,103 @@ int few_rows_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const 
   return after_launch(ctx, "few_rows_igrad_kernel", KIND_SMALL_N, 8.0 * n * cols * out_vectors);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward through a layer with very FEW INPUT COLUMNS and a large batch: Y = X W^T + b (RY = X RW^T + Rb; X has no
+// R-vector), cols <= 32.  The LSTM's x projection (bench/lstm.go:140 -- the x part of concat(state, x), I = 30 wide, for
+// all T x B rows at once, lstm.cu) is this shape: 32768 x 2048 outputs with a contraction of 30.  As tensor-core tiles that
+// is two k-tiles per 64 x 64 tile, all prologue and epilogue (measured 0.94 ms for 1.07 GB of output = 1.1 TB/s); as a
+// register-tiled streaming pass -- a block stages 64 rows of X and 64 rows of W / RW transposed in shared memory, every
+// thread accumulates a 4 x 4 block of outputs for both products -- it is bound by the output stream.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kFewColsMax = 32;
+
+template <bool DUAL>
+__global__ void __launch_bounds__(256) few_cols_fwd_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ W,
+                                                           const double* __restrict__ RW, long long ldw,
+                                                           const double* __restrict__ b, const double* __restrict__ Rb,
+                                                           double* __restrict__ Y, double* __restrict__ RY, long long ldy, long long n,
+                                                           int rows, int K) {
+  __shared__ double xs[kFewColsMax][64], ws[kFewColsMax][64], rws[DUAL ? kFewColsMax : 1][64];
+  const long long r0 = (long long)blockIdx.y * 64;
+  const int c0 = blockIdx.x * 64;
+  for (int e = threadIdx.x; e < 64 * K; e += 256) {
+    const int r = e / K, k = e - r * K;
+    xs[k][r] = (r0 + r < n) ? X[(r0 + r) * ldx + k] : 0.0;
+    const bool in = c0 + r < rows;
+    ws[k][r] = in ? W[(long long)(c0 + r) * ldw + k] : 0.0;
+    if (DUAL) rws[k][r] = in ? RW[(long long)(c0 + r) * ldw + k] : 0.0;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4], racc[DUAL ? 4 : 1][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[i][j] = 0.0;
+      if (DUAL) racc[i][j] = 0.0;
+    }
+  for (int k = 0; k < K; ++k) {
+    const double4 xv = *reinterpret_cast<const double4*>(&xs[k][ty * 4]);
+    const double4 wv = *reinterpret_cast<const double4*>(&ws[k][tx * 4]);
+    const double x[4] = {xv.x, xv.y, xv.z, xv.w}, w[4] = {wv.x, wv.y, wv.z, wv.w};
+    double rw[4] = {0.0, 0.0, 0.0, 0.0};
+    if (DUAL) {
+      const double4 rv = *reinterpret_cast<const double4*>(&rws[k][tx * 4]);
+      rw[0] = rv.x; rw[1] = rv.y; rw[2] = rv.z; rw[3] = rv.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[i][j] = fma(x[i], w[j], acc[i][j]);
+        if (DUAL) racc[DUAL ? i : 0][j] = fma(x[i], rw[j], racc[DUAL ? i : 0][j]);
+      }
+  }
+  const int c = c0 + tx * 4;
+  const bool vec = ((ldy & 1) == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) && (!DUAL || (reinterpret_cast<uintptr_t>(RY) & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long r = r0 + ty * 4 + i;
+    if (r >= n) continue;
+    double y[4], ry[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool in = c + j < rows;
+      y[j] = acc[i][j] + ((b && in) ? b[c + j] : 0.0);                                    // lin_add.go:15-17
+      ry[j] = DUAL ? racc[DUAL ? i : 0][j] + ((Rb && in) ? Rb[c + j] : 0.0) : 0.0;        // lin_add.go:37-42
+    }
+    if (vec && c + 3 < rows) {
+      *reinterpret_cast<double2*>(Y + r * ldy + c) = make_double2(y[0], y[1]);
+      *reinterpret_cast<double2*>(Y + r * ldy + c + 2) = make_double2(y[2], y[3]);
+      if (DUAL) {
+        *reinterpret_cast<double2*>(RY + r * ldy + c) = make_double2(ry[0], ry[1]);
+        *reinterpret_cast<double2*>(RY + r * ldy + c + 2) = make_double2(ry[2], ry[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (c + j >= rows) continue;
+        Y[r * ldy + c + j] = y[j];
+        if (DUAL) RY[r * ldy + c + j] = ry[j];
+      }
+    }
+  }
+}
+
+bool few_cols_fwd_applicable(af_ctx* ctx, long long rows, long long cols, long long n) {
+  return ctx->gemm_path != 1 && !ctx->small_n_off && cols >= 1 && cols <= kFewColsMax && n > 16 && rows >= 1 &&
+         (n + 63) / 64 <= 65535 && rows < (1ll << 30);
+}
+
+// Y (n x rows, pitch ldy) = X (n x cols, pitch ldx) W^T (rows x cols, pitch ldw) + b; RY likewise with RW, Rb when RY != NULL
+int few_cols_fwd_launch(af_ctx* ctx, const double* X, long long ldx, const double* W, const double* RW, long long ldw,
+                        const double* b, const double* Rb, double* Y, double* RY, long long ldy, long long rows, long long cols,
+                        long long n) {
+  const dim3 grid((unsigned)((rows + 63) / 64), (unsigned)((n + 63) / 64));
+  if (RY) few_cols_fwd_kernel<true><<<grid, 256, 0, ctx->stream>>>(X, ldx, W, RW, ldw, b, Rb, Y, RY, ldy, n, (int)rows, (int)cols);
+  else few_cols_fwd_kernel<false><<<grid, 256, 0, ctx->stream>>>(X, ldx, W, nullptr, ldw, b, nullptr, Y, nullptr, ldy, n, (int)rows, (int)cols);
+  return after_launch(ctx, "few_cols_fwd_kernel", KIND_SMALL_N, 8.0 * n * rows * (RY ? 2.0 : 1.0));
+}
+
 }  // namespace af

@@ -239,6 +239,36 @@ def measure_dgemm_peak(torch, size=8192, iters=6):
     return 2.0 * size ** 3 / (best * 1e-3) / 1e12
 
 
+def measure_dgemm_same_shapes(torch, n, sizes, iters=5):
+    """Context for `roofline.frac`: cuBLAS Dgemm (torch.matmul f64) on the bench network's OWN contraction shapes -- the
+    nine products of each layer's forward / input-gradient / weight-gradient launches, run one product at a time as the
+    reference's bench_cblas path would (lin_tran.go:99-355).  Flop-weighted rate over the layers wider than 16 outputs."""
+    tot_flops, tot_ms = 0.0, 0.0
+    for l in range(len(sizes) - 1):
+        K, M = sizes[l], sizes[l + 1]
+        if M <= 16:
+            continue
+        x = torch.rand(n, K, dtype=torch.float64, device="cuda")
+        w = torch.rand(M, K, dtype=torch.float64, device="cuda")
+        u = torch.rand(n, M, dtype=torch.float64, device="cuda")
+        shapes = [(lambda: torch.matmul(x, w.t()), 3 if l else 2),   # forward: X W^T, X RW^T (+ RX W^T)
+                  (lambda: torch.matmul(u.t(), x), 3 if l else 2)]   # weight gradient: U^T X, UR^T X (+ U^T RX)
+        if l:
+            shapes.append((lambda: torch.matmul(u, w), 3))           # input gradient: U W, UR W, U RW
+        for fn, products in shapes:
+            fn(); fn()
+            best = 1e30
+            for _ in range(iters):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); e1.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            tot_flops += products * 2.0 * n * K * M
+            tot_ms += products * best
+        del x, w, u
+    torch.cuda.empty_cache()
+    return tot_flops / (tot_ms * 1e-3) / 1e12 if tot_ms else None
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -429,6 +459,7 @@ def gpu_arm(args):
     other_ms = sum(ms_arr[i] for i in range(count.value) if kinds[i] != 0)
     traced_ms = sum(ms_arr[i] for i in range(count.value))
     peak = measure_dgemm_peak(torch) if rank == 0 else None
+    same_shape = measure_dgemm_same_shapes(torch, n, LAYER_SIZES) if rank == 0 else None
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory) ----
     def pinned(count_):
@@ -532,6 +563,8 @@ def gpu_arm(args):
                          "traced_steps": traced,
                          "peak_source": "cuBLAS Dgemm 8192^3 (torch.matmul f64, best of 6) measured in this run; "
                                         "MEASURED_PEAKS.json has no FP64 entry",
+                         "cublas_dgemm_on_the_same_shapes_tflops": same_shape,
+                         "frac_of_cublas_on_the_same_shapes": (achieved / same_shape) if (achieved and same_shape) else None,
                          "whole_step_tflops": flops_per_sample(LAYER_SIZES) * n * K / (ms_total * 1e-3) / 1e12 * world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),

@@ -352,13 +352,16 @@ def test_mlp_pipelined_host_steps_match_blocking_steps(api):
         plan.wait()
     for k in range(steps):
         out, rout, grads, rgrads = want[k]
-        assert np.array_equal(bufs[k]["out"], out) and np.array_equal(bufs[k]["rout"], rout)
+        # (tolerance, not bit equality: contractions that split their k range combine partial tiles with floating-point
+        # atomics, so two runs of the same step may differ in the last bits -- DESIGN.md 3.1 "reproducibility")
+        close(bufs[k]["out"], out, f"step {k} Output")
+        close(bufs[k]["rout"], rout, f"step {k} ROutput")
         for i in range(P):
             close(bufs[k]["grads"][i], grads[i], f"step {k} grad[{i}]")
             close(bufs[k]["rgrads"][i], rgrads[i], f"step {k} rgrad[{i}]")
     # and the blocking call still works afterwards (rebinds slot 0)
     out, rout, grads, rgrads = plan.step_host(xs[0])
-    assert np.array_equal(out, want[0][0])
+    close(out, want[0][0], "Output of the blocking call after the pipelined ones")
     plan.close()
 
 
