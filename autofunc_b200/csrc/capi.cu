@@ -364,6 +364,11 @@ static int dense_fwd_impl(af_ctx* ctx, const double* W, const double* RW, const 
   e.epi = epi; e.out0 = Y; e.out1 = RY; e.ldo = rows; e.bias0 = b; e.bias1 = Rb;
   if (small_n_applicable(ctx, rows, cols, n, {W, RW, X, RX}))  // the reference's Gemv branch, lin_tran.go:90-99,138-152
     return small_fwd_launch(ctx, W, RW, X, RX, rows, cols, n, e, dual);
+  // at most 16 output rows and a large batch (a 10-class head): one streaming pass, not 64 x 16 tensor-core tiles
+  if ((epi == EPI_STORE || epi == EPI_BIAS || epi == EPI_BIAS_SIGMOID) &&
+      few_rows_fwd_applicable(ctx, rows, cols, n, {W, RW, X, RX, Y, RY}))
+    return few_rows_fwd_launch(ctx, W, dual ? RW : nullptr, b, dual ? Rb : nullptr, X, dual ? RX : nullptr, Y, dual ? RY : nullptr,
+                               epi == EPI_BIAS_SIGMOID, nullptr, rows, cols, n, dual);
   if (cols == 0) {
     // empty contraction: fall through the generic kernel (Kd == 0 gives acc = 0)
     int saved = ctx->gemm_path;
@@ -703,11 +708,32 @@ int af_mlp_get_param(af_mlp* m, int index, double* h, int64_t len) {
   return af_download(m->ctx, h, m->param[index], len);
 }
 
-static int mlp_forward_launches(af_mlp* m, int with_r);
-static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap);
+// Head fusion: when the last layer has at most 16 outputs (the bench network's 10-class head) and the step continues into
+// the backward pass, its forward kernel also applies the top sigmoid backward to the upstream (or generates the unit
+// upstream of bench/mlp.go:118-126) and, unless `head_bias` is false, accumulates the head's bias gradient
+// (small_n.cu: few_rows_fwd_kernel).  The backward pass is then told to skip those launches.
+struct MlpHead {
+  bool backprop = false;   // in: the caller will run the backward pass right after this forward pass
+  bool unit = false;       // in: upstream is outGrad = 1 / outRGrad = 0, not yet materialised
+  bool bias = true;        // in: accumulators are ready to receive the head's bias gradient during the forward pass
+  bool done = false;       // out: the head kernel ran the top sigmoid backward
+  bool bias_done = false;  // out: ... and the head's bias gradient
+};
+static bool mlp_head_fusable(af_mlp* m, int with_r) {
+  const int L = m->L;
+  const bool R = with_r != 0;
+  return !m->grad_ready &&
+         few_rows_fwd_applicable(m->ctx, m->sizes[L], m->sizes[L - 1], m->n,
+                                 {m->param[2 * L - 2], R ? m->rvec[2 * L - 2] : nullptr, m->act[L - 1], R ? m->ract[L - 1] : nullptr,
+                                  m->act[L], R ? m->ract[L] : nullptr});
+}
+static int mlp_forward_launches(af_mlp* m, int with_r, MlpHead* head = nullptr);
+static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap, const MlpHead* head = nullptr);
 static int mlp_step_launches(af_mlp* m, int with_r, int backprop) {
-  AF_TRY(mlp_forward_launches(m, with_r));
-  return backprop ? mlp_backward_launches(m, with_r, false) : AF_OK;
+  MlpHead head;
+  head.backprop = backprop != 0;
+  AF_TRY(mlp_forward_launches(m, with_r, &head));
+  return backprop ? mlp_backward_launches(m, with_r, false, &head) : AF_OK;
 }
 
 static int mlp_pipeline_init(af_mlp* m);
@@ -790,15 +816,23 @@ static int mlp_fresh_step(af_mlp* m, int with_r, const double* hU, const double*
   const int mode = dp ? (m->dp_mode != AF_DP_OFF ? m->dp_mode : AF_DP_OVERLAP) : AF_DP_OFF;
   const bool unit = !hU && !hUR;
   const bool captured = m->use_graph && !m->grad_ready && !ctx->tracing && ctx->stream != nullptr && ctx->stream != cudaStreamLegacy;
+  // the head's forward kernel can generate the unit upstream itself (MlpHead): no fill / zero launches then
+  const bool unit_in_head = unit && !captured && !mlp_small_ok(m) && mlp_head_fusable(m, with_r);
   if (mode >= AF_DP_OVERLAP && !captured && !mlp_small_ok(m) && !m->grad_ready) {
-    // the previous step's reduce may still be running (deferred join): only the accumulators depend on it, so the
-    // forward pass goes first and the join sits in front of the zeroing
-    if (mode == AF_DP_DEFERRED) AF_TRY(mlp_forward_launches(m, with_r));
+    MlpHead head;
+    head.backprop = true;
+    head.unit = unit_in_head;
+    if (!unit_in_head) AF_TRY(mlp_load_upstream(m, with_r, hU, hUR));  // (the upstream buffers are no one else's)
+    if (mode == AF_DP_DEFERRED) {
+      // the previous step's reduce may still be running (deferred join): only the accumulators depend on it, so the
+      // forward pass goes first -- without the head's bias gradient -- and the join sits in front of the zeroing
+      head.bias = false;
+      AF_TRY(mlp_forward_launches(m, with_r, &head));
+    }
     AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
-    AF_TRY(mlp_load_upstream(m, with_r, hU, hUR));
     AF_CUDA(cudaMemsetAsync(m->grad[0], 0, (size_t)m->gr_doubles * 8, ctx->stream));
-    if (mode != AF_DP_DEFERRED) AF_TRY(mlp_forward_launches(m, with_r));
-    AF_TRY(mlp_backward_launches(m, with_r, true));
+    if (mode != AF_DP_DEFERRED) AF_TRY(mlp_forward_launches(m, with_r, &head));
+    AF_TRY(mlp_backward_launches(m, with_r, true, &head));
     if (mode == AF_DP_OVERLAP) AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
     return AF_OK;
   }
@@ -809,7 +843,7 @@ static int mlp_fresh_step(af_mlp* m, int with_r, const double* hU, const double*
     if (rc == AF_ENOTSUP) ctx->small_mlp_off = true;  // cooperative launch refused: per-kernel path from now on
   }
   if (rc == AF_ENOTSUP) {
-    AF_TRY(mlp_load_upstream(m, with_r, hU, hUR));
+    if (!unit_in_head || mlp_small_ok(m)) AF_TRY(mlp_load_upstream(m, with_r, hU, hUR));
     if (mlp_small_ok(m)) {
       rc = mlp_small_step(m, with_r, 1, true, false);
       if (rc == AF_ENOTSUP) ctx->small_mlp_off = true;
@@ -817,7 +851,16 @@ static int mlp_fresh_step(af_mlp* m, int with_r, const double* hU, const double*
   }
   if (rc == AF_ENOTSUP) {
     AF_TRY(af_mlp_zero_grads(m));
-    rc = af_mlp_step(m, with_r, 1);
+    if (unit_in_head && !mlp_small_ok(m)) {  // eager launches (no step graph at this batch size), unit upstream from the head kernel
+      MlpHead head;
+      head.backprop = true;
+      head.unit = true;
+      AF_TRY(mlp_forward_launches(m, with_r, &head));
+      rc = mlp_backward_launches(m, with_r, false, &head);
+    } else {
+      if (unit_in_head) AF_TRY(mlp_load_upstream(m, with_r, hU, hUR));  // (the persistent kernel was refused just now)
+      rc = af_mlp_step(m, with_r, 1);
+    }
   }
   AF_TRY(rc);
   if (dp) AF_TRY(dp_allreduce(ctx, m->grad[0], m->gr_doubles, ctx->stream));
@@ -898,8 +941,10 @@ int af_mlp_step_dp(af_mlp* m, int with_r) {
   const bool captured = m->use_graph && !m->grad_ready && !ctx->tracing && ctx->stream != nullptr && ctx->stream != cudaStreamLegacy;
   if (mode >= AF_DP_OVERLAP && !captured && !mlp_small_ok(m) && !m->grad_ready) {
     AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
-    AF_TRY(mlp_forward_launches(m, with_r));
-    AF_TRY(mlp_backward_launches(m, with_r, true));
+    MlpHead head;
+    head.backprop = true;
+    AF_TRY(mlp_forward_launches(m, with_r, &head));
+    AF_TRY(mlp_backward_launches(m, with_r, true, &head));
     if (mode == AF_DP_OVERLAP) AF_TRY(mlp_dp_join_slot(m, m->bound_slot));
     return AF_OK;
   }
@@ -910,7 +955,7 @@ int af_mlp_step_dp(af_mlp* m, int with_r) {
 
 }  // extern "C"
 
-static int mlp_forward_launches(af_mlp* m, int with_r) {
+static int mlp_forward_launches(af_mlp* m, int with_r, MlpHead* head) {
   af_ctx* ctx = m->ctx;
   const int L = m->L;
   const int64_t n = m->n;
@@ -920,6 +965,17 @@ static int mlp_forward_launches(af_mlp* m, int with_r) {
   // The input is not in the RVector (bench/mlp.go:52; variable.go:85-91) so RX of layer 1 is zero.
   for (int l = 0; l < L; ++l) {
     const double* RX = (R && l > 0) ? m->ract[l] : nullptr;
+    if (l == L - 1 && head && head->backprop && mlp_head_fusable(m, with_r)) {
+      FewRowsHead h;
+      h.unit = head->unit;
+      h.U = m->delta[L]; h.UR = R ? m->rdelta[L] : nullptr;
+      if (head->bias) { h.gb = m->grad[2 * l + 1]; h.rgb = R ? m->rgrad[2 * l + 1] : nullptr; }
+      AF_TRY(few_rows_fwd_launch(ctx, m->param[2 * l], rv(2 * l), m->param[2 * l + 1], rv(2 * l + 1), m->act[l], RX, m->act[l + 1],
+                                 R ? m->ract[l + 1] : nullptr, 1, &h, m->sizes[l + 1], m->sizes[l], n, R));
+      head->done = true;
+      head->bias_done = head->bias;
+      continue;
+    }
     AF_TRY(af_dense_fwd(ctx, m->param[2 * l], rv(2 * l), m->param[2 * l + 1], rv(2 * l + 1), m->act[l], RX,
                         m->act[l + 1], R ? m->ract[l + 1] : nullptr, m->sizes[l + 1], m->sizes[l], n, 1));
   }
@@ -932,16 +988,20 @@ static int mlp_forward_launches(af_mlp* m, int with_r) {
 // (their all-reduce rides with a neighbour's), then the large layers largest first, and every completed run of adjacent
 // layer blocks is all-reduced on the communicator's stream while the remaining contractions run (stream-K launches are
 // sized for sm_count - reserved SMs meanwhile).  The results are identical: every product reads the same operands.
-static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap) {
+static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap, const MlpHead* head) {
   af_ctx* ctx = m->ctx;
   const int L = m->L;
   const int64_t n = m->n;
   const bool R = with_r != 0;
   auto rv = [&](int idx) -> const double* { return (R && m->has_rvec[idx]) ? m->rvec[idx] : nullptr; };
-  // top sigmoid (math_funcs.go:326-333 / 357-374) on the caller's upstream, in place
+  // top sigmoid (math_funcs.go:326-333 / 357-374) on the caller's upstream, in place -- unless the head's forward
+  // kernel already did it (MlpHead)
   const int64_t top = n * m->sizes[L];
-  if (R) AF_TRY(af_sigmoid_bwd_r(ctx, m->act[L], m->ract[L], m->delta[L], m->rdelta[L], top));
-  else AF_TRY(af_sigmoid_bwd(ctx, m->act[L], m->delta[L], top));
+  const bool head_done = head && head->done, head_bias_done = head && head->bias_done;
+  if (!head_done) {
+    if (R) AF_TRY(af_sigmoid_bwd_r(ctx, m->act[L], m->ract[L], m->delta[L], m->rdelta[L], top));
+    else AF_TRY(af_sigmoid_bwd(ctx, m->act[L], m->delta[L], top));
+  }
   auto input_gradient = [&](int l) -> int {  // lin_tran.go:420-423 with the sigmoid backward of the layer below fused in
     return af_dense_igrad(ctx, m->delta[l + 1], R ? m->rdelta[l + 1] : nullptr, m->param[2 * l], rv(2 * l), m->act[l],
                           R ? m->ract[l] : nullptr, m->delta[l], R ? m->rdelta[l] : nullptr, m->sizes[l + 1], m->sizes[l], n);
@@ -953,7 +1013,8 @@ static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap) {
       const double* U = m->delta[l + 1];
       const double* UR = R ? m->rdelta[l + 1] : nullptr;
       // lin_add.go:94-104 batched: gb += colsum(U), rgb += colsum(UR)
-      AF_TRY(colsum_launch(ctx, U, UR, m->grad[2 * l + 1], R ? m->rgrad[2 * l + 1] : nullptr, rows, n));
+      if (!(l == L - 1 && head_bias_done))
+        AF_TRY(colsum_launch(ctx, U, UR, m->grad[2 * l + 1], R ? m->rgrad[2 * l + 1] : nullptr, rows, n));
       // lin_tran.go:410-418
       const double* RX = (R && l > 0) ? m->ract[l] : nullptr;
       double* gW = m->grad[2 * l];
@@ -1037,7 +1098,8 @@ static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap) {
     const int64_t rows = m->sizes[l + 1], cols = m->sizes[l];
     const double* U = m->delta[l + 1];
     const double* UR = R ? m->rdelta[l + 1] : nullptr;
-    AF_TRY(colsum_launch(ctx, U, UR, m->grad[2 * l + 1], R ? m->rgrad[2 * l + 1] : nullptr, rows, n));
+    if (!(l == L - 1 && head_bias_done))
+      AF_TRY(colsum_launch(ctx, U, UR, m->grad[2 * l + 1], R ? m->rgrad[2 * l + 1] : nullptr, rows, n));
     AF_TRY(af_lintran_wgrad_r(ctx, U, UR, m->act[l], (R && l > 0) ? m->ract[l] : nullptr, m->grad[2 * l],
                               R ? m->rgrad[2 * l] : nullptr, rows, cols, n));
     done[l] = 1;

@@ -171,6 +171,21 @@ bool few_rows_igrad_applicable(af_ctx* ctx, long long rows, long long cols, long
 int few_rows_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, long long rows,
                           long long cols, long long n, const GemmEpilogue& e, bool dual);
 
+// forward through a layer with at most 16 output rows and a large batch (streaming, small_n.cu); with `head` the kernel
+// also runs the top of the backward pass on its outputs: sigmoid backward on the upstream U / UR (n x rows, in place; or
+// on outGrad = 1 / outRGrad = 0 when `unit`) and the bias gradient gb / rgb (either may be NULL)
+struct FewRowsHead {
+  bool unit = false;
+  double* U = nullptr;
+  double* UR = nullptr;
+  double* gb = nullptr;
+  double* rgb = nullptr;
+};
+bool few_rows_fwd_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs);
+int few_rows_fwd_launch(af_ctx* ctx, const double* W, const double* RW, const double* b, const double* Rb, const double* X,
+                        const double* RX, double* S, double* RS, int act, const FewRowsHead* head, long long rows, long long cols,
+                        long long n, bool dual);
+
 // forward through a layer with at most 32 input columns and a large batch (streaming, small_n.cu): Y = X W^T + b
 bool few_cols_fwd_applicable(af_ctx* ctx, long long rows, long long cols, long long n);
 int few_cols_fwd_launch(af_ctx* ctx, const double* X, long long ldx, const double* W, const double* RW, long long ldw,

@@ -10,6 +10,7 @@
 // n samples' partial sums in registers, and applies the fused elementwise step where one thread block
 // owns a complete output (forward); the input gradient is split over row chunks and combined with
 // red.global.add.f64, its elementwise step applied afterwards by a tiny pass.
+#include <atomic>
 #include "common.h"
 #include "gemm_dmma.cuh"
 
@@ -178,44 +179,88 @@ __global__ void __launch_bounds__(kSmallThreads) small_igrad_kernel(const double
 // 11 % pipe utilisation measured), it is a streaming pass over the n x K outputs.  Thread = (sample, column pair);
 // W / RW (M x K, a few tens of KB) come from L1, the epilogue (sigmoid backward of the layer below, or plain store)
 // is applied in registers, so HBM sees S, RS once and D, DR once.
-constexpr int kFewRowsSpt = 4;  // samples per thread: every W / RW load from L1 is reused for four samples
+constexpr int kFewRowsSpt = 4;  // samples per thread: every W / RW value read from shared memory is reused for four samples
 
+// W / RW are staged once per (persistent) block in shared memory and the block walks the batch in groups of four samples,
+// whose upstream rows U / UR (4 x M values) go through shared memory too: a thread's inner loop touches no global memory
+// (first version: W / RW through L1 at 50 % hit rate plus 80 broadcast loads of U per thread -- ncu: long_scoreboard,
+// 35 us for 67 MB).
 template <bool DUAL>
-__global__ void __launch_bounds__(256) few_rows_igrad_kernel(const double* __restrict__ U, const double* __restrict__ UR,
-                                                             const double* __restrict__ W, const double* __restrict__ RW,
-                                                             int rows, int cols, long long n, const GemmArgs p) {
+__global__ void __launch_bounds__(256, 2) few_rows_igrad_kernel(const double* __restrict__ U, const double* __restrict__ UR,
+                                                                const double* __restrict__ W, const double* __restrict__ RW,
+                                                                int rows, int cols, long long n, const GemmArgs p) {
+  extern __shared__ __align__(16) double few_smem[];
+  double* ws = few_smem;                           // [rows][cols]
+  double* rws = ws + (size_t)rows * cols;          // [rows][cols]
+  double* us = rws + (size_t)rows * cols;          // [kFewRowsSpt][16]
+  double* urs = us + kFewRowsSpt * 16;
+  const bool has_rw = DUAL && RW != nullptr;
+  for (int e = threadIdx.x * 2; e < rows * cols; e += 512) {
+    *reinterpret_cast<double2*>(ws + e) = ld2(W + e);
+    *reinterpret_cast<double2*>(rws + e) = has_rw ? ld2(RW + e) : make_double2(0.0, 0.0);
+  }
   const int half = cols / 2;
   const bool vec_ok = (p.ldo & 1) == 0 && (p.epi != EPI_SIGMOID_BWD || (p.lds & 1) == 0);
+  const bool fused_sig = p.epi == EPI_SIGMOID_BWD && vec_ok;
   const long long groups = (n + kFewRowsSpt - 1) / kFewRowsSpt;
-  const long long total = groups * half;
-  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
-    const long long ig = idx / half;
-    const int k = 2 * (int)(idx - ig * half);
+  for (long long ig = blockIdx.x; ig < groups; ig += gridDim.x) {
     const long long i0 = ig * kFewRowsSpt;
-    double2 d[kFewRowsSpt], dr[kFewRowsSpt];
-#pragma unroll
-    for (int q = 0; q < kFewRowsSpt; ++q) d[q] = dr[q] = make_double2(0.0, 0.0);
-#pragma unroll 2
-    for (int m = 0; m < rows; ++m) {
-      const double2 wv = ld2(W + (long long)m * cols + k);
-      double2 rwv = make_double2(0.0, 0.0);
-      if (DUAL && RW) rwv = ld2(RW + (long long)m * cols + k);
+    __syncthreads();  // the previous group's upstream rows have been consumed (and, first trip, W / RW are staged)
+    if (threadIdx.x < kFewRowsSpt * 16) {
+      const int q = threadIdx.x >> 4, m = threadIdx.x & 15;
+      const bool in = m < rows && i0 + q < n;
+      us[threadIdx.x] = in ? U[(i0 + q) * rows + m] : 0.0;
+      urs[threadIdx.x] = (DUAL && UR && in) ? UR[(i0 + q) * rows + m] : 0.0;
+    }
+    __syncthreads();
+    for (int kp = threadIdx.x; kp < half; kp += 256) {
+      const int k = 2 * kp;
+      // the sigmoid-backward epilogue reads S / RS at the output position: issue those loads first
+      double2 sx[kFewRowsSpt], rsx[kFewRowsSpt];
 #pragma unroll
       for (int q = 0; q < kFewRowsSpt; ++q) {
-        if (i0 + q < n) {
-          const double um = U[(i0 + q) * rows + m];
+        sx[q] = rsx[q] = make_double2(0.0, 0.0);
+        if (fused_sig && i0 + q < n) {
+          sx[q] = ld2(p.s + (i0 + q) * p.lds + k);
+          if (DUAL && p.rs) rsx[q] = ld2(p.rs + (i0 + q) * p.lds + k);
+        }
+      }
+      double2 d[kFewRowsSpt], dr[kFewRowsSpt];
+#pragma unroll
+      for (int q = 0; q < kFewRowsSpt; ++q) d[q] = dr[q] = make_double2(0.0, 0.0);
+#pragma unroll 2
+      for (int m = 0; m < rows; ++m) {
+        const double2 wv = *reinterpret_cast<const double2*>(ws + m * cols + k);
+        const double2 rwv = *reinterpret_cast<const double2*>(rws + m * cols + k);
+#pragma unroll
+        for (int q = 0; q < kFewRowsSpt; ++q) {
+          const double um = us[q * 16 + m];
           d[q].x = fma(um, wv.x, d[q].x); d[q].y = fma(um, wv.y, d[q].y);
           if (DUAL) {
-            const double urm = UR ? UR[(i0 + q) * rows + m] : 0.0;
+            const double urm = urs[q * 16 + m];
             dr[q].x = fma(urm, wv.x, fma(um, rwv.x, dr[q].x));
             dr[q].y = fma(urm, wv.y, fma(um, rwv.y, dr[q].y));
           }
         }
       }
-    }
 #pragma unroll
-    for (int q = 0; q < kFewRowsSpt; ++q)
-      if (i0 + q < n) epi_pair<DUAL>(p, vec_ok, i0 + q, k, d[q].x, d[q].y, dr[q].x, dr[q].y);
+      for (int q = 0; q < kFewRowsSpt; ++q) {
+        if (i0 + q >= n) continue;
+        if (fused_sig) {
+          // math_funcs.go:365-371, operand order kept: u' = x(1-x)u ; uR' = xR(1-x)u - x xR u + x(1-x)uR
+          const long long o = (i0 + q) * p.ldo + k;
+          const double x0 = sx[q].x, x1 = sx[q].y, u0 = d[q].x, u1 = d[q].y;
+          if (p.out0) *reinterpret_cast<double2*>(p.out0 + o) = make_double2(x0 * (1 - x0) * u0, x1 * (1 - x1) * u1);
+          if (DUAL && p.out1) {
+            const double r0 = rsx[q].x, r1 = rsx[q].y;
+            *reinterpret_cast<double2*>(p.out1 + o) = make_double2(r0 * (1 - x0) * u0 - x0 * r0 * u0 + x0 * (1 - x0) * dr[q].x,
+                                                                   r1 * (1 - x1) * u1 - x1 * r1 * u1 + x1 * (1 - x1) * dr[q].y);
+          }
+        } else {
+          epi_pair<DUAL>(p, vec_ok, i0 + q, k, d[q].x, d[q].y, dr[q].x, dr[q].y);
+        }
+      }
+    }
   }
 }
 
@@ -298,6 +343,7 @@ int small_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const dou
 bool few_rows_igrad_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs) {
   if (ctx->gemm_path == 1 || ctx->small_n_off) return false;
   if (rows < 1 || rows > 16 || n <= 16 || (cols & 1) || cols < 2 || cols > (1 << 30)) return false;
+  if (2 * rows * cols * 8 > 100 * 1024) return false;  // W and RW staged in shared memory, two blocks per SM
   for (const void* p : ptrs)
     if (p && !aligned16(p)) return false;
   return true;
@@ -308,13 +354,191 @@ int few_rows_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const 
   GemmArgs a{};
   a.I = (int)n; a.J = (int)cols; a.Kd = (int)rows; a.epi = e.epi; a.out0 = e.out0; a.out1 = dual ? e.out1 : nullptr;
   a.ldo = e.ldo; a.s = e.s; a.rs = e.rs; a.lds = e.lds;
-  const long long total = (n + kFewRowsSpt - 1) / kFewRowsSpt * (cols / 2);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 8ll * ctx->sm_count) blocks = 8ll * ctx->sm_count;
-  if (dual) few_rows_igrad_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(U, UR, W, RW, (int)rows, (int)cols, n, a);
-  else few_rows_igrad_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(U, nullptr, W, nullptr, (int)rows, (int)cols, n, a);
+  long long blocks = (n + kFewRowsSpt - 1) / kFewRowsSpt;  // one group of four samples per block trip; persistent blocks
+  if (blocks > 2ll * ctx->sm_count) blocks = 2ll * ctx->sm_count;
+  const size_t smem = ((size_t)2 * rows * cols + 2 * kFewRowsSpt * 16) * 8;
+  static std::atomic<unsigned long long> configured{0};
+  if (!(configured.load(std::memory_order_acquire) >> (ctx->device & 63) & 1ull)) {
+    AF_CUDA(cudaFuncSetAttribute(few_rows_igrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 102 * 1024));
+    AF_CUDA(cudaFuncSetAttribute(few_rows_igrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 102 * 1024));
+    configured.fetch_or(1ull << (ctx->device & 63), std::memory_order_release);
+  }
+  if (dual) few_rows_igrad_kernel<true><<<(unsigned)blocks, 256, smem, ctx->stream>>>(U, UR, W, RW, (int)rows, (int)cols, n, a);
+  else few_rows_igrad_kernel<false><<<(unsigned)blocks, 256, smem, ctx->stream>>>(U, nullptr, W, nullptr, (int)rows, (int)cols, n, a);
   const double out_vectors = (dual ? 2.0 : 1.0) * (e.epi == EPI_SIGMOID_BWD ? 2.0 : 1.0);
   return after_launch(ctx, "few_rows_igrad_kernel", KIND_SMALL_N, 8.0 * n * cols * out_vectors);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward through a layer with FEW OUTPUT ROWS and a large batch (the 10-class head of the bench network, the LSTM's
+// 10-wide output layer over all T x B rows): S = act(X W^T + b), RS likewise (lin_tran.go:79-177, lin_add.go:13-50,
+// math_funcs.go:288-315).  rows <= 16 is no tensor-core work -- as 64 x 16 tiles with split-K atomics, a zeroing pass
+// and a deferred elementwise pass it took 21 + 6 us on the bench step -- it is one streaming pass over X / RX: a warp
+// takes two samples, its lanes split the contraction in column pairs (W / RW, a few tens of KB, come from L1), the
+// partial sums are combined with shuffles, and lane m finishes output m.
+// With `bwd` the same lane also runs the TOP of the backward pass on its output (bench/mlp.go:52-54 calls
+// PropagateRGradient right after ApplyR): the sigmoid backward of math_funcs.go:365-371 on the caller's upstream --
+// or on outGrad = 1 / outRGrad = 0 (bench/mlp.go:118-126) generated in registers when `unit` -- written in place, and
+// the bias gradient (lin_add.go:94-104), so the fill / zero / sigmoid-backward / column-sum launches of the head vanish.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kFewRowsMax = 16;
+
+// W / RW are staged ONCE per block in shared memory (rows x cols doubles each; the bench head: 2 x 40 KB) and the blocks
+// are persistent over the batch (two per SM): the first version read them through L1 with 226 registers and one block
+// per SM -- 24 % of those loads missed, every warp stalled on each of them (ncu: long_scoreboard, 12 % warps active) and
+// the kernel took 75 us for 33 MB.
+template <bool DUAL>
+__global__ void __launch_bounds__(256, 2) few_rows_fwd_kernel(const double* __restrict__ W, const double* __restrict__ RW,
+                                                              const double* __restrict__ b, const double* __restrict__ Rb,
+                                                              const double* __restrict__ X, const double* __restrict__ RX,
+                                                              double* __restrict__ S, double* __restrict__ RS, int act, int bwd, int unit,
+                                                              double* __restrict__ U, double* __restrict__ UR, double* __restrict__ gb,
+                                                              double* __restrict__ rgb, int rows, int cols, long long n) {
+  extern __shared__ __align__(16) double few_smem[];
+  double* ws = few_smem;                     // [rows][cols]
+  double* rws = few_smem + (size_t)rows * cols;  // [rows][cols] (DUAL with RW only)
+  const bool has_rw = DUAL && RW != nullptr;
+  for (int e = threadIdx.x * 2; e < rows * cols; e += 512) {
+    *reinterpret_cast<double2*>(ws + e) = ld2(W + e);
+    if (has_rw) *reinterpret_cast<double2*>(rws + e) = ld2(RW + e);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * 256) >> 5;
+  const int half = cols / 2;
+  const bool has_rx = DUAL && RX != nullptr;
+  double gsum = 0.0, rgsum = 0.0;  // lane m: bias-gradient partial of output m over this warp's samples
+  for (long long i = warp; i < n; i += nwarps) {
+    double z[kFewRowsMax], rz[DUAL ? kFewRowsMax : 1];
+#pragma unroll
+    for (int m = 0; m < kFewRowsMax; ++m) {
+      z[m] = 0.0;
+      if (DUAL) rz[m] = 0.0;
+    }
+    const double* xr = X + i * cols;
+    const double* rxr = has_rx ? RX + i * cols : nullptr;
+    // two column pairs per trip: four independent global loads in flight before the first use
+    for (int kp = lane; kp < half; kp += 64) {
+      const int kq = kp + 32;
+      const bool second = kq < half;
+      const double2 x0 = ld2(xr + 2 * kp);
+      const double2 x1 = second ? ld2(xr + 2 * kq) : make_double2(0.0, 0.0);
+      double2 r0 = make_double2(0.0, 0.0), r1 = make_double2(0.0, 0.0);
+      if (has_rx) {
+        r0 = ld2(rxr + 2 * kp);
+        if (second) r1 = ld2(rxr + 2 * kq);
+      }
+      const int kq_s = second ? kq : kp;  // (x1 = r1 = 0 then: the duplicate column pair contributes nothing)
+#pragma unroll
+      for (int m = 0; m < kFewRowsMax; ++m) {
+        if (m < rows) {
+          const double2 w0 = *reinterpret_cast<const double2*>(ws + m * cols + 2 * kp);
+          const double2 w1 = *reinterpret_cast<const double2*>(ws + m * cols + 2 * kq_s);
+          z[m] = fma(x1.y, w1.y, fma(x1.x, w1.x, fma(x0.y, w0.y, fma(x0.x, w0.x, z[m]))));
+          if (DUAL) {
+            double a = rz[m];
+            if (has_rw) {
+              const double2 q0 = *reinterpret_cast<const double2*>(rws + m * cols + 2 * kp);
+              const double2 q1 = *reinterpret_cast<const double2*>(rws + m * cols + 2 * kq_s);
+              a = fma(x1.y, q1.y, fma(x1.x, q1.x, fma(x0.y, q0.y, fma(x0.x, q0.x, a))));
+            }
+            if (has_rx) a = fma(r1.y, w1.y, fma(r1.x, w1.x, fma(r0.y, w0.y, fma(r0.x, w0.x, a))));
+            rz[m] = a;
+          }
+        }
+      }
+    }
+    // butterfly: afterwards every lane holds every total; lane m keeps output m (selected with predicated moves --
+    // a lane-indexed read of the register arrays would put them in local memory)
+    double mine = 0.0, rmine = 0.0;
+#pragma unroll
+    for (int m = 0; m < kFewRowsMax; ++m) {
+      if (m < rows) {
+        double v = z[m], rv = DUAL ? rz[m] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (DUAL) rv += __shfl_xor_sync(0xffffffffu, rv, o);
+        }
+        if (lane == m) { mine = v; rmine = rv; }
+      }
+    }
+    if (lane < rows) {
+      const long long o = i * rows + lane;
+      const double zb = mine + (b ? b[lane] : 0.0);      // lin_add.go:15-17
+      const double s = act ? sigmoid_f64(zb) : zb;       // math_funcs.go:292
+      double rs = 0.0;
+      if (DUAL) {
+        const double rzb = rmine + (Rb ? Rb[lane] : 0.0);  // lin_add.go:37-42
+        rs = act ? s * (1 - s) * rzb : rzb;                // math_funcs.go:305-309
+      }
+      if (S) S[o] = s;
+      if (DUAL && RS) RS[o] = rs;
+      if (bwd) {
+        // math_funcs.go:365-371, operand order kept: u' = x(1-x)u ; uR' = xR(1-x)u - x xR u + x(1-x)uR
+        const double u = unit ? 1.0 : U[o];
+        const double du = s * (1 - s) * u;
+        U[o] = du;
+        gsum += du;
+        if (DUAL) {
+          const double ur = (unit || !UR) ? 0.0 : UR[o];
+          const double dur = rs * (1 - s) * u - s * rs * u + s * (1 - s) * ur;
+          UR[o] = dur;
+          rgsum += dur;
+        }
+      }
+    }
+  }
+  if (bwd && (gb || (DUAL && rgb))) {  // lin_add.go:94-104 batched: gb += colsum(U'), rgb += colsum(UR')
+    // one atomic per block and output: thousands of same-address float64 atomics would serialise in L2
+    __shared__ double part[2][8][kFewRowsMax];
+    const int w = threadIdx.x >> 5;
+    if (lane < kFewRowsMax) { part[0][w][lane] = gsum; part[1][w][lane] = rgsum; }
+    __syncthreads();
+    if (threadIdx.x < rows) {
+      double a = 0.0, r = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { a += part[0][q][threadIdx.x]; r += part[1][q][threadIdx.x]; }
+      if (gb) atomicAdd(gb + threadIdx.x, a);
+      if (DUAL && rgb) atomicAdd(rgb + threadIdx.x, r);
+    }
+  }
+}
+
+bool few_rows_fwd_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs) {
+  if (ctx->gemm_path == 1 || ctx->small_n_off) return false;
+  if (rows < 1 || rows > kFewRowsMax || n <= 16 || (cols & 1) || cols < 2 || cols > (1 << 30)) return false;
+  if (2 * rows * cols * 8 > 100 * 1024) return false;  // W and RW staged in shared memory, two blocks per SM
+  for (const void* p : ptrs)
+    if (p && !aligned16(p)) return false;
+  return true;
+}
+
+// S / RS = act(X W^T + b) as one streaming pass; `head` != NULL adds the top of the backward pass (see the kernel)
+int few_rows_fwd_launch(af_ctx* ctx, const double* W, const double* RW, const double* b, const double* Rb, const double* X,
+                        const double* RX, double* S, double* RS, int act, const FewRowsHead* head, long long rows, long long cols,
+                        long long n, bool dual) {
+  long long blocks = (n + 7) / 8;  // one warp per sample at a time; persistent blocks, two per SM
+  if (blocks > 2ll * ctx->sm_count) blocks = 2ll * ctx->sm_count;
+  const int bwd = head ? 1 : 0, unit = head && head->unit ? 1 : 0;
+  double* U = head ? head->U : nullptr;
+  double* UR = head ? head->UR : nullptr;
+  double* gb = head ? head->gb : nullptr;
+  double* rgb = head ? head->rgb : nullptr;
+  const size_t smem = (size_t)rows * cols * 8 * ((dual && RW) ? 2 : 1);
+  static std::atomic<unsigned long long> configured{0};
+  if (!(configured.load(std::memory_order_acquire) >> (ctx->device & 63) & 1ull)) {
+    AF_CUDA(cudaFuncSetAttribute(few_rows_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    AF_CUDA(cudaFuncSetAttribute(few_rows_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured.fetch_or(1ull << (ctx->device & 63), std::memory_order_release);
+  }
+  if (dual)
+    few_rows_fwd_kernel<true><<<(unsigned)blocks, 256, smem, ctx->stream>>>(W, RW, b, Rb, X, RX, S, RS, act, bwd, unit, U, UR, gb, rgb,
+                                                                            (int)rows, (int)cols, n);
+  else
+    few_rows_fwd_kernel<false><<<(unsigned)blocks, 256, smem, ctx->stream>>>(W, nullptr, b, nullptr, X, nullptr, S, nullptr, act, bwd,
+                                                                             unit, U, nullptr, gb, nullptr, (int)rows, (int)cols, n);
+  return after_launch(ctx, "few_rows_fwd_kernel", KIND_SMALL_N, 8.0 * n * cols * (dual && RX ? 2.0 : 1.0));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

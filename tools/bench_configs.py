@@ -159,6 +159,12 @@ def lstm_config(ctx, I, H, O, T, B, steps):
         reduce_slab(slab.ptr, slab.n)
     slab = plan.grad_slab()
     ms = timed(step, steps)
+    fwd_ms = timed(lambda: plan.forward(True), steps)
+
+    def bwd_only():
+        api.check(ctx.lib.af_copy(ctx.h, up.ptr, upv.ptr, up.n))
+        plan.backward(True)
+    bwd_ms = timed(bwd_only, steps)
     if os.environ.get("AF_TRACE"):
         cap = 4096
         kinds, work, msa, cnt = (C.c_int * cap)(), (C.c_double * cap)(), (C.c_float * cap)(), C.c_int(0)
@@ -176,6 +182,7 @@ def lstm_config(ctx, I, H, O, T, B, steps):
     flops = 18.0 * (4 * H + O) * (H + I) * T * B
     plan.close()
     emit({"config": f"C4 lstm I={I} H={H} O={O} T={T} B={B} fwd+BPTT+R", "lanes_per_gpu": B, "ms_per_step": ms,
+          "forward_ms": fwd_ms, "backward_ms": bwd_ms,
           "sequences_per_s": WORLD * B / ms * 1e3, "tflops_reference_count": WORLD * flops / ms / 1e9})
 
 
