@@ -534,3 +534,74 @@ def test_bench_configuration_matches_oracle_at_full_size(api, sizes, scaled):
         close(grads[i], ograd[v], f"grad[{i}]")
         close(rgrads[i], orgrad[v], f"rgrad[{i}]")
     plan.close()
+
+
+# ---- the streaming kernels for very narrow layers (small_n.cu) ------------------------------------------------------
+@pytest.mark.parametrize("rows,cols,n", [(10, 512, 4096), (1, 2, 17), (16, 66, 130), (3, 6400, 19), (7, 30, 1000)])
+@pytest.mark.parametrize("with_r", [True, False])
+@pytest.mark.parametrize("activation", [1, 0])
+def test_few_rows_forward_matches_oracle(api, rows, cols, n, with_r, activation):
+    """af_dense_fwd on a layer with <= 16 outputs and a large batch takes few_rows_fwd_kernel (one streaming pass with the
+    weights staged in shared memory; wider-than-shared-memory weights fall back to the tensor-core tiles): against
+    LinTran -> LinAdd (-> Sigmoid) of the oracle, with the R operands present, absent one at a time, and the non-R form."""
+    ctx = api.context()
+    L, h = ctx.lib, ctx.h
+    W, RW, b, Rb = _rand(41, rows * cols), _rand(42, rows * cols), _rand(43, rows), _rand(44, rows)
+    X, RX = _rand(45, n * cols), _rand(46, n * cols)
+    z = X.reshape(n, cols) @ W.reshape(rows, cols).T + b
+    dW, dRW, db, dRb, dX, dRX = (ctx.upload(a) for a in (W, RW, b, Rb, X, RX))
+    for use_rw, use_rx in ([(True, True), (False, True), (True, False)] if with_r else [(False, False)]):
+        rz = np.zeros((n, rows)) + (Rb if with_r else 0.0)
+        if use_rw:
+            rz = rz + X.reshape(n, cols) @ RW.reshape(rows, cols).T
+        if use_rx:
+            rz = rz + RX.reshape(n, cols) @ W.reshape(rows, cols).T
+        s = 1 / (1 + np.exp(-z)) if activation else z
+        rs = s * (1 - s) * rz if activation else rz
+        dS, dRS = ctx.empty(n * rows), (ctx.empty(n * rows) if with_r else None)
+        api.check(L.af_dense_fwd(h, dW.ptr, dRW.ptr if use_rw else None, db.ptr, dRb.ptr if with_r else None, dX.ptr,
+                                 dRX.ptr if use_rx else None, dS.ptr, dRS.ptr if with_r else None, rows, cols, n, activation))
+        close(dS.numpy(), s.reshape(-1), f"S rw={use_rw} rx={use_rx}")
+        if with_r:
+            close(dRS.numpy(), rs.reshape(-1), f"RS rw={use_rw} rx={use_rx}")
+
+
+@pytest.mark.parametrize("n,unit", [(4096, True), (300, False), (77, True)])
+@pytest.mark.parametrize("with_r", [True, False])
+def test_mlp_head_fusion_matches_unfused_steps_and_oracle(api, n, unit, with_r):
+    """The 10-class head of the bench network runs its forward, the top sigmoid backward (on a given upstream, or on
+    outGrad = 1 / outRGrad = 0 generated in the kernel) and its bias gradient in ONE kernel.  Against the oracle, and
+    against the same plan with the streaming kernels switched off (tensor-core tiles + separate launches)."""
+    sizes = [64, 96, 10]
+    onet = ref.MLP(sizes, weight_scale=lambda k: 1 / np.sqrt(k))
+    x = onet.make_input(n)
+    up = None if unit else ref.splitmix_uniform(77, n * 10)
+    upr = None if (unit or not with_r) else ref.splitmix_uniform(78, n * 10)
+    if with_r:
+        ores, ograd, orgrad = onet.step_r(x, n, up, upr)
+    else:
+        ores, ograd = onet.step(x, n, up)
+    ctx = api.context()
+    results = []
+    for small_n in (1, 0):
+        api.check(ctx.lib.af_set_option(ctx.h, b"small_n", small_n))
+        try:
+            plan = api.MLPPlan(sizes, n)
+            for i, v in enumerate(onet.variables):
+                plan.set_param(i, v.vector)
+                plan.set_rvector(i, onet.rvec[v])
+            for rep in range(2):
+                out, rout, grads, rgrads = plan.step_host(x.vector, with_r=with_r, upstream=up, upstream_r=upr)
+                close(out, ores.output(), f"Output small_n={small_n} rep={rep}")
+                for i, v in enumerate(onet.variables):
+                    close(grads[i], ograd[v], f"grad[{i}] small_n={small_n} rep={rep}")
+                    if with_r:
+                        close(rgrads[i], orgrad[v], f"rgrad[{i}] small_n={small_n} rep={rep}")
+                if with_r:
+                    close(rout, ores.routput(), f"ROutput small_n={small_n} rep={rep}")
+            results.append(grads)
+            plan.close()
+        finally:
+            api.check(ctx.lib.af_set_option(ctx.h, b"small_n", 1))
+    for a, b_ in zip(*results):
+        close(a, b_, "fused vs unfused head")
