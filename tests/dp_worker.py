@@ -92,6 +92,23 @@ def main():
             for i, pv in enumerate(onet.variables):
                 close(plan.grad(i).numpy(), ograd[pv], f"resident grad[{i}] n={n_total} mode={mode}")
                 close(plan.rgrad(i).numpy(), orgrad[pv], f"resident rgrad[{i}] n={n_total} mode={mode}")
+            # af_mlp_step_dp: the caller zeroes the accumulators and supplies the upstream (here a non-unit one)
+            up = ref.splitmix_uniform(900, n_total * sizes[-1]).reshape(n_total, -1)[start:start + count].reshape(-1)
+            upr = ref.splitmix_uniform(901, n_total * sizes[-1]).reshape(n_total, -1)[start:start + count].reshape(-1)
+            plan.zero_grads()
+            ctx.lib.af_upload(ctx.h, plan.upstream().ptr, np.ascontiguousarray(up).ctypes.data, up.size)
+            ctx.lib.af_upload(ctx.h, plan.upstream_r().ptr, np.ascontiguousarray(upr).ctypes.data, upr.size)
+            plan.step_dp(True)
+            plan.dp_join()
+            ctx.sync()
+            _, og2, org2 = onet.step_r(ref.Variable(x.reshape(-1)), n_total,
+                                       ref.splitmix_uniform(900, n_total * sizes[-1]), ref.splitmix_uniform(901, n_total * sizes[-1]))
+            for i, pv in enumerate(onet.variables):
+                close(plan.grad(i).numpy(), og2[pv], f"step_dp grad[{i}] n={n_total} mode={mode}")
+                close(plan.rgrad(i).numpy(), org2[pv], f"step_dp rgrad[{i}] n={n_total} mode={mode}")
+            plan.step_fresh_dp(True)  # back to the unit-upstream gradients for the checks below
+            plan.dp_join()
+            ctx.sync()
             # every rank holds bit-identical sums (replicas must not drift apart under AddToVars)
             slab = plan.grad_slab().numpy()
             t = torch.from_numpy(slab.copy()).cuda()
