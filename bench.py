@@ -174,46 +174,62 @@ def reference_arm(args):
 # clocks sampler (NVML)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
-               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
-               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+    """SM clocks and throttle reasons DURING the timed region, the way /opt/skills/guides/B200_PROFILING.md does it: an
+    `nvidia-smi --query-gpu ... -lms` child process started before the region and stopped after it.  (Round 1 polled
+    NVML from a thread of the benchmark process itself; with NCCL in the same process every poll stalled that rank's
+    kernel launches -- measured at 2 GPUs: 5.6-5.9 ms per step with the in-process sampler, 4.68 ms without.)"""
+    FIELDS = ["timestamp", "clocks.sm", "clocks.max.sm", "clocks_event_reasons.hw_slowdown", "clocks_event_reasons.hw_thermal_slowdown",
+              "clocks_event_reasons.sw_thermal_slowdown", "clocks_event_reasons.sw_power_cap"]
 
-    def __init__(self, index):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._thread = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-        except Exception:
-            self.nv = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if r & bit and name != "gpu_idle":
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop.wait(0.02)
+    def __init__(self, gpu_id, period_ms=25):
+        self.gpu_id, self.period_ms, self.proc = str(gpu_id), period_ms, None
 
     def start(self):
-        if self.nv:
-            self._thread = threading.Thread(target=self._run, daemon=True)
-            self._thread.start()
+        import subprocess
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + ",".join(self.FIELDS), "--format=csv,noheader,nounits",
+                                          "-i", self.gpu_id, "-lms", str(self.period_ms)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import atexit
+            atexit.register(lambda p=self.proc: p.poll() is None and p.kill())  # never leave the looping child behind
+        except Exception:
+            self.proc = None
+
+    def mark(self):
+        """called at the start of the timed region: samples taken before this instant are dropped (the child is started
+        early -- nvidia-smi needs a good part of a second to come up -- and samples every period from then on)"""
+        self.t0 = time.time()
 
     def stop(self):
-        if self._thread:
-            self._stop.set()
-            self._thread.join()
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        import datetime
+        t1 = time.time()
+        rows, max_mhz = [], None
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                out = ""
+            for line in out.splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) != len(self.FIELDS):
+                    continue
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    mhz, max_mhz = int(float(f[1])), int(float(f[2]))
+                except ValueError:
+                    continue
+                active = [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:])
+                          if v == "Active"]
+                rows.append((ts, mhz, active))
+        t0 = getattr(self, "t0", 0.0)
+        inside = [r for r in rows if t0 <= r[0] <= t1 + 0.001 * self.period_ms]
+        if not inside and rows:  # a region shorter than one period: the sample nearest to it
+            inside = [min(rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))]
+        reasons = sorted({a for r in inside for a in r[2]})
+        return {"sm_mhz": statistics.median([r[1] for r in inside]) if inside else None, "sm_max_mhz": max_mhz,
+                "reasons": reasons, "samples": len(inside),
+                "how": f"nvidia-smi --query-gpu -lms {self.period_ms} child process; samples inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -286,6 +302,10 @@ def gpu_arm(args):
     n = args.batch
     K, W = args.steps, args.warmup
 
+    gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    sampler = ClockSampler(gpu_uuid if gpu_uuid.startswith("GPU-") else "GPU-" + gpu_uuid) if (rank == 0 and not args.no_clocks) else None
+    if sampler:
+        sampler.start()  # early: the child needs a while to come up; only samples inside the timed region are kept
     stream = torch.cuda.Stream()  # a real stream: kernels, copies and the timing events are ordered on it
     torch.cuda.set_stream(stream)
     ctx = api.Context(local_rank, stream=stream.cuda_stream)
@@ -365,30 +385,37 @@ def gpu_arm(args):
     # Per-launch device times for the roofline come from the LAST `traced` steps of the timed region (one CUDA event after
     # every launch costs ~1 % of the step, so the other steps run untraced); the clocks are sampled by rank 0 only --
     # eight processes polling NVML every 20 ms slowed every rank's launches by 0.2 ms per step at N = 8.
-    traced = min(K, 4)
+    traced = min(K, args.trace_steps)
     cap = 64 * traced + 8
     kinds, work, ms_arr = (C.c_int * cap)(), (C.c_double * cap)(), (C.c_float * cap)()
     count = C.c_int(0)
+    # (the trace's CUDA events are created here, outside the timed region: creating ~260 events between two timed steps
+    # stalled the enqueueing thread for milliseconds once NCCL's threads were contending for the driver)
+    api.check(ctx.lib.af_trace_begin(ctx.h, cap))
+    api.check(ctx.lib.af_trace_end(ctx.h, cap, kinds, work, ms_arr, C.byref(count)))
+    barrier()
     launches0 = ctx.launch_count()
     dp_calls0 = ctx.dp_calls()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for k in range(K):
-        if k == K - traced:
+        if traced and k == K - traced:
             api.check(ctx.lib.af_trace_begin(ctx.h, cap))
         step()
     drain()
     e1.record(stream)
     barrier()
     clocks = sampler.stop() if sampler else None
-    api.check(ctx.lib.af_trace_end(ctx.h, cap, kinds, work, ms_arr, C.byref(count)))
+    if traced:
+        api.check(ctx.lib.af_trace_end(ctx.h, cap, kinds, work, ms_arr, C.byref(count)))
+    else:
+        count.value = 0
     launches = ctx.launch_count() - launches0
     dp_calls = ctx.dp_calls() - dp_calls0
     if args.trace and rank == 0:
-        per_step = count.value // traced
+        per_step = count.value // max(1, traced)
         names = {0: "gemm_dual", 1: "gemm_single", 2: "gemm_generic", 3: "elementwise", 4: "reduce", 5: "streaming"}
         for i in range(count.value - per_step, count.value):
             rate = work[i] / (ms_arr[i] * 1e-3) / 1e12 if ms_arr[i] > 0 else 0.0
@@ -559,7 +586,7 @@ def gpu_arm(args):
                          "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
                          "algorithmic_flops_per_launch": gemm_flops / gemm_n if gemm_n else None,
                          "kernel_share_of_step": gemm_ms / traced_ms if traced_ms else None,
-                         "other_kernels_ms_per_step": other_ms / traced,
+                         "other_kernels_ms_per_step": other_ms / max(1, traced),
                          "traced_steps": traced,
                          "peak_source": "cuBLAS Dgemm 8192^3 (torch.matmul f64, best of 6) measured in this run; "
                                         "MEASURED_PEAKS.json has no FP64 entry",
@@ -569,7 +596,7 @@ def gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "other_modes": other_modes,  # Run(b,false) / Run(b,true) of bench/mlp.go:29-41, resident, same batch
-            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples", "how")} if clocks else None,
         }
         if traffic_note:
             line["roofline"]["traffic_note"] = traffic_note
@@ -673,6 +700,9 @@ def main():
     ap.add_argument("--profile-step", action="store_true",
                     help="run only the warm-up and timed steps (no other modes, peak measurement, end-to-end or CPU legs): "
                          "the command to put under ncu for a launch list of the step")
+    ap.add_argument("--trace-steps", dest="trace_steps", type=int, default=4,
+                    help="how many of the last timed steps carry the per-launch event trace the roofline is computed from (0: none)")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample NVML clocks during the timed region (A/B of the sampler's cost)")
     ap.add_argument("--legacy-step", action="store_true", help="N = 1: zero_grads + fill + zero + af_mlp_step (four calls) instead of af_mlp_step_fresh_dp")
     ap.add_argument("--trace", action="store_true", help="print the last step's per-launch device times to stderr")
     args = ap.parse_args()

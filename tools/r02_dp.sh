@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 run() { timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) "$@"; }
 timeout 900 python -m pytest tests/test_gpu_dp.py -x -q -m gpu --durations=5 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest dp rc=$?"; tail -8 gpurun_out/${tag}_pytest.log
 timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err; echo "bench n1 rc=$?"
-for mode in overlap deferred blocking; do
+for mode in ${MODES:-overlap deferred blocking}; do
   run bench.py --gpus $N --steps 10 --warmup 3 --dp-mode $mode --no-strong $extra > gpurun_out/${tag}_bench_n${N}_${mode}.json 2> gpurun_out/${tag}_bench_n${N}_${mode}.err; echo "bench n$N $mode rc=$?"
   tail -3 gpurun_out/${tag}_bench_n${N}_${mode}.err
 done
