@@ -36,9 +36,11 @@ def reduce_slab(ptr, n):
         api.check(ctx.lib.af_allreduce_sum(ctx.h, ptr, n))
 
 
-def timed(fn, steps, warmup=3):
+def timed(fn, steps, warmup=3, after=None):
     for _ in range(warmup):
         fn()
+    if after:
+        after()
     torch.cuda.synchronize()
     if WORLD > 1:
         import torch.distributed as dist
@@ -48,6 +50,8 @@ def timed(fn, steps, warmup=3):
     e0.record()
     for _ in range(steps):
         fn()
+    if after:
+        after()
     e1.record()
     e1.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -77,10 +81,14 @@ def mlp_config(ctx, name, sizes, n, steps, flops):
     up, upr = plan.upstream(), plan.upstream_r()
     slab_ptr, slab_n = plan.grad(0).ptr, (plan.input().ptr - plan.grad(0).ptr) // 8
 
-    def step():  # one bench iteration: fresh accumulators, outGrad = 1, outRGrad = 0, RunR(backProp=true)
-        plan.step_fresh(True)
-        reduce_slab(slab_ptr, slab_n)
-    ms = timed(step, steps)
+    # one bench iteration: fresh accumulators, outGrad = 1, outRGrad = 0, RunR(backProp=true); under torchrun the sum over
+    # ranks is scheduled by the library (af_mlp_step_fresh_dp, deferred join: DESIGN.md 5); the last join is inside the timing
+    mode = {"blocking": 1, "overlap": 2, "deferred": 3}[os.environ.get("AF_DP_MODE", "deferred")]
+    plan.set_dp(mode if WORLD > 1 else 0)
+
+    def step():
+        plan.step_fresh_dp(True)
+    ms = timed(step, steps, after=plan.dp_join)
     if os.environ.get("AF_TRACE"):
         cap = 256
         kinds, work, msa, cnt = (C.c_int * cap)(), (C.c_double * cap)(), (C.c_float * cap)(), C.c_int(0)
