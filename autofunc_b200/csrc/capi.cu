@@ -279,8 +279,9 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->lstm_fused_off = value == 0;
     return AF_OK;
   }
-  if (!strcmp(name, "pdl")) {
+  if (!strcmp(name, "pdl")) {  // 1: programmatic dependent launch in the LSTM time loops' dependent chains; 0 (default): plain launches
     ctx->pdl_off = value == 0;
+    ctx->pdl_fused_off = value == 0;
     return AF_OK;
   }
   if (!strcmp(name, "small_mlp")) {

@@ -30,7 +30,9 @@ struct af_ctx {
   bool lstm_split_off = true;   // opt-in (af_set_option "lstm_split" 1): two concurrent half-batch kernel chains; measured 24.6 vs 24.2 ms
   bool lstm_fused_off = false;  // A/B switch (af_set_option "lstm_fused" 0): the per-kernel LSTM steps of round 1
   bool pdl = false;      // inside a dependent-kernel chain (LSTM time loops): launch with programmatic stream serialization
-  bool pdl_off = true;   // opt-in (af_set_option "pdl" 1): measured 24.6 vs 24.25 ms on the C4 LSTM, so off by default
+  bool pdl_off = true;   // per-kernel LSTM chains: opt-in (af_set_option "pdl" 1): measured 24.6 vs 24.25 ms on the C4 LSTM
+  bool pdl_fused_off = true;   // fused LSTM steps (lstm_step.cu): opt-in as well -- forward 9.10 vs 9.23 ms, but the backward
+                               // chain's cluster launches ran 23.5 vs 16.2 ms under programmatic dependent launch
   unsigned* barrier_word = nullptr;  // grid-barrier counter of the persistent small-batch kernel
   unsigned barrier_base = 0;         // its value once every launch queued so far has finished
   int64_t launches = 0;

@@ -365,6 +365,11 @@ template <> struct TileCfg<3> { static constexpr int WI = 4, WJ = 4, TI = 4, TJ 
 //   CFG 4 "step"   : 4x2 warps of 16x32 ->  64 x 64 with EIGHT warps: the LSTM time steps (lstm_step.cu) are 128-tile
 //                    launches, one CTA per SM -- two warps per sub-partition cover each other's barrier waits and fragment
 //                    loads (with CFG 2's four warps the same launch ran at 60 % of the pipe: 82 vs 50 us per step)
+//                    (MIN_CTAS = 2 -- <= 128 registers, so that a programmatically launched successor step can sit beside
+//                    the running one and prefetch its weight tiles -- was measured: the register cap costs 3 us per step
+//                    (72.5 vs 69.5 us), the forward chain gains 1 us per step from the early launch and the cluster
+//                    launches of the backward chain get much slower under programmatic dependent launch (23.5 vs
+//                    16.2 ms): one CTA per SM and plain launches stay the default, af_set_option "pdl" 1 is the A/B switch)
 template <> struct TileCfg<4> { static constexpr int WI = 4, WJ = 2, TI = 2, TJ = 4, STAGES = 3, MIN_CTAS = 1, PREFETCH = 1; };
 
 template <int NACC, int CFG>
@@ -384,11 +389,15 @@ struct GemmSmem {
   static constexpr int kThreads = kWarps * 32;
   static constexpr uint32_t kBarOffset = kStages * kStageBytes;
   static constexpr uint32_t kTotal = kBarOffset + 2 * kStages * 8 + 1024;  // + alignment slack
-  // SPECIAL = 2: exchange buffer of the cluster split-K, [source CTA][value][lane] doubles, after the barriers
+  // SPECIAL = 2: exchange buffer of the cluster split-K, [source CTA][warp of the quarter][value][lane] doubles.  It
+  // ALIASES the stage ring: it is first written after a cluster barrier that every thread of every CTA of the cluster
+  // reaches only when its main loop is over (all TMA tiles landed and consumed), so the kernel needs no extra shared memory
+  // and two CTAs fit on an SM.
   static constexpr int kSplit = 4;
-  static constexpr uint32_t kXchgOffset = kBarOffset + 128;
+  static constexpr uint32_t kXchgOffset = 0;
   static constexpr uint32_t kXchgBytes = kSplit * (kWarps / kSplit) * NACC * T::TI * T::TJ * 2 * 32 * 8;
-  static constexpr uint32_t kTotalCluster = kXchgOffset + kXchgBytes + 1024;
+  static constexpr uint32_t kTotalCluster = kTotal;
+  static_assert(kXchgBytes <= kBarOffset, "the exchange buffer must fit inside the stage ring");
   static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "swizzle atoms must stay 1024-byte aligned");
   static_assert((T::TI == 1 || (T::TI * 8) % 16 == 0) && (T::TJ == 1 || (T::TJ * 8) % 16 == 0), "frag_addr assumes 16-row alignment");
 };
@@ -440,7 +449,7 @@ __device__ __forceinline__ uint32_t frag_addr(uint32_t base, int t) {
 //      to CTA w through distributed shared memory, and CTA w adds the four partials in rank order (deterministic, no
 //      atomics, no zeroing) and runs the cell backward of the previous time step on its 32 x 32 quarter of the tile.
 template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI, int SPECIAL = 0>
-__global__ void __launch_bounds__(TileCfg<CFG>::WI * TileCfg<CFG>::WJ * 32, SPECIAL == 2 ? 1 : TileCfg<CFG>::MIN_CTAS)
+__global__ void __launch_bounds__(TileCfg<CFG>::WI * TileCfg<CFG>::WJ * 32, TileCfg<CFG>::MIN_CTAS)
 gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs p,
                  const SpecialArgs<SPECIAL> sp) {
@@ -477,7 +486,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  pdl_wait();  // everything above overlapped the predecessor's tail; its output is visible from here on
+  if (SPECIAL == 0) pdl_wait();  // everything above overlapped the predecessor's tail; its output is visible from here on
 
   // Producer role: lane 0 of warp 0 keeps kStages-1 units in flight.  It is folded into a consumer
   // warp (not an extra warp) because registers are allocated per SM sub-partition: an extra warp would put
@@ -495,23 +504,34 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   int p_q = tile0, p_tj = tile_of(tile0) % p.tiles_j, p_ti = tile_of(tile0) / p.tiles_j;
   int p_b = kt0, p_len = (kt_total - kt0 < nun) ? kt_total - kt0 : nun, p_done = 0, p_tau = 0;  // current segment (MULTI)
   int p_kt = seg_start(p_b, p_len, 0);
-  auto produce = [&](int t) {
-    const int s = t % kStages;
-    const uint32_t ph = (t / kStages) & 1;
-    mbar_wait(bars + 8 * (kStages + s), ph ^ 1);  // all warps released the stage's previous unit
-    const uint32_t full = bars + 8 * s;
-    const uint32_t st = base + s * L::kStageBytes;
-    const int k0 = p_kt * kBK, i0 = p_ti * BM, j0 = p_tj * BN;
-    mbar_expect_tx(full, tx_bytes);
-    tma_load_tile<ALAY, BM>(st + L::kA0, &tmA0, full, i0, k0);
-    if (SPECIAL == 1) {  // rows of the tile = {4 gates} x {16 hidden units}: box {16 k, 16 units, 4 gates}
+  // the B operand of unit (k-tile kt) into stage `st`; SPECIAL = 1: rows of the tile = {4 gates} x {16 hidden units},
+  // box {16 k, 16 units, 4 gates} of the 3-D gate map
+  auto load_b = [&](uint32_t st, uint32_t full, int kt) {
+    const int k0 = kt * kBK, j0 = p_tj * BN;
+    if (SPECIAL == 1) {
       tma_load_3d(st + L::kB0, &tmB0, full, k0, p_tj * 16, 0);
       if (has_b1) tma_load_3d(st + L::kB1, &tmB1, full, k0, p_tj * 16, 0);
     } else {
       tma_load_tile<BLAY, BN>(st + L::kB0, &tmB0, full, j0, k0);
       if (has_b1) tma_load_tile<BLAY, BN>(st + L::kB1, &tmB1, full, j0, k0);
     }
+  };
+  auto load_a = [&](uint32_t st, uint32_t full, int kt) {
+    const int k0 = kt * kBK, i0 = p_ti * BM;
+    tma_load_tile<ALAY, BM>(st + L::kA0, &tmA0, full, i0, k0);
     if (has_a1) tma_load_tile<ALAY, BM>(st + L::kA1, &tmA1, full, i0, k0);
+  };
+  auto produce = [&](int t, bool b_loaded = false) {
+    const int s = t % kStages;
+    const uint32_t ph = (t / kStages) & 1;
+    const uint32_t full = bars + 8 * s;
+    const uint32_t st = base + s * L::kStageBytes;
+    if (!b_loaded) {
+      mbar_wait(bars + 8 * (kStages + s), ph ^ 1);  // all warps released the stage's previous unit
+      mbar_expect_tx(full, tx_bytes);
+      load_b(st, full, p_kt);
+    }
+    load_a(st, full, p_kt);
     ++p_kt;
     if (MULTI) {
       if (p_kt == p_b + p_len) p_kt = p_b;  // wrap inside the segment (a rotated walk; otherwise the segment ends here)
@@ -528,7 +548,22 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   };
-  if (threadIdx.x == 0) {
+  if (SPECIAL != 0) {
+    // LSTM time steps are chains of dependent launches (programmatic dependent launch, lstm_step.cu): this CTA may have
+    // become resident while the previous step is still computing.  The B operand -- the weights -- does not depend on
+    // it, so the first stages' weight tiles are requested BEFORE griddepcontrol.wait and only the A tiles (the state the
+    // previous step is producing) after it: launch latency, barrier set-up and half of the pipeline fill leave the chain.
+    if (threadIdx.x == 0) {
+      for (int t = 0; t < kStages - 1 && t < nun; ++t) {
+        mbar_expect_tx(bars + 8 * t, tx_bytes);
+        load_b(base + t * L::kStageBytes, bars + 8 * t, p_kt + t);  // (!MULTI: units are consecutive k-tiles of one tile)
+      }
+    }
+    pdl_wait();
+    if (threadIdx.x == 0) {
+      for (int t = 0; t < kStages - 1 && t < nun; ++t) produce(t, true);
+    }
+  } else if (threadIdx.x == 0) {
     for (int t = 0; t < kStages - 1 && t < nun; ++t) produce(t);
   }
 

@@ -40,7 +40,7 @@ int launch_fwd(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, const
   static std::atomic<unsigned long long> configured{0};
   AF_TRY(set_smem_once(ctx, kern, smem, configured));
   const cudaError_t le = launch_kernel(kern, dim3(grid), dim3(GemmSmem<NACC, kCfg>::kThreads), (size_t)smem, ctx->stream,
-                                       ctx->pdl && !ctx->pdl_off, maps[0], maps[1], maps[2], maps[3], args, SpecialArgs<1>{st});
+                                       ctx->pdl && !ctx->pdl_fused_off, maps[0], maps[1], maps[2], maps[3], args, SpecialArgs<1>{st});
   if (le != cudaSuccess) return cuda_fail(le, "lstm forward step launch");
   const int products = 1 + (NACC == 2 ? (args.has_a1 ? 1 : 0) + (args.has_b1 ? 1 : 0) : 0);
   return after_launch(ctx, "gemm_dmma_kernel<lstm fwd step>", NACC == 2 ? KIND_GEMM_DUAL : KIND_GEMM_SINGLE,
@@ -61,7 +61,7 @@ int launch_bwd(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, const
   attr[0].val.clusterDim.x = GemmSmem<NACC, kCfg>::kSplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = (ctx->pdl && !ctx->pdl_off) ? 2 : 1;
+  cfg.attrs = attr; cfg.numAttrs = (ctx->pdl && !ctx->pdl_fused_off) ? 2 : 1;
   const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], args, SpecialArgs<2>{st});
   if (le != cudaSuccess) return cuda_fail(le, "lstm backward step launch (cluster of 4)");
   const int products = 1 + (NACC == 2 ? (args.has_a1 ? 1 : 0) + (args.has_b1 ? 1 : 0) : 0);
