@@ -501,6 +501,10 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // in lockstep by every CTA and a panel's k-slice is fetched from DRAM once for all the tiles that use it
   // (streamk_walk.h: sk_seg_start).
   auto seg_start = [&](int b, int len, int tau) -> int { return sk_seg_start(b, len, tau, kt_total, MULTI && p.rotate); };
+#ifndef AF_ROTATE_PRODUCER
+#define AF_ROTATE_PRODUCER 0
+#endif
+  const bool prod_lane = AF_ROTATE_PRODUCER ? (lane == 0) : (threadIdx.x == 0);
   int p_q = tile0, p_tj = tile_of(tile0) % p.tiles_j, p_ti = tile_of(tile0) / p.tiles_j;
   int p_b = kt0, p_len = (kt_total - kt0 < nun) ? kt_total - kt0 : nun, p_done = 0, p_tau = 0;  // current segment (MULTI)
   int p_kt = seg_start(p_b, p_len, 0);
@@ -521,17 +525,25 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_load_tile<ALAY, BM>(st + L::kA0, &tmA0, full, i0, k0);
     if (has_a1) tma_load_tile<ALAY, BM>(st + L::kA1, &tmA1, full, i0, k0);
   };
-  auto produce = [&](int t, bool b_loaded = false) {
+  // `issue` = false advances the walk without requesting tiles.  It exists for the ROTATING producer experiment
+  // (-DAF_ROTATE_PRODUCER=1: lane 0 of every warp tracks the unit walk and unit t's tiles are requested by lane 0 of warp
+  // t mod (warps), so that the empty-barrier wait and the TMA issue do not always stall warp 0's sub-partition).  Measured
+  // on one box, alternating (tools/r02_ab_prod.sh): bench 878.0 k vs 892.7 k samples/s with the fixed producer, C3 31.95
+  // vs 31.42 ms, C4 26.9 vs 25.2 ms -- every warp now pays the walk's bookkeeping each unit, which costs more than
+  // spreading the stall returns.  The fixed producer (lane 0 of warp 0) stays.
+  auto produce = [&](int t, bool b_loaded = false, bool issue = true) {
     const int s = t % kStages;
     const uint32_t ph = (t / kStages) & 1;
     const uint32_t full = bars + 8 * s;
     const uint32_t st = base + s * L::kStageBytes;
-    if (!b_loaded) {
-      mbar_wait(bars + 8 * (kStages + s), ph ^ 1);  // all warps released the stage's previous unit
-      mbar_expect_tx(full, tx_bytes);
-      load_b(st, full, p_kt);
+    if (issue) {
+      if (!b_loaded) {
+        mbar_wait(bars + 8 * (kStages + s), ph ^ 1);  // all warps released the stage's previous unit
+        mbar_expect_tx(full, tx_bytes);
+        load_b(st, full, p_kt);
+      }
+      load_a(st, full, p_kt);
     }
-    load_a(st, full, p_kt);
     ++p_kt;
     if (MULTI) {
       if (p_kt == p_b + p_len) p_kt = p_b;  // wrap inside the segment (a rotated walk; otherwise the segment ends here)
@@ -560,11 +572,11 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
     pdl_wait();
-    if (threadIdx.x == 0) {
-      for (int t = 0; t < kStages - 1 && t < nun; ++t) produce(t, true);
+    if (prod_lane) {
+      for (int t = 0; t < kStages - 1 && t < nun; ++t) produce(t, true, warp == 0);
     }
-  } else if (threadIdx.x == 0) {
-    for (int t = 0; t < kStages - 1 && t < nun; ++t) produce(t);
+  } else if (prod_lane) {
+    for (int t = 0; t < kStages - 1 && t < nun; ++t) produce(t, false, warp == 0);
   }
 
   // ---------------- consumers: WI (i) x WJ (j) warps ----------------
@@ -804,7 +816,8 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     for (; un < seg_end; ++un) {
       const int s = un % kStages;
       const uint32_t st = base + s * L::kStageBytes;
-      if (threadIdx.x == 0 && un + kStages - 1 < nun) produce(un + kStages - 1);
+      if (prod_lane && un + kStages - 1 < nun)
+        produce(un + kStages - 1, false, !AF_ROTATE_PRODUCER || warp == (un + kStages - 1) % kConsumerWarps);
       __syncwarp();
       if (T::PREFETCH) {
 #pragma unroll
