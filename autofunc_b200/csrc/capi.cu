@@ -267,6 +267,11 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->sk_rotate = value;
     return AF_OK;
   }
+  if (!strcmp(name, "small_wgrad_max")) {
+    if (value < 0 || value > 16) return fail(AF_EINVAL, "small_wgrad_max must lie in [0, 16]");
+    ctx->small_wgrad_max = value;
+    return AF_OK;
+  }
   if (!strcmp(name, "small_n")) {
     ctx->small_n_off = value == 0;
     return AF_OK;
@@ -401,7 +406,7 @@ static int wgrad_impl(af_ctx* ctx, const double* U, const double* UR, const doub
   if (rows * cols == 0 || n == 0) return AF_OK;
   const bool dual = rgW != nullptr;
   if (!gW && !rgW) return AF_OK;
-  if (small_n_applicable(ctx, rows, cols, n, {X, RX, gW, rgW}, 16))  // Ger branch, lin_tran.go:187-196,223-241
+  if (small_n_applicable(ctx, rows, cols, n, {X, RX, gW, rgW}, ctx->small_wgrad_max))  // Ger branch, lin_tran.go:187-196,223-241
     return small_wgrad_launch(ctx, U, dual ? UR : nullptr, X, dual ? RX : nullptr, gW, rgW, rows, cols, n);
   GemmOperand A{U, dual ? UR : nullptr, LAY_RC, rows};
   GemmOperand B{X, dual ? RX : nullptr, LAY_RC, cols};

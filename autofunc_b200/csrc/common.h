@@ -25,6 +25,10 @@ struct af_ctx {
   // stream-K launches with long unit ranges walk each tile segment's k-tiles in rotated order (gemm_dmma.cuh: seg_start)
   // so that all CTAs sweep k in lockstep and share operand panels in L2 (af_set_option "sk_rotate" 0/1: A/B)
   int sk_rotate = 1;
+  // batches up to this size take the streaming rank-n weight-gradient update (af_set_option "small_wgrad_max").  Round 1: 16
+  // (C1, n = 10: 29.6 us streaming vs 41.0 us as tensor-core tiles); since the accumulate epilogue fetches a fragment row of
+  // C before adding to it the tiles take 22.5 us there, so 9..16 samples go to the tensor cores (C1 graph 55.4 -> 49.5 us)
+  int small_wgrad_max = 8;
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu
   bool lstm_split_off = true;   // opt-in (af_set_option "lstm_split" 1): two concurrent half-batch kernel chains; measured 24.6 vs 24.2 ms

@@ -783,6 +783,41 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       return;
     }
     if constexpr (SPECIAL == 0) {
+      if (p.epi == EPI_ACCUM && vec_ok) {
+        // beta = 1 accumulation (lin_tran.go:210,267-268) with plain stores: fetch a whole fragment row of C before adding
+        // to it.  Written pair by pair (load, add, store, load, ...) the stores fence the next load -- the outputs may alias
+        // as far as the compiler knows -- and a thread paid 32 serialised L2 round trips per tile.
+#pragma unroll
+        for (int t = 0; t < TI; ++t) {
+          const long long i = i0 + wi0 + 8 * t + g;
+          if (i >= p.I) continue;
+          double2 c0[TJ], c1[TJ];
+#pragma unroll
+          for (int u = 0; u < TJ; ++u) {
+            const int j = j0 + wj0 + 8 * u + 2 * j4;
+            c0[u] = c1[u] = make_double2(0.0, 0.0);
+            if (j + 1 < p.J) {
+              if (p.out0) c0[u] = *reinterpret_cast<const double2*>(p.out0 + i * p.ldo + j);
+              if (DUAL && p.out1) c1[u] = *reinterpret_cast<const double2*>(p.out1 + i * p.ldo + j);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < TJ; ++u) {
+            const int j = j0 + wj0 + 8 * u + 2 * j4;
+            if (j + 1 < p.J) {
+              if (p.out0)
+                *reinterpret_cast<double2*>(p.out0 + i * p.ldo + j) = make_double2(c0[u].x + acc0[t][u][0], c0[u].y + acc0[t][u][1]);
+              if (DUAL && p.out1)
+                *reinterpret_cast<double2*>(p.out1 + i * p.ldo + j) =
+                    make_double2(c1[u].x + acc1[DUAL ? t : 0][u][0], c1[u].y + acc1[DUAL ? t : 0][u][1]);
+            } else if (j < p.J) {
+              epi_pair<DUAL>(p, vec_ok, i, j, acc0[t][u][0], acc0[t][u][1], DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0,
+                             DUAL ? acc1[DUAL ? t : 0][u][1] : 0.0);
+            }
+          }
+        }
+        return;
+      }
 #pragma unroll
       for (int t = 0; t < TI; ++t) {
         const long long i = i0 + wi0 + 8 * t + g;

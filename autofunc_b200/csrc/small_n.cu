@@ -268,9 +268,9 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 }  // namespace
 
-// nmax: 8 for the forward and input-gradient passes; 16 for the weight gradient, whose rank-n update streams faster
-// than the transposed tensor-core tiles up to there (C1, n = 10: 29.6 vs 41.0 us; the other two passes measured
-// 52 vs 27 and 44 vs 26 us, so they keep the tensor-core path for n = 9..16)
+// nmax: 8 for all three passes (ctx->small_wgrad_max for the weight gradient; 16 in round 1, when the rank-n update
+// streamed faster than the tensor-core tiles up to there -- 29.6 vs 41.0 us on C1, n = 10 -- until the tiles' accumulate
+// epilogue stopped serialising its read-modify-writes: 22.5 us; the other two passes measured 52 vs 27 and 44 vs 26 us)
 bool small_n_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs,
                         int nmax) {
   if (ctx->gemm_path == 1 || ctx->small_n_off) return false;
