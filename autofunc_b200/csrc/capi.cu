@@ -375,6 +375,11 @@ static int dense_fwd_impl(af_ctx* ctx, const double* W, const double* RW, const 
       few_rows_fwd_applicable(ctx, rows, cols, n, {W, RW, X, RX, Y, RY}))
     return few_rows_fwd_launch(ctx, W, dual ? RW : nullptr, b, dual ? Rb : nullptr, X, dual ? RX : nullptr, Y, dual ? RY : nullptr,
                                epi == EPI_BIAS_SIGMOID, nullptr, rows, cols, n, dual);
+  // at most 32 input columns, a large batch and no R-input (a first layer on narrow features; the LSTM's x projection):
+  // a register-tiled streaming pass bound by the output stream, not two-k-tile tensor-core tiles
+  if ((epi == EPI_STORE || epi == EPI_BIAS) && !(dual && RX) && Y && (!dual || RY) && few_cols_fwd_applicable(ctx, rows, cols, n))
+    return few_cols_fwd_launch(ctx, X, cols, W, dual ? RW : nullptr, cols, b, dual ? Rb : nullptr, Y, dual ? RY : nullptr, rows, rows,
+                               cols, n);
   if (cols == 0) {
     // empty contraction: fall through the generic kernel (Kd == 0 gives acc = 0)
     int saved = ctx->gemm_path;

@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(256) few_cols_fwd_kernel(const double* __restr
     xs[k][r] = (r0 + r < n) ? X[(r0 + r) * ldx + k] : 0.0;
     const bool in = c0 + r < rows;
     ws[k][r] = in ? W[(long long)(c0 + r) * ldw + k] : 0.0;
-    if (DUAL) rws[k][r] = in ? RW[(long long)(c0 + r) * ldw + k] : 0.0;
+    if (DUAL) rws[k][r] = (in && RW) ? RW[(long long)(c0 + r) * ldw + k] : 0.0;  // RW == NULL: zero R-vector (variable.go:85-91)
   }
   __syncthreads();
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;

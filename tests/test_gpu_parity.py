@@ -605,3 +605,28 @@ def test_mlp_head_fusion_matches_unfused_steps_and_oracle(api, n, unit, with_r):
             api.check(ctx.lib.af_set_option(ctx.h, b"small_n", 1))
     for a, b_ in zip(*results):
         close(a, b_, "fused vs unfused head")
+
+
+@pytest.mark.parametrize("rows,cols,n", [(2048, 30, 700), (50, 7, 130), (64, 32, 64), (3, 1, 17)])
+@pytest.mark.parametrize("with_r,use_rw", [(True, True), (True, False), (False, False)])
+@pytest.mark.parametrize("bias", [True, False])
+def test_few_cols_forward_matches_oracle(api, rows, cols, n, with_r, use_rw, bias):
+    """af_dense_fwd / af_lintran_fwd_r on a layer with <= 32 inputs, a large batch and no R-input take
+    few_cols_fwd_kernel (the LSTM's x projection: I = 30): Y = X W^T (+ b), RY = X RW^T (+ Rb)."""
+    ctx = api.context()
+    L, h = ctx.lib, ctx.h
+    W, RW, b, Rb, X = _rand(51, rows * cols), _rand(52, rows * cols), _rand(53, rows), _rand(54, rows), _rand(55, n * cols)
+    y = X.reshape(n, cols) @ W.reshape(rows, cols).T + (b if bias else 0.0)
+    ry = (X.reshape(n, cols) @ RW.reshape(rows, cols).T if use_rw else np.zeros((n, rows))) + (Rb if bias else 0.0)
+    dW, dRW, db, dRb, dX = (ctx.upload(a) for a in (W, RW, b, Rb, X))
+    dY, dRY = ctx.empty(n * rows), (ctx.empty(n * rows) if with_r else None)
+    if bias:
+        api.check(L.af_dense_fwd(h, dW.ptr, dRW.ptr if use_rw else None, db.ptr, dRb.ptr if with_r else None, dX.ptr, None,
+                                 dY.ptr, dRY.ptr if with_r else None, rows, cols, n, 0))
+    elif with_r:
+        api.check(L.af_lintran_fwd_r(h, dW.ptr, dRW.ptr if use_rw else None, dX.ptr, None, dY.ptr, dRY.ptr, rows, cols, n))
+    else:
+        api.check(L.af_lintran_fwd(h, dW.ptr, dX.ptr, dY.ptr, rows, cols, n))
+    close(dY.numpy(), y.reshape(-1), "Y")
+    if with_r:
+        close(dRY.numpy(), ry.reshape(-1), "RY")
