@@ -874,7 +874,7 @@ static int mlp_fresh_step(af_mlp* m, int with_r, const double* hU, const double*
     }
   }
   AF_TRY(rc);
-  if (dp) AF_TRY(dp_allreduce(ctx, m->grad[0], m->gr_doubles, ctx->stream));
+  if (dp) AF_TRY(dp_allreduce(ctx, m->grad[0], m->gr_doubles, ctx->stream, true));
   return AF_OK;
 }
 
@@ -960,7 +960,7 @@ int af_mlp_step_dp(af_mlp* m, int with_r) {
     return AF_OK;
   }
   AF_TRY(af_mlp_step(m, with_r, 1));
-  if (dp) AF_TRY(dp_allreduce(ctx, m->grad[0], m->gr_doubles, ctx->stream));
+  if (dp) AF_TRY(dp_allreduce(ctx, m->grad[0], m->gr_doubles, ctx->stream, true));
   return AF_OK;
 }
 

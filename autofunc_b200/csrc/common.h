@@ -56,7 +56,9 @@ struct af_ctx {
   // bumped by af_set_option / af_set_gemm_path: plan-owned CUDA graphs captured under an older epoch are re-captured
   int64_t option_epoch = 0;
   // ---- data parallelism (dp.cu): one NCCL communicator per context, its own high-priority stream ----
-  void* comm = nullptr;           // ncclComm_t
+  void* comm = nullptr;           // ncclComm_t, capped at dp_max_ctas CTAs: reduces that overlap the contractions
+  void* comm_wide = nullptr;      // its uncapped twin (ncclCommSplit) for reduces that run alone; NULL: use `comm`
+  cudaEvent_t dp_order_ev = nullptr;
   int dp_rank = 0, dp_nranks = 1;
   cudaStream_t dp_stream = nullptr;
   int dp_max_ctas = 8;            // CTA cap of the communicator (af_set_option "dp_max_ctas", before af_dp_init)
@@ -130,7 +132,7 @@ struct DeviceGuard {
 // ---- data parallelism (dp.cu) ----------------------------------------------------------------
 // sum all-reduce of d_ptr[0..n) across the context's communicator, enqueued on `stream` (Gradient.Add across ranks,
 // gradient.go:28-30,108-120).  No-op when the context has no communicator or a single rank.
-int dp_allreduce(af_ctx* ctx, double* d_ptr, long long n, cudaStream_t stream);
+int dp_allreduce(af_ctx* ctx, double* d_ptr, long long n, cudaStream_t stream, bool wide = false);
 inline bool dp_active(const af_ctx* ctx) { return ctx->comm != nullptr && ctx->dp_nranks > 1; }
 
 // ---- contraction front end (gemm.cu) --------------------------------------------------------

@@ -549,7 +549,7 @@ int af_lstm_step_dp(af_lstm* m, int with_r) {
   AF_TRY(af_lstm_forward(m, with_r));
   AF_TRY(af_lstm_backward(m, with_r));
   DeviceGuard guard(m->ctx->device);
-  return dp_allreduce(m->ctx, m->gW4, m->grad_doubles, m->ctx->stream);
+  return dp_allreduce(m->ctx, m->gW4, m->grad_doubles, m->ctx->stream, true);
 }
 
 int af_lstm_run_host(af_lstm* m, int with_r, const double* h_x, const double* h_up, const double* h_upr, double* h_out,
