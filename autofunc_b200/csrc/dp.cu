@@ -153,8 +153,8 @@ int af_dp_init(af_ctx* ctx, int nranks, int rank, const void* id128) {
     ncclConfig_t wide_cfg = NCCL_CONFIG_INITIALIZER;
     wide_cfg.maxCTAs = 32;  // explicit: an undefined field of a split's config may inherit the parent's cap
     ncclComm_t wide = nullptr;
-    AF_NCCL(g_nccl.CommSplit(comm, 0, rank, &wide, &wide_cfg));
-    ctx->comm_wide = wide;
+    // (not fatal: without the twin every reduce simply uses the capped communicator)
+    if (g_nccl.CommSplit(comm, 0, rank, &wide, &wide_cfg) == ncclSuccess) ctx->comm_wide = wide;
   }
   return AF_OK;
 }
