@@ -139,7 +139,7 @@ func (g *Group) NewMLP(sizes []int, n int, vars []*autofunc.Variable, rv autofun
 	g.plans = make([]*C.af_mlp, len(g.ctxs))
 	for r, c := range g.ctxs {
 		check(C.af_mlp_create(c, &cs[0], C.int(len(sizes)-1), C.int64_t(g.rows[r]), &g.plans[r]))
-		check(C.af_mlp_set_dp(g.plans[r], DPOverlap))
+		check(C.af_mlp_set_dp(g.plans[r], C.int(DPOverlap)))
 		for i, v := range vars {
 			check(C.af_mlp_set_param(g.plans[r], C.int(i), hostPtr(v.Vector), C.int64_t(len(v.Vector))))
 			if rvec, ok := rv[v]; ok {

@@ -221,3 +221,56 @@ def test_roofline_traffic_is_tied_to_the_kernel_sources():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     tj = json.load(open(os.path.join(root, "profiles", "roofline_traffic.json")))
     assert "dram_bytes_per_launch" in tj and "kernel_source_sha" in tj
+
+
+def _header_param_kinds():
+    """name -> list of parameter kinds ('ptr', 'i64', 'int', 'f64') parsed from the prototypes of the header."""
+    text = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER_PATH).read(), flags=re.S)
+    kinds = {}
+    for m in re.finditer(r"\b(af_[a-z0-9_]+)\s*\(", text):
+        args, _ = _split_args(text, m.end() - 1)
+        ks = []
+        for a in args:
+            if a in ("", "void"):
+                continue
+            if "*" in a or "af_grad_ready_fn" in a:
+                ks.append("ptr")
+            elif "int64_t" in a:
+                ks.append("i64")
+            elif "double" in a:
+                ks.append("f64")
+            elif re.search(r"\bint\b", a):
+                ks.append("int")
+            else:
+                ks.append("?")
+        kinds[m.group(1)] = ks
+    return kinds
+
+
+def test_go_shim_argument_kinds_match_the_prototypes():
+    """One step beyond arity: in every C.af_*(...) call of the uncompiled cgo shim a scalar parameter
+    must be passed a value of the matching C type -- C.int64_t(...) for int64_t, C.int(...) for int, C.double(...) for double
+    (or a literal, or a variable the file declares with that conversion) -- and a pointer parameter must not be passed a
+    scalar conversion.  cgo performs no implicit numeric conversions, so each of these would be a compile error."""
+    kinds = _header_param_kinds()
+    assert kinds["af_lintran_fwd"] == ["ptr", "ptr", "ptr", "ptr", "i64", "i64", "i64"]
+    assert kinds["af_mlp_create"] == ["ptr", "ptr", "int", "i64", "ptr"] and kinds["af_scale"] == ["ptr", "ptr", "f64", "i64"]
+    conv = {"i64": "C.int64_t(", "int": "C.int(", "f64": "C.double("}
+    checked = 0
+    for name, src in _go_sources().items():
+        code = re.sub(r"//[^\n]*", "", src)
+        code = re.sub(r"/\*.*?\*/", "", code, flags=re.S)
+        declared = {k: set(re.findall(r"\b([A-Za-z_]\w*)\s*:?=\s*" + re.escape(c), code)) for k, c in conv.items()}
+        for m in re.finditer(r"\bC\.(af_[a-z0-9_]+)\(", code):
+            args, _ = _split_args(code, m.end() - 1)
+            for i, (arg, kind) in enumerate(zip(args, kinds[m.group(1)])):
+                arg = arg.strip()
+                where = f"{name}: {m.group(1)} argument {i + 1} ({arg!r}) for a {kind} parameter"
+                if kind == "ptr":
+                    assert not arg.startswith(tuple(conv.values())) and not re.fullmatch(r"-?[1-9]\d*(\.\d+)?", arg), where
+                elif kind in conv:
+                    ok = (arg.startswith(conv[kind]) or re.fullmatch(r"-?\d+" if kind != "f64" else r"-?\d+(\.\d*)?", arg) is not None
+                          or arg in declared[kind])
+                    assert ok, where
+                checked += 1
+    assert checked > 400
