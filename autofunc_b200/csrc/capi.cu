@@ -293,6 +293,22 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->small_mlp_off = value == 0;
     return AF_OK;
   }
+  if (!strcmp(name, "deterministic")) {
+    if (value != 0 && value != 1) return fail(AF_EINVAL, "deterministic must be 0 or 1");
+    if (ctx->recording) return fail(AF_EINVAL, "deterministic cannot change while a graph is being recorded");
+    if (value == 1 && ctx->scratch_doubles < kDeterministicScratchDoubles) {
+      // ordered column sums park their per-block partial sums here (elementwise.cu: colsum_launch)
+      DeviceGuard guard(ctx->device);
+      AF_CUDA(cudaStreamSynchronize(ctx->stream));
+      double* bigger = nullptr;
+      AF_CUDA(cudaMalloc(&bigger, kDeterministicScratchDoubles * sizeof(double)));
+      if (ctx->scratch) cudaFree(ctx->scratch);
+      ctx->scratch = bigger;
+      ctx->scratch_doubles = kDeterministicScratchDoubles;
+    }
+    ctx->deterministic = value == 1;
+    return AF_OK;
+  }
   return fail(AF_EINVAL, std::string("unknown option ") + name);
 }
 
@@ -444,7 +460,8 @@ static int igrad_impl(af_ctx* ctx, const double* U, const double* UR, const doub
   GemmEpilogue e;
   e.epi = S ? EPI_SIGMOID_BWD : EPI_STORE;
   e.out0 = D; e.out1 = DR; e.ldo = cols; e.s = S; e.rs = RS; e.lds = cols;
-  if (rows > 0 && small_n_applicable(ctx, rows, cols, n, {W, RW, D, DR}))  // Gemv T branch, lin_tran.go:285-288,329-334
+  // Gemv T branch, lin_tran.go:285-288,329-334 (its row chunks meet in red.global.add.f64: not in deterministic mode)
+  if (rows > 0 && !ctx->deterministic && small_n_applicable(ctx, rows, cols, n, {W, RW, D, DR}))
     return small_igrad_launch(ctx, U, UR, W, RW, rows, cols, n, e, dual);
   if (few_rows_igrad_applicable(ctx, rows, cols, n, {W, RW, D, DR, S, RS}))  // <= 16 output rows: a streaming pass, not a GEMM
     return few_rows_igrad_launch(ctx, U, UR, W, RW, rows, cols, n, e, dual);
@@ -733,7 +750,8 @@ struct MlpHead {
 static bool mlp_head_fusable(af_mlp* m, int with_r) {
   const int L = m->L;
   const bool R = with_r != 0;
-  return !m->grad_ready &&
+  // (the head kernel adds per-block bias-gradient partial sums with atomics: not in deterministic mode)
+  return !m->grad_ready && !m->ctx->deterministic &&
          few_rows_fwd_applicable(m->ctx, m->sizes[L], m->sizes[L - 1], m->n,
                                  {m->param[2 * L - 2], R ? m->rvec[2 * L - 2] : nullptr, m->act[L - 1], R ? m->ract[L - 1] : nullptr,
                                   m->act[L], R ? m->ract[L] : nullptr});

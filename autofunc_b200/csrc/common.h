@@ -29,6 +29,12 @@ struct af_ctx {
   // (C1, n = 10: 29.6 us streaming vs 41.0 us as tensor-core tiles); since the accumulate epilogue fetches a fragment row of
   // C before adding to it the tiles take 22.5 us there, so 9..16 samples go to the tensor cores (C1 graph 55.4 -> 49.5 us)
   int small_wgrad_max = 8;
+  // af_set_option "deterministic" 1: every sum is taken in an order fixed by the shapes alone -- contractions run whole
+  // tiles per CTA (no split-K / stream-K partial tiles through red.global.add.f64), column sums fold their partial sums in
+  // block order, the atomics-based small-batch kernels (small_n.cu input gradient, small_mlp.cu) and the fused head's
+  // per-block bias-gradient atomics are not used.  Results are then bit-identical from run to run, like the reference's
+  // (a sequential program); the default (0) is the faster schedule whose last bits depend on the arrival order of partials.
+  bool deterministic = false;
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu
   bool lstm_split_off = true;   // opt-in (af_set_option "lstm_split" 1): two concurrent half-batch kernel chains; measured 24.6 vs 24.2 ms
@@ -70,6 +76,9 @@ struct af_ctx {
 };
 
 namespace af {
+
+// device scratch once af_set_option "deterministic" 1 is in force: the ordered column sums' partial sums (8 MB)
+constexpr int64_t kDeterministicScratchDoubles = 1ll << 20;
 
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);

@@ -13,7 +13,7 @@ __device__ __forceinline__ double sigm(double x) { return 1.0 / (1.0 + exp(-x));
 // column sums of an n x len row-major matrix, accumulated into out[len] (and outR from UR)
 __global__ void __launch_bounds__(256) colsum_kernel(const double* __restrict__ U, const double* __restrict__ UR,
                                                      double* __restrict__ gb, double* __restrict__ rgb, long long len,
-                                                     long long n, long long rows_per_block) {
+                                                     long long n, long long rows_per_block, double* __restrict__ part) {
   __shared__ double sm0[8][33];
   __shared__ double sm1[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const double* __restrict__ 
   if (ty == 0 && c < len) {
 #pragma unroll
     for (int y = 1; y < 8; ++y) { a0 += sm0[y][tx]; a1 += sm1[y][tx]; }
-    if (gridDim.y == 1) {
+    if (part) {  // deterministic mode: block row y parks its partial sums, colsum_fold_kernel adds them up in y order
+      part[(2ll * blockIdx.y) * len + c] = a0;
+      part[(2ll * blockIdx.y + 1) * len + c] = a1;
+    } else if (gridDim.y == 1) {
       if (gb) gb[c] += a0;
       if (rgb) rgb[c] += a1;
     } else {
@@ -53,6 +56,20 @@ __global__ void __launch_bounds__(256) colsum_kernel(const double* __restrict__ 
       if (rgb) atomicAdd(rgb + c, a1);
     }
   }
+}
+
+// deterministic column sums, stage 2: out[c] += part[0][c] + part[1][c] + ... in block-row order
+__global__ void __launch_bounds__(256) colsum_fold_kernel(const double* __restrict__ part, int nparts, double* __restrict__ gb,
+                                                          double* __restrict__ rgb, long long len) {
+  const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (c >= len) return;
+  double a0 = 0.0, a1 = 0.0;
+  for (int y = 0; y < nparts; ++y) {
+    a0 += part[(2ll * y) * len + c];
+    a1 += part[(2ll * y + 1) * len + c];
+  }
+  if (gb) gb[c] += a0;
+  if (rgb) rgb[c] += a1;
 }
 
 // stage 1 of SumAll: per-block partial sums (warp shuffle tree); stage 2: one block folds them
@@ -96,12 +113,22 @@ int colsum_launch(af_ctx* ctx, const double* U, const double* UR, double* gb, do
   long long want = (8ll * ctx->sm_count + colblocks - 1) / colblocks;
   long long maxsplit = (n + 63) / 64;
   if (want > maxsplit) want = maxsplit;
+  // deterministic mode: the partial sums of the block rows are parked in the context's scratch and folded in order
+  const bool ordered = ctx->deterministic && want > 1;
+  if (ordered) {
+    const long long cap = ctx->scratch_doubles / (2 * len);
+    if (want > cap) want = cap;
+  }
   if (want < 1) want = 1;
   const long long rpb = (n + want - 1) / want;
   const long long ysplit = (n + rpb - 1) / rpb;
   dim3 grid((unsigned)colblocks, (unsigned)ysplit);
-  colsum_kernel<<<grid, 256, 0, ctx->stream>>>(U, UR, gb, rgb, len, n, rpb);
-  return after_launch(ctx, "colsum_kernel", KIND_REDUCE, 8.0 * len * n * ((gb ? 1 : 0) + (rgb ? 1 : 0)));
+  double* part = (ordered && ysplit > 1) ? ctx->scratch : nullptr;
+  colsum_kernel<<<grid, 256, 0, ctx->stream>>>(U, UR, gb, rgb, len, n, rpb, part);
+  AF_TRY(after_launch(ctx, "colsum_kernel", KIND_REDUCE, 8.0 * len * n * ((gb ? 1 : 0) + (rgb ? 1 : 0))));
+  if (!part) return AF_OK;
+  colsum_fold_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(part, (int)ysplit, gb, rgb, len);
+  return after_launch(ctx, "colsum_fold_kernel", KIND_REDUCE, 16.0 * len * ysplit);
 }
 
 }  // namespace af

@@ -180,7 +180,9 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   // (A0,A1) <-> (B0,B1).
   const bool contiguous_out = (e.ldo == J);
   bool swapped = false;
-  if (I <= 16 && J > 16 && (accumulate || contiguous_out)) {
+  // (deterministic mode: only where the transposed result can be added in place -- transposed STORES go through the
+  // atomic partial-tile path and its deferred epilogue)
+  if (I <= 16 && J > 16 && (accumulate || (contiguous_out && !ctx->deterministic))) {
     std::swap(A, B);
     std::swap(I, J);
     std::swap(args.has_a1, args.has_b1);
@@ -208,7 +210,9 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   // Store-type outputs pay cd more on the two atomic paths (zeroing + gemm_epilogue_kernel afterwards).
   const double cf = 3.5, cd = accumulate ? 0.0 : 3.0;
   auto waves_of = [&](long long ctas) { return (double)((ctas + slots - 1) / slots); };
-  const bool may_split = kt_total >= 8 && (accumulate || contiguous_out);
+  // deterministic mode: whole tiles per CTA only -- split-K and stream-K add partial tiles with red.global.add.f64 in
+  // arrival order
+  const bool may_split = kt_total >= 8 && (accumulate || contiguous_out) && !ctx->deterministic;
   const bool must_defer = swapped && !accumulate;  // transposed stores always go through the deferred epilogue
   int mode = 0, best_s = 1;                         // 0 = one tile per CTA, 1 = aligned split, 2 = stream-K
   double best = must_defer ? 1e300 : waves_of(tiles) * (kt_total + 0.5);

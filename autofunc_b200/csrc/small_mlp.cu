@@ -323,7 +323,7 @@ int launch_variant(af_ctx* ctx, SmallMlpArgs& a, double bytes) {
 }  // namespace
 
 bool small_mlp_applicable(af_ctx* ctx, int L, const int64_t* sizes, int64_t n) {
-  if (ctx->gemm_path == 1 || ctx->small_n_off || ctx->small_mlp_off) return false;
+  if (ctx->gemm_path == 1 || ctx->small_n_off || ctx->small_mlp_off || ctx->deterministic) return false;  // (input-gradient atomics)
   // n = 5..8 stay on the per-kernel graph: their R variant needs > 200 registers (one group of 8 warps per SM) and
   // measured slower (183 vs 147 us at n = 8)
   if (n < 1 || n > 4 || L < 1 || L > kMaxLayers) return false;

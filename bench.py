@@ -311,7 +311,7 @@ def gpu_arm(args):
     ctx = api.Context(local_rank, stream=stream.cuda_stream)
     api.set_context(ctx)
     ctx.set_gemm_path(2)  # TMA + DMMA or an error; never a silent fallback
-    for name in ("big_cfg", "persist_tiles", "sk_bias", "sk_rotate", "dp_max_ctas", "dp_reserve_sms"):
+    for name in ("big_cfg", "persist_tiles", "sk_bias", "sk_rotate", "dp_max_ctas", "dp_reserve_sms", "deterministic"):
         v = getattr(args, name)
         if v is not None:
             ctx.set_option(name, v)
@@ -579,7 +579,8 @@ def gpu_arm(args):
                                                  "timed region"}[args.dp_mode],
                        "l2": "no flush: each step streams ~%.0f MB of activations/upstreams (> 126 MB L2)" %
                              (n * sum(LAYER_SIZES) * 8 * 4 / 1e6),
-                       "flops_per_sample": flops_per_sample(LAYER_SIZES)},
+                       "flops_per_sample": flops_per_sample(LAYER_SIZES),
+                       "deterministic": bool(args.deterministic)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if (achieved and peak) else None, "traffic": traffic,
                          "kernel": "gemm_dmma_kernel<*,*,2> (TMA + DMMA.8x8x4 dual contraction)",
@@ -691,6 +692,8 @@ def main():
                     help="stream-K launches walk each tile segment's k-tiles in rotated order so CTAs sweep k in lockstep (L2 reuse): 0 / 1")
     ap.add_argument("--persist-tiles", dest="persist_tiles", type=int, default=None,
                     help="multi-wave contractions as persistent CTAs over whole tiles: 0 off, 1 contiguous, 2 wave order")
+    ap.add_argument("--deterministic", type=int, default=None, choices=[0, 1],
+                    help="1: af_set_option deterministic (run-to-run bit-identical sums: whole tiles per CTA, ordered column sums); default 0")
     ap.add_argument("--dp-mode", dest="dp_mode", default="deferred", choices=sorted(DP_MODES),
                     help="N > 1: how the library schedules the sum over ranks (include/autofunc_b200.h AF_DP_*)")
     ap.add_argument("--dp-max-ctas", dest="dp_max_ctas", type=int, default=None, help="CTA cap of the library's NCCL communicator (default 8)")

@@ -92,6 +92,13 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * "dp_max_ctas": CTA cap of the context's communicator (ncclConfig_t.maxCTAs; default 8, 0 = NCCL's own choice); read by
  * af_dp_init.  "dp_reserve_sms": SMs the plans leave to an all-reduce that runs beside their contractions (default =
  * dp_max_ctas): stream-K launches issued while a reduce is in flight are sized for sm_count - dp_reserve_sms SMs.
+ * "deterministic": 1 = every floating-point sum is taken in an order fixed by the shapes alone, so results are
+ * bit-identical from run to run like the reference's (a sequential program): contractions compute whole output tiles per
+ * CTA (no split-K / stream-K partial tiles combined with red.global.add.f64), column sums fold their per-block partial
+ * sums in block order, and the atomics-based small-batch kernels and the fused head's bias-gradient atomics are not
+ * used.  0 (default) = the faster schedule, whose last bits (well inside 1e-12 + 1e-10 |ref|) depend on the arrival
+ * order of partial sums.  Cost measured on the bench step: DESIGN.md 3.1.  (The LSTM's fused time steps are
+ * deterministic in both modes; the sum over ranks is NCCL's, which is run-to-run deterministic for a fixed communicator.)
  * Plan-owned CUDA graphs captured before a change of any option are re-captured.                        */
 int af_set_option(af_ctx* ctx, const char* name, int value);
 
