@@ -51,6 +51,8 @@ PROTOTYPES = {
     "af_lintran_wgrad_r": (INT, [P, D, D, D, D, D, D, I64, I64, I64]),
     "af_lintran_igrad": (INT, [P, D, D, D, I64, I64, I64]),
     "af_lintran_igrad_r": (INT, [P, D, D, D, D, D, D, I64, I64, I64]),
+    "af_lintran_backward": (INT, [P, D, D, D, D, D, I64, I64, I64, INT]),
+    "af_lintran_backward_r": (INT, [P, D, D, D, D, D, D, D, D, D, D, I64, I64, I64, INT]),
     "af_bias_fwd": (INT, [P, D, D, D, I64, I64]),
     "af_bias_fwd_r": (INT, [P, D, D, D, D, D, D, I64, I64]),
     "af_bias_grad": (INT, [P, D, D, I64, I64]),

@@ -680,14 +680,17 @@ class _LinTranResult(_DeviceResult):
     def constant(self, g):
         return self.matrix.data.constant(g) and self.input.constant(g)
 
-    def _bwd(self, sess, dU, grad):  # lin_tran.go:373-382
+    def _bwd(self, sess, dU, grad):  # lin_tran.go:373-382 -- both gradients from ONE call (af_lintran_backward)
         ctx, m = context(), self.matrix
-        if not m.data.constant(grad):
-            acc = sess.accumulator(grad, m.data)
-            check(ctx.lib.af_lintran_wgrad(ctx.h, dU.ptr, self.x.ptr, acc.ptr, m.rows, m.cols, self.n))
-        if not self.input.constant(grad):
-            d = ctx.empty(self.n * m.cols)
-            check(ctx.lib.af_lintran_igrad(ctx.h, dU.ptr, m.data.device().ptr, d.ptr, m.rows, m.cols, self.n))
+        acc = sess.accumulator(grad, m.data) if not m.data.constant(grad) else None
+        need_d = not self.input.constant(grad)
+        if acc is None and not need_d:
+            return
+        into = sess.accumulator(grad, self.input) if (need_d and isinstance(self.input, Variable) and self.input in grad) else None
+        d = into if into is not None else (ctx.empty(self.n * m.cols) if need_d else None)
+        check(ctx.lib.af_lintran_backward(ctx.h, dU.ptr, m.data.device().ptr if need_d else None, self.x.ptr, _p(acc), _p(d),
+                                          m.rows, m.cols, self.n, 1 if into is not None else 0))
+        if need_d and into is None:
             _down(self.input, sess, d, grad)
 
 
@@ -699,17 +702,27 @@ class _LinTranRResult(_DeviceResult):
     def constant(self, rg, g):
         return self.input.constant(rg, g) and self.rdata.constant(rg, g)
 
-    def _bwd_r(self, sess, dU, dUR, rgrad, grad):  # lin_tran.go:408-425
+    def _bwd_r(self, sess, dU, dUR, rgrad, grad):  # lin_tran.go:408-425 -- all four gradients from ONE call
         ctx, m = context(), self.matrix
         gacc = sess.accumulator(grad, m.data) if (grad is not None and not m.data.constant(grad)) else None
         racc = sess.accumulator(rgrad, m.data) if m.data in rgrad else None
-        if gacc is not None or racc is not None:
-            check(ctx.lib.af_lintran_wgrad_r(ctx.h, dU.ptr, dUR.ptr, self.x.ptr, _p(self.xr), _p(gacc), _p(racc),
-                                             m.rows, m.cols, self.n))
-        if not self.input.constant(rgrad, grad):
+        need_d = not self.input.constant(rgrad, grad)
+        if gacc is None and racc is None and not need_d:
+            return
+        # the input is an RVariable present in both maps: its PropagateRGradient (variable.go:113-123) is `+=` into the
+        # accumulators, which the call does itself
+        v = self.input.variable if isinstance(self.input, RVariable) else None
+        direct = need_d and v is not None and grad is not None and v in grad and v in rgrad
+        if direct:
+            d, dr = sess.accumulator(grad, v), sess.accumulator(rgrad, v)
+        elif need_d:
             d, dr = ctx.empty(self.n * m.cols), ctx.empty(self.n * m.cols)
-            check(ctx.lib.af_lintran_igrad_r(ctx.h, dU.ptr, dUR.ptr, self.rdata._d().ptr, _p(self.rdata._dr()),
-                                             d.ptr, dr.ptr, m.rows, m.cols, self.n))
+        else:
+            d = dr = None
+        check(ctx.lib.af_lintran_backward_r(ctx.h, dU.ptr, dUR.ptr, self.rdata._d().ptr if need_d else None,
+                                            _p(self.rdata._dr()) if need_d else None, self.x.ptr, _p(self.xr), _p(gacc), _p(racc),
+                                            _p(d), _p(dr), m.rows, m.cols, self.n, 1 if direct else 0))
+        if need_d and not direct:
             _down_r(self.input, sess, d, dr, rgrad, grad)
 
 

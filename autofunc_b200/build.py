@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libautofunc_b200.so")
-SOURCES = ["capi.cu", "gemm.cu", "elementwise.cu", "mathops.cu", "lstm.cu", "small_n.cu", "small_mlp.cu", "dp.cu", "lstm_step.cu"]
+SOURCES = ["capi.cu", "gemm.cu", "elementwise.cu", "mathops.cu", "lstm.cu", "small_n.cu", "small_mlp.cu", "dp.cu", "lstm_step.cu", "few_samples.cu"]
 HEADERS = ["common.h", "ew.cuh", "gemm_dmma.cuh", "streamk_walk.h", os.path.join("..", "..", "include", "autofunc_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",

@@ -89,9 +89,13 @@ static int ctx_create_impl(int device, void* stream, bool own, af_ctx** out) {
     delete c;
     return fail(AF_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   }
-  c->scratch_doubles = 8192;
+  c->scratch_doubles = kScratchDoubles;
   e = cudaMalloc(&c->scratch, c->scratch_doubles * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&c->fold_tickets, kFoldTickets * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(c->fold_tickets, 0, kFoldTickets * sizeof(unsigned));
   if (e != cudaSuccess) {
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->fold_tickets) cudaFree(c->fold_tickets);
     if (own) cudaStreamDestroy(c->stream);
     delete c;
     return cuda_fail(e, "cudaMalloc(scratch)");
@@ -111,6 +115,7 @@ int af_ctx_destroy(af_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   af_dp_destroy(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->fold_tickets) cudaFree(ctx->fold_tickets);
   if (ctx->barrier_word) cudaFree(ctx->barrier_word);
   for (cudaEvent_t ev : ctx->trace_events) cudaEventDestroy(ev);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -293,19 +298,27 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->small_mlp_off = value == 0;
     return AF_OK;
   }
+  if (!strcmp(name, "few_samples")) {
+    ctx->few_samples_off = value == 0;
+    return AF_OK;
+  }
+  if (!strcmp(name, "few_samples_blocks")) {
+    if (value < 1 || value > 16) return fail(AF_EINVAL, "few_samples_blocks must lie in [1, 16]");
+    ctx->few_samples_blocks = value;
+    return AF_OK;
+  }
+  if (!strcmp(name, "few_samples_tma")) {
+    ctx->few_samples_tma = value != 0;
+    return AF_OK;
+  }
+  if (!strcmp(name, "few_samples_min")) {
+    if (value < 1 || value > 17) return fail(AF_EINVAL, "few_samples_min must lie in [1, 17]");
+    ctx->few_samples_min = value;
+    return AF_OK;
+  }
   if (!strcmp(name, "deterministic")) {
     if (value != 0 && value != 1) return fail(AF_EINVAL, "deterministic must be 0 or 1");
     if (ctx->recording) return fail(AF_EINVAL, "deterministic cannot change while a graph is being recorded");
-    if (value == 1 && ctx->scratch_doubles < kDeterministicScratchDoubles) {
-      // ordered column sums park their per-block partial sums here (elementwise.cu: colsum_launch)
-      DeviceGuard guard(ctx->device);
-      AF_CUDA(cudaStreamSynchronize(ctx->stream));
-      double* bigger = nullptr;
-      AF_CUDA(cudaMalloc(&bigger, kDeterministicScratchDoubles * sizeof(double)));
-      if (ctx->scratch) cudaFree(ctx->scratch);
-      ctx->scratch = bigger;
-      ctx->scratch_doubles = kDeterministicScratchDoubles;
-    }
     ctx->deterministic = value == 1;
     return AF_OK;
   }
@@ -384,6 +397,11 @@ static int dense_fwd_impl(af_ctx* ctx, const double* W, const double* RW, const 
   GemmOperand B{W, dual ? RW : nullptr, LAY_KC, cols};
   GemmEpilogue e;
   e.epi = epi; e.out0 = Y; e.out1 = RY; e.ldo = rows; e.bias0 = b; e.bias1 = Rb;
+  // 9..16 samples (C1 is n = 10): one streaming tensor-core pass over W, K split over blocks and folded in order
+  if ((epi == EPI_STORE || epi == EPI_BIAS || epi == EPI_BIAS_SIGMOID) && few_samples_applicable(ctx, rows, cols, n, {W, RW, X, RX})) {
+    const int rc = few_samples_fwd_launch(ctx, W, RW, X, RX, rows, cols, n, e, dual);
+    if (rc != AF_ENOTSUP) return rc;
+  }
   if (small_n_applicable(ctx, rows, cols, n, {W, RW, X, RX}))  // the reference's Gemv branch, lin_tran.go:90-99,138-152
     return small_fwd_launch(ctx, W, RW, X, RX, rows, cols, n, e, dual);
   // at most 16 output rows and a large batch (a 10-class head): one streaming pass, not 64 x 16 tensor-core tiles
@@ -427,6 +445,10 @@ static int wgrad_impl(af_ctx* ctx, const double* U, const double* UR, const doub
   if (rows * cols == 0 || n == 0) return AF_OK;
   const bool dual = rgW != nullptr;
   if (!gW && !rgW) return AF_OK;
+  if (few_samples_applicable(ctx, rows, cols, n, {gW, rgW})) {  // 9..16 samples: the rank-n update as one streaming pass
+    const int rc = few_samples_bwd_launch(ctx, U, UR, nullptr, nullptr, X, RX, gW, rgW, nullptr, nullptr, nullptr, nullptr, rows, cols, n, false);
+    if (rc != AF_ENOTSUP) return rc;
+  }
   if (small_n_applicable(ctx, rows, cols, n, {X, RX, gW, rgW}, ctx->small_wgrad_max))  // Ger branch, lin_tran.go:187-196,223-241
     return small_wgrad_launch(ctx, U, dual ? UR : nullptr, X, dual ? RX : nullptr, gW, rgW, rows, cols, n);
   GemmOperand A{U, dual ? UR : nullptr, LAY_RC, rows};
@@ -460,6 +482,10 @@ static int igrad_impl(af_ctx* ctx, const double* U, const double* UR, const doub
   GemmEpilogue e;
   e.epi = S ? EPI_SIGMOID_BWD : EPI_STORE;
   e.out0 = D; e.out1 = DR; e.ldo = cols; e.s = S; e.rs = RS; e.lds = cols;
+  if (rows > 0 && few_samples_applicable(ctx, rows, cols, n, {D, DR, S, RS})) {  // 9..16 samples: one streaming pass over W
+    const int rc = few_samples_bwd_launch(ctx, U, UR, W, RW, nullptr, nullptr, nullptr, nullptr, D, DR, S, RS, rows, cols, n, false);
+    if (rc != AF_ENOTSUP) return rc;
+  }
   // Gemv T branch, lin_tran.go:285-288,329-334 (its row chunks meet in red.global.add.f64: not in deterministic mode)
   if (rows > 0 && !ctx->deterministic && small_n_applicable(ctx, rows, cols, n, {W, RW, D, DR}))
     return small_igrad_launch(ctx, U, UR, W, RW, rows, cols, n, e, dual);
@@ -488,6 +514,51 @@ int af_lintran_igrad_r(af_ctx* ctx, const double* U, const double* UR, const dou
   if (cols * n == 0) return AF_OK;
   AF_NEED(U); AF_NEED(W); AF_NEED(DR);
   return igrad_impl(ctx, U, UR, W, RW, nullptr, nullptr, D, DR, rows, cols, n);
+}
+
+// linTranRResult.PropagateRGradient (lin_tran.go:393-425) as one call: dataGradient(R) and inputGradient(R)
+static int backward_impl(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, const double* X,
+                         const double* RX, double* gW, double* rgW, double* D, double* DR, int64_t rows, int64_t cols, int64_t n,
+                         bool accumulate_input) {
+  const bool do_w = (gW || rgW) && rows * cols != 0 && n != 0, do_i = (D || DR) && cols * n != 0;
+  if (do_w && do_i && rows > 0 && few_samples_applicable(ctx, rows, cols, n, {gW, rgW, D, DR})) {  // one pass over W for both
+    const int rc = few_samples_bwd_launch(ctx, U, UR, W, RW, X, RX, gW, rgW, D, DR, nullptr, nullptr, rows, cols, n, accumulate_input);
+    if (rc != AF_ENOTSUP) return rc;
+  }
+  if (do_w) AF_TRY(wgrad_impl(ctx, U, UR, X, RX, gW, rgW, rows, cols, n));
+  if (!do_i) return AF_OK;
+  if (!accumulate_input) return igrad_impl(ctx, U, UR, W, RW, nullptr, nullptr, D, DR, rows, cols, n);
+  if (rows == 0) return AF_OK;  // D += 0
+  if (few_samples_applicable(ctx, rows, cols, n, {D, DR})) {
+    const int rc = few_samples_bwd_launch(ctx, U, UR, W, RW, nullptr, nullptr, nullptr, nullptr, D, DR, nullptr, nullptr, rows, cols, n, true);
+    if (rc != AF_ENOTSUP) return rc;
+  }
+  const bool dual = DR != nullptr;
+  GemmOperand A{U, dual ? UR : nullptr, LAY_KC, rows};
+  GemmOperand B{W, dual ? RW : nullptr, LAY_RC, cols};
+  GemmEpilogue e;
+  e.epi = EPI_ACCUM; e.out0 = D; e.out1 = DR; e.ldo = cols;
+  return gemm_launch(ctx, A, B, dual, n, cols, rows, e);
+}
+
+int af_lintran_backward(af_ctx* ctx, const double* U, const double* W, const double* X, double* gW, double* D, int64_t rows,
+                        int64_t cols, int64_t n, int accumulate_input) {
+  AF_CHECK_CTX(ctx); AF_TRY(check_dims(rows, cols, n));
+  AF_NEED(U);
+  if (gW) AF_NEED(X);
+  if (D) AF_NEED(W);
+  return backward_impl(ctx, U, nullptr, W, nullptr, X, nullptr, gW, nullptr, D, nullptr, rows, cols, n, accumulate_input != 0);
+}
+
+int af_lintran_backward_r(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, const double* X,
+                          const double* RX, double* gW, double* rgW, double* D, double* DR, int64_t rows, int64_t cols, int64_t n,
+                          int accumulate_input) {
+  AF_CHECK_CTX(ctx); AF_TRY(check_dims(rows, cols, n));
+  AF_NEED(U);
+  if (gW || rgW) AF_NEED(X);
+  if (D || DR) AF_NEED(W);
+  if (D && !DR) return fail(AF_EINVAL, "af_lintran_backward_r: d_DR is required with d_D (use af_lintran_backward for the plain form)");
+  return backward_impl(ctx, U, UR, W, RW, X, RX, gW, rgW, D, DR, rows, cols, n, accumulate_input != 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1049,6 +1120,17 @@ static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap, const M
       double* gW = m->grad[2 * l];
       double* rgW = R ? m->rgrad[2 * l] : nullptr;
       const int chunks = (m->grad_ready && l == 0 && m->grad_ready_chunks > 1) ? m->grad_ready_chunks : 1;
+      // 9..16 samples: one pass over W_l for its weight gradient AND the input gradient toward layer l - 1, the sigmoid
+      // backward of that layer applied by the block that folds the row strips (csrc/few_samples.cu)
+      if (chunks == 1 && l > 0 && few_samples_applicable(ctx, rows, cols, n, {gW, rgW, m->delta[l], m->rdelta[l], m->act[l], m->ract[l]})) {
+        const int rc = few_samples_bwd_launch(ctx, U, UR, m->param[2 * l], rv(2 * l), m->act[l], RX, gW, rgW, m->delta[l],
+                                              R ? m->rdelta[l] : nullptr, m->act[l], R ? m->ract[l] : nullptr, rows, cols, n, false);
+        if (rc != AF_ENOTSUP) {
+          AF_TRY(rc);
+          if (m->grad_ready) m->grad_ready(m->grad_ready_user, gW, block_end(l) - gW);
+          continue;
+        }
+      }
       if (chunks == 1) {
         AF_TRY(af_lintran_wgrad_r(ctx, U, UR, m->act[l], RX, gW, rgW, rows, cols, n));
         if (m->grad_ready)  // the whole layer block gW_l .. rgb_l is complete

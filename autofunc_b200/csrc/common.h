@@ -35,6 +35,13 @@ struct af_ctx {
   // per-block bias-gradient atomics are not used.  Results are then bit-identical from run to run, like the reference's
   // (a sequential program); the default (0) is the faster schedule whose last bits depend on the arrival order of partials.
   bool deterministic = false;
+  // LinTran passes for few_samples_min <= n <= 16 samples run as the streaming tensor-core kernels of few_samples.cu
+  // (af_set_option "few_samples" 0/1, "few_samples_min"): forward, and the weight + input gradient in ONE pass over W
+  bool few_samples_off = false;
+  int few_samples_min = 5;
+  int few_samples_blocks = 3;  // resident blocks per SM the few-samples launches are sized for ("few_samples_blocks")
+  bool few_samples_tma = true;  // backward pass through warp-private TMA rings ("few_samples_tma" 0: the register-staged kernel)
+  unsigned* fold_tickets = nullptr;  // ticket counters of the last-block-folds reductions (kFoldTickets, zero between launches)
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu
   bool lstm_split_off = true;   // opt-in (af_set_option "lstm_split" 1): two concurrent half-batch kernel chains; measured 24.6 vs 24.2 ms
@@ -77,8 +84,10 @@ struct af_ctx {
 
 namespace af {
 
-// device scratch once af_set_option "deterministic" 1 is in force: the ordered column sums' partial sums (8 MB)
-constexpr int64_t kDeterministicScratchDoubles = 1ll << 20;
+// device scratch of a context (16 MB): partial sums of SumAll, of the ordered column sums (deterministic mode) and of the
+// few-samples kernels' split extents.  Fixed size: captured graphs hold its address.
+constexpr int64_t kScratchDoubles = 1ll << 21;
+constexpr int kFoldTickets = 4096;
 
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
@@ -172,6 +181,8 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool du
 int gemm_make_map(af_ctx* ctx, CUtensorMap* map, const double* p, int layout, long long rows, long long kd, long long ld,
                   int tile_rows);
 int gemm_make_gate_map(af_ctx* ctx, CUtensorMap* map, const double* w4, long long H, long long C);
+int gemm_make_plain_map(af_ctx* ctx, CUtensorMap* map, const double* p, long long rows, long long cols, long long ld, int box_rows,
+                        int box_cols);
 
 // small-batch (n <= 16) streaming kernels, small_n.cu: the reference's Gemv / Ger branch
 bool small_n_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs,
@@ -182,6 +193,17 @@ int small_wgrad_launch(af_ctx* ctx, const double* U, const double* UR, const dou
                        double* rgW, long long rows, long long cols, long long n);
 int small_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, long long rows,
                        long long cols, long long n, const GemmEpilogue& e, bool dual);
+
+// LinTran with 9..16 samples (few_samples.cu): streaming tensor-core passes over W.  The launchers return AF_ENOTSUP --
+// nothing launched, no error text -- when a shape does not fit the scratch; callers then take their other path.
+bool few_samples_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs);
+int few_samples_fwd_launch(af_ctx* ctx, const double* W, const double* RW, const double* X, const double* RX, long long rows,
+                           long long cols, long long n, const GemmEpilogue& e, bool dual);
+// weight gradient (gW / rgW, either may be NULL) and input gradient (D / DR; both NULL = none) in one pass; S / RS: sigmoid
+// backward of the layer below applied to the input gradient; accumulate_d: D += instead of D =
+int few_samples_bwd_launch(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, const double* X,
+                           const double* RX, double* gW, double* rgW, double* D, double* DR, const double* S, const double* RS,
+                           long long rows, long long cols, long long n, bool accumulate_d);
 
 // input gradient through a layer with at most 16 output rows and a large batch (streaming, small_n.cu)
 bool few_rows_igrad_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs);

@@ -53,6 +53,22 @@ int gemm_make_map(af_ctx* ctx, CUtensorMap* map, const double* p, int layout, lo
   return AF_OK;
 }
 
+// Unswizzled 2-D map of a row-major matrix (element (r, c) at p[r*ld + c]) with box {box_cols, box_rows}: the box lands
+// in shared memory as box_rows lines of box_cols doubles (few_samples.cu: the sample-side operands U / UR).
+int gemm_make_plain_map(af_ctx* ctx, CUtensorMap* map, const double* p, long long rows, long long cols, long long ld, int box_rows,
+                        int box_cols) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(p), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AF_ECUDA, "cuTensorMapEncodeTiled (plain map) failed with CUresult " + std::to_string((int)r));
+  return AF_OK;
+}
+
 // The stacked LSTM gate matrix W4 (4H x C, gate-major rows: bench/lstm.go's four H x C matrices one after another) as a
 // 3-D tensor {k, unit, gate} with box {16, 16, 4}: one box = the 64 rows {4 gates} x {16 units} of a forward-step tile
 // (gemm_dmma_kernel SPECIAL = 1), landing in shared memory as 64 consecutive 128-byte lines exactly like a KC tile.

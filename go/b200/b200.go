@@ -359,14 +359,16 @@ func (r *linTranRResult) PropagateRGradient(u, uR linalg.Vector, rg autofunc.RGr
 func (r *linTranRResult) bwdR(s *session, u, uR *devVec, rg autofunc.RGradient, g autofunc.Gradient) {
 	m := r.m
 	gW, rgW := s.gradAcc(g, m.Data), s.rgradAcc(rg, m.Data)
-	if gW != nil || rgW != nil {
-		check(C.af_lintran_wgrad_r(context(), u.p, uR.p, r.x.p, ptr(r.xR), ptr(gW), ptr(rgW),
-			C.int64_t(m.Rows), C.int64_t(m.Cols), C.int64_t(r.n)))
-	}
-	if !r.in.Constant(rg, g) {
+	if r.in.Constant(rg, g) {
+		if gW != nil || rgW != nil {
+			check(C.af_lintran_wgrad_r(context(), u.p, uR.p, r.x.p, ptr(r.xR), ptr(gW), ptr(rgW),
+				C.int64_t(m.Rows), C.int64_t(m.Cols), C.int64_t(r.n)))
+		}
+	} else {
+		// both gradients from one call: with 9..16 samples the library streams W once for the two of them
 		d, dR := newDev(r.n*m.Cols), newDev(r.n*m.Cols)
-		check(C.af_lintran_igrad_r(context(), u.p, uR.p, r.w.p, ptr(r.rw), d.p, dR.p,
-			C.int64_t(m.Rows), C.int64_t(m.Cols), C.int64_t(r.n)))
+		check(C.af_lintran_backward_r(context(), u.p, uR.p, r.w.p, ptr(r.rw), r.x.p, ptr(r.xR), ptr(gW), ptr(rgW), d.p, dR.p,
+			C.int64_t(m.Rows), C.int64_t(m.Cols), C.int64_t(r.n), C.int(0)))
 		downR(r.in, s, d, dR, rg, g)
 	}
 }

@@ -92,6 +92,11 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * "dp_max_ctas": CTA cap of the context's communicator (ncclConfig_t.maxCTAs; default 8, 0 = NCCL's own choice); read by
  * af_dp_init.  "dp_reserve_sms": SMs the plans leave to an all-reduce that runs beside their contractions (default =
  * dp_max_ctas): stream-K launches issued while a reduce is in flight are sized for sm_count - dp_reserve_sms SMs.
+ * "few_samples": 1 (default) = LinTran passes with few_samples_min..16 samples ("few_samples_min", default 5) run as the
+ * streaming tensor-core kernels of csrc/few_samples.cu (forward; weight + input gradient in one pass over W); 0 = the
+ * Gemv / Ger kernels up to 8 samples and the transposed narrow tiles / rank-n tiles of the contraction kernel above.
+ * "few_samples_blocks": resident blocks per SM those launches are sized for (default 3); "few_samples_tma": 1 (default) =
+ * the backward pass brings its operands through warp-private TMA rings, 0 = register-staged loads.
  * "deterministic": 1 = every floating-point sum is taken in an order fixed by the shapes alone, so results are
  * bit-identical from run to run like the reference's (a sequential program): contractions compute whole output tiles per
  * CTA (no split-K / stream-K partial tiles combined with red.global.add.f64), column sums fold their per-block partial
@@ -137,6 +142,19 @@ int af_lintran_igrad(af_ctx*, const double* d_U, const double* d_W, double* d_D,
 int af_lintran_igrad_r(af_ctx*, const double* d_U, const double* d_UR, const double* d_W,
                        const double* d_RW, double* d_D, double* d_DR,
                        int64_t rows, int64_t cols, int64_t n);
+
+/* linTranResult.PropagateGradient / linTranRResult.PropagateRGradient as ONE call (lin_tran.go:361-391 / 393-425): the
+ * weight gradient (G3+G4) and the input gradient (G5+G6) from the same upstream.
+ *   d_gW / d_rgW NULL: W is not in that map (skipped);  d_D and d_DR both NULL: the input is constant (lin_tran.go:419).
+ *   accumulate_input != 0: D += U W and DR += UR W + U RW -- what the input's own PropagateRGradient does next when it is
+ *   a Variable (variable.go:43-47,113-123) -- instead of D = ..., DR = ...
+ * For 9..16 samples (the reference's LinTranBenchmark runs 10) one streaming pass over W serves both gradients; other
+ * batch sizes run the two passes of af_lintran_wgrad_r and af_lintran_igrad_r.                     */
+int af_lintran_backward(af_ctx*, const double* d_U, const double* d_W, const double* d_X, double* d_gW, double* d_D,
+                        int64_t rows, int64_t cols, int64_t n, int accumulate_input);
+int af_lintran_backward_r(af_ctx*, const double* d_U, const double* d_UR, const double* d_W, const double* d_RW,
+                          const double* d_X, const double* d_RX, double* d_gW, double* d_rgW, double* d_D,
+                          double* d_DR, int64_t rows, int64_t cols, int64_t n, int accumulate_input);
 
 /* ---- LinAdd (lin_add.go) in its batched form Add(x, Repeat(b,n)) ------------------------- */
 /* Y = X + b (per sample), RY = RX + Rb.  lin_add.go:13-50; arithmetic.go:17; slices.go:216.    */

@@ -834,12 +834,15 @@ class LinTranRResult : public DeviceRResult {
   void bwdR(Session& s, Dev u, Dev uR, RGradient& rgrad, Gradient* grad) override {  // lin_tran.go:408-425
     Variable* w = m_.Data.get();
     Dev gacc = AccOrNull(s, grad, w), racc = AccOrNull(s, &rgrad, w);
-    if (gacc || racc)
-      check(af_lintran_wgrad_r(ctx(), u->p, uR->p, x_->p, ptr(xr_), mptr(gacc), mptr(racc), m_.Rows, m_.Cols, n_));
-    if (!in_->Constant(rgrad, grad)) {
+    const bool down = !in_->Constant(rgrad, grad);
+    if (!down) {
+      if (gacc || racc)
+        check(af_lintran_wgrad_r(ctx(), u->p, uR->p, x_->p, ptr(xr_), mptr(gacc), mptr(racc), m_.Rows, m_.Cols, n_));
+    } else {
+      // both gradients from one call: with 9..16 samples the library streams W once for the two of them
       Dev d = DevVec::Empty((int64_t)n_ * m_.Cols), dr = DevVec::Empty((int64_t)n_ * m_.Cols);
-      check(af_lintran_igrad_r(ctx(), u->p, uR->p, rdata_->dev()->p, ptr(rdata_->devR()), d->p, dr->p, m_.Rows,
-                               m_.Cols, n_));
+      check(af_lintran_backward_r(ctx(), u->p, uR->p, rdata_->dev()->p, ptr(rdata_->devR()), x_->p, ptr(xr_), mptr(gacc),
+                                  mptr(racc), d->p, dr->p, m_.Rows, m_.Cols, n_, 0));
       in_->bwdR(s, d, dr, rgrad, grad);
     }
   }

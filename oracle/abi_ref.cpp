@@ -162,6 +162,31 @@ int af_lintran_igrad_r(af_ctx* c, const double* U, const double* UR, const doubl
 int af_lintran_igrad(af_ctx* c, const double* U, const double* W, double* D, int64_t rows, int64_t cols, int64_t n) {
   return af_lintran_igrad_r(c, U, nullptr, W, nullptr, D, nullptr, rows, cols, n);
 }
+// linTranRResult.PropagateRGradient as one call (lin_tran.go:393-425): both gradients; accumulate_input: D += , DR +=
+int af_lintran_backward_r(af_ctx* c, const double* U, const double* UR, const double* W, const double* RW, const double* X,
+                          const double* RX, double* gW, double* rgW, double* D, double* DR, int64_t rows, int64_t cols, int64_t n,
+                          int accumulate_input) {
+  CTX(c);
+  SHAPE(rows, cols, n);
+  if (gW || rgW) {
+    int rc = af_lintran_wgrad_r(c, U, UR, X, RX, gW, rgW, rows, cols, n);
+    if (rc) return rc;
+  }
+  if (!D && !DR) return AF_OK;
+  if (!accumulate_input) return af_lintran_igrad_r(c, U, UR, W, RW, D, DR, rows, cols, n);
+  std::vector<double> d((size_t)(cols * n)), dr((size_t)(cols * n));
+  int rc = af_lintran_igrad_r(c, U, UR, W, RW, D ? d.data() : nullptr, DR ? dr.data() : nullptr, rows, cols, n);
+  if (rc) return rc;
+  for (int64_t i = 0; i < cols * n; i++) {
+    if (D) D[i] += d[i];
+    if (DR) DR[i] += dr[i];
+  }
+  return AF_OK;
+}
+int af_lintran_backward(af_ctx* c, const double* U, const double* W, const double* X, double* gW, double* D, int64_t rows,
+                        int64_t cols, int64_t n, int accumulate_input) {
+  return af_lintran_backward_r(c, U, nullptr, W, nullptr, X, nullptr, gW, nullptr, D, nullptr, rows, cols, n, accumulate_input);
+}
 
 // ---- LinAdd, batched (lin_add.go:13-109) ----------------------------------------------------------------------
 int af_bias_fwd_r(af_ctx* c, const double* X, const double* RX, const double* b, const double* Rb, double* Y,

@@ -119,12 +119,25 @@ def lintran_config(ctx, steps):
     gW, rgW, gX, rgX = ctx.zeros(rows * cols), ctx.zeros(rows * cols), ctx.zeros(n * cols), ctx.zeros(n * cols)
     L, h = ctx.lib, ctx.h
 
+    split = os.environ.get("AF_C1_SPLIT") == "1"  # A/B: the round-1 call sequence (three passes + two accumulations)
+
+    only = os.environ.get("AF_C1_ONLY", "")  # timing experiments: "fwd" or "bwd" alone
+
     def step():  # bench/lintran.go:83-89: BatchR + PropagateRGradient with W and X both in the maps
-        api.check(L.af_lintran_fwd_r(h, d["W"].ptr, d["RW"].ptr, d["X"].ptr, d["RX"].ptr, Y.ptr, RY.ptr, rows, cols, n))
-        api.check(L.af_lintran_wgrad_r(h, d["U"].ptr, d["UR"].ptr, d["X"].ptr, d["RX"].ptr, gW.ptr, rgW.ptr, rows, cols, n))
-        api.check(L.af_lintran_igrad_r(h, d["U"].ptr, d["UR"].ptr, d["W"].ptr, d["RW"].ptr, D.ptr, DR.ptr, rows, cols, n))
-        api.check(L.af_axpy(h, 1.0, D.ptr, gX.ptr, n * cols))
-        api.check(L.af_axpy(h, 1.0, DR.ptr, rgX.ptr, n * cols))
+        if only != "bwd":
+            api.check(L.af_lintran_fwd_r(h, d["W"].ptr, d["RW"].ptr, d["X"].ptr, d["RX"].ptr, Y.ptr, RY.ptr, rows, cols, n))
+        if only == "fwd":
+            return
+        if split:
+            api.check(L.af_lintran_wgrad_r(h, d["U"].ptr, d["UR"].ptr, d["X"].ptr, d["RX"].ptr, gW.ptr, rgW.ptr, rows, cols, n))
+            api.check(L.af_lintran_igrad_r(h, d["U"].ptr, d["UR"].ptr, d["W"].ptr, d["RW"].ptr, D.ptr, DR.ptr, rows, cols, n))
+            api.check(L.af_axpy(h, 1.0, D.ptr, gX.ptr, n * cols))
+            api.check(L.af_axpy(h, 1.0, DR.ptr, rgX.ptr, n * cols))
+        else:
+            # linTranRResult.PropagateRGradient (lin_tran.go:393-425) as one call: both weight gradients, and the input
+            # gradients added into the input variable's accumulators (variable.go:113-123)
+            api.check(L.af_lintran_backward_r(h, d["U"].ptr, d["UR"].ptr, d["W"].ptr, d["RW"].ptr, d["X"].ptr, d["RX"].ptr,
+                                              gW.ptr, rgW.ptr, gX.ptr, rgX.ptr, rows, cols, n, 1))
         reduce_slab(gW.ptr, rows * cols)   # the parameter's accumulators; X's gradients stay with their shard
         reduce_slab(rgW.ptr, rows * cols)
     ms_eager = timed(step, steps)
@@ -207,14 +220,14 @@ def main():
     if WORLD > 1:
         from autofunc_b200 import parallel
         parallel.dp_init_torch(ctx, LOCAL)  # torch.distributed only ships the communicator id
-    for opt in ("pdl", "small_mlp", "small_n", "lstm_split", "lstm_fused", "persist_tiles", "sk_bias"):  # A/B switches: AF_OPT_PDL=0 etc.
+    for opt in ("pdl", "small_mlp", "small_n", "lstm_split", "lstm_fused", "persist_tiles", "sk_bias", "few_samples", "few_samples_min", "few_samples_blocks", "few_samples_tma", "deterministic"):  # A/B switches: AF_OPT_PDL=0 etc.
         v = os.environ.get("AF_OPT_" + opt.upper())
         if v is not None:
             api.check(ctx.lib.af_set_option(ctx.h, opt.encode(), int(v)))
     if "c1" in which:
         lintran_config(ctx, 50)
     if "c2" in which:
-        for n in (1, 4, 8, 64, 1024):
+        for n in (1, 4, 8, 10, 16, 64, 1024):
             mlp_config(ctx, f"C2 mlp n={n}", [1000, 2000, 512, 10], n, 20, executed_flops([1000, 2000, 512, 10], n))
     if "c3" in which:
         s = [2048] * 5

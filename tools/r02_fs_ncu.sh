@@ -1,0 +1,5 @@
+#!/bin/bash
+t=${1:-r02fsn}
+mkdir -p gpurun_out
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:few_samples -s 4 -c 2 -f -o gpurun_out/${t}_c1_full env AF_C1_GRAPH=0 python tools/bench_configs.py c1 > gpurun_out/${t}_ncu_full.log 2>&1; echo "ncu rc=$?"
+ls -la gpurun_out/${t}_c1_full.ncu-rep
