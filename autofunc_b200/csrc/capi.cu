@@ -302,6 +302,11 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->few_samples_off = value == 0;
     return AF_OK;
   }
+  if (!strcmp(name, "few_rows_wgrad")) {
+    if (value < 0 || value > 2) return fail(AF_EINVAL, "few_rows_wgrad must be 0, 1 or 2");
+    ctx->few_rows_wgrad = value;
+    return AF_OK;
+  }
   if (!strcmp(name, "few_samples_blocks")) {
     if (value < 1 || value > 16) return fail(AF_EINVAL, "few_samples_blocks must lie in [1, 16]");
     ctx->few_samples_blocks = value;
@@ -449,6 +454,10 @@ static int wgrad_impl(af_ctx* ctx, const double* U, const double* UR, const doub
     const int rc = few_samples_bwd_launch(ctx, U, UR, nullptr, nullptr, X, RX, gW, rgW, nullptr, nullptr, nullptr, nullptr, rows, cols, n, false);
     if (rc != AF_ENOTSUP) return rc;
   }
+  // <= 16 output rows and a large batch (the 10-class head): the streaming kernel with ordered sums
+  if ((ctx->few_rows_wgrad == 2 || (ctx->few_rows_wgrad == 1 && ctx->deterministic)) &&
+      few_rows_wgrad_applicable(ctx, rows, cols, n, {X, RX, gW, rgW}))
+    return few_rows_wgrad_launch(ctx, U, UR, X, RX, gW, rgW, rows, cols, n);
   if (small_n_applicable(ctx, rows, cols, n, {X, RX, gW, rgW}, ctx->small_wgrad_max))  // Ger branch, lin_tran.go:187-196,223-241
     return small_wgrad_launch(ctx, U, dual ? UR : nullptr, X, dual ? RX : nullptr, gW, rgW, rows, cols, n);
   GemmOperand A{U, dual ? UR : nullptr, LAY_RC, rows};

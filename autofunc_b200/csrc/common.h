@@ -39,6 +39,8 @@ struct af_ctx {
   // (af_set_option "few_samples" 0/1, "few_samples_min"): forward, and the weight + input gradient in ONE pass over W
   bool few_samples_off = false;
   int few_samples_min = 5;
+  // the <= 16-row weight gradient over a large batch (few_rows_wgrad_kernel): 0 never, 1 in deterministic mode only, 2 always
+  int few_rows_wgrad = 1;
   int few_samples_blocks = 3;  // resident blocks per SM the few-samples launches are sized for ("few_samples_blocks")
   bool few_samples_tma = true;  // backward pass through warp-private TMA rings ("few_samples_tma" 0: the register-staged kernel)
   unsigned* fold_tickets = nullptr;  // ticket counters of the last-block-folds reductions (kFoldTickets, zero between launches)
@@ -204,6 +206,11 @@ int few_samples_fwd_launch(af_ctx* ctx, const double* W, const double* RW, const
 int few_samples_bwd_launch(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW, const double* X,
                            const double* RX, double* gW, double* rgW, double* D, double* DR, const double* S, const double* RS,
                            long long rows, long long cols, long long n, bool accumulate_d);
+
+// weight gradient of a layer with at most 16 output rows and a large batch (few_samples.cu): deterministic two-level sum
+bool few_rows_wgrad_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs);
+int few_rows_wgrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* X, const double* RX, double* gW, double* rgW,
+                          long long rows, long long cols, long long n);
 
 // input gradient through a layer with at most 16 output rows and a large batch (streaming, small_n.cu)
 bool few_rows_igrad_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs);

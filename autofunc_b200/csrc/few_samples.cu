@@ -683,6 +683,121 @@ few_samples_bwd_tma_kernel(const __grid_constant__ CUtensorMap mW, const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// weight gradient of a layer with FEW OUTPUT ROWS and a large batch (the bench network's 10-class head: gW[10][512] +=
+// U^T X over 4096 samples; lin_tran.go:179-270).  The contraction runs over the batch, the output is tiny: as
+// tensor-core tiles it needs split-K (atomics) or, in deterministic mode, eight whole-K tiles on eight CTAs (207 us on
+// the bench step).  Here a block owns 64 columns and a chunk of samples; its eight warps take a slice of the chunk each
+// (lane = column pair, rows x 2 x {g, rg} accumulators in registers, the X / RX stream coalesced), add their sums in warp
+// order through shared memory, and the chunks meet in the ordered last-block fold: deterministic, no atomics, no zeroing.
+// ------------------------------------------------------------------------------------------------------------------
+struct FrWgradArgs {
+  const double* U; const double* UR; const double* X; const double* RX;
+  double* gW; double* rgW;
+  double* part; unsigned* tickets;
+  int rows, cols, chunks, dual;
+  long long n, per_chunk;   // samples per chunk (a multiple of 8)
+};
+
+template <int MMAX>
+__global__ void __launch_bounds__(256, MMAX <= 8 ? 2 : 1) few_rows_wgrad_kernel(const FrWgradArgs a) {
+  constexpr int NQ = 2 * MMAX * 2;                 // {g, rg} x row x pair
+  __shared__ double buf[NQ * 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 64 + 2 * lane;
+  const bool col_ok = c < a.cols;
+  const bool has_ur = a.dual && a.UR != nullptr, has_rx = a.dual && a.RX != nullptr;
+  const long long per_warp = a.per_chunk >> 3;
+  const long long s0 = (long long)blockIdx.y * a.per_chunk + warp * per_warp;
+  long long s1 = s0 + per_warp;
+  if (s1 > a.n) s1 = a.n;
+  double g[MMAX][2], rg[MMAX][2];
+#pragma unroll
+  for (int m = 0; m < MMAX; ++m) g[m][0] = g[m][1] = rg[m][0] = rg[m][1] = 0.0;
+  constexpr int UNR = 4;                      // samples whose X / RX loads are in flight together
+  for (long long i = s0; i < s1; i += UNR) {
+    double2 x[UNR], rx[UNR];
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      const bool ok = col_ok && i + q < s1;
+      x[q] = ok ? ld2g(a.X + (i + q) * a.cols + c) : make_double2(0.0, 0.0);
+      rx[q] = (ok && has_rx) ? ld2g(a.RX + (i + q) * a.cols + c) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < UNR; ++q) {
+      if (i + q < s1) {
+        const double* u = a.U + (i + q) * a.rows;
+        const double* ur = a.UR + (i + q) * a.rows;
+#pragma unroll
+        for (int m = 0; m < MMAX; ++m) {
+          if (m < a.rows) {
+            const double um = __ldg(u + m);          // the same address in every lane: one broadcast transaction
+            g[m][0] = fma(um, x[q].x, g[m][0]); g[m][1] = fma(um, x[q].y, g[m][1]);
+            if (a.dual) {
+              rg[m][0] = fma(um, rx[q].x, rg[m][0]); rg[m][1] = fma(um, rx[q].y, rg[m][1]);
+              if (has_ur) {
+                const double urm = __ldg(ur + m);
+                rg[m][0] = fma(urm, x[q].x, rg[m][0]); rg[m][1] = fma(urm, x[q].y, rg[m][1]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // the eight warps' sums, added in warp order
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int m = 0; m < MMAX; ++m)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int q0 = ((0 * MMAX + m) * 2 + e) * 32 + lane, q1 = ((1 * MMAX + m) * 2 + e) * 32 + lane;
+          buf[q0] = (w == 0 ? 0.0 : buf[q0]) + g[m][e];
+          buf[q1] = (w == 0 ? 0.0 : buf[q1]) + rg[m][e];
+        }
+    }
+    __syncthreads();
+  }
+  constexpr int PER = NQ * 32 / 256;
+  const int colblocks = gridDim.x;
+  double total[PER];
+#pragma unroll
+  for (int r = 0; r < PER; ++r) total[r] = buf[r * 256 + threadIdx.x];
+  if (a.chunks > 1) {
+    double* mine = a.part + ((long long)blockIdx.y * colblocks + blockIdx.x) * (NQ * 32);
+#pragma unroll
+    for (int r = 0; r < PER; ++r) mine[r * 256 + threadIdx.x] = total[r];
+    if (!fold_ticket(a.tickets + blockIdx.x, (unsigned)a.chunks)) return;
+    const double* p = a.part + (long long)blockIdx.x * (NQ * 32);
+    const long long stride = (long long)colblocks * (NQ * 32);
+#pragma unroll
+    for (int r = 0; r < PER; ++r) total[r] = 0.0;
+    for (int c0 = 0; c0 < a.chunks; c0 += 4) {   // chunk order, four chunks' loads in flight per element
+      double x[PER][4];
+#pragma unroll
+      for (int r = 0; r < PER; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[r][q] = __ldcg(p + (long long)min(c0 + q, a.chunks - 1) * stride + r * 256 + threadIdx.x);
+#pragma unroll
+      for (int r = 0; r < PER; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) total[r] += (c0 + q < a.chunks) ? x[r][q] : 0.0;
+    }
+  }
+  // element (q, lane): q = ((which * MMAX + m) * 2 + pair)  ->  gW / rgW [m][blockIdx.x * 64 + 2 lane + pair]
+#pragma unroll
+  for (int r = 0; r < PER; ++r) {
+    const int e = r * 256 + threadIdx.x;
+    const int l = e & 31, q = e >> 5;
+    const int pair = q & 1, m = (q >> 1) % MMAX, which = q / (2 * MMAX);
+    const int k = blockIdx.x * 64 + 2 * l + pair;
+    if (m >= a.rows || k >= a.cols) continue;
+    double* out = which ? a.rgW : a.gW;
+    if (out) out[(long long)m * a.cols + k] += total[r];
+  }
+}
+
 bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // resident blocks per SM for a kernel at a given dynamic shared-memory size (queried once per size class)
@@ -781,6 +896,22 @@ int launch_bwd_tma(af_ctx* ctx, FsBwdArgs& a) {
   return after_launch(ctx, "few_samples_bwd_tma_kernel", KIND_SMALL_N, bytes);
 }
 
+template <int MMAX>
+int launch_few_rows_wgrad(af_ctx* ctx, FrWgradArgs& a) {
+  constexpr int NQ = 2 * MMAX * 2;
+  auto kern = few_rows_wgrad_kernel<MMAX>;
+  const long long colblocks = (a.cols + 63) / 64;
+  long long chunks = ((MMAX <= 8 ? 2ll : 1ll) * ctx->sm_count) / colblocks;   // resident blocks per SM (register-bound)
+  const long long max_by_n = (a.n + 63) / 64, max_by_scratch = ctx->scratch_doubles / (colblocks * NQ * 32);
+  if (chunks > max_by_n) chunks = max_by_n;
+  if (chunks > max_by_scratch) chunks = max_by_scratch;
+  if (chunks < 1) chunks = 1;
+  a.per_chunk = ((a.n + chunks - 1) / chunks + 7) / 8 * 8;
+  a.chunks = (int)((a.n + a.per_chunk - 1) / a.per_chunk);
+  kern<<<dim3((unsigned)colblocks, (unsigned)a.chunks), 256, 0, ctx->stream>>>(a);
+  return after_launch(ctx, "few_rows_wgrad_kernel", KIND_SMALL_N, 8.0 * a.n * a.cols * ((a.dual && a.RX) ? 2 : 1));
+}
+
 }  // namespace
 
 // 16-byte pairs everywhere: even pitches, aligned bases; the fold groups' ticket counters bound the extents
@@ -828,6 +959,26 @@ int few_samples_bwd_launch(af_ctx* ctx, const double* U, const double* UR, const
   if (n <= 8) return launch_bwd<2>(ctx, a);
   if (n <= 12) return launch_bwd<3>(ctx, a);
   return launch_bwd<4>(ctx, a);
+}
+
+// gW (rows x cols, rows <= 16) += U^T X over a large batch, rgW += UR^T X + U^T RX; deterministic
+bool few_rows_wgrad_applicable(af_ctx* ctx, long long rows, long long cols, long long n, std::initializer_list<const void*> ptrs) {
+  if (ctx->gemm_path == 1 || ctx->small_n_off || !ctx->fold_tickets) return false;
+  if (rows < 1 || rows > 16 || n < 64 || cols < 2 || (cols & 1) || (cols + 63) / 64 > kFoldTickets || cols > (1 << 28)) return false;
+  for (const void* p : ptrs)
+    if (p && !aligned16p(p)) return false;
+  return true;
+}
+
+int few_rows_wgrad_launch(af_ctx* ctx, const double* U, const double* UR, const double* X, const double* RX, double* gW, double* rgW,
+                          long long rows, long long cols, long long n) {
+  FrWgradArgs a{};
+  a.dual = rgW ? 1 : 0;
+  a.U = U; a.UR = a.dual ? UR : nullptr; a.X = X; a.RX = a.dual ? RX : nullptr; a.gW = gW; a.rgW = rgW;
+  a.part = ctx->scratch; a.tickets = ctx->fold_tickets;
+  a.rows = (int)rows; a.cols = (int)cols; a.n = n;
+  if (rows <= 8) return launch_few_rows_wgrad<8>(ctx, a);
+  return rows <= 12 ? launch_few_rows_wgrad<12>(ctx, a) : launch_few_rows_wgrad<16>(ctx, a);
 }
 
 }  // namespace af

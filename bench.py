@@ -315,6 +315,9 @@ def gpu_arm(args):
         v = getattr(args, name)
         if v is not None:
             ctx.set_option(name, v)
+    for kv in args.opt:  # A/B switches of the library by name (af_set_option), e.g. --opt few_rows_wgrad=2
+        name, _, v = kv.partition("=")
+        ctx.set_option(name, int(v))
     dp_info = None
     if world > 1:
         # the communicator lives inside libautofunc_b200 (af_dp_init); torch only carries its 128-byte id
@@ -694,6 +697,7 @@ def main():
                     help="multi-wave contractions as persistent CTAs over whole tiles: 0 off, 1 contiguous, 2 wave order")
     ap.add_argument("--deterministic", type=int, default=None, choices=[0, 1],
                     help="1: af_set_option deterministic (run-to-run bit-identical sums: whole tiles per CTA, ordered column sums); default 0")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="af_set_option(NAME, VALUE) before the run (A/B switches)")
     ap.add_argument("--dp-mode", dest="dp_mode", default="deferred", choices=sorted(DP_MODES),
                     help="N > 1: how the library schedules the sum over ranks (include/autofunc_b200.h AF_DP_*)")
     ap.add_argument("--dp-max-ctas", dest="dp_max_ctas", type=int, default=None, help="CTA cap of the library's NCCL communicator (default 8)")

@@ -201,3 +201,44 @@ def test_lintran_benchmark_step_through_the_operator_api(api):
     for name, want, got in zip(("Output", "ROutput", "grad[W]", "grad[X]", "rgrad[W]", "rgrad[X]", "plain grad[W]", "plain grad[X]"),
                                results[0], results[1]):
         close(got, want, name)
+
+
+# ---- the <= 16-row weight gradient over a large batch (few_rows_wgrad_kernel: the 10-class head of bench/mlp.go) ----
+@pytest.mark.parametrize("rows,cols,n", [(10, 512, 4096),   # the bench network's head at the headline batch
+                                        (1, 2, 64), (8, 66, 257), (12, 130, 1000), (16, 1000, 333), (9, 4098, 70)])
+@pytest.mark.parametrize("variant", ["dual", "no_rx", "single"])
+def test_few_rows_weight_gradient_matches_oracle_and_repeats_bit_for_bit(api, rows, cols, n, variant):
+    """dataGradient / dataGradientR (lin_tran.go:179-270) with few output rows, `+=` into non-zero accumulators; the
+    kernel's sums are ordered (warp order, then chunk order), so two runs give the same bits."""
+    ctx = api.context()
+    ctx.set_option("few_rows_wgrad", 2)
+    try:
+        X, RX = ref.splitmix_uniform(3, n * cols), ref.splitmix_uniform(4, n * cols)
+        U, UR = ref.splitmix_uniform(5, n * rows), ref.splitmix_uniform(6, n * rows)
+        G0, RG0 = ref.splitmix_uniform(7, rows * cols), ref.splitmix_uniform(8, rows * cols)
+        wv = ref.Variable(np.zeros(rows * cols))
+        lt = ref.LinTran(wv, rows, cols)
+        g, rg = {wv: G0.copy()}, RG0.copy()
+        lt.data_gradient(U, X, g)
+        lt.data_gradient_r(U, UR, X, RX if variant == "dual" else np.zeros_like(X), rg)
+        L, h = ctx.lib, ctx.h
+        dX, dRX, dU, dUR = (ctx.upload(a) for a in (X, RX, U, UR))
+        runs = []
+        for _ in range(3):
+            dG, dRG = ctx.upload(G0), ctx.upload(RG0)
+            before = ctx.launch_count()
+            if variant == "single":
+                api.check(L.af_lintran_wgrad(h, dU.ptr, dX.ptr, dG.ptr, rows, cols, n))
+            else:
+                api.check(L.af_lintran_wgrad_r(h, dU.ptr, dUR.ptr, dX.ptr, dRX.ptr if variant == "dual" else None,
+                                               dG.ptr, dRG.ptr, rows, cols, n))
+            assert ctx.launch_count() - before == 1, "one launch: no zeroing, no separate fold kernel"
+            runs.append((dG.numpy(), dRG.numpy()))
+        close(runs[0][0], g[wv], "G3 dataGradient")
+        if variant != "single":
+            close(runs[0][1], rg, "G4 dataGradientR")
+        for a, b in runs[1:]:
+            assert np.array_equal(a.view(np.uint64), runs[0][0].view(np.uint64))
+            assert np.array_equal(b.view(np.uint64), runs[0][1].view(np.uint64))
+    finally:
+        ctx.set_option("few_rows_wgrad", 1)
