@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 #include <vector>
 
 #include "common.h"
@@ -281,6 +282,14 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->small_n_off = value == 0;
     return AF_OK;
   }
+  if (!strcmp(name, "short_rows")) {
+    ctx->short_rows_off = value == 0;
+    return AF_OK;
+  }
+  if (!strcmp(name, "fused_colsum")) {
+    ctx->fused_colsum_off = value == 0;
+    return AF_OK;
+  }
   if (!strcmp(name, "lstm_split")) {
     ctx->lstm_split_off = value == 0;
     return AF_OK;
@@ -482,8 +491,11 @@ int af_lintran_wgrad_r(af_ctx* ctx, const double* U, const double* UR, const dou
   return wgrad_impl(ctx, U, UR, X, RX, gW, rgW, rows, cols, n);
 }
 
+// colsum0 / colsum1 / colsum_done (optional, with S): the kernels that can also add the column sums of D / DR -- the bias
+// gradient of the layer below, lin_add.go:94-104 -- to colsum0 / colsum1 and then set *colsum_done
 static int igrad_impl(af_ctx* ctx, const double* U, const double* UR, const double* W, const double* RW,
-                      const double* S, const double* RS, double* D, double* DR, int64_t rows, int64_t cols, int64_t n) {
+                      const double* S, const double* RS, double* D, double* DR, int64_t rows, int64_t cols, int64_t n,
+                      double* colsum0 = nullptr, double* colsum1 = nullptr, bool* colsum_done = nullptr) {
   if (cols * n == 0) return AF_OK;
   const bool dual = DR != nullptr;
   GemmOperand A{U, dual ? UR : nullptr, LAY_KC, rows};
@@ -491,6 +503,9 @@ static int igrad_impl(af_ctx* ctx, const double* U, const double* UR, const doub
   GemmEpilogue e;
   e.epi = S ? EPI_SIGMOID_BWD : EPI_STORE;
   e.out0 = D; e.out1 = DR; e.ldo = cols; e.s = S; e.rs = RS; e.lds = cols;
+  if (S && colsum_done && !ctx->fused_colsum_off && !ctx->deterministic) {
+    e.colsum0 = colsum0; e.colsum1 = dual ? colsum1 : nullptr; e.colsum_done = colsum_done;
+  }
   if (rows > 0 && few_samples_applicable(ctx, rows, cols, n, {D, DR, S, RS})) {  // 9..16 samples: one streaming pass over W
     const int rc = few_samples_bwd_launch(ctx, U, UR, W, RW, nullptr, nullptr, nullptr, nullptr, D, DR, S, RS, rows, cols, n, false);
     if (rc != AF_ENOTSUP) return rc;
@@ -1111,9 +1126,15 @@ static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap, const M
     if (R) AF_TRY(af_sigmoid_bwd_r(ctx, m->act[L], m->ract[L], m->delta[L], m->rdelta[L], top));
     else AF_TRY(af_sigmoid_bwd(ctx, m->act[L], m->delta[L], top));
   }
+  // bias_done[l]: gb_l / rgb_l (lin_add.go:94-104) were already added -- by the head's forward kernel (top layer) or by the
+  // epilogue of the input-gradient launch that produced layer l's upstream
+  std::unique_ptr<bool[]> bias_done(new bool[L]());
+  bias_done[L - 1] = head_bias_done;
   auto input_gradient = [&](int l) -> int {  // lin_tran.go:420-423 with the sigmoid backward of the layer below fused in
-    return af_dense_igrad(ctx, m->delta[l + 1], R ? m->rdelta[l + 1] : nullptr, m->param[2 * l], rv(2 * l), m->act[l],
-                          R ? m->ract[l] : nullptr, m->delta[l], R ? m->rdelta[l] : nullptr, m->sizes[l + 1], m->sizes[l], n);
+    if (m->sizes[l] * n == 0) return AF_OK;
+    return igrad_impl(ctx, m->delta[l + 1], R ? m->rdelta[l + 1] : nullptr, m->param[2 * l], rv(2 * l), m->act[l],
+                      R ? m->ract[l] : nullptr, m->delta[l], R ? m->rdelta[l] : nullptr, m->sizes[l + 1], m->sizes[l], n,
+                      m->grad[2 * l - 1], R ? m->rgrad[2 * l - 1] : nullptr, &bias_done[l - 1]);
   };
   auto block_end = [&](int l) -> double* { return l + 1 < L ? m->grad[2 * l + 2] : m->grad[0] + m->gr_doubles; };
   if (!dp_overlap) {
@@ -1122,7 +1143,7 @@ static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap, const M
       const double* U = m->delta[l + 1];
       const double* UR = R ? m->rdelta[l + 1] : nullptr;
       // lin_add.go:94-104 batched: gb += colsum(U), rgb += colsum(UR)
-      if (!(l == L - 1 && head_bias_done))
+      if (!bias_done[l])
         AF_TRY(colsum_launch(ctx, U, UR, m->grad[2 * l + 1], R ? m->rgrad[2 * l + 1] : nullptr, rows, n));
       // lin_tran.go:410-418
       const double* RX = (R && l > 0) ? m->ract[l] : nullptr;
@@ -1218,7 +1239,7 @@ static int mlp_backward_launches(af_mlp* m, int with_r, bool dp_overlap, const M
     const int64_t rows = m->sizes[l + 1], cols = m->sizes[l];
     const double* U = m->delta[l + 1];
     const double* UR = R ? m->rdelta[l + 1] : nullptr;
-    if (!(l == L - 1 && head_bias_done))
+    if (!bias_done[l])
       AF_TRY(colsum_launch(ctx, U, UR, m->grad[2 * l + 1], R ? m->rgrad[2 * l + 1] : nullptr, rows, n));
     AF_TRY(af_lintran_wgrad_r(ctx, U, UR, m->act[l], (R && l > 0) ? m->ract[l] : nullptr, m->grad[2 * l],
                               R ? m->rgrad[2 * l] : nullptr, rows, cols, n));

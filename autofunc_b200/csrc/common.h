@@ -44,6 +44,8 @@ struct af_ctx {
   int few_samples_blocks = 3;  // resident blocks per SM the few-samples launches are sized for ("few_samples_blocks")
   bool few_samples_tma = true;  // backward pass through warp-private TMA rings ("few_samples_tma" 0: the register-staged kernel)
   unsigned* fold_tickets = nullptr;  // ticket counters of the last-block-folds reductions (kFoldTickets, zero between launches)
+  bool short_rows_off = false;  // A/B switch ("short_rows" 0): rows of <= 32 entries through the staged group kernels (mathops.cu)
+  bool fused_colsum_off = false;  // A/B switch ("fused_colsum" 0): the MLP plan's bias gradients always as colsum_kernel passes
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu
   bool lstm_split_off = true;   // opt-in (af_set_option "lstm_split" 1): two concurrent half-batch kernel chains; measured 24.6 vs 24.2 ms
@@ -173,6 +175,11 @@ struct GemmEpilogue {
   const double* rs = nullptr;
   long long lds = 0;
   bool prezeroed = false;  // store-type outputs are already zero: a split / stream-K launch may skip its memsets
+  // EPI_SIGMOID_BWD only: if the launch can, it also adds the column sums of out0 / out1 to colsum0 / colsum1 (the bias
+  // gradient of the layer below, lin_add.go:94-104) and sets *colsum_done; otherwise the caller sums in a pass of its own
+  double* colsum0 = nullptr;
+  double* colsum1 = nullptr;
+  bool* colsum_done = nullptr;
 };
 // acc0 = A0 B0^T ; acc1 = A0 B1^T + A1 B0^T (dual when `dual`), I x J, contraction Kd
 int gemm_launch(af_ctx* ctx, const GemmOperand& A, const GemmOperand& B, bool dual, long long I, long long J,

@@ -270,6 +270,15 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
     units_per_cta = sk_units;
     args.rotate = (ctx->sk_rotate && sk_units >= 64) ? 1 : 0;
   }
+  // column sums of a sigmoid-backward output ride on the epilogue of whole-tile launches (float64 atomics: not in
+  // deterministic mode, whose column sums are folded in block order by colsum_kernel)
+  if (mode == 0 && !swapped && cfg == 2 && e.epi == EPI_SIGMOID_BWD && (e.colsum0 || e.colsum1) && e.colsum_done &&
+      !ctx->deterministic && !ctx->fused_colsum_off && A.layout == LAY_KC && B.layout == LAY_RC) {
+    args.epi = EPI_SIGMOID_BWD_COLSUM;
+    args.bias0 = e.colsum0;
+    args.bias1 = dual ? e.colsum1 : nullptr;
+    *e.colsum_done = true;
+  }
   if (mode == 1 || mode == 2) {
     if (!accumulate) {
       deferred = true;

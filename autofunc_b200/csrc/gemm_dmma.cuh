@@ -52,6 +52,11 @@ enum : int {
   EPI_SIGMOID_BWD = 3,   // sigmoid R-backward with (S,RS) read at (i,j)         (math_funcs.go:365-371)
   EPI_ACCUM = 4,         // out += acc   (beta = 1, lin_tran.go:210,267-268)
   EPI_ACCUM_ATOMIC = 5,  // out += acc with red.global.add.f64 (split-K)
+  // EPI_SIGMOID_BWD, and the column sums of what was stored are added to colsum0 / colsum1 = the bias gradient of the
+  // layer below (lin_add.go:94-104 batched), which otherwise costs one more pass over the upstream it was computed
+  // from.  The two targets travel in GemmArgs::bias0 / bias1 (unused by this epilogue; the parameter block keeps its
+  // size).  Only whole-tile launches of the <KC, RC> instantiation and few_rows_igrad_kernel take it.
+  EPI_SIGMOID_BWD_COLSUM = 6,
 };
 
 // Operands of the fused LSTM step epilogues (SPECIAL = 1 / 2 below; lstm_step.cu).  Everything is one time step's
@@ -187,7 +192,8 @@ __device__ __forceinline__ void epi_transform(const GemmArgs& p, long long i, in
       }
       break;
     }
-    case EPI_SIGMOID_BWD: {
+    case EPI_SIGMOID_BWD:
+    case EPI_SIGMOID_BWD_COLSUM: {
       // math_funcs.go:365-371, operand order kept: u' = x(1-x)u ; uR' = xR(1-x)u - x xR u + x(1-x)uR
       double x = p.s[i * p.lds + j];
       double u = v0;
@@ -817,6 +823,59 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
         }
         return;
+      }
+      if constexpr (ALAY == LAY_KC && BLAY == LAY_RC && !MULTI && CFG == 2) {
+        if (p.epi == EPI_SIGMOID_BWD_COLSUM) {
+          // sigmoid backward of the layer below on the finished tile, stored, and the tile's column sums: a thread adds its
+          // TI rows, three butterfly steps add the eight row lanes, lanes 0..3 send one red.global.add.f64 per column
+          double cs0[TJ][2], cs1[TJ][2];
+#pragma unroll
+          for (int u = 0; u < TJ; ++u) cs0[u][0] = cs0[u][1] = cs1[u][0] = cs1[u][1] = 0.0;
+#pragma unroll
+          for (int t = 0; t < TI; ++t) {
+            const long long i = i0 + wi0 + 8 * t + g;
+            if (i >= p.I) continue;
+#pragma unroll
+            for (int u = 0; u < TJ; ++u) {
+              const int j = j0 + wj0 + 8 * u + 2 * j4;
+              if (j >= p.J) continue;
+              const bool two = j + 1 < p.J;
+              double a0 = acc0[t][u][0], a1 = acc0[t][u][1];
+              double r0 = DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0, r1 = DUAL ? acc1[DUAL ? t : 0][u][1] : 0.0;
+              epi_transform<DUAL>(p, i, j, a0, r0);
+              if (two) epi_transform<DUAL>(p, i, j + 1, a1, r1);
+              const long long o = i * p.ldo + j;
+              if (two && vec_ok) {
+                if (p.out0) *reinterpret_cast<double2*>(p.out0 + o) = make_double2(a0, a1);
+                if (DUAL && p.out1) *reinterpret_cast<double2*>(p.out1 + o) = make_double2(r0, r1);
+              } else {
+                if (p.out0) { p.out0[o] = a0; if (two) p.out0[o + 1] = a1; }
+                if (DUAL && p.out1) { p.out1[o] = r0; if (two) p.out1[o + 1] = r1; }
+              }
+              cs0[u][0] += a0; cs1[u][0] += r0;
+              if (two) { cs0[u][1] += a1; cs1[u][1] += r1; }
+            }
+          }
+          double* colsum0 = const_cast<double*>(p.bias0);
+          double* colsum1 = const_cast<double*>(p.bias1);
+#pragma unroll
+          for (int u = 0; u < TJ; ++u)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              double a = cs0[u][e], r = cs1[u][e];
+#pragma unroll
+              for (int o = 4; o < 32; o <<= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (DUAL) r += __shfl_xor_sync(0xffffffffu, r, o);
+              }
+              const int j = j0 + wj0 + 8 * u + 2 * j4 + e;
+              if (g == 0 && j < p.J) {
+                if (colsum0) atomicAdd(colsum0 + j, a);
+                if (DUAL && colsum1) atomicAdd(colsum1 + j, r);
+              }
+            }
+          return;
+        }
       }
 #pragma unroll
       for (int t = 0; t < TI; ++t) {

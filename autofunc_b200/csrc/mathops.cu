@@ -269,6 +269,146 @@ __global__ void __launch_bounds__(256) softmax_bwd_staged_kernel(const double* _
   if (UR) stage_out(UR, sur, base, elems);
 }
 
+// ---- short rows (len <= kShortRow: the 10-class head): ONE THREAD PER ROW for the sums only --------------------------
+// The staged kernels above touch shared memory six times per entry (stage, read, write e, read e, write y, unstage), do
+// all of a row's arithmetic in a 4- or 8-lane group between two block barriers, and reduce with shuffles; on rows of 10
+// that serialised phase -- every exp() of the chunk waits for the chunk's last load -- and the shared-memory traffic cost
+// as much as the HBM stream itself (0.64-0.70 of the copy rate).  Here the per-ENTRY work rides on the coalesced phases,
+// spread over all 256 threads like in the elementwise kernels: the load phase evaluates e = exp(x invT) and eR as the
+// loads arrive and parks them in shared memory at an ODD row pitch (len | 1: thread r reading entry k of row r is free
+// of bank conflicts); one thread per row then only adds its row up (sequentially: no shuffles) and leaves the row's two
+// scalars in shared memory; the store phase scales on the way out.  Every vector crosses HBM once, exp() is evaluated once.
+constexpr int kShortRow = 32;  // (e * magic) >> 16 is exact while chunk * len <= 65536
+constexpr int kShortChunk = 2048;     // doubles per staged vector (pitched), forward: 2 vectors = 32 KB per block
+constexpr int kShortChunkBwd = 1024;  // backward: 4 vectors = 32 KB per block
+
+struct ShortRowGeom {
+  int len, pitch, rows_per_block, magic;  // e / len == (e * magic) >> 16 for e * len < 65536
+};
+
+// formulas and operand order of softmax_fwd_staged_kernel (math_funcs.go:487-509)
+template <bool R>
+__global__ void __launch_bounds__(256) softmax_fwd_short_kernel(const double* __restrict__ X, const double* __restrict__ RX,
+                                                                double* __restrict__ Y, double* __restrict__ RY,
+                                                                double invT, long long n, const ShortRowGeom g) {
+  constexpr int PER = kShortChunk / 256;
+  __shared__ double se[kShortChunk];             // e
+  __shared__ double ser[R ? kShortChunk : 1];    // eR
+  __shared__ double sinv[256], sinvr[R ? 256 : 1];
+  const long long row0 = (long long)blockIdx.x * g.rows_per_block;
+  const int nrows = (int)min((long long)g.rows_per_block, n - row0);
+  const int elems = nrows * g.len;
+  const long long base = row0 * g.len;
+  int row[PER], at[PER];   // entry u of this thread: its row in the chunk and its pitched slot
+  {
+    double x[PER], xr[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int e = threadIdx.x + u * 256;
+      row[u] = (e * g.magic) >> 16;
+      at[u] = row[u] * g.pitch + (e - row[u] * g.len);
+      x[u] = e < elems ? X[base + e] : 0.0;
+      if (R) xr[u] = (e < elems && RX) ? RX[base + e] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u)
+      if (threadIdx.x + u * 256 < elems) {
+        const double ev = exp(x[u] * invT);
+        se[at[u]] = ev;
+        if (R) ser[at[u]] = ev * (xr[u] * invT);
+      }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nrows) {
+    const int o = threadIdx.x * g.pitch;
+    double s = 0.0, srsum = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < g.len; ++k) {
+      s += se[o + k];
+      if (R) srsum += ser[o + k];
+    }
+    const double inv = 1.0 / s;
+    sinv[threadIdx.x] = inv;
+    if (R) sinvr[threadIdx.x] = -(inv * inv) * srsum;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int e = threadIdx.x + u * 256;
+    if (e < elems) {
+      const double ev = se[at[u]], inv = sinv[row[u]];
+      if (R) RY[base + e] = ev * sinvr[row[u]] + ser[at[u]] * inv;
+      Y[base + e] = ev * inv;
+    }
+  }
+}
+
+template <bool R>
+__global__ void __launch_bounds__(256) softmax_bwd_short_kernel(const double* __restrict__ Y, const double* __restrict__ RY,
+                                                                double* __restrict__ U, double* __restrict__ UR, double invT,
+                                                                long long n, const ShortRowGeom g) {
+  constexpr int PER = kShortChunkBwd / 256;
+  __shared__ double su[kShortChunkBwd], sy[kShortChunkBwd];
+  __shared__ double sur[R ? kShortChunkBwd : 1], sry[R ? kShortChunkBwd : 1];
+  __shared__ double sa[256], sb[R ? 256 : 1];
+  const long long row0 = (long long)blockIdx.x * g.rows_per_block;
+  const int nrows = (int)min((long long)g.rows_per_block, n - row0);
+  const int elems = nrows * g.len;
+  const long long base = row0 * g.len;
+  int row[PER], at[PER];
+  {
+    double u_[PER], y_[PER], ur_[PER], ry_[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int e = threadIdx.x + u * 256;
+      row[u] = (e * g.magic) >> 16;
+      at[u] = row[u] * g.pitch + (e - row[u] * g.len);
+      const bool ok = e < elems;
+      u_[u] = ok ? U[base + e] : 0.0;
+      y_[u] = ok ? Y[base + e] : 0.0;
+      if (R) { ur_[u] = ok ? UR[base + e] : 0.0; ry_[u] = (ok && RY) ? RY[base + e] : 0.0; }
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u)
+      if (threadIdx.x + u * 256 < elems) {
+        su[at[u]] = u_[u]; sy[at[u]] = y_[u];
+        if (R) { sur[at[u]] = ur_[u]; sry[at[u]] = ry_[u]; }
+      }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nrows) {
+    const int o = threadIdx.x * g.pitch;
+    double a = 0.0, b = 0.0;  // <u,y> ; <uR,y> + <u,yR>
+#pragma unroll 4
+    for (int k = 0; k < g.len; ++k) {
+      const double u = su[o + k], y = sy[o + k];
+      a += u * y;
+      if (R) b += sur[o + k] * y + u * sry[o + k];
+    }
+    sa[threadIdx.x] = a;
+    if (R) sb[threadIdx.x] = b;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int e = threadIdx.x + u * 256;
+    if (e < elems) {
+      const double uv = su[at[u]], y = sy[at[u]], a = sa[row[u]];
+      if (R) UR[base + e] = invT * (sry[at[u]] * (uv - a) + y * (sur[at[u]] - sb[row[u]]));
+      U[base + e] = invT * (y * (uv - a));
+    }
+  }
+}
+
+inline ShortRowGeom short_row_geom(long long len, int chunk) {
+  ShortRowGeom g;
+  g.len = (int)len;
+  g.pitch = (int)len | 1;
+  g.rows_per_block = std::min(256, chunk / g.pitch);
+  g.magic = (65536 + g.len - 1) / g.len;
+  return g;
+}
+
 // group width for a row length: the smallest sub-warp that covers the row in <= 2 strides, a full warp up to
 // 32 * kRowCache entries, one block beyond that
 // one block pass per 256/G rows (measured: capping the grid and walking rows persistently is slower -- a block's rows
@@ -556,6 +696,13 @@ int af_softmax_fwd_r(af_ctx* ctx, const double* X, const double* RX, double temp
   if (len < 0 || n < 0) return fail(AF_ESHAPE, "negative length");
   if (len == 0 || n == 0) return AF_OK;
   const double invT = (temperature != 0 && temperature != 1) ? 1 / temperature : 1.0;
+  if (len <= kShortRow && !ctx->short_rows_off) {
+    const ShortRowGeom g = short_row_geom(len, kShortChunk);
+    const unsigned grid = (unsigned)((n + g.rows_per_block - 1) / g.rows_per_block);
+    if (RY) softmax_fwd_short_kernel<true><<<grid, 256, 0, ctx->stream>>>(X, RX, Y, RY, invT, (long long)n, g);
+    else softmax_fwd_short_kernel<false><<<grid, 256, 0, ctx->stream>>>(X, nullptr, Y, nullptr, invT, (long long)n, g);
+    return after_launch(ctx, "softmax_fwd_short_kernel", KIND_REDUCE, 8.0 * len * n * (RY ? 4 : 2));
+  }
   if (len <= kSoftChunk) {
     const int rpc = (int)(kSoftChunk / len);
     const unsigned grid = (unsigned)((n + rpc - 1) / rpc);
@@ -573,6 +720,16 @@ int af_softmax_bwd_r(af_ctx* ctx, const double* Y, const double* RY, double temp
   if (len < 0 || n < 0) return fail(AF_ESHAPE, "negative length");
   if (len == 0 || n == 0) return AF_OK;
   const double invT = (temperature != 0 && temperature != 1) ? 1 / temperature : 1.0;
+  if (len <= kShortRow && !ctx->short_rows_off) {
+    const ShortRowGeom g = short_row_geom(len, kShortChunkBwd);
+    const unsigned grid = (unsigned)((n + g.rows_per_block - 1) / g.rows_per_block);
+    if (UR) {
+      softmax_bwd_short_kernel<true><<<grid, 256, 0, ctx->stream>>>(Y, RY, U, UR, invT, (long long)n, g);
+    } else {
+      softmax_bwd_short_kernel<false><<<grid, 256, 0, ctx->stream>>>(Y, nullptr, U, nullptr, invT, (long long)n, g);
+    }
+    return after_launch(ctx, "softmax_bwd_short_kernel", KIND_REDUCE, 8.0 * len * n * (UR ? 6 : 3));
+  }
   if (len <= kSoftChunk) {
     const int rpc = (int)(kSoftChunk / len);
     const unsigned grid = (unsigned)((n + rpc - 1) / rpc);

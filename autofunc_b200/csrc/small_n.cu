@@ -200,8 +200,11 @@ __global__ void __launch_bounds__(256, 2) few_rows_igrad_kernel(const double* __
     *reinterpret_cast<double2*>(rws + e) = has_rw ? ld2(RW + e) : make_double2(0.0, 0.0);
   }
   const int half = cols / 2;
-  const bool vec_ok = (p.ldo & 1) == 0 && (p.epi != EPI_SIGMOID_BWD || (p.lds & 1) == 0);
-  const bool fused_sig = p.epi == EPI_SIGMOID_BWD && vec_ok;
+  const bool with_colsum = p.epi == EPI_SIGMOID_BWD_COLSUM;  // (the host checked: vectorised path, one column pair per thread)
+  const bool sig = p.epi == EPI_SIGMOID_BWD || with_colsum;
+  const bool vec_ok = (p.ldo & 1) == 0 && (!sig || (p.lds & 1) == 0);
+  const bool fused_sig = sig && vec_ok;
+  double2 cs = make_double2(0.0, 0.0), csr = make_double2(0.0, 0.0);  // column sums of this thread's pair over the block's samples
   const long long groups = (n + kFewRowsSpt - 1) / kFewRowsSpt;
   for (long long ig = blockIdx.x; ig < groups; ig += gridDim.x) {
     const long long i0 = ig * kFewRowsSpt;
@@ -250,17 +253,27 @@ __global__ void __launch_bounds__(256, 2) few_rows_igrad_kernel(const double* __
           // math_funcs.go:365-371, operand order kept: u' = x(1-x)u ; uR' = xR(1-x)u - x xR u + x(1-x)uR
           const long long o = (i0 + q) * p.ldo + k;
           const double x0 = sx[q].x, x1 = sx[q].y, u0 = d[q].x, u1 = d[q].y;
-          if (p.out0) *reinterpret_cast<double2*>(p.out0 + o) = make_double2(x0 * (1 - x0) * u0, x1 * (1 - x1) * u1);
+          const double2 v = make_double2(x0 * (1 - x0) * u0, x1 * (1 - x1) * u1);
+          if (p.out0) *reinterpret_cast<double2*>(p.out0 + o) = v;
+          cs.x += v.x; cs.y += v.y;
           if (DUAL && p.out1) {
             const double r0 = rsx[q].x, r1 = rsx[q].y;
-            *reinterpret_cast<double2*>(p.out1 + o) = make_double2(r0 * (1 - x0) * u0 - x0 * r0 * u0 + x0 * (1 - x0) * dr[q].x,
-                                                                   r1 * (1 - x1) * u1 - x1 * r1 * u1 + x1 * (1 - x1) * dr[q].y);
+            const double2 vr = make_double2(r0 * (1 - x0) * u0 - x0 * r0 * u0 + x0 * (1 - x0) * dr[q].x,
+                                            r1 * (1 - x1) * u1 - x1 * r1 * u1 + x1 * (1 - x1) * dr[q].y);
+            *reinterpret_cast<double2*>(p.out1 + o) = vr;
+            csr.x += vr.x; csr.y += vr.y;
           }
         } else {
           epi_pair<DUAL>(p, vec_ok, i0 + q, k, d[q].x, d[q].y, dr[q].x, dr[q].y);
         }
       }
     }
+  }
+  if (with_colsum && (int)threadIdx.x < half) {  // lin_add.go:94-104 for the layer below: gb += colsum(D), rgb += colsum(DR)
+    double* gb = const_cast<double*>(p.bias0);
+    double* rgb = const_cast<double*>(p.bias1);
+    if (gb) { atomicAdd(gb + 2 * threadIdx.x, cs.x); atomicAdd(gb + 2 * threadIdx.x + 1, cs.y); }
+    if (DUAL && rgb) { atomicAdd(rgb + 2 * threadIdx.x, csr.x); atomicAdd(rgb + 2 * threadIdx.x + 1, csr.y); }
   }
 }
 
@@ -354,6 +367,13 @@ int few_rows_igrad_launch(af_ctx* ctx, const double* U, const double* UR, const 
   GemmArgs a{};
   a.I = (int)n; a.J = (int)cols; a.Kd = (int)rows; a.epi = e.epi; a.out0 = e.out0; a.out1 = dual ? e.out1 : nullptr;
   a.ldo = e.ldo; a.s = e.s; a.rs = e.rs; a.lds = e.lds;
+  // the bias gradient of the layer below (column sums of what this pass stores) rides along when every thread keeps ONE
+  // column pair for the whole launch (cols <= 512) and the fused, vectorised sigmoid-backward path is taken
+  if (e.epi == EPI_SIGMOID_BWD && e.colsum_done && (e.colsum0 || e.colsum1) && cols <= 512 && (e.ldo & 1) == 0 && (e.lds & 1) == 0) {
+    a.epi = EPI_SIGMOID_BWD_COLSUM;
+    a.bias0 = e.colsum0; a.bias1 = dual ? e.colsum1 : nullptr;
+    *e.colsum_done = true;
+  }
   long long blocks = (n + kFewRowsSpt - 1) / kFewRowsSpt;  // one group of four samples per block trip; persistent blocks
   if (blocks > 2ll * ctx->sm_count) blocks = 2ll * ctx->sm_count;
   const size_t smem = ((size_t)2 * rows * cols + 2 * kFewRowsSpt * 16) * 8;

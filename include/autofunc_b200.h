@@ -104,6 +104,10 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * used.  0 (default) = the faster schedule, whose last bits (well inside 1e-12 + 1e-10 |ref|) depend on the arrival
  * order of partial sums.  Cost measured on the bench step: DESIGN.md 3.1.  (The LSTM's fused time steps are
  * deterministic in both modes; the sum over ranks is NCCL's, which is run-to-run deterministic for a fixed communicator.)
+ * "few_rows_wgrad": the weight gradient of a layer with <= 16 output rows over a batch of >= 64 samples (the bench
+ * network's 10-class head) as a streaming kernel with ordered sums: 0 never, 1 (default) in deterministic mode, 2 always.
+ * "short_rows": 1 (default) = softmax over rows of <= 32 entries: per-entry work in the coalesced phases, one thread per row for the sums;
+ * 0 = the staged group kernels that serve longer rows.
  * Plan-owned CUDA graphs captured before a change of any option are re-captured.                        */
 int af_set_option(af_ctx* ctx, const char* name, int value);
 

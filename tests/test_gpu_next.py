@@ -156,7 +156,9 @@ def test_unary_functions_match_oracle(api, name, n):
 
 @pytest.mark.parametrize("rows,length,temp", [(1, 7, 0.0), (37, 10, 0.0), (4096, 10, 3.0), (5, 1024, 1.0), (3, 3001, 0.5),
                                               (300, 257, 2.0), (50, 24, 0.0), (45, 32, 1.5), (20, 200, 0.0),
-                                              (9, 256, 0.0), (33, 16, 0.0)])
+                                              (9, 256, 0.0), (33, 16, 0.0),
+                                              # rows of <= 16 entries: one thread per row (softmax_*_short_kernel)
+                                              (1000, 2, 0.0), (300, 1, 2.0), (777, 13, 0.5), (5000, 16, 0.0), (187, 10, 0.0)])
 def test_batched_softmax_matches_oracle(api, rows, length, temp):
     """One fused launch per direction vs the reference's chain under RFuncBatcher (batcher.go:57-84)."""
     n = rows * length

@@ -607,6 +607,51 @@ def test_mlp_head_fusion_matches_unfused_steps_and_oracle(api, n, unit, with_r):
         close(a, b_, "fused vs unfused head")
 
 
+@pytest.mark.parametrize("sizes,n", [([130, 200, 96, 10], 300),     # ragged tiles: 200 = 3.1 x 64 columns, 300 = 4.7 x 64 rows
+                                     ([64, 512, 10], 1000),          # the head's input gradient sums the 512 columns below it
+                                     ([40, 66, 130, 34, 10], 257),   # three tensor-core input gradients in a row
+                                     ([1000, 2000, 512, 10], 512)])  # the bench network
+@pytest.mark.parametrize("with_r", [True, False])
+def test_mlp_bias_gradient_fused_into_input_gradient_matches_separate_pass_and_oracle(api, sizes, n, with_r):
+    """lin_add.go:94-104 batched is a column sum of the layer's upstream; the input-gradient launch that PRODUCES that
+    upstream (sigmoid backward fused, math_funcs.go:365-371) adds the sums from its epilogue.  Against the oracle, and
+    against the same plan with the fusion off (af_set_option "fused_colsum" 0: colsum_kernel passes), which must need
+    more launches."""
+    onet = ref.MLP(sizes, weight_scale=lambda k: 1 / np.sqrt(k))
+    x = onet.make_input(n)
+    if with_r:
+        ores, ograd, orgrad = onet.step_r(x, n)
+    else:
+        ores, ograd = onet.step(x, n)
+    ctx = api.context()
+    results, launches = [], []
+    for fused in (1, 0):
+        ctx.set_option("fused_colsum", fused)
+        try:
+            plan = api.MLPPlan(sizes, n)
+            for i, v in enumerate(onet.variables):
+                plan.set_param(i, v.vector)
+                plan.set_rvector(i, onet.rvec[v])
+            for rep in range(2):  # accumulators are zeroed per step: the second step must give the same sums
+                before = ctx.launch_count()
+                out, rout, grads, rgrads = plan.step_host(x.vector, with_r=with_r)
+                count = ctx.launch_count() - before
+                close(out, ores.output(), f"Output fused={fused} rep={rep}")
+                for i, v in enumerate(onet.variables):
+                    close(grads[i], ograd[v], f"grad[{i}] fused={fused} rep={rep}")
+                    if with_r:
+                        close(rgrads[i], orgrad[v], f"rgrad[{i}] fused={fused} rep={rep}")
+            results.append(grads)
+            launches.append(count)
+            plan.close()
+        finally:
+            ctx.set_option("fused_colsum", 1)
+    for a, b_ in zip(*results):
+        close(a, b_, "fused vs separate bias gradient")
+    if n > 256:  # (batches <= 256 replay a recorded graph: the launch counter then counts the graph's kernels all the same)
+        assert launches[0] < launches[1], f"fusion saved no launch: {launches}"
+
+
 @pytest.mark.parametrize("rows,cols,n", [(2048, 30, 700), (50, 7, 130), (64, 32, 64), (3, 1, 17)])
 @pytest.mark.parametrize("with_r,use_rw", [(True, True), (True, False), (False, False)])
 @pytest.mark.parametrize("bias", [True, False])

@@ -54,8 +54,20 @@ def main():
         ("softmax_bwd_r rows of 1024", 48, lambda: L.af_softmax_bwd_r(h, a, b, 0.0, c, d, 1024, rows)),
         ("softmax_fwd_r rows of 10", 32, lambda: L.af_softmax_fwd_r(h, a, b, 0.0, c, d, 10, n // 10)),
         ("softmax_bwd_r rows of 10", 48, lambda: L.af_softmax_bwd_r(h, a, b, 0.0, c, d, 10, n // 10)),
+        ("softmax_fwd_r rows of 16", 32, lambda: L.af_softmax_fwd_r(h, a, b, 0.0, c, d, 16, n // 16)),
+        ("softmax_bwd_r rows of 16", 48, lambda: L.af_softmax_bwd_r(h, a, b, 0.0, c, d, 16, n // 16)),
+        ("softmax_fwd_r rows of 32", 32, lambda: L.af_softmax_fwd_r(h, a, b, 0.0, c, d, 32, n // 32)),
+        ("softmax_bwd_r rows of 32", 48, lambda: L.af_softmax_bwd_r(h, a, b, 0.0, c, d, 32, n // 32)),
+        ("softmax_fwd_r rows of 4", 32, lambda: L.af_softmax_fwd_r(h, a, b, 0.0, c, d, 4, n // 4)),
+        # A/B: the staged group kernels that served short rows before (af_set_option "short_rows" 0)
+        ("softmax_fwd_r rows of 10 [short_rows=0]", 32, lambda: L.af_softmax_fwd_r(h, a, b, 0.0, c, d, 10, n // 10)),
+        ("softmax_bwd_r rows of 10 [short_rows=0]", 48, lambda: L.af_softmax_bwd_r(h, a, b, 0.0, c, d, 10, n // 10)),
     ]
+    only = os.environ.get("AF_STREAM_ONLY")  # substring filter, e.g. AF_STREAM_ONLY=softmax
     for name, bpe, call in cases:
+        if only and only not in name:
+            continue
+        ctx.set_option("short_rows", 0 if "[short_rows=0]" in name else 1)
         for v in bufs:  # the backward kernels overwrite their operands in place: restore (device to device)
             api.check(L.af_copy(h, v.ptr, pristine.ptr, n))
         for _ in range(warm):  # ~15 ms of back-to-back launches: clocks are up before the timed region
