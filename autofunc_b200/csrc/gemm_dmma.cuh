@@ -824,15 +824,44 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         return;
       }
-      if constexpr (ALAY == LAY_KC && BLAY == LAY_RC && !MULTI && CFG == 2) {
-        if (p.epi == EPI_SIGMOID_BWD_COLSUM) {
-          // sigmoid backward of the layer below on the finished tile, stored, and the tile's column sums: a thread adds its
-          // TI rows, three butterfly steps add the eight row lanes, lanes 0..3 send one red.global.add.f64 per column
+      if constexpr (ALAY == LAY_KC && BLAY == LAY_RC && !MULTI) {  // (whole tiles per CTA; stream-K defers its epilogue)
+        // ---- sigmoid backward of the layer below on the finished tile (input-gradient launches; math_funcs.go:365-371,
+        // operand order kept), optionally with the tile's column sums (EPI_SIGMOID_BWD_COLSUM) ----
+        // S / RS at the output positions are usually cold (written by the forward pass, hundreds of MB ago).  Fetched pair by
+        // pair between the stores -- the outputs may alias them as far as the compiler knows -- a thread paid TI x TJ
+        // serialised DRAM round trips per tile while its CTA issued no DMMA.  Here a whole fragment row (TJ pairs of both
+        // vectors) is requested through the read-only path BEFORE the previous row is computed and stored: TI round
+        // trips, each hidden behind a row's arithmetic.
+        const bool sig = p.epi == EPI_SIGMOID_BWD || p.epi == EPI_SIGMOID_BWD_COLSUM;
+        if (sig && vec_ok && (p.lds & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.s) | reinterpret_cast<uintptr_t>(p.rs)) & 15) == 0) {
+          const bool with_colsum = p.epi == EPI_SIGMOID_BWD_COLSUM;
+          const bool has_rs = DUAL && p.rs != nullptr;
           double cs0[TJ][2], cs1[TJ][2];
 #pragma unroll
           for (int u = 0; u < TJ; ++u) cs0[u][0] = cs0[u][1] = cs1[u][0] = cs1[u][1] = 0.0;
+          double2 sx[2][TJ], rx[2][TJ];
+          auto fetch = [&](int buf, int t) {
+            const long long i = i0 + wi0 + 8 * t + g;
+#pragma unroll
+            for (int u = 0; u < TJ; ++u) {
+              const int j = j0 + wj0 + 8 * u + 2 * j4;
+              sx[buf][u] = rx[buf][u] = make_double2(0.0, 0.0);
+              if (i < p.I && j < p.J) {
+                const long long o = i * p.lds + j;
+                if (j + 1 < p.J) {
+                  sx[buf][u] = __ldg(reinterpret_cast<const double2*>(p.s + o));
+                  if (has_rs) rx[buf][u] = __ldg(reinterpret_cast<const double2*>(p.rs + o));
+                } else {
+                  sx[buf][u].x = __ldg(p.s + o);
+                  if (has_rs) rx[buf][u].x = __ldg(p.rs + o);
+                }
+              }
+            }
+          };
+          fetch(0, 0);
 #pragma unroll
           for (int t = 0; t < TI; ++t) {
+            if (t + 1 < TI) fetch((t + 1) & 1, t + 1);
             const long long i = i0 + wi0 + 8 * t + g;
             if (i >= p.I) continue;
 #pragma unroll
@@ -840,40 +869,49 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
               const int j = j0 + wj0 + 8 * u + 2 * j4;
               if (j >= p.J) continue;
               const bool two = j + 1 < p.J;
-              double a0 = acc0[t][u][0], a1 = acc0[t][u][1];
-              double r0 = DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0, r1 = DUAL ? acc1[DUAL ? t : 0][u][1] : 0.0;
-              epi_transform<DUAL>(p, i, j, a0, r0);
-              if (two) epi_transform<DUAL>(p, i, j + 1, a1, r1);
+              const double2 x = sx[t & 1][u], xr = rx[t & 1][u];
+              const double u0 = acc0[t][u][0], u1 = acc0[t][u][1];
+              // u' = x(1-x)u ; uR' = xR(1-x)u - x xR u + x(1-x)uR
+              const double a0 = x.x * (1 - x.x) * u0, a1 = x.y * (1 - x.y) * u1;
+              double r0 = 0.0, r1 = 0.0;
+              if (DUAL) {
+                r0 = xr.x * (1 - x.x) * u0 - x.x * xr.x * u0 + x.x * (1 - x.x) * acc1[DUAL ? t : 0][u][0];
+                r1 = xr.y * (1 - x.y) * u1 - x.y * xr.y * u1 + x.y * (1 - x.y) * acc1[DUAL ? t : 0][u][1];
+              }
               const long long o = i * p.ldo + j;
-              if (two && vec_ok) {
+              if (two) {
                 if (p.out0) *reinterpret_cast<double2*>(p.out0 + o) = make_double2(a0, a1);
                 if (DUAL && p.out1) *reinterpret_cast<double2*>(p.out1 + o) = make_double2(r0, r1);
               } else {
-                if (p.out0) { p.out0[o] = a0; if (two) p.out0[o + 1] = a1; }
-                if (DUAL && p.out1) { p.out1[o] = r0; if (two) p.out1[o + 1] = r1; }
+                if (p.out0) p.out0[o] = a0;
+                if (DUAL && p.out1) p.out1[o] = r0;
               }
               cs0[u][0] += a0; cs1[u][0] += r0;
               if (two) { cs0[u][1] += a1; cs1[u][1] += r1; }
             }
           }
-          double* colsum0 = const_cast<double*>(p.bias0);
-          double* colsum1 = const_cast<double*>(p.bias1);
+          if (with_colsum) {
+            // a thread has added its TI rows; three butterfly steps add the eight row lanes, lanes 0..3 send one
+            // red.global.add.f64 per column (the targets travel in bias0 / bias1, see EPI_SIGMOID_BWD_COLSUM)
+            double* colsum0 = const_cast<double*>(p.bias0);
+            double* colsum1 = const_cast<double*>(p.bias1);
 #pragma unroll
-          for (int u = 0; u < TJ; ++u)
+            for (int u = 0; u < TJ; ++u)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              double a = cs0[u][e], r = cs1[u][e];
+              for (int e = 0; e < 2; ++e) {
+                double a = cs0[u][e], r = cs1[u][e];
 #pragma unroll
-              for (int o = 4; o < 32; o <<= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, o);
-                if (DUAL) r += __shfl_xor_sync(0xffffffffu, r, o);
+                for (int o = 4; o < 32; o <<= 1) {
+                  a += __shfl_xor_sync(0xffffffffu, a, o);
+                  if (DUAL) r += __shfl_xor_sync(0xffffffffu, r, o);
+                }
+                const int j = j0 + wj0 + 8 * u + 2 * j4 + e;
+                if (g == 0 && j < p.J) {
+                  if (colsum0) atomicAdd(colsum0 + j, a);
+                  if (DUAL && colsum1) atomicAdd(colsum1 + j, r);
+                }
               }
-              const int j = j0 + wj0 + 8 * u + 2 * j4 + e;
-              if (g == 0 && j < p.J) {
-                if (colsum0) atomicAdd(colsum0 + j, a);
-                if (DUAL && colsum1) atomicAdd(colsum1 + j, r);
-              }
-            }
+          }
           return;
         }
       }
