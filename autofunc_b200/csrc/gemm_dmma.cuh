@@ -325,6 +325,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// request the line holding `p` into L2 (no register, no dependency): epilogue operands that are known when the CTA starts
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // thread-block cluster helpers (SPECIAL = 2: split-K over a cluster, partial tiles exchanged through DSMEM)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -577,6 +579,48 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         load_b(base + t * L::kStageBytes, bars + 8 * t, p_kt + t);  // (!MULTI: units are consecutive k-tiles of one tile)
       }
     }
+    // The cell epilogue reads, at this thread's output positions, vectors that were written long before this step -- the x
+    // projection / the forward pass's gates and states / the output layer's gradient: hundreds of MB ago, so they come
+    // from DRAM -- and the step cannot end before they arrive.  They do not depend on the previous step either: request
+    // them into L2 now, the main loop covers the latency.
+    if constexpr (SPECIAL == 1) {
+      const LstmStepArgs& c = sp.lstm;
+      const int tl = tile_of(tile0);
+      const int unit = (tl % p.tiles_j) * 16 + (warp % T::WJ) * 8 + 2 * (lane & 3);
+#pragma unroll
+      for (int t = 0; t < TI; ++t) {
+        const long long i = (long long)(tl / p.tiles_j) * BM + (warp / T::WJ) * (TI * 8) + 8 * t + (lane >> 2);
+        if (i < p.I) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            prefetch_l2(c.G + i * 4 * c.H + unit + u * c.H);
+            if (DUAL) prefetch_l2(c.RG + i * 4 * c.H + unit + u * c.H);
+          }
+        }
+      }
+    }
+    if constexpr (SPECIAL == 2) {
+      constexpr int NQ = kConsumerWarps / L::kSplit, NV1 = TI * TJ * 2, PER = NQ * NV1 / kConsumerWarps;
+      const LstmStepArgs& c = sp.lstm;
+      const int tl = tile_of(tile0);
+      const int sw = (int)cluster_ctarank() * NQ + (warp * PER) / NV1;
+#pragma unroll
+      for (int x = 0; x < PER; x += 2) {
+        const int v = (warp * PER) % NV1 + x;
+        const long long i = (long long)(tl / p.tiles_j) * BM + (sw / T::WJ) * (TI * 8) + 8 * (v / (TJ * 2)) + (lane >> 2);
+        const int j = (tl % p.tiles_j) * BN + (sw % T::WJ) * (TJ * 8) + 8 * ((v / 2) % TJ) + 2 * (lane & 3);
+        if (i < p.I && j < p.J) {
+          const long long gi = i * 4 * c.H + j, si = i * c.ld + j;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            prefetch_l2(c.Gm + gi + u * c.H);
+            if (DUAL) prefetch_l2(c.RGm + gi + u * c.H);
+          }
+          prefetch_l2(c.INm + si); prefetch_l2(c.INt + si); prefetch_l2(c.DAUGm + si);
+          if (DUAL) { prefetch_l2(c.RINm + si); prefetch_l2(c.RINt + si); prefetch_l2(c.RDAUGm + si); }
+        }
+      }
+    }
     pdl_wait();
     if (prod_lane) {
       for (int t = 0; t < kStages - 1 && t < nun; ++t) produce(t, true, warp == 0);
@@ -663,6 +707,27 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const LstmStepArgs& c = sp.lstm;
       const int H = c.H;
       const int unit = (tile % p.tiles_j) * 16 + (warp % T::WJ) * 8 + 2 * j4;  // and unit + 1
+      // all rows' operands first (G / RG are read and written in place, so the compiler cannot move row t + 1's loads above
+      // row t's stores on its own: one round trip instead of TI)
+      double2 zx[TI][4], rzx[TI][4], spv[TI], rspv[TI];
+#pragma unroll
+      for (int t = 0; t < TI; ++t) {
+        const long long i = i0 + wi0 + 8 * t + g;
+        spv[t] = rspv[t] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) zx[t][u] = rzx[t][u] = make_double2(0.0, 0.0);
+        if (i < p.I) {
+          const double* gp = c.G + i * 4 * H + unit;
+          const long long si = i * c.ld + unit;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            zx[t][u] = *reinterpret_cast<const double2*>(gp + u * H);  // x W_x^T + b of gate u
+            if (DUAL) rzx[t][u] = *reinterpret_cast<const double2*>(c.RG + i * 4 * H + unit + u * H);
+          }
+          spv[t] = *reinterpret_cast<const double2*>(c.INp + si);
+          if (DUAL) rspv[t] = *reinterpret_cast<const double2*>(c.RINp + si);
+        }
+      }
 #pragma unroll
       for (int t = 0; t < TI; ++t) {
         const long long i = i0 + wi0 + 8 * t + g;
@@ -672,17 +737,11 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           double2 z[4], rz[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const double2 x = *reinterpret_cast<const double2*>(gp + u * H);  // x W_x^T + b of gate u
-            z[u] = make_double2(acc0[t][u][0] + x.x, acc0[t][u][1] + x.y);
-            if (DUAL) {
-              const double2 rx = *reinterpret_cast<const double2*>(c.RG + i * 4 * H + unit + u * H);
-              rz[u] = make_double2(acc1[DUAL ? t : 0][u][0] + rx.x, acc1[DUAL ? t : 0][u][1] + rx.y);
-            } else {
-              rz[u] = make_double2(0.0, 0.0);
-            }
+            z[u] = make_double2(acc0[t][u][0] + zx[t][u].x, acc0[t][u][1] + zx[t][u].y);
+            if (DUAL) rz[u] = make_double2(acc1[DUAL ? t : 0][u][0] + rzx[t][u].x, acc1[DUAL ? t : 0][u][1] + rzx[t][u].y);
+            else rz[u] = make_double2(0.0, 0.0);
           }
-          const double2 sp = *reinterpret_cast<const double2*>(c.INp + si);
-          const double2 rsp = DUAL ? *reinterpret_cast<const double2*>(c.RINp + si) : make_double2(0.0, 0.0);
+          const double2 sp = spv[t], rsp = rspv[t];
           const LstmCellFwd a = lstm_cell_fwd<DUAL>(z[0].x, z[1].x, z[2].x, z[3].x, sp.x, rz[0].x, rz[1].x, rz[2].x, rz[3].x, rsp.x);
           const LstmCellFwd b = lstm_cell_fwd<DUAL>(z[0].y, z[1].y, z[2].y, z[3].y, sp.y, rz[0].y, rz[1].y, rz[2].y, rz[3].y, rsp.y);
           *reinterpret_cast<double2*>(gp) = make_double2(a.i, b.i);
@@ -714,6 +773,42 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const LstmStepArgs& c = sp.lstm;
       const uint32_t xchg = base + L::kXchgOffset;
       const uint32_t rank = cluster_ctarank();
+      const int H = c.H;
+      const int first = warp * PER;                 // this warp's chunk of the quarter's NQ x NV1 values
+      const int sub = first / NV1;                  // which warp of the quarter produced them
+      const int sw = (int)rank * NQ + sub;          // ... and its position in the tile
+      const int sw_i0 = (sw / T::WJ) * (TI * 8), sw_j0 = (sw % T::WJ) * (TJ * 8);
+      // The cell's operands at this thread's output positions do not depend on the exchange: request them BEFORE the two
+      // cluster barriers (and all pairs before the first store -- SGF is read and written in place, so the compiler cannot
+      // hoist the second pair's loads above the first pair's stores): their latency, requested into L2 when the CTA started,
+      // hides behind the exchange instead of following it pair by pair.
+      constexpr int NX = PER / 2;
+      struct CellOperands { double2 carry, gI, gM, gF, gO, sp, sn, dm, rcarry, rI, rM, rF, rO, rsp, rsn, rdm; };
+      CellOperands op[NX];
+#pragma unroll
+      for (int xi = 0; xi < NX; ++xi) {
+        const int v = first % NV1 + 2 * xi;         // even: the pair (e = 0, 1) of one 8 x 8 block
+        const int t = v / (TJ * 2), u = (v / 2) % TJ;
+        const long long i = i0 + sw_i0 + 8 * t + g;
+        const int j = j0 + sw_j0 + 8 * u + 2 * j4;  // and j + 1
+        CellOperands& o = op[xi];
+        o.carry = o.gI = o.gM = o.gF = o.gO = o.sp = o.sn = o.dm = make_double2(0.0, 0.0);
+        o.rcarry = o.rI = o.rM = o.rF = o.rO = o.rsp = o.rsn = o.rdm = make_double2(0.0, 0.0);
+        if (i >= p.I || j >= p.J) continue;
+        const long long ei = i * H + j, gi = i * 4 * H + j, si = i * c.ld + j;
+        o.carry = *reinterpret_cast<const double2*>(c.SGF + ei);
+        o.gI = *reinterpret_cast<const double2*>(c.Gm + gi); o.gM = *reinterpret_cast<const double2*>(c.Gm + gi + H);
+        o.gF = *reinterpret_cast<const double2*>(c.Gm + gi + 2 * H); o.gO = *reinterpret_cast<const double2*>(c.Gm + gi + 3 * H);
+        o.sp = *reinterpret_cast<const double2*>(c.INm + si); o.sn = *reinterpret_cast<const double2*>(c.INt + si);
+        o.dm = *reinterpret_cast<const double2*>(c.DAUGm + si);
+        if (DUAL) {
+          o.rcarry = *reinterpret_cast<const double2*>(c.RSGF + ei);
+          o.rI = *reinterpret_cast<const double2*>(c.RGm + gi); o.rM = *reinterpret_cast<const double2*>(c.RGm + gi + H);
+          o.rF = *reinterpret_cast<const double2*>(c.RGm + gi + 2 * H); o.rO = *reinterpret_cast<const double2*>(c.RGm + gi + 3 * H);
+          o.rsp = *reinterpret_cast<const double2*>(c.RINm + si); o.rsn = *reinterpret_cast<const double2*>(c.RINt + si);
+          o.rdm = *reinterpret_cast<const double2*>(c.RDAUGm + si);
+        }
+      }
       cluster_sync();  // every CTA of the cluster is running and past its main loop: exchange buffers may be written
       {
         // this warp's partial sums go to the CTA that owns its quarter: slot [source rank][warp within quarter][value][lane]
@@ -730,17 +825,12 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
       }
       cluster_sync();  // all partials have landed (release / acquire at cluster scope)
-      const int H = c.H;
-      const int first = warp * PER;                 // this warp's chunk of the quarter's NQ x NV1 values
-      const int sub = first / NV1;                  // which warp of the quarter produced them
-      const int sw = (int)rank * NQ + sub;          // ... and its position in the tile
-      const int sw_i0 = (sw / T::WJ) * (TI * 8), sw_j0 = (sw % T::WJ) * (TJ * 8);
 #pragma unroll
-      for (int x = 0; x < PER; x += 2) {
-        const int v = first % NV1 + x;              // even: the pair (e = 0, 1) of one 8 x 8 block
+      for (int xi = 0; xi < NX; ++xi) {
+        const int v = first % NV1 + 2 * xi;
         const int t = v / (TJ * 2), u = (v / 2) % TJ;
         const long long i = i0 + sw_i0 + 8 * t + g;
-        const int j = j0 + sw_j0 + 8 * u + 2 * j4;  // and j + 1
+        const int j = j0 + sw_j0 + 8 * u + 2 * j4;
         if (i >= p.I || j >= p.J) continue;
         double s0[2], s1[2];
 #pragma unroll
@@ -754,25 +844,12 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           }
           s0[e] = a; s1[e] = r;
         }
-        const long long ei = i * H + j, gi = i * 4 * H + j, si = i * c.ld + j;
-        const double2 carry = *reinterpret_cast<const double2*>(c.SGF + ei);
-        const double2 gI = *reinterpret_cast<const double2*>(c.Gm + gi), gM = *reinterpret_cast<const double2*>(c.Gm + gi + H);
-        const double2 gF = *reinterpret_cast<const double2*>(c.Gm + gi + 2 * H), gO = *reinterpret_cast<const double2*>(c.Gm + gi + 3 * H);
-        const double2 sp = *reinterpret_cast<const double2*>(c.INm + si), sn = *reinterpret_cast<const double2*>(c.INt + si);
-        const double2 dm = *reinterpret_cast<const double2*>(c.DAUGm + si);
-        double2 rcarry, rI, rM, rF, rO, rsp, rsn, rdm;
-        rcarry = rI = rM = rF = rO = rsp = rsn = rdm = make_double2(0.0, 0.0);
-        if (DUAL) {
-          rcarry = *reinterpret_cast<const double2*>(c.RSGF + ei);
-          rI = *reinterpret_cast<const double2*>(c.RGm + gi); rM = *reinterpret_cast<const double2*>(c.RGm + gi + H);
-          rF = *reinterpret_cast<const double2*>(c.RGm + gi + 2 * H); rO = *reinterpret_cast<const double2*>(c.RGm + gi + 3 * H);
-          rsp = *reinterpret_cast<const double2*>(c.RINm + si); rsn = *reinterpret_cast<const double2*>(c.RINt + si);
-          rdm = *reinterpret_cast<const double2*>(c.RDAUGm + si);
-        }
-        const LstmCellBwd a = lstm_cell_bwd<DUAL>(gI.x, gM.x, gF.x, gO.x, sp.x, sn.x, dm.x, carry.x + s0[0], rI.x, rM.x, rF.x, rO.x,
-                                                  rsp.x, rsn.x, rdm.x, rcarry.x + s1[0]);
-        const LstmCellBwd b = lstm_cell_bwd<DUAL>(gI.y, gM.y, gF.y, gO.y, sp.y, sn.y, dm.y, carry.y + s0[1], rI.y, rM.y, rF.y, rO.y,
-                                                  rsp.y, rsn.y, rdm.y, rcarry.y + s1[1]);
+        const long long ei = i * H + j, gi = i * 4 * H + j;
+        const CellOperands& o = op[xi];
+        const LstmCellBwd a = lstm_cell_bwd<DUAL>(o.gI.x, o.gM.x, o.gF.x, o.gO.x, o.sp.x, o.sn.x, o.dm.x, o.carry.x + s0[0], o.rI.x, o.rM.x,
+                                                  o.rF.x, o.rO.x, o.rsp.x, o.rsn.x, o.rdm.x, o.rcarry.x + s1[0]);
+        const LstmCellBwd b = lstm_cell_bwd<DUAL>(o.gI.y, o.gM.y, o.gF.y, o.gO.y, o.sp.y, o.sn.y, o.dm.y, o.carry.y + s0[1], o.rI.y, o.rM.y,
+                                                  o.rF.y, o.rO.y, o.rsp.y, o.rsn.y, o.rdm.y, o.rcarry.y + s1[1]);
         *reinterpret_cast<double2*>(c.D4m + gi) = make_double2(a.di, b.di);
         *reinterpret_cast<double2*>(c.D4m + gi + H) = make_double2(a.dm, b.dm);
         *reinterpret_cast<double2*>(c.D4m + gi + 2 * H) = make_double2(a.df, b.df);
