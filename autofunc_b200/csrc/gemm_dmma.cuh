@@ -908,7 +908,9 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         // pair between the stores -- the outputs may alias them as far as the compiler knows -- a thread paid TI x TJ
         // serialised DRAM round trips per tile while its CTA issued no DMMA.  Here a whole fragment row (TJ pairs of both
         // vectors) is requested through the read-only path BEFORE the previous row is computed and stored: TI round
-        // trips, each hidden behind a row's arithmetic.
+        // trips, each hidden behind a row's arithmetic.  (Requesting the tile into L2 when the CTA starts was measured on
+        // top of this and lost 6 us on the bench's layer-2 launch, 793.6 vs 787.5 us: the prefetches compete with the
+        // first operand tiles.)
         const bool sig = p.epi == EPI_SIGMOID_BWD || p.epi == EPI_SIGMOID_BWD_COLSUM;
         if (sig && vec_ok && (p.lds & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.s) | reinterpret_cast<uintptr_t>(p.rs)) & 15) == 0) {
           const bool with_colsum = p.epi == EPI_SIGMOID_BWD_COLSUM;
