@@ -696,50 +696,58 @@ struct FrWgradArgs {
   double* gW; double* rgW;
   double* part; unsigned* tickets;
   int rows, cols, chunks, dual;
-  long long n, per_chunk;   // samples per chunk (a multiple of 8)
+  long long n, per_chunk;   // samples per chunk (a multiple of the 64-sample tile)
 };
 
+constexpr int kFrwTile = 64;  // samples per staged tile: eight per warp
+
 template <int MMAX>
-__global__ void __launch_bounds__(256, MMAX <= 8 ? 2 : 1) few_rows_wgrad_kernel(const FrWgradArgs a) {
+__global__ void __launch_bounds__(256, 1) few_rows_wgrad_kernel(const FrWgradArgs a) {
   constexpr int NQ = 2 * MMAX * 2;                 // {g, rg} x row x pair
   __shared__ double buf[NQ * 32];
+  // the tile's upstream rows U / UR (64 x rows values each) go through shared memory: read straight from global -- one
+  // broadcast load per (sample, row), each consumed at once -- the kernel was a chain of L1 / L2 round trips (ncu: 20
+  // cycles per issued instruction, long_scoreboard; 63.6 us on the bench head)
+  __shared__ double su[kFrwTile * MMAX], sur[kFrwTile * MMAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 64 + 2 * lane;
   const bool col_ok = c < a.cols;
   const bool has_ur = a.dual && a.UR != nullptr, has_rx = a.dual && a.RX != nullptr;
-  const long long per_warp = a.per_chunk >> 3;
-  const long long s0 = (long long)blockIdx.y * a.per_chunk + warp * per_warp;
-  long long s1 = s0 + per_warp;
-  if (s1 > a.n) s1 = a.n;
+  const long long c0 = (long long)blockIdx.y * a.per_chunk;            // per_chunk is a multiple of kFrwTile
+  const long long c1 = min(c0 + a.per_chunk, a.n);
   double g[MMAX][2], rg[MMAX][2];
 #pragma unroll
   for (int m = 0; m < MMAX; ++m) g[m][0] = g[m][1] = rg[m][0] = rg[m][1] = 0.0;
-  constexpr int UNR = 4;                      // samples whose X / RX loads are in flight together
-  for (long long i = s0; i < s1; i += UNR) {
-    double2 x[UNR], rx[UNR];
+  constexpr int SPW = kFrwTile / 8;           // samples per warp and tile, all of whose X / RX loads are in flight together
+  for (long long t0 = c0; t0 < c1; t0 += kFrwTile) {
+    const long long s0 = t0 + warp * SPW;
+    double2 x[SPW], rx[SPW];
 #pragma unroll
-    for (int q = 0; q < UNR; ++q) {
-      const bool ok = col_ok && i + q < s1;
-      x[q] = ok ? ld2g(a.X + (i + q) * a.cols + c) : make_double2(0.0, 0.0);
-      rx[q] = (ok && has_rx) ? ld2g(a.RX + (i + q) * a.cols + c) : make_double2(0.0, 0.0);
+    for (int q = 0; q < SPW; ++q) {
+      const bool ok = col_ok && s0 + q < c1;
+      x[q] = ok ? ld2g(a.X + (s0 + q) * a.cols + c) : make_double2(0.0, 0.0);
+      rx[q] = (ok && has_rx) ? ld2g(a.RX + (s0 + q) * a.cols + c) : make_double2(0.0, 0.0);
     }
+    __syncthreads();  // the previous tile's upstream rows have been consumed
+    const int live = (int)min((long long)kFrwTile, c1 - t0) * a.rows;   // U[t0 .. t0 + 64) is one contiguous run
+    for (int e = threadIdx.x; e < kFrwTile * a.rows; e += 256) {
+      su[e] = e < live ? a.U[t0 * a.rows + e] : 0.0;
+      sur[e] = (e < live && has_ur) ? a.UR[t0 * a.rows + e] : 0.0;
+    }
+    __syncthreads();
 #pragma unroll
-    for (int q = 0; q < UNR; ++q) {
-      if (i + q < s1) {
-        const double* u = a.U + (i + q) * a.rows;
-        const double* ur = a.UR + (i + q) * a.rows;
+    for (int q = 0; q < SPW; ++q) {
+      const double* u = su + (warp * SPW + q) * a.rows;   // (samples past the end were staged as zeros)
+      const double* ur = sur + (warp * SPW + q) * a.rows;
 #pragma unroll
-        for (int m = 0; m < MMAX; ++m) {
-          if (m < a.rows) {
-            const double um = __ldg(u + m);          // the same address in every lane: one broadcast transaction
-            g[m][0] = fma(um, x[q].x, g[m][0]); g[m][1] = fma(um, x[q].y, g[m][1]);
-            if (a.dual) {
-              rg[m][0] = fma(um, rx[q].x, rg[m][0]); rg[m][1] = fma(um, rx[q].y, rg[m][1]);
-              if (has_ur) {
-                const double urm = __ldg(ur + m);
-                rg[m][0] = fma(urm, x[q].x, rg[m][0]); rg[m][1] = fma(urm, x[q].y, rg[m][1]);
-              }
-            }
+      for (int m = 0; m < MMAX; ++m) {
+        if (m < a.rows) {
+          const double um = u[m];                      // the same address in every lane: a broadcast
+          g[m][0] = fma(um, x[q].x, g[m][0]); g[m][1] = fma(um, x[q].y, g[m][1]);
+          if (a.dual) {
+            const double urm = ur[m];
+            rg[m][0] = fma(urm, x[q].x, fma(um, rx[q].x, rg[m][0]));
+            rg[m][1] = fma(urm, x[q].y, fma(um, rx[q].y, rg[m][1]));
           }
         }
       }
@@ -901,12 +909,12 @@ int launch_few_rows_wgrad(af_ctx* ctx, FrWgradArgs& a) {
   constexpr int NQ = 2 * MMAX * 2;
   auto kern = few_rows_wgrad_kernel<MMAX>;
   const long long colblocks = (a.cols + 63) / 64;
-  long long chunks = ((MMAX <= 8 ? 2ll : 1ll) * ctx->sm_count) / colblocks;   // resident blocks per SM (register-bound)
+  long long chunks = ctx->sm_count / colblocks;   // one resident block per SM (accumulators + a tile's X / RX pairs in registers)
   const long long max_by_n = (a.n + 63) / 64, max_by_scratch = ctx->scratch_doubles / (colblocks * NQ * 32);
   if (chunks > max_by_n) chunks = max_by_n;
   if (chunks > max_by_scratch) chunks = max_by_scratch;
   if (chunks < 1) chunks = 1;
-  a.per_chunk = ((a.n + chunks - 1) / chunks + 7) / 8 * 8;
+  a.per_chunk = ((a.n + chunks - 1) / chunks + kFrwTile - 1) / kFrwTile * kFrwTile;
   a.chunks = (int)((a.n + a.per_chunk - 1) / a.per_chunk);
   kern<<<dim3((unsigned)colblocks, (unsigned)a.chunks), 256, 0, ctx->stream>>>(a);
   return after_launch(ctx, "few_rows_wgrad_kernel", KIND_SMALL_N, 8.0 * a.n * a.cols * ((a.dual && a.RX) ? 2 : 1));
