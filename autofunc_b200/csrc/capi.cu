@@ -260,6 +260,7 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
   }
   if (!strcmp(name, "persist_tiles")) {
     if (value < 0 || value > 2) return fail(AF_EINVAL, "persist_tiles must be 0, 1 or 2");
+    if (value != 0 && !AF_PERSIST_TILES) return fail(AF_ENOTSUP, "persist_tiles: the library was built without -DAF_PERSIST_TILES=1 (the mode measured slower)");
     ctx->persist_tiles = value;
     return AF_OK;
   }

@@ -255,7 +255,7 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   // launches).  Give each of <= `slots` CTAs m whole tiles instead: the TMA ring runs on into the next tile while the
   // current one is stored, the epilogue stays fused (no atomics, no zeroing, no deferred pass).
   long long tiles_per_cta = 0;
-  if (mode == 0 && ctx->persist_tiles && cfg != 0 && tiles > slots) {
+  if (AF_PERSIST_TILES && mode == 0 && ctx->persist_tiles && cfg != 0 && tiles > slots) {
     tiles_per_cta = (tiles + slots - 1) / slots;
     mode = 3;
   }

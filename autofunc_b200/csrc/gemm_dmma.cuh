@@ -865,7 +865,66 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       return;
     }
-    if constexpr (SPECIAL == 0) {
+#ifndef AF_PERSIST_TILES
+#define AF_PERSIST_TILES 0  // 1: compile the persistent whole-tile mode (af_set_option "persist_tiles"; measured slower) into the stream-K kernels
+#endif
+    if constexpr (SPECIAL == 0 && MULTI && !AF_PERSIST_TILES) {
+      // stream-K: tile segments always meet in red.global.add.f64 (the elementwise step, if any, follows in
+      // gemm_epilogue_kernel).  Nothing else is compiled into these instantiations: their main loops lose 2-3 % whenever
+      // the epilogue code around them grows (register allocation is per kernel).
+#pragma unroll
+      for (int t = 0; t < TI; ++t) {
+        const long long i = i0 + wi0 + 8 * t + g;
+        if (i < p.I) {
+#pragma unroll
+          for (int u = 0; u < TJ; ++u) {
+            const int j = j0 + wj0 + 8 * u + 2 * j4;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              if (j + e < p.J) {
+                const long long o = p.transpose_out ? (long long)(j + e) * p.ldo + i : i * p.ldo + j + e;
+                if (p.out0) atomicAdd(p.out0 + o, acc0[t][u][e]);
+                if (DUAL && p.out1) atomicAdd(p.out1 + o, acc1[DUAL ? t : 0][u][e]);
+              }
+            }
+          }
+        }
+      }
+      return;
+    }
+    if constexpr (SPECIAL == 0 && !(MULTI && !AF_PERSIST_TILES)) {
+      if (!MULTI && ALAY == LAY_KC && BLAY == LAY_KC && p.epi == EPI_BIAS_SIGMOID && vec_ok && i0 + BM <= p.I && j0 + BN <= p.J) {
+        // dense forward on an interior tile (lin_add.go:15-17,37-42 + math_funcs.go:292,305-309): one straight-line
+        // batch per fragment row -- TJ x 2 independent sigmoids in flight -- instead of the generic path below, which
+        // decides the epilogue kind and the bounds anew for every column pair and so runs one exp / reciprocal chain at
+        // a time (a 64 x 64 tile is 32 such chains per thread, with the CTA issuing no DMMA meanwhile).  Compiled into the
+        // one-tile forward instantiation only: the other instantiations' main loops are sensitive to any growth of their
+        // epilogues (the stream-K launches lost 20-25 us each with this block present and never taken).
+        double2 bz[TJ], rbz[TJ];
+#pragma unroll
+        for (int u = 0; u < TJ; ++u) {
+          const int j = j0 + wj0 + 8 * u + 2 * j4;
+          bz[u] = p.bias0 ? make_double2(__ldg(p.bias0 + j), __ldg(p.bias0 + j + 1)) : make_double2(0.0, 0.0);
+          rbz[u] = (DUAL && p.bias1) ? make_double2(__ldg(p.bias1 + j), __ldg(p.bias1 + j + 1)) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int t = 0; t < TI; ++t) {
+          const long long row = (i0 + wi0 + 8 * t + g) * p.ldo + j0 + wj0 + 2 * j4;
+          double2 sg[TJ];
+#pragma unroll
+          for (int u = 0; u < TJ; ++u)
+            sg[u] = make_double2(sigmoid_f64(acc0[t][u][0] + bz[u].x), sigmoid_f64(acc0[t][u][1] + bz[u].y));
+#pragma unroll
+          for (int u = 0; u < TJ; ++u) {
+            if (p.out0) *reinterpret_cast<double2*>(p.out0 + row + 8 * u) = sg[u];
+            if (DUAL && p.out1)
+              *reinterpret_cast<double2*>(p.out1 + row + 8 * u) =
+                  make_double2(sg[u].x * (1 - sg[u].x) * (acc1[DUAL ? t : 0][u][0] + rbz[u].x),
+                               sg[u].y * (1 - sg[u].y) * (acc1[DUAL ? t : 0][u][1] + rbz[u].y));
+          }
+        }
+        return;
+      }
       if (p.epi == EPI_ACCUM && vec_ok) {
         // beta = 1 accumulation (lin_tran.go:210,267-268) with plain stores: fetch a whole fragment row of C before adding
         // to it.  Written pair by pair (load, add, store, load, ...) the stores fence the next load -- the outputs may alias

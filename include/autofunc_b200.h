@@ -86,7 +86,8 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * k-tiles in rotated order, so that all CTAs sweep k in lockstep and share operand panels in L2 (DRAM reads of the bench
  * weight gradient 2.44 GB -> 0.46 GB, same time); 0 = every segment ascending from its first k-tile.
  * "sk_bias": stream-K's cost in the work-decomposition model, percent (A/B of the model's threshold).
- * "persist_tiles": 1 | 2 = multi-wave one-tile-per-CTA launches as persistent CTAs over whole tiles (measured slower; 0).
+ * "persist_tiles": 1 | 2 = multi-wave one-tile-per-CTA launches as persistent CTAs over whole tiles (measured slower; only in
+ * builds with -DAF_PERSIST_TILES=1, AF_ENOTSUP otherwise: keeping the mode compiled in cost the stream-K launches 2-3 %).
  * "small_mlp": 1 (default) = af_mlp_step with <= 4 samples runs as ONE persistent cooperative kernel
  * (all layers, both directions, grid barriers between phases); 0 = the per-kernel CUDA graph.
  * "dp_max_ctas": CTA cap of the context's communicator (ncclConfig_t.maxCTAs; default 8, 0 = NCCL's own choice); read by
