@@ -175,14 +175,22 @@ __device__ __forceinline__ LstmCellBwd lstm_cell_bwd(double i, double m, double 
   return c;
 }
 
-template <bool DUAL>
+// FAM: the epilogue families an instantiation can meet (the others are not compiled into it -- the tensor-core kernels'
+// main loops lose speed with every block of epilogue code around them): 1 = bias / bias + sigmoid (forward),
+// 2 = sigmoid backward (input gradient), 4 = plain accumulation (weight gradient, accumulating input gradients);
+// plain and atomic stores are always there.
+enum : int { FAM_BIAS = 1, FAM_SIGMOID_BWD = 2, FAM_ACCUM = 4, FAM_ALL = 7 };
+
+template <bool DUAL, int FAM = FAM_ALL>
 __device__ __forceinline__ void epi_transform(const GemmArgs& p, long long i, int j, double& v0, double& v1) {
   switch (p.epi) {
     case EPI_BIAS:
+      if (!(FAM & FAM_BIAS)) break;
       if (p.bias0) v0 += p.bias0[j];
       if (DUAL && p.bias1) v1 += p.bias1[j];
       break;
     case EPI_BIAS_SIGMOID: {
+      if (!(FAM & FAM_BIAS)) break;
       double z = v0 + (p.bias0 ? p.bias0[j] : 0.0);
       double s = sigmoid_f64(z);
       v0 = s;
@@ -194,6 +202,7 @@ __device__ __forceinline__ void epi_transform(const GemmArgs& p, long long i, in
     }
     case EPI_SIGMOID_BWD:
     case EPI_SIGMOID_BWD_COLSUM: {
+      if (!(FAM & FAM_SIGMOID_BWD)) break;
       // math_funcs.go:365-371, operand order kept: u' = x(1-x)u ; uR' = xR(1-x)u - x xR u + x(1-x)uR
       double x = p.s[i * p.lds + j];
       double u = v0;
@@ -209,29 +218,29 @@ __device__ __forceinline__ void epi_transform(const GemmArgs& p, long long i, in
   }
 }
 
-template <bool DUAL>
+template <bool DUAL, int FAM = FAM_ALL>
 __device__ __forceinline__ void epi_elem(const GemmArgs& p, long long i, int j, double v0, double v1) {
   long long o = p.transpose_out ? (long long)j * p.ldo + i : i * p.ldo + j;
-  if (p.epi == EPI_ACCUM) {
+  if ((FAM & FAM_ACCUM) && p.epi == EPI_ACCUM) {
     if (p.out0) p.out0[o] += v0;
     if (DUAL && p.out1) p.out1[o] += v1;
   } else if (p.epi == EPI_ACCUM_ATOMIC) {
     if (p.out0) atomicAdd(p.out0 + o, v0);
     if (DUAL && p.out1) atomicAdd(p.out1 + o, v1);
   } else {
-    epi_transform<DUAL>(p, i, j, v0, v1);
+    epi_transform<DUAL, FAM>(p, i, j, v0, v1);
     if (p.out0) p.out0[o] = v0;
     if (DUAL && p.out1) p.out1[o] = v1;
   }
 }
 
 // two adjacent columns (j, j+1), j even; 16-byte accesses when the row pitch allows
-template <bool DUAL>
+template <bool DUAL, int FAM = FAM_ALL>
 __device__ __forceinline__ void epi_pair(const GemmArgs& p, bool vec_ok, long long i, int j, double a0, double a1,
                                          double r0, double r1) {
   if (j + 1 < p.J && vec_ok) {
     long long o = i * p.ldo + j;
-    if (p.epi == EPI_ACCUM) {
+    if ((FAM & FAM_ACCUM) && p.epi == EPI_ACCUM) {
       if (p.out0) {
         double2 c = *reinterpret_cast<double2*>(p.out0 + o);
         c.x += a0; c.y += a1;
@@ -246,14 +255,14 @@ __device__ __forceinline__ void epi_pair(const GemmArgs& p, bool vec_ok, long lo
       if (p.out0) { atomicAdd(p.out0 + o, a0); atomicAdd(p.out0 + o + 1, a1); }
       if (DUAL && p.out1) { atomicAdd(p.out1 + o, r0); atomicAdd(p.out1 + o + 1, r1); }
     } else {
-      epi_transform<DUAL>(p, i, j, a0, r0);
-      epi_transform<DUAL>(p, i, j + 1, a1, r1);
+      epi_transform<DUAL, FAM>(p, i, j, a0, r0);
+      epi_transform<DUAL, FAM>(p, i, j + 1, a1, r1);
       if (p.out0) *reinterpret_cast<double2*>(p.out0 + o) = make_double2(a0, a1);
       if (DUAL && p.out1) *reinterpret_cast<double2*>(p.out1 + o) = make_double2(r0, r1);
     }
   } else {
-    if (j < p.J) epi_elem<DUAL>(p, i, j, a0, r0);
-    if (j + 1 < p.J) epi_elem<DUAL>(p, i, j + 1, a1, r1);
+    if (j < p.J) epi_elem<DUAL, FAM>(p, i, j, a0, r0);
+    if (j + 1 < p.J) epi_elem<DUAL, FAM>(p, i, j + 1, a1, r1);
   }
 }
 
@@ -464,6 +473,10 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   using L = GemmSmem<NACC, CFG>;
   using T = TileCfg<CFG>;
   constexpr bool DUAL = (NACC == 2);
+  // epilogue families by call site: <KC,KC> forward, <KC,RC> input gradient (incl. accumulating ones), <RC,RC> weight gradient
+  constexpr int FAM = (ALAY == LAY_KC && BLAY == LAY_KC) ? FAM_BIAS
+                      : (ALAY == LAY_KC && BLAY == LAY_RC) ? (FAM_SIGMOID_BWD | FAM_ACCUM)
+                      : (ALAY == LAY_RC && BLAY == LAY_RC) ? FAM_ACCUM : FAM_ALL;
   constexpr int TI = T::TI, TJ = T::TJ, BM = L::kBMc, BN = L::kBNc, kStages = L::kStages, kConsumerWarps = L::kWarps;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle atoms are 1024-B aligned
@@ -925,7 +938,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         return;
       }
-      if (p.epi == EPI_ACCUM && vec_ok) {
+      if ((FAM & FAM_ACCUM) && p.epi == EPI_ACCUM && vec_ok) {
         // beta = 1 accumulation (lin_tran.go:210,267-268) with plain stores: fetch a whole fragment row of C before adding
         // to it.  Written pair by pair (load, add, store, load, ...) the stores fence the next load -- the outputs may alias
         // as far as the compiler knows -- and a thread paid 32 serialised L2 round trips per tile.
@@ -953,7 +966,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 *reinterpret_cast<double2*>(p.out1 + i * p.ldo + j) =
                     make_double2(c1[u].x + acc1[DUAL ? t : 0][u][0], c1[u].y + acc1[DUAL ? t : 0][u][1]);
             } else if (j < p.J) {
-              epi_pair<DUAL>(p, vec_ok, i, j, acc0[t][u][0], acc0[t][u][1], DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0,
+              epi_pair<DUAL, FAM>(p, vec_ok, i, j, acc0[t][u][0], acc0[t][u][1], DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0,
                              DUAL ? acc1[DUAL ? t : 0][u][1] : 0.0);
             }
           }
@@ -1061,7 +1074,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           for (int u = 0; u < TJ; ++u) {
             const int j = j0 + wj0 + 8 * u + 2 * j4;
             if (j < p.J)
-              epi_pair<DUAL>(p, vec_ok, i, j, acc0[t][u][0], acc0[t][u][1], DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0,
+              epi_pair<DUAL, FAM>(p, vec_ok, i, j, acc0[t][u][0], acc0[t][u][1], DUAL ? acc1[DUAL ? t : 0][u][0] : 0.0,
                              DUAL ? acc1[DUAL ? t : 0][u][1] : 0.0);
           }
         }
