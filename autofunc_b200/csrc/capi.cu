@@ -287,6 +287,10 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->short_rows_off = value == 0;
     return AF_OK;
   }
+  if (!strcmp(name, "ops_runtime")) {
+    ctx->ops_runtime = value != 0;
+    return AF_OK;
+  }
   if (!strcmp(name, "fused_colsum")) {
     ctx->fused_colsum_off = value == 0;
     return AF_OK;

@@ -45,6 +45,7 @@ struct af_ctx {
   bool few_samples_tma = true;  // backward pass through warp-private TMA rings ("few_samples_tma" 0: the register-staged kernel)
   unsigned* fold_tickets = nullptr;  // ticket counters of the last-block-folds reductions (kFoldTickets, zero between launches)
   bool short_rows_off = false;  // A/B switch ("short_rows" 0): rows of <= 32 entries through the staged group kernels (mathops.cu)
+  bool ops_runtime = false;  // A/B switch ("ops_runtime" 1): the big contractions read the R operands' presence at run time (gemm_dmma_kernel OPS = -1)
   bool fused_colsum_off = false;  // A/B switch ("fused_colsum" 0): the MLP plan's bias gradients always as colsum_kernel passes
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu

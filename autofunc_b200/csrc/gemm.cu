@@ -96,9 +96,9 @@ double gemm_flops(const GemmArgs& a, bool dual) {
   return 2.0 * a.I * a.J * a.Kd * products;
 }
 
-template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI>
-int launch_dmma_impl(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3 grid) {
-  auto kern = gemm_dmma_kernel<ALAY, BLAY, NACC, CFG, MULTI>;
+template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI, int OPS = -1>
+int launch_dmma_ops(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3 grid) {
+  auto kern = gemm_dmma_kernel<ALAY, BLAY, NACC, CFG, MULTI, 0, OPS>;
   const int smem = (int)GemmSmem<NACC, CFG>::kTotal;
   // per template instantiation; the attribute is per device AND function.  Contexts on different devices may be driven
   // by different host threads: a device's bit is published only after its attribute call has returned (two threads may
@@ -112,6 +112,21 @@ int launch_dmma_impl(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args,
                                        ctx->pdl && !ctx->pdl_off, maps[0], maps[1], maps[2], maps[3], args, SpecialArgs<0>{});
   if (le != cudaSuccess) return cuda_fail(le, "gemm_dmma_kernel launch");
   return after_launch(ctx, "gemm_dmma_kernel", NACC == 2 ? KIND_GEMM_DUAL : KIND_GEMM_SINGLE, gemm_flops(args, NACC == 2));
+}
+
+// the paired configuration of the big dual contractions is compiled per set of present R operands (gemm_dmma_kernel OPS)
+template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI>
+int launch_dmma_impl(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3 grid) {
+  // (one-tile launches only: the stream-K instantiations measured SLOWER with the presence compiled in -- bench weight
+  // gradients 762 -> 795 and 1057 -> 1103 us -- while the one-tile forward / input-gradient launches gain 6-8 us each)
+  if constexpr (NACC == 2 && CFG == 2 && !MULTI) {
+    if (!ctx->ops_runtime) {
+      if (args.has_a1 && args.has_b1) return launch_dmma_ops<ALAY, BLAY, NACC, CFG, MULTI, 3>(ctx, maps, args, grid);
+      if (args.has_b1) return launch_dmma_ops<ALAY, BLAY, NACC, CFG, MULTI, 2>(ctx, maps, args, grid);
+      if (args.has_a1) return launch_dmma_ops<ALAY, BLAY, NACC, CFG, MULTI, 1>(ctx, maps, args, grid);
+    }
+  }
+  return launch_dmma_ops<ALAY, BLAY, NACC, CFG, MULTI, -1>(ctx, maps, args, grid);
 }
 
 // stream-K (ranges spanning tiles) is instantiated for the default and the narrow configuration only

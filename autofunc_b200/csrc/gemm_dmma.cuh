@@ -465,7 +465,11 @@ __device__ __forceinline__ uint32_t frag_addr(uint32_t base, int t) {
 //      split-K: CTA r of the cluster takes k-tiles [r kt/4, (r+1) kt/4)); every CTA sends warp w's partial accumulators
 //      to CTA w through distributed shared memory, and CTA w adds the four partials in rank order (deterministic, no
 //      atomics, no zeroing) and runs the cell backward of the previous time step on its 32 x 32 quarter of the tile.
-template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI, int SPECIAL = 0>
+// OPS: which R operands exist, as a compile-time fact: -1 = read GemmArgs::has_a1 / has_b1 at run time (every k-step then
+// branches around the products of an absent operand: eight branches per k-tile that cut the DMMA stream into basic
+// blocks), 1 = A1 only, 2 = B1 only, 3 = both.  The one-tile launches of the paired 64 x 64 configuration are instantiated
+// per case (gemm.cu), everything else takes -1.
+template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI, int SPECIAL = 0, int OPS = -1>
 __global__ void __launch_bounds__(TileCfg<CFG>::WI * TileCfg<CFG>::WJ * 32, TileCfg<CFG>::MIN_CTAS)
 gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const GemmArgs p,
@@ -493,7 +497,8 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (p.units_per_tile != kt_total && nun > kt_total - kt0) nun = kt_total - kt0;
   if (MULTI && p.wave_tiles > 0) nun = (p.wave_tiles - ((int)blockIdx.x < p.wave_rem ? 0 : 1)) * kt_total;
   if (nun <= 0) return;
-  const bool has_a1 = DUAL && p.has_a1, has_b1 = DUAL && p.has_b1;
+  const bool has_a1 = OPS < 0 ? (DUAL && p.has_a1) : (DUAL && (OPS & 1) != 0);
+  const bool has_b1 = OPS < 0 ? (DUAL && p.has_b1) : (DUAL && (OPS & 2) != 0);
   // sequence position -> output tile (identity unless the launch is wave-ordered)
   auto tile_of = [&](int q) { return (MULTI && p.wave_tiles > 0) ? (q % p.wave_tiles) * (int)gridDim.x + q / p.wave_tiles : q; };
 
