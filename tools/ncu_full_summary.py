@@ -37,7 +37,7 @@ def main():
           "L2 hit % | regs | smem bank conflicts | top stall reasons (warps stalled per issue)")
     launches = []
     for r in data:
-        name = re.sub(r"\(.*", "", r[col["Kernel Name"]].replace("void ", "")).strip()
+        name = re.sub(r"\(.*", "", r[col["Kernel Name"]].replace("void ", "").replace("(int)", "").replace("(bool)", "")).strip()
         stalls = sorted(((val(r, h), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")])
                          for h in stall_cols), reverse=True)[:4]
         d = {"kernel": name, "grid": r[col["Grid Size"]], "block": r[col["Block Size"]],

@@ -29,6 +29,7 @@ def main():
     agg = defaultdict(lambda: defaultdict(float))
     for d in launches.values():
         name = d["name"].replace("void ", "").replace("unnamed>::", "")
+        name = name.replace("(int)", "").replace("(bool)", "")
         name = re.sub(r"\[lambda.*", "[lambda]", name)
         name = re.sub(r"\((?:af::|const|double|long|int|unsigned|CUtensorMap|GemmArgs|SmallMlpArgs).*", "", name).strip()[:110]
         a = agg[name]
