@@ -107,6 +107,10 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * deterministic in both modes; the sum over ranks is NCCL's, which is run-to-run deterministic for a fixed communicator.)
  * "few_rows_wgrad": the weight gradient of a layer with <= 16 output rows over a batch of >= 64 samples (the bench
  * network's 10-class head) as a streaming kernel with ordered sums: 0 never, 1 (default) in deterministic mode, 2 always.
+ * "fused_colsum": 1 (default) = the MLP plans' bias gradients (column sums of a layer's upstream, lin_add.go:94-104) are
+ * added by the epilogue of the input-gradient launch that produces that upstream (float64 atomics; never in deterministic
+ * mode); 0 = always a colsum_kernel pass.  "ops_runtime": 1 = the one-tile launches of the big contractions read the R
+ * operands' presence at run time instead of taking the instantiation compiled for it (A/B; default 0).
  * "short_rows": 1 (default) = softmax over rows of <= 32 entries: per-entry work in the coalesced phases, one thread per row for the sums;
  * 0 = the staged group kernels that serve longer rows.
  * Plan-owned CUDA graphs captured before a change of any option are re-captured.                        */
