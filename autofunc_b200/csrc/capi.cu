@@ -117,6 +117,8 @@ int af_ctx_destroy(af_ctx* ctx) {
   af_dp_destroy(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->fold_tickets) cudaFree(ctx->fold_tickets);
+  if (ctx->sk_part) cudaFree(ctx->sk_part);
+  if (ctx->sk_flags) cudaFree(ctx->sk_flags);
   if (ctx->barrier_word) cudaFree(ctx->barrier_word);
   for (cudaEvent_t ev : ctx->trace_events) cudaEventDestroy(ev);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -289,6 +291,11 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
   }
   if (!strcmp(name, "ops_runtime")) {
     ctx->ops_runtime = value != 0;
+    return AF_OK;
+  }
+  if (!strcmp(name, "sk_fixup")) {
+    if (value < 0 || value > 2) return fail(AF_EINVAL, "sk_fixup must be 0, 1 or 2");
+    ctx->sk_fixup = value;
     return AF_OK;
   }
   if (!strcmp(name, "fused_colsum")) {

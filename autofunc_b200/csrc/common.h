@@ -46,6 +46,9 @@ struct af_ctx {
   unsigned* fold_tickets = nullptr;  // ticket counters of the last-block-folds reductions (kFoldTickets, zero between launches)
   bool short_rows_off = false;  // A/B switch ("short_rows" 0): rows of <= 32 entries through the staged group kernels (mathops.cu)
   bool ops_runtime = false;  // A/B switch ("ops_runtime" 1): the big contractions read the R operands' presence at run time (gemm_dmma_kernel OPS = -1)
+  int sk_fixup = 1;               // stream-K with the ordered fix-up ("sk_fixup"): 0 never, 1 in deterministic mode, 2 wherever stream-K is chosen
+  double* sk_part = nullptr;      // its workspace: one partial tile per CTA ...
+  unsigned* sk_flags = nullptr;   // ... and one flag per CTA and warp (gemm.cu: fixup_workspace)
   bool fused_colsum_off = false;  // A/B switch ("fused_colsum" 0): the MLP plan's bias gradients always as colsum_kernel passes
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu

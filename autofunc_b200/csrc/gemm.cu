@@ -114,6 +114,36 @@ int launch_dmma_ops(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, 
   return after_launch(ctx, "gemm_dmma_kernel", NACC == 2 ? KIND_GEMM_DUAL : KIND_GEMM_SINGLE, gemm_flops(args, NACC == 2));
 }
 
+// stream-K with the ordered fix-up (gemm_dmma_kernel SPECIAL = 3): paired configuration only
+template <int ALAY, int BLAY, int NACC>
+int launch_dmma_fixup(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3 grid) {
+  auto kern = gemm_dmma_kernel<ALAY, BLAY, NACC, 2, true, 3>;
+  const int smem = (int)GemmSmem<NACC, 2>::kTotal;
+  static std::atomic<unsigned long long> configured{0};
+  if (!(configured.load(std::memory_order_acquire) >> (ctx->device & 63) & 1ull)) {
+    AF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured.fetch_or(1ull << (ctx->device & 63), std::memory_order_release);
+  }
+  SpecialArgs<3> sp{};
+  sp.fix.part = ctx->sk_part;
+  sp.fix.flags = ctx->sk_flags;
+  const cudaError_t le = launch_kernel(kern, grid, dim3(GemmSmem<NACC, 2>::kThreads), (size_t)smem, ctx->stream,
+                                       ctx->pdl && !ctx->pdl_off, maps[0], maps[1], maps[2], maps[3], args, sp);
+  if (le != cudaSuccess) return cuda_fail(le, "gemm_dmma_kernel (stream-K fix-up) launch");
+  return after_launch(ctx, "gemm_dmma_kernel", NACC == 2 ? KIND_GEMM_DUAL : KIND_GEMM_SINGLE, gemm_flops(args, NACC == 2));
+}
+
+// workspace of the fix-up: one partial tile per CTA of a stream-K launch (two per SM) and one flag per CTA and warp
+int fixup_workspace(af_ctx* ctx) {
+  if (ctx->sk_part) return AF_OK;
+  const size_t ctas = 2 * (size_t)ctx->sm_count + 1;
+  const size_t part_bytes = ctas * 2 * 4 * 4 * 2 * GemmSmem<2, 2>::kThreads * sizeof(double);  // NACC x TI x TJ x 2 values per thread
+  AF_CUDA(cudaMalloc(&ctx->sk_part, part_bytes));
+  AF_CUDA(cudaMalloc(&ctx->sk_flags, ctas * GemmSmem<2, 2>::kWarps * sizeof(unsigned)));
+  AF_CUDA(cudaMemsetAsync(ctx->sk_flags, 0, ctas * GemmSmem<2, 2>::kWarps * sizeof(unsigned), ctx->stream));
+  return AF_OK;
+}
+
 // the paired configuration of the big dual contractions is compiled per set of present R operands (gemm_dmma_kernel OPS)
 template <int ALAY, int BLAY, int NACC, int CFG, bool MULTI>
 int launch_dmma_impl(af_ctx* ctx, const CUtensorMap* maps, const GemmArgs& args, dim3 grid) {
@@ -265,6 +295,21 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
     const double c = bias * 0.01 * (sk_units + cf * segs) + cd;
     if (cfg != 0 && (c < best * 0.98 || (must_defer && mode == 0))) { best = c; mode = 2; }
   }
+  // Stream-K with the ORDERED fix-up (SPECIAL = 3 of the kernel: no atomics, no zeroing, no deferred pass, the same bits on
+  // every run): the paired configuration, ranges of at least 16 k-tiles.  af_set_option "sk_fixup": 0 never, 1 (default) in deterministic mode -- which otherwise only has whole
+  // tiles per CTA --, 2 wherever stream-K is chosen.
+  const bool fixup_ok = cfg == 2 && !swapped && kt_total >= 8 && sk_units >= 16 &&
+                        (long long)((args.total_units + sk_units - 1) / sk_units) <= 2ll * ctx->sm_count &&
+                        (ctx->sk_fixup == 2 || (ctx->sk_fixup == 1 && ctx->deterministic));
+  if (fixup_ok) {
+    if (mode == 2) {
+      mode = 4;
+    } else if (mode == 0 && ctx->deterministic) {
+      const double segs = 1.0 + (double)(sk_units - 1) / kt_total;
+      const int bias = (sk_units >= 64 && (accumulate || tiles < 4 * slots)) ? ctx->sk_bias_long : ctx->sk_bias;
+      if (bias * 0.01 * (sk_units + cf * segs) < best * 0.98) mode = 4;
+    }
+  }
   // Persistent whole tiles: a launch of several waves of one-tile CTAs pays every CTA's prologue (barrier setup,
   // pipeline fill) and epilogue in the open (ncu: tensor pipe 85 % of elapsed vs 92 % for the 296-CTA stream-K
   // launches).  Give each of <= `slots` CTAs m whole tiles instead: the TMA ring runs on into the next tile while the
@@ -281,10 +326,11 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   } else if (mode == 1) {
     units_per_cta = (kt_total + best_s - 1) / best_s;
     units_per_tile = units_per_cta * best_s;
-  } else if (mode == 2) {
+  } else if (mode == 2 || mode == 4) {
     units_per_cta = sk_units;
     args.rotate = (ctx->sk_rotate && sk_units >= 64) ? 1 : 0;
   }
+  if (mode == 4) AF_TRY(fixup_workspace(ctx));
   // column sums of a sigmoid-backward output ride on the epilogue of whole-tile launches (float64 atomics: not in
   // deterministic mode, whose column sums are folded in block order by colsum_kernel)
   if (mode == 0 && !swapped && cfg == 2 && e.epi == EPI_SIGMOID_BWD && (e.colsum0 || e.colsum1) && e.colsum_done &&
@@ -323,6 +369,19 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
   const int nacc = dual ? 2 : 1;
   int rc = AF_EINVAL;
   bool dispatched = false;
+  if (mode == 4) {
+#define AF_FIXUP(AL, BL)                                                                                                   \
+  if (!dispatched && A.layout == AL && B.layout == BL) {                                                                   \
+    dispatched = true;                                                                                                     \
+    rc = nacc == 2 ? launch_dmma_fixup<AL, BL, 2>(ctx, maps, args, grid) : launch_dmma_fixup<AL, BL, 1>(ctx, maps, args, grid); \
+  }
+    AF_FIXUP(LAY_KC, LAY_KC)
+    AF_FIXUP(LAY_KC, LAY_RC)
+    AF_FIXUP(LAY_RC, LAY_RC)
+#undef AF_FIXUP
+    if (!dispatched) return fail(AF_EINVAL, "unsupported operand layout combination");
+    return rc;
+  }
 #define AF_DISPATCH(AL, BL)                                                                        \
   if (!dispatched && A.layout == AL && B.layout == BL) {                                           \
     dispatched = true;                                                                             \

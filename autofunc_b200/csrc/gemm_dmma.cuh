@@ -107,6 +107,10 @@ struct GemmArgs {
 template <int SPECIAL> struct SpecialArgs {};
 template <> struct SpecialArgs<1> { LstmStepArgs lstm; };
 template <> struct SpecialArgs<2> { LstmStepArgs lstm; };
+// SPECIAL = 3: the plain contraction as stream-K with an ORDERED fix-up instead of atomics (see the kernel): a workspace
+// of one partial tile per CTA ([CTA][value][thread] doubles) and one flag per CTA and warp
+struct FixupArgs { double* part; unsigned* flags; };
+template <> struct SpecialArgs<3> { FixupArgs fix; };
 
 // ---------------------------------------------------------------------------------------------
 // epilogue element functions (shared by the DMMA kernel and the generic kernel)
@@ -477,6 +481,9 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   using L = GemmSmem<NACC, CFG>;
   using T = TileCfg<CFG>;
   constexpr bool DUAL = (NACC == 2);
+  constexpr bool FIXUP = (SPECIAL == 3);                 // stream-K with the ordered fix-up (MULTI only)
+  constexpr bool PLAIN = (SPECIAL == 0 || SPECIAL == 3); // not an LSTM step kernel
+  static_assert(!FIXUP || MULTI, "the fix-up is a stream-K mode");
   // epilogue families by call site: <KC,KC> forward, <KC,RC> input gradient (incl. accumulating ones), <RC,RC> weight gradient
   constexpr int FAM = (ALAY == LAY_KC && BLAY == LAY_KC) ? FAM_BIAS
                       : (ALAY == LAY_KC && BLAY == LAY_RC) ? (FAM_SIGMOID_BWD | FAM_ACCUM)
@@ -512,7 +519,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  if (SPECIAL == 0) pdl_wait();  // everything above overlapped the predecessor's tail; its output is visible from here on
+  if (PLAIN) pdl_wait();  // everything above overlapped the predecessor's tail; its output is visible from here on
 
   // Producer role: lane 0 of warp 0 keeps kStages-1 units in flight.  It is folded into a consumer
   // warp (not an extra warp) because registers are allocated per SM sub-partition: an extra warp would put
@@ -586,7 +593,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   };
-  if (SPECIAL != 0) {
+  if (!PLAIN) {
     // LSTM time steps are chains of dependent launches (programmatic dependent launch, lstm_step.cu): this CTA may have
     // become resident while the previous step is still computing.  The B operand -- the weights -- does not depend on
     // it, so the first stages' weight tiles are requested BEFORE griddepcontrol.wait and only the A tiles (the state the
@@ -716,9 +723,70 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // registers -> global for the tile that just ended (or was interrupted by the end of this CTA's range)
   const bool vec_ok = !p.transpose_out && ((p.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.out0) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.out1) & 15) == 0);
-  auto flush = [&](int q) {
+  // kind (FIXUP only): 0 = the segment is a whole tile, 1 = it is the TAIL of a tile whose first k-tiles belong to the
+  // previous CTA (computed first in time: park the partial sums), 2 = it is the HEAD of a tile that the next CTA finishes
+  // (computed last: fetch that CTA's partial, add, run the real epilogue)
+  auto flush = [&](int q, int kind = 0, int head_len = 0) {
     const int tile = tile_of(q);
     const int i0 = (tile / p.tiles_j) * BM, j0 = (tile % p.tiles_j) * BN;
+    if constexpr (FIXUP) {
+      // Stream-K without atomics.  A tile that is split has one HEAD -- the CTA whose range ends inside it, holding its first
+      // k-tiles -- and one or more followers: the next CTA(s), whose ranges begin (or lie entirely) inside it.  A follower
+      // meets the tile at the very start of its life: it parks its partial accumulators in the workspace -- thread-private
+      // slots, [CTA][value][thread], no index arithmetic on the other side; a CTA parks at most one partial, its first
+      // segment -- and raises its warp's flag.  The head meets the tile at the very end of its life: it takes the parked
+      // values in CTA order, adds them to its own (one fixed order, the same bits on every run) and runs the ordinary fused
+      // epilogue with plain stores.
+      // No zeroing pass, no red.global.add.f64, no deferred elementwise kernel.  All CTAs of the launch are co-resident or
+      // dispatched in index order, so the wait cannot deadlock; it is bounded like the mbarrier waits.
+      constexpr int NV1 = TI * TJ * 2, NV = NACC * NV1, NT = kConsumerWarps * 32;
+      if (kind == 1) {
+        double* mine = sp.fix.part + (size_t)blockIdx.x * (NV * NT) + threadIdx.x;
+#pragma unroll
+        for (int t = 0; t < TI; ++t)
+#pragma unroll
+          for (int u = 0; u < TJ; ++u)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int v = (t * TJ + u) * 2 + e;
+              __stcg(mine + v * NT, acc0[t][u][e]);
+              if (DUAL) __stcg(mine + (NV1 + v) * NT, acc1[DUAL ? t : 0][u][e]);
+            }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sp.fix.flags + blockIdx.x * kConsumerWarps + warp), "r"(1u) : "memory");
+        return;
+      }
+      if (kind == 2) {
+        // the followers: CTA c + 1 holds the next units_per_cta k-tiles of this tile (all of its range, if the tile is
+        // longer than a range), c + 2 the ones after that, ... until the tile's last k-tile; their partials are added in
+        // that order
+        const int followers = (kt_total - head_len + p.units_per_cta - 1) / p.units_per_cta;
+        for (int fo = 1; fo <= followers; ++fo) {
+          unsigned* f = sp.fix.flags + (blockIdx.x + fo) * kConsumerWarps + warp;
+          unsigned seen = 0;
+          for (uint32_t left = kMbarSpinLimit; left != 0; --left) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+            if (seen) break;
+            __nanosleep(64);
+          }
+          if (!seen) __trap();
+          const double* theirs = sp.fix.part + (size_t)(blockIdx.x + fo) * (NV * NT) + threadIdx.x;
+#pragma unroll
+          for (int t = 0; t < TI; ++t)
+#pragma unroll
+            for (int u = 0; u < TJ; ++u)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int v = (t * TJ + u) * 2 + e;
+                acc0[t][u][e] += __ldcg(theirs + v * NT);
+                if (DUAL) acc1[DUAL ? t : 0][u][e] += __ldcg(theirs + (NV1 + v) * NT);
+              }
+          __syncwarp();
+          if (lane == 0) *f = 0;  // (one writer and one reader per launch: ready for the next launch or graph replay)
+        }
+      }
+    }
     if constexpr (SPECIAL == 1) {
       // ---- LSTM forward cell (see LstmStepArgs): accumulator block u of this thread IS gate u of its two units ----
       static_assert(SPECIAL != 1 || (TJ == 4 && T::WJ == 2 && BLAY == LAY_KC), "the gate layout assumes 4 blocks of 8 units per warp");
@@ -886,7 +954,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #ifndef AF_PERSIST_TILES
 #define AF_PERSIST_TILES 0  // 1: compile the persistent whole-tile mode (af_set_option "persist_tiles"; measured slower) into the stream-K kernels
 #endif
-    if constexpr (SPECIAL == 0 && MULTI && !AF_PERSIST_TILES) {
+    if constexpr (PLAIN && MULTI && !AF_PERSIST_TILES && !FIXUP) {
       // stream-K: tile segments always meet in red.global.add.f64 (the elementwise step, if any, follows in
       // gemm_epilogue_kernel).  Nothing else is compiled into these instantiations: their main loops lose 2-3 % whenever
       // the epilogue code around them grows (register allocation is per kernel).
@@ -910,7 +978,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       return;
     }
-    if constexpr (SPECIAL == 0 && !(MULTI && !AF_PERSIST_TILES)) {
+    if constexpr (PLAIN && (FIXUP || !(MULTI && !AF_PERSIST_TILES))) {
       if (!MULTI && ALAY == LAY_KC && BLAY == LAY_KC && p.epi == EPI_BIAS_SIGMOID && vec_ok && i0 + BM <= p.I && j0 + BN <= p.J) {
         // dense forward on an interior tile (lin_add.go:15-17,37-42 + math_funcs.go:292,305-309): one straight-line
         // batch per fragment row -- TJ x 2 independent sigmoids in flight -- instead of the generic path below, which
@@ -1090,6 +1158,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   // Outer loop: one iteration per tile segment of this CTA's unit range; the epilogue stays outside the
   // hot loop.  The ring and the fragment prefetch simply continue into the next segment.
   int kt_cur = kt0, tile_cur = tile0;
+  int seg_kt0 = kt0, seg_un0 = 0;  // FIXUP: first k-tile and first unit of the segment being accumulated
   if (T::PREFETCH) {
     mbar_wait(bars + 0, 0);
     load_frags(0, base, 0);
@@ -1132,12 +1201,18 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (lane == 0) mbar_arrive(bars + 8 * (kStages + s));
     }
     if (!MULTI || un >= nun) break;  // the last (or only) segment is flushed after the loop
-    flush(tile_cur);
+    if constexpr (FIXUP) {
+      flush(tile_cur, seg_kt0 > 0 ? 1 : 0);  // (a segment flushed here ends at its tile's last k-tile)
+      seg_kt0 = 0; seg_un0 = un;
+    } else {
+      flush(tile_cur);
+    }
     zero_acc();
     kt_cur = 0;
     ++tile_cur;
   }
-  flush(tile_cur);
+  if constexpr (FIXUP) flush(tile_cur, seg_kt0 > 0 ? 1 : (nun - seg_un0 == kt_total ? 0 : 2), nun - seg_un0);
+  else flush(tile_cur);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -147,6 +147,77 @@ def test_lintran_entry_points_are_bit_reproducible(api, det, rows, cols, n):
         close(first[5], (URm @ Wm + Um @ RWm).ravel(), "DR")
 
 
+@pytest.mark.parametrize("rows,cols,n", [(512, 2000, 4096),    # the bench network's layer 2: stream-K forward and weight gradient
+                                        (2000, 1000, 4096),   # its layer 1: stream-K weight gradient (ragged 64-tiles both ways)
+                                        (2000, 1000, 1024),   # n = 1024: stream-K forward and input gradient too
+                                        (700, 530, 900)])     # ragged everywhere
+@pytest.mark.parametrize("mode", ["deterministic", "sk_fixup_everywhere"])
+def test_streamk_ordered_fixup_matches_oracle_and_repeats_bit_for_bit(api, rows, cols, n, mode):
+    """Stream-K WITHOUT atomics (gemm_dmma_kernel SPECIAL = 3): the CTA that holds a split tile's first k-tiles fetches the
+    other CTA's parked partial sums, adds them in one fixed order and runs the ordinary fused epilogue.  In deterministic
+    mode it replaces the whole-tile launches wherever stream-K balances better; with af_set_option "sk_fixup" 2 it also
+    replaces the default schedule's red.global.add.f64 launches.  Every LinTran entry point (G1-G6, `+=` into non-zero
+    accumulators) and the fused dense layer (bias + sigmoid forward, sigmoid backward in the input gradient) against
+    numpy, and bit equality between runs."""
+    ctx = api.context()
+    lib = ctx.lib
+    if mode == "deterministic":
+        ctx.set_option("deterministic", 1)
+    else:
+        ctx.set_option("sk_fixup", 2)
+    try:
+        W, RW = ref.splitmix_uniform(1, rows * cols) * 0.05, ref.splitmix_uniform(2, rows * cols)
+        X, RX = ref.splitmix_uniform(3, n * cols), ref.splitmix_uniform(4, n * cols)
+        U, UR = ref.splitmix_uniform(5, n * rows), ref.splitmix_uniform(6, n * rows)
+        b, Rb = ref.splitmix_uniform(9, rows), ref.splitmix_uniform(10, rows)
+        Sp, RSp = ref.splitmix_uniform(11, n * cols, 0.05, 0.95), ref.splitmix_uniform(12, n * cols)
+        G0 = ref.splitmix_uniform(7, rows * cols)
+        dev = {k: ctx.upload(v) for k, v in dict(W=W, RW=RW, X=X, RX=RX, U=U, UR=UR, b=b, Rb=Rb, Sp=Sp, RSp=RSp).items()}
+
+        def run():
+            Y, RY = ctx.zeros(n * rows), ctx.zeros(n * rows)
+            S, RS = ctx.zeros(n * rows), ctx.zeros(n * rows)
+            gW, rgW = ctx.upload(G0), ctx.upload(G0)
+            D, DR = ctx.zeros(n * cols), ctx.zeros(n * cols)
+            E, ER = ctx.zeros(n * cols), ctx.zeros(n * cols)
+            api.check(lib.af_lintran_fwd_r(ctx.h, dev["W"].ptr, dev["RW"].ptr, dev["X"].ptr, dev["RX"].ptr, Y.ptr, RY.ptr, rows, cols, n))
+            api.check(lib.af_dense_fwd(ctx.h, dev["W"].ptr, dev["RW"].ptr, dev["b"].ptr, dev["Rb"].ptr, dev["X"].ptr, dev["RX"].ptr,
+                                       S.ptr, RS.ptr, rows, cols, n, 1))
+            api.check(lib.af_lintran_wgrad_r(ctx.h, dev["U"].ptr, dev["UR"].ptr, dev["X"].ptr, dev["RX"].ptr, gW.ptr, rgW.ptr, rows, cols, n))
+            api.check(lib.af_lintran_igrad_r(ctx.h, dev["U"].ptr, dev["UR"].ptr, dev["W"].ptr, dev["RW"].ptr, D.ptr, DR.ptr, rows, cols, n))
+            api.check(lib.af_dense_igrad(ctx.h, dev["U"].ptr, dev["UR"].ptr, dev["W"].ptr, dev["RW"].ptr, dev["Sp"].ptr, dev["RSp"].ptr,
+                                         E.ptr, ER.ptr, rows, cols, n))
+            return [v.numpy() for v in (Y, RY, S, RS, gW, rgW, D, DR, E, ER)]
+
+        names = ("Y", "RY", "S", "RS", "gW", "rgW", "D", "DR", "E", "ER")
+        first = run()
+        for rep in range(1, 3):
+            for name, a, c in zip(names, first, run()):
+                if mode == "deterministic":  # (elsewhere the launches that stream-K does not take may still use atomics)
+                    same_bits(a, c, f"{mode} {rows}x{cols} n={n} run {rep} {name}")
+                else:
+                    close(c, a, f"{mode} {rows}x{cols} n={n} run {rep} {name}")
+        Wm, RWm, Xm, RXm, Um, URm = (a.reshape(s) for a, s in ((W, (rows, cols)), (RW, (rows, cols)), (X, (n, cols)),
+                                                                (RX, (n, cols)), (U, (n, rows)), (UR, (n, rows))))
+        y, ry = Xm @ Wm.T, RXm @ Wm.T + Xm @ RWm.T
+        close(first[0], y.ravel(), "Y")
+        close(first[1], ry.ravel(), "RY")
+        sg = 1.0 / (1.0 + np.exp(-(y + b)))
+        close(first[2], sg.ravel(), "S = sigmoid(XW^T + b)")
+        close(first[3], (sg * (1 - sg) * (ry + Rb)).ravel(), "RS")
+        close(first[4], G0 + (Um.T @ Xm).ravel(), "gW")
+        close(first[5], G0 + (URm.T @ Xm + Um.T @ RXm).ravel(), "rgW")
+        d, dr = Um @ Wm, URm @ Wm + Um @ RWm
+        close(first[6], d.ravel(), "D")
+        close(first[7], dr.ravel(), "DR")
+        s_, rs_ = Sp.reshape(n, cols), RSp.reshape(n, cols)
+        close(first[8], (s_ * (1 - s_) * d).ravel(), "E = sigmoid'(S) D")
+        close(first[9], (rs_ * (1 - s_) * d - s_ * rs_ * d + s_ * (1 - s_) * dr).ravel(), "ER")
+    finally:
+        ctx.set_option("deterministic", 0)
+        ctx.set_option("sk_fixup", 1)
+
+
 @pytest.mark.parametrize("I,H,O,T,B,fused", [(16, 64, 10, 6, 70, 1), (16, 64, 10, 6, 70, 0), (30, 512, 10, 128, 256, 1)])
 def test_lstm_is_bit_reproducible(api, det, I, H, O, T, B, fused):
     """bench/lstm.go forward + BPTT + R through af_lstm_*: fused time steps and the per-kernel path."""
