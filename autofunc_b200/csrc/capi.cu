@@ -293,6 +293,11 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->ops_runtime = value != 0;
     return AF_OK;
   }
+  if (!strcmp(name, "sk_fix_bias")) {
+    if (value < 50 || value > 200) return fail(AF_EINVAL, "sk_fix_bias is a percentage between 50 and 200");
+    ctx->sk_fix_bias = value;
+    return AF_OK;
+  }
   if (!strcmp(name, "sk_fixup")) {
     if (value < 0 || value > 2) return fail(AF_EINVAL, "sk_fixup must be 0, 1 or 2");
     ctx->sk_fixup = value;

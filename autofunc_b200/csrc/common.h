@@ -46,7 +46,8 @@ struct af_ctx {
   unsigned* fold_tickets = nullptr;  // ticket counters of the last-block-folds reductions (kFoldTickets, zero between launches)
   bool short_rows_off = false;  // A/B switch ("short_rows" 0): rows of <= 32 entries through the staged group kernels (mathops.cu)
   bool ops_runtime = false;  // A/B switch ("ops_runtime" 1): the big contractions read the R operands' presence at run time (gemm_dmma_kernel OPS = -1)
-  int sk_fixup = 1;               // stream-K with the ordered fix-up ("sk_fixup"): 0 never, 1 in deterministic mode, 2 wherever stream-K is chosen
+  int sk_fixup = 1;               // stream-K with the ordered fix-up ("sk_fixup"): 0 never, 1 deterministic mode + store-type launches, 2 wherever stream-K is chosen
+  int sk_fix_bias = 103;          // its cost in the decomposition model for store-type launches, percent ("sk_fix_bias")
   double* sk_part = nullptr;      // its workspace: one partial tile per CTA ...
   unsigned* sk_flags = nullptr;   // ... and one flag per CTA and warp (gemm.cu: fixup_workspace)
   bool fused_colsum_off = false;  // A/B switch ("fused_colsum" 0): the MLP plan's bias gradients always as colsum_kernel passes

@@ -296,18 +296,23 @@ int gemm_launch(af_ctx* ctx, const GemmOperand& A_in, const GemmOperand& B_in, b
     if (cfg != 0 && (c < best * 0.98 || (must_defer && mode == 0))) { best = c; mode = 2; }
   }
   // Stream-K with the ORDERED fix-up (SPECIAL = 3 of the kernel: no atomics, no zeroing, no deferred pass, the same bits on
-  // every run): the paired configuration, ranges of at least 16 k-tiles.  af_set_option "sk_fixup": 0 never, 1 (default) in deterministic mode -- which otherwise only has whole
-  // tiles per CTA --, 2 wherever stream-K is chosen.
+  // every run): the paired configuration, ranges of at least 16 k-tiles, one wave.  af_set_option "sk_fixup": 0 never;
+  // 1 (default) = in deterministic mode wherever stream-K balances better than whole tiles (the mode has nothing else),
+  // in the default mode for STORE-type launches -- they save the zeroing and the deferred elementwise pass; accumulating
+  // launches keep red.global.add.f64, measured 8-18 us faster per bench weight gradient --; 2 = wherever stream-K is chosen.
+  // Store-type launches are costed without the deferred pass (cd) and with their own bias ("sk_fix_bias", percent).
   const bool fixup_ok = cfg == 2 && !swapped && kt_total >= 8 && sk_units >= 16 &&
-                        (long long)((args.total_units + sk_units - 1) / sk_units) <= 2ll * ctx->sm_count &&
-                        (ctx->sk_fixup == 2 || (ctx->sk_fixup == 1 && ctx->deterministic));
+                        (long long)((args.total_units + sk_units - 1) / sk_units) <= slots &&
+                        (ctx->sk_fixup == 2 || (ctx->sk_fixup == 1 && (ctx->deterministic || !accumulate)));
   if (fixup_ok) {
+    const double segs = 1.0 + (double)(sk_units - 1) / kt_total;
     if (mode == 2) {
       mode = 4;
-    } else if (mode == 0 && ctx->deterministic) {
-      const double segs = 1.0 + (double)(sk_units - 1) / kt_total;
+    } else if (ctx->deterministic) {
       const int bias = (sk_units >= 64 && (accumulate || tiles < 4 * slots)) ? ctx->sk_bias_long : ctx->sk_bias;
-      if (bias * 0.01 * (sk_units + cf * segs) < best * 0.98) mode = 4;
+      if (mode == 0 && bias * 0.01 * (sk_units + cf * segs) < best * 0.98) mode = 4;
+    } else if (!accumulate) {
+      if (ctx->sk_fix_bias * 0.01 * (sk_units + cf * segs) < best * 0.98) mode = 4;
     }
   }
   // Persistent whole tiles: a launch of several waves of one-tile CTAs pays every CTA's prologue (barrier setup,

@@ -979,7 +979,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       return;
     }
     if constexpr (PLAIN && (FIXUP || !(MULTI && !AF_PERSIST_TILES))) {
-      if (!MULTI && ALAY == LAY_KC && BLAY == LAY_KC && p.epi == EPI_BIAS_SIGMOID && vec_ok && i0 + BM <= p.I && j0 + BN <= p.J) {
+      if ((!MULTI || FIXUP) && ALAY == LAY_KC && BLAY == LAY_KC && p.epi == EPI_BIAS_SIGMOID && vec_ok && i0 + BM <= p.I && j0 + BN <= p.J) {
         // dense forward on an interior tile (lin_add.go:15-17,37-42 + math_funcs.go:292,305-309): one straight-line
         // batch per fragment row -- TJ x 2 independent sigmoids in flight -- instead of the generic path below, which
         // decides the epilogue kind and the bounds anew for every column pair and so runs one exp / reciprocal chain at
@@ -1046,7 +1046,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
         return;
       }
-      if constexpr (ALAY == LAY_KC && BLAY == LAY_RC && !MULTI) {  // (whole tiles per CTA; stream-K defers its epilogue)
+      if constexpr (ALAY == LAY_KC && BLAY == LAY_RC && (!MULTI || FIXUP)) {  // (whole tiles per CTA, or the fix-up's finished tiles)
         // ---- sigmoid backward of the layer below on the finished tile (input-gradient launches; math_funcs.go:365-371,
         // operand order kept), optionally with the tile's column sums (EPI_SIGMOID_BWD_COLSUM) ----
         // S / RS at the output positions are usually cold (written by the forward pass, hundreds of MB ago).  Fetched pair by
