@@ -100,13 +100,18 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * the backward pass brings its operands through warp-private TMA rings, 0 = register-staged loads.
  * "deterministic": 1 = every floating-point sum is taken in an order fixed by the shapes alone, so results are
  * bit-identical from run to run like the reference's (a sequential program): contractions compute whole output tiles per
- * CTA (no split-K / stream-K partial tiles combined with red.global.add.f64), column sums fold their per-block partial
+ * CTA or stream-K ranges with the ordered fix-up ("sk_fixup"; no partial tiles combined with red.global.add.f64), column sums fold their per-block partial
  * sums in block order, and the atomics-based small-batch kernels and the fused head's bias-gradient atomics are not
  * used.  0 (default) = the faster schedule, whose last bits (well inside 1e-12 + 1e-10 |ref|) depend on the arrival
  * order of partial sums.  Cost measured on the bench step: DESIGN.md 3.1.  (The LSTM's fused time steps are
  * deterministic in both modes; the sum over ranks is NCCL's, which is run-to-run deterministic for a fixed communicator.)
  * "few_rows_wgrad": the weight gradient of a layer with <= 16 output rows over a batch of >= 64 samples (the bench
  * network's 10-class head) as a streaming kernel with ordered sums: 0 never, 1 (default) in deterministic mode, 2 always.
+ * "sk_fixup": stream-K launches whose partial tiles meet in an ORDERED fix-up instead of red.global.add.f64 (the CTA holding
+ * a split tile's first k-tiles adds the following CTAs' parked partial sums in CTA order and runs the fused epilogue; no
+ * zeroing, no deferred elementwise pass, bit-reproducible): 0 never, 1 (default) = everywhere in deterministic mode and for
+ * store-type launches in the default mode, 2 = for every stream-K launch.  "sk_fix_bias": its cost in the decomposition
+ * model for store-type launches, percent (default 103; A/B).
  * "fused_colsum": 1 (default) = the MLP plans' bias gradients (column sums of a layer's upstream, lin_add.go:94-104) are
  * added by the epilogue of the input-gradient launch that produces that upstream (float64 atomics; never in deterministic
  * mode); 0 = always a colsum_kernel pass.  "ops_runtime": 1 = the one-tile launches of the big contractions read the R
