@@ -306,7 +306,8 @@ int af_dense_fwd(af_ctx*, const double* d_W, const double* d_RW, const double* d
                  int64_t rows, int64_t cols, int64_t n, int activation);
 /* Input-gradient with the PREVIOUS layer's sigmoid backward fused in (G5+G6+E4):
  *   D = U W ; DR = UR W + U RW ; then, when d_Sprev != NULL, the in-place sigmoid R-backward of
- *   math_funcs.go:365-371 with (S,RS) = (Sprev, RSprev), written to d_D / d_DR.                */
+ *   math_funcs.go:365-371 with (S,RS) = (Sprev, RSprev), written to d_D / d_DR.  d_D / d_DR must not overlap
+ *   d_Sprev / d_RSprev (the kernels read them through the read-only path).                      */
 int af_dense_igrad(af_ctx*, const double* d_U, const double* d_UR, const double* d_W, const double* d_RW,
                    const double* d_Sprev, const double* d_RSprev, double* d_D, double* d_DR,
                    int64_t rows, int64_t cols, int64_t n);
