@@ -80,3 +80,80 @@ def test_rotated_walk_is_a_permutation_and_mostly_in_lockstep(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("OK aligned ")
     assert float(r.stdout.split()[-1]) > 0.7  # 0.758 measured: whole tiles fully, partial segments on one side of the wrap
+
+
+# ---- the ordered fix-up of stream-K (gemm_dmma_kernel SPECIAL = 3): roles of a launch's CTAs ------------------------------
+def _fixup_roles(kt_total, units_per_cta, total_units):
+    """The kernel's segment walk restated (gemm_dmma.cuh: the outer loop of the consumers and its FIXUP flush calls): per
+    CTA the list of (tile, first k-tile, length, kind, head_len) it flushes; kind 0 = whole tile, 1 = parks its partial,
+    2 = head (adds the followers' partials, runs the epilogue)."""
+    out = []
+    n_ctas = (total_units + units_per_cta - 1) // units_per_cta
+    for c in range(n_ctas):
+        u0 = c * units_per_cta
+        nun = min(u0 + units_per_cta, total_units) - u0
+        tile, kt0 = divmod(u0, kt_total)
+        kt_cur, un, seg_kt0, seg_un0, segs = kt0, 0, kt0, 0, []
+        while un < nun:
+            seg_end = min(un + (kt_total - kt_cur), nun)
+            un = seg_end
+            if un >= nun:
+                break
+            segs.append((tile, seg_kt0, un - seg_un0, 1 if seg_kt0 > 0 else 0, 0))
+            seg_kt0, seg_un0, kt_cur, tile = 0, un, 0, tile + 1
+        last = nun - seg_un0
+        segs.append((tile, seg_kt0, last, 1 if seg_kt0 > 0 else (0 if last == kt_total else 2), last))
+        out.append(segs)
+    return out
+
+
+def test_streamk_fixup_roles_cover_every_tile_once_in_cta_order():
+    """Every tile is finished by exactly one CTA (a whole-tile segment, or the head); a head's followers -- the next
+    ceil((kt_total - head_len) / units_per_cta) CTAs, as the kernel computes -- each park exactly one partial, their
+    FIRST segment, and together with the head they cover the tile's k-tiles exactly once, in ascending order; no CTA
+    parks more than one partial (one workspace slot per CTA) and a parked partial is always consumed."""
+    import random
+    rng = random.Random(7)
+    cases = [(125, 216, 512 * 125), (256, 443, 512 * 256), (256, 222, 256 * 256), (63, 436, 2048 * 63)]  # the bench's launches
+    for _ in range(400):
+        kt = rng.randint(8, 300)
+        tiles = rng.randint(1, 700)
+        slots = rng.randint(1, 296)
+        total = tiles * kt
+        cases.append((kt, max(16, (total + slots - 1) // slots), total))
+    for kt, U, total in cases:
+        roles = _fixup_roles(kt, U, total)
+        parked = {}      # cta -> (tile, first k-tile, length)
+        finished = {}    # tile -> cta
+        heads = []
+        for c, segs in enumerate(roles):
+            n_parked = 0
+            for i, (tile, k0, ln, kind, head_len) in enumerate(segs):
+                assert ln > 0
+                if kind == 1:
+                    assert i == 0 and k0 > 0, "only a CTA's first segment can start inside a tile"
+                    n_parked += 1
+                    parked[c] = (tile, k0, ln)
+                elif kind == 0:
+                    assert k0 == 0 and ln == kt
+                    assert tile not in finished
+                    finished[tile] = c
+                else:
+                    assert i == len(segs) - 1 and k0 == 0 and ln < kt and head_len == ln
+                    assert tile not in finished
+                    finished[tile] = c
+                    heads.append((c, tile, ln))
+            assert n_parked <= 1
+        assert sorted(finished) == list(range(total // kt)), (kt, U, total)
+        consumed = set()
+        for c, tile, head_len in heads:
+            followers = (kt - head_len + U - 1) // U        # the kernel's formula
+            k = head_len
+            for fo in range(1, followers + 1):
+                assert c + fo in parked, (kt, U, total, c, fo)
+                ptile, pk0, pln = parked[c + fo]
+                assert ptile == tile and pk0 == k, "followers continue the tile in CTA order"
+                k += pln
+                consumed.add(c + fo)
+            assert k == kt, "head + followers cover the tile exactly"
+        assert consumed == set(parked), "every parked partial has exactly one reader"
