@@ -320,6 +320,10 @@ int af_set_option(af_ctx* ctx, const char* name, int value) {
     ctx->pdl_fused_off = value == 0;
     return AF_OK;
   }
+  if (!strcmp(name, "small_mlp_head")) {
+    ctx->small_mlp_head_off = value == 0;
+    return AF_OK;
+  }
   if (!strcmp(name, "small_mlp")) {
     ctx->small_mlp_off = value == 0;
     return AF_OK;

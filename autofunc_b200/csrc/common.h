@@ -52,6 +52,7 @@ struct af_ctx {
   unsigned* sk_flags = nullptr;   // ... and one flag per CTA and warp (gemm.cu: fixup_workspace)
   bool fused_colsum_off = false;  // A/B switch ("fused_colsum" 0): the MLP plan's bias gradients always as colsum_kernel passes
   bool small_n_off = false;  // A/B switch: route n <= 16 through the tensor-core kernel instead of small_n.cu
+  bool small_mlp_head_off = false;  // A/B switch ("small_mlp_head" 0): the persistent step runs the top layer as two grid-wide phases again
   bool small_mlp_off = false;  // A/B switch: af_mlp_step with n <= 8 replays the per-kernel graph instead of small_mlp.cu
   bool lstm_split_off = true;   // opt-in (af_set_option "lstm_split" 1): two concurrent half-batch kernel chains; measured 24.6 vs 24.2 ms
   bool lstm_fused_off = false;  // A/B switch (af_set_option "lstm_fused" 0): the per-kernel LSTM steps of round 1

@@ -45,6 +45,7 @@ struct SmallMlpArgs {
   int backprop;
   int fresh;                       // accumulators start this step at zero: store instead of read-modify-write
   int unit_upstream;               // the top upstream is outGrad = 1, outRGrad = 0, generated in registers
+  int head_local;                  // the top layer (<= 16 outputs) runs forward + backward redundantly in every group: two grid barriers fewer
   unsigned* bar;                   // grid barrier counter: monotonic across launches (never reset)
   unsigned bar_base;               // its value when this launch starts
 };
@@ -149,9 +150,14 @@ __device__ __forceinline__ void forward_phase(const SmallMlpArgs& a, int l, doub
 }
 
 // ---- B_l ------------------------------------------------------------------------------------------------
+// `hd` != NULL: layer l lies directly below a head that ran locally (head_phase): its raw upstream U = W_head^T d_head
+// (and the R form) is formed here from the head's deltas hd / hdr ([NMAX][kHeadMax], in shared memory) instead of being
+// read from delta[l + 1], which nobody wrote.
+constexpr int kHeadMax = 16;
 template <int NMAX, bool R>
 __device__ __forceinline__ void backward_phase(const SmallMlpArgs& a, int l, double* sd /* [2][NMAX][kMChunkMax] */,
-                                               int group, int tid, int vblock, int nvblocks) {
+                                               int group, int tid, int vblock, int nvblocks, const double* hd = nullptr,
+                                               const double* hdr = nullptr) {
   const int K = a.sizes[l], M = a.sizes[l + 1], n = a.n, mchunk = a.bwd_mchunk[l];
   const double* __restrict__ W = a.W[l];
   const double* __restrict__ RW = R ? a.RW[l] : nullptr;
@@ -180,10 +186,29 @@ __device__ __forceinline__ void backward_phase(const SmallMlpArgs& a, int l, dou
       double d = 0.0, dr = 0.0;
       if (i < n && mm < mc) {
         const long long o = (long long)i * M + m0 + mm;
-        const double x = S[o], p = top_unit ? 1.0 : U[o];
+        double p = top_unit ? 1.0 : 0.0, pr = 0.0;
+        if (hd) {
+          // input gradient of the head toward this layer's output m0 + mm (lin_tran.go:285-288,329-334, Gemv T):
+          // column m0 + mm of W_head / RW_head against the head's deltas of sample i
+          const int Mh = a.sizes[a.L], col = m0 + mm;
+          const double* __restrict__ Wh = a.W[a.L - 1];
+          const double* __restrict__ RWh = R ? a.RW[a.L - 1] : nullptr;
+          for (int r = 0; r < Mh; ++r) {
+            const double w = Wh[(long long)r * M + col], dh = hd[i * kHeadMax + r];
+            p = fma(dh, w, p);
+            if (R) {
+              pr = fma(hdr[i * kHeadMax + r], w, pr);
+              if (RWh) pr = fma(dh, RWh[(long long)r * M + col], pr);
+            }
+          }
+        } else if (!top_unit) {
+          p = U[o];
+          if (R) pr = UR[o];
+        }
+        const double x = S[o];
         d = x * (1 - x) * p;
         if (R) {
-          const double xr = RS[o], pr = top_unit ? 0.0 : UR[o];
+          const double xr = RS[o];
           dr = xr * (1 - x) * p - x * xr * p + x * (1 - x) * pr;
         }
       }
@@ -253,6 +278,149 @@ __device__ __forceinline__ void backward_phase(const SmallMlpArgs& a, int l, dou
   }
 }
 
+// ---- the head, locally -----------------------------------------------------------------------------------
+// The top layer of the bench network has 10 outputs: as F_L and B_L it is two phases with almost no work in them -- a
+// handful of groups compute ten dot products, then ONE group runs the rank-n update of a 10 x 512 matrix -- and each
+// costs every CTA a grid barrier.  Its forward needs nothing but the complete activations of the layer below, and
+// everything its backward produces is either tiny (gW_L, gb_L) or needed only row by row by the layer below (the input
+// gradient).  So every group computes the head's forward REDUNDANTLY right after the barrier that completes the layer
+// below (W_L and RW_L are a few tens of KB from L2; a CTA's groups share the rows), forms the head's deltas in shared memory
+// (hd / hdr), group 0 of CTA 0
+// stores S_L / RS_L and the head's weight and bias gradients, and B_{L-1} starts at once, building its raw upstream from
+// W_L's columns and the deltas (backward_phase, `hd`).  Two grid barriers and two serial phases leave the step.
+// rows of the head whose loads are in flight together (a row at a time would be ten dependent L2 round trips)
+template <int NMAX> struct HeadBatch { static constexpr int MB = NMAX == 1 ? 5 : (NMAX == 2 ? 3 : 2); };
+
+template <int NMAX, bool R>
+__device__ __forceinline__ void head_phase(const SmallMlpArgs& a, double* hpart /* [8][MB][2 NMAX] */, double* hd, double* hdr,
+                                           int group, int ngroups, int tid) {
+  constexpr int MB = HeadBatch<NMAX>::MB;
+  const int l = a.L - 1, K = a.sizes[l], M = a.sizes[l + 1], n = a.n;
+  const double* __restrict__ W = a.W[l];
+  const double* __restrict__ RW = R ? a.RW[l] : nullptr;
+  const double* __restrict__ X = a.act[l];
+  const double* __restrict__ RX = (R && l > 0) ? a.ract[l] : nullptr;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool fresh = a.fresh != 0, top_unit = a.unit_upstream != 0;
+  // forward: the CTA's groups share the head's rows (hd / hdr belong to the CTA); a group's threads split the contraction in
+  // column pairs, MB rows of W at a time, all samples
+  const int rpg = (M + ngroups - 1) / ngroups, m_end = min(M, (group + 1) * rpg);
+  for (int m0 = group * rpg; m0 < m_end; m0 += MB) {
+    double y[MB][NMAX], ry[MB][NMAX];
+#pragma unroll
+    for (int j = 0; j < MB; ++j)
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) y[j][i] = ry[j][i] = 0.0;
+    for (int k = 2 * tid; k < K; k += 2 * kThreads) {
+      double2 wv[MB], rwv[MB], xv[NMAX], rxv[NMAX];
+#pragma unroll
+      for (int j = 0; j < MB; ++j) {
+        const bool ok = m0 + j < m_end;
+        wv[j] = ok ? ld2(W + (long long)(m0 + j) * K + k) : make_double2(0.0, 0.0);
+        rwv[j] = (ok && R && RW) ? ld2(RW + (long long)(m0 + j) * K + k) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) {
+        xv[i] = i < n ? ld2(X + (long long)i * K + k) : make_double2(0.0, 0.0);
+        rxv[i] = (i < n && R && RX) ? ld2(RX + (long long)i * K + k) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int j = 0; j < MB; ++j)
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) {
+          y[j][i] = fma(xv[i].x, wv[j].x, fma(xv[i].y, wv[j].y, y[j][i]));
+          if (R) ry[j][i] = fma(rxv[i].x, wv[j].x, fma(rxv[i].y, wv[j].y, fma(xv[i].x, rwv[j].x, fma(xv[i].y, rwv[j].y, ry[j][i]))));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < MB; ++j)
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          y[j][i] += __shfl_xor_sync(0xffffffffu, y[j][i], o);
+          if (R) ry[j][i] += __shfl_xor_sync(0xffffffffu, ry[j][i], o);
+        }
+        if (lane == 0) {
+          hpart[(warp * MB + j) * 2 * NMAX + 2 * i] = y[j][i];
+          hpart[(warp * MB + j) * 2 * NMAX + 2 * i + 1] = ry[j][i];
+        }
+      }
+    group_sync(group);
+    if (tid < MB * NMAX) {  // thread (j, i) finishes sample i of output m0 + j: bias, sigmoid, R form, top of the backward pass
+      const int j = tid / NMAX, i = tid - j * NMAX, m = m0 + j;
+      if (m < m_end && i < n) {
+        double z = 0.0, zr = 0.0;
+        for (int q = 0; q < 8; ++q) {
+          z += hpart[(q * MB + j) * 2 * NMAX + 2 * i];
+          zr += hpart[(q * MB + j) * 2 * NMAX + 2 * i + 1];
+        }
+        z += a.b[l][m];
+        const double sg = 1.0 / (1.0 + exp(-z));
+        const long long o = (long long)i * M + m;
+        double rs = 0.0;
+        if (R) {
+          zr += a.Rb[l] ? a.Rb[l][m] : 0.0;
+          rs = sg * (1 - sg) * zr;
+        }
+        // math_funcs.go:365-371 on the caller's upstream (or outGrad = 1 / outRGrad = 0), operand order kept
+        const double u = top_unit ? 1.0 : a.delta[a.L][o];
+        hd[i * kHeadMax + m] = sg * (1 - sg) * u;
+        if (R) {
+          const double ur = top_unit ? 0.0 : a.rdelta[a.L][o];
+          hdr[i * kHeadMax + m] = rs * (1 - sg) * u - sg * rs * u + sg * (1 - sg) * ur;
+        }
+        if (blockIdx.x == 0) {
+          a.act[l + 1][o] = sg;
+          if (R) a.ract[l + 1][o] = rs;
+        }
+      }
+    }
+    group_sync(group);  // hpart[] is reused by the next rows
+  }
+  __syncthreads();  // every group's rows are in hd / hdr (all groups of a CTA reach this point together: they left the
+                    // grid barrier together and run the same head)
+  if (blockIdx.x != 0 || group != 0) return;
+  // the head's own gradients, once: gb_L += sum_i d_i (lin_add.go:94-104), gW_L += d x^T, rgW_L += d Rx^T + dR x^T (Ger)
+  if (tid < M) {
+    double g = 0.0, rg = 0.0;
+    for (int i = 0; i < n; ++i) { g += hd[i * kHeadMax + tid]; if (R) rg += hdr[i * kHeadMax + tid]; }
+    a.gb[l][tid] = fresh ? g : a.gb[l][tid] + g;
+    if (R) a.rgb[l][tid] = fresh ? rg : a.rgb[l][tid] + rg;
+  }
+  for (int k = 2 * tid; k < K; k += 2 * kThreads) {
+    double2 xv[NMAX], rxv[NMAX];
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) {
+      xv[i] = rxv[i] = make_double2(0.0, 0.0);
+      if (i < n) {
+        xv[i] = ld2(X + (long long)i * K + k);
+        if (R && RX) rxv[i] = ld2(RX + (long long)i * K + k);
+      }
+    }
+    for (int m = 0; m < M; ++m) {
+      const long long o = (long long)m * K + k;
+      double2 g = make_double2(0.0, 0.0), rg = make_double2(0.0, 0.0);
+      if (!fresh) g = ld2(a.gW[l] + o);
+      if (R && !fresh) rg = ld2(a.rgW[l] + o);
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) {
+        if (i < n) {
+          const double d = hd[i * kHeadMax + m];
+          g.x = fma(d, xv[i].x, g.x); g.y = fma(d, xv[i].y, g.y);
+          if (R) {
+            const double dr = hdr[i * kHeadMax + m];
+            rg.x = fma(d, rxv[i].x, fma(dr, xv[i].x, rg.x));
+            rg.y = fma(d, rxv[i].y, fma(dr, xv[i].y, rg.y));
+          }
+        }
+      }
+      st2(a.gW[l] + o, g);
+      if (R) st2(a.rgW[l] + o, rg);
+    }
+  }
+}
+
 template <int NMAX, bool R, int G>
 __global__ void __launch_bounds__(kThreads * G, 1) small_mlp_step_kernel(const SmallMlpArgs a) {
   __shared__ double part[G][8][2 * NMAX];
@@ -269,6 +437,21 @@ __global__ void __launch_bounds__(kThreads * G, 1) small_mlp_step_kernel(const S
         if (R) a.rdelta[l][e] = 0.0;
       }
     }
+  }
+  if (a.head_local) {  // (host: backprop, L >= 2, head of <= kHeadMax outputs)
+    __shared__ double hd[NMAX * kHeadMax], hdr[NMAX * kHeadMax];
+    __shared__ double hpart[G][8 * HeadBatch<NMAX>::MB * 2 * NMAX];
+    for (int l = 0; l + 1 < a.L; ++l) {
+      forward_phase<NMAX, R>(a, l, part[group], group, tid, vblock, nvblocks);
+      grid_barrier(a.bar, generation);
+    }
+    head_phase<NMAX, R>(a, hpart[group], hd, hdr, group, G, tid);
+    for (int l = a.L - 2; l >= 0; --l) {
+      backward_phase<NMAX, R>(a, l, sd[group], group, tid, vblock, nvblocks, l == a.L - 2 ? hd : nullptr,
+                              l == a.L - 2 ? hdr : nullptr);
+      if (l > 0) grid_barrier(a.bar, generation);
+    }
+    return;
   }
   for (int l = 0; l < a.L; ++l) {
     forward_phase<NMAX, R>(a, l, part[group], group, tid, vblock, nvblocks);
@@ -304,7 +487,8 @@ int launch_variant(af_ctx* ctx, SmallMlpArgs& a, double bytes) {
     a.bwd_mchunk[l] = (int)mchunk;
   }
   // every block arrives at every barrier, so the counter ends this launch at base + barriers * grid
-  const unsigned barriers = (unsigned)((a.L - 1) + (a.backprop ? 1 + (a.L - 1) : 0));
+  const unsigned barriers = a.head_local ? (unsigned)((a.L - 1) + (a.L - 2))
+                                         : (unsigned)((a.L - 1) + (a.backprop ? 1 + (a.L - 1) : 0));
   a.bar_base = ctx->barrier_base;
   ctx->barrier_base += barriers * (unsigned)grid;
   void* params[] = {(void*)&a};
@@ -348,6 +532,7 @@ int small_mlp_launch(af_ctx* ctx, int L, const int64_t* sizes, int64_t n, double
   SmallMlpArgs a{};
   a.L = L; a.n = (int)n; a.backprop = backprop ? 1 : 0; a.bar = ctx->barrier_word;
   a.fresh = fresh ? 1 : 0; a.unit_upstream = unit_upstream ? 1 : 0;
+  a.head_local = (backprop && L >= 2 && sizes[L] <= kHeadMax && !ctx->small_mlp_head_off) ? 1 : 0;
   double bytes = 0;
   for (int l = 0; l <= L; ++l) {
     a.sizes[l] = (int)sizes[l];

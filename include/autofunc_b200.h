@@ -90,6 +90,8 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * builds with -DAF_PERSIST_TILES=1, AF_ENOTSUP otherwise: keeping the mode compiled in cost the stream-K launches 2-3 %).
  * "small_mlp": 1 (default) = af_mlp_step with <= 4 samples runs as ONE persistent cooperative kernel
  * (all layers, both directions, grid barriers between phases); 0 = the per-kernel CUDA graph.
+ * "small_mlp_head": 1 (default) = that kernel runs a top layer of <= 16 outputs (forward, top sigmoid backward, its
+ * gradients) locally in every CTA instead of as two grid-wide phases: two grid barriers fewer; 0 = A/B.
  * "dp_max_ctas": CTA cap of the context's communicator (ncclConfig_t.maxCTAs; default 8, 0 = NCCL's own choice); read by
  * af_dp_init.  "dp_reserve_sms": SMs the plans leave to an all-reduce that runs beside their contractions (default =
  * dp_max_ctas): stream-K launches issued while a reduce is in flight are sized for sm_count - dp_reserve_sms SMs.

@@ -220,7 +220,7 @@ def main():
     if WORLD > 1:
         from autofunc_b200 import parallel
         parallel.dp_init_torch(ctx, LOCAL)  # torch.distributed only ships the communicator id
-    for opt in ("pdl", "small_mlp", "small_n", "lstm_split", "lstm_fused", "persist_tiles", "sk_bias", "few_samples", "few_samples_min", "few_samples_blocks", "few_samples_tma", "deterministic"):  # A/B switches: AF_OPT_PDL=0 etc.
+    for opt in ("pdl", "small_mlp", "small_mlp_head", "small_n", "lstm_split", "lstm_fused", "persist_tiles", "sk_bias", "few_samples", "few_samples_min", "few_samples_blocks", "few_samples_tma", "deterministic"):  # A/B switches: AF_OPT_PDL=0 etc.
         v = os.environ.get("AF_OPT_" + opt.upper())
         if v is not None:
             api.check(ctx.lib.af_set_option(ctx.h, opt.encode(), int(v)))
