@@ -94,9 +94,18 @@ static int ctx_create_impl(int device, void* stream, bool own, af_ctx** out) {
   e = cudaMalloc(&c->scratch, c->scratch_doubles * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&c->fold_tickets, kFoldTickets * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMemset(c->fold_tickets, 0, kFoldTickets * sizeof(unsigned));
+  // workspace of the ordered stream-K fix-up (gemm.cu: fixup_workspace has the same sizes): allocated here, not at first use,
+  // because a plan may re-capture its step graph right after an option change -- and cudaMalloc is not allowed while a
+  // thread-local capture is open
+  const size_t fix_ctas = 2 * (size_t)c->sm_count + 1;
+  if (e == cudaSuccess) e = cudaMalloc(&c->sk_part, fix_ctas * 2 * 4 * 4 * 2 * GemmSmem<2, 2>::kThreads * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&c->sk_flags, fix_ctas * GemmSmem<2, 2>::kWarps * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(c->sk_flags, 0, fix_ctas * GemmSmem<2, 2>::kWarps * sizeof(unsigned));
   if (e != cudaSuccess) {
     if (c->scratch) cudaFree(c->scratch);
     if (c->fold_tickets) cudaFree(c->fold_tickets);
+    if (c->sk_part) cudaFree(c->sk_part);
+    if (c->sk_flags) cudaFree(c->sk_flags);
     if (own) cudaStreamDestroy(c->stream);
     delete c;
     return cuda_fail(e, "cudaMalloc(scratch)");
