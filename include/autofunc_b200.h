@@ -109,6 +109,9 @@ int af_set_gemm_path(af_ctx* ctx, int mode);
  * deterministic in both modes; the sum over ranks is NCCL's, which is run-to-run deterministic for a fixed communicator.)
  * "few_rows_wgrad": the weight gradient of a layer with <= 16 output rows over a batch of >= 64 samples (the bench
  * network's 10-class head) as a streaming kernel with ordered sums: 0 never, 1 (default) in deterministic mode, 2 always.
+ * "lstm_fused": 1 (default) = the LSTM plans' time steps are the fused kernels (gate contraction + cell, cluster split-K +
+ * cell backward); 0 = one contraction and one cell kernel per step (A/B).  "small_wgrad_max": batches up to this many
+ * samples (default 8, at most 16) take the streaming rank-n weight-gradient update instead of tensor-core tiles.
  * "sk_fixup": stream-K launches whose partial tiles meet in an ORDERED fix-up instead of red.global.add.f64 (the CTA holding
  * a split tile's first k-tiles adds the following CTAs' parked partial sums in CTA order and runs the fused epilogue; no
  * zeroing, no deferred elementwise pass, bit-reproducible): 0 never, 1 (default) = everywhere in deterministic mode and for

@@ -274,3 +274,15 @@ def test_go_shim_argument_kinds_match_the_prototypes():
                     assert ok, where
                 checked += 1
     assert checked > 400
+
+
+def test_every_option_the_library_accepts_is_documented_in_the_header():
+    """af_set_option takes its knobs by name; a name the header does not explain is a knob nobody can find."""
+    import re
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(ROOT, "autofunc_b200", "csrc", "capi.cu")).read()
+    names = re.findall(r'!strcmp\(name, "([a-z_0-9]+)"\)', src)
+    assert len(names) >= 20
+    hdr = open(os.path.join(ROOT, "include", "autofunc_b200.h")).read()
+    missing = [n for n in names if f'"{n}"' not in hdr]
+    assert not missing, f"options without a description in include/autofunc_b200.h: {missing}"
