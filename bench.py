@@ -694,7 +694,8 @@ def main():
     ap.add_argument("--sk-rotate", dest="sk_rotate", type=int, default=None,
                     help="stream-K launches walk each tile segment's k-tiles in rotated order so CTAs sweep k in lockstep (L2 reuse): 0 / 1")
     ap.add_argument("--persist-tiles", dest="persist_tiles", type=int, default=None,
-                    help="multi-wave contractions as persistent CTAs over whole tiles: 0 off, 1 contiguous, 2 wave order")
+                    help="multi-wave contractions as persistent CTAs over whole tiles: 0 off, 1 contiguous, 2 wave order "
+                         "(needs a library built with -DAF_PERSIST_TILES=1; the mode measured slower and is compiled out by default)")
     ap.add_argument("--deterministic", type=int, default=None, choices=[0, 1],
                     help="1: af_set_option deterministic (run-to-run bit-identical sums: whole tiles per CTA, ordered column sums); default 0")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="af_set_option(NAME, VALUE) before the run (A/B switches)")
